@@ -1,0 +1,203 @@
+"""ctypes door onto oracle/_build/liboracle.so — test infrastructure only.
+
+The oracle is the CPU restatement of the JPEG XL work the reference reaches through libjxl
+(N/Decoder/JxlDecoder.cpp:252, N/Encoder/JxlEncoder.cpp:128,367). PARITY UNPINNED: no libjxl,
+no golden vectors exist offline. Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+REF_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libpixelformat_ref.so")
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL)
+
+
+class EncodeParams(C.Structure):
+    _fields_ = [("distance", C.c_float)] + [(n, C.c_int32) for n in (
+        "effort", "lossless", "gab", "epf", "varblocks", "cfl", "adaptive_quant", "force_strategy", "use_prefix", "container",
+        "modular_group_shift", "orientation", "skip_lf_smoothing", "threads", "bits", "exp_bits", "color_space", "white_point",
+        "primaries", "tf", "intent")] + [("intensity_target", C.c_float), ("premultiplied", C.c_int32), ("black_channel", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.jxlo_encode.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(EncodeParams), C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+        L.jxlo_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+        L.jxlo_image_free.argtypes = [C.c_void_p]
+        L.jxlo_free.argtypes = [C.c_void_p]
+        L.jxlo_image_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        for n in ("jxlo_image_pixels", "jxlo_image_name", "jxlo_image_exif"):
+            getattr(L, n).argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+            getattr(L, n).restype = C.c_void_p
+        L.jxlo_image_xmp.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+        L.jxlo_image_xmp.restype = C.c_void_p
+        L.jxlo_image_stage_f32.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.jxlo_image_stage_f32.restype = C.c_size_t
+        L.jxlo_image_stage_coeffs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.jxlo_image_stage_coeffs.restype = C.c_size_t
+        L.jxlo_signature_check.argtypes = [C.c_void_p, C.c_size_t]
+        L.jxlo_transform_to_pixels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.jxlo_transform_from_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jxlo_llf_from_dc.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jxlo_dequant_table.argtypes = [C.c_int, C.c_void_p]
+        L.jxlo_dequant_table.restype = C.c_size_t
+        L.jxlo_natural_order.argtypes = [C.c_int, C.c_void_p]
+        L.jxlo_natural_order.restype = C.c_size_t
+        L.jxlo_xyb_to_srgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jxlo_srgb8_to_xyb.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def default_params(**kw):
+    p = EncodeParams()
+    lib().jxlo_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def encode(pixels, num_color=None, has_alpha=None, exif=b"", xmp=b"", **kw):
+    """pixels: HxWxC uint8 or float32 array (C = colour [+black] [+alpha])."""
+    a = np.ascontiguousarray(pixels)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    h, w, c = a.shape
+    black = int(kw.get("black_channel", 0))
+    if num_color is None:
+        num_color = 1 if (c - black) <= 2 else 3
+    if has_alpha is None:
+        has_alpha = (c - black - num_color) == 1
+    assert c == num_color + black + int(has_alpha)
+    is_float = a.dtype != np.uint8
+    if is_float:
+        a = a.astype(np.float32)
+    p = default_params(**kw)
+    out = C.c_void_p()
+    n = C.c_size_t()
+    err = C.create_string_buffer(512)
+    rc = lib().jxlo_encode(a.ctypes.data, int(is_float), w, h, num_color, int(has_alpha), C.byref(p), exif, len(exif), xmp, len(xmp),
+                           C.byref(out), C.byref(n), err, 512)
+    if rc:
+        raise OracleError(err.value.decode())
+    data = C.string_at(out, n.value)
+    lib().jxlo_free(out)
+    return data
+
+
+_DT = {0: np.uint8, 1: np.uint16, 2: np.float16, 3: np.float32}
+
+
+class Decoded:
+    pass
+
+
+def decode(data, threads=1, keep_stages=False):
+    img = C.c_void_p()
+    err = C.create_string_buffer(512)
+    buf = bytes(data)
+    rc = lib().jxlo_decode(buf, len(buf), threads, int(keep_stages), C.byref(img), err, 512)
+    if rc:
+        raise OracleError(err.value.decode())
+    try:
+        info = (C.c_int32 * 16)()
+        lib().jxlo_image_info(img, info)
+        d = Decoded()
+        (d.width, d.height, d.format, d.sample_type, d.has_alpha, d.num_channels, d.xpad, d.ypad, d.known_profile, d.orientation,
+         d.is_container, d.has_exif, d.num_xmp, d.bits, d.exp_bits, d.xyb) = list(info)
+        n = C.c_size_t()
+        p = lib().jxlo_image_pixels(img, C.byref(n))
+        raw = np.frombuffer(C.string_at(p, n.value), dtype=_DT[d.sample_type])
+        d.pixels = raw.reshape(d.height, d.width, -1).copy()
+        p = lib().jxlo_image_name(img, C.byref(n))
+        d.name = C.string_at(p, n.value) if n.value else b""
+        p = lib().jxlo_image_exif(img, C.byref(n))
+        d.exif = C.string_at(p, n.value) if d.has_exif else None
+        d.xmp = []
+        for k in range(d.num_xmp):
+            p = lib().jxlo_image_xmp(img, k, C.byref(n))
+            d.xmp.append(C.string_at(p, n.value))
+        if keep_stages and d.xpad:
+            d.stages = {}
+            for which, name in ((0, "idct"), (1, "gab"), (2, "epf"), (3, "lf")):
+                ptr = C.c_void_p()
+                cnt = lib().jxlo_image_stage_f32(img, which, C.byref(ptr))
+                if cnt:
+                    arr = np.frombuffer(C.string_at(ptr, cnt * 4), dtype=np.float32).copy()
+                    d.stages[name] = arr.reshape(3, -1)
+            ptr = C.c_void_p()
+            cnt = lib().jxlo_image_stage_coeffs(img, C.byref(ptr))
+            if cnt:
+                d.stages["coeffs"] = np.frombuffer(C.string_at(ptr, cnt * 4), dtype=np.int32).copy().reshape(3, -1)
+        return d
+    finally:
+        lib().jxlo_image_free(img)
+
+
+def synthetic_image(w, h, seed=0, channels=3):
+    """Deterministic photo-like test image (SURVEY.md §8d recipe): gradients + 1/f noise + hard-edged shapes."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    yy, xx = np.meshgrid(np.linspace(0, 1, h, dtype=np.float32), np.linspace(0, 1, w, dtype=np.float32), indexing="ij")
+    corners = rng.random((4, 3)).astype(np.float32)
+    L = ((1 - yy)[..., None] * ((1 - xx)[..., None] * corners[0] + xx[..., None] * corners[1]) +
+         yy[..., None] * ((1 - xx)[..., None] * corners[2] + xx[..., None] * corners[3]))
+    fy = np.fft.fftfreq(h)[:, None] * h
+    fx = np.fft.rfftfreq(w)[None, :] * w
+    f = np.sqrt(fy * fy + fx * fx)
+    filt = 1.0 / np.maximum(f, 1.0 / 64)
+    base = rng.standard_normal((h, w)).astype(np.float32)
+    N = np.empty((h, w, 3), np.float32)
+    for c in range(3):
+        white = 0.6 * base + 0.4 * rng.standard_normal((h, w)).astype(np.float32)
+        n = np.fft.irfft2(np.fft.rfft2(white) * filt, s=(h, w)).astype(np.float32)
+        n -= n.min()
+        n /= max(float(n.max()), 1e-9)
+        N[..., c] = n
+    E = np.zeros((h, w, 3), np.float32)
+    for _ in range(24):
+        x0, y0 = int(rng.integers(0, w)), int(rng.integers(0, h))
+        x1, y1 = min(w, x0 + int(rng.integers(4, max(5, w // 4)))), min(h, y0 + int(rng.integers(4, max(5, h // 4))))
+        E[y0:y1, x0:x1] = rng.random(3)
+    Y, X = np.ogrid[:h, :w]
+    for _ in range(12):
+        cx, cy, r = int(rng.integers(0, w)), int(rng.integers(0, h)), int(rng.integers(3, max(4, min(w, h) // 8)))
+        E[(X - cx) ** 2 + (Y - cy) ** 2 <= r * r] = rng.random(3)
+    img = np.clip(0.55 * L + 0.30 * N + 0.15 * E, 0, 1)
+    out = np.round(255 * img).astype(np.uint8)
+    if channels == 1:
+        return out[..., 1:2].copy()
+    if channels == 4:
+        r2 = ((xx - 0.5) ** 2 + (yy - 0.5) ** 2) * 4
+        a = np.clip(1.6 - 1.8 * r2 + 0.3 * (rng.random((h, w)).astype(np.float32) - 0.5), 0, 1)
+        a[a > 0.62] = 1.0
+        a[a < 0.05] = 0.0
+        return np.concatenate([out, np.round(255 * a).astype(np.uint8)[..., None]], axis=2)
+    return out
+
+
+def psnr(a, b, peak=255.0):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    mse = float(np.mean(d * d))
+    return 99.0 if mse == 0 else 10 * np.log10(peak * peak / mse)
