@@ -1,0 +1,512 @@
+"""pdn-jpegxl_b200 — host-side mirror of the reference's managed interop layer, over ctypes.
+
+`dotnet` is absent in this image, so the C# caller contract of the reference is restated here
+in Python with the same names, argument meaning and error behaviour:
+
+  JpegXLNative.LoadImage / SaveImage / GetLibJxlVersion   I/JpegXLNative.cs:23-126 (+ error mapping :128-239)
+  DecoderImage (callback sink)                            I/DecoderImage.cs:41-263
+  DecoderLayerData (pixel repack, alpha -> 8 bit)         I/DecoderLayerData.cs:26-105,164-992, I/TransparencyMapping.cs:19-55
+  JpegXLLoad.Load (RGB24 (+A8) -> BGRA32 surface)         S/JpegXLLoad.cs:30-115,219-249
+  EncoderOptions / QualityToDistanceLookupTable           I/EncoderOptions.cs:24-31, I/QualityToDistanceLookupTable.cs:26-65
+  StreamIOCallbacks (HRESULT-returning Write/Seek)        I/StreamIOCallbacks.cs:52-114
+  BitmapUtil2.EnumerateLockRects                          S/BitmapUtil2.cs:30-77
+
+The native library (libJpegXLFileTypeIO_X64.so, built by build.py with nvcc for sm_100a) does all
+codec work in CUDA kernels. It is loaded eagerly; if it is missing, importing this package fails
+loudly — there is no Python or CPU fallback.
+"""
+import ctypes as C
+import io
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libJpegXLFileTypeIO_X64.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise NativeLibraryMissing(
+        "%s not found next to %s. Build it with `python pdn-jpegxl_b200/build.py` (nvcc, sm_100a). "
+        "The engine has no CPU fallback." % (LIB_NAME, __file__))
+
+_lib = C.CDLL(LIB_PATH)
+
+
+# ---- struct mirrors (I/BitmapData.cs, I/DecoderCallbacks.cs, I/ErrorInfo.cs, I/EncoderOptions.Marshaller.cs, I/IOCallbacks.cs) ----
+class BitmapData(C.Structure):
+    _fields_ = [("scan0", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("stride", C.c_uint32)]
+
+
+class ErrorInfo(C.Structure):
+    _fields_ = [("errorMessage", C.c_char * 256)]
+
+
+class EncoderOptionsNative(C.Structure):
+    _fields_ = [("distance", C.c_float), ("effort", C.c_int32), ("lossless", C.c_bool)]
+
+
+class EncoderImageMetadataNative(C.Structure):
+    _fields_ = [("exif", C.c_void_p), ("exifSize", C.c_size_t), ("iccProfile", C.c_void_p), ("iccProfileSize", C.c_size_t),
+                ("xmp", C.c_void_p), ("xmpSize", C.c_size_t)]
+
+
+SetBasicInfoFn = C.CFUNCTYPE(None, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_bool)
+SetMetadataFn = C.CFUNCTYPE(C.c_bool, C.POINTER(C.c_uint8), C.c_size_t)
+SetKnownColorProfileFn = C.CFUNCTYPE(C.c_bool, C.c_int32)
+SetLayerDataFn = C.CFUNCTYPE(C.c_bool, C.POINTER(C.c_uint8), C.POINTER(C.c_char), C.c_size_t)
+ProgressFn = C.CFUNCTYPE(C.c_bool, C.c_int32)
+WriteFn = C.CFUNCTYPE(C.c_int32, C.POINTER(C.c_uint8), C.c_size_t)
+SeekFn = C.CFUNCTYPE(C.c_int32, C.c_uint64)
+
+
+class DecoderCallbacks(C.Structure):
+    _fields_ = [("setBasicInfo", SetBasicInfoFn), ("setIccProfile", SetMetadataFn), ("setKnownColorProfile", SetKnownColorProfileFn),
+                ("setExif", SetMetadataFn), ("setXmp", SetMetadataFn), ("setLayerData", SetLayerDataFn)]
+
+
+class IOCallbacks(C.Structure):
+    _fields_ = [("Write", WriteFn), ("Seek", SeekFn)]
+
+
+EXPORTS = ["GetLibJxlVersion", "LoadImage", "SaveImage", "JxlB200LoadImageBgra", "JxlB200PeekInfo", "JxlB200DecodeBatch", "JxlB200EncodeToMemory",
+           "JxlB200Free", "JxlB200LastStageTimes", "JxlB200KernelLaunchCount", "JxlB200DebugDecodeStage", "JxlB200CudaAvailable"]
+
+_lib.GetLibJxlVersion.restype = C.c_uint32
+_lib.LoadImage.argtypes = [C.POINTER(DecoderCallbacks), C.c_void_p, C.c_size_t, C.POINTER(ErrorInfo)]
+_lib.LoadImage.restype = C.c_int32
+_lib.SaveImage.argtypes = [C.POINTER(BitmapData), C.POINTER(EncoderOptionsNative), C.POINTER(EncoderImageMetadataNative), C.POINTER(IOCallbacks),
+                           C.POINTER(ErrorInfo), ProgressFn]
+_lib.SaveImage.restype = C.c_int32
+_lib.JxlB200LoadImageBgra.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200LoadImageBgra.restype = C.c_int32
+_lib.JxlB200PeekInfo.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200PeekInfo.restype = C.c_int32
+_lib.JxlB200DecodeBatch.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200DecodeBatch.restype = C.c_int32
+_lib.JxlB200EncodeToMemory.argtypes = [C.POINTER(BitmapData), C.POINTER(EncoderOptionsNative), C.POINTER(EncoderImageMetadataNative), C.c_int32,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ErrorInfo)]
+_lib.JxlB200EncodeToMemory.restype = C.c_int32
+_lib.JxlB200Free.argtypes = [C.c_void_p]
+_lib.JxlB200LastStageTimes.argtypes = [C.POINTER(C.c_float)]
+_lib.JxlB200KernelLaunchCount.restype = C.c_int64
+_lib.JxlB200DebugDecodeStage.argtypes = [C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200DebugDecodeStage.restype = C.c_int64
+_lib.JxlB200CudaAvailable.argtypes = [C.POINTER(ErrorInfo)]
+_lib.JxlB200CudaAvailable.restype = C.c_int32
+
+# ---- enums (I/DecoderStatus.cs, I/EncoderStatus.cs, I/JpegXLImageChannelRepresentation.cs, I/KnownColorProfile.cs, I/HResult.cs) ----
+DECODER_STATUS = ["Ok", "NullParameter", "InvalidParameter", "OutOfMemory", "HasAnimation", "HasMultipleFrames", "ImageDimensionExceedsInt32",
+                  "UnsupportedChannelFormat", "CreateLayerError", "CreateMetadataError", "DecodeError", "MetadataError", "InvalidFileSignature"]
+ENCODER_STATUS = ["Ok", "NullParameter", "OutOfMemory", "UserCancelled", "EncodeError", "WriteError"]
+IMAGE_FORMAT = ["Gray", "Rgb", "Cmyk"]
+CHANNEL_REPRESENTATION = ["Uint8", "Uint16", "Float16", "Float32"]
+KNOWN_COLOR_PROFILE = ["Srgb", "LinearSrgb", "LinearGray", "GraySrgbTRC", "DisplayP3", "Rec709", "Rec2020Linear", "Rec2020PQ"]
+S_OK, E_POINTER, E_ABORT, E_OUTOFMEMORY, SEEK_ERROR = 0, -2147467261, -2147467260, -2147024882, -2147024871
+_DTYPES = [np.uint8, np.uint16, np.float16, np.float32]
+
+
+class FormatException(Exception):
+    """FormatException thrown by I/JpegXLNative.cs:128-239 for every non-Ok status."""
+
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+class OperationCanceledException(Exception):
+    pass
+
+
+class OutOfMemoryException(MemoryError):
+    pass
+
+
+# ---- QualityToDistanceLookupTable (I/QualityToDistanceLookupTable.cs:26-65) and EncoderOptions (I/EncoderOptions.cs:24-31) ----
+def quality_to_distance(quality):
+    q = int(quality)
+    if q >= 30:
+        return float(np.float32(0.1) + np.float32(100 - q) * np.float32(0.09))
+    if q <= 8:
+        return 15.0
+    return float(np.float32(6.4) + np.float32(np.power(np.float32(2.5), np.float32(30 - q) / np.float32(5.0))) / np.float32(6.25))
+
+
+class EncoderOptions:
+    def __init__(self, quality=90, lossless=False, effort=7):
+        self.distance = 0.0 if lossless else quality_to_distance(quality)
+        self.lossless = bool(lossless)
+        self.effort = int(effort)
+
+
+class EncoderImageMetadata:
+    def __init__(self, exif=None, icc=None, xmp=None):
+        self.exif, self.icc, self.xmp = exif, icc, xmp
+
+
+# ---- TransparencyMapping (I/TransparencyMapping.cs:19-55) ----
+def alpha_to_eight_bit(alpha):
+    a = np.asarray(alpha)
+    if a.dtype == np.uint8:
+        return a
+    if a.dtype == np.uint16:
+        return (a // 257).astype(np.uint8)
+    if a.dtype == np.float16:   # evaluated in half precision, then truncated
+        return (np.clip(a, np.float16(0), np.float16(1)) * np.float16(255)).astype(np.float16).astype(np.uint8)
+    return (np.clip(a.astype(np.float32), np.float32(0), np.float32(1)) * np.float32(255)).astype(np.uint8)
+
+
+def enumerate_lock_rects(width, height, bits_per_pixel):
+    """BitmapUtil2.EnumerateLockRects (S/BitmapUtil2.cs:30-77): full-width strips under WIC's 4 GB lock limit."""
+    stride = (width * bits_per_pixel + 7) >> 3
+    copy_height = max(1, ((1 << 30) // 4) // stride)
+    y = 0
+    while y < height:
+        yield (0, y, width, min(y + copy_height, height))
+        y += copy_height
+
+
+class DecoderLayerData:
+    """I/DecoderLayerData.cs: splits the native interleaved buffer into a colour bitmap and an 8-bit alpha bitmap."""
+
+    def __init__(self, pixels, name, width, height, fmt, representation, has_transparency):
+        self.name = name
+        ncolor = {"Gray": 1, "Rgb": 3, "Cmyk": 4}[fmt]
+        nch = ncolor + (1 if has_transparency else 0)
+        arr = np.frombuffer(pixels, dtype=_DTYPES[representation]).reshape(height, width, nch)
+        if fmt == "Cmyk" and representation != 0:
+            raise FormatException("DecodeError", "unsupported CMYK channel representation")
+        color = arr[..., :ncolor]
+        if fmt == "Gray":
+            color = np.repeat(color, 3, axis=2)   # gray is replicated to RGB (I/DecoderLayerData.cs:164-330)
+        self.color = np.ascontiguousarray(color)
+        self.transparency = alpha_to_eight_bit(np.ascontiguousarray(arr[..., ncolor])) if has_transparency else None
+        self.format = fmt
+        self.representation = representation
+
+
+class DecoderImage:
+    """I/DecoderImage.cs: the callback sink handed to the native LoadImage."""
+
+    def __init__(self):
+        self.width = self.height = 0
+        self.format = None
+        self.channel_representation = 0
+        self.has_transparency = False
+        self.icc_profile = None
+        self.known_color_profile = None
+        self.exif = None
+        self.xmp = None
+        self.layer_data = None
+        self.exception = None
+        self.callback_log = []
+        self._cb = DecoderCallbacks(SetBasicInfoFn(self._set_basic_info), SetMetadataFn(self._set_icc), SetKnownColorProfileFn(self._set_known),
+                                    SetMetadataFn(self._set_exif), SetMetadataFn(self._set_xmp), SetLayerDataFn(self._set_layer))
+
+    def get_decoder_callbacks(self):
+        return self._cb
+
+    def _guard(self, fn):
+        try:
+            fn()
+            return True
+        except Exception as e:   # exceptions never cross the boundary (I/DecoderImage.cs:126-130)
+            self.exception = e
+            return False
+
+    def _set_basic_info(self, w, h, fmt, rep, transparency):
+        self.callback_log.append("setBasicInfo")
+        self.width, self.height, self.format, self.channel_representation, self.has_transparency = w, h, IMAGE_FORMAT[fmt], rep, bool(transparency)
+
+    def _set_icc(self, data, n):
+        self.callback_log.append("setIccProfile")
+        return self._guard(lambda: setattr(self, "icc_profile", C.string_at(data, n)))
+
+    def _set_known(self, profile):
+        self.callback_log.append("setKnownColorProfile")
+        return self._guard(lambda: setattr(self, "known_color_profile", KNOWN_COLOR_PROFILE[profile]))
+
+    def _set_exif(self, data, n):
+        self.callback_log.append("setExif")
+        return self._guard(lambda: setattr(self, "exif", C.string_at(data, n)))
+
+    def _set_xmp(self, data, n):
+        self.callback_log.append("setXmp")
+
+        def keep_first():
+            if self.xmp is None:   # managed side keeps the first packet (I/DecoderImage.cs:248)
+                self.xmp = C.string_at(data, n)
+        return self._guard(keep_first)
+
+    def _set_layer(self, pixels, name, name_len):
+        self.callback_log.append("setLayerData")
+
+        def make():
+            bps = [1, 2, 2, 4][self.channel_representation]
+            ncolor = {"Gray": 1, "Rgb": 3, "Cmyk": 4}[self.format]
+            nbytes = self.width * self.height * (ncolor + (1 if self.has_transparency else 0)) * bps
+            layer_name = C.string_at(name, name_len).decode("utf-8") if name and name_len else None   # trailing NUL kept (Appendix C-3)
+            self.layer_data = DecoderLayerData(C.string_at(pixels, nbytes), layer_name, self.width, self.height, self.format,
+                                               self.channel_representation, self.has_transparency)
+        return self._guard(make)
+
+
+def _message(ei):
+    return ei.errorMessage.decode("utf-8", "replace")
+
+
+class JpegXLNative:
+    """I/JpegXLNative.cs."""
+
+    @staticmethod
+    def GetLibJxlVersion():
+        v = _lib.GetLibJxlVersion()
+        return ((v >> 24) & 0xff, (v >> 16) & 0xff, (v >> 8) & 0xff)
+
+    @staticmethod
+    def LoadImage(data, decoder_image):
+        buf = bytes(data)
+        ei = ErrorInfo()
+        cb = decoder_image.get_decoder_callbacks()
+        status = _lib.LoadImage(C.byref(cb), buf, len(buf), C.byref(ei))
+        if status != 0:
+            JpegXLNative._handle_decoder_error(status, ei, decoder_image)
+
+    @staticmethod
+    def _handle_decoder_error(status, ei, decoder_image):
+        name = DECODER_STATUS[status]
+        if name in ("CreateLayerError", "CreateMetadataError") and decoder_image.exception is not None:
+            raise decoder_image.exception
+        if name == "OutOfMemory":
+            raise OutOfMemoryException()
+        msg = _message(ei)
+        if name == "DecodeError" and msg:
+            raise FormatException(name, msg)
+        raise FormatException(name, {"InvalidFileSignature": "The file is not a valid JPEG XL image.", "DecodeError": "An error occurred when decoding the image.",
+                                     "UnsupportedChannelFormat": "The image has an unsupported channel format.",
+                                     "ImageDimensionExceedsInt32": "The image dimensions are too large."}.get(name, name))
+
+    @staticmethod
+    def SaveImage(surface_bgra, options, metadata, progress_callback, output_stream):
+        surf = np.ascontiguousarray(surface_bgra, dtype=np.uint8)
+        h, w, c = surf.shape
+        assert c == 4
+        bitmap = BitmapData(surf.ctypes.data, w, h, surf.strides[0])
+        opts = EncoderOptionsNative(options.distance, options.effort, options.lossless)
+        keep = []
+
+        def blob(b):
+            if not b:
+                return None, 0
+            arr = (C.c_uint8 * len(b)).from_buffer_copy(b)
+            keep.append(arr)
+            return C.cast(arr, C.c_void_p), len(b)
+
+        meta = EncoderImageMetadataNative()
+        meta.exif, meta.exifSize = blob(metadata.exif)
+        meta.iccProfile, meta.iccProfileSize = blob(metadata.icc)
+        meta.xmp, meta.xmpSize = blob(metadata.xmp)
+        io_cb = StreamIOCallbacks(output_stream)
+        native_io = io_cb.get_native()
+        ei = ErrorInfo()
+        ei.errorMessage = b"\xcc" * 255   # the managed caller passes it uninitialised (I/JpegXLNative.cs:102)
+        prog = ProgressFn(progress_callback) if progress_callback else C.cast(None, ProgressFn)
+        status = _lib.SaveImage(C.byref(bitmap), C.byref(opts), C.byref(meta), C.byref(native_io), C.byref(ei), prog)
+        if status != 0:
+            name = ENCODER_STATUS[status]
+            if name == "UserCancelled":
+                raise OperationCanceledException()
+            if name == "OutOfMemory":
+                raise OutOfMemoryException()
+            if name == "WriteError" and io_cb.exception is not None:
+                raise io_cb.exception
+            msg = _message(ei) if name == "EncodeError" else ""
+            raise FormatException(name, msg or name)
+
+
+class StreamIOCallbacks:
+    """I/StreamIOCallbacks.cs:52-114: Write/Seek over a stream, returning HRESULTs."""
+
+    def __init__(self, stream):
+        self.stream = stream
+        self.exception = None
+        self._w = WriteFn(self._write)
+        self._s = SeekFn(self._seek)
+
+    def get_native(self):
+        return IOCallbacks(self._w, self._s)
+
+    def _write(self, buf, n):
+        if not buf:
+            return E_POINTER
+        try:
+            self.stream.write(C.string_at(buf, n))
+            return S_OK
+        except Exception as e:
+            self.exception = e
+            return E_ABORT if isinstance(e, OperationCanceledException) else -2147467259
+
+    def _seek(self, pos):
+        try:
+            self.stream.seek(pos)
+            return S_OK
+        except Exception as e:
+            self.exception = e
+            return SEEK_ERROR
+
+
+class Document:
+    def __init__(self, width, height):
+        self.width, self.height = width, height
+        self.surface = np.zeros((height, width, 4), np.uint8)   # BGRA32 (Paint.NET Surface)
+        self.color_profile = None
+        self.exif = None
+        self.xmp = None
+        self.layer_name = None
+
+
+class JpegXLLoad:
+    """S/JpegXLLoad.cs:30-115, 219-249 for the 8-bit Gray/RGB(A) path (the WIC / Direct2D branches are out of scope)."""
+
+    @staticmethod
+    def Load(data):
+        image = DecoderImage()
+        JpegXLNative.LoadImage(data, image)
+        layer = image.layer_data
+        doc = Document(image.width, image.height)
+        doc.color_profile = image.known_color_profile or image.icc_profile
+        doc.exif, doc.xmp, doc.layer_name = image.exif, image.xmp, layer.name
+        if layer.format == "Cmyk" or layer.representation != 0:
+            raise NotImplementedError("CMYK / >8-bit surfaces need the host's WIC colour conversion (S/JpegXLLoad.cs:146-172,312-319), out of scope")
+        for (x0, y0, x1, y1) in enumerate_lock_rects(doc.width, doc.height, 24):
+            src = layer.color[y0:y1, x0:x1]
+            dst = doc.surface[y0:y1, x0:x1]
+            dst[..., 0] = src[..., 2]   # SetLayerColorDataFromRgbImage: dst.B = src.B ... (S/JpegXLLoad.cs:219-241)
+            dst[..., 1] = src[..., 1]
+            dst[..., 2] = src[..., 0]
+        doc.surface[..., 3] = layer.transparency if layer.transparency is not None else 255   # S/JpegXLLoad.cs:243-249,111
+        return doc
+
+
+class JpegXLSave:
+    """S/JpegXLSave.cs:30-63."""
+
+    @staticmethod
+    def Save(surface_bgra, output_stream, quality=90, lossless=False, effort=7, progress_callback=None, exif=None, icc=None, xmp=None):
+        JpegXLNative.SaveImage(surface_bgra, EncoderOptions(quality, lossless, effort), EncoderImageMetadata(exif, icc, xmp), progress_callback, output_stream)
+
+
+# ---- extensions ----
+def cuda_available():
+    ei = ErrorInfo()
+    ok = _lib.JxlB200CudaAvailable(C.byref(ei))
+    return bool(ok), _message(ei)
+
+
+def peek_info(data):
+    buf = bytes(data)
+    info = (C.c_int32 * 8)()
+    ei = ErrorInfo()
+    st = _lib.JxlB200PeekInfo(buf, len(buf), info, C.byref(ei))
+    if st != 0:
+        raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
+    return dict(width=info[0], height=info[1], format=IMAGE_FORMAT[info[2]], representation=info[3], has_transparency=bool(info[4]),
+                num_channels=info[5], known_profile=(KNOWN_COLOR_PROFILE[info[6]] if info[6] >= 0 else None), is_container=bool(info[7]))
+
+
+def load_image_bgra(data):
+    info = peek_info(data)
+    buf = bytes(data)
+    out = np.empty((info["height"], info["width"], 4), np.uint8)
+    w, h = C.c_int32(), C.c_int32()
+    ei = ErrorInfo()
+    st = _lib.JxlB200LoadImageBgra(buf, len(buf), out.ctypes.data, out.nbytes, C.byref(w), C.byref(h), C.byref(ei))
+    if st != 0:
+        raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
+    return out
+
+
+def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, width=None, height=None, stride=None):
+    if device_ptr is None:
+        surf = np.ascontiguousarray(surface_bgra, dtype=np.uint8)
+        h, w, _ = surf.shape
+        bitmap = BitmapData(surf.ctypes.data, w, h, surf.strides[0])
+    else:
+        bitmap = BitmapData(device_ptr, width, height, stride)
+    opts = EncoderOptionsNative(options.distance, options.effort, options.lossless)
+    meta = EncoderImageMetadataNative()
+    keep = []
+    if metadata is not None:
+        for field, size, b in (("exif", "exifSize", metadata.exif), ("iccProfile", "iccProfileSize", metadata.icc), ("xmp", "xmpSize", metadata.xmp)):
+            if b:
+                arr = (C.c_uint8 * len(b)).from_buffer_copy(b)
+                keep.append(arr)
+                setattr(meta, field, C.cast(arr, C.c_void_p))
+                setattr(meta, size, len(b))
+    out = C.c_void_p()
+    n = C.c_size_t()
+    ei = ErrorInfo()
+    st = _lib.JxlB200EncodeToMemory(C.byref(bitmap), C.byref(opts), C.byref(meta), 1 if device_ptr is not None else 0, C.byref(out), C.byref(n), C.byref(ei))
+    if st != 0:
+        raise FormatException(ENCODER_STATUS[st], _message(ei) or ENCODER_STATUS[st])
+    data = C.string_at(out, n.value)
+    _lib.JxlB200Free(out)
+    return data
+
+
+def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None):
+    """Host path: datas = list of bytes, out_arrays = list of writable numpy arrays. Device path: device_inputs/device_outputs = lists of int pointers."""
+    n = len(datas) if device_inputs is None else len(device_inputs)
+    ptrs = (C.c_void_p * n)()
+    lens = (C.c_size_t * n)()
+    outs = (C.c_void_p * n)()
+    olens = (C.c_size_t * n)()
+    keep = []
+    for i in range(n):
+        if device_inputs is None:
+            b = bytes(datas[i])
+            keep.append(b)
+            ptrs[i] = C.cast(C.c_char_p(b), C.c_void_p)
+            lens[i] = len(b)
+        else:
+            ptrs[i] = device_inputs[i]
+            lens[i] = sizes[i]
+        if device_outputs is None:
+            outs[i] = out_arrays[i].ctypes.data
+            olens[i] = out_arrays[i].nbytes
+        else:
+            outs[i] = device_outputs[i]
+            olens[i] = out_sizes[i]
+    statuses = (C.c_int32 * n)()
+    ei = ErrorInfo()
+    st = _lib.JxlB200DecodeBatch(device, n, ptrs, lens, outs, olens, int(bgra), int(device_inputs is None), int(device_outputs is None), max_in_flight, statuses, C.byref(ei))
+    if st != 0:
+        raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
+    return list(statuses)
+
+
+def last_stage_times():
+    t = (C.c_float * 8)()
+    _lib.JxlB200LastStageTimes(t)
+    return dict(zip(["h2d", "lf", "ac", "recon", "filters", "output", "d2h", "total"], list(t)))
+
+
+def kernel_launch_count():
+    return int(_lib.JxlB200KernelLaunchCount())
+
+
+def debug_decode_stage(data, which, capacity):
+    buf = bytes(data)
+    out = np.empty(capacity, np.float32)
+    dims = (C.c_int32 * 2)()
+    ei = ErrorInfo()
+    n = _lib.JxlB200DebugDecodeStage(buf, len(buf), which, out.ctypes.data, capacity, dims, C.byref(ei))
+    if n == 0:
+        raise FormatException("DecodeError", _message(ei) or "debug stage unavailable")
+    return out[:n].copy(), (dims[0], dims[1])

@@ -1,0 +1,193 @@
+// pdn-jpegxl_b200 engine — the C-ABI layer: LoadImage / SaveImage / GetLibJxlVersion with the
+// exact observable behaviour of the reference's native DLL, plus the documented extensions.
+//   LoadImage  restates DecoderReadImage           N/Decoder/JxlDecoder.cpp:796-852 (callback order :461-784, :389-400)
+//   SaveImage  restates EncoderWriteImage          N/Encoder/JxlEncoder.cpp:147-392 and OutputProcessor (N/Encoder/OutputProcessor.cpp:18-151)
+//   error text restates SetErrorMessage            N/Common.cpp:18-53
+// No exception crosses the boundary; every failure becomes a status code (+ optional message).
+#include "../../include/JxlFileTypeIO.h"
+#include "engine.h"
+#include "dev/kernels.h"
+#include <cstring>
+#include <cstdlib>
+#include <algorithm>
+#include <deque>
+
+using namespace jxlgpu;
+
+namespace {
+
+void SetErrorMessage(ErrorInfo* ei, const char* msg) {   // N/Common.cpp:18-30: dropped when empty or longer than 255 chars
+  if (ei && msg) { size_t n = strlen(msg); if (n > 0 && n <= 255) { memcpy(ei->errorMessage, msg, n); ei->errorMessage[n] = 0; } }
+}
+void SetErrorMessage(ErrorInfo* ei, const std::string& s) { if (s.size() > 255) SetErrorMessage(ei, s.substr(0, 255).c_str()); else SetErrorMessage(ei, s.c_str()); }
+
+thread_local StageTimes g_last_times;
+
+const int32_t kSOk = 0, kEPointer = int32_t(0x80004003), kEAbort = int32_t(0x80004004), kEOutOfMemory = int32_t(0x8007000E);
+
+// N/Encoder/OutputProcessor.cpp: <= 64 KiB chunks, sticky first failure, progress tick per buffer request.
+class OutputProcessor {
+ public:
+  explicit OutputProcessor(IOCallbacks* cb) : cb_(cb) {}
+  void InitializeProgressReporting(ProgressProc p, int32_t initial, int32_t max, int32_t step) { progress_ = p; pct_ = initial; max_ = max; step_ = step; }
+  EncoderStatus GetWriteStatus() const { return status_; }
+  // mirrors GetBuffer/ReleaseBuffer pairs: returns false once a callback failed or the user cancelled
+  bool Write(const uint8_t* data, size_t size) {
+    size_t pos = 0;
+    while (pos < size) {
+      if (status_ != EncoderStatus_Ok || !ReportProgress()) return false;
+      size_t n = std::min<size_t>(65536, size - pos); SetIfFailed(cb_->Write(data + pos, n)); pos += n;
+    }
+    return status_ == EncoderStatus_Ok;
+  }
+  void Seek(uint64_t p) { SetIfFailed(cb_->Seek(p)); }
+ private:
+  bool ReportProgress() { bool r = true; if (progress_) { if (pct_ < max_) pct_ += step_; r = progress_(pct_); if (!r) status_ = EncoderStatus_UserCanceled; } return r; }
+  void SetIfFailed(int32_t hr) { if (hr < 0) { if (hr == kEAbort) status_ = EncoderStatus_UserCanceled; else if (hr == kEOutOfMemory) status_ = EncoderStatus_OutOfMemory; else status_ = EncoderStatus_WriteError; } }
+  IOCallbacks* cb_; EncoderStatus status_ = EncoderStatus_Ok; ProgressProc progress_ = nullptr; int32_t pct_ = 0, max_ = 0, step_ = 0;
+};
+
+bool ReportProgress(ProgressProc p, int32_t pct) { return p ? p(pct) : true; }
+
+}  // namespace
+
+extern "C" {
+
+uint32_t GetLibJxlVersion(void) { return (0u << 24) | (11u << 16) | (1u << 8); }   // bitstream behaviour follows libjxl 0.11.x
+
+DecoderStatus LoadImage(DecoderCallbacks* callbacks, const uint8_t* data, size_t dataSize, ErrorInfo* errorInfo) {
+  if (!callbacks || !data) return DecoderStatus_NullParameter;
+  try {
+    // pass 1: basic info, colour profile, metadata boxes (N/Decoder/JxlDecoder.cpp:412-793)
+    DecodeResult info = ParseInfo(data, dataSize);
+    if (info.status != Status::Ok) { SetErrorMessage(errorInfo, info.message); return DecoderStatus(info.status); }
+    const ParsedInfo& pi = info.info;
+    callbacks->setBasicInfo(int32_t(pi.width), int32_t(pi.height), pi.format, pi.sample_type, pi.has_alpha);
+    if (pi.known_profile >= 0) { if (!callbacks->setKnownColorProfile(pi.known_profile)) return DecoderStatus_CreateMetadataError; }
+    else if (!pi.icc.empty()) { std::vector<uint8_t> icc = pi.icc; if (!callbacks->setIccProfile(icc.data(), icc.size())) return DecoderStatus_CreateMetadataError; }
+    if (pi.is_container) {
+      if (pi.has_exif) { std::vector<uint8_t> e = pi.exif; if (!callbacks->setExif(e.data(), e.size())) return DecoderStatus_CreateMetadataError; }
+      for (const auto& x : pi.xmp) { std::vector<uint8_t> b = x; if (!callbacks->setXmp(b.data(), b.size())) return DecoderStatus_CreateMetadataError; }
+    }
+    // pass 2: the frame (N/Decoder/JxlDecoder.cpp:217-410)
+    DecodeRequest req; req.data = data; req.size = dataSize;
+    DecodeResult res = DecodeOnGpu(req); g_last_times = res.times;
+    if (res.status != Status::Ok) { SetErrorMessage(errorInfo, res.message); return DecoderStatus(res.status); }
+    // layer name: length passed includes the NUL terminator (N/Decoder/JxlDecoder.cpp:274,366-370 — Appendix C-3)
+    std::vector<char> name; if (!res.info.frame_name.empty()) { name.assign(res.info.frame_name.begin(), res.info.frame_name.end()); name.push_back(0); }
+    if (!callbacks->setLayerData(res.pixels, name.empty() ? nullptr : name.data(), name.size())) return DecoderStatus_CreateLayerError;
+  } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; }
+  catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; }
+  catch (...) { return DecoderStatus_DecodeError; }
+  return DecoderStatus_Ok;
+}
+
+EncoderStatus SaveImage(const BitmapData* bitmap, const EncoderOptions* options, const EncoderImageMetadata* metadata, IOCallbacks* callbacks, ErrorInfo* errorInfo, ProgressProc progressCallback) {
+  if (!bitmap || !options || !callbacks || !metadata) return EncoderStatus_NullParameter;
+  if (errorInfo) errorInfo->errorMessage[0] = 0;   // the managed caller passes it uninitialised (I/JpegXLNative.cs:102)
+  try {
+    // progress sequence 0, 5, 15, 20, 25, then +5 per output buffer from 30 capped at 90, then 95 (N/Encoder/JxlEncoder.cpp:162-362)
+    if (!ReportProgress(progressCallback, 0)) return EncoderStatus_UserCanceled;
+    EncodeRequest req; req.bgra = bitmap->scan0; req.width = bitmap->width; req.height = bitmap->height; req.stride = bitmap->stride;
+    req.distance = options->distance; req.effort = options->effort; req.lossless = options->lossless;
+    req.exif = metadata->exif; req.exif_size = metadata->exifSize; req.icc = metadata->iccProfile; req.icc_size = metadata->iccProfileSize; req.xmp = metadata->xmp; req.xmp_size = metadata->xmpSize;
+    if (!ReportProgress(progressCallback, 5)) return EncoderStatus_UserCanceled;
+    if (!ReportProgress(progressCallback, 15)) return EncoderStatus_UserCanceled;
+    if (!ReportProgress(progressCallback, 20)) return EncoderStatus_UserCanceled;
+    if (!ReportProgress(progressCallback, 25)) return EncoderStatus_UserCanceled;
+    OutputProcessor out(callbacks); out.InitializeProgressReporting(progressCallback, 30, 90, 5);
+    EncodeResult res = EncodeOnGpu(req); g_last_times = res.times;
+    if (res.status != EncStatus::Ok) { SetErrorMessage(errorInfo, res.message); return EncoderStatus(res.status); }
+    // libjxl streams output while encoding; the engine produces the file after the kernels finish and streams it the same way
+    size_t half = res.file.size() / 2;
+    bool ok = out.Write(res.file.data(), half);
+    if (!ok) { EncoderStatus st = out.GetWriteStatus(); if (st == EncoderStatus_Ok) { SetErrorMessage(errorInfo, "JxlEncoderAddImageFrame failed."); st = EncoderStatus_EncodeError; } return st; }
+    if (!ReportProgress(progressCallback, 95)) return EncoderStatus_UserCanceled;
+    ok = out.Write(res.file.data() + half, res.file.size() - half);
+    if (!ok) { EncoderStatus st = out.GetWriteStatus(); if (st != EncoderStatus_Ok) return st; SetErrorMessage(errorInfo, "JxlEncoderFlushInput failed."); return EncoderStatus_EncodeError; }
+  } catch (const std::bad_alloc&) { return EncoderStatus_OutOfMemory; }
+  catch (...) { return EncoderStatus_EncodeError; }
+  return EncoderStatus_Ok;
+}
+
+DecoderStatus JxlB200PeekInfo(const uint8_t* data, size_t dataSize, int32_t* info, ErrorInfo* errorInfo) {
+  if (!data || !info) return DecoderStatus_NullParameter;
+  DecodeResult r = ParseInfo(data, dataSize); if (r.status != Status::Ok) { SetErrorMessage(errorInfo, r.message); return DecoderStatus(r.status); }
+  info[0] = int32_t(r.info.width); info[1] = int32_t(r.info.height); info[2] = r.info.format; info[3] = r.info.sample_type; info[4] = r.info.has_alpha; info[5] = r.info.num_channels; info[6] = r.info.known_profile; info[7] = r.info.is_container;
+  return DecoderStatus_Ok;
+}
+
+DecoderStatus JxlB200LoadImageBgra(const uint8_t* data, size_t dataSize, uint8_t* surface, size_t surfaceBytes, int32_t* width, int32_t* height, ErrorInfo* errorInfo) {
+  if (!data || !surface) return DecoderStatus_NullParameter;
+  try {
+    DecodeRequest req; req.data = data; req.size = dataSize; req.bgra = true; DecodeResult res = DecodeOnGpu(req); g_last_times = res.times;
+    if (res.status != Status::Ok) { SetErrorMessage(errorInfo, res.message); return DecoderStatus(res.status); }
+    if (surfaceBytes < res.pixel_bytes) { SetErrorMessage(errorInfo, "surface buffer too small"); return DecoderStatus_InvalidParameter; }
+    memcpy(surface, res.pixels, res.pixel_bytes); if (width) *width = int32_t(res.out_width); if (height) *height = int32_t(res.out_height);
+  } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
+  return DecoderStatus_Ok;
+}
+
+DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes, uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
+                                 int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, DecoderStatus* statuses, ErrorInfo* errorInfo) {
+  if (!datas || !dataSizes || !outputs || !outputBytes || count < 0) return DecoderStatus_NullParameter;
+  DecoderStatus first = DecoderStatus_Ok;
+  try {
+    std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return DecoderStatus_DecodeError; }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
+    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 64)); std::vector<cudaStream_t> streams(nstreams);
+    for (auto& s : streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; std::vector<uint8_t> host_copy; };
+    std::deque<InFlight> q;
+    auto retire = [&]() {
+      InFlight& f = q.front(); DecodeFinish(f.job, &f.res); DecoderStatus st = DecoderStatus(f.res.status);
+      if (st == DecoderStatus_Ok) {
+        if (f.res.pixel_bytes > outputBytes[f.idx]) st = DecoderStatus_InvalidParameter;
+        else if (hostOutputs) memcpy(outputs[f.idx], f.res.pixels, f.res.pixel_bytes);
+        else if (cudaMemcpyAsync(outputs[f.idx], f.res.pixels, f.res.pixel_bytes, cudaMemcpyDeviceToDevice, f.job ? streams[f.idx % nstreams] : nullptr) != cudaSuccess || cudaStreamSynchronize(streams[f.idx % nstreams]) != cudaSuccess) st = DecoderStatus_DecodeError;
+      } else if (first == DecoderStatus_Ok) SetErrorMessage(errorInfo, f.res.message);
+      if (statuses) statuses[f.idx] = st; if (st != DecoderStatus_Ok && first == DecoderStatus_Ok) first = st;
+      q.pop_front();
+    };
+    for (int i = 0; i < count; i++) {
+      if (int(q.size()) >= nstreams) retire();
+      q.emplace_back(); InFlight& f = q.back(); f.idx = i; DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i];
+      if (hostInputs) req.data = datas[i];
+      else { f.host_copy.resize(dataSizes[i]); if (cudaMemcpy(f.host_copy.data(), datas[i], dataSizes[i], cudaMemcpyDeviceToHost) != cudaSuccess) { f.res.status = Status::DecodeError; f.res.message = "cannot read device input"; continue; } req.data = f.host_copy.data(); req.device_input = datas[i]; }
+      f.job = DecodeEnqueue(req, streams[i % nstreams], &f.res);
+    }
+    while (!q.empty()) retire();
+    for (auto& s : streams) cudaStreamDestroy(s);
+  } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
+  return first;
+}
+
+EncoderStatus JxlB200EncodeToMemory(const BitmapData* bitmap, const EncoderOptions* options, const EncoderImageMetadata* metadata, int32_t deviceInput, uint8_t** out, size_t* outSize, ErrorInfo* errorInfo) {
+  if (!bitmap || !options || !out || !outSize) return EncoderStatus_NullParameter;
+  try {
+    EncodeRequest req; req.bgra = bitmap->scan0; req.width = bitmap->width; req.height = bitmap->height; req.stride = bitmap->stride; req.distance = options->distance; req.effort = options->effort; req.lossless = options->lossless; req.device_input = deviceInput != 0;
+    if (metadata) { req.exif = metadata->exif; req.exif_size = metadata->exifSize; req.icc = metadata->iccProfile; req.icc_size = metadata->iccProfileSize; req.xmp = metadata->xmp; req.xmp_size = metadata->xmpSize; }
+    EncodeResult res = EncodeOnGpu(req); g_last_times = res.times;
+    if (res.status != EncStatus::Ok) { SetErrorMessage(errorInfo, res.message); return EncoderStatus(res.status); }
+    *out = static_cast<uint8_t*>(malloc(res.file.size() ? res.file.size() : 1)); if (!*out) return EncoderStatus_OutOfMemory; memcpy(*out, res.file.data(), res.file.size()); *outSize = res.file.size();
+  } catch (const std::bad_alloc&) { return EncoderStatus_OutOfMemory; } catch (...) { return EncoderStatus_EncodeError; }
+  return EncoderStatus_Ok;
+}
+void JxlB200Free(void* p) { free(p); }
+
+void JxlB200LastStageTimes(float* ms8) { if (!ms8) return; const StageTimes& t = g_last_times; ms8[0] = t.h2d; ms8[1] = t.lf; ms8[2] = t.ac; ms8[3] = t.recon; ms8[4] = t.filters; ms8[5] = t.output; ms8[6] = t.d2h; ms8[7] = t.total; }
+int64_t JxlB200KernelLaunchCount(void) { return LaunchCount(); }
+int32_t JxlB200CudaAvailable(ErrorInfo* errorInfo) { std::string why; bool ok = CudaAvailable(&why); if (!ok) SetErrorMessage(errorInfo, why); return ok ? 1 : 0; }
+
+int64_t JxlB200DebugDecodeStage(const uint8_t* data, size_t dataSize, int32_t which, float* out, int64_t capacity, int32_t* dims2, ErrorInfo* errorInfo) {
+  if (!data || !out) return 0;
+  try {
+    DecodeRequest req; req.data = data; req.size = dataSize; DecodeResult res = DecodeOnGpu(req);
+    if (res.status != Status::Ok) { SetErrorMessage(errorInfo, res.message); return 0; }
+    if (which == 4) { std::vector<int16_t> c; if (!DecodeDebugCoeffs(res.job, &c) || int64_t(c.size()) > capacity) return 0; for (size_t i = 0; i < c.size(); i++) out[i] = float(c[i]); return int64_t(c.size()); }
+    std::vector<float> v; int xp = 0, yp = 0; if (!DecodeDebugPlanes(res.job, which, &v, &xp, &yp) || int64_t(v.size()) > capacity) return 0;
+    memcpy(out, v.data(), v.size() * 4); if (dims2) { dims2[0] = xp; dims2[1] = yp; } return int64_t(v.size());
+  } catch (...) { return 0; }
+}
+
+}  // extern "C"

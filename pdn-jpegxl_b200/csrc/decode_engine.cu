@@ -1,0 +1,440 @@
+// pdn-jpegxl_b200 engine — decode orchestration: host front-end parse -> flat device tables ->
+// kernel pipeline -> pixel buffer. This is the engine behind LoadImage; it restates what
+// DecoderReadImage drives through libjxl (N/Decoder/JxlDecoder.cpp:796-852): header/metadata
+// pass (:412-793), format decisions (:461-561), first frame only (:398-400), interleaved
+// tightly-packed output (:289-323), straight alpha (:233), CMYK merge (:159-215).
+// There is no CPU decode path: without a CUDA device every call fails with DecodeError.
+#include "engine.h"
+#include "dev/kernels.h"
+#include "host/headers.h"
+#include "host/modular_host.h"
+#include "host/vardct_tables.h"
+#include <dlfcn.h>
+#include <map>
+#include <mutex>
+#include <chrono>
+
+namespace jxlgpu {
+
+// ---------------------------------------------------------------- small utilities
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw Error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #expr); } while (0)
+
+bool CudaAvailable(std::string* why) {
+  int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { if (why) *why = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + "); the engine has no CPU fallback"; cudaGetLastError(); return false; }
+  return true;
+}
+
+// Caching allocators (device + pinned host). cudaMalloc / cudaHostAlloc cost milliseconds; a decode is a handful of ms.
+class Pool {
+ public:
+  explicit Pool(bool pinned) : pinned_(pinned) {}
+  void* Get(size_t bytes) {
+    size_t sz = Round(bytes); { std::lock_guard<std::mutex> lk(mu_); auto it = free_.find(sz); if (it != free_.end() && !it->second.empty()) { void* p = it->second.back(); it->second.pop_back(); cached_ -= sz; return p; } }
+    void* p = nullptr; cudaError_t e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz);
+    if (e != cudaSuccess) { cudaGetLastError(); Trim(); e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz); }
+    if (e != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+    return p;
+  }
+  void Put(void* p, size_t bytes) { if (!p) return; size_t sz = Round(bytes); std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; if (cached_ > limit_) TrimLocked(); }
+  void Trim() { std::lock_guard<std::mutex> lk(mu_); TrimLocked(); }
+ private:
+  static size_t Round(size_t b) { size_t g = b < (1u << 20) ? 4096 : (size_t(1) << 20); return (b + g - 1) / g * g; }
+  void TrimLocked() { for (auto& kv : free_) for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } free_.clear(); cached_ = 0; }
+  bool pinned_; std::mutex mu_; std::map<size_t, std::vector<void*>> free_; size_t cached_ = 0; size_t limit_ = size_t(48) << 30;
+};
+static Pool& DevPool() { static Pool p(false); return p; }
+static Pool& HostPool() { static Pool p(true); return p; }
+void TrimPools() { DevPool().Trim(); HostPool().Trim(); }
+
+struct DevBuf { void* p = nullptr; size_t n = 0; bool host = false; void Alloc(size_t bytes, bool pinned = false) { Free(); host = pinned; n = bytes ? bytes : 1; p = (pinned ? HostPool() : DevPool()).Get(n); } void Free() { if (p) (host ? HostPool() : DevPool()).Put(p, n); p = nullptr; n = 0; } ~DevBuf() { Free(); } template <class T> T* as() const { return static_cast<T*>(p); } };
+
+static const DTables* DeviceTables() {
+  static std::mutex mu; static std::map<int, DTables*> per_dev; std::lock_guard<std::mutex> lk(mu); int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+  auto it = per_dev.find(dev); if (it != per_dev.end()) return it->second;
+  std::unique_ptr<DTables> h(new DTables); FillDeviceTables(h.get()); DTables* d = nullptr; CUDA_OK(cudaMalloc(&d, sizeof(DTables))); CUDA_OK(cudaMemcpy(d, h.get(), sizeof(DTables), cudaMemcpyHostToDevice)); per_dev[dev] = d; return d;
+}
+
+static std::vector<uint8_t> BrotliDecompress(const uint8_t* data, size_t size) {
+  typedef int (*Fn)(size_t, const uint8_t*, size_t*, uint8_t*);
+  static Fn fn = []() -> Fn { void* h = dlopen("libbrotlidec.so.1", RTLD_NOW); return h ? reinterpret_cast<Fn>(dlsym(h, "BrotliDecoderDecompress")) : nullptr; }();
+  JXLG_CHECK(fn != nullptr, "brob box: libbrotlidec.so.1 not available");
+  for (size_t cap = std::max<size_t>(size * 8, 1 << 16); cap <= (size_t(1) << 31); cap *= 4) { std::vector<uint8_t> out(cap); size_t n = cap; if (fn(size, data, &n, out.data()) == 1) { out.resize(n); return out; } }
+  throw Error("brob box: brotli stream invalid or too large");
+}
+std::vector<uint8_t> ReadIccStream(BitReader&) { throw Error("ICC-stream colour profiles are not supported yet"); }
+void WriteIccStream(BitWriter&, const std::vector<uint8_t>&) { throw Error("ICC-stream colour profiles are not supported yet"); }
+
+// ---------------------------------------------------------------- pass 1: info + metadata
+struct Headers { ContainerInfo ci; ImageMetadata meta; size_t frame_pos = 0; /* byte offset of the first frame in the codestream */ };
+
+static int KnownProfileOf(const ColorEncoding& c) {   // N/Decoder/JxlDecoder.cpp:36-108
+  if (c.want_icc || c.have_gamma) return -1;
+  if (c.color_space == kCsRGB && c.white_point == kWpD65) {
+    if (c.tf == kTfLinear) { if (c.primaries == kPrSRGB) return 1; if (c.primaries == kPr2100) return 6; }
+    else if (c.tf == kTfSRGB) { if (c.primaries == kPrSRGB) return 0; if (c.primaries == kPrP3) return 4; }
+    else if (c.tf == kTf709) { if (c.primaries == kPrSRGB) return 5; }
+    else if (c.primaries == kPr2100) { if (c.tf == kTfPQ) return 7; }
+  } else if (c.color_space == kCsGray && c.white_point == kWpD65) { if (c.tf == kTfLinear) return 2; if (c.tf == kTfSRGB) return 3; }
+  return -1;
+}
+// Output encoding of the samples (Appendix C-1): original enum encoding when expressible without a CMS, else sRGB.
+static ColorEncoding OutputEncoding(const ImageMetadata& m) {
+  ColorEncoding t; if (!m.xyb_encoded) return m.ce;
+  bool ok = !m.ce.want_icc && (m.ce.have_gamma || (m.ce.tf != kTfUnknown && m.ce.tf != kTfHLG)) && m.ce.color_space != kCsXYB && m.ce.color_space != kCsUnknown;
+  if (ok) return m.ce; t.color_space = m.ce.color_space == kCsGray ? kCsGray : kCsRGB; t.intent = 0; return t;
+}
+
+static Status ParseHeadersInto(const uint8_t* data, size_t size, Headers* h, ParsedInfo* info, std::string* msg) {
+  int sig = SignatureCheck(data, size); if (sig == 0) return Status::InvalidFileSignature;
+  h->ci = ParseContainer(data, size); info->is_container = h->ci.is_container; const std::vector<uint8_t>& cs = h->ci.codestream;
+  JXLG_CHECK(cs.size() >= 2 && cs[0] == 0xFF && cs[1] == 0x0A, "codestream signature");
+  BitReader br(cs.data() + 2, cs.size() - 2); h->meta = ReadImageHeaders(br); const ImageMetadata& m = h->meta; h->frame_pos = 2 + br.pos / 8;
+  // BASIC_INFO decisions, N/Decoder/JxlDecoder.cpp:461-561
+  if (m.xsize > 0x7fffffffu || m.ysize > 0x7fffffffu) return Status::ImageDimensionExceedsInt32;
+  int alpha = m.alpha_index(); uint32_t alpha_bits = alpha >= 0 ? m.ec[alpha].bd.bits : 0; info->has_alpha = alpha_bits != 0; int black = -1; bool first_alpha = false;
+  for (size_t i = 0; i < m.ec.size(); i++) {
+    if (m.ec[i].type == kEcBlack) { if (black < 0) black = int(i); else return Status::UnsupportedChannelFormat; }
+    else if (m.ec[i].type == kEcAlpha) { if (info->has_alpha && !first_alpha) first_alpha = true; else return Status::UnsupportedChannelFormat; }
+  }
+  int cc = m.num_color_channels(); info->num_channels = cc + (info->has_alpha ? 1 : 0); info->format = cc == 1 ? 0 : (black >= 0 ? 2 : 1); info->sample_type = 0; info->width = m.xsize; info->height = m.ysize;
+  if (m.bd.exp_bits > 0) {
+    if (info->format == 2) { *msg = "Floating point CMYK images are not supported."; return Status::DecodeError; }
+    if (m.bd.bits <= 16) info->sample_type = 2; else if (m.bd.bits <= 32) info->sample_type = 3; else { *msg = "Unsupported floating point bit depth: " + std::to_string(m.bd.bits) + "."; return Status::DecodeError; }
+  } else if (m.bd.bits > 8) {
+    if (m.bd.bits <= 16) { if (info->format == 2) { *msg = "CMYK64 images are not supported."; return Status::DecodeError; } info->sample_type = 1; }
+    else { *msg = "Unsupported integer bit depth: " + std::to_string(m.bd.bits) + "."; return Status::DecodeError; }
+  }
+  if (m.orientation >= 5) std::swap(info->width, info->height);
+  // COLOR_ENCODING, :562-686 — the profile reported is the one describing the delivered samples
+  ColorEncoding out_ce = OutputEncoding(m); info->known_profile = KnownProfileOf(out_ce); if (m.ce.want_icc && !m.xyb_encoded) info->icc = m.icc;
+  // BOX events, :687-784: first Exif box only, every xml box, brob decompressed; container files only
+  for (const Box& b : h->ci.boxes) {
+    const uint8_t* p = b.data; size_t n = b.size; char type[5]; memcpy(type, b.type, 5); std::vector<uint8_t> tmp;
+    if (!strcmp(type, "brob") && n >= 4) { memcpy(type, p, 4); type[4] = 0; if (!strcmp(type, "Exif") || !strcmp(type, "xml ")) { tmp = BrotliDecompress(p + 4, n - 4); p = tmp.data(); n = tmp.size(); } }
+    if (!strcmp(type, "Exif")) { if (!info->has_exif) { info->has_exif = true; info->exif.assign(p, p + n); } } else if (!strcmp(type, "xml ")) info->xmp.emplace_back(p, p + n);
+  }
+  return Status::Ok;
+}
+
+DecodeResult ParseInfo(const uint8_t* data, size_t size) {
+  DecodeResult r; if (!data) { r.status = Status::NullParameter; return r; }
+  try { Headers h; r.status = ParseHeadersInto(data, size, &h, &r.info, &r.message); }
+  catch (const std::bad_alloc&) { r.status = Status::OutOfMemory; } catch (const std::exception& e) { r.status = Status::DecodeError; r.message = e.what(); }
+  return r;
+}
+
+// ---------------------------------------------------------------- blob builder
+struct Blob {
+  std::vector<uint8_t> b;
+  uint32_t Add(const void* p, size_t n, size_t align = 16) { size_t o = (b.size() + align - 1) / align * align; b.resize(o + n); if (n) memcpy(&b[o], p, n); JXLG_CHECK(b.size() < (size_t(1) << 31), "table blob too large"); return uint32_t(o); }
+  DCode AddCode(const Code& c) {
+    JXLG_CHECK(!c.lz77, "LZ77-enabled entropy streams are not supported by the GPU decoder yet");
+    DCode d; memset(&d, 0, sizeof(d)); d.num_ctx = uint32_t(c.ctx_map.size()); d.num_clusters = uint32_t(c.cfg.size()); d.log_alpha = uint32_t(c.log_alpha); d.use_prefix = c.use_prefix;
+    d.ctx_map_off = Add(c.ctx_map.data(), c.ctx_map.size()); std::vector<DHybrid> cfg(c.cfg.size()); for (size_t i = 0; i < cfg.size(); i++) cfg[i] = DHybrid{uint8_t(c.cfg[i].split_exp), uint8_t(c.cfg[i].msb), uint8_t(c.cfg[i].lsb), 0};
+    d.cfg_off = Add(cfg.data(), cfg.size() * sizeof(DHybrid));
+    if (!c.use_prefix) {
+      size_t ts = size_t(1) << c.log_alpha; std::vector<uint64_t> al(c.ans.size() * ts);
+      for (size_t k = 0; k < c.ans.size(); k++) { const AnsTable& t = c.ans[k]; for (size_t i = 0; i < ts; i++) al[k * ts + i] = PackAlias(t.cutoff[i], t.right[i], t.off1[i], t.freq[i], t.freq[t.right[i]]); }
+      d.alias_off = Add(al.data(), al.size() * 8);
+    } else {
+      std::vector<uint32_t> desc(2 * c.prefix.size());
+      for (size_t k = 0; k < c.prefix.size(); k++) { const PrefixTable& t = c.prefix[k]; std::vector<uint32_t> lut(size_t(1) << t.max_len);
+        if (t.max_len == 0) lut[0] = uint32_t(t.single) << 4; else for (size_t i = 0; i < lut.size(); i++) lut[i] = (uint32_t(t.lut_sym[i]) << 4) | t.lut_len[i];
+        desc[2 * k] = Add(lut.data(), lut.size() * 4); desc[2 * k + 1] = uint32_t(t.max_len); }
+      d.prefix_off = Add(desc.data(), desc.size() * 4);
+    }
+    return d;
+  }
+};
+
+static const std::vector<float>& DefaultDequant(int t) { static std::vector<float> tab[kNumQuantTables]; static std::once_flag once; std::call_once(once, []() { for (int i = 0; i < kNumQuantTables; i++) tab[i] = ComputeDequantTable(i, LibraryEncoding(i)); }); return tab[t]; }
+static const std::vector<uint32_t>& NaturalOrderCached(int o) { static std::vector<uint32_t> tab[kNumOrders]; static std::once_flag once; std::call_once(once, []() { for (int i = 0; i < kNumOrders; i++) { int s = kOrderStrategy[i]; tab[i] = NaturalOrder(std::min(kCoveredX[s], kCoveredY[s]), std::max(kCoveredX[s], kCoveredY[s])); } }); return tab[o]; }
+
+static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
+  auto read_params = [&](DctParams& p) { p.num_bands = int(br.ReadBits(4)) + 1; for (int c = 0; c < 3; c++) { for (int i = 0; i < p.num_bands; i++) p.bands[c][i] = br.F16(); JXLG_CHECK(p.bands[c][0] >= 1e-8f, "distance band"); p.bands[c][0] *= 64.0f; } };
+  QuantEncoding e; e.mode = int(br.ReadBits(3)); bool small = kTableRows[t] == 1 && kTableCols[t] == 1;
+  switch (e.mode) {
+    case kQModeLibrary: return LibraryEncoding(t);
+    case kQModeId: JXLG_CHECK(small, "quant mode/table mismatch"); for (int c = 0; c < 3; c++) for (int i = 0; i < 3; i++) e.idw[c][i] = br.F16() * 64.0f; break;
+    case kQModeDCT2: JXLG_CHECK(small, "quant mode/table mismatch"); for (int c = 0; c < 3; c++) for (int i = 0; i < 6; i++) e.dct2w[c][i] = br.F16() * 64.0f; break;
+    case kQModeDCT4: JXLG_CHECK(small, "quant mode/table mismatch"); for (int c = 0; c < 3; c++) for (int i = 0; i < 2; i++) e.dct4mul[c][i] = br.F16(); read_params(e.dct4); break;
+    case kQModeDCT4x8: JXLG_CHECK(small, "quant mode/table mismatch"); for (int c = 0; c < 3; c++) e.dct4x8mul[c] = br.F16(); read_params(e.dct4x8); break;
+    case kQModeDCT: read_params(e.dct); break;
+    default: throw Error("AFV / RAW quant table encodings are not supported");
+  }
+  return e;
+}
+
+// ---------------------------------------------------------------- the job
+class DecodeJob {
+ public:
+  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
+  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err;
+  cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
+  bool has_tree = false; Tree tree; Code tree_code; GroupHeader gheader; size_t global_decoded = 0; uint64_t global_data_bitpos = 0; bool global_has_data = false;
+  std::vector<Code> ac_codes; uint32_t hf_blob_mark = 0;
+  ~DecodeJob() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+
+  void Setup(const DecodeRequest& req);
+  void ParseLfGlobal(BitReader& br);
+  void ParseHfGlobal(BitReader& br);
+  void AllocateAndUpload(const DecodeRequest& req);
+  void UploadFrame();
+  void Run(const DecodeRequest& req);
+};
+
+void DecodeJob::ParseLfGlobal(BitReader& br) {
+  const ImageMetadata& m = hd.meta;
+  JXLG_CHECK(!(fh.flags & (kFlagPatches | kFlagSplines | kFlagNoise)), "patches/splines/noise are not supported");
+  float lf_dequant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256}; uint32_t global_scale = 1, quant_lf = 16; BlockCtxMap bctx; uint32_t color_factor = 84; float base_x = 0.f, base_b = 1.f; int32_t xlf = 0, blf = 0;
+  if (fh.encoding == 0) {
+    JXLG_CHECK(!(fh.flags & kFlagUseLfFrame), "LF frames are not supported");
+    if (!br.Bool()) for (int c = 0; c < 3; c++) { lf_dequant[c] = br.F16() * (1.0f / 128.0f); JXLG_CHECK(lf_dequant[c] >= 1e-8f, "lf dequant"); }
+    global_scale = br.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193)); quant_lf = br.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));
+    if (!br.Bool()) {
+      bctx.num_lf_ctxs = 1; for (int j = 0; j < 3; j++) { uint32_t n = br.ReadBits(4); bctx.lf_thr[j].resize(n); for (auto& t : bctx.lf_thr[j]) t = UnpackSigned(br.U32(Bits(4), BitsOffset(8, 16), BitsOffset(16, 272), BitsOffset(32, 65808))); bctx.num_lf_ctxs *= n + 1; }
+      uint32_t nq = br.ReadBits(4); bctx.qf_thr.resize(nq); for (auto& t : bctx.qf_thr) t = br.U32(Bits(2), BitsOffset(3, 4), BitsOffset(5, 12), BitsOffset(8, 44)) + 1;
+      JXLG_CHECK(bctx.num_lf_ctxs * (nq + 1) <= 64, "block context map too large"); size_t ncl = 0; bctx.map = DecodeContextMap(br, size_t(3) * kNumOrders * bctx.num_lf_ctxs * (nq + 1), &ncl); JXLG_CHECK(ncl <= 16, "too many block contexts"); bctx.num_ctxs = uint32_t(ncl);
+    }
+    if (!br.Bool()) { color_factor = br.U32(Val(84), Val(256), BitsOffset(8, 2), BitsOffset(16, 258)); base_x = br.F16(); base_b = br.F16(); xlf = int32_t(br.ReadBits(8)) - 128; blf = int32_t(br.ReadBits(8)) - 128; }
+    float inv_gs = 65536.0f / float(global_scale), lfinv = inv_gs / float(quant_lf);
+    for (int c = 0; c < 3; c++) h.lf_fac[c] = lf_dequant[c] * lfinv;
+    h.inv_color_factor = 1.0f / float(color_factor); h.base_x = base_x; h.base_b = base_b; h.cfl_x_lf = base_x + float(xlf) / float(color_factor); h.cfl_b_lf = base_b + float(blf) / float(color_factor);
+    h.inv_gs = inv_gs; h.quant_scale = float(global_scale) / 65536.0f; h.xm = std::pow(0.8f, float(fh.x_qm_scale) - 2.0f); h.bm = std::pow(0.8f, float(fh.b_qm_scale) - 2.0f);
+    for (int i = 0; i < 4; i++) h.quant_bias[i] = m.opsin.quant_bias[i];
+    h.nb_block_ctx = bctx.num_ctxs; h.num_lf_ctxs = bctx.num_lf_ctxs; h.n_qf_thr = uint32_t(bctx.qf_thr.size()); for (size_t i = 0; i < bctx.qf_thr.size(); i++) h.qf_thr[i] = bctx.qf_thr[i];
+    for (int j = 0; j < 3; j++) { h.n_lf_thr[j] = uint32_t(bctx.lf_thr[j].size()); for (size_t i = 0; i < bctx.lf_thr[j].size(); i++) h.lf_thr[j][i] = bctx.lf_thr[j][i]; }
+    h.bctx_map_off = blob.Add(bctx.map.data(), bctx.map.size());
+  }
+  has_tree = br.Bool();
+  if (has_tree) {
+    size_t nch = (fh.encoding == 1 ? 3 : 0) + m.ec.size(); size_t limit = std::min<size_t>(size_t(1) << 22, 1024 + size_t(fh.xsize) * fh.ysize * std::max<size_t>(nch, 1) / 16); limit = std::max<size_t>(limit, 1 << 16);
+    tree = DecodeTree(br, limit); tree_code = DecodeCode(br, NumLeaves(tree));
+    std::vector<DTreeNode> nodes(tree.size()); uint32_t uses_wp = 0;
+    for (size_t i = 0; i < tree.size(); i++) { const TreeNode& n = tree[i];
+      if (n.property >= 0) { nodes[i] = make_int4(n.property, n.splitval, n.lchild, n.rchild); if (n.property == 15) uses_wp = 1; JXLG_CHECK(n.property < 16, "MA-tree properties of previous channels are not supported by the GPU decoder yet"); }
+      else { nodes[i] = make_int4(-1, (n.leaf_id << 4) | n.predictor, n.offset, int(n.multiplier)); if (n.predictor == 6) uses_wp = 1; } }
+    h.tree_off = blob.Add(nodes.data(), nodes.size() * sizeof(DTreeNode)); h.tree_size = uint32_t(nodes.size()); h.uses_wp = uses_wp; h.mod_code = blob.AddCode(tree_code);
+  }
+  h.has_tree = has_tree;
+  // global Modular image: colour channels (Modular frames) + extra channels
+  std::vector<DModChannel> ch;
+  if (fh.encoding == 1) { JXLG_CHECK(!m.xyb_encoded, "XYB-encoded Modular frames are not supported"); int nc = m.ce.color_space == kCsGray ? 1 : 3; for (int c = 0; c < nc; c++) ch.push_back(DModChannel{fh.xsize, fh.ysize, 0, 0, 0}); }
+  for (size_t i = 0; i < m.ec.size(); i++) { JXLG_CHECK(fh.ec_upsampling[i] == 1, "upsampling is not supported"); uint32_t s = m.ec[i].dim_shift; ch.push_back(DModChannel{DivCeil(fh.xsize, 1u << s), DivCeil(fh.ysize, 1u << s), s, s, 0}); }
+  JXLG_CHECK(ch.size() <= 8, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size()); h.num_rct = 0; h.first_group_channel = 0; global_has_data = false;
+  uint64_t off = 0; for (auto& c : ch) { c.plane_off = off; off += uint64_t(c.w) * c.h; } for (size_t i = 0; i < ch.size(); i++) h.mod_ch[i] = ch[i];
+  h.mod_bitdepth = m.bd.bits;
+  if (!ch.empty()) {
+    gheader = ReadGroupHeader(br);
+    for (const Transform& t : gheader.transforms) { JXLG_CHECK(t.id == 0, "palette / squeeze transforms are not supported by the GPU decoder yet"); JXLG_CHECK(t.begin_c + 3 <= ch.size() && h.num_rct < 4, "RCT channel range");
+      JXLG_CHECK(ch[t.begin_c].w == ch[t.begin_c + 1].w && ch[t.begin_c].w == ch[t.begin_c + 2].w && ch[t.begin_c].h == ch[t.begin_c + 1].h && ch[t.begin_c].h == ch[t.begin_c + 2].h, "RCT channel sizes");
+      h.rct_begin[h.num_rct] = t.begin_c; h.rct_type[h.num_rct] = t.rct_type; h.num_rct++; }
+    size_t c = 0; for (; c < ch.size(); c++) if (ch[c].w > fh.group_dim || ch[c].h > fh.group_dim) break;
+    global_decoded = c; h.first_group_channel = uint32_t(c);
+    size_t nonempty = 0; for (size_t i = 0; i < c; i++) if (ch[i].w && ch[i].h) nonempty++;
+    if (nonempty) { JXLG_CHECK(gheader.use_global_tree && has_tree, "local MA trees are not supported by the GPU decoder yet"); global_has_data = true; }
+  }
+}
+
+void DecodeJob::ParseHfGlobal(BitReader& br) {
+  bool all_default = br.Bool();
+  for (int t = 0; t < kNumQuantTables; t++) { if (all_default) { const std::vector<float>& d = DefaultDequant(t); h.dq_off[t] = blob.Add(d.data(), d.size() * 4); } else { std::vector<float> d = ComputeDequantTable(t, ReadQuantEncodingHost(br, t)); h.dq_off[t] = blob.Add(d.data(), d.size() * 4); } }
+  h.num_hf_presets = 1 + br.ReadBits(CeilLog2(fh.num_groups));
+  uint32_t nat_off[kNumOrders]; for (int o = 0; o < kNumOrders; o++) { const auto& n = NaturalOrderCached(o); nat_off[o] = blob.Add(n.data(), n.size() * 4); }
+  ac_codes.resize(fh.passes.num_passes);
+  for (uint32_t p = 0; p < fh.passes.num_passes; p++) {
+    uint32_t used = br.U32(Val(0x5F), Val(0x13), Val(0), Bits(13)); for (int i = 0; i < kNumOrders * 3; i++) h.order_off[p][i] = nat_off[i / 3];
+    if (used) { Code c = DecodeCode(br, 8); SymbolReader r(&c, &br);
+      for (int o = 0; o < kNumOrders; o++) if (used >> o & 1) for (int chn = 0; chn < 3; chn++) { const auto& nat = NaturalOrderCached(o); size_t size = nat.size(); std::vector<uint32_t> perm = ReadPermutation(r, size / 64, size), out(size);
+        for (size_t k = 0; k < size; k++) out[k] = nat[perm[k]]; h.order_off[p][o * 3 + chn] = blob.Add(out.data(), out.size() * 4); }
+      JXLG_CHECK(r.CheckFinal(), "coefficient order ANS final state"); }
+    ac_codes[p] = DecodeCode(br, size_t(495) * h.num_hf_presets * h.nb_block_ctx); h.ac_code[p] = blob.AddCode(ac_codes[p]);
+  }
+}
+
+void DecodeJob::Setup(const DecodeRequest& req) {
+  const ImageMetadata& m = hd.meta; const std::vector<uint8_t>& cs = hd.ci.codestream; size_t pos = hd.frame_pos;
+  if (m.have_preview) { ImageMetadata pm = m; pm.xsize = m.preview_x; pm.ysize = m.preview_y; BitReader br(cs.data() + pos, cs.size() - pos); FrameHeader pf = ReadFrameHeader(br, pm); Toc t = ReadToc(br, pf); pos += br.pos / 8 + t.total; JXLG_CHECK(pos <= cs.size(), "preview frame truncated"); }
+  BitReader br(cs.data() + pos, cs.size() - pos); fh = ReadFrameHeader(br, m);
+  JXLG_CHECK(fh.frame_type == kFrameRegular || fh.frame_type == kFrameSkipProgressive, "reference-only / LF frames are not supported");
+  JXLG_CHECK(fh.upsampling == 1, "upsampling is not supported"); JXLG_CHECK(!fh.do_ycbcr, "YCbCr (JPEG-recompressed) frames are not supported");
+  JXLG_CHECK(!fh.have_crop || (fh.x0 == 0 && fh.y0 == 0 && fh.width == m.xsize && fh.height == m.ysize), "cropped frames are not supported");
+  JXLG_CHECK(fh.passes.num_passes <= uint32_t(kMaxPasses), "too many passes");
+  toc = ReadToc(br, fh); frame_off = pos + br.pos / 8; JXLG_CHECK(frame_off + toc.total <= cs.size(), "JxlDecoderProcessInput needs more input, but it already received the entire image.");
+  info.frame_name = fh.name; info.bpp = double(cs.size()) * 8.0 / (double(m.xsize) * m.ysize);
+  memset(&h, 0, sizeof(h)); bgra = req.bgra; device_output = req.device_output;
+  h.xsize = fh.xsize; h.ysize = fh.ysize; h.xb = fh.xblocks; h.yb = fh.yblocks; h.xpad = h.xb * 8; h.ypad = h.yb * 8; h.xt = (h.xb + 7) / 8; h.yt = (h.yb + 7) / 8; h.xgroups = fh.xgroups; h.ygroups = fh.ygroups; h.num_groups = fh.num_groups;
+  h.xlfgroups = fh.xlfgroups; h.ylfgroups = fh.ylfgroups; h.num_lf_groups = fh.num_lf_groups; h.group_dim = fh.group_dim; h.num_passes = fh.passes.num_passes; h.encoding = fh.encoding; h.flags = uint32_t(fh.flags);
+  for (uint32_t p = 0; p < h.num_passes; p++) { h.pass_shift[p] = p + 1 < h.num_passes ? fh.passes.shift[p] : 0;
+    int min_shift = 3, max_shift = 2; for (uint32_t i = 0;; i++) { for (uint32_t j = 0; j < fh.passes.num_ds; j++) if (i == fh.passes.last_pass[j]) min_shift = FloorLog2(fh.passes.downsample[j]); if (i + 1 == h.num_passes) min_shift = 0; if (i == p) break; max_shift = min_shift - 1; }
+    h.pass_min_shift[p] = min_shift; h.pass_max_shift[p] = max_shift; }
+  const LoopFilter& l = fh.lf; h.lpf.gab = l.gab; h.lpf.epf_iters = l.epf_iters; memcpy(h.lpf.gab_w, l.gab_w, sizeof(l.gab_w)); memcpy(h.lpf.epf_sharp_lut, l.epf_sharp_lut, sizeof(l.epf_sharp_lut)); memcpy(h.lpf.epf_channel_scale, l.epf_channel_scale, sizeof(l.epf_channel_scale));
+  h.lpf.epf_quant_mul = l.epf_quant_mul; h.lpf.pass0_sigma_scale = l.epf_pass0_sigma_scale; h.lpf.pass2_sigma_scale = l.epf_pass2_sigma_scale; h.lpf.border_sad_mul = l.epf_border_sad_mul; h.lpf.sigma_for_modular = l.epf_sigma_for_modular;
+  if (fh.encoding == 1) JXLG_CHECK(!l.gab && !l.epf_iters, "restoration filters on Modular frames are not supported by the GPU decoder yet");
+  // colour
+  DColor& c = h.color; memcpy(c.opsin_inv, m.opsin.inv, sizeof(c.opsin_inv)); for (int i = 0; i < 3; i++) { c.opsin_bias[i] = m.opsin.bias[i]; c.opsin_bias_cbrt[i] = std::cbrt(m.opsin.bias[i]); }
+  c.itscale = 255.0f / m.tm.intensity_target; c.intensity_target = m.tm.intensity_target; c.xyb_encoded = m.xyb_encoded; c.num_color = m.ce.color_space == kCsGray && !m.xyb_encoded ? 1 : 3; if (fh.encoding == 1) c.num_color = m.ce.color_space == kCsGray ? 1 : 3;
+  ColorEncoding oe = OutputEncoding(m); c.tf = oe.have_gamma ? 0 : oe.tf; c.gamma = oe.have_gamma ? float(oe.gamma) * 1e-7f : 1.0f;
+  { // linear sRGB -> target primaries
+    for (int i = 0; i < 9; i++) c.to_target[i] = (i % 4 == 0) ? 1.f : 0.f;
+    if (!(oe.primaries == kPrSRGB && oe.white_point == kWpD65) && oe.color_space == kCsRGB) {
+      auto prim = [](const ColorEncoding& ce, double p[3][2], double w[2]) {
+        switch (ce.white_point) { case kWpD65: w[0] = 0.3127; w[1] = 0.3290; break; case kWpE: w[0] = w[1] = 1.0 / 3; break; case kWpDCI: w[0] = 0.314; w[1] = 0.351; break; default: w[0] = ce.white_xy[0] * 1e-6; w[1] = ce.white_xy[1] * 1e-6; }
+        static const double srgb[3][2] = {{0.639998686, 0.330010138}, {0.300003784, 0.600003357}, {0.150002046, 0.059997204}}, bt2100[3][2] = {{0.708, 0.292}, {0.170, 0.797}, {0.131, 0.046}}, p3[3][2] = {{0.680, 0.320}, {0.265, 0.690}, {0.150, 0.060}};
+        const double (*src)[2] = ce.primaries == kPr2100 ? bt2100 : ce.primaries == kPrP3 ? p3 : srgb; for (int i = 0; i < 3; i++) for (int k = 0; k < 2; k++) p[i][k] = ce.primaries == kPrCustom ? ce.prim_xy[i][k] * 1e-6 : src[i][k]; };
+      auto inv3 = [](const double mm[9], double o[9]) { double det = mm[0] * (mm[4] * mm[8] - mm[5] * mm[7]) - mm[1] * (mm[3] * mm[8] - mm[5] * mm[6]) + mm[2] * (mm[3] * mm[7] - mm[4] * mm[6]); JXLG_CHECK(std::fabs(det) > 1e-12, "singular colour matrix"); double id = 1 / det;
+        o[0] = (mm[4] * mm[8] - mm[5] * mm[7]) * id; o[1] = (mm[2] * mm[7] - mm[1] * mm[8]) * id; o[2] = (mm[1] * mm[5] - mm[2] * mm[4]) * id; o[3] = (mm[5] * mm[6] - mm[3] * mm[8]) * id; o[4] = (mm[0] * mm[8] - mm[2] * mm[6]) * id; o[5] = (mm[2] * mm[3] - mm[0] * mm[5]) * id;
+        o[6] = (mm[3] * mm[7] - mm[4] * mm[6]) * id; o[7] = (mm[1] * mm[6] - mm[0] * mm[7]) * id; o[8] = (mm[0] * mm[4] - mm[1] * mm[3]) * id; };
+      auto rgb2xyz = [&](const double p[3][2], const double w[2], double mm[9]) { double P[9]; for (int i = 0; i < 3; i++) { P[i] = p[i][0] / p[i][1]; P[3 + i] = 1.0; P[6 + i] = (1 - p[i][0] - p[i][1]) / p[i][1]; } double W[3] = {w[0] / w[1], 1.0, (1 - w[0] - w[1]) / w[1]}, Pi[9]; inv3(P, Pi);
+        double S[3]; for (int i = 0; i < 3; i++) S[i] = Pi[3 * i] * W[0] + Pi[3 * i + 1] * W[1] + Pi[3 * i + 2] * W[2]; for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) mm[3 * r + cc] = P[3 * r + cc] * S[cc]; };
+      ColorEncoding s; double ps[3][2], ws[2], pt[3][2], wt[2], A[9], B[9], Bi[9]; prim(s, ps, ws); prim(oe, pt, wt); rgb2xyz(ps, ws, A); rgb2xyz(pt, wt, B); inv3(B, Bi);
+      for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) { double v = 0; for (int k = 0; k < 3; k++) v += Bi[3 * r + k] * A[3 * k + cc]; c.to_target[3 * r + cc] = float(v); }
+    }
+  }
+  // output description
+  DOutput& o = h.out; o.sample_type = uint32_t(info.sample_type); o.num_channels = uint32_t(info.num_channels); o.color_channels = uint32_t(m.num_color_channels()); o.orientation = m.orientation; o.bgra = bgra ? 1 : 0;
+  o.out_w = m.orientation >= 5 ? fh.ysize : fh.xsize; o.out_h = m.orientation >= 5 ? fh.xsize : fh.ysize; o.bits = m.bd.bits; o.exp_bits = m.bd.exp_bits;
+  size_t ec_base = fh.encoding == 1 ? (m.ce.color_space == kCsGray ? 1 : 3) : 0; int alpha = info.has_alpha ? m.alpha_index() : -1, black = m.black_index();
+  o.alpha_plane = alpha >= 0 ? int32_t(ec_base + alpha) : -1; o.black_plane = info.format == 2 ? int32_t(ec_base + black) : -1; o.premultiplied = alpha >= 0 && m.ec[alpha].alpha_associated;
+  if (alpha >= 0) { o.alpha_bits = m.ec[alpha].bd.bits; o.alpha_exp_bits = m.ec[alpha].bd.exp_bits; } if (black >= 0) o.black_bits = m.ec[black].bd.bits;
+  if (bgra) JXLG_CHECK(info.format != 2, "BGRA surface output is not defined for CMYK images");
+  for (size_t i = 0; i < m.ec.size(); i++) JXLG_CHECK(m.ec[i].dim_shift < 3, "extra channels with dim_shift >= 3 (Modular LF-group data) are not supported by the GPU decoder yet");
+}
+
+void DecodeJob::UploadFrame() { CUDA_OK(cudaMemcpyAsync(d_frame.p, &h, sizeof(DFrame), cudaMemcpyHostToDevice, stream)); }
+
+void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
+  const std::vector<uint8_t>& cs = hd.ci.codestream; comp_size = cs.size();
+  size_t cells = size_t(h.xb) * h.yb, px = size_t(h.xpad) * h.ypad, tiles = size_t(h.xt) * h.yt; bool vardct = h.encoding == 0;
+  d_frame.Alloc(sizeof(DFrame)); d_err.Alloc(64); h_err.Alloc(64, true);
+  d_comp.Alloc(comp_size + 64);
+  if (vardct) {
+    d_lfq.Alloc(cells * 3 * 4); d_lf.Alloc(cells * 3 * 4); d_lf_tmp.Alloc(cells * 3 * 4); d_acs.Alloc(cells); d_qf.Alloc(cells); d_sharp.Alloc(cells); d_lfidx.Alloc(cells); d_ytox.Alloc(tiles); d_ytob.Alloc(tiles);
+    d_hfmeta.Alloc((size_t(h.num_lf_groups) * kHfMetaScratchInts + h.num_lf_groups) * 4); d_coeffs.Alloc(size_t(h.num_groups) * 3 * 65536 * 2); d_xyb.Alloc(px * 3 * 4); d_xyb_tmp.Alloc(px * 3 * 4); d_sigma.Alloc(cells * 4);
+  }
+  uint64_t mod_ints = 0; for (uint32_t i = 0; i < h.num_mod_channels; i++) mod_ints += uint64_t(h.mod_ch[i].w) * h.mod_ch[i].h; if (mod_ints) d_mod.Alloc(mod_ints * 4);
+  if (h.uses_wp) d_wp.Alloc((size_t(h.num_lf_groups) + h.num_groups + 1) * 5 * 2 * (kMaxWpWidth + 2) * 4); else d_wp.Alloc(16);
+  const DOutput& o = h.out; size_t bps = o.sample_type == 0 ? 1 : o.sample_type == 3 ? 4 : 2; size_t chans = bgra ? 4 : (o.num_channels + (o.black_plane >= 0 ? 1 : 0)); if (bgra) bps = 1;
+  out_bytes = size_t(o.out_w) * o.out_h * chans * bps; d_out.Alloc(out_bytes); if (!device_output) h_out.Alloc(out_bytes, true);
+  h.comp = d_comp.as<uint8_t>(); h.lfq = d_lfq.as<int32_t>(); h.lf = d_lf.as<float>(); h.lf_tmp = d_lf_tmp.as<float>(); h.acs = d_acs.as<uint8_t>(); h.hf_mul_m1 = d_qf.as<uint8_t>(); h.sharp = d_sharp.as<uint8_t>(); h.lf_idx = d_lfidx.as<uint8_t>();
+  h.ytox = d_ytox.as<int8_t>(); h.ytob = d_ytob.as<int8_t>(); h.hfmeta_scratch = d_hfmeta.as<int32_t>(); h.coeffs = d_coeffs.as<int16_t>(); h.xyb = d_xyb.as<float>(); h.xyb_tmp = d_xyb_tmp.as<float>(); h.inv_sigma = d_sigma.as<float>();
+  h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
+  bool smooth = vardct && !(h.flags & kFlagSkipAdaptiveLfSmoothing) && h.xb > 2 && h.yb > 2; h.lf_src = smooth ? h.lf_tmp : h.lf;
+  CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream));
+  if (req.device_input) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input, comp_size, cudaMemcpyDeviceToDevice, stream)); else CUDA_OK(cudaMemcpyAsync(d_comp.p, cs.data(), comp_size, cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaMemsetAsync(d_comp.as<uint8_t>() + comp_size, 0, 64, stream));
+}
+
+static const char* DevErrorText(uint32_t e) {
+  switch (e) { case kErrOverrun: return "section truncated (read past its end)"; case kErrAnsFinal: return "ANS final state mismatch"; case kErrBadStrategy: return "invalid or unsupported (AFV) AC strategy"; case kErrBlockBounds: return "AC strategy block out of bounds";
+    case kErrTooManyNz: return "too many non-zero coefficients"; case kErrNzMismatch: return "non-zero count mismatch"; case kErrUnsupportedStream: return "unsupported Modular stream geometry"; case kErrCoefRange: return "coefficient exceeds 16 bits";
+    case kErrHfMeta: return "HF metadata inconsistent"; case kErrLocalTree: return "local MA trees are not supported by the GPU decoder yet"; case kErrGroupTransform: return "per-group Modular transforms are not supported by the GPU decoder yet";
+    case kErrHybrid: return "hybrid integer too large"; case kErrPrefix: return "invalid prefix code"; case kErrCflRange: return "CfL factor out of range"; case kErrSharpness: return "EPF sharpness out of range"; case kErrPreset: return "invalid HF preset"; case kErrRefProps: return "unsupported MA-tree property";
+    default: return "device decode error"; }
+}
+
+void DecodeJob::Run(const DecodeRequest& req) {
+  const std::vector<uint8_t>& cs = hd.ci.codestream; const bool vardct = h.encoding == 0; const size_t nsec = toc.size.size(); const bool single = nsec == 1;
+  const size_t nlog = size_t(h.num_passes) * h.num_groups + h.num_lf_groups + 2;
+  // host parse: LfGlobal (+ HfGlobal when it has its own section)
+  BitReader lfg(cs.data() + frame_off + toc.offset[0], toc.size[0]); ParseLfGlobal(lfg); JXLG_CHECK(!lfg.overrun, "LfGlobal truncated");
+  uint64_t base_bits = uint64_t(frame_off) * 8; uint64_t after_lfglobal = (uint64_t(frame_off) + toc.offset[0]) * 8 + lfg.pos;
+  if (!single && vardct) { BitReader hb(cs.data() + frame_off + toc.offset[1 + h.num_lf_groups], toc.size[1 + h.num_lf_groups]); ParseHfGlobal(hb); JXLG_CHECK(!hb.overrun, "HfGlobal truncated"); }
+  std::vector<uint64_t> sec(2 * nlog + 2, 0);
+  for (size_t i = 0; i < nlog; i++) { size_t t = single ? 0 : i; sec[i] = base_bits + uint64_t(toc.offset[t]) * 8; sec[nlog + i] = base_bits + uint64_t(toc.offset[t] + toc.size[t]) * 8; }
+  h.sec_off = blob.Add(sec.data(), sec.size() * 8);
+  AllocateAndUpload(req);
+  auto upload_blob = [&]() { if (d_blob.n < blob.b.size() + 16) d_blob.Alloc(std::max<size_t>(blob.b.size() * 2, 1 << 16)); h.blob = d_blob.as<uint8_t>(); CUDA_OK(cudaMemcpyAsync(d_blob.p, blob.b.data(), blob.b.size(), cudaMemcpyHostToDevice, stream)); UploadFrame(); };
+  upload_blob();
+  const DFrame* d = d_frame.as<DFrame>();
+  if (timed) cudaEventRecord(ev[0], stream);
+  // global Modular stream
+  if (global_has_data) { LaunchModularGlobal(d, after_lfglobal, uint32_t(global_decoded), stream); CountLaunch(); }
+  else if (single) CUDA_OK(cudaMemcpyAsync(h.end_bitpos, &after_lfglobal, 8, cudaMemcpyHostToDevice, stream));
+  if (vardct) { LaunchLfGroups(d, h, stream); CountLaunch(); }
+  else if (single) { /* Modular frame, single section: LF group and HfGlobal parts are empty; groups continue where the global stream ended */ CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, h.end_bitpos, 8, cudaMemcpyDeviceToDevice, stream)); }
+  if (single && vardct) {   // HfGlobal follows the LF group in the same bit stream: need its end position on the host
+    uint64_t pos[3] = {0, 0, 0}; CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    uint32_t e = *h_err.as<uint32_t>(); JXLG_CHECK(e == 0, DevErrorText(e)); memcpy(pos, h_err.as<uint8_t>() + 16, 24);
+    size_t byte = size_t(pos[1] / 8); JXLG_CHECK(byte <= cs.size(), "LF group ran past the end of the file");
+    BitReader hb(cs.data(), cs.size()); hb.pos = size_t(pos[1]); ParseHfGlobal(hb); JXLG_CHECK(!hb.overrun, "HfGlobal truncated"); uint64_t after = hb.pos;
+    upload_blob(); CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, &after, 8, cudaMemcpyHostToDevice, stream));
+  }
+  if (timed) cudaEventRecord(ev[1], stream);
+  if (vardct) { bool smooth = h.lf_src == h.lf_tmp; LaunchLfDequant(d, h, smooth, stream); CountLaunch(smooth ? 2 : 1); }
+  for (uint32_t p = 0; p < h.num_passes; p++) { LaunchAcGroups(d, h, int(p), stream); CountLaunch(); }
+  if (timed) cudaEventRecord(ev[2], stream);
+  if (vardct) LaunchReconstruct(d, h, stream);
+  if (timed) cudaEventRecord(ev[3], stream);
+  if (vardct) LaunchFilters(d, h, stream);
+  if (h.num_rct) LaunchInverseRct(d, h, stream);
+  if (timed) cudaEventRecord(ev[4], stream);
+  LaunchOutput(d, h, stream);
+  if (timed) cudaEventRecord(ev[5], stream);
+  if (!device_output) CUDA_OK(cudaMemcpyAsync(h_out.p, d_out.p, out_bytes, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream));
+  if (timed) cudaEventRecord(ev[6], stream);
+}
+
+std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res) {
+  std::shared_ptr<DecodeJob> job;
+  if (!req.data) { res->status = Status::NullParameter; return job; }
+  try {
+    std::string why; if (!CudaAvailable(&why)) { res->status = Status::DecodeError; res->message = why; return job; }
+    job = std::make_shared<DecodeJob>(); job->stream = stream;
+    res->status = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res->message); if (res->status != Status::Ok) { job.reset(); return job; }
+    job->Setup(req); job->Run(req); res->info = job->info;
+  } catch (const std::bad_alloc&) { res->status = Status::OutOfMemory; job.reset(); }
+  catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); if (job) res->info = job->info; job.reset(); }
+  return job;
+}
+
+void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res) {
+  if (!job) return;
+  cudaError_t e = cudaStreamSynchronize(job->stream);
+  if (e != cudaSuccess) { res->status = Status::DecodeError; res->message = std::string("CUDA: ") + cudaGetErrorString(e); return; }
+  uint32_t de = *job->h_err.as<uint32_t>();
+  if (de) { res->status = Status::DecodeError; res->message = DevErrorText(de); return; }
+  res->info = job->info; res->pixels = job->device_output ? job->d_out.as<uint8_t>() : job->h_out.as<uint8_t>(); res->pixel_bytes = job->out_bytes; res->out_width = job->h.out.out_w; res->out_height = job->h.out.out_h; res->job = job;
+  if (job->timed) { auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, job->ev[a], job->ev[b]); return t; };
+    res->times.lf = ms(0, 1); res->times.ac = ms(1, 2); res->times.recon = ms(2, 3); res->times.filters = ms(3, 4); res->times.output = ms(4, 5); res->times.d2h = ms(5, 6); res->times.total = ms(0, 6); }
+}
+
+DecodeResult DecodeOnGpu(const DecodeRequest& req) {
+  DecodeResult res; cudaStream_t st = nullptr;
+  std::string why; if (!req.data) { res.status = Status::NullParameter; return res; }
+  if (SignatureCheck(req.data, req.size) == 0) { res.status = Status::InvalidFileSignature; return res; }
+  if (!CudaAvailable(&why)) { res.status = Status::DecodeError; res.message = why; return res; }
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { res.status = Status::DecodeError; res.message = "cudaStreamCreate failed"; return res; }
+  {
+    std::shared_ptr<DecodeJob> job;
+    // timing events are cheap; always record so callers can read stage times
+    DecodeRequest r2 = req; (void)r2;
+    job = std::shared_ptr<DecodeJob>(); DecodeResult tmp;
+    // enqueue with stage timing enabled
+    struct Timed { static void Enable(DecodeJob* j) { j->timed = true; for (int i = 0; i < 7; i++) cudaEventCreate(&j->ev[i]); } };
+    try {
+      job = std::make_shared<DecodeJob>(); job->stream = st; Timed::Enable(job.get());
+      res.status = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res.message);
+      if (res.status == Status::Ok) { job->Setup(req); job->Run(req); DecodeFinish(job, &res); }
+    } catch (const std::bad_alloc&) { res.status = Status::OutOfMemory; }
+    catch (const std::exception& e) { res.status = Status::DecodeError; res.message = e.what(); if (job) res.info = job->info; }
+    if (res.status != Status::Ok) cudaStreamSynchronize(st);
+  }
+  // the stream must outlive the job's pending work; everything was synchronised above
+  cudaStreamDestroy(st);
+  return res;
+}
+
+bool DecodeDebugPlanes(const std::shared_ptr<DecodeJob>& job, int which, std::vector<float>* out, int* xpad, int* ypad) {
+  if (!job || job->h.encoding != 0) return false; size_t px = size_t(job->h.xpad) * job->h.ypad; *xpad = int(job->h.xpad); *ypad = int(job->h.ypad);
+  const float* src = nullptr; size_t n = px * 3;
+  if (which == 0) src = job->h.xyb; else if (which == 1) src = job->h.xyb_tmp; else if (which == 3) { src = job->h.lf_src; n = size_t(job->h.xb) * job->h.yb * 3; } else return false;
+  out->resize(n); return cudaMemcpy(out->data(), src, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+bool DecodeDebugCoeffs(const std::shared_ptr<DecodeJob>& job, std::vector<int16_t>* out) {
+  if (!job || job->h.encoding != 0) return false; size_t n = size_t(job->h.num_groups) * 3 * 65536; out->resize(n); return cudaMemcpy(out->data(), job->h.coeffs, n * 2, cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+
+}  // namespace jxlgpu

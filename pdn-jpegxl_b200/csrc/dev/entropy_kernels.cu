@@ -1,0 +1,222 @@
+// pdn-jpegxl_b200 engine — entropy-decoding kernels (sm_100a).
+//   k_lf_group : one CTA per LF group (2048x2048 px): LF coefficients (Modular, 3 channels at 1/8 res),
+//                HF metadata (CfL maps, block strategies + hf multipliers, EPF sharpness), varblock placement.
+//   k_ac_group : one CTA per 256x256 AC group and pass: zero-fill + ANS/prefix coefficient decode with the
+//                context model of SURVEY.md A.8 "PassGroup AC decode", then the group's Modular channels
+//                (alpha / lossless colour).
+// A section is a serial bit stream (per-symbol adaptive contexts), so one thread is productive per CTA; the
+// other lanes zero-fill, stage tables and post-process. Throughput comes from the number of sections in
+// flight (192 AC groups for 12 MP, x batch). Replaces libjxl's DecodeGroup / ModularFrameDecoder work reached
+// from N/Decoder/JxlDecoder.cpp:252.
+#include "frame.cuh"
+#include "kernels.h"
+
+namespace jxlgpu {
+
+__device__ __constant__ uint8_t kFreqCtx[64] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 15, 16, 16, 17, 17, 18, 18, 19, 19, 20, 20, 21, 21, 22, 22,
+  23, 23, 23, 23, 24, 24, 24, 24, 25, 25, 25, 25, 26, 26, 26, 26, 27, 27, 27, 27, 28, 28, 28, 28, 29, 29, 29, 29, 30, 30, 30, 30};
+__device__ __constant__ uint8_t kNumNzCtx[64] = {0, 0, 31, 62, 62, 93, 93, 93, 93, 123, 123, 123, 123, 152, 152, 152, 152, 152, 152, 152, 152, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180,
+  206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
+
+// Parses a Modular GroupHeader (A.7 "Sub-bitstream header"). Streams that need host-side parsing
+// (local MA trees, per-group transforms) are reported as unsupported instead of being mis-decoded.
+__device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f) {
+  BitRd& br = md.rd.br;
+  bool use_global = br.Read(1);
+  if (!br.Read(1)) { md.wp.p1 = br.Read(5); md.wp.p2 = br.Read(5); md.wp.p3a = br.Read(5); md.wp.p3b = br.Read(5); md.wp.p3c = br.Read(5); md.wp.p3d = br.Read(5); md.wp.p3e = br.Read(5); for (int i = 0; i < 4; i++) md.wp.w[i] = br.Read(4); }
+  else { md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12; }
+  uint32_t nt = br.ReadU32(0, 0, 0, 1, 4, 2, 8, 18);
+  if (!use_global || !f.has_tree) { md.rd.err = kErrLocalTree; return false; }
+  if (nt != 0) { md.rd.err = kErrGroupTransform; return false; }
+  return true;
+}
+
+__device__ void BindModDecoder(ModDecoder& md, const DFrame& f) {
+  md.cv.Bind(f.blob, f.mod_code); md.tree = reinterpret_cast<const DTreeNode*>(f.blob + f.tree_off); md.uses_wp = f.uses_wp != 0; md.rd.err = 0;
+}
+
+__global__ void __launch_bounds__(32) k_lf_group(const DFrame* fp) {
+  const DFrame& f = *fp; const int g = blockIdx.x, lane = threadIdx.x;
+  const int gx = g % int(f.xlfgroups), gy = g / int(f.xlfgroups), cx0 = gx * 256, cy0 = gy * 256;
+  const int w = min(256, int(f.xb) - cx0), h = min(256, int(f.yb) - cy0), tw = (w + 7) / 8, th = (h + 7) / 8;
+  int32_t* scratch = f.hfmeta_scratch + size_t(g) * kHfMetaScratchInts;
+  int32_t* s_cflx = scratch; int32_t* s_cflb = scratch + 1024; int32_t* s_info = scratch + 2048; int32_t* s_sharp = scratch + 2048 + 2 * 65536;
+  __shared__ uint32_t sh_nb, sh_ok;
+  if (lane == 0) {
+    sh_ok = 0; sh_nb = 0;
+    ModDecoder md; BindModDecoder(md, f);
+    const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
+    uint64_t start = single ? f.end_bitpos[0] : sec[1 + g]; uint64_t end = single ? sec[nsec] : sec[nsec + 1 + g];
+    md.rd.br.Init(f.comp, start);
+    int32_t* wp = f.wp_scratch + size_t(g) * WPScratchInts(kMaxWpWidth);
+    uint32_t extra_prec = md.rd.br.Read(2);
+    f.hfmeta_scratch[size_t(f.num_lf_groups) * kHfMetaScratchInts + g] = int32_t(extra_prec);
+    bool ok = ReadGroupHeaderDev(md, f);
+    if (ok) {
+      md.rd.Init(md.cv); const int sid = 1 + g; size_t plane = size_t(f.xb) * f.yb;
+      const int dst[3] = {1, 0, 2};   // stream channel order is Y, X, B (A.8 LfGroup)
+      for (int c = 0; c < 3; c++) md.DecodeChannel(c, sid, f.lfq + dst[c] * plane + size_t(cy0) * f.xb + cx0, f.xb, w, h, wp);
+      if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
+    }
+    // (Modular LF-group channels — extra channels with dim_shift >= 3 — are rejected on the host.)
+    if (ok && !md.rd.err) {
+      uint32_t nb = md.rd.br.Read(CeilLog2Dev(uint32_t(w * h))) + 1; sh_nb = nb;
+      ok = ReadGroupHeaderDev(md, f);
+      if (ok) {
+        md.rd.Init(md.cv); const int sid = 1 + 2 * int(f.num_lf_groups) + g;
+        md.DecodeChannel(0, sid, s_cflx, tw, tw, th, wp); md.DecodeChannel(1, sid, s_cflb, tw, tw, th, wp);
+        if (nb <= 65536u) { md.DecodeChannel(2, sid, s_info, nb, int(nb), 2, wp); md.DecodeChannel(3, sid, s_sharp, w, w, h, wp); } else md.rd.err = kErrHfMeta;
+        if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
+      }
+    }
+    uint64_t pos = md.rd.br.BitPos(); if (pos > end) md.rd.err = md.rd.err ? md.rd.err : kErrOverrun;
+    if (single) f.end_bitpos[1] = pos;
+    SetError(f.err, md.rd.err); sh_ok = (ok && !md.rd.err) ? 1 : 0;
+  }
+  __syncwarp();
+  if (!sh_ok) return;
+  // ---- parallel post-processing: CfL maps, sharpness, clear block map
+  uint32_t bad = 0;
+  for (int i = lane; i < tw * th; i += 32) { int y = i / tw, x = i % tw; int32_t a = s_cflx[i], b = s_cflb[i]; if (a < -128 || a > 127 || b < -128 || b > 127) bad = kErrCflRange;
+    size_t o = size_t(cy0 / 8 + y) * f.xt + cx0 / 8 + x; f.ytox[o] = int8_t(a); f.ytob[o] = int8_t(b); }
+  for (int i = lane; i < w * h; i += 32) { int y = i / w, x = i % w; int32_t v = s_sharp[i]; if (v < 0 || v > 7) bad = kErrSharpness; size_t o = size_t(cy0 + y) * f.xb + cx0 + x; f.sharp[o] = uint8_t(v); f.acs[o] = 0xFF; }
+  if (bad) SetError(f.err, bad);
+  __syncwarp();
+  // ---- varblock placement: raster scan, each block at the first uncovered cell (A.8 LfGroup)
+  if (lane == 0) {
+    uint32_t nb = sh_nb, num = 0, e = 0;
+    for (int y = 0; y < h && !e; y++) for (int x = 0; x < w; x++) {
+      size_t o = size_t(cy0 + y) * f.xb + cx0 + x; if (f.acs[o] != 0xFF) continue;
+      if (num >= nb) { e = kErrHfMeta; break; }
+      int32_t s = s_info[num]; if (s < 0 || s >= 27) { e = kErrBadStrategy; break; }
+      int bw = CoveredX(s), bh = CoveredY(s);
+      if (x + bw > w || y + bh > h || (x & 31) + bw > 32 || (y & 31) + bh > 32) { e = kErrBlockBounds; break; }
+      int32_t qf = max(0, min(255, s_info[nb + num]));
+      for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { size_t p = o + size_t(iy) * f.xb + ix; if (f.acs[p] != 0xFF) e = kErrBlockBounds; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = uint8_t(qf); }
+      f.acs[o] = uint8_t(s | 0x80); num++;
+    }
+    SetError(f.err, e);
+  }
+}
+
+// LF dequantisation + chroma-from-luma + block-context LF index (A.8 "Dequant", BlockCtxMap)
+__global__ void k_lf_dequant(const DFrame* fp) {
+  const DFrame& f = *fp; size_t plane = size_t(f.xb) * f.yb; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= plane) return;
+  int y = int(i / f.xb), x = int(i % f.xb); int g = (y / 256) * int(f.xlfgroups) + x / 256;
+  float mul = 1.0f / float(1u << uint32_t(f.hfmeta_scratch[size_t(f.num_lf_groups) * kHfMetaScratchInts + g]));
+  int32_t qx = f.lfq[i], qy = f.lfq[plane + i], qb = f.lfq[2 * plane + i];
+  float Y = float(qy) * (f.lf_fac[1] * mul); f.lf[plane + i] = Y; f.lf[i] = float(qx) * (f.lf_fac[0] * mul) + f.cfl_x_lf * Y; f.lf[2 * plane + i] = float(qb) * (f.lf_fac[2] * mul) + f.cfl_b_lf * Y;
+  uint32_t bx = 0, by = 0, bb = 0;
+  for (uint32_t t = 0; t < f.n_lf_thr[0]; t++) bx += qx > f.lf_thr[0][t]; for (uint32_t t = 0; t < f.n_lf_thr[1]; t++) by += qy > f.lf_thr[1][t]; for (uint32_t t = 0; t < f.n_lf_thr[2]; t++) bb += qb > f.lf_thr[2][t];
+  f.lf_idx[i] = uint8_t((bx * (f.n_lf_thr[2] + 1) + bb) * (f.n_lf_thr[1] + 1) + by);
+}
+
+// Adaptive LF smoothing (A.8): lf -> lf_tmp, 3 channels; borders copied.
+__global__ void k_lf_smooth(const DFrame* fp) {
+  const DFrame& f = *fp; const int w = int(f.xb), h = int(f.yb); size_t plane = size_t(w) * h; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= plane) return;
+  int y = int(i / w), x = int(i % w);
+  if (x == 0 || y == 0 || x == w - 1 || y == h - 1) { for (int c = 0; c < 3; c++) f.lf_tmp[c * plane + i] = f.lf[c * plane + i]; return; }
+  const float kW1 = 0.20345139757231578f, kW2 = 0.0334829185968739f, kW0 = 1.0f - 4.0f * (kW1 + kW2);
+  float sm[3], mc[3], gap = 0.5f;
+  for (int c = 0; c < 3; c++) { const float* p = f.lf + c * plane + i; float corner = p[-w - 1] + p[-w + 1] + p[w - 1] + p[w + 1], edge = p[-w] + p[-1] + p[1] + p[w]; mc[c] = p[0]; sm[c] = mc[c] * kW0 + edge * kW1 + corner * kW2;
+    gap = fmaxf(gap, fabsf((mc[c] - sm[c]) / f.lf_fac[c])); }
+  float factor = fmaxf(0.f, 3.0f - 4.0f * gap);
+  for (int c = 0; c < 3; c++) f.lf_tmp[c * plane + i] = (sm[c] - mc[c]) * factor + mc[c];
+}
+
+// Decodes the group-local Modular channels (extra channels of VarDCT frames, everything of Modular frames).
+__device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, int pass, bool* need_init) {
+  const int gd = int(f.group_dim), gx = g % int(f.xgroups), gy = g / int(f.xgroups), x0 = gx * gd, y0 = gy * gd;
+  int nch = 0;
+  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
+    int rx0 = x0 >> ch.hshift, ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) continue; int rw = min(gd >> ch.hshift, int(ch.w) - rx0), rh = min(gd >> ch.vshift, int(ch.h) - ry0); if (rw > 0 && rh > 0) nch++; }
+  if (nch == 0) return;
+  if (!ReadGroupHeaderDev(md, f)) return;
+  md.rd.Init(md.cv); *need_init = false;
+  const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g; int k = 0;
+  int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth);
+  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
+    int rx0 = x0 >> ch.hshift, ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) continue; int rw = min(gd >> ch.hshift, int(ch.w) - rx0), rh = min(gd >> ch.vshift, int(ch.h) - ry0); if (rw <= 0 || rh <= 0) continue;
+    md.DecodeChannel(k++, sid, f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, ch.w, rw, rh, wp); }
+  if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
+}
+
+__global__ void __launch_bounds__(128) k_ac_group(const DFrame* fp, int pass) {
+  const DFrame& f = *fp; const int g = blockIdx.x, tid = threadIdx.x;
+  const int gx = g % int(f.xgroups), gy = g / int(f.xgroups);
+  __shared__ uint8_t s_nz[3][32 * 32]; __shared__ uint8_t s_acs[32 * 32], s_qf[32 * 32], s_lfidx[32 * 32];
+  const bool vardct = f.encoding == 0; int w = 0, h = 0;
+  if (vardct) {
+    const int cx0 = gx * 32, cy0 = gy * 32; w = min(32, int(f.xb) - cx0); h = min(32, int(f.yb) - cy0);
+    if (pass == 0) { int4* z = reinterpret_cast<int4*>(f.coeffs + size_t(g) * 3 * 65536); int4 zero = make_int4(0, 0, 0, 0); for (int i = tid; i < 3 * 65536 * 2 / 16; i += 128) z[i] = zero; }
+    for (int i = tid; i < 32 * 32; i += 128) { int by = i >> 5, bx = i & 31; s_nz[0][i] = s_nz[1][i] = s_nz[2][i] = 0;
+      if (by < h && bx < w) { size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; s_acs[i] = f.acs[o]; s_qf[i] = f.hf_mul_m1[o]; s_lfidx[i] = f.lf_idx[o]; } else s_acs[i] = 0; }
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
+  const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
+  uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
+  ModDecoder md; BindModDecoder(md, f); md.rd.br.Init(f.comp, start);
+  uint32_t err = 0;
+  if (vardct) {
+    CodeView cv; cv.Bind(f.blob, f.ac_code[pass]); SymReader& rd = md.rd;
+    uint32_t preset = rd.br.Read(CeilLog2Dev(f.num_hf_presets)); if (preset >= f.num_hf_presets) err = kErrPreset;
+    if (!err) {
+      rd.Init(cv);
+      const uint32_t nbctx = f.nb_block_ctx, ctx_offset = 495 * nbctx * preset, shift = f.pass_shift[pass];
+      const uint8_t* bmap = f.blob + f.bctx_map_off; int16_t* coef = f.coeffs + size_t(g) * 3 * 65536;
+      for (int by = 0; by < h && !err; by++) for (int bx = 0; bx < w && !err; bx++) {
+        const int cell = by * 32 + bx; const uint8_t a = s_acs[cell]; if (!(a & 0x80)) continue;
+        const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); const uint32_t covered = uint32_t(bw * bh), log2c = 31 - __clz(covered), size = covered * 64; const int ord = StrategyOrder(s);
+        const uint32_t qf = uint32_t(s_qf[cell]) + 1; uint32_t qf_idx = 0; for (uint32_t t = 0; t < f.n_qf_thr; t++) qf_idx += qf > f.qf_thr[t];
+        for (int ci = 0; ci < 3; ci++) {
+          const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2;
+          uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : s_nz[c][cell - 32]; else if (by == 0) pred = s_nz[c][cell - 1]; else pred = (uint32_t(s_nz[c][cell - 32]) + s_nz[c][cell - 1] + 1) >> 1;
+          uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u; idx = idx * 13 + ord; idx = idx * (f.n_qf_thr + 1) + qf_idx; idx = idx * f.num_lf_ctxs + s_lfidx[cell]; const uint32_t bctx = bmap[idx];
+          uint32_t nzb = pred > 64 ? 64 : pred; nzb = nzb < 8 ? nzb : (nzb >= 64 ? 36 : 4 + nzb / 2);
+          uint32_t nz = rd.Read(cv, ctx_offset + nzb * nbctx + bctx);
+          if (nz + covered > size) { err = kErrTooManyNz; break; }
+          { uint8_t v = uint8_t((nz + covered - 1) >> log2c); for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) s_nz[c][cell + iy * 32 + ix] = v; }
+          const uint32_t* order = reinterpret_cast<const uint32_t*>(f.blob + f.order_off[pass][ord * 3 + c]);
+          const uint32_t histo = ctx_offset + nbctx * 37 + 458 * bctx; uint32_t prev = nz > size / 16 ? 0 : 1; int16_t* cc = coef + c * 65536;
+          for (uint32_t k = covered; k < size && nz != 0; k++) {
+            uint32_t zctx = (uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) + kFreqCtx[k >> log2c]) * 2 + prev;
+            uint32_t u = rd.Read(cv, histo + zctx);
+            if (u) { int32_t v = int32_t(uint32_t(UnpackSignedDev(u)) << shift); uint32_t addr = CoefAddr(by, bx, bw, order[k]);
+              if (pass) v += cc[addr]; if (v > 32767 || v < -32768) err = kErrCoefRange; cc[addr] = int16_t(v); prev = 1; nz--; } else prev = 0;
+          }
+          if (nz != 0) { err = kErrNzMismatch; break; }
+        }
+      }
+      if (!err && !rd.FinalOk(cv)) err = kErrAnsFinal;
+      if (!err) err = rd.err;
+    }
+  }
+  if (!err) { bool need_init = true; md.rd.err = 0; DecodeModularGroupDev(md, f, g, pass, &need_init); err = md.rd.err; }
+  uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
+  SetError(f.err, err);
+}
+
+// Global Modular stream (channels small enough to live in the LfGlobal section), decoded by one thread.
+__global__ void k_modular_global(const DFrame* fp, uint64_t start_bitpos, uint32_t num_channels) {
+  const DFrame& f = *fp; if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ModDecoder md; BindModDecoder(md, f); md.rd.br.Init(f.comp, start_bitpos);
+  // header already parsed on the host (it carries the global transforms); the ANS state word follows
+  md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12;
+  md.rd.Init(md.cv);
+  int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + f.num_groups) * WPScratchInts(kMaxWpWidth);
+  for (uint32_t c = 0; c < num_channels; c++) { const DModChannel& ch = f.mod_ch[c]; md.DecodeChannel(int(c), 0, f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), wp); }
+  if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
+  f.end_bitpos[0] = md.rd.br.BitPos();
+  SetError(f.err, md.rd.err);
+}
+
+void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { if (h.num_lf_groups) k_lf_group<<<h.num_lf_groups, 32, 0, st>>>(d); }
+void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st) {
+  size_t plane = size_t(h.xb) * h.yb; unsigned blocks = unsigned((plane + 255) / 256); k_lf_dequant<<<blocks, 256, 0, st>>>(d); if (smooth) k_lf_smooth<<<blocks, 256, 0, st>>>(d);
+}
+void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st) { k_ac_group<<<h.num_groups, 128, 0, st>>>(d, pass); }
+void LaunchModularGlobal(const DFrame* d, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st) { k_modular_global<<<1, 32, 0, st>>>(d, start_bitpos, num_channels); }
+
+}  // namespace jxlgpu

@@ -1,0 +1,66 @@
+// pdn-jpegxl_b200 engine — per-frame device descriptors (host fills, kernels read).
+// One DFrame describes one JPEG XL frame being decoded on one GPU: geometry,
+// quantiser / chroma-from-luma / block-context parameters from LfGlobal (A.8), entropy codes
+// and the MA tree (A.6/A.7), loop-filter and colour parameters (A.10), plus the device
+// buffers the stage kernels pass data through. Layout in HBM is documented in DESIGN.md.
+#pragma once
+#include "common.cuh"
+#include "modular.cuh"
+
+namespace jxlgpu {
+
+static const int kMaxPasses = 11;
+
+struct DLoopFilter {
+  uint32_t gab, epf_iters; float gab_w[6]; float epf_sharp_lut[8]; float epf_channel_scale[3]; float epf_quant_mul, pass0_sigma_scale, pass2_sigma_scale, border_sad_mul, sigma_for_modular;
+};
+struct DColor {
+  float opsin_inv[9]; float opsin_bias[3]; float opsin_bias_cbrt[3]; float itscale; float intensity_target; float to_target[9];   // linear sRGB -> target primaries
+  uint32_t tf; float gamma; uint32_t xyb_encoded; uint32_t num_color;   // tf: host ColorEncoding tf enum, 0 = pure gamma (gamma = exponent)
+};
+struct DOutput {
+  uint32_t sample_type;    // 0 u8, 1 u16, 2 f16, 3 f32
+  uint32_t num_channels;   // colour + alpha as the reference counts them (N/Decoder/JxlDecoder.cpp:494)
+  uint32_t color_channels; int32_t alpha_plane; int32_t black_plane; uint32_t premultiplied; uint32_t orientation; uint32_t bgra;   // bgra: fused BGRA32 surface pack (S/JpegXLLoad.cs:219-249)
+  uint32_t out_w, out_h;   // post-orientation dimensions
+  uint32_t alpha_bits, alpha_exp_bits, black_bits, bits, exp_bits;
+};
+struct DModChannel { uint32_t w, h, hshift, vshift; uint64_t plane_off; };   // plane_off: int32 element offset into DFrame::mod_planes
+
+// Per-device constant tables (built once): scaled DCT cosines c[k*N+i] = ck*cos((2i+1)k*pi/2N) for N = 1..256 and
+// the LF->LLF resample scales. cos_off[log2 N] is the float offset of the N x N table.
+struct DTables { float cosines[1 + 4 + 16 + 64 + 256 + 1024 + 4096 + 16384 + 65536]; float resample[6][32]; };
+__host__ __device__ inline uint32_t CosOff(int log2n) { const uint32_t o[9] = {0, 1, 5, 21, 85, 341, 1365, 5461, 21845}; return o[log2n]; }
+
+struct DFrame {
+  uint32_t xsize, ysize, xb, yb, xpad, ypad, xt, yt, xgroups, ygroups, num_groups, xlfgroups, ylfgroups, num_lf_groups, group_dim, num_passes, encoding, flags;
+  uint32_t pass_shift[kMaxPasses]; int32_t pass_min_shift[kMaxPasses], pass_max_shift[kMaxPasses];
+  float lf_fac[3], cfl_x_lf, cfl_b_lf, inv_gs, xm, bm, base_x, base_b, inv_color_factor, quant_bias[4], quant_scale;
+  uint32_t nb_block_ctx, num_lf_ctxs, n_lf_thr[3], n_qf_thr; int32_t lf_thr[3][15]; uint32_t qf_thr[15]; uint32_t bctx_map_off;
+  uint32_t num_hf_presets; DCode mod_code; uint32_t has_tree, tree_off, tree_size, uses_wp; DCode ac_code[kMaxPasses]; uint32_t order_off[kMaxPasses][13 * 3];
+  uint32_t dq_off[17];       // float[3*size] per quant table, byte offsets into blob
+  uint32_t sec_off;          // uint64 sec_bitpos[nsec] then uint64 sec_bitend[nsec], byte offset into blob
+  uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8]; uint32_t mod_bitdepth; uint32_t num_rct; uint32_t rct_begin[4], rct_type[4];
+  DLoopFilter lpf; DColor color; DOutput out;
+  // device buffers
+  const uint8_t* comp; const uint8_t* blob;
+  int32_t* lfq; float* lf; float* lf_tmp; uint8_t* acs; uint8_t* hf_mul_m1; uint8_t* sharp; uint8_t* lf_idx; int8_t* ytox; int8_t* ytob; int32_t* hfmeta_scratch;
+  const float* lf_src; const struct DTables* tables;
+  int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos;
+};
+static const uint32_t kHfMetaScratchInts = 2 * 1024 + 2 * 65536 + 65536;
+
+#ifdef __CUDACC__
+__device__ __forceinline__ const uint64_t* SecBitPos(const DFrame& f) { return reinterpret_cast<const uint64_t*>(f.blob + f.sec_off); }
+#endif
+
+// AC strategy geometry tables (SURVEY.md A.8 "AC strategies")
+__host__ __device__ inline int CoveredX(int s) { const uint8_t t[27] = {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32}; return t[s]; }
+__host__ __device__ inline int CoveredY(int s) { const uint8_t t[27] = {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16}; return t[s]; }
+__host__ __device__ inline int StrategyOrder(int s) { const uint8_t t[27] = {0, 1, 1, 1, 2, 3, 4, 4, 5, 5, 6, 6, 1, 1, 1, 1, 1, 1, 7, 8, 8, 9, 10, 10, 11, 12, 12}; return t[s]; }
+__host__ __device__ inline int QuantTableOf(int s) { const uint8_t t[27] = {0, 1, 2, 3, 4, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10, 10, 11, 12, 12, 13, 14, 14, 15, 16, 16}; return t[s]; }
+// "cell-chunked" coefficient addressing inside a 256x256 group: storage position p of the varblock whose first cell
+// is (by,bx) lives in the (p/64)-th covered cell (raster order inside the block).
+__host__ __device__ inline uint32_t CoefAddr(int by, int bx, int bw, uint32_t p) { uint32_t j = p >> 6; return (uint32_t(by + int(j) / bw) * 32u + uint32_t(bx + int(j) % bw)) * 64u + (p & 63u); }
+
+}  // namespace jxlgpu

@@ -1,0 +1,18 @@
+// pdn-jpegxl_b200 engine — host-callable launch wrappers for the sm_100a kernels.
+#pragma once
+#include "frame.cuh"
+
+namespace jxlgpu {
+// decode
+void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st);
+void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st);
+void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st);
+void LaunchModularGlobal(const DFrame* d, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st);
+void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st);       // dequant + CfL + LLF + inverse transforms
+void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st);           // gaborish + EPF (result in h.xyb)
+void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st);
+void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st);            // colour transform + sample conversion + interleave (+BGRA)
+void FillDeviceTables(DTables* host_tables);
+int LaunchCount();                                                                 // kernels launched by this process so far (bench gpu_launches)
+void CountLaunch(int n = 1);
+}  // namespace jxlgpu

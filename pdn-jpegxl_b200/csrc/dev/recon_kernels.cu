@@ -1,0 +1,332 @@
+// pdn-jpegxl_b200 engine — reconstruction kernels (sm_100a), all HBM-bound fp32 stages:
+//   k_reconstruct : HF dequant + chroma-from-luma + LLF-from-LF + inverse transform for every varblock of a
+//                   256x256 group (SURVEY.md A.8 "Dequant", A.9). int16 coefficients in, fp32 XYB planes out:
+//                   6 B + 12 B = 18 algorithmic bytes per pixel.
+//   k_inv_sigma, k_gaborish, k_epf : restoration filters (A.10), 24 B/px per pass.
+//   k_output / k_output_modular : XYB -> linear -> transfer function -> sample type, interleave, optional
+//                   fused BGRA32 surface pack (15-16 B/px for 8-bit RGB/BGRA), bit-exact integer path for lossless.
+// Replaces libjxl's dequant / IDCT / render-pipeline stages reached from N/Decoder/JxlDecoder.cpp:252 and the
+// managed repack loops I/DecoderLayerData.cs:667-992 + S/JpegXLLoad.cs:219-249 (bgra mode).
+#include "frame.cuh"
+#include "kernels.h"
+#include <atomic>
+#include <cuda_fp16.h>
+#include <cmath>
+
+namespace jxlgpu {
+
+static std::atomic<int> g_launches{0};
+int LaunchCount() { return g_launches.load(); }
+void CountLaunch(int n) { g_launches.fetch_add(n); }
+
+void FillDeviceTables(DTables* t) {
+  for (int l = 0; l <= 8; l++) { int n = 1 << l; float* c = t->cosines + CosOff(l);
+    for (int k = 0; k < n; k++) for (int i = 0; i < n; i++) c[size_t(k) * n + i] = float((k == 0 ? 1.0 : std::sqrt(2.0)) * std::cos((2 * i + 1) * k * M_PI / (2.0 * n))); }
+  for (int l = 0; l < 6; l++) { int n = 1 << l; for (int u = 0; u < 32; u++) { double p = 1; if (u < n) for (int k = 0; k < 3; k++) p *= std::cos(u * M_PI * double(1 << k) / (16.0 * n)); t->resample[l][u] = float(1.0 / p); } }
+}
+
+__device__ __forceinline__ float AdjustQuantBiasDev(int q, float b1, float b3) { if (q == 0) return 0.f; if (q == 1) return b1; if (q == -1) return -b1; return float(q) - b3 / float(q); }
+__device__ __forceinline__ int Log2Dev(int n) { return 31 - __clz(n); }
+
+// 8x8 special transforms (A.9 [L]); coef/px in registers or shared memory, stride in floats
+__device__ void SpecialTransform8x8(int s, const float* coef, float* px, size_t stride, const float* cos4, const float* cos8) {
+  if (s == 2) {   // DCT2X2: three Hadamard levels
+    float b[64], t[64]; for (int i = 0; i < 64; i++) b[i] = coef[i];
+    for (int S = 2; S <= 8; S *= 2) { int n = S / 2;
+      for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) { float c00 = b[y * 8 + x], c01 = b[y * 8 + n + x], c10 = b[(y + n) * 8 + x], c11 = b[(y + n) * 8 + n + x];
+        t[y * 2 * 8 + x * 2] = c00 + c01 + c10 + c11; t[y * 2 * 8 + x * 2 + 1] = c00 + c01 - c10 - c11; t[(y * 2 + 1) * 8 + x * 2] = c00 - c01 + c10 - c11; t[(y * 2 + 1) * 8 + x * 2 + 1] = c00 - c01 - c10 + c11; }
+      for (int y = 0; y < S; y++) for (int x = 0; x < S; x++) b[y * 8 + x] = t[y * 8 + x]; }
+    for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) px[y * stride + x] = b[y * 8 + x];
+    return;
+  }
+  if (s == 3 || s == 1) {
+    float a = coef[0], b = coef[1], c = coef[8], d = coef[9]; float dcs[4] = {a + b + c + d, a + b - c - d, a - b + c - d, a - b - c + d};
+    for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) {
+      if (s == 3) {   // DCT4X4: storage blk[hf][vf]
+        float blk[16]; blk[0] = dcs[y * 2 + x]; for (int iy = 0; iy < 4; iy++) for (int ix = 0; ix < 4; ix++) if (ix || iy) blk[iy * 4 + ix] = coef[(y + iy * 2) * 8 + x + ix * 2];
+        float tmp[16];
+        for (int hf = 0; hf < 4; hf++) for (int py = 0; py < 4; py++) { float sacc = 0; for (int vf = 0; vf < 4; vf++) sacc += blk[hf * 4 + vf] * cos4[vf * 4 + py]; tmp[hf * 4 + py] = sacc; }
+        for (int py = 0; py < 4; py++) for (int pxx = 0; pxx < 4; pxx++) { float sacc = 0; for (int hf = 0; hf < 4; hf++) sacc += tmp[hf * 4 + py] * cos4[hf * 4 + pxx]; px[(y * 4 + py) * stride + x * 4 + pxx] = sacc; }
+      } else {        // IDENTITY
+        float block_dc = dcs[y * 2 + x], rs = 0; for (int iy = 0; iy < 4; iy++) for (int ix = 0; ix < 4; ix++) if (ix || iy) rs += coef[(y + iy * 2) * 8 + x + ix * 2];
+        float center = block_dc - rs * (1.0f / 16); px[(4 * y + 1) * stride + 4 * x + 1] = center;
+        for (int iy = 0; iy < 4; iy++) for (int ix = 0; ix < 4; ix++) { if (ix == 1 && iy == 1) continue; px[(y * 4 + iy) * stride + x * 4 + ix] = coef[(y + iy * 2) * 8 + x + ix * 2] + center; }
+        px[y * 4 * stride + x * 4] = coef[(y + 2) * 8 + x + 2] + center;
+      }
+    }
+    return;
+  }
+  // DCT4X8 (s==12): two 4-row x 8-col halves stacked vertically, storage blk[vf(4)][hf(8)];
+  // DCT8X4 (s==13): two 8-row x 4-col halves side by side, storage blk[hf(4)][vf(8)]
+  float dcs[2] = {coef[0] + coef[8], coef[0] - coef[8]};
+  for (int k = 0; k < 2; k++) {
+    float blk[32]; blk[0] = dcs[k]; for (int iy = 0; iy < 4; iy++) for (int ix = 0; ix < 8; ix++) if (ix || iy) blk[iy * 8 + ix] = coef[(k + iy * 2) * 8 + ix];
+    float tmp[32];   // tmp[r][j]: r = short-axis frequency (4), j = long-axis position (8)
+    for (int r = 0; r < 4; r++) for (int j = 0; j < 8; j++) { float sacc = 0; for (int c = 0; c < 8; c++) sacc += blk[r * 8 + c] * cos8[c * 8 + j]; tmp[r * 8 + j] = sacc; }
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 8; j++) { float sacc = 0; for (int r = 0; r < 4; r++) sacc += tmp[r * 8 + j] * cos4[r * 4 + i];
+      if (s == 12) px[(k * 4 + i) * stride + j] = sacc; else px[j * stride + k * 4 + i] = sacc; }
+  }
+}
+
+// LLF corner from the LF samples of the block (A.9 "LLF from DC"). lanes cooperate; writes into storage-layout S.
+__device__ void LlfFromLf(const DFrame& f, int c, int cy, int cx, const float* lfp, int lf_stride, float* S, int SW, int lane, int nlanes) {
+  const DTables& t = *f.tables; const int ly = Log2Dev(cy), lx = Log2Dev(cx); const float* cv = t.cosines + CosOff(ly); const float* ch = t.cosines + CosOff(lx);
+  for (int idx = lane; idx < cy * cx; idx += nlanes) { int v = idx / cx, hfr = idx % cx; float acc = 0;
+    for (int y = 0; y < cy; y++) { float rowacc = 0; for (int x = 0; x < cx; x++) rowacc += lfp[y * lf_stride + x] * ch[hfr * cx + x]; acc += rowacc * cv[v * cy + y]; }
+    float val = acc / float(cy * cx) * t.resample[ly][v] * t.resample[lx][hfr];
+    if (cy < cx) S[v * SW + hfr] = val; else S[hfr * SW + v] = val; }
+  (void)c;
+}
+
+static const int kReconWarps = 8;
+// dynamic smem per warp: Sy[1024] Sc[1024] T[1024] floats
+__global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* fp) {
+  const DFrame& f = *fp; const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
+  extern __shared__ float smem[]; float* Sy = smem + warp * 3072; float* Sc = Sy + 1024; float* T = Sc + 1024;
+  const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const DTables& tb = *f.tables;
+  // ---- small varblocks (both sides <= 32 px): one warp per block
+  for (int cell = warp; cell < 1024; cell += kReconWarps) {
+    const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
+    const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
+    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw > 4 || bh > 4) continue;
+    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(f.blob + f.dq_off[QuantTableOf(s)]);
+    const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
+    const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
+    const bool plain = (s == 0) || (s >= 4 && s <= 11);
+    for (int c3 = 0; c3 < 3; c3++) {
+      const int c = c3 == 0 ? 1 : c3 == 1 ? 0 : 2; float* S = c == 1 ? Sy : Sc;
+      const float mulc = c == 1 ? scale : c == 0 ? scale * f.xm : scale * f.bm, kc = c == 0 ? kx : kb, b1 = f.quant_bias[c], b3 = f.quant_bias[3];
+      for (int p = lane; p < size; p += 32) { int q = coef[c * 65536 + CoefAddr(by, bx, bw, uint32_t(p))]; float v = AdjustQuantBiasDev(q, b1, b3) * dq[c * size + p] * mulc; if (c != 1) v += kc * Sy[p]; S[p] = v; }
+      __syncwarp();
+      LlfFromLf(f, c, bh, bw, f.lf_src + c * lfplane + o, int(f.xb), S, SW, lane, 32);
+      __syncwarp();
+      float* out = f.xyb + c * plane + size_t(cy0 + by) * 8 * f.xpad + size_t(cx0 + bx) * 8;
+      if (plain) {
+        const float* cl = tb.cosines + CosOff(Log2Dev(SW)); const float* cs = tb.cosines + CosOff(Log2Dev(SH));
+        for (int idx = lane; idx < SH * SW; idx += 32) { int r = idx / SW, j = idx % SW; float acc = 0; for (int k = 0; k < SW; k++) acc += S[r * SW + k] * cl[k * SW + j]; T[idx] = acc; }
+        __syncwarp();
+        for (int idx = lane; idx < SH * SW; idx += 32) { int i = idx / SW, j = idx % SW; float acc = 0; for (int r = 0; r < SH; r++) acc += T[r * SW + j] * cs[r * SH + i];
+          if (H >= W) out[size_t(j) * f.xpad + i] = acc; else out[size_t(i) * f.xpad + j] = acc; }
+      } else if (s >= 14 && s <= 17) { if (lane == 0) SetError(f.err, kErrBadStrategy); }
+      else if (lane == 0) SpecialTransform8x8(s, S, out, f.xpad, tb.cosines + CosOff(2), tb.cosines + CosOff(3));
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- large varblocks (a side >= 64 px): the whole CTA per block, staged through the XYB planes themselves
+  const int NT = kReconWarps * 32;
+  for (int cell = 0; cell < 1024; cell++) {
+    const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
+    const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
+    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw <= 4 && bh <= 4) continue;
+    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(f.blob + f.dq_off[QuantTableOf(s)]);
+    const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
+    const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
+    const size_t base = size_t(cy0 + by) * 8 * f.xpad + size_t(cx0 + bx) * 8;
+    // stage 0: dequantised coefficients, storage position p kept at linear index p of the block's pixel rect (in xyb_tmp)
+    for (int p = tid; p < size; p += NT) { uint32_t ad = CoefAddr(by, bx, bw, uint32_t(p)); size_t dst = base + size_t(p / W) * f.xpad + p % W;
+      float y = AdjustQuantBiasDev(coef[65536 + ad], f.quant_bias[1], f.quant_bias[3]) * dq[size + p] * scale;
+      float x = AdjustQuantBiasDev(coef[ad], f.quant_bias[0], f.quant_bias[3]) * dq[p] * (scale * f.xm) + kx * y;
+      float b = AdjustQuantBiasDev(coef[2 * 65536 + ad], f.quant_bias[2], f.quant_bias[3]) * dq[2 * size + p] * (scale * f.bm) + kb * y;
+      f.xyb_tmp[dst] = x; f.xyb_tmp[plane + dst] = y; f.xyb_tmp[2 * plane + dst] = b; }
+    __syncthreads();
+    {  // LLF corner
+      const int ly = Log2Dev(bh), lx = Log2Dev(bw); const float* cv = tb.cosines + CosOff(ly); const float* ch = tb.cosines + CosOff(lx);
+      for (int idx = tid; idx < 3 * bh * bw; idx += NT) { int c = idx / (bh * bw), r = idx % (bh * bw), v = r / bw, hfr = r % bw; const float* lfp = f.lf_src + c * lfplane + o; float acc = 0;
+        for (int y = 0; y < bh; y++) { float ra = 0; for (int x = 0; x < bw; x++) ra += lfp[size_t(y) * f.xb + x] * ch[hfr * bw + x]; acc += ra * cv[v * bh + y]; }
+        float val = acc / float(bh * bw) * tb.resample[ly][v] * tb.resample[lx][hfr]; int p = bh < bw ? v * SW + hfr : hfr * SW + v;
+        f.xyb_tmp[c * plane + base + size_t(p / W) * f.xpad + p % W] = val; }
+    }
+    __syncthreads();
+    const float* cl = tb.cosines + CosOff(Log2Dev(SW)); const float* cs = tb.cosines + CosOff(Log2Dev(SH));
+    for (int c = 0; c < 3; c++) {   // pass A: along the long axis, xyb_tmp -> xyb (linear index = r*SW + j)
+      for (int idx = tid; idx < size; idx += NT) { int r = idx / SW, j = idx % SW; float acc = 0;
+        for (int k = 0; k < SW; k++) { int p = r * SW + k; acc += f.xyb_tmp[c * plane + base + size_t(p / W) * f.xpad + p % W] * cl[k * SW + j]; }
+        f.xyb[c * plane + base + size_t(idx / W) * f.xpad + idx % W] = acc; }
+    }
+    __syncthreads();
+    for (int c = 0; c < 3; c++) {   // pass B: along the short axis, xyb -> xyb_tmp at final pixel positions
+      for (int idx = tid; idx < size; idx += NT) { int i = idx / SW, j = idx % SW; float acc = 0;
+        for (int r = 0; r < SH; r++) { int p = r * SW + j; acc += f.xyb[c * plane + base + size_t(p / W) * f.xpad + p % W] * cs[r * SH + i]; }
+        int py = H >= W ? j : i, pxx = H >= W ? i : j; f.xyb_tmp[c * plane + base + size_t(py) * f.xpad + pxx] = acc; }
+    }
+    __syncthreads();
+    for (int c = 0; c < 3; c++) for (int idx = tid; idx < size; idx += NT) { size_t ad = c * plane + base + size_t(idx / W) * f.xpad + idx % W; f.xyb[ad] = f.xyb_tmp[ad]; }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ restoration filters
+__device__ __forceinline__ int MirrorDev(int x, int n) { while (x < 0 || x >= n) { if (x < 0) x = -x - 1; else x = 2 * n - 1 - x; } return x; }
+
+__global__ void k_inv_sigma(const DFrame* fp) {
+  const DFrame& f = *fp; size_t n = size_t(f.xb) * f.yb; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
+  const float kInvSigmaNum = -1.1715728752538099024f;
+  if (f.encoding == 1) { f.inv_sigma[i] = kInvSigmaNum / f.lpf.sigma_for_modular; return; }
+  float sigma_quant = f.lpf.epf_quant_mul / (f.quant_scale * float(int(f.hf_mul_m1[i]) + 1) * kInvSigmaNum);
+  float sigma = fminf(-1e-4f, sigma_quant * f.lpf.epf_sharp_lut[f.sharp[i]]); f.inv_sigma[i] = 1.0f / sigma;
+}
+
+__global__ void k_gaborish(const DFrame* fp, const float* __restrict__ src, float* __restrict__ dst) {
+  const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+  const size_t plane = size_t(f.xpad) * f.ypad; const int yu = MirrorDev(y - 1, ys), yd = MirrorDev(y + 1, ys), xl = MirrorDev(x - 1, xs), xr = MirrorDev(x + 1, xs);
+#pragma unroll
+  for (int c = 0; c < 3; c++) { const float* p = src + c * plane; const float* t = p + size_t(yu) * f.xpad; const float* m = p + size_t(y) * f.xpad; const float* b = p + size_t(yd) * f.xpad;
+    float w1 = f.lpf.gab_w[2 * c], w2 = f.lpf.gab_w[2 * c + 1]; float mul = 1.0f / (1.0f + 4.0f * (w1 + w2));
+    dst[c * plane + size_t(y) * f.xpad + x] = m[x] * mul + (t[x] + b[x] + m[xl] + m[xr]) * (w1 * mul) + (t[xl] + t[xr] + b[xl] + b[xr]) * (w2 * mul); }
+}
+
+template <int PASS>
+__global__ void k_epf(const DFrame* fp, const float* __restrict__ src, float* __restrict__ dst) {
+  const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+  const size_t plane = size_t(f.xpad) * f.ypad; const size_t at = size_t(y) * f.xpad + x;
+  const float is = f.inv_sigma[size_t(y >> 3) * f.xb + (x >> 3)];
+  if (is < -3.90524291751269967465540850526868f) { for (int c = 0; c < 3; c++) dst[c * plane + at] = src[c * plane + at]; return; }
+  const float sigma_scale = PASS == 0 ? f.lpf.pass0_sigma_scale : PASS == 2 ? f.lpf.pass2_sigma_scale : 1.0f; const float sm = sigma_scale * 1.65f;
+  const bool border = ((y & 7) == 0 || (y & 7) == 7 || (x & 7) == 0 || (x & 7) == 7); const float inv = is * (border ? sm * f.lpf.border_sad_mul : sm);
+  const int n12[12][2] = {{-2, 0}, {-1, -1}, {-1, 0}, {-1, 1}, {0, -2}, {0, -1}, {0, 1}, {0, 2}, {1, -1}, {1, 0}, {1, 1}, {2, 0}}; const int n4[4][2] = {{-1, 0}, {0, -1}, {0, 1}, {1, 0}};
+  const int plus[5][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+  const int nn = PASS == 0 ? 12 : 4;
+  float wsum = 1.0f, acc[3]; for (int c = 0; c < 3; c++) acc[c] = src[c * plane + at];
+  for (int i = 0; i < nn; i++) {
+    const int dy = PASS == 0 ? n12[i][0] : n4[i][0], dx = PASS == 0 ? n12[i][1] : n4[i][1]; float sad = 0;
+    for (int c = 0; c < 3; c++) { const float* p = src + c * plane; float s = 0;
+      if (PASS == 2) s = fabsf(p[size_t(MirrorDev(y + dy, ys)) * f.xpad + MirrorDev(x + dx, xs)] - p[at]);
+      else for (int k = 0; k < 5; k++) { int yy = y + plus[k][0], xx = x + plus[k][1]; s += fabsf(p[size_t(MirrorDev(yy + dy, ys)) * f.xpad + MirrorDev(xx + dx, xs)] - p[size_t(MirrorDev(yy, ys)) * f.xpad + MirrorDev(xx, xs)]); }
+      sad += s * f.lpf.epf_channel_scale[c]; }
+    float wgt = fmaxf(0.f, 1.0f + sad * inv); wsum += wgt; const size_t nat = size_t(MirrorDev(y + dy, ys)) * f.xpad + MirrorDev(x + dx, xs);
+    for (int c = 0; c < 3; c++) acc[c] += wgt * src[c * plane + nat];
+  }
+  const float iw = 1.0f / wsum; for (int c = 0; c < 3; c++) dst[c * plane + at] = acc[c] * iw;
+}
+
+// ------------------------------------------------------------------ inverse RCT on the global Modular image
+__global__ void k_inverse_rct(const DFrame* fp, uint32_t begin_c, uint32_t type) {
+  const DFrame& f = *fp; const DModChannel& c0 = f.mod_ch[begin_c]; size_t n = size_t(c0.w) * c0.h; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
+  int32_t* p0 = f.mod_planes + f.mod_ch[begin_c].plane_off; int32_t* p1 = f.mod_planes + f.mod_ch[begin_c + 1].plane_off; int32_t* p2 = f.mod_planes + f.mod_ch[begin_c + 2].plane_off;
+  uint32_t perm = type / 7, k = type % 7; int32_t A = p0[i], B = p1[i], C = p2[i], o[3];
+  if (k == 6) { int32_t t = A - (C >> 1); int32_t G = C + t; int32_t Bl = t - (B >> 1); int32_t R = Bl + B; o[0] = R; o[1] = G; o[2] = Bl; }
+  else { int32_t D = A, E = B, F = C; if (k & 1) F += A; if ((k >> 1) == 1) E += A; if ((k >> 1) == 2) E += (A + F) >> 1; o[0] = D; o[1] = E; o[2] = F; }
+  int32_t r[3]; r[perm % 3] = o[0]; r[(perm + 1 + perm / 3) % 3] = o[1]; r[(perm + 2 - perm / 3) % 3] = o[2];
+  p0[i] = r[0]; p1[i] = r[1]; p2[i] = r[2];
+}
+
+// ------------------------------------------------------------------ output
+__device__ __forceinline__ float TfFromLinearDev(float v, uint32_t tf, float gamma, float intensity_target) {
+  float a = fabsf(v), r;
+  switch (tf) {
+    case 0: r = powf(a, gamma); break;
+    case 8: r = a; break;
+    case 13: r = a <= 0.0031308f ? 12.92f * a : 1.055f * powf(a, 1.0f / 2.4f) - 0.055f; break;
+    case 1: r = a < 0.018f ? 4.5f * a : 1.099f * powf(a, 0.45f) - 0.099f; break;
+    case 16: { const float m1 = 2610.0f / 16384, m2 = 2523.0f / 4096 * 128, c1 = 3424.0f / 4096, c2 = 2413.0f / 4096 * 32, c3 = 2392.0f / 4096 * 32;
+      float yv = fminf(1.0f, a * intensity_target / 10000.0f); float p = powf(yv, m1); r = powf((c1 + c2 * p) / (1.0f + c3 * p), m2); break; }
+    case 17: r = powf(a, 1.0f / 2.6f); break;
+    default: r = a; break;
+  }
+  return v < 0 ? -r : r;
+}
+__device__ __forceinline__ float IntToFloatSampleDev(int32_t v, uint32_t bits, uint32_t exp_bits) {
+  if (exp_bits == 0) return float(double(v) / double((1ull << bits) - 1));
+  if (bits == 32 && exp_bits == 8) return __int_as_float(v);
+  int mant_bits = int(bits) - int(exp_bits) - 1; uint32_t u = uint32_t(v); bool sign = (u >> (bits - 1)) & 1; u &= (1u << (bits - 1)) - 1; if (u == 0) return sign ? -0.f : 0.f;
+  int e = int(u >> mant_bits); uint32_t mant = u & ((1u << mant_bits) - 1); int bias = (1 << (exp_bits - 1)) - 1; double r;
+  if (e == 0) r = ldexp(double(mant), 1 - bias - mant_bits); else r = ldexp(double(mant | (1u << mant_bits)), e - bias - mant_bits);
+  return float(sign ? -r : r);
+}
+__device__ __forceinline__ void StoreSampleDev(uint8_t* dst, uint32_t type, float v) {
+  switch (type) {
+    case 0: *dst = uint8_t(__float2int_rn(fminf(1.f, fmaxf(0.f, v)) * 255.0f)); break;
+    case 1: *reinterpret_cast<uint16_t*>(dst) = uint16_t(__float2int_rn(fminf(1.f, fmaxf(0.f, v)) * 65535.0f)); break;
+    case 2: *reinterpret_cast<__half*>(dst) = __float2half_rn(v); break;
+    default: *reinterpret_cast<float*>(dst) = v; break;
+  }
+}
+// (x,y) in decoded frame coordinates -> element index in the oriented output image
+__device__ __forceinline__ size_t OrientedIndex(const DFrame& f, int x, int y) {
+  const int W = int(f.xsize), H = int(f.ysize); int ox, oy;
+  switch (f.out.orientation) { case 2: ox = W - 1 - x; oy = y; break; case 3: ox = W - 1 - x; oy = H - 1 - y; break; case 4: ox = x; oy = H - 1 - y; break;
+    case 5: ox = y; oy = x; break; case 6: ox = H - 1 - y; oy = x; break; case 7: ox = H - 1 - y; oy = W - 1 - x; break; case 8: ox = y; oy = W - 1 - x; break; default: ox = x; oy = y; }
+  return size_t(oy) * f.out.out_w + ox;
+}
+
+__global__ void k_output(const DFrame* fp, const float* __restrict__ xyb) {
+  const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+  const DOutput& o = f.out; float rgb[3];
+  if (f.encoding == 0) {
+    const size_t plane = size_t(f.xpad) * f.ypad, at = size_t(y) * f.xpad + x; const float X = xyb[at], Y = xyb[plane + at], B = xyb[2 * plane + at];
+    float gm[3] = {Y + X, Y - X, B}, mix[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { float v = gm[c] - f.color.opsin_bias_cbrt[c]; mix[c] = v * v * v + f.color.opsin_bias[c]; }
+    float lin[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) lin[c] = (f.color.opsin_inv[3 * c] * mix[0] + f.color.opsin_inv[3 * c + 1] * mix[1] + f.color.opsin_inv[3 * c + 2] * mix[2]) * f.color.itscale;
+#pragma unroll
+    for (int c = 0; c < 3; c++) rgb[c] = TfFromLinearDev(f.color.to_target[3 * c] * lin[0] + f.color.to_target[3 * c + 1] * lin[1] + f.color.to_target[3 * c + 2] * lin[2], f.color.tf, f.color.gamma, f.color.intensity_target);
+  } else {
+    const uint32_t nc = f.color.num_color;
+    for (uint32_t c = 0; c < 3; c++) { const DModChannel& ch = f.mod_ch[c < nc ? c : nc - 1]; rgb[c] = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(y) * ch.w + x], o.bits, o.exp_bits); }
+  }
+  float a = 1.0f;
+  if (o.alpha_plane >= 0) { const DModChannel& ch = f.mod_ch[o.alpha_plane]; int sx = min(x >> ch.hshift, int(ch.w) - 1), sy = min(y >> ch.vshift, int(ch.h) - 1); a = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(sy) * ch.w + sx], o.alpha_bits, o.alpha_exp_bits); }
+  if (o.premultiplied) { float mul = 1.0f / fmaxf(1.0f / 67108864.0f, a); rgb[0] *= mul; rgb[1] *= mul; rgb[2] *= mul; }
+  const size_t oi = OrientedIndex(f, x, y);
+  if (o.bgra) {   // BGRA32 surface: B,G,R from the 8-bit conversion, A = alpha plane mapped to 8 bits (I/TransparencyMapping.cs:19-32) or 255
+    uint8_t r8 = uint8_t(__float2int_rn(fminf(1.f, fmaxf(0.f, rgb[0])) * 255.0f)), g8 = uint8_t(__float2int_rn(fminf(1.f, fmaxf(0.f, rgb[1])) * 255.0f)), b8 = uint8_t(__float2int_rn(fminf(1.f, fmaxf(0.f, rgb[2])) * 255.0f));
+    if (o.color_channels == 1) { g8 = r8; b8 = r8; }
+    uint8_t a8 = 255; if (o.alpha_plane >= 0) a8 = uint8_t(__float2int_rn(fminf(1.f, fmaxf(0.f, a)) * 255.0f));
+    reinterpret_cast<uint32_t*>(f.out_px)[oi] = uint32_t(b8) | (uint32_t(g8) << 8) | (uint32_t(r8) << 16) | (uint32_t(a8) << 24); return;
+  }
+  const uint32_t bps = o.sample_type == 0 ? 1 : o.sample_type == 3 ? 4 : 2; uint8_t* dst = f.out_px + oi * size_t(bps) * (o.num_channels + (o.black_plane >= 0 ? 1 : 0));
+  if (o.black_plane >= 0) {   // CMYK merge, N/Decoder/JxlDecoder.cpp:159-215 (u8 only): 255 - C,M,Y,K then optional A
+    const DModChannel& ch = f.mod_ch[o.black_plane]; float k = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(min(y >> ch.vshift, int(ch.h) - 1)) * ch.w + min(x >> ch.hshift, int(ch.w) - 1)], o.black_bits, 0);
+    uint8_t t[4]; for (int c = 0; c < 3; c++) StoreSampleDev(&t[c], 0, rgb[c]); StoreSampleDev(&t[3], 0, k);
+    for (int c = 0; c < 4; c++) dst[c] = uint8_t(0xff - t[c]); if (o.alpha_plane >= 0) StoreSampleDev(dst + 4, 0, a); return;
+  }
+  for (uint32_t c = 0; c < o.color_channels; c++) StoreSampleDev(dst + bps * c, o.sample_type, rgb[c]);
+  if (o.alpha_plane >= 0) StoreSampleDev(dst + bps * o.color_channels, o.sample_type, a);
+}
+
+// Lossless 8/16-bit integer fast path: samples pass through untouched (bit-exact by construction).
+__global__ void k_output_int(const DFrame* fp) {
+  const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+  const DOutput& o = f.out; const size_t oi = OrientedIndex(f, x, y); const uint32_t nc = f.color.num_color; int32_t v[4]; uint32_t n = 0;
+  for (uint32_t c = 0; c < o.color_channels; c++) { const DModChannel& ch = f.mod_ch[c < nc ? c : nc - 1]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }
+  if (o.alpha_plane >= 0) { const DModChannel& ch = f.mod_ch[o.alpha_plane]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }
+  const int32_t mx = o.sample_type == 0 ? 255 : 65535;
+  if (o.bgra) { uint8_t r8 = uint8_t(min(max(v[0], 0), 255)), g8 = o.color_channels == 1 ? r8 : uint8_t(min(max(v[1], 0), 255)), b8 = o.color_channels == 1 ? r8 : uint8_t(min(max(v[2], 0), 255)); uint8_t a8 = o.alpha_plane >= 0 ? uint8_t(min(max(v[n - 1], 0), 255)) : 255;
+    reinterpret_cast<uint32_t*>(f.out_px)[oi] = uint32_t(b8) | (uint32_t(g8) << 8) | (uint32_t(r8) << 16) | (uint32_t(a8) << 24); return; }
+  if (o.sample_type == 0) { uint8_t* dst = f.out_px + oi * n; for (uint32_t c = 0; c < n; c++) dst[c] = uint8_t(min(max(v[c], 0), mx)); }
+  else { uint16_t* dst = reinterpret_cast<uint16_t*>(f.out_px) + oi * n; for (uint32_t c = 0; c < n; c++) dst[c] = uint16_t(min(max(v[c], 0), mx)); }
+}
+
+void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st) {
+  static bool attr = false; size_t smem = size_t(kReconWarps) * 3072 * sizeof(float);
+  if (!attr) { cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr = true; }
+  k_reconstruct<<<h.num_groups, kReconWarps * 32, smem, st>>>(d); CountLaunch();
+}
+// Runs gaborish + EPF; ping-pongs between xyb and xyb_tmp. Returns the buffer holding the result.
+void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {
+  dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8); float* a = h.xyb; float* b = h.xyb_tmp;
+  if (h.lpf.gab) { k_gaborish<<<grid, blk, 0, st>>>(d, a, b); CountLaunch(); std::swap(a, b); }
+  if (h.lpf.epf_iters) {
+    size_t n = size_t(h.xb) * h.yb; k_inv_sigma<<<unsigned((n + 255) / 256), 256, 0, st>>>(d); CountLaunch();
+    if (h.lpf.epf_iters == 3) { k_epf<0><<<grid, blk, 0, st>>>(d, a, b); CountLaunch(); std::swap(a, b); }
+    k_epf<1><<<grid, blk, 0, st>>>(d, a, b); CountLaunch(); std::swap(a, b);
+    if (h.lpf.epf_iters >= 2) { k_epf<2><<<grid, blk, 0, st>>>(d, a, b); CountLaunch(); std::swap(a, b); }
+  }
+}
+const float* FilteredPlanes(const DFrame& h) { int n = (h.lpf.gab ? 1 : 0) + (h.lpf.epf_iters == 3 ? 3 : int(h.lpf.epf_iters)); return (n & 1) ? h.xyb_tmp : h.xyb; }
+void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st) {
+  for (uint32_t i = h.num_rct; i-- > 0;) { const DModChannel& c0 = h.mod_ch[h.rct_begin[i]]; size_t n = size_t(c0.w) * c0.h; k_inverse_rct<<<unsigned((n + 255) / 256), 256, 0, st>>>(d, h.rct_begin[i], h.rct_type[i]); CountLaunch(); }
+}
+void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st) {
+  dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8);
+  bool int_path = h.encoding == 1 && !h.color.xyb_encoded && h.out.exp_bits == 0 && h.out.black_plane < 0 && !h.out.premultiplied && (h.out.sample_type == 0 ? h.out.bits == 8 : (h.out.sample_type == 1 && h.out.bits == 16)) &&
+                  (h.out.alpha_plane < 0 || (h.out.alpha_bits == h.out.bits && h.out.alpha_exp_bits == 0 && h.mod_ch[h.out.alpha_plane].hshift == 0));
+  if (int_path) k_output_int<<<grid, blk, 0, st>>>(d); else k_output<<<grid, blk, 0, st>>>(d, FilteredPlanes(h));
+  CountLaunch();
+}
+
+}  // namespace jxlgpu

@@ -1,0 +1,66 @@
+// pdn-jpegxl_b200 engine — internal C++ interface between the C-ABI layer (abi.cc) and the
+// CUDA decode / encode pipelines. Nothing here is exported; the exported surface is
+// include/JxlFileTypeIO.h (the reference's N/JxlFileTypeIO.h:29-43 plus documented extensions).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+#include <memory>
+#include <cuda_runtime.h>
+
+namespace jxlgpu {
+
+enum class Status : int32_t { Ok = 0, NullParameter, InvalidParameter, OutOfMemory, HasAnimation, HasMultipleFrames, ImageDimensionExceedsInt32, UnsupportedChannelFormat,
+                              CreateLayerError, CreateMetadataError, DecodeError, MetadataError, InvalidFileSignature };
+
+struct ParsedInfo {   // what pass 1 of the reference reports (N/Decoder/JxlDecoder.cpp:412-793)
+  uint32_t width = 0, height = 0; int format = 1; int sample_type = 0; bool has_alpha = false; int num_channels = 3;
+  int known_profile = -1; std::vector<uint8_t> icc; bool is_container = false; bool has_exif = false; std::vector<uint8_t> exif; std::vector<std::vector<uint8_t>> xmp;
+  std::string frame_name; double bpp = 0;
+};
+
+struct DecodeRequest {
+  const uint8_t* data = nullptr; size_t size = 0;
+  bool bgra = false;            // fused BGRA32 surface output (extension; replaces I/DecoderLayerData.cs + S/JpegXLLoad.cs:219-249 passes)
+  bool device_output = false;   // leave pixels in device memory (bench `value`: inputs/outputs resident in HBM)
+  const uint8_t* device_input = nullptr;   // optional: the same file bytes already resident in device memory
+  int device = -1;              // -1: current device
+};
+
+struct StageTimes { float h2d = 0, lf = 0, ac = 0, recon = 0, filters = 0, output = 0, d2h = 0, total = 0; };
+
+class DecodeJob;   // opaque
+struct DecodeResult {
+  Status status = Status::Ok; std::string message; ParsedInfo info;
+  uint8_t* pixels = nullptr; size_t pixel_bytes = 0;   // pinned host memory (or device memory when device_output), owned by the job
+  uint32_t out_width = 0, out_height = 0; StageTimes times;
+  std::shared_ptr<DecodeJob> job;                       // keeps `pixels` alive
+};
+
+// Parses headers + metadata only (pass 1 of the reference). Never touches the GPU.
+DecodeResult ParseInfo(const uint8_t* data, size_t size);
+// Full decode on the GPU. Fails loudly (DecodeError with a message) when no CUDA device is usable: there is no CPU fallback.
+DecodeResult DecodeOnGpu(const DecodeRequest& req);
+// Asynchronous variant for batches: enqueue everything on `stream`, return without synchronising. Finish() waits and reads the error word.
+std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res);
+void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res);
+// stage dumps for parity tests (3 planes xpad*ypad floats or coefficient ints), copied to host
+bool DecodeDebugPlanes(const std::shared_ptr<DecodeJob>& job, int which, std::vector<float>* out, int* xpad, int* ypad);
+bool DecodeDebugCoeffs(const std::shared_ptr<DecodeJob>& job, std::vector<int16_t>* out);
+
+bool CudaAvailable(std::string* why);
+void TrimPools();
+
+// ---- encoder
+struct EncodeRequest {
+  const uint8_t* bgra = nullptr; uint32_t width = 0, height = 0, stride = 0;   // BitmapData (N/Common.h:17-23)
+  float distance = 1.0f; int effort = 7; bool lossless = false;
+  const uint8_t* exif = nullptr; size_t exif_size = 0; const uint8_t* icc = nullptr; size_t icc_size = 0; const uint8_t* xmp = nullptr; size_t xmp_size = 0;
+  bool device_input = false;   // bgra points at device memory (bench)
+};
+enum class EncStatus : int32_t { Ok = 0, NullParameter, OutOfMemory, UserCanceled, EncodeError, WriteError };
+struct EncodeResult { EncStatus status = EncStatus::Ok; std::string message; std::vector<uint8_t> file; StageTimes times; int pixel_format = 2; /* 0 Gray 1 GrayAlpha 2 Rgb 3 Rgba */ };
+EncodeResult EncodeOnGpu(const EncodeRequest& req);
+
+}  // namespace jxlgpu

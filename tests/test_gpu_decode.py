@@ -1,0 +1,103 @@
+"""-m gpu parity tests: CUDA decode through the C ABI vs the CPU oracle on the same files.
+Bars (BASELINE.json north_star): bit-exact for lossless / integer stages, <= 1 LSB max-abs for 8-bit lossy."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode_gpu(P, data):
+    image = P.DecoderImage()
+    P.JpegXLNative.LoadImage(data, image)
+    return image
+
+
+@pytest.mark.parametrize("w,h,kw", [
+    (64, 48, dict(effort=3)),                       # single group, single TOC entry
+    (300, 200, dict(effort=3)),                     # 2 groups
+    (520, 392, dict(effort=7)),                     # gab + EPF + varblocks + CfL + adaptive quant
+    (519, 387, dict(effort=7, distance=3.0)),       # ragged size, EPF 2 iterations
+    (300, 200, dict(effort=7, distance=8.0)),       # EPF 3 iterations
+    (2100, 300, dict(effort=5, use_prefix=1)),      # 2 LF groups, prefix codes
+])
+def test_vardct_rgb8_matches_oracle(gpu, oracle, w, h, kw):
+    img = oracle.synthetic_image(w, h, seed=w + h)
+    data = oracle.encode(img, **kw)
+    ref = oracle.decode(data, threads=4).pixels
+    got = _decode_gpu(gpu, data).layer_data.color
+    assert got.shape == ref.shape
+    err = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert int(err.max()) <= 1, "max abs error %d LSB" % int(err.max())
+    assert oracle.psnr(got, ref) >= 60.0
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 18, 19, 20, 21, 22, 23, 24, 25, 26])
+def test_every_supported_ac_strategy(gpu, oracle, strategy):
+    img = oracle.synthetic_image(531, 277, seed=strategy)
+    data = oracle.encode(img, effort=3, force_strategy=strategy)
+    ref = oracle.decode(data, threads=4).pixels
+    got = _decode_gpu(gpu, data).layer_data.color
+    assert int(np.abs(got.astype(np.int32) - ref.astype(np.int32)).max()) <= 1
+
+
+@pytest.mark.parametrize("w,h,channels,shift", [(200, 150, 3, 1), (300, 260, 4, 1), (100, 90, 1, 1), (700, 300, 3, 0), (1100, 600, 4, 2)])
+def test_lossless_modular_bit_exact(gpu, oracle, w, h, channels, shift):
+    img = oracle.synthetic_image(w, h, seed=11 * channels + w, channels=channels)
+    data = oracle.encode(img, lossless=1, modular_group_shift=shift)
+    image = _decode_gpu(gpu, data)
+    layer = image.layer_data
+    ref = oracle.decode(data).pixels
+    assert np.array_equal(ref, img)
+    if channels == 1:
+        assert np.array_equal(layer.color[..., 0], img[..., 0])
+    else:
+        assert np.array_equal(layer.color, img[..., :3])
+    if channels == 4:
+        assert np.array_equal(layer.transparency, img[..., 3])
+
+
+def test_lossy_with_alpha(gpu, oracle):
+    img = oracle.synthetic_image(300, 260, seed=3, channels=4)
+    data = oracle.encode(img, effort=7)
+    ref = oracle.decode(data).pixels
+    image = _decode_gpu(gpu, data)
+    assert image.has_transparency and image.format == "Rgb"
+    assert int(np.abs(image.layer_data.color.astype(np.int32) - ref[..., :3].astype(np.int32)).max()) <= 1
+    assert np.array_equal(image.layer_data.transparency, img[..., 3])     # alpha is coded losslessly
+
+
+def test_bgra_surface_matches_managed_repack(gpu, oracle):
+    """JxlB200LoadImageBgra == LoadImage + DecoderLayerData + JpegXLLoad repack (I/DecoderLayerData.cs, S/JpegXLLoad.cs:219-249)."""
+    for ch in (3, 4):
+        img = oracle.synthetic_image(333, 222, seed=ch, channels=ch)
+        data = oracle.encode(img, effort=5)
+        doc = gpu.JpegXLLoad.Load(data)
+        fused = gpu.load_image_bgra(data)
+        assert np.array_equal(doc.surface, fused)
+
+
+def test_callback_order_and_metadata(gpu, oracle):
+    img = oracle.synthetic_image(64, 64, seed=1)
+    exif = b"\x00\x00\x00\x00II*\x00\x08\x00\x00\x00\x00\x00"
+    data = oracle.encode(img, effort=3, exif=exif, xmp=b"<x:xmpmeta/>")
+    image = _decode_gpu(gpu, data)
+    assert image.callback_log == ["setBasicInfo", "setKnownColorProfile", "setExif", "setXmp", "setLayerData"]
+    assert image.known_color_profile == "Srgb" and image.exif == exif and image.xmp == b"<x:xmpmeta/>"
+    assert (image.width, image.height, image.format, image.channel_representation) == (64, 64, "Rgb", 0)
+
+
+def test_truncated_and_invalid_inputs(gpu, oracle):
+    img = oracle.synthetic_image(300, 200, seed=2)
+    data = oracle.encode(img, effort=3)
+    with pytest.raises(gpu.FormatException) as e:
+        _decode_gpu(gpu, data[: len(data) // 2])
+    assert e.value.status == "DecodeError"
+    with pytest.raises(gpu.FormatException) as e:
+        _decode_gpu(gpu, b"not a jxl file at all")
+    assert e.value.status == "InvalidFileSignature"
+    corrupt = bytearray(data)
+    corrupt[len(corrupt) * 3 // 4] ^= 0x5A
+    try:
+        _decode_gpu(gpu, bytes(corrupt))   # either decodes to something or reports DecodeError; it must not crash
+    except gpu.FormatException as ex:
+        assert ex.status == "DecodeError"
