@@ -9,6 +9,7 @@
 // managed repack loops I/DecoderLayerData.cs:667-992 + S/JpegXLLoad.cs:219-249 (bgra mode).
 #include "frame.cuh"
 #include "kernels.h"
+#include "enc_frame.cuh"
 #include <atomic>
 #include <cuda_fp16.h>
 #include <cmath>
@@ -317,6 +318,7 @@ void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {
     if (h.lpf.epf_iters >= 2) { k_epf<2><<<grid, blk, 0, st>>>(d, a, b); CountLaunch(); std::swap(a, b); }
   }
 }
+void LaunchGaborishPlanes(const DFrame* d, const DFrame& h, const float* src, float* dst, cudaStream_t st) { dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8); k_gaborish<<<grid, blk, 0, st>>>(d, src, dst); CountLaunch(); }
 const float* FilteredPlanes(const DFrame& h) { int n = (h.lpf.gab ? 1 : 0) + (h.lpf.epf_iters == 3 ? 3 : int(h.lpf.epf_iters)); return (n & 1) ? h.xyb_tmp : h.xyb; }
 void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st) {
   for (uint32_t i = h.num_rct; i-- > 0;) { const DModChannel& c0 = h.mod_ch[h.rct_begin[i]]; size_t n = size_t(c0.w) * c0.h; k_inverse_rct<<<unsigned((n + 255) / 256), 256, 0, st>>>(d, h.rct_begin[i], h.rct_type[i]); CountLaunch(); }

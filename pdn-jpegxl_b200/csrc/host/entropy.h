@@ -416,15 +416,20 @@ inline void WritePrefixCode(BitWriter& bw, const std::vector<uint8_t>& len, uint
 }
 }  // namespace detail
 
-// Builds clustered histograms + tables from all token streams that will share this code.
+// Builds clustered histograms + tables from per-context token-symbol histograms h[ctx][symbol].
+inline EncCode BuildCodeFromHist(std::vector<std::vector<uint64_t>> h, size_t num_ctx, const EncOptions& opt);
+// Builds them from all token streams that will share this code.
 inline EncCode BuildCode(const std::vector<const std::vector<Token>*>& streams, size_t num_ctx, const EncOptions& opt) {
-  EncCode e; e.num_ctx = num_ctx; e.use_prefix = opt.use_prefix;
   std::vector<std::vector<uint64_t>> h(num_ctx);
-  uint32_t max_tok = 0;
   for (auto* s : streams) for (const Token& t : *s) {
     uint32_t tok, nb, bits; HybridEncode(opt.cfg, t.value, &tok, &nb, &bits);
-    JXLG_CHECK(t.ctx < num_ctx, "token ctx"); auto& hh = h[t.ctx]; if (hh.size() <= tok) hh.resize(tok + 1, 0); hh[tok]++; max_tok = std::max(max_tok, tok);
+    JXLG_CHECK(t.ctx < num_ctx, "token ctx"); auto& hh = h[t.ctx]; if (hh.size() <= tok) hh.resize(tok + 1, 0); hh[tok]++;
   }
+  return BuildCodeFromHist(std::move(h), num_ctx, opt);
+}
+inline EncCode BuildCodeFromHist(std::vector<std::vector<uint64_t>> h, size_t num_ctx, const EncOptions& opt) {
+  EncCode e; e.num_ctx = num_ctx; e.use_prefix = opt.use_prefix; h.resize(num_ctx);
+  uint32_t max_tok = 0; for (auto& hh : h) { while (!hh.empty() && hh.back() == 0) hh.pop_back(); if (!hh.empty()) max_tok = std::max<uint32_t>(max_tok, uint32_t(hh.size() - 1)); }
   // greedy clustering by entropy cost increase
   std::vector<std::vector<uint64_t>> ch; e.ctx_map.assign(num_ctx, 0);
   std::vector<size_t> order(num_ctx); for (size_t i = 0; i < num_ctx; i++) order[i] = i;
