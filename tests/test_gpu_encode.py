@@ -69,8 +69,10 @@ def test_progress_sequence_and_cancel(gpu, oracle):
     seen = []
     out = io.BytesIO()
     gpu.JpegXLSave.Save(_bgra(img), out, progress_callback=lambda p: (seen.append(p), True)[1])
+    # 0,5,15,20,25, then +5 per output buffer starting from 30 (capped at 90), 95 before the flush, buffers continue after it
     assert seen[:5] == [0, 5, 15, 20, 25] and seen[5] == 35 and 95 in seen and max(seen) == 95
-    assert all(b >= a or b == 95 for a, b in zip(seen, seen[1:]))
+    rest = [p for p in seen[5:] if p != 95]
+    assert all(b >= a for a, b in zip(rest, rest[1:])) and max(rest) <= 90
     with pytest.raises(gpu.OperationCanceledException):
         gpu.JpegXLSave.Save(_bgra(img), io.BytesIO(), progress_callback=lambda p: p < 20)
 
