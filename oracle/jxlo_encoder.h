@@ -45,7 +45,7 @@ struct TreeBuilder {
   }
 };
 inline Tree MakeVarDctTree(uint32_t nlf, int num_ec) {
-  TreeBuilder b; int sharp = b.Leaf(1), hfmul = b.Leaf(1), strat = b.Leaf(1), cflc = b.Leaf(5);
+  TreeBuilder b; int sharp = b.Leaf(0), hfmul = b.Leaf(0), strat = b.Leaf(0), cflc = b.Leaf(0);   // Zero predictor: constant maps decode as zero-entropy rows
   int blockinfo = b.Split(2, 0, hfmul, strat); int hfmeta = b.Split(0, 1, b.Split(0, 2, sharp, blockinfo), cflc);
   int groups = num_ec > 0 ? b.Channels(num_ec, 0, 5) : b.Leaf(5);
   int upper = b.Split(1, int32_t(3 * nlf + 17), groups, hfmeta);

@@ -133,8 +133,13 @@ struct Blob {
     DCode d; memset(&d, 0, sizeof(d)); d.num_ctx = uint32_t(c.ctx_map.size()); d.num_clusters = uint32_t(c.cfg.size()); d.log_alpha = uint32_t(c.log_alpha); d.use_prefix = c.use_prefix;
     d.ctx_map_off = Add(c.ctx_map.data(), c.ctx_map.size()); std::vector<DHybrid> cfg(c.cfg.size()); for (size_t i = 0; i < cfg.size(); i++) cfg[i] = DHybrid{uint8_t(c.cfg[i].split_exp), uint8_t(c.cfg[i].msb), uint8_t(c.cfg[i].lsb), 0};
     d.cfg_off = Add(cfg.data(), cfg.size() * sizeof(DHybrid));
+    std::vector<uint32_t> info(c.cfg.size());
+    for (size_t k = 0; k < c.cfg.size(); k++) { uint32_t cs = 0xffff;
+      if (!c.use_prefix) { for (size_t sy = 0; sy < c.ans[k].freq.size(); sy++) if (c.ans[k].freq[sy] == kAnsTab) cs = uint32_t(sy); } else if (c.prefix[k].max_len == 0) cs = uint32_t(c.prefix[k].single);
+      info[k] = c.cfg[k].split_exp | (c.cfg[k].msb << 8) | (c.cfg[k].lsb << 12) | (cs << 16); }
+    d.info_off = Add(info.data(), info.size() * 4);
     if (!c.use_prefix) {
-      size_t ts = size_t(1) << c.log_alpha; std::vector<uint64_t> al(c.ans.size() * ts);
+      size_t ts = size_t(1) << c.log_alpha; std::vector<DAlias> al(c.ans.size() * ts);
       for (size_t k = 0; k < c.ans.size(); k++) { const AnsTable& t = c.ans[k]; for (size_t i = 0; i < ts; i++) al[k * ts + i] = PackAlias(t.cutoff[i], t.right[i], t.off1[i], t.freq[i], t.freq[t.right[i]]); }
       d.alias_off = Add(al.data(), al.size() * 8);
     } else {
@@ -224,7 +229,7 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
   for (size_t i = 0; i < m.ec.size(); i++) { JXLG_CHECK(fh.ec_upsampling[i] == 1, "upsampling is not supported"); uint32_t s = m.ec[i].dim_shift; ch.push_back(DModChannel{DivCeil(fh.xsize, 1u << s), DivCeil(fh.ysize, 1u << s), s, s, 0}); }
   JXLG_CHECK(ch.size() <= 8, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size()); h.num_rct = 0; h.first_group_channel = 0; global_has_data = false;
   uint64_t off = 0; for (auto& c : ch) { c.plane_off = off; off += uint64_t(c.w) * c.h; } for (size_t i = 0; i < ch.size(); i++) h.mod_ch[i] = ch[i];
-  h.mod_bitdepth = m.bd.bits;
+  h.mod_bitdepth = m.bd.bits; { uint32_t mb = m.bd.bits; for (const auto& e : m.ec) mb = std::max(mb, e.bd.bits); h.mod_wide = (mb > 20 || !m.modular_16bit) ? 1 : 0; }
   if (!ch.empty()) {
     gheader = ReadGroupHeader(br);
     for (const Transform& t : gheader.transforms) { JXLG_CHECK(t.id == 0, "palette / squeeze transforms are not supported by the GPU decoder yet"); JXLG_CHECK(t.begin_c + 3 <= ch.size() && h.num_rct < 4, "RCT channel range");
@@ -341,16 +346,22 @@ void DecodeJob::Run(const DecodeRequest& req) {
   BitReader lfg(cs.data() + frame_off + toc.offset[0], toc.size[0]); ParseLfGlobal(lfg); JXLG_CHECK(!lfg.overrun, "LfGlobal truncated");
   uint64_t base_bits = uint64_t(frame_off) * 8; uint64_t after_lfglobal = (uint64_t(frame_off) + toc.offset[0]) * 8 + lfg.pos;
   if (!single && vardct) { BitReader hb(cs.data() + frame_off + toc.offset[1 + h.num_lf_groups], toc.size[1 + h.num_lf_groups]); ParseHfGlobal(hb); JXLG_CHECK(!hb.overrun, "HfGlobal truncated"); }
+  {  // shared-memory budgets for the staged tables (host knows the exact sizes)
+    auto code_bytes = [](const DCode& c) { return ((c.num_clusters * 4 + 15) & ~15u) + ((c.num_ctx + 15) & ~15u) + (c.use_prefix ? 0u : (((c.num_clusters << c.log_alpha) * 8 + 15) & ~15u)); };
+    uint32_t modb = has_tree ? code_bytes(h.mod_code) + ((h.tree_size * 16 + 15) & ~15u) : 0, acb = 0;
+    if (vardct && !single) for (uint32_t p = 0; p < h.num_passes; p++) acb = std::max(acb, code_bytes(h.ac_code[p]));
+    h.lf_smem = std::min<uint32_t>(modb + 64, 96 * 1024); h.ac_smem = std::min<uint32_t>(acb + (h.num_mod_channels > h.first_group_channel ? modb : 0) + 64, 96 * 1024); if (single) h.ac_smem = 96 * 1024;
+  }
   std::vector<uint64_t> sec(2 * nlog + 2, 0);
   for (size_t i = 0; i < nlog; i++) { size_t t = single ? 0 : i; sec[i] = base_bits + uint64_t(toc.offset[t]) * 8; sec[nlog + i] = base_bits + uint64_t(toc.offset[t] + toc.size[t]) * 8; }
   h.sec_off = blob.Add(sec.data(), sec.size() * 8);
   AllocateAndUpload(req);
-  auto upload_blob = [&]() { if (d_blob.n < blob.b.size() + 16) d_blob.Alloc(std::max<size_t>(blob.b.size() * 2, 1 << 16)); h.blob = d_blob.as<uint8_t>(); CUDA_OK(cudaMemcpyAsync(d_blob.p, blob.b.data(), blob.b.size(), cudaMemcpyHostToDevice, stream)); UploadFrame(); };
+  auto upload_blob = [&]() { blob.b.resize((blob.b.size() + 31) / 16 * 16, 0); if (d_blob.n < blob.b.size() + 16) d_blob.Alloc(std::max<size_t>(blob.b.size() * 2, 1 << 16)); h.blob = d_blob.as<uint8_t>(); CUDA_OK(cudaMemcpyAsync(d_blob.p, blob.b.data(), blob.b.size(), cudaMemcpyHostToDevice, stream)); UploadFrame(); };
   upload_blob();
   const DFrame* d = d_frame.as<DFrame>();
   if (timed) cudaEventRecord(ev[0], stream);
   // global Modular stream
-  if (global_has_data) { LaunchModularGlobal(d, after_lfglobal, uint32_t(global_decoded), stream); CountLaunch(); }
+  if (global_has_data) { LaunchModularGlobal(d, h, after_lfglobal, uint32_t(global_decoded), stream); CountLaunch(); }
   else if (single) CUDA_OK(cudaMemcpyAsync(h.end_bitpos, &after_lfglobal, 8, cudaMemcpyHostToDevice, stream));
   if (vardct) { LaunchLfGroups(d, h, stream); CountLaunch(); }
   else if (single) { /* Modular frame, single section: LF group and HfGlobal parts are empty; groups continue where the global stream ended */ CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, h.end_bitpos, 8, cudaMemcpyDeviceToDevice, stream)); }

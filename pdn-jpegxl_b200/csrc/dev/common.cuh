@@ -18,10 +18,13 @@ struct DCode {
   uint32_t cfg_off;       // DHybrid[num_clusters]
   uint32_t alias_off;     // uint64[num_clusters << log_alpha]            (ANS)
   uint32_t prefix_off;    // uint32[2*num_clusters] {lut byte offset, max_len} (prefix)
+  uint32_t info_off;      // uint32[num_clusters]: split_exp[0,8) | msb[8,12) | lsb[12,16) | const symbol[16,32) (0xffff: none). A constant
+                          // symbol is the only symbol of a zero-entropy cluster: decoding it reads no bits and leaves the ANS state unchanged.
 };
-// alias entry: cutoff[0,13) right[13,21) off1[21,34) freq0[34,47) freq1[47,60)
-__host__ __device__ inline uint64_t PackAlias(uint32_t cutoff, uint32_t right, uint32_t off1, uint32_t freq0, uint32_t freq1) {
-  return uint64_t(cutoff) | (uint64_t(right) << 13) | (uint64_t(off1) << 21) | (uint64_t(freq0) << 34) | (uint64_t(freq1) << 47);
+// alias entry as two 32-bit words: x = cutoff[0,8) | right[8,16) | off1[16,32); y = freq0[0,16) | freq1[16,32)
+struct DAlias { uint32_t x, y; };
+__host__ __device__ inline DAlias PackAlias(uint32_t cutoff, uint32_t right, uint32_t off1, uint32_t freq0, uint32_t freq1) {
+  DAlias a; a.x = cutoff | (right << 8) | (off1 << 16); a.y = freq0 | (freq1 << 16); return a;
 }
 
 enum DevError : uint32_t {
@@ -32,28 +35,46 @@ enum DevError : uint32_t {
 #ifdef __CUDACC__
 __device__ __forceinline__ void SetError(uint32_t* err, uint32_t code) { if (code) atomicCAS(err, 0u, code); }
 
+// 32-bit-lane bit reader: `lo`/`hi` hold 64 buffered bits, `used` (< 32) bits of `lo` are consumed, `nxt` is prefetched.
 struct BitRd {
-  const uint32_t* words; uint64_t buf; int n; uint32_t nxt; uint32_t widx;   // widx: index of the next word to prefetch
-  __device__ __forceinline__ void Init(const uint8_t* base16, uint64_t bitpos) {   // base16: 4-byte aligned buffer start
-    words = reinterpret_cast<const uint32_t*>(base16); widx = uint32_t(bitpos >> 5); int drop = int(bitpos & 31);
-    uint32_t w0 = __ldg(words + widx); uint32_t w1 = __ldg(words + widx + 1); nxt = __ldg(words + widx + 2); widx += 3;
-    buf = (uint64_t(w0) | (uint64_t(w1) << 32)) >> drop; n = 64 - drop;
+  const uint32_t* words; uint32_t lo, hi, nxt, used, widx;   // widx: index of the next word to prefetch
+  __device__ __forceinline__ void Init(const uint8_t* base4, uint64_t bitpos) {   // base4: 4-byte aligned buffer start
+    words = reinterpret_cast<const uint32_t*>(base4); widx = uint32_t(bitpos >> 5); used = uint32_t(bitpos & 31);
+    lo = __ldg(words + widx); hi = __ldg(words + widx + 1); nxt = __ldg(words + widx + 2); widx += 3;
   }
-  __device__ __forceinline__ void Refill() { if (n <= 32) { buf |= uint64_t(nxt) << n; n += 32; nxt = __ldg(words + widx); widx++; } }
-  __device__ __forceinline__ uint32_t Peek(int nb) { Refill(); return uint32_t(buf) & ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u)); }
-  __device__ __forceinline__ void Skip(int nb) { buf >>= nb; n -= nb; }
-  __device__ __forceinline__ uint32_t Read(int nb) { if (nb == 0) return 0; uint32_t v = Peek(nb); Skip(nb); return v; }
-  __device__ __forceinline__ uint64_t BitPos() const { return uint64_t(widx - 1) * 32 - uint64_t(n); }   // absolute bit position consumed so far
+  __device__ __forceinline__ uint32_t Peek32() const { return __funnelshift_r(lo, hi, used); }
+  __device__ __forceinline__ uint32_t Peek(int nb) const { uint32_t v = Peek32(); return nb >= 32 ? v : (v & ((1u << nb) - 1u)); }
+  __device__ __forceinline__ void Skip(int nb) { used += uint32_t(nb); if (used >= 32) { used -= 32; lo = hi; hi = nxt; nxt = __ldg(words + widx); widx++; } }   // nb <= 32
+  __device__ __forceinline__ uint32_t Read(int nb) { uint32_t v = Peek(nb); Skip(nb); return v; }
+  __device__ __forceinline__ uint64_t BitPos() const { return uint64_t(widx - 3) * 32 + used; }   // absolute bit position consumed so far
   __device__ __forceinline__ uint32_t ReadU32(int n0, uint32_t o0, int n1, uint32_t o1, int n2, uint32_t o2, int n3, uint32_t o3) {
     uint32_t sel = Read(2); int nb = sel == 0 ? n0 : sel == 1 ? n1 : sel == 2 ? n2 : n3; uint32_t off = sel == 0 ? o0 : sel == 1 ? o1 : sel == 2 ? o2 : o3; return Read(nb) + off;
   }
 };
 
+// Cooperative copy of a read-only table into the CTA's dynamic shared memory; when it does not fit it stays in global
+// memory (generic pointers work for both). Every thread computes the same pointer; caller must __syncthreads() after.
+__device__ __forceinline__ const void* StageBytes(uint8_t* dsm, uint32_t cap, uint32_t& used, const void* src, uint32_t bytes, int tid, int nt) {
+  uint32_t need = (bytes + 15u) & ~15u; if (bytes == 0 || used + need > cap) return src;
+  uint32_t* d = reinterpret_cast<uint32_t*>(dsm + used); const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+  for (uint32_t i = tid; i < need / 4; i += nt) d[i] = s[i];
+  used += need; return d;
+}
+
 struct CodeView {   // resolved pointers (generic address space: shared or global)
-  const uint8_t* ctx_map; const DHybrid* cfg; const uint64_t* alias; const uint32_t* prefix_desc; const uint8_t* blob; uint32_t log_alpha, use_prefix;
+  const uint8_t* ctx_map; const DHybrid* cfg; const DAlias* alias; const uint32_t* prefix_desc; const uint32_t* info; const uint8_t* blob; uint32_t log_alpha, use_prefix, num_ctx, num_clusters;
   __device__ __forceinline__ void Bind(const uint8_t* blob_, const DCode& c) {
-    blob = blob_; ctx_map = blob_ + c.ctx_map_off; cfg = reinterpret_cast<const DHybrid*>(blob_ + c.cfg_off); alias = reinterpret_cast<const uint64_t*>(blob_ + c.alias_off);
-    prefix_desc = reinterpret_cast<const uint32_t*>(blob_ + c.prefix_off); log_alpha = c.log_alpha; use_prefix = c.use_prefix;
+    blob = blob_; ctx_map = blob_ + c.ctx_map_off; cfg = reinterpret_cast<const DHybrid*>(blob_ + c.cfg_off); alias = reinterpret_cast<const DAlias*>(blob_ + c.alias_off);
+    prefix_desc = reinterpret_cast<const uint32_t*>(blob_ + c.prefix_off); info = reinterpret_cast<const uint32_t*>(blob_ + c.info_off); log_alpha = c.log_alpha; use_prefix = c.use_prefix; num_ctx = c.num_ctx; num_clusters = c.num_clusters;
+  }
+  // true when every hot table sits in shared memory (lets the compiler emit LDS instead of generic loads)
+  __device__ __forceinline__ bool AllShared() const { return __isShared(ctx_map) && __isShared(info) && (use_prefix || __isShared(alias)); }
+  __device__ __forceinline__ void AssumeShared() const { __builtin_assume(__isShared(ctx_map)); __builtin_assume(__isShared(info)); __builtin_assume(__isShared(alias)); }
+  // stage the hot tables (cluster map, hybrid configs, constant flags, alias tables) into shared memory
+  __device__ __forceinline__ void Stage(uint8_t* dsm, uint32_t cap, uint32_t& used, int tid, int nt) {
+    info = static_cast<const uint32_t*>(StageBytes(dsm, cap, used, info, num_clusters * 4, tid, nt));
+    ctx_map = static_cast<const uint8_t*>(StageBytes(dsm, cap, used, ctx_map, num_ctx, tid, nt));
+    if (!use_prefix) alias = static_cast<const DAlias*>(StageBytes(dsm, cap, used, alias, (num_clusters << log_alpha) * 8, tid, nt));
   }
 };
 
@@ -66,11 +87,11 @@ struct SymReader {
       if (max_len == 0) return lut[0] >> 4;
       uint32_t e = lut[br.Peek(int(max_len))]; uint32_t len = e & 15; if (len == 0) { err = kErrPrefix; len = 1; } br.Skip(int(len)); return e >> 4;
     }
-    uint32_t log_entry = 12 - cv.log_alpha; uint32_t idx = state & 0xfff, i = idx >> log_entry, pos = idx & ((1u << log_entry) - 1);
-    uint64_t e = cv.alias[(cluster << cv.log_alpha) + i];
-    bool g = pos >= uint32_t(e & 0x1fff); uint32_t sym = g ? uint32_t(e >> 13) & 0xff : i; uint32_t off = (g ? uint32_t(e >> 21) & 0x1fff : 0u) + pos; uint32_t freq = g ? uint32_t(e >> 47) & 0x1fff : uint32_t(e >> 34) & 0x1fff;
-    state = freq * (state >> 12) + off;
-    if (state < 65536u) state = (state << 16) | br.Read(16);
+    const uint32_t log_entry = 12 - cv.log_alpha, idx = state & 0xfff, i = idx >> log_entry, pos = idx & ((1u << log_entry) - 1);
+    const DAlias e = cv.alias[(cluster << cv.log_alpha) + i];
+    const bool g = pos >= (e.x & 0xffu); const uint32_t sym = g ? ((e.x >> 8) & 0xffu) : i, off = g ? (e.x >> 16) : 0u, freq = g ? (e.y >> 16) : (e.y & 0xffffu);
+    state = freq * (state >> 12) + off + pos;
+    if (state < 65536u) { state = (state << 16) | br.Peek(16); br.Skip(16); }
     return sym;
   }
   __device__ __forceinline__ uint32_t Hybrid(const DHybrid h, uint32_t t) {
@@ -80,7 +101,12 @@ struct SymReader {
     uint32_t low = t & ((1u << h.lsb) - 1); t >>= h.lsb; uint32_t hi = (t & ((1u << h.msb) - 1)) | (1u << h.msb);
     return (((hi << nb) | br.Read(int(nb))) << h.lsb) | low;
   }
-  __device__ __forceinline__ uint32_t Read(const CodeView& cv, uint32_t ctx) { uint32_t cl = cv.ctx_map[ctx]; uint32_t t = ReadToken(cv, cl); return Hybrid(cv.cfg[cl], t); }
+  __device__ __forceinline__ uint32_t ReadCluster(const CodeView& cv, uint32_t cl) {
+    const uint32_t info = cv.info[cl]; uint32_t t = info >> 16; if (t == 0xffffu) t = ReadToken(cv, cl);
+    if (t < (1u << (info & 0xff))) return t;
+    DHybrid h; h.split_exp = uint8_t(info & 0xff); h.msb = uint8_t((info >> 8) & 15); h.lsb = uint8_t((info >> 12) & 15); return Hybrid(h, t);
+  }
+  __device__ __forceinline__ uint32_t Read(const CodeView& cv, uint32_t ctx) { return ReadCluster(cv, cv.ctx_map[ctx]); }
   __device__ __forceinline__ bool FinalOk(const CodeView& cv) const { return cv.use_prefix || state == 0x130000u; }
 };
 

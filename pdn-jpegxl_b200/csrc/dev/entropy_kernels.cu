@@ -31,20 +31,26 @@ __device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f) {
   return true;
 }
 
-__device__ void BindModDecoder(ModDecoder& md, const DFrame& f) {
-  md.cv.Bind(f.blob, f.mod_code); md.tree = reinterpret_cast<const DTreeNode*>(f.blob + f.tree_off); md.uses_wp = f.uses_wp != 0; md.rd.err = 0;
+__device__ void BindModDecoder(ModDecoder& md, const DFrame& f, ChanLut* lut) {
+  md.cv.Bind(f.blob, f.mod_code); md.tree = reinterpret_cast<const DTreeNode*>(f.blob + f.tree_off); md.uses_wp = f.uses_wp != 0; md.wide = f.mod_wide != 0; md.rd.err = 0; md.lut = lut;
+}
+// Stages the Modular code tables and the MA tree into shared memory (all threads of the CTA call this, then sync).
+__device__ void StageModDecoder(ModDecoder& md, const DFrame& f, uint8_t* dsm, uint32_t cap, uint32_t& used, int tid, int nt) {
+  if (!f.has_tree) return;
+  md.cv.Stage(dsm, cap, used, tid, nt); md.tree = static_cast<const DTreeNode*>(StageBytes(dsm, cap, used, md.tree, f.tree_size * 16, tid, nt));
 }
 
-__global__ void __launch_bounds__(32) k_lf_group(const DFrame* fp) {
-  const DFrame& f = *fp; const int g = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame f) {
+  const int g = blockIdx.x, lane = threadIdx.x;
   const int gx = g % int(f.xlfgroups), gy = g / int(f.xlfgroups), cx0 = gx * 256, cy0 = gy * 256;
   const int w = min(256, int(f.xb) - cx0), h = min(256, int(f.yb) - cy0), tw = (w + 7) / 8, th = (h + 7) / 8;
   int32_t* scratch = f.hfmeta_scratch + size_t(g) * kHfMetaScratchInts;
   int32_t* s_cflx = scratch; int32_t* s_cflb = scratch + 1024; int32_t* s_info = scratch + 2048; int32_t* s_sharp = scratch + 2048 + 2 * 65536;
-  __shared__ uint32_t sh_nb, sh_ok;
+  __shared__ uint32_t sh_nb, sh_ok; __shared__ ChanLut sh_lut; extern __shared__ __align__(16) uint8_t dsm[];
+  ModDecoder md; BindModDecoder(md, f, &sh_lut); { uint32_t used = 0; StageModDecoder(md, f, dsm, f.lf_smem, used, lane, 32); }
+  __syncthreads();
   if (lane == 0) {
     sh_ok = 0; sh_nb = 0;
-    ModDecoder md; BindModDecoder(md, f);
     const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
     uint64_t start = single ? f.end_bitpos[0] : sec[1 + g]; uint64_t end = single ? sec[nsec] : sec[nsec + 1 + g];
     md.rd.br.Init(f.comp, start);
@@ -83,8 +89,13 @@ __global__ void __launch_bounds__(32) k_lf_group(const DFrame* fp) {
   if (bad) SetError(f.err, bad);
   __syncwarp();
   // ---- varblock placement: raster scan, each block at the first uncovered cell (A.8 LfGroup)
-  if (lane == 0) {
-    uint32_t nb = sh_nb, num = 0, e = 0;
+  const uint32_t nb = sh_nb; bool all1 = nb == uint32_t(w * h);
+  if (all1) for (uint32_t i = lane; i < nb; i += 32) { int32_t s = s_info[i]; if (s < 0 || s >= 27 || CoveredX(s) != 1 || CoveredY(s) != 1) all1 = false; }
+  all1 = __all_sync(0xffffffffu, all1);
+  if (all1) {   // common case (only 8x8 strategies): block i sits in cell i, fully parallel
+    for (uint32_t i = lane; i < nb; i += 32) { size_t o = size_t(cy0 + i / w) * f.xb + cx0 + i % w; f.acs[o] = uint8_t(s_info[i] | 0x80); f.hf_mul_m1[o] = uint8_t(max(0, min(255, s_info[nb + i]))); }
+  } else if (lane == 0) {
+    uint32_t num = 0, e = 0;
     for (int y = 0; y < h && !e; y++) for (int x = 0; x < w; x++) {
       size_t o = size_t(cy0 + y) * f.xb + cx0 + x; if (f.acs[o] != 0xFF) continue;
       if (num >= nb) { e = kErrHfMeta; break; }
@@ -141,11 +152,61 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
 }
 
-__global__ void __launch_bounds__(128) k_ac_group(const DFrame* fp, int pass) {
-  const DFrame& f = *fp; const int g = blockIdx.x, tid = threadIdx.x;
+// AC coefficients of one 256x256 group and pass (A.8 "PassGroup AC decode"). kSmem: every code table is in shared memory.
+template <bool kSmem>
+__device__ __noinline__ uint32_t DecodeAcCoeffs(const DFrame& f, SymReader& rd_io, const CodeView& cv_in, int pass, int g, int w, int h,
+                                                 uint8_t (*s_nz)[32 * 32], const uint8_t* s_acs, const uint8_t* s_qf, const uint8_t* s_lfidx) {
+  CodeView cv = cv_in; if (kSmem) cv.AssumeShared();
+  SymReader rd = rd_io;   // keep the reader state in registers (the by-reference copy lives in local memory)
+  struct WriteBack { SymReader& dst; SymReader& src; __device__ ~WriteBack() { dst = src; } } wb{rd_io, rd};
+  uint32_t err = 0, bad_range = 0;
+  const uint32_t preset = rd.br.Read(CeilLog2Dev(f.num_hf_presets)); if (preset >= f.num_hf_presets) return kErrPreset;
+  rd.Init(cv);
+  const uint32_t nbctx = f.nb_block_ctx, ctx_offset = 495 * nbctx * preset, shift = f.pass_shift[pass], n_qf_thr = f.n_qf_thr, num_lf_ctxs = f.num_lf_ctxs;
+  const uint8_t* bmap = f.blob + f.bctx_map_off; int16_t* coef = f.coeffs + size_t(g) * 3 * 65536;
+  for (int by = 0; by < h; by++) for (int bx = 0; bx < w; bx++) {
+    const int cell = by * 32 + bx; const uint8_t a = s_acs[cell]; if (!(a & 0x80)) continue;
+    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); const uint32_t covered = uint32_t(bw * bh), log2c = 31 - __clz(covered), size = covered * 64; const int ord = StrategyOrder(s);
+    const uint32_t qf = uint32_t(s_qf[cell]) + 1; uint32_t qf_idx = 0; for (uint32_t t = 0; t < n_qf_thr; t++) qf_idx += qf > f.qf_thr[t];
+    const uint32_t lbw = 31 - __clz(uint32_t(bw)), bwm = uint32_t(bw) - 1;
+#pragma unroll 1
+    for (int ci = 0; ci < 3; ci++) {
+      const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; uint8_t* nzrow = s_nz[c];
+      uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : nzrow[cell - 32]; else if (by == 0) pred = nzrow[cell - 1]; else pred = (uint32_t(nzrow[cell - 32]) + nzrow[cell - 1] + 1) >> 1;
+      uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u; idx = idx * 13 + ord; idx = idx * (n_qf_thr + 1) + qf_idx; idx = idx * num_lf_ctxs + s_lfidx[cell]; const uint32_t bctx = bmap[idx];
+      uint32_t nzb = pred > 64 ? 64 : pred; nzb = nzb < 8 ? nzb : (nzb >= 64 ? 36 : 4 + nzb / 2);
+      uint32_t nz = rd.Read(cv, ctx_offset + nzb * nbctx + bctx);
+      if (nz + covered > size) return kErrTooManyNz;
+      { const uint8_t v = uint8_t((nz + covered - 1) >> log2c); if (covered == 1) nzrow[cell] = v; else for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) nzrow[cell + iy * 32 + ix] = v; }
+      if (nz == 0) continue;
+      const uint32_t* order = reinterpret_cast<const uint32_t*>(f.blob + f.order_off[pass][ord * 3 + c]);
+      const uint32_t histo = ctx_offset + nbctx * 37 + 458 * bctx; uint32_t prev = nz > size / 16 ? 0 : 1; int16_t* cc = coef + c * 65536 + cell * 64;
+      uint32_t nzctx = uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) * 2 + histo; uint32_t k = covered;
+      do {
+        const uint32_t u = rd.Read(cv, nzctx + uint32_t(kFreqCtx[k >> log2c]) * 2 + prev); prev = u != 0;
+        if (u) {
+          int32_t v = int32_t(uint32_t(UnpackSignedDev(u)) << shift); const uint32_t p = order[k], j = p >> 6; const uint32_t addr = (((j >> lbw) << 5) + (j & bwm)) * 64 + (p & 63);
+          if (pass) v += cc[addr]; bad_range |= uint32_t(v + 32768) >> 16; cc[addr] = int16_t(v); nz--; nzctx = uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) * 2 + histo;
+        }
+        k++;
+      } while (k < size && nz != 0);
+      if (nz != 0) return kErrNzMismatch;
+    }
+  }
+  if (!rd.FinalOk(cv)) err = kErrAnsFinal;
+  if (!err && bad_range) err = kErrCoefRange;
+  if (!err) err = rd.err;
+  return err;
+}
+
+__global__ void __launch_bounds__(128) k_ac_group(const __grid_constant__ DFrame f, int pass) {
+  const int g = blockIdx.x, tid = threadIdx.x;
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups);
-  __shared__ uint8_t s_nz[3][32 * 32]; __shared__ uint8_t s_acs[32 * 32], s_qf[32 * 32], s_lfidx[32 * 32];
+  __shared__ uint8_t s_nz[3][32 * 32]; __shared__ uint8_t s_acs[32 * 32], s_qf[32 * 32], s_lfidx[32 * 32]; __shared__ ChanLut sh_lut; extern __shared__ __align__(16) uint8_t dsm[];
   const bool vardct = f.encoding == 0; int w = 0, h = 0;
+  ModDecoder md; BindModDecoder(md, f, &sh_lut); CodeView cv; uint32_t used = 0;
+  if (vardct) { cv.Bind(f.blob, f.ac_code[pass]); cv.Stage(dsm, f.ac_smem, used, tid, 128); }
+  if (f.num_mod_channels > f.first_group_channel) StageModDecoder(md, f, dsm, f.ac_smem, used, tid, 128);
   if (vardct) {
     const int cx0 = gx * 32, cy0 = gy * 32; w = min(32, int(f.xb) - cx0); h = min(32, int(f.yb) - cy0);
     if (pass == 0) { int4* z = reinterpret_cast<int4*>(f.coeffs + size_t(g) * 3 * 65536); int4 zero = make_int4(0, 0, 0, 0); for (int i = tid; i < 3 * 65536 * 2 / 16; i += 128) z[i] = zero; }
@@ -157,51 +218,21 @@ __global__ void __launch_bounds__(128) k_ac_group(const DFrame* fp, int pass) {
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
-  ModDecoder md; BindModDecoder(md, f); md.rd.br.Init(f.comp, start);
+  md.rd.br.Init(f.comp, start);
   uint32_t err = 0;
-  if (vardct) {
-    CodeView cv; cv.Bind(f.blob, f.ac_code[pass]); SymReader& rd = md.rd;
-    uint32_t preset = rd.br.Read(CeilLog2Dev(f.num_hf_presets)); if (preset >= f.num_hf_presets) err = kErrPreset;
-    if (!err) {
-      rd.Init(cv);
-      const uint32_t nbctx = f.nb_block_ctx, ctx_offset = 495 * nbctx * preset, shift = f.pass_shift[pass];
-      const uint8_t* bmap = f.blob + f.bctx_map_off; int16_t* coef = f.coeffs + size_t(g) * 3 * 65536;
-      for (int by = 0; by < h && !err; by++) for (int bx = 0; bx < w && !err; bx++) {
-        const int cell = by * 32 + bx; const uint8_t a = s_acs[cell]; if (!(a & 0x80)) continue;
-        const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); const uint32_t covered = uint32_t(bw * bh), log2c = 31 - __clz(covered), size = covered * 64; const int ord = StrategyOrder(s);
-        const uint32_t qf = uint32_t(s_qf[cell]) + 1; uint32_t qf_idx = 0; for (uint32_t t = 0; t < f.n_qf_thr; t++) qf_idx += qf > f.qf_thr[t];
-        for (int ci = 0; ci < 3; ci++) {
-          const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2;
-          uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : s_nz[c][cell - 32]; else if (by == 0) pred = s_nz[c][cell - 1]; else pred = (uint32_t(s_nz[c][cell - 32]) + s_nz[c][cell - 1] + 1) >> 1;
-          uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u; idx = idx * 13 + ord; idx = idx * (f.n_qf_thr + 1) + qf_idx; idx = idx * f.num_lf_ctxs + s_lfidx[cell]; const uint32_t bctx = bmap[idx];
-          uint32_t nzb = pred > 64 ? 64 : pred; nzb = nzb < 8 ? nzb : (nzb >= 64 ? 36 : 4 + nzb / 2);
-          uint32_t nz = rd.Read(cv, ctx_offset + nzb * nbctx + bctx);
-          if (nz + covered > size) { err = kErrTooManyNz; break; }
-          { uint8_t v = uint8_t((nz + covered - 1) >> log2c); for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) s_nz[c][cell + iy * 32 + ix] = v; }
-          const uint32_t* order = reinterpret_cast<const uint32_t*>(f.blob + f.order_off[pass][ord * 3 + c]);
-          const uint32_t histo = ctx_offset + nbctx * 37 + 458 * bctx; uint32_t prev = nz > size / 16 ? 0 : 1; int16_t* cc = coef + c * 65536;
-          for (uint32_t k = covered; k < size && nz != 0; k++) {
-            uint32_t zctx = (uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) + kFreqCtx[k >> log2c]) * 2 + prev;
-            uint32_t u = rd.Read(cv, histo + zctx);
-            if (u) { int32_t v = int32_t(uint32_t(UnpackSignedDev(u)) << shift); uint32_t addr = CoefAddr(by, bx, bw, order[k]);
-              if (pass) v += cc[addr]; if (v > 32767 || v < -32768) err = kErrCoefRange; cc[addr] = int16_t(v); prev = 1; nz--; } else prev = 0;
-          }
-          if (nz != 0) { err = kErrNzMismatch; break; }
-        }
-      }
-      if (!err && !rd.FinalOk(cv)) err = kErrAnsFinal;
-      if (!err) err = rd.err;
-    }
-  }
+  if (vardct) err = cv.AllShared() ? DecodeAcCoeffs<true>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx) : DecodeAcCoeffs<false>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx);
   if (!err) { bool need_init = true; md.rd.err = 0; DecodeModularGroupDev(md, f, g, pass, &need_init); err = md.rd.err; }
   uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
   SetError(f.err, err);
 }
 
 // Global Modular stream (channels small enough to live in the LfGlobal section), decoded by one thread.
-__global__ void k_modular_global(const DFrame* fp, uint64_t start_bitpos, uint32_t num_channels) {
-  const DFrame& f = *fp; if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  ModDecoder md; BindModDecoder(md, f); md.rd.br.Init(f.comp, start_bitpos);
+__global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t start_bitpos, uint32_t num_channels) {
+  __shared__ ChanLut sh_lut; extern __shared__ __align__(16) uint8_t dsm[];
+  ModDecoder md; BindModDecoder(md, f, &sh_lut); { uint32_t used = 0; StageModDecoder(md, f, dsm, f.lf_smem, used, threadIdx.x, 32); }
+  __syncthreads();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  md.rd.br.Init(f.comp, start_bitpos);
   // header already parsed on the host (it carries the global transforms); the ANS state word follows
   md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12;
   md.rd.Init(md.cv);
@@ -212,11 +243,13 @@ __global__ void k_modular_global(const DFrame* fp, uint64_t start_bitpos, uint32
   SetError(f.err, md.rd.err);
 }
 
-void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { if (h.num_lf_groups) k_lf_group<<<h.num_lf_groups, 32, 0, st>>>(d); }
+static void EnsureSmemAttr() { static bool done = false; if (done) return; done = true;
+  cudaFuncSetAttribute(k_lf_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
+void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (h.num_lf_groups) k_lf_group<<<h.num_lf_groups, 32, h.lf_smem, st>>>(h); }
 void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st) {
   size_t plane = size_t(h.xb) * h.yb; unsigned blocks = unsigned((plane + 255) / 256); k_lf_dequant<<<blocks, 256, 0, st>>>(d); if (smooth) k_lf_smooth<<<blocks, 256, 0, st>>>(d);
 }
-void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st) { k_ac_group<<<h.num_groups, 128, 0, st>>>(d, pass); }
-void LaunchModularGlobal(const DFrame* d, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st) { k_modular_global<<<1, 32, 0, st>>>(d, start_bitpos, num_channels); }
+void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st) { EnsureSmemAttr(); k_ac_group<<<h.num_groups, 128, h.ac_smem, st>>>(h, pass); }
+void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st) { EnsureSmemAttr(); k_modular_global<<<1, 32, h.lf_smem, st>>>(h, start_bitpos, num_channels); }
 
 }  // namespace jxlgpu

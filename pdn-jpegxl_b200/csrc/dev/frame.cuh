@@ -39,8 +39,9 @@ struct DFrame {
   uint32_t nb_block_ctx, num_lf_ctxs, n_lf_thr[3], n_qf_thr; int32_t lf_thr[3][15]; uint32_t qf_thr[15]; uint32_t bctx_map_off;
   uint32_t num_hf_presets; DCode mod_code; uint32_t has_tree, tree_off, tree_size, uses_wp; DCode ac_code[kMaxPasses]; uint32_t order_off[kMaxPasses][13 * 3];
   uint32_t dq_off[17];       // float[3*size] per quant table, byte offsets into blob
+  uint32_t lf_smem, ac_smem; // dynamic shared memory budgets (bytes) for the table staging of k_lf_group / k_ac_group
   uint32_t sec_off;          // uint64 sec_bitpos[nsec] then uint64 sec_bitend[nsec], byte offset into blob
-  uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8]; uint32_t mod_bitdepth; uint32_t num_rct; uint32_t rct_begin[4], rct_type[4];
+  uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8]; uint32_t mod_bitdepth, mod_wide; uint32_t num_rct; uint32_t rct_begin[4], rct_type[4];
   DLoopFilter lpf; DColor color; DOutput out;
   // device buffers
   const uint8_t* comp; const uint8_t* blob;

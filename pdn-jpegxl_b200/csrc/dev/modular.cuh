@@ -62,8 +62,102 @@ __device__ __forceinline__ void WPUpdate(WPScratch& s, const WPPred& o, long lon
   for (int i = 0; i < 4; i++) { uint32_t err = uint32_t((llabs(o.prediction[i] - val) + 3) >> 3); s.pe[i][cur + x] = err; s.pe[i][prev + x + 1] += err; }
 }
 
+// Per-channel lookup table for the common case of an MA subtree that tests a single dynamic property with uniform
+// leaves (predictor fixed, offset 0, multiplier 1): context cluster = lut[#thresholds below the property value].
+// When every threshold lies in [-128, 126] the lookup is a direct 256-entry table on the clamped property value.
+struct ChanLut { int32_t thr[32]; uint16_t cluster[33]; uint8_t direct[256]; int32_t n, prop, predictor, ok, has_direct; };
+
+// T = int32_t when all sums of four samples fit 32 bits (bit depth <= 20), else int64_t (libjxl's pixel_type_w).
+template <typename T> struct ModMath {
+  static __device__ __forceinline__ T Abs(T v) { return v < 0 ? -v : v; }
+  static __device__ __forceinline__ T PropValue(int p, int chan, int stream_id, int x, int y, T N, T W, T NW, T NE, T NN, T WW, int32_t prev_grad, int32_t wp_err, uint32_t* err) {
+    switch (p) {
+      case 0: return chan; case 1: return stream_id; case 2: return y; case 3: return x; case 4: return Abs(N); case 5: return Abs(W); case 6: return N; case 7: return W;
+      case 8: return W - prev_grad; case 9: return W + N - NW; case 10: return W - NW; case 11: return NW - N; case 12: return N - NE; case 13: return N - NN; case 14: return W - WW; case 15: return wp_err;
+      default: *err = kErrRefProps; return 0;
+    }
+  }
+  static __device__ __forceinline__ T Gradient(T N, T W, T NW) { T lo = min(W, N), hi = max(W, N); return max(lo, min(hi, W + N - NW)); }
+  static __device__ __forceinline__ T Prediction(int pr, T N, T W, T NW, T NE, T NN, T WW, T NEE, T wpred) {
+    switch (pr) {
+      case 0: return 0; case 1: return W; case 2: return N; case 3: return (W + N) / 2;
+      case 4: { T p = W + N - NW; return Abs(p - W) < Abs(p - N) ? W : N; }
+      case 5: return Gradient(N, W, NW);
+      case 6: return wpred; case 7: return NE; case 8: return NW; case 9: return WW; case 10: return (W + NW) / 2; case 11: return (N + NW) / 2; case 12: return (N + NE) / 2;
+      default: return (6 * N - 2 * NN + 7 * W + WW + NEE + 3 * NE + 8) / 16;
+    }
+  }
+};
+
 struct ModDecoder {
-  SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; uint32_t max_prop;
+  SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; ChanLut* lut;   // lut: per-decoding-thread scratch (shared memory)
+
+  // In-order walk of the subtree under `root` (<= branch first): ascending thresholds, leaves per interval.
+  __device__ void BuildLut(int root) {
+    ChanLut& L = *lut; L.ok = 0; L.n = 0; L.prop = -1; L.predictor = -1; L.has_direct = 0; int nleaf = 0;
+    int stack[40]; uint8_t state[40]; int sp = 0; stack[0] = root; state[0] = 0;
+    while (sp >= 0) {
+      DTreeNode nd = tree[stack[sp]];
+      if (nd.x < 0) {   // leaf
+        if (nd.z != 0 || nd.w != 1) return; int pr = nd.y & 15; if (L.predictor < 0) L.predictor = pr; else if (L.predictor != pr) return;
+        if (nleaf > 32) return; L.cluster[nleaf++] = cv.ctx_map[uint32_t(nd.y) >> 4]; sp--; continue;
+      }
+      if (nd.x < 2 || nd.x > 15) return; if (L.prop < 0) L.prop = nd.x; else if (L.prop != nd.x) return;
+      if (state[sp] == 0) { state[sp] = 1; if (sp >= 38) return; stack[sp + 1] = nd.w; state[sp + 1] = 0; sp++; }
+      else if (state[sp] == 1) { state[sp] = 2; if (L.n >= 32) return; L.thr[L.n++] = nd.y; stack[sp + 1] = nd.z; state[sp + 1] = 0; sp++; }
+      else sp--;
+    }
+    if (nleaf != L.n + 1) return;
+    for (int i = 1; i < L.n; i++) if (L.thr[i] < L.thr[i - 1]) return;
+    if (L.prop < 0) L.prop = 2;   // single leaf: any property, zero thresholds
+    bool direct = true; for (int i = 0; i < L.n; i++) if (L.thr[i] < -128 || L.thr[i] > 126) direct = false;
+    if (direct) { for (int v = -128; v <= 127; v++) { int cnt = 0; for (int i = 0; i < L.n; i++) cnt += v > L.thr[i]; L.direct[v + 128] = uint8_t(L.cluster[cnt]); } L.has_direct = 1; }
+    L.ok = 1;
+  }
+
+  // kMode 0: generic tree walk; 1: LUT fast path (any property/predictor); 2: LUT fast path specialised for property 8 + gradient predictor
+  template <typename T, int kMode, bool kSmem>
+  __device__ __noinline__ void DecodeRows(int root, DTreeNode n, int chan, int stream_id, int32_t* out, size_t stride, int w, int h, int32_t* wp_base) {
+    typedef ModMath<T> M; WPScratch ws; WPPred wo; wo.max_err = 0; if (this->uses_wp) { ws.Bind(wp_base, w); ws.Clear(); }
+    SymReader rd = this->rd; CodeView cv = this->cv; const DTreeNode* tree = this->tree; const DWPHeader wp = this->wp; const bool uses_wp = this->uses_wp; ChanLut* lut = this->lut;   // registers, not *this
+    struct WriteBack { SymReader& dst; SymReader& src; __device__ ~WriteBack() { dst = src; } } wb{this->rd, rd};
+    __builtin_assume(__isShared(lut)); if (kSmem) cv.AssumeShared();
+    const ChanLut& L = *lut; const int fprop = L.prop, fpred = L.predictor, fn = L.n; const bool direct = L.has_direct != 0;
+    const bool need_nn = uses_wp || kMode == 0 || (kMode == 1 && (fprop == 13 || fpred == 13));
+    for (int y = 0; y < h; y++) {
+      int32_t* cur = out + size_t(y) * stride; const int32_t* up = cur - stride; const int32_t* up2 = up - stride;
+      T W = 0, WW = 0, N, NW, NE, NEE; int32_t prev_grad = 0;
+      if (y) { N = up[0]; NE = w > 1 ? up[1] : N; NEE = w > 2 ? up[2] : NE; W = N; NW = W; WW = W; } else { N = NW = NE = NEE = 0; W = WW = 0; }
+      if (kMode == 1 && fpred == 0 && !uses_wp && (fn == 0 || fprop == 2)) {   // zero-entropy row: the context cluster has a single symbol and the predictor is Zero
+        int cnt = 0; for (int i = 0; i < fn; i++) cnt += y > L.thr[i]; const uint32_t info = cv.info[L.cluster[cnt]]; const uint32_t t = info >> 16;
+        if (t != 0xffffu && t < (1u << (info & 0xff))) { const int32_t cval = UnpackSignedDev(t); for (int x = 0; x < w; x++) cur[x] = cval; continue; }
+      }
+      for (int x = 0; x < w; x++) {
+        const T nee_next = (y && x + 3 < w) ? T(up[x + 3]) : T(0);   // issued early: independent of the symbol being decoded
+        T NN = (need_nn && y > 1) ? T(up2[x]) : N;
+        T wpred = 0; if (uses_wp) wpred = T(WPPredict(wp, ws, wo, x, y, w, N, W, NE, NW, NN));
+        uint32_t tok; T pred; int32_t offset = 0; uint32_t mult = 1;
+        if (kMode != 0) {
+          const int32_t v = kMode == 2 ? int32_t(W) - prev_grad : int32_t(M::PropValue(fprop, chan, stream_id, x, y, N, W, NW, NE, NN, WW, prev_grad, wo.max_err, &rd.err));
+          uint32_t cl;
+          if (direct) cl = L.direct[min(max(v, -128), 127) + 128]; else { int cnt = 0; for (int i = 0; i < fn; i++) cnt += v > L.thr[i]; cl = L.cluster[cnt]; }
+          tok = rd.ReadCluster(cv, cl); pred = kMode == 2 ? M::Gradient(N, W, NW) : M::Prediction(fpred, N, W, NW, NE, NN, WW, NEE, wpred);
+        } else {
+          DTreeNode nd = n;
+          while (nd.x >= 0) { int32_t v = int32_t(M::PropValue(nd.x, chan, stream_id, x, y, N, W, NW, NE, NN, WW, prev_grad, wo.max_err, &rd.err)); nd = tree[v > nd.y ? nd.z : nd.w]; }
+          tok = rd.Read(cv, uint32_t(nd.y) >> 4); pred = M::Prediction(nd.y & 15, N, W, NW, NE, NN, WW, NEE, wpred); offset = nd.z; mult = uint32_t(nd.w);
+        }
+        const int32_t val = kMode != 0 ? int32_t(T(UnpackSignedDev(tok)) + pred) : int32_t((long long)UnpackSignedDev(tok) * (long long)mult + offset + (long long)pred);
+        cur[x] = val;
+        if (uses_wp) WPUpdate(ws, wo, val, x, y);
+        prev_grad = int32_t(W + N - NW);
+        { T oldW = W; W = val; WW = x >= 1 ? oldW : W; }
+        if (y) { NW = N; N = NE; NE = NEE; NEE = (x + 3 < w) ? nee_next : NE; }
+        else { N = W; NW = W; NE = W; NEE = W; }
+      }
+    }
+  }
+
   // Decodes one channel in raster order into out[y*stride + x]. wp_base: scratch for the weighted predictor (may be null when !uses_wp).
   __device__ void DecodeChannel(int chan, int stream_id, int32_t* out, size_t stride, int w, int h, int32_t* wp_base) {
     if (w <= 0 || h <= 0) return;
@@ -71,51 +165,13 @@ struct ModDecoder {
     int root = 0; DTreeNode n = tree[0];
     while (n.x == 0 || n.x == 1) { int v = n.x == 0 ? chan : stream_id; root = v > n.y ? n.z : n.w; n = tree[root]; }
     if (uses_wp && w > int(kMaxWpWidth)) { rd.err = kErrUnsupportedStream; return; }
-    WPScratch ws; WPPred wo; if (uses_wp) { ws.Bind(wp_base, w); ws.Clear(); }
-    const bool single_leaf = n.x < 0;
-    for (int y = 0; y < h; y++) {
-      int32_t* cur = out + size_t(y) * stride; const int32_t* up = cur - stride; const int32_t* up2 = up - stride;
-      long long W = 0, WW = 0, N, NW, NE, NEE; int32_t prev_grad = 0;
-      // prime the rolling window for x = 0
-      if (y) { N = up[0]; NE = w > 1 ? up[1] : N; NEE = w > 2 ? up[2] : NE; W = N; NW = W; WW = W; } else { N = NW = NE = NEE = 0; W = WW = 0; }
-      for (int x = 0; x < w; x++) {
-        long long NN = y > 1 ? (long long)up2[x] : N;
-        long long wpred = 0; if (uses_wp) wpred = WPPredict(wp, ws, wo, x, y, w, N, W, NE, NW, NN);
-        DTreeNode nd = n;
-        if (!single_leaf) {
-          int idx = root;
-          while (nd.x >= 0) {
-            long long v;
-            switch (nd.x) {
-              case 0: v = chan; break; case 1: v = stream_id; break; case 2: v = y; break; case 3: v = x; break;
-              case 4: v = llabs(N); break; case 5: v = llabs(W); break; case 6: v = N; break; case 7: v = W; break;
-              case 8: v = W - prev_grad; break; case 9: v = W + N - NW; break; case 10: v = W - NW; break; case 11: v = NW - N; break;
-              case 12: v = N - NE; break; case 13: v = N - NN; break; case 14: v = W - WW; break; case 15: v = wo.max_err; break;
-              default: v = 0; rd.err = kErrRefProps; break;
-            }
-            idx = int32_t(v) > nd.y ? nd.z : nd.w; nd = tree[idx];
-          }
-        }
-        uint32_t tok = rd.Read(cv, uint32_t(nd.y) >> 4);
-        long long pred;
-        switch (nd.y & 15) {
-          case 0: pred = 0; break; case 1: pred = W; break; case 2: pred = N; break; case 3: pred = (W + N) / 2; break;
-          case 4: { long long p = W + N - NW; pred = llabs(p - W) < llabs(p - N) ? W : N; break; }
-          case 5: { long long lo = min(W, N), hi = max(W, N); pred = max(lo, min(hi, W + N - NW)); break; }
-          case 6: pred = wpred; break; case 7: pred = NE; break; case 8: pred = NW; break; case 9: pred = WW; break;
-          case 10: pred = (W + NW) / 2; break; case 11: pred = (N + NW) / 2; break; case 12: pred = (N + NE) / 2; break;
-          default: pred = (6 * N - 2 * NN + 7 * W + WW + NEE + 3 * NE + 8) / 16; break;
-        }
-        int32_t val = int32_t((long long)UnpackSignedDev(tok) * (long long)uint32_t(nd.w) + nd.z + pred);
-        cur[x] = val;
-        if (uses_wp) WPUpdate(ws, wo, val, x, y);
-        prev_grad = int32_t(W + N - NW);
-        // roll the window to x+1
-        { long long oldW = W; W = val; WW = x >= 1 ? oldW : W; }
-        if (y) { NW = N; N = NE; NE = NEE; NEE = (x + 3 < w) ? (long long)up[x + 3] : NE; }
-        else { N = W; NW = W; NE = W; NEE = W; }
-      }
-    }
+    BuildLut(root); const ChanLut& L = *lut;
+    const bool sm = cv.AllShared() && !cv.use_prefix;
+    if (wide || uses_wp) { if (L.ok) DecodeRows<long long, 1, false>(root, n, chan, stream_id, out, stride, w, h, wp_base); else DecodeRows<long long, 0, false>(root, n, chan, stream_id, out, stride, w, h, wp_base); }
+    else if (L.ok && sm && L.prop == 8 && L.predictor == 5) DecodeRows<int32_t, 2, true>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else if (L.ok && sm) DecodeRows<int32_t, 1, true>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else if (L.ok) DecodeRows<int32_t, 1, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else DecodeRows<int32_t, 0, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
   }
 };
 #endif

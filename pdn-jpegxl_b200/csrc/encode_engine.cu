@@ -40,7 +40,7 @@ struct TreeBuilder {
   }
 };
 Tree MakeVarDctTree(uint32_t nlf, int num_ec) {
-  TreeBuilder b; int sharp = b.Leaf(1), hfmul = b.Leaf(1), strat = b.Leaf(1), cflc = b.Leaf(5);
+  TreeBuilder b; int sharp = b.Leaf(0), hfmul = b.Leaf(0), strat = b.Leaf(0), cflc = b.Leaf(0);   // Zero predictor: constant maps decode as zero-entropy rows
   int blockinfo = b.Split(2, 0, hfmul, strat); int hfmeta = b.Split(0, 1, b.Split(0, 2, sharp, blockinfo), cflc);
   int groups = num_ec > 0 ? b.Channels(num_ec, 0, 5) : b.Leaf(5); int upper = b.Split(1, int32_t(3 * nlf + 17), groups, hfmeta);
   int lfc = b.Channels(3, 0, 5); int global = b.Leaf(5); int lower = b.Split(1, 0, lfc, global);
@@ -59,7 +59,7 @@ void TokenizeSmallChannel(const std::vector<int32_t>& px, int w, int h, int chan
     auto at = [&](int yy, int xx) { return px[size_t(yy) * w + xx]; };
     int32_t W = x ? at(y, x - 1) : (y ? at(y - 1, x) : 0), N = y ? at(y - 1, x) : W, NW = (x && y) ? at(y - 1, x - 1) : W;
     const TreeNode& leaf = LeafFor(tree, chan, stream, y, W - prev_grad);
-    int32_t pred = leaf.predictor == 1 ? W : std::max(std::min(W, N), std::min(std::max(W, N), W + N - NW)); JXLG_CHECK(leaf.predictor == 1 || leaf.predictor == 5, "fixed tree predictor");
+    int32_t pred = leaf.predictor == 0 ? 0 : leaf.predictor == 1 ? W : std::max(std::min(W, N), std::min(std::max(W, N), W + N - NW)); JXLG_CHECK(leaf.predictor == 0 || leaf.predictor == 1 || leaf.predictor == 5, "fixed tree predictor");
     out->push_back({uint32_t(leaf.leaf_id), PackSigned(at(y, x) - pred)}); prev_grad = W + N - NW; } }
 }
 
