@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <algorithm>
 #include <deque>
+#include <chrono>
+#include <cstdio>
 
 using namespace jxlgpu;
 
@@ -137,6 +139,7 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
     int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 64)); std::vector<cudaStream_t> streams(nstreams);
     for (auto& s : streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    cudaStream_t copy_stream = nullptr; cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking); void* pin = nullptr; size_t pin_cap = 0;
     struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; std::vector<uint8_t> host_copy; };
     std::deque<InFlight> q;
     auto retire = [&]() {
@@ -149,15 +152,22 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
       if (statuses) statuses[f.idx] = st; if (st != DecoderStatus_Ok && first == DecoderStatus_Ok) first = st;
       q.pop_front();
     };
+    const bool trace = getenv("JXLB200_TRACE") != nullptr; double t_enq = 0, t_ret = 0; auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int i = 0; i < count; i++) {
-      if (int(q.size()) >= nstreams) retire();
+      if (int(q.size()) >= nstreams) { double t0 = now(); retire(); t_ret += now() - t0; }
+      double t0 = now();
       q.emplace_back(); InFlight& f = q.back(); f.idx = i; DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i];
       if (hostInputs) req.data = datas[i];
-      else { f.host_copy.resize(dataSizes[i]); if (cudaMemcpy(f.host_copy.data(), datas[i], dataSizes[i], cudaMemcpyDeviceToHost) != cudaSuccess) { f.res.status = Status::DecodeError; f.res.message = "cannot read device input"; continue; } req.data = f.host_copy.data(); req.device_input = datas[i]; }
-      f.job = DecodeEnqueue(req, streams[i % nstreams], &f.res);
+      else {   // headers are parsed on the host: fetch the file through a pinned buffer on an idle stream (a plain cudaMemcpy would serialise with the kernels in flight)
+        if (pin_cap < dataSizes[i]) { if (pin) cudaFreeHost(pin); pin_cap = dataSizes[i] * 2 + 4096; if (cudaHostAlloc(&pin, pin_cap, cudaHostAllocDefault) != cudaSuccess) { pin = nullptr; pin_cap = 0; return DecoderStatus_OutOfMemory; } }
+        if (cudaMemcpyAsync(pin, datas[i], dataSizes[i], cudaMemcpyDeviceToHost, copy_stream) != cudaSuccess || cudaStreamSynchronize(copy_stream) != cudaSuccess) { f.res.status = Status::DecodeError; f.res.message = "cannot read device input"; continue; }
+        f.host_copy.assign(static_cast<uint8_t*>(pin), static_cast<uint8_t*>(pin) + dataSizes[i]); req.data = f.host_copy.data(); req.device_input = datas[i]; }
+      f.job = DecodeEnqueue(req, streams[i % nstreams], &f.res); t_enq += now() - t0;
     }
-    while (!q.empty()) retire();
-    for (auto& s : streams) cudaStreamDestroy(s);
+    { double t0 = now(); while (!q.empty()) retire(); t_ret += now() - t0; }
+    if (trace) DumpHostTrace();
+    if (trace) fprintf(stderr, "[jxlb200] batch of %d: host enqueue %.2f ms total (%.2f ms/image), retire/wait %.2f ms\n", count, t_enq, t_enq / std::max(count, 1), t_ret);
+    for (auto& s : streams) cudaStreamDestroy(s); cudaStreamDestroy(copy_stream); if (pin) cudaFreeHost(pin);
   } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
   return first;
 }

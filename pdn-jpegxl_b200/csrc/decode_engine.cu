@@ -13,8 +13,15 @@
 #include <map>
 #include <mutex>
 #include <chrono>
+#include <cstdio>
 
 namespace jxlgpu {
+
+// host-side phase timers (JXLB200_TRACE=1): where the serial CPU time of an enqueue goes
+struct HostTrace { double t[8] = {0}; int n = 0; };
+static thread_local HostTrace g_trace;
+static inline double NowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+void DumpHostTrace() { if (!g_trace.n) return; fprintf(stderr, "[jxlb200] host ms/image: headers %.2f setup %.2f lfglobal %.2f hfglobal %.2f alloc+upload %.2f blob %.2f launch %.2f\n", g_trace.t[0] / g_trace.n, g_trace.t[1] / g_trace.n, g_trace.t[2] / g_trace.n, g_trace.t[3] / g_trace.n, g_trace.t[4] / g_trace.n, g_trace.t[5] / g_trace.n, g_trace.t[6] / g_trace.n); g_trace = HostTrace(); }
 
 // ---------------------------------------------------------------- small utilities
 #define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw Error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #expr); } while (0)
@@ -175,10 +182,10 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 class DecodeJob {
  public:
   Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
-  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err;
+  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc;
   cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
   bool has_tree = false; Tree tree; Code tree_code; GroupHeader gheader; size_t global_decoded = 0; uint64_t global_data_bitpos = 0; bool global_has_data = false;
-  std::vector<Code> ac_codes; uint32_t hf_blob_mark = 0;
+  std::vector<Code> ac_codes; uint32_t hf_blob_mark = 0; uint32_t frame_uploads = 0;
   ~DecodeJob() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
 
   void Setup(const DecodeRequest& req);
@@ -307,7 +314,7 @@ void DecodeJob::Setup(const DecodeRequest& req) {
   for (size_t i = 0; i < m.ec.size(); i++) JXLG_CHECK(m.ec[i].dim_shift < 3, "extra channels with dim_shift >= 3 (Modular LF-group data) are not supported by the GPU decoder yet");
 }
 
-void DecodeJob::UploadFrame() { CUDA_OK(cudaMemcpyAsync(d_frame.p, &h, sizeof(DFrame), cudaMemcpyHostToDevice, stream)); }
+void DecodeJob::UploadFrame() { if (!h_misc.p) h_misc.Alloc(2 * sizeof(DFrame) + 64, true); DFrame* slot = h_misc.as<DFrame>() + (frame_uploads++ & 1); *slot = h; CUDA_OK(cudaMemcpyAsync(d_frame.p, slot, sizeof(DFrame), cudaMemcpyHostToDevice, stream)); }
 
 void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   const std::vector<uint8_t>& cs = hd.ci.codestream; comp_size = cs.size();
@@ -327,7 +334,8 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
   bool smooth = vardct && !(h.flags & kFlagSkipAdaptiveLfSmoothing) && h.xb > 2 && h.yb > 2; h.lf_src = smooth ? h.lf_tmp : h.lf;
   CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream));
-  if (req.device_input) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input, comp_size, cudaMemcpyDeviceToDevice, stream)); else CUDA_OK(cudaMemcpyAsync(d_comp.p, cs.data(), comp_size, cudaMemcpyHostToDevice, stream));
+  if (req.device_input && hd.ci.contiguous_offset != size_t(-1)) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input + hd.ci.contiguous_offset, comp_size, cudaMemcpyDeviceToDevice, stream));
+  else { h_comp.Alloc(comp_size, true); memcpy(h_comp.p, cs.data(), comp_size); CUDA_OK(cudaMemcpyAsync(d_comp.p, h_comp.p, comp_size, cudaMemcpyHostToDevice, stream)); }   // pinned staging: a pageable source would serialise the stream
   CUDA_OK(cudaMemsetAsync(d_comp.as<uint8_t>() + comp_size, 0, 64, stream));
 }
 
@@ -343,9 +351,11 @@ void DecodeJob::Run(const DecodeRequest& req) {
   const std::vector<uint8_t>& cs = hd.ci.codestream; const bool vardct = h.encoding == 0; const size_t nsec = toc.size.size(); const bool single = nsec == 1;
   const size_t nlog = size_t(h.num_passes) * h.num_groups + h.num_lf_groups + 2;
   // host parse: LfGlobal (+ HfGlobal when it has its own section)
-  BitReader lfg(cs.data() + frame_off + toc.offset[0], toc.size[0]); ParseLfGlobal(lfg); JXLG_CHECK(!lfg.overrun, "LfGlobal truncated");
+  double tt = NowMs();
+  BitReader lfg(cs.data() + frame_off + toc.offset[0], toc.size[0]); ParseLfGlobal(lfg); JXLG_CHECK(!lfg.overrun, "LfGlobal truncated"); g_trace.t[2] += NowMs() - tt; tt = NowMs();
   uint64_t base_bits = uint64_t(frame_off) * 8; uint64_t after_lfglobal = (uint64_t(frame_off) + toc.offset[0]) * 8 + lfg.pos;
   if (!single && vardct) { BitReader hb(cs.data() + frame_off + toc.offset[1 + h.num_lf_groups], toc.size[1 + h.num_lf_groups]); ParseHfGlobal(hb); JXLG_CHECK(!hb.overrun, "HfGlobal truncated"); }
+  g_trace.t[3] += NowMs() - tt; tt = NowMs();
   {  // shared-memory budgets for the staged tables (host knows the exact sizes)
     auto code_bytes = [](const DCode& c) { return ((c.num_clusters * 4 + 15) & ~15u) + ((c.num_ctx + 15) & ~15u) + (c.use_prefix ? 0u : (((c.num_clusters << c.log_alpha) * 8 + 15) & ~15u)); };
     uint32_t modb = has_tree ? code_bytes(h.mod_code) + ((h.tree_size * 16 + 15) & ~15u) : 0, acb = 0;
@@ -355,14 +365,14 @@ void DecodeJob::Run(const DecodeRequest& req) {
   std::vector<uint64_t> sec(2 * nlog + 2, 0);
   for (size_t i = 0; i < nlog; i++) { size_t t = single ? 0 : i; sec[i] = base_bits + uint64_t(toc.offset[t]) * 8; sec[nlog + i] = base_bits + uint64_t(toc.offset[t] + toc.size[t]) * 8; }
   h.sec_off = blob.Add(sec.data(), sec.size() * 8);
-  AllocateAndUpload(req);
-  auto upload_blob = [&]() { blob.b.resize((blob.b.size() + 31) / 16 * 16, 0); if (d_blob.n < blob.b.size() + 16) d_blob.Alloc(std::max<size_t>(blob.b.size() * 2, 1 << 16)); h.blob = d_blob.as<uint8_t>(); CUDA_OK(cudaMemcpyAsync(d_blob.p, blob.b.data(), blob.b.size(), cudaMemcpyHostToDevice, stream)); UploadFrame(); };
-  upload_blob();
+  AllocateAndUpload(req); g_trace.t[4] += NowMs() - tt; tt = NowMs();
+  auto upload_blob = [&]() { blob.b.resize((blob.b.size() + 31) / 16 * 16, 0); if (d_blob.n < blob.b.size() + 16) d_blob.Alloc(std::max<size_t>(blob.b.size() * 2, 1 << 16)); h.blob = d_blob.as<uint8_t>(); h_blob.Alloc(blob.b.size(), true); memcpy(h_blob.p, blob.b.data(), blob.b.size()); CUDA_OK(cudaMemcpyAsync(d_blob.p, h_blob.p, blob.b.size(), cudaMemcpyHostToDevice, stream)); UploadFrame(); };
+  upload_blob(); g_trace.t[5] += NowMs() - tt; tt = NowMs();
   const DFrame* d = d_frame.as<DFrame>();
   if (timed) cudaEventRecord(ev[0], stream);
   // global Modular stream
   if (global_has_data) { LaunchModularGlobal(d, h, after_lfglobal, uint32_t(global_decoded), stream); CountLaunch(); }
-  else if (single) CUDA_OK(cudaMemcpyAsync(h.end_bitpos, &after_lfglobal, 8, cudaMemcpyHostToDevice, stream));
+  else if (single) { uint64_t* slot = reinterpret_cast<uint64_t*>(h_misc.as<uint8_t>() + 2 * sizeof(DFrame)); slot[0] = after_lfglobal; CUDA_OK(cudaMemcpyAsync(h.end_bitpos, slot, 8, cudaMemcpyHostToDevice, stream)); }
   if (vardct) { LaunchLfGroups(d, h, stream); CountLaunch(); }
   else if (single) { /* Modular frame, single section: LF group and HfGlobal parts are empty; groups continue where the global stream ended */ CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, h.end_bitpos, 8, cudaMemcpyDeviceToDevice, stream)); }
   if (single && vardct) {   // HfGlobal follows the LF group in the same bit stream: need its end position on the host
@@ -370,7 +380,7 @@ void DecodeJob::Run(const DecodeRequest& req) {
     uint32_t e = *h_err.as<uint32_t>(); JXLG_CHECK(e == 0, DevErrorText(e)); memcpy(pos, h_err.as<uint8_t>() + 16, 24);
     size_t byte = size_t(pos[1] / 8); JXLG_CHECK(byte <= cs.size(), "LF group ran past the end of the file");
     BitReader hb(cs.data(), cs.size()); hb.pos = size_t(pos[1]); ParseHfGlobal(hb); JXLG_CHECK(!hb.overrun, "HfGlobal truncated"); uint64_t after = hb.pos;
-    upload_blob(); CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, &after, 8, cudaMemcpyHostToDevice, stream));
+    upload_blob(); { uint64_t* slot = reinterpret_cast<uint64_t*>(h_misc.as<uint8_t>() + 2 * sizeof(DFrame)) + 1; slot[0] = after; CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, slot, 8, cudaMemcpyHostToDevice, stream)); }
   }
   if (timed) cudaEventRecord(ev[1], stream);
   if (vardct) { bool smooth = h.lf_src == h.lf_tmp; LaunchLfDequant(d, h, smooth, stream); CountLaunch(smooth ? 2 : 1); }
@@ -386,6 +396,7 @@ void DecodeJob::Run(const DecodeRequest& req) {
   if (!device_output) CUDA_OK(cudaMemcpyAsync(h_out.p, d_out.p, out_bytes, cudaMemcpyDeviceToHost, stream));
   CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream));
   if (timed) cudaEventRecord(ev[6], stream);
+  g_trace.t[6] += NowMs() - tt; g_trace.n++;
 }
 
 std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res) {
@@ -393,9 +404,9 @@ std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t 
   if (!req.data) { res->status = Status::NullParameter; return job; }
   try {
     std::string why; if (!CudaAvailable(&why)) { res->status = Status::DecodeError; res->message = why; return job; }
-    job = std::make_shared<DecodeJob>(); job->stream = stream;
+    job = std::make_shared<DecodeJob>(); job->stream = stream; double t0 = NowMs();
     res->status = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res->message); if (res->status != Status::Ok) { job.reset(); return job; }
-    job->Setup(req); job->Run(req); res->info = job->info;
+    g_trace.t[0] += NowMs() - t0; t0 = NowMs(); job->Setup(req); g_trace.t[1] += NowMs() - t0; job->Run(req); res->info = job->info;
   } catch (const std::bad_alloc&) { res->status = Status::OutOfMemory; job.reset(); }
   catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); if (job) res->info = job->info; job.reset(); }
   return job;

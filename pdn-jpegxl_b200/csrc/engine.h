@@ -51,6 +51,7 @@ bool DecodeDebugCoeffs(const std::shared_ptr<DecodeJob>& job, std::vector<int16_
 
 bool CudaAvailable(std::string* why);
 void TrimPools();
+void DumpHostTrace();
 
 // ---- encoder
 struct EncodeRequest {

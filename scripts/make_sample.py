@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 import numpy as np, pkgload
-from oracle_py import synthetic_image   # image recipe only (numpy); no oracle codec involved
+from synth import synthetic_image
 P = pkgload.load()
 w, h, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 img = synthetic_image(w, h, seed=0)
