@@ -13,6 +13,8 @@ VarDCT d=1.0 files per GPU (BASELINE config 3, files sharded across ranks, no da
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per in-flight image stream (default 8 serialises streams)
 import subprocess
 import sys
 import threading

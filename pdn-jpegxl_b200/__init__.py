@@ -35,6 +35,7 @@ if not os.path.exists(LIB_PATH):
         "%s not found next to %s. Build it with `python pdn-jpegxl_b200/build.py` (nvcc, sm_100a). "
         "The engine has no CPU fallback." % (LIB_NAME, __file__))
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # see abi.cu: one hardware queue per in-flight image stream
 _lib = C.CDLL(LIB_PATH)
 
 

@@ -11,12 +11,17 @@
 #include <cstdlib>
 #include <algorithm>
 #include <deque>
+#include <map>
 #include <chrono>
 #include <cstdio>
 
 using namespace jxlgpu;
 
 namespace {
+
+// More hardware work queues than the default 8, so that the per-image CUDA streams of a batch do not share (and serialise on) a queue.
+// Only effective when set before the process creates its CUDA context; never overrides the user's own setting.
+struct EnvInit { EnvInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_env_init;
 
 void SetErrorMessage(ErrorInfo* ei, const char* msg) {   // N/Common.cpp:18-30: dropped when empty or longer than 255 chars
   if (ei && msg) { size_t n = strlen(msg); if (n > 0 && n <= 255) { memcpy(ei->errorMessage, msg, n); ei->errorMessage[n] = 0; } }
@@ -137,18 +142,26 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
   try {
     std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return DecoderStatus_DecodeError; }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
-    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 64)); std::vector<cudaStream_t> streams(nstreams);
-    for (auto& s : streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    cudaStream_t copy_stream = nullptr; cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking); void* pin = nullptr; size_t pin_cap = 0;
-    struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; std::vector<uint8_t> host_copy; };
+    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 64)); int cur_dev = 0; cudaGetDevice(&cur_dev);
+    // streams are created once per device and thread and reused by later batches (stream creation is not free)
+    static thread_local std::map<int, std::vector<cudaStream_t>> stream_cache; std::vector<cudaStream_t>& all_streams = stream_cache[cur_dev];
+    while (int(all_streams.size()) < nstreams + 1) { cudaStream_t s = nullptr; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaStreamCreate failed"); return DecoderStatus_DecodeError; } all_streams.push_back(s); }
+    cudaStream_t copy_stream = all_streams[0]; std::vector<cudaStream_t> streams(all_streams.begin() + 1, all_streams.begin() + 1 + nstreams); void* pin = nullptr; size_t pin_bytes = 0;
+    struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; };
     std::deque<InFlight> q;
+    // device-resident inputs: the headers are parsed on the host, so fetch all files once through one pinned buffer (asynchronously, one sync)
+    std::vector<size_t> in_off(count + 1, 0); const uint8_t* host_in = nullptr;
+    if (!hostInputs) { for (int i = 0; i < count; i++) in_off[i + 1] = in_off[i] + ((dataSizes[i] + 63) & ~size_t(63));
+      pin_bytes = in_off[count] + 64; pin = PinnedGet(pin_bytes);
+      for (int i = 0; i < count; i++) cudaMemcpyAsync(static_cast<uint8_t*>(pin) + in_off[i], datas[i], dataSizes[i], cudaMemcpyDeviceToHost, copy_stream);
+      if (cudaStreamSynchronize(copy_stream) != cudaSuccess) { SetErrorMessage(errorInfo, "cannot read device inputs"); return DecoderStatus_DecodeError; } host_in = static_cast<uint8_t*>(pin); }
+    // host outputs that are page-locked receive the pixels directly (no staging copy)
+    std::vector<uint8_t> out_is_pinned(count, 0);
+    if (hostOutputs) for (int i = 0; i < count; i++) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, outputs[i]) == cudaSuccess && at.type == cudaMemoryTypeHost) out_is_pinned[i] = 1; else cudaGetLastError(); }
     auto retire = [&]() {
       InFlight& f = q.front(); DecodeFinish(f.job, &f.res); DecoderStatus st = DecoderStatus(f.res.status);
-      if (st == DecoderStatus_Ok) {
-        if (f.res.pixel_bytes > outputBytes[f.idx]) st = DecoderStatus_InvalidParameter;
-        else if (hostOutputs) memcpy(outputs[f.idx], f.res.pixels, f.res.pixel_bytes);
-        else if (cudaMemcpyAsync(outputs[f.idx], f.res.pixels, f.res.pixel_bytes, cudaMemcpyDeviceToDevice, f.job ? streams[f.idx % nstreams] : nullptr) != cudaSuccess || cudaStreamSynchronize(streams[f.idx % nstreams]) != cudaSuccess) st = DecoderStatus_DecodeError;
-      } else if (first == DecoderStatus_Ok) SetErrorMessage(errorInfo, f.res.message);
+      if (st == DecoderStatus_Ok) { if (f.res.pixel_bytes > outputBytes[f.idx]) st = DecoderStatus_InvalidParameter; else if (!f.direct) memcpy(outputs[f.idx], f.res.pixels, f.res.pixel_bytes); }
+      else if (first == DecoderStatus_Ok) SetErrorMessage(errorInfo, f.res.message);
       if (statuses) statuses[f.idx] = st; if (st != DecoderStatus_Ok && first == DecoderStatus_Ok) first = st;
       q.pop_front();
     };
@@ -156,18 +169,15 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
     for (int i = 0; i < count; i++) {
       if (int(q.size()) >= nstreams) { double t0 = now(); retire(); t_ret += now() - t0; }
       double t0 = now();
-      q.emplace_back(); InFlight& f = q.back(); f.idx = i; DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i];
-      if (hostInputs) req.data = datas[i];
-      else {   // headers are parsed on the host: fetch the file through a pinned buffer on an idle stream (a plain cudaMemcpy would serialise with the kernels in flight)
-        if (pin_cap < dataSizes[i]) { if (pin) cudaFreeHost(pin); pin_cap = dataSizes[i] * 2 + 4096; if (cudaHostAlloc(&pin, pin_cap, cudaHostAllocDefault) != cudaSuccess) { pin = nullptr; pin_cap = 0; return DecoderStatus_OutOfMemory; } }
-        if (cudaMemcpyAsync(pin, datas[i], dataSizes[i], cudaMemcpyDeviceToHost, copy_stream) != cudaSuccess || cudaStreamSynchronize(copy_stream) != cudaSuccess) { f.res.status = Status::DecodeError; f.res.message = "cannot read device input"; continue; }
-        f.host_copy.assign(static_cast<uint8_t*>(pin), static_cast<uint8_t*>(pin) + dataSizes[i]); req.data = f.host_copy.data(); req.device_input = datas[i]; }
+      q.emplace_back(); InFlight& f = q.back(); f.idx = i; DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i]; req.out_capacity = outputBytes[i];
+      if (hostInputs) req.data = datas[i]; else { req.data = host_in + in_off[i]; req.device_input = datas[i]; }
+      if (!hostOutputs) { req.out_device = outputs[i]; f.direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f.direct = true; }
       f.job = DecodeEnqueue(req, streams[i % nstreams], &f.res); t_enq += now() - t0;
     }
     { double t0 = now(); while (!q.empty()) retire(); t_ret += now() - t0; }
     if (trace) DumpHostTrace();
     if (trace) fprintf(stderr, "[jxlb200] batch of %d: host enqueue %.2f ms total (%.2f ms/image), retire/wait %.2f ms\n", count, t_enq, t_enq / std::max(count, 1), t_ret);
-    for (auto& s : streams) cudaStreamDestroy(s); cudaStreamDestroy(copy_stream); if (pin) cudaFreeHost(pin);
+    if (pin) PinnedPut(pin, pin_bytes);
   } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
   return first;
 }

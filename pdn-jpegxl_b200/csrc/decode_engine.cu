@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <chrono>
+#include <atomic>
 #include <cstdio>
 
 namespace jxlgpu {
@@ -53,6 +54,8 @@ class Pool {
 static Pool& DevPool() { static Pool p(false); return p; }
 static Pool& HostPool() { static Pool p(true); return p; }
 void TrimPools() { DevPool().Trim(); HostPool().Trim(); }
+void* PinnedGet(size_t bytes) { return HostPool().Get(bytes ? bytes : 1); }
+void PinnedPut(void* p, size_t bytes) { HostPool().Put(p, bytes ? bytes : 1); }
 
 struct DevBuf { void* p = nullptr; size_t n = 0; bool host = false; void Alloc(size_t bytes, bool pinned = false) { Free(); host = pinned; n = bytes ? bytes : 1; p = (pinned ? HostPool() : DevPool()).Get(n); } void Free() { if (p) (host ? HostPool() : DevPool()).Put(p, n); p = nullptr; n = 0; } ~DevBuf() { Free(); } template <class T> T* as() const { return static_cast<T*>(p); } };
 
@@ -182,10 +185,10 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 class DecodeJob {
  public:
   Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
-  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc;
+  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother;
   cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
   bool has_tree = false; Tree tree; Code tree_code; GroupHeader gheader; size_t global_decoded = 0; uint64_t global_data_bitpos = 0; bool global_has_data = false;
-  std::vector<Code> ac_codes; uint32_t hf_blob_mark = 0; uint32_t frame_uploads = 0;
+  std::vector<Code> ac_codes; uint32_t hf_blob_mark = 0; uint32_t frame_uploads = 0; uint8_t* ext_out_device = nullptr; uint8_t* ext_out_pinned = nullptr;
   ~DecodeJob() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
 
   void Setup(const DecodeRequest& req);
@@ -319,7 +322,7 @@ void DecodeJob::UploadFrame() { if (!h_misc.p) h_misc.Alloc(2 * sizeof(DFrame) +
 void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   const std::vector<uint8_t>& cs = hd.ci.codestream; comp_size = cs.size();
   size_t cells = size_t(h.xb) * h.yb, px = size_t(h.xpad) * h.ypad, tiles = size_t(h.xt) * h.yt; bool vardct = h.encoding == 0;
-  d_frame.Alloc(sizeof(DFrame)); d_err.Alloc(64); h_err.Alloc(64, true);
+  d_frame.Alloc(sizeof(DFrame)); d_err.Alloc(64); h_err.Alloc(64, true); d_gother.Alloc(size_t(h.num_groups) * 4);
   d_comp.Alloc(comp_size + 64);
   if (vardct) {
     d_lfq.Alloc(cells * 3 * 4); d_lf.Alloc(cells * 3 * 4); d_lf_tmp.Alloc(cells * 3 * 4); d_acs.Alloc(cells); d_qf.Alloc(cells); d_sharp.Alloc(cells); d_lfidx.Alloc(cells); d_ytox.Alloc(tiles); d_ytob.Alloc(tiles);
@@ -328,12 +331,16 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   uint64_t mod_ints = 0; for (uint32_t i = 0; i < h.num_mod_channels; i++) mod_ints += uint64_t(h.mod_ch[i].w) * h.mod_ch[i].h; if (mod_ints) d_mod.Alloc(mod_ints * 4);
   if (h.uses_wp) d_wp.Alloc((size_t(h.num_lf_groups) + h.num_groups + 1) * 5 * 2 * (kMaxWpWidth + 2) * 4); else d_wp.Alloc(16);
   const DOutput& o = h.out; size_t bps = o.sample_type == 0 ? 1 : o.sample_type == 3 ? 4 : 2; size_t chans = bgra ? 4 : (o.num_channels + (o.black_plane >= 0 ? 1 : 0)); if (bgra) bps = 1;
-  out_bytes = size_t(o.out_w) * o.out_h * chans * bps; d_out.Alloc(out_bytes); if (!device_output) h_out.Alloc(out_bytes, true);
+  out_bytes = size_t(o.out_w) * o.out_h * chans * bps;
+  if (req.out_device || req.out_pinned) JXLG_CHECK(req.out_capacity >= out_bytes, "output buffer too small");
+  if (!req.out_device) d_out.Alloc(out_bytes); if (!device_output && !req.out_pinned) h_out.Alloc(out_bytes, true);
+  ext_out_device = req.out_device; ext_out_pinned = req.out_pinned;
   h.comp = d_comp.as<uint8_t>(); h.lfq = d_lfq.as<int32_t>(); h.lf = d_lf.as<float>(); h.lf_tmp = d_lf_tmp.as<float>(); h.acs = d_acs.as<uint8_t>(); h.hf_mul_m1 = d_qf.as<uint8_t>(); h.sharp = d_sharp.as<uint8_t>(); h.lf_idx = d_lfidx.as<uint8_t>();
   h.ytox = d_ytox.as<int8_t>(); h.ytob = d_ytob.as<int8_t>(); h.hfmeta_scratch = d_hfmeta.as<int32_t>(); h.coeffs = d_coeffs.as<int16_t>(); h.xyb = d_xyb.as<float>(); h.xyb_tmp = d_xyb_tmp.as<float>(); h.inv_sigma = d_sigma.as<float>();
-  h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
+  h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = req.out_device ? req.out_device : d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
   bool smooth = vardct && !(h.flags & kFlagSkipAdaptiveLfSmoothing) && h.xb > 2 && h.yb > 2; h.lf_src = smooth ? h.lf_tmp : h.lf;
-  CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream));
+  h.group_other = d_gother.as<uint32_t>();
+  CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream)); CUDA_OK(cudaMemsetAsync(d_gother.p, 0, size_t(h.num_groups) * 4, stream));
   if (req.device_input && hd.ci.contiguous_offset != size_t(-1)) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input + hd.ci.contiguous_offset, comp_size, cudaMemcpyDeviceToDevice, stream));
   else { h_comp.Alloc(comp_size, true); memcpy(h_comp.p, cs.data(), comp_size); CUDA_OK(cudaMemcpyAsync(d_comp.p, h_comp.p, comp_size, cudaMemcpyHostToDevice, stream)); }   // pinned staging: a pageable source would serialise the stream
   CUDA_OK(cudaMemsetAsync(d_comp.as<uint8_t>() + comp_size, 0, 64, stream));
@@ -360,6 +367,7 @@ void DecodeJob::Run(const DecodeRequest& req) {
     auto code_bytes = [](const DCode& c) { return ((c.num_clusters * 4 + 15) & ~15u) + ((c.num_ctx + 15) & ~15u) + (c.use_prefix ? 0u : (((c.num_clusters << c.log_alpha) * 8 + 15) & ~15u)); };
     uint32_t modb = has_tree ? code_bytes(h.mod_code) + ((h.tree_size * 16 + 15) & ~15u) : 0, acb = 0;
     if (vardct && !single) for (uint32_t p = 0; p < h.num_passes; p++) acb = std::max(acb, code_bytes(h.ac_code[p]));
+    { static std::atomic<uint32_t> job_counter{0}; h.lf_cta_offset = (job_counter.fetch_add(1) * 4u) % 144u; }
     h.lf_smem = std::min<uint32_t>(modb + 64, 96 * 1024); h.ac_smem = std::min<uint32_t>(acb + (h.num_mod_channels > h.first_group_channel ? modb : 0) + 64, 96 * 1024); if (single) h.ac_smem = 96 * 1024;
   }
   std::vector<uint64_t> sec(2 * nlog + 2, 0);
@@ -393,7 +401,7 @@ void DecodeJob::Run(const DecodeRequest& req) {
   if (timed) cudaEventRecord(ev[4], stream);
   LaunchOutput(d, h, stream);
   if (timed) cudaEventRecord(ev[5], stream);
-  if (!device_output) CUDA_OK(cudaMemcpyAsync(h_out.p, d_out.p, out_bytes, cudaMemcpyDeviceToHost, stream));
+  if (!device_output) CUDA_OK(cudaMemcpyAsync(ext_out_pinned ? ext_out_pinned : h_out.as<uint8_t>(), h.out_px, out_bytes, cudaMemcpyDeviceToHost, stream));
   CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream));
   if (timed) cudaEventRecord(ev[6], stream);
   g_trace.t[6] += NowMs() - tt; g_trace.n++;
@@ -418,7 +426,7 @@ void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res) {
   if (e != cudaSuccess) { res->status = Status::DecodeError; res->message = std::string("CUDA: ") + cudaGetErrorString(e); return; }
   uint32_t de = *job->h_err.as<uint32_t>();
   if (de) { res->status = Status::DecodeError; res->message = DevErrorText(de); return; }
-  res->info = job->info; res->pixels = job->device_output ? job->d_out.as<uint8_t>() : job->h_out.as<uint8_t>(); res->pixel_bytes = job->out_bytes; res->out_width = job->h.out.out_w; res->out_height = job->h.out.out_h; res->job = job;
+  res->info = job->info; res->pixels = job->device_output ? job->h.out_px : (job->ext_out_pinned ? job->ext_out_pinned : job->h_out.as<uint8_t>()); res->pixel_bytes = job->out_bytes; res->out_width = job->h.out.out_w; res->out_height = job->h.out.out_h; res->job = job;
   if (job->timed) { auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, job->ev[a], job->ev[b]); return t; };
     res->times.lf = ms(0, 1); res->times.ac = ms(1, 2); res->times.recon = ms(2, 3); res->times.filters = ms(3, 4); res->times.output = ms(4, 5); res->times.d2h = ms(5, 6); res->times.total = ms(0, 6); }
 }

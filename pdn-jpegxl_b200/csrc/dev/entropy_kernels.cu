@@ -41,7 +41,10 @@ __device__ void StageModDecoder(ModDecoder& md, const DFrame& f, uint8_t* dsm, u
 }
 
 __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame f) {
-  const int g = blockIdx.x, lane = threadIdx.x;
+  // The first-wave CTA->SM mapping is deterministic, so concurrent images would stack their few LF CTAs on the same SMs:
+  // each launch prepends `lf_cta_offset` empty CTAs to land on different SMs.
+  if (blockIdx.x < f.lf_cta_offset) return;
+  const int g = int(blockIdx.x - f.lf_cta_offset), lane = threadIdx.x;
   const int gx = g % int(f.xlfgroups), gy = g / int(f.xlfgroups), cx0 = gx * 256, cy0 = gy * 256;
   const int w = min(256, int(f.xb) - cx0), h = min(256, int(f.yb) - cy0), tw = (w + 7) / 8, th = (h + 7) / 8;
   int32_t* scratch = f.hfmeta_scratch + size_t(g) * kHfMetaScratchInts;
@@ -93,7 +96,8 @@ __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame 
   if (all1) for (uint32_t i = lane; i < nb; i += 32) { int32_t s = s_info[i]; if (s < 0 || s >= 27 || CoveredX(s) != 1 || CoveredY(s) != 1) all1 = false; }
   all1 = __all_sync(0xffffffffu, all1);
   if (all1) {   // common case (only 8x8 strategies): block i sits in cell i, fully parallel
-    for (uint32_t i = lane; i < nb; i += 32) { size_t o = size_t(cy0 + i / w) * f.xb + cx0 + i % w; f.acs[o] = uint8_t(s_info[i] | 0x80); f.hf_mul_m1[o] = uint8_t(max(0, min(255, s_info[nb + i]))); }
+    for (uint32_t i = lane; i < nb; i += 32) { const int yy = cy0 + int(i / w), xx = cx0 + int(i % w); size_t o = size_t(yy) * f.xb + xx; f.acs[o] = uint8_t(s_info[i] | 0x80); f.hf_mul_m1[o] = uint8_t(max(0, min(255, s_info[nb + i])));
+      if (s_info[i] != 0) atomicAdd(f.group_other + (yy >> 5) * f.xgroups + (xx >> 5), 1u); }
   } else if (lane == 0) {
     uint32_t num = 0, e = 0;
     for (int y = 0; y < h && !e; y++) for (int x = 0; x < w; x++) {
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame 
       if (x + bw > w || y + bh > h || (x & 31) + bw > 32 || (y & 31) + bh > 32) { e = kErrBlockBounds; break; }
       int32_t qf = max(0, min(255, s_info[nb + num]));
       for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { size_t p = o + size_t(iy) * f.xb + ix; if (f.acs[p] != 0xFF) e = kErrBlockBounds; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = uint8_t(qf); }
-      f.acs[o] = uint8_t(s | 0x80); num++;
+      f.acs[o] = uint8_t(s | 0x80); num++; if (s != 0) atomicAdd(f.group_other + ((cy0 + y) >> 5) * f.xgroups + ((cx0 + x) >> 5), 1u);
     }
     SetError(f.err, e);
   }
@@ -199,22 +203,27 @@ __device__ __noinline__ uint32_t DecodeAcCoeffs(const DFrame& f, SymReader& rd_i
   return err;
 }
 
-__global__ void __launch_bounds__(128) k_ac_group(const __grid_constant__ DFrame f, int pass) {
-  const int g = blockIdx.x, tid = threadIdx.x;
-  const int gx = g % int(f.xgroups), gy = g / int(f.xgroups);
-  __shared__ uint8_t s_nz[3][32 * 32]; __shared__ uint8_t s_acs[32 * 32], s_qf[32 * 32], s_lfidx[32 * 32]; __shared__ ChanLut sh_lut; extern __shared__ __align__(16) uint8_t dsm[];
+// One CTA decodes kAcGroupsPerCta groups: warp w owns group blockIdx.x*kAcGroupsPerCta + w (lane 0 walks the bit stream, the
+// other lanes zero-fill and stage), and the warps share one shared-memory copy of the code tables.
+static const int kAcGroupsPerCta = 4;
+__global__ void __launch_bounds__(32 * kAcGroupsPerCta) k_ac_group(const __grid_constant__ DFrame f, int pass) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const int g = blockIdx.x * kAcGroupsPerCta + warp; const bool active = g < int(f.num_groups);
+  const int gx = active ? g % int(f.xgroups) : 0, gy = active ? g / int(f.xgroups) : 0;
+  __shared__ uint8_t s_nz_all[kAcGroupsPerCta][3][32 * 32]; __shared__ uint8_t s_acs_all[kAcGroupsPerCta][32 * 32], s_qf_all[kAcGroupsPerCta][32 * 32], s_lfidx_all[kAcGroupsPerCta][32 * 32];
+  __shared__ ChanLut sh_lut[kAcGroupsPerCta]; extern __shared__ __align__(16) uint8_t dsm[];
+  uint8_t (*s_nz)[32 * 32] = s_nz_all[warp]; uint8_t* s_acs = s_acs_all[warp]; uint8_t* s_qf = s_qf_all[warp]; uint8_t* s_lfidx = s_lfidx_all[warp];
   const bool vardct = f.encoding == 0; int w = 0, h = 0;
-  ModDecoder md; BindModDecoder(md, f, &sh_lut); CodeView cv; uint32_t used = 0;
-  if (vardct) { cv.Bind(f.blob, f.ac_code[pass]); cv.Stage(dsm, f.ac_smem, used, tid, 128); }
-  if (f.num_mod_channels > f.first_group_channel) StageModDecoder(md, f, dsm, f.ac_smem, used, tid, 128);
-  if (vardct) {
+  ModDecoder md; BindModDecoder(md, f, &sh_lut[warp]); CodeView cv; uint32_t used = 0;
+  if (vardct) { cv.Bind(f.blob, f.ac_code[pass]); cv.Stage(dsm, f.ac_smem, used, tid, 32 * kAcGroupsPerCta); }
+  if (f.num_mod_channels > f.first_group_channel) StageModDecoder(md, f, dsm, f.ac_smem, used, tid, 32 * kAcGroupsPerCta);
+  if (vardct && active) {
     const int cx0 = gx * 32, cy0 = gy * 32; w = min(32, int(f.xb) - cx0); h = min(32, int(f.yb) - cy0);
-    if (pass == 0) { int4* z = reinterpret_cast<int4*>(f.coeffs + size_t(g) * 3 * 65536); int4 zero = make_int4(0, 0, 0, 0); for (int i = tid; i < 3 * 65536 * 2 / 16; i += 128) z[i] = zero; }
-    for (int i = tid; i < 32 * 32; i += 128) { int by = i >> 5, bx = i & 31; s_nz[0][i] = s_nz[1][i] = s_nz[2][i] = 0;
+    if (pass == 0) { int4* z = reinterpret_cast<int4*>(f.coeffs + size_t(g) * 3 * 65536); const int4 zero = make_int4(0, 0, 0, 0); for (int i = lane; i < 3 * 65536 * 2 / 16; i += 32) z[i] = zero; }
+    for (int i = lane; i < 32 * 32; i += 32) { int by = i >> 5, bx = i & 31; s_nz[0][i] = s_nz[1][i] = s_nz[2][i] = 0;
       if (by < h && bx < w) { size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; s_acs[i] = f.acs[o]; s_qf[i] = f.hf_mul_m1[o]; s_lfidx[i] = f.lf_idx[o]; } else s_acs[i] = 0; }
   }
   __syncthreads();
-  if (tid != 0) return;
+  if (lane != 0 || !active) return;
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
@@ -245,11 +254,11 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
 
 static void EnsureSmemAttr() { static bool done = false; if (done) return; done = true;
   cudaFuncSetAttribute(k_lf_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
-void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (h.num_lf_groups) k_lf_group<<<h.num_lf_groups, 32, h.lf_smem, st>>>(h); }
+void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (h.num_lf_groups) k_lf_group<<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); }
 void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st) {
   size_t plane = size_t(h.xb) * h.yb; unsigned blocks = unsigned((plane + 255) / 256); k_lf_dequant<<<blocks, 256, 0, st>>>(d); if (smooth) k_lf_smooth<<<blocks, 256, 0, st>>>(d);
 }
-void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st) { EnsureSmemAttr(); k_ac_group<<<h.num_groups, 128, h.ac_smem, st>>>(h, pass); }
+void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st) { EnsureSmemAttr(); k_ac_group<<<(h.num_groups + kAcGroupsPerCta - 1) / kAcGroupsPerCta, 32 * kAcGroupsPerCta, h.ac_smem, st>>>(h, pass); }
 void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st) { EnsureSmemAttr(); k_modular_global<<<1, 32, h.lf_smem, st>>>(h, start_bitpos, num_channels); }
 
 }  // namespace jxlgpu

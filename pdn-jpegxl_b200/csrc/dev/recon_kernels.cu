@@ -79,10 +79,65 @@ __device__ void LlfFromLf(const DFrame& f, int c, int cy, int cx, const float* l
   (void)c;
 }
 
+// ------------------------------------------------------------------ DCT8 fast path
+// c[k*8+i] = ck * cos((2i+1) k pi / 16), c0 = 1, ck = sqrt(2) (A.9 scaling: inverse is the plain DCT-III sum)
+__device__ constexpr float kCos8[64] = {1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.387039845e+00f, 1.175875602e+00f, 7.856949584e-01f, 2.758993793e-01f, -2.758993793e-01f, -7.856949584e-01f, -1.175875602e+00f, -1.387039845e+00f, 1.306562965e+00f, 5.411961001e-01f, -5.411961001e-01f, -1.306562965e+00f, -1.306562965e+00f, -5.411961001e-01f, 5.411961001e-01f, 1.306562965e+00f, 1.175875602e+00f, -2.758993793e-01f, -1.387039845e+00f, -7.856949584e-01f, 7.856949584e-01f, 1.387039845e+00f, 2.758993793e-01f, -1.175875602e+00f, 1.000000000e+00f, -1.000000000e+00f, -1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, -1.000000000e+00f, -1.000000000e+00f, 1.000000000e+00f, 7.856949584e-01f, -1.387039845e+00f, 2.758993793e-01f, 1.175875602e+00f, -1.175875602e+00f, -2.758993793e-01f, 1.387039845e+00f, -7.856949584e-01f, 5.411961001e-01f, -1.306562965e+00f, 1.306562965e+00f, -5.411961001e-01f, -5.411961001e-01f, 1.306562965e+00f, -1.306562965e+00f, 5.411961001e-01f, 2.758993793e-01f, -7.856949584e-01f, 1.175875602e+00f, -1.387039845e+00f, 1.387039845e+00f, -1.175875602e+00f, 7.856949584e-01f, -2.758993793e-01f};
+
+// Dequant + chroma-from-luma + LLF + 8x8 IDCT for every DCT8 varblock. One warp handles 4 horizontally adjacent cells per
+// iteration: lane (b = lane>>3, r = lane&7) loads storage row r of block b (one 16-byte load: 8 int16 coefficients, the
+// 4 blocks are 512 contiguous bytes), transforms along the row in registers, transposes through 1.1 KB of padded shared
+// memory and writes one 32-byte pixel row segment; a warp writes 8 rows x 128 contiguous bytes per channel.
+__global__ void __launch_bounds__(256) k_reconstruct_dct8(const __grid_constant__ DFrame f) {
+  const int g = blockIdx.x >> 2, quarter = blockIdx.x & 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = lane >> 3, r = lane & 7;
+  const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
+  __shared__ float s_dq[3 * 64]; __shared__ float s_t[8][4 * 72];
+  if (tid < 192) s_dq[tid] = reinterpret_cast<const float*>(f.blob + f.dq_off[0])[tid];
+  __syncthreads();
+  const int by = quarter * 8 + warp; if (by >= h) return;
+  const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; float* st = s_t[warp];
+  const size_t tile_row = size_t((cy0 + by) >> 3) * f.xt;
+#pragma unroll 1
+  for (int it = 0; it < 8; it++) {
+    const int bx = it * 4 + b; const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const bool valid = bx < w && f.acs[o] == 0x80;   // strategy 0 (DCT8), first (only) cell
+    float scale = 0.f, kx = 0.f, kb = 0.f;
+    if (valid) { scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = tile_row + ((cx0 + bx) >> 3); kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor; kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor; }
+    float y8[8];
+#pragma unroll
+    for (int ci = 0; ci < 3; ci++) {
+      const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; float v[8];
+      int4 raw = make_int4(0, 0, 0, 0); if (valid) raw = *reinterpret_cast<const int4*>(coef + c * 65536 + (by * 32 + bx) * 64 + r * 8);
+      const int q[8] = {int(short(raw.x & 0xffff)), raw.x >> 16, int(short(raw.y & 0xffff)), raw.y >> 16, int(short(raw.z & 0xffff)), raw.z >> 16, int(short(raw.w & 0xffff)), raw.w >> 16};
+      const float mulc = c == 1 ? scale : c == 0 ? scale * f.xm : scale * f.bm, kc = c == 0 ? kx : kb, b1 = f.quant_bias[c], b3 = f.quant_bias[3];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { float a = AdjustQuantBiasDev(q[j], b1, b3) * s_dq[c * 64 + r * 8 + j] * mulc; if (c == 1) y8[j] = a; else a += kc * y8[j]; v[j] = a; }
+      if (valid && r == 0) v[0] = f.lf_src[c * lfplane + o];   // LLF of an 8x8 block is the LF sample itself
+      // storage row r holds S[hf = r][vf = 0..7]: transform along vf -> T[hf = r][y]
+      float t[8];
+#pragma unroll
+      for (int y = 0; y < 8; y++) { float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) a = fmaf(v[j], kCos8[j * 8 + y], a); t[y] = a; }
+      __syncwarp();
+      *reinterpret_cast<float4*>(st + b * 72 + r * 8) = make_float4(t[0], t[1], t[2], t[3]); *reinterpret_cast<float4*>(st + b * 72 + r * 8 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+      __syncwarp();
+      float u[8];
+#pragma unroll
+      for (int hf = 0; hf < 8; hf++) u[hf] = st[b * 72 + hf * 8 + r];   // lane (b, y = r) gathers T[hf][y]
+      float px[8];
+#pragma unroll
+      for (int x = 0; x < 8; x++) { float a = 0.f;
+#pragma unroll
+        for (int hf = 0; hf < 8; hf++) a = fmaf(u[hf], kCos8[hf * 8 + x], a); px[x] = a; }
+      if (valid) { float* out = f.xyb + c * plane + (size_t(cy0 + by) * 8 + r) * f.xpad + size_t(cx0 + bx) * 8; *reinterpret_cast<float4*>(out) = make_float4(px[0], px[1], px[2], px[3]); *reinterpret_cast<float4*>(out + 4) = make_float4(px[4], px[5], px[6], px[7]); }
+    }
+  }
+}
+
 static const int kReconWarps = 8;
 // dynamic smem per warp: Sy[1024] Sc[1024] T[1024] floats
 __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* fp) {
   const DFrame& f = *fp; const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (f.group_other[g] == 0) return;   // every varblock of this group is a DCT8: k_reconstruct_dct8 did all the work
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
   extern __shared__ float smem[]; float* Sy = smem + warp * 3072; float* Sc = Sy + 1024; float* T = Sc + 1024;
   const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const DTables& tb = *f.tables;
@@ -90,7 +145,7 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
   for (int cell = warp; cell < 1024; cell += kReconWarps) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
     const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
-    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw > 4 || bh > 4) continue;
+    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw > 4 || bh > 4 || s == 0) continue;   // DCT8 is handled by k_reconstruct_dct8
     const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(f.blob + f.dq_off[QuantTableOf(s)]);
     const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
     const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
@@ -305,7 +360,7 @@ __global__ void k_output_int(const DFrame* fp) {
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st) {
   static bool attr = false; size_t smem = size_t(kReconWarps) * 3072 * sizeof(float);
   if (!attr) { cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr = true; }
-  k_reconstruct<<<h.num_groups, kReconWarps * 32, smem, st>>>(d); CountLaunch();
+  k_reconstruct_dct8<<<h.num_groups * 4, 256, 0, st>>>(h); k_reconstruct<<<h.num_groups, kReconWarps * 32, smem, st>>>(d); CountLaunch(2);
 }
 // Runs gaborish + EPF; ping-pongs between xyb and xyb_tmp. Returns the buffer holding the result.
 void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {

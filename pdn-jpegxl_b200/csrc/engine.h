@@ -26,6 +26,9 @@ struct DecodeRequest {
   bool device_output = false;   // leave pixels in device memory (bench `value`: inputs/outputs resident in HBM)
   const uint8_t* device_input = nullptr;   // optional: the same file bytes already resident in device memory
   int device = -1;              // -1: current device
+  uint8_t* out_device = nullptr;    // optional: decode straight into this device buffer (out_capacity bytes)
+  uint8_t* out_pinned = nullptr;    // optional: copy the pixels straight into this page-locked host buffer (out_capacity bytes)
+  size_t out_capacity = 0;
 };
 
 struct StageTimes { float h2d = 0, lf = 0, ac = 0, recon = 0, filters = 0, output = 0, d2h = 0, total = 0; };
@@ -52,6 +55,8 @@ bool DecodeDebugCoeffs(const std::shared_ptr<DecodeJob>& job, std::vector<int16_
 bool CudaAvailable(std::string* why);
 void TrimPools();
 void DumpHostTrace();
+void* PinnedGet(size_t bytes);            // cached page-locked host memory (cudaHostAlloc costs far more than a decode)
+void PinnedPut(void* p, size_t bytes);
 
 // ---- encoder
 struct EncodeRequest {
