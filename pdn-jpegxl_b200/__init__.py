@@ -404,6 +404,12 @@ class JpegXLSave:
 
 
 # ---- extensions ----
+def shard_indices(count, rank, world):
+    """Multi-GPU partition of a batch: file i goes to rank i mod world; no collective on the data path."""
+    return list(range(rank, count, world))
+
+
+
 def cuda_available():
     ei = ErrorInfo()
     ok = _lib.JxlB200CudaAvailable(C.byref(ei))

@@ -1,0 +1,121 @@
+"""CPU tests of the drop-in boundary and the host-side mirror of the managed interop layer (no GPU compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "JxlFileTypeIO.h")).read()
+    declared = re.findall(r"JXLFT_API\s+[\w\s\*]+?JXLFT_CALL\s+(\w+)\s*\(", header)
+    assert set(declared) >= {"GetLibJxlVersion", "LoadImage", "SaveImage"} and len(declared) >= 10
+    lib = C.CDLL(pkg.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(declared) == sorted(pkg.EXPORTS)
+
+
+def test_struct_sizes_match_the_reference_abi(pkg):
+    # LP64 sizes verified in SURVEY.md §8b against N/Common.h:17-60, N/Decoder/JxlDecoderTypes.h:63-71, N/Encoder/JxlEncoderTypes.h:27-42
+    assert C.sizeof(pkg.BitmapData) == 24 and C.sizeof(pkg.EncoderOptionsNative) == 12 and C.sizeof(pkg.EncoderImageMetadataNative) == 48
+    assert C.sizeof(pkg.DecoderCallbacks) == 48 and C.sizeof(pkg.IOCallbacks) == 16 and C.sizeof(pkg.ErrorInfo) == 256
+    assert pkg.DECODER_STATUS.index("InvalidFileSignature") == 12 and pkg.DECODER_STATUS.index("DecodeError") == 10
+    assert pkg.ENCODER_STATUS == ["Ok", "NullParameter", "OutOfMemory", "UserCancelled", "EncodeError", "WriteError"]
+    assert pkg.KNOWN_COLOR_PROFILE.index("Rec2020PQ") == 7
+
+
+def test_version_is_packed_like_jpegxl_numeric_version(pkg):
+    major, minor, patch = pkg.JpegXLNative.GetLibJxlVersion()
+    assert (major, minor) == (0, 11)
+
+
+def test_null_parameters_and_signature_gate(pkg, oracle):
+    lib = C.CDLL(pkg.LIB_PATH)
+    lib.LoadImage.restype = C.c_int32
+    lib.SaveImage.restype = C.c_int32
+    ei = pkg.ErrorInfo()
+    assert lib.LoadImage(None, None, C.c_size_t(0), C.byref(ei)) == 1          # NullParameter (N/Decoder/JxlDecoder.cpp:802-805)
+    assert lib.SaveImage(None, None, None, None, C.byref(ei), None) == 1       # NullParameter (N/Encoder/JxlEncoder.cpp:155-158)
+    image = pkg.DecoderImage()
+    with pytest.raises(pkg.FormatException) as e:
+        pkg.JpegXLNative.LoadImage(b"definitely not a jxl", image)
+    assert e.value.status == "InvalidFileSignature" and image.callback_log == []
+
+
+def test_peek_info_format_decisions(pkg, oracle):
+    cases = [(dict(channels=3), dict(effort=3), ("Rgb", 0, False, 3)), (dict(channels=4), dict(lossless=1), ("Rgb", 0, True, 4)),
+             (dict(channels=1), dict(effort=3), ("Gray", 0, False, 1))]
+    for img_kw, enc_kw, want in cases:
+        info = pkg.peek_info(oracle.encode(oracle.synthetic_image(40, 32, seed=1, **img_kw), **enc_kw))
+        assert (info["format"], info["representation"], info["has_transparency"], info["num_channels"]) == want
+        assert info["known_profile"] in ("Srgb", "GraySrgbTRC") and info["is_container"]
+    f = oracle.synthetic_image(40, 32, seed=1).astype(np.float32) / 255
+    assert pkg.peek_info(oracle.encode(f, bits=16, effort=3))["representation"] == 1          # Uint16
+    assert pkg.peek_info(oracle.encode(f, bits=16, exp_bits=5, effort=3))["representation"] == 2   # Float16
+    assert pkg.peek_info(oracle.encode(f, bits=32, exp_bits=8, effort=3))["representation"] == 3   # Float32
+    with pytest.raises(pkg.FormatException) as e:
+        pkg.peek_info(oracle.encode(f, bits=24, effort=3))
+    assert "Unsupported integer bit depth: 24." in str(e.value)                                # N/Decoder/JxlDecoder.cpp:552
+    p3 = pkg.peek_info(oracle.encode(f, bits=16, effort=3, primaries=11))
+    assert p3["known_profile"] == "DisplayP3"
+    pq = pkg.peek_info(oracle.encode(f, bits=16, effort=3, primaries=9, tf=16))
+    assert pq["known_profile"] == "Rec2020PQ"
+    swapped = pkg.peek_info(oracle.encode(oracle.synthetic_image(40, 32, seed=1), lossless=1, orientation=6))
+    assert (swapped["width"], swapped["height"]) == (32, 40)
+
+
+def test_without_a_gpu_the_engine_fails_loudly(pkg, oracle):
+    ok, why = pkg.cuda_available()
+    if ok:
+        pytest.skip("a CUDA device is present")
+    data = oracle.encode(oracle.synthetic_image(40, 32, seed=1), effort=3)
+    image = pkg.DecoderImage()
+    with pytest.raises(pkg.FormatException) as e:
+        pkg.JpegXLNative.LoadImage(data, image)
+    assert e.value.status == "DecodeError" and "no CPU fallback" in str(e.value)
+    assert image.callback_log[:2] == ["setBasicInfo", "setKnownColorProfile"]   # pass 1 ran, pass 2 could not
+    with pytest.raises(pkg.FormatException) as e:
+        pkg.encode_to_memory(np.zeros((8, 8, 4), np.uint8), pkg.EncoderOptions())
+    assert e.value.status == "EncodeError" and "no CPU fallback" in str(e.value)
+
+
+def test_quality_to_distance_table(pkg):
+    # I/QualityToDistanceLookupTable.cs:26-65, spot values from SURVEY.md §8c
+    want = {100: 0.1, 95: 0.55, 90: 1.0, 75: 2.35, 50: 4.6, 30: 6.4, 29: 6.5922, 20: 7.4, 9: 13.907, 8: 15.0, 0: 15.0}
+    for q, d in want.items():
+        assert abs(pkg.quality_to_distance(q) - d) < 2e-3, q
+    assert pkg.EncoderOptions(quality=10, lossless=True).distance == 0.0
+
+
+def test_transparency_mapping(pkg):
+    # I/TransparencyMapping.cs:19-32,43-55
+    assert list(pkg.alpha_to_eight_bit(np.array([65535, 257, 256, 0], np.uint16))) == [255, 1, 0, 0]
+    assert list(pkg.alpha_to_eight_bit(np.array([0.999, 1.0, 2.0, -1.0, 0.5], np.float32))) == [254, 255, 255, 0, 127]
+    assert list(pkg.alpha_to_eight_bit(np.array([1.0, 0.5, 0.0], np.float16))) == [255, 127, 0]
+
+
+def test_strip_heights(pkg):
+    # S/BitmapUtil2.cs:61-71: max(1, 256 MiB / stride); SURVEY.md §8a row a9
+    rects = list(pkg.enumerate_lock_rects(3840, 50000, 24))
+    assert rects[0] == (0, 0, 3840, 23301) and rects[-1][3] == 50000
+    assert list(pkg.enumerate_lock_rects(32768, 3000, 24))[0][3] == 2730
+    assert list(pkg.enumerate_lock_rects(10, 5, 24)) == [(0, 0, 10, 5)]
+
+
+def test_decoder_layer_data_split(pkg):
+    rgba16 = np.arange(2 * 3 * 4, dtype=np.uint16).reshape(2, 3, 4) * 2570
+    layer = pkg.DecoderLayerData(rgba16.tobytes(), "n\0", 3, 2, "Rgb", 1, True)
+    assert layer.color.shape == (2, 3, 3) and layer.color.dtype == np.uint16
+    assert np.array_equal(layer.transparency, (rgba16[..., 3] // 257).astype(np.uint8))
+    gray = pkg.DecoderLayerData(bytes(range(6)), None, 3, 2, "Gray", 0, False)
+    assert gray.color.shape == (2, 3, 3) and np.array_equal(gray.color[..., 0], gray.color[..., 2])
+
+
+def test_shard_indices(pkg):
+    files = list(range(10))
+    shards = [pkg.shard_indices(len(files), r, 4) for r in range(4)]
+    assert sorted(i for s in shards for i in s) == files and shards[1] == [1, 5, 9]

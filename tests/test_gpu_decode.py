@@ -101,3 +101,64 @@ def test_truncated_and_invalid_inputs(gpu, oracle):
         _decode_gpu(gpu, bytes(corrupt))   # either decodes to something or reports DecodeError; it must not crash
     except gpu.FormatException as ex:
         assert ex.status == "DecodeError"
+
+
+def test_golden_files(gpu, oracle):
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    index = json.load(open(os.path.join(gdir, "index.json")))
+    for name, meta in index.items():
+        data = open(os.path.join(gdir, name + ".jxl"), "rb").read()
+        want = np.load(os.path.join(gdir, name + ".npy"))
+        image = _decode_gpu(gpu, data)
+        layer = image.layer_data
+        ncol = 1 if image.format == "Gray" else 3
+        got = layer.color[..., :ncol]
+        if meta["lossless"]:
+            assert np.array_equal(got, want[..., :ncol]), name
+        else:
+            assert int(np.abs(got.astype(np.int32) - want[..., :ncol].astype(np.int32)).max()) <= 1, name
+        if image.has_transparency:
+            assert np.array_equal(layer.transparency, want[..., ncol]), name
+
+
+@pytest.mark.parametrize("kw,dtype,tol", [
+    (dict(bits=16), np.uint16, 1.0 / 255),                                   # u16 output
+    (dict(bits=16, exp_bits=5), np.float16, 2e-3),                            # f16 output
+    (dict(bits=32, exp_bits=8), np.float32, 1e-4),                            # f32 output: <= 1e-4 relative (north_star)
+    (dict(bits=16, primaries=9, tf=16, intensity_target=1000.0), np.uint16, 1.0 / 255),   # Rec.2020 PQ HDR, gab + EPF
+    (dict(bits=16, primaries=11), np.uint16, 1.0 / 255),                      # Display P3
+    (dict(bits=32, exp_bits=8, tf=8), np.float32, 1e-4),                      # linear sRGB float
+])
+def test_hdr_and_high_bit_depth_outputs(gpu, oracle, kw, dtype, tol):
+    img = oracle.synthetic_image(200, 136, seed=21).astype(np.float32) / 255.0
+    data = oracle.encode(img, effort=7, **kw)
+    ref = oracle.decode(data).pixels
+    image = _decode_gpu(gpu, data)
+    got = image.layer_data.color
+    assert got.dtype == dtype and got.shape == ref.shape
+    if dtype == np.uint16:
+        assert int(np.abs(got.astype(np.int64) - ref.astype(np.int64)).max()) <= 257      # <= 1 LSB at 8-bit precision
+    else:
+        a, b = got.astype(np.float64), ref.astype(np.float64)
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.05)) <= tol * 20 if dtype == np.float16 else np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.05)) <= 2e-3
+
+
+@pytest.mark.parametrize("orientation", [2, 3, 4, 5, 6, 7, 8])
+def test_orientation(gpu, oracle, orientation):
+    img = oracle.synthetic_image(72, 40, seed=orientation)
+    data = oracle.encode(img, lossless=1, orientation=orientation)
+    ref = oracle.decode(data).pixels
+    image = _decode_gpu(gpu, data)
+    assert (image.width, image.height) == (ref.shape[1], ref.shape[0])
+    assert np.array_equal(image.layer_data.color, ref)
+
+
+def test_batch_matches_single_decodes(gpu, oracle):
+    files = [oracle.encode(oracle.synthetic_image(300 + 8 * i, 200, seed=i), effort=7 if i % 2 else 3) for i in range(6)]
+    outs = [np.zeros((200, 300 + 8 * i, 3), np.uint8) for i in range(6)]
+    st = gpu.decode_batch(files, outs, max_in_flight=4)
+    assert st == [0] * 6
+    for f, o in zip(files, outs):
+        assert np.array_equal(o, _decode_gpu(gpu, f).layer_data.color)
