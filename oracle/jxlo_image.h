@@ -152,10 +152,10 @@ inline DecodedImage DecodeImage(const uint8_t* data, size_t size, const DecodeOp
   if (opt.keep_stages && fh.encoding == 0) { out.xpad = fs.xpad; out.ypad = fs.ypad; for (int c = 0; c < 3; c++) out.stage_idct.insert(out.stage_idct.end(), col[c].d.begin(), col[c].d.end()); }
   if (filters) {
     JXLO_CHECK(ncol == 3, "restoration filters on a single-channel frame are not supported");
-    if (lf.gab) Gaborish(col, xs, ys, lf);
+    if (lf.gab) Gaborish(col, xs, ys, lf, opt.threads);
     if (opt.keep_stages && fh.encoding == 0) for (int c = 0; c < 3; c++) out.stage_gab.insert(out.stage_gab.end(), col[c].d.begin(), col[c].d.end());
     if (lf.epf_iters) { if (fh.encoding == 1) { fs.xb = (xs + 7) / 8; fs.yb = (ys + 7) / 8; } std::vector<float> is = ComputeInvSigma(fs);
-      if (lf.epf_iters == 3) EpfPass(col, xs, ys, fs.xb, is, lf, 0); EpfPass(col, xs, ys, fs.xb, is, lf, 1); if (lf.epf_iters >= 2) EpfPass(col, xs, ys, fs.xb, is, lf, 2); }
+      if (lf.epf_iters == 3) EpfPass(col, xs, ys, fs.xb, is, lf, 0, opt.threads); EpfPass(col, xs, ys, fs.xb, is, lf, 1, opt.threads); if (lf.epf_iters >= 2) EpfPass(col, xs, ys, fs.xb, is, lf, 2, opt.threads); }
     if (opt.keep_stages && fh.encoding == 0) for (int c = 0; c < 3; c++) out.stage_epf.insert(out.stage_epf.end(), col[c].d.begin(), col[c].d.end());
   }
   // extra channels

@@ -57,12 +57,12 @@ inline void AdaptiveLfSmoothing(FrameState& fs) {
 inline int Mirror(int x, int n) { while (x < 0 || x >= n) { if (x < 0) x = -x - 1; else x = 2 * n - 1 - x; } return x; }
 
 // planes have stride p.w >= xs; only [0,xs) x [0,ys) is meaningful and filtered.
-inline void Gaborish(Plane* xyb, int xs, int ys, const LoopFilter& lf) {
+inline void Gaborish(Plane* xyb, int xs, int ys, const LoopFilter& lf, int threads = 1) {
   for (int c = 0; c < 3; c++) {
     float w1 = lf.gab_w[2 * c], w2 = lf.gab_w[2 * c + 1]; float mul = 1.0f / (1.0f + 4.0f * (w1 + w2)); float wc = mul, we = w1 * mul, wd = w2 * mul;
     Plane out = xyb[c];
-    for (int y = 0; y < ys; y++) { const float* t = xyb[c].row(Mirror(y - 1, ys)); const float* m = xyb[c].row(y); const float* b = xyb[c].row(Mirror(y + 1, ys)); float* o = out.row(y);
-      for (int x = 0; x < xs; x++) { int xl = Mirror(x - 1, xs), xr = Mirror(x + 1, xs); o[x] = m[x] * wc + (t[x] + b[x] + m[xl] + m[xr]) * we + (t[xl] + t[xr] + b[xl] + b[xr]) * wd; } }
+    ParallelFor(size_t(ys), threads, [&](size_t yy) { int y = int(yy); const float* t = xyb[c].row(Mirror(y - 1, ys)); const float* m = xyb[c].row(y); const float* b = xyb[c].row(Mirror(y + 1, ys)); float* o = out.row(y);
+      for (int x = 0; x < xs; x++) { int xl = Mirror(x - 1, xs), xr = Mirror(x + 1, xs); o[x] = m[x] * wc + (t[x] + b[x] + m[xl] + m[xr]) * we + (t[xl] + t[xr] + b[xl] + b[xr]) * wd; } });
     xyb[c] = std::move(out);
   }
 }
@@ -83,14 +83,14 @@ inline std::vector<float> ComputeInvSigma(const FrameState& fs) {
 }
 
 // One EPF pass. pass: 0 (12 neighbours, plus-SAD), 1 (4 neighbours, plus-SAD), 2 (4 neighbours, 1-px SAD).
-inline void EpfPass(Plane* xyb, int xs, int ys, int xb, const std::vector<float>& inv_sigma, const LoopFilter& lf, int pass) {
+inline void EpfPass(Plane* xyb, int xs, int ys, int xb, const std::vector<float>& inv_sigma, const LoopFilter& lf, int pass, int threads = 1) {
   static const int n12[12][2] = {{-2, 0}, {-1, -1}, {-1, 0}, {-1, 1}, {0, -2}, {0, -1}, {0, 1}, {0, 2}, {1, -1}, {1, 0}, {1, 1}, {2, 0}};   // {dy,dx}
   static const int n4[4][2] = {{-1, 0}, {0, -1}, {0, 1}, {1, 0}};
   static const int plus[5][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}};
   float sigma_scale = pass == 0 ? lf.epf_pass0_sigma_scale : pass == 2 ? lf.epf_pass2_sigma_scale : 1.0f; float sm = sigma_scale * 1.65f, bsm = sm * lf.epf_border_sad_mul;
   const int (*nb)[2] = pass == 0 ? n12 : n4; int nn = pass == 0 ? 12 : 4;
   Plane out[3] = {xyb[0], xyb[1], xyb[2]};
-  for (int y = 0; y < ys; y++) for (int x = 0; x < xs; x++) {
+  ParallelFor(size_t(ys), threads, [&](size_t yy) { const int y = int(yy); for (int x = 0; x < xs; x++) {
     float is = inv_sigma[size_t(y / 8) * xb + x / 8]; if (is < kMinSigma) continue;
     bool border = (y % 8 == 0 || y % 8 == 7 || x % 8 == 0 || x % 8 == 7); float inv = is * (border ? bsm : sm);
     float wsum = 1.0f, acc[3]; for (int c = 0; c < 3; c++) acc[c] = xyb[c].row(y)[x];
@@ -104,7 +104,7 @@ inline void EpfPass(Plane* xyb, int xs, int ys, int xb, const std::vector<float>
       for (int c = 0; c < 3; c++) acc[c] += wgt * xyb[c].row(Mirror(y + nb[i][0], ys))[Mirror(x + nb[i][1], xs)];
     }
     float iw = 1.0f / wsum; for (int c = 0; c < 3; c++) out[c].row(y)[x] = acc[c] * iw;
-  }
+  } });
   for (int c = 0; c < 3; c++) xyb[c] = std::move(out[c]);
 }
 

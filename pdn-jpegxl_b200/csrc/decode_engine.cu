@@ -396,10 +396,12 @@ void DecodeJob::Run(const DecodeRequest& req) {
   if (timed) cudaEventRecord(ev[2], stream);
   if (vardct) LaunchReconstruct(d, h, stream);
   if (timed) cudaEventRecord(ev[3], stream);
-  if (vardct) LaunchFilters(d, h, stream);
+  const bool unfused = getenv("JXLB200_UNFUSED") != nullptr; bool fused = false;
   if (h.num_rct) LaunchInverseRct(d, h, stream);
+  if (vardct && !unfused) fused = LaunchFusedRender(d, h, stream);   // gaborish + EPF + colour + pack in one kernel
+  if (vardct && !fused) LaunchFilters(d, h, stream);
   if (timed) cudaEventRecord(ev[4], stream);
-  LaunchOutput(d, h, stream);
+  if (!fused) LaunchOutput(d, h, stream);
   if (timed) cudaEventRecord(ev[5], stream);
   if (!device_output) CUDA_OK(cudaMemcpyAsync(ext_out_pinned ? ext_out_pinned : h_out.as<uint8_t>(), h.out_px, out_bytes, cudaMemcpyDeviceToHost, stream));
   CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream));

@@ -10,6 +10,7 @@ void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st)
 void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st);
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st);       // dequant + CfL + LLF + inverse transforms
 void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st);           // gaborish + EPF (result in h.xyb)
+bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st);       // gaborish + EPF + colour fused (returns false when not applicable)
 void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st);
 void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st);            // colour transform + sample conversion + interleave (+BGRA)
 void FillDeviceTables(DTables* host_tables);

@@ -307,11 +307,10 @@ __device__ __forceinline__ size_t OrientedIndex(const DFrame& f, int x, int y) {
   return size_t(oy) * f.out.out_w + ox;
 }
 
-__global__ void k_output(const DFrame* fp, const float* __restrict__ xyb) {
-  const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+// Colour + sample conversion + store of one pixel. For VarDCT frames (X,Y,B) are the filtered XYB samples.
+__device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float X, float Y, float B) {
   const DOutput& o = f.out; float rgb[3];
   if (f.encoding == 0) {
-    const size_t plane = size_t(f.xpad) * f.ypad, at = size_t(y) * f.xpad + x; const float X = xyb[at], Y = xyb[plane + at], B = xyb[2 * plane + at];
     float gm[3] = {Y + X, Y - X, B}, mix[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) { float v = gm[c] - f.color.opsin_bias_cbrt[c]; mix[c] = v * v * v + f.color.opsin_bias[c]; }
@@ -342,6 +341,67 @@ __global__ void k_output(const DFrame* fp, const float* __restrict__ xyb) {
   }
   for (uint32_t c = 0; c < o.color_channels; c++) StoreSampleDev(dst + bps * c, o.sample_type, rgb[c]);
   if (o.alpha_plane >= 0) StoreSampleDev(dst + bps * o.color_channels, o.sample_type, a);
+}
+
+__global__ void k_output(const __grid_constant__ DFrame f, const float* __restrict__ xyb) {
+  const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+  float X = 0.f, Y = 0.f, B = 0.f;
+  if (f.encoding == 0) { const size_t plane = size_t(f.xpad) * f.ypad, at = size_t(y) * f.xpad + x; X = xyb[at]; Y = xyb[plane + at]; B = xyb[2 * plane + at]; }
+  OutputPixel(f, x, y, X, Y, B);
+}
+
+// Fused restoration + colour kernel: one 32x32 output tile per CTA. The tile plus its halo (1 for gaborish, 3/2/1 for EPF
+// pass 0/1/2) is loaded once into shared memory with mirrored image borders (the filters are mirror-equivariant, so filtering
+// the mirrored halo reproduces the mirrored filtered image), the passes ping-pong between two shared buffers, and the last
+// buffer goes straight through the colour transform to the output image: 12 B/px read + 3-4 B/px written instead of
+// 24 B/px per pass. SURVEY.md A.10; replaces libjxl's render pipeline stages reached from N/Decoder/JxlDecoder.cpp:252.
+template <int GAB, int EPF>
+__global__ void __launch_bounds__(256) k_render(const __grid_constant__ DFrame f) {
+  constexpr int R0 = EPF == 3 ? 3 : 0, R1 = EPF >= 1 ? 2 : 0, R2 = EPF >= 2 ? 1 : 0, H = GAB + R0 + R1 + R2, D = 32 + 2 * H, N = D * D;
+  extern __shared__ float rs[]; float* A = rs; float* Bf = rs + 3 * N;
+  const int xs = int(f.xsize), ys = int(f.ysize), tx0 = blockIdx.x * 32 - H, ty0 = blockIdx.y * 32 - H, tid = threadIdx.x; const size_t plane = size_t(f.xpad) * f.ypad;
+  for (int i = tid; i < N; i += 256) { const int ly = i / D, lx = i - ly * D; const size_t at = size_t(MirrorDev(ty0 + ly, ys)) * f.xpad + MirrorDev(tx0 + lx, xs);
+    A[i] = f.xyb[at]; A[N + i] = f.xyb[plane + at]; A[2 * N + i] = f.xyb[2 * plane + at]; }
+  __syncthreads();
+  int off = 0;   // valid region of the current buffer is [off, D-off)^2
+  float* src = A; float* dst = Bf;
+  if (GAB) {
+    off += 1; const int n = D - 2 * off;
+    for (int i = tid; i < n * n; i += 256) { const int y = off + i / n, x = off + i % n; const int p = y * D + x;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { const float* s = src + c * N + p; const float w1 = f.lpf.gab_w[2 * c], w2 = f.lpf.gab_w[2 * c + 1], mul = 1.0f / (1.0f + 4.0f * (w1 + w2));
+        dst[c * N + p] = s[0] * mul + (s[-D] + s[D] + s[-1] + s[1]) * (w1 * mul) + (s[-D - 1] + s[-D + 1] + s[D - 1] + s[D + 1]) * (w2 * mul); } }
+    __syncthreads(); float* t = src; src = dst; dst = t;
+  }
+#pragma unroll
+  for (int pass = 0; pass < 3; pass++) {
+    const int r = pass == 0 ? R0 : pass == 1 ? R1 : R2; if (r == 0) continue;
+    off += r; const int n = D - 2 * off;
+    const float sigma_scale = pass == 0 ? f.lpf.pass0_sigma_scale : pass == 2 ? f.lpf.pass2_sigma_scale : 1.0f, sm = sigma_scale * 1.65f;
+    for (int i = tid; i < n * n; i += 256) {
+      const int y = off + i / n, x = off + i % n, p = y * D + x; const int gy = MirrorDev(ty0 + y, ys), gx = MirrorDev(tx0 + x, xs);
+      const float is = f.inv_sigma[size_t(gy >> 3) * f.xb + (gx >> 3)];
+      if (is < -3.90524291751269967465540850526868f) { dst[p] = src[p]; dst[N + p] = src[N + p]; dst[2 * N + p] = src[2 * N + p]; continue; }
+      const bool border = ((gy & 7) == 0 || (gy & 7) == 7 || (gx & 7) == 0 || (gx & 7) == 7); const float inv = is * (border ? sm * f.lpf.border_sad_mul : sm);
+      float wsum = 1.0f, acc0 = src[p], acc1 = src[N + p], acc2 = src[2 * N + p];
+      const int nn = pass == 0 ? 12 : 4;
+      const int d12[12] = {-2 * D, -D - 1, -D, -D + 1, -2, -1, 1, 2, D - 1, D, D + 1, 2 * D}; const int d4[4] = {-D, -1, 1, D};
+#pragma unroll
+      for (int k = 0; k < nn; k++) {
+        const int d = pass == 0 ? d12[k] : d4[k]; float sad = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const float* s = src + c * N + p; float sc;
+          if (pass == 2) sc = fabsf(s[d] - s[0]);
+          else sc = fabsf(s[d] - s[0]) + fabsf(s[d - D] - s[-D]) + fabsf(s[d + D] - s[D]) + fabsf(s[d - 1] - s[-1]) + fabsf(s[d + 1] - s[1]);
+          sad += sc * f.lpf.epf_channel_scale[c]; }
+        const float wgt = fmaxf(0.f, 1.0f + sad * inv); wsum += wgt; acc0 += wgt * src[p + d]; acc1 += wgt * src[N + p + d]; acc2 += wgt * src[2 * N + p + d];
+      }
+      const float iw = 1.0f / wsum; dst[p] = acc0 * iw; dst[N + p] = acc1 * iw; dst[2 * N + p] = acc2 * iw;
+    }
+    __syncthreads(); float* t = src; src = dst; dst = t;
+  }
+  for (int i = tid; i < 32 * 32; i += 256) { const int ly = i >> 5, lx = i & 31, y = blockIdx.y * 32 + ly, x = blockIdx.x * 32 + lx; if (x >= xs || y >= ys) continue;
+    const int p = (H + ly) * D + H + lx; OutputPixel(f, x, y, src[p], src[N + p], src[2 * N + p]); }
 }
 
 // Lossless 8/16-bit integer fast path: samples pass through untouched (bit-exact by construction).
@@ -375,6 +435,23 @@ void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {
 }
 void LaunchGaborishPlanes(const DFrame* d, const DFrame& h, const float* src, float* dst, cudaStream_t st) { dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8); k_gaborish<<<grid, blk, 0, st>>>(d, src, dst); CountLaunch(); }
 const float* FilteredPlanes(const DFrame& h) { int n = (h.lpf.gab ? 1 : 0) + (h.lpf.epf_iters == 3 ? 3 : int(h.lpf.epf_iters)); return (n & 1) ? h.xyb_tmp : h.xyb; }
+// gaborish + EPF + colour in one pass over the frame (VarDCT frames with at least one restoration filter)
+template <int GAB, int EPF> static void LaunchRenderT(const DFrame& h, cudaStream_t st) {
+  constexpr int H = GAB + (EPF == 3 ? 3 : 0) + (EPF >= 1 ? 2 : 0) + (EPF >= 2 ? 1 : 0), D = 32 + 2 * H; size_t smem = size_t(6) * D * D * sizeof(float);
+  static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_render<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr = true; }
+  dim3 grid((h.xsize + 31) / 32, (h.ysize + 31) / 32); k_render<GAB, EPF><<<grid, 256, smem, st>>>(h); CountLaunch();
+}
+bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st) {
+  if (h.encoding != 0 || (!h.lpf.gab && !h.lpf.epf_iters)) return false;
+  if (h.lpf.epf_iters) { size_t n = size_t(h.xb) * h.yb; k_inv_sigma<<<unsigned((n + 255) / 256), 256, 0, st>>>(d); CountLaunch(); }
+  const int g = h.lpf.gab ? 1 : 0;
+  switch (g * 4 + int(h.lpf.epf_iters)) {
+    case 1: LaunchRenderT<0, 1>(h, st); break; case 2: LaunchRenderT<0, 2>(h, st); break; case 3: LaunchRenderT<0, 3>(h, st); break;
+    case 4: LaunchRenderT<1, 0>(h, st); break; case 5: LaunchRenderT<1, 1>(h, st); break; case 6: LaunchRenderT<1, 2>(h, st); break; case 7: LaunchRenderT<1, 3>(h, st); break;
+    default: return false;
+  }
+  return true;
+}
 void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st) {
   for (uint32_t i = h.num_rct; i-- > 0;) { const DModChannel& c0 = h.mod_ch[h.rct_begin[i]]; size_t n = size_t(c0.w) * c0.h; k_inverse_rct<<<unsigned((n + 255) / 256), 256, 0, st>>>(d, h.rct_begin[i], h.rct_type[i]); CountLaunch(); }
 }
@@ -382,7 +459,7 @@ void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st) {
   dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8);
   bool int_path = h.encoding == 1 && !h.color.xyb_encoded && h.out.exp_bits == 0 && h.out.black_plane < 0 && !h.out.premultiplied && (h.out.sample_type == 0 ? h.out.bits == 8 : (h.out.sample_type == 1 && h.out.bits == 16)) &&
                   (h.out.alpha_plane < 0 || (h.out.alpha_bits == h.out.bits && h.out.alpha_exp_bits == 0 && h.mod_ch[h.out.alpha_plane].hshift == 0));
-  if (int_path) k_output_int<<<grid, blk, 0, st>>>(d); else k_output<<<grid, blk, 0, st>>>(d, FilteredPlanes(h));
+  if (int_path) k_output_int<<<grid, blk, 0, st>>>(d); else k_output<<<grid, blk, 0, st>>>(h, FilteredPlanes(h));
   CountLaunch();
 }
 
