@@ -244,6 +244,9 @@ def main():
         stage_bytes = {"lf": (comp_px * 0.12 + (12 + 3) / 64.0), "ac": (comp_px * 0.88 + 6.0), "recon": 18.0, "filters": 24.0 * 2, "output": 15.0}
         names = {"lf": "k_lf_group (LF coefficients + HF metadata entropy decode; latency-bound serial streams)", "ac": "k_ac_group (AC coefficient entropy decode; latency-bound serial streams)",
                  "recon": "k_reconstruct (dequant + CfL + IDCT)", "filters": "k_gaborish + k_epf<1>", "output": "k_output (XYB->sRGB + interleave)"}
+        if acc.get("output", 0.0) < 1e-3 and acc.get("filters", 0.0) > 0:   # fused path: one kernel reads XYB once and writes RGB8 once
+            stage_bytes["filters"] = 15.0
+            names["filters"] = "k_render<GAB,EPF> (gaborish + EPF + XYB->sRGB + interleave fused; XYB read once, RGB8 written once)"
         stages = {}
         for k in ("lf", "ac", "recon", "filters", "output"):
             ms = acc.get(k, 0.0)

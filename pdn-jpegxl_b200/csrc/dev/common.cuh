@@ -94,6 +94,22 @@ struct SymReader {
     if (state < 65536u) { state = (state << 16) | br.Peek(16); br.Skip(16); }
     return sym;
   }
+  __device__ __forceinline__ uint32_t ReadTokenAns(const CodeView& cv, uint32_t cluster) {
+    const uint32_t log_entry = 12 - cv.log_alpha, idx = state & 0xfff, i = idx >> log_entry, pos = idx & ((1u << log_entry) - 1);
+    const DAlias e = cv.alias[(cluster << cv.log_alpha) + i];
+    const bool g = pos >= (e.x & 0xffu); const uint32_t sym = g ? ((e.x >> 8) & 0xffu) : i, off = g ? (e.x >> 16) : 0u, freq = g ? (e.y >> 16) : (e.y & 0xffffu);
+    state = freq * (state >> 12) + off + pos;
+    if (state < 65536u) { state = (state << 16) | br.Peek(16); br.Skip(16); }
+    return sym;
+  }
+  // hybrid-uint tail for tokens >= split (info: packed per-cluster word)
+  __device__ __noinline__ uint32_t HybridSlow(uint32_t info, uint32_t t) { DHybrid h; h.split_exp = uint8_t(info & 0xff); h.msb = uint8_t((info >> 8) & 15); h.lsb = uint8_t((info >> 12) & 15); return Hybrid(h, t); }
+  __device__ __forceinline__ uint32_t ReadClusterAns(const CodeView& cv, uint32_t cl) {
+    const uint32_t info = cv.info[cl]; uint32_t t = info >> 16; if (t == 0xffffu) t = ReadTokenAns(cv, cl);
+    if (t < (1u << (info & 0xff))) return t;
+    return HybridSlow(info, t);
+  }
+  __device__ __forceinline__ uint32_t ReadAns(const CodeView& cv, uint32_t ctx) { return ReadClusterAns(cv, cv.ctx_map[ctx]); }
   __device__ __forceinline__ uint32_t Hybrid(const DHybrid h, uint32_t t) {
     uint32_t split = 1u << h.split_exp; if (t < split) return t;
     uint32_t ml = uint32_t(h.msb) + h.lsb; uint32_t nb = h.split_exp - ml + ((t - split) >> ml);

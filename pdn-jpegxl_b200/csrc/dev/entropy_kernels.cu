@@ -179,7 +179,7 @@ __device__ __noinline__ uint32_t DecodeAcCoeffs(const DFrame& f, SymReader& rd_i
       uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : nzrow[cell - 32]; else if (by == 0) pred = nzrow[cell - 1]; else pred = (uint32_t(nzrow[cell - 32]) + nzrow[cell - 1] + 1) >> 1;
       uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u; idx = idx * 13 + ord; idx = idx * (n_qf_thr + 1) + qf_idx; idx = idx * num_lf_ctxs + s_lfidx[cell]; const uint32_t bctx = bmap[idx];
       uint32_t nzb = pred > 64 ? 64 : pred; nzb = nzb < 8 ? nzb : (nzb >= 64 ? 36 : 4 + nzb / 2);
-      uint32_t nz = rd.Read(cv, ctx_offset + nzb * nbctx + bctx);
+      uint32_t nz = kSmem ? rd.ReadAns(cv, ctx_offset + nzb * nbctx + bctx) : rd.Read(cv, ctx_offset + nzb * nbctx + bctx);
       if (nz + covered > size) return kErrTooManyNz;
       { const uint8_t v = uint8_t((nz + covered - 1) >> log2c); if (covered == 1) nzrow[cell] = v; else for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) nzrow[cell + iy * 32 + ix] = v; }
       if (nz == 0) continue;
@@ -187,7 +187,7 @@ __device__ __noinline__ uint32_t DecodeAcCoeffs(const DFrame& f, SymReader& rd_i
       const uint32_t histo = ctx_offset + nbctx * 37 + 458 * bctx; uint32_t prev = nz > size / 16 ? 0 : 1; int16_t* cc = coef + c * 65536 + cell * 64;
       uint32_t nzctx = uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) * 2 + histo; uint32_t k = covered;
       do {
-        const uint32_t u = rd.Read(cv, nzctx + uint32_t(kFreqCtx[k >> log2c]) * 2 + prev); prev = u != 0;
+        const uint32_t zc = nzctx + uint32_t(kFreqCtx[k >> log2c]) * 2 + prev; const uint32_t u = kSmem ? rd.ReadAns(cv, zc) : rd.Read(cv, zc); prev = u != 0;
         if (u) {
           int32_t v = int32_t(uint32_t(UnpackSignedDev(u)) << shift); const uint32_t p = order[k], j = p >> 6; const uint32_t addr = (((j >> lbw) << 5) + (j & bwm)) * 64 + (p & 63);
           if (pass) v += cc[addr]; bad_range |= uint32_t(v + 32768) >> 16; cc[addr] = int16_t(v); nz--; nzctx = uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) * 2 + histo;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(32 * kAcGroupsPerCta) k_ac_group(const __grid_
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
   md.rd.br.Init(f.comp, start);
   uint32_t err = 0;
-  if (vardct) err = cv.AllShared() ? DecodeAcCoeffs<true>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx) : DecodeAcCoeffs<false>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx);
+  if (vardct) err = (cv.AllShared() && !cv.use_prefix) ? DecodeAcCoeffs<true>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx) : DecodeAcCoeffs<false>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx);
   if (!err) { bool need_init = true; md.rd.err = 0; DecodeModularGroupDev(md, f, g, pass, &need_init); err = md.rd.err; }
   uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
   SetError(f.err, err);

@@ -158,6 +158,28 @@ struct ModDecoder {
     }
   }
 
+  // Lean path: ANS code with every table in shared memory, no weighted predictor, int32 samples, gradient predictor,
+  // context = direct LUT of property 8 (previous residual). This is the LF-coefficient / alpha / lossless hot loop.
+  __device__ __noinline__ void DecodeRowsLean(int32_t* out, size_t stride, int w, int h) {
+    SymReader rd = this->rd; CodeView cv = this->cv; ChanLut* lut = this->lut; __builtin_assume(__isShared(lut)); cv.AssumeShared();
+    struct WriteBack { SymReader& dst; SymReader& src; __device__ ~WriteBack() { dst = src; } } wb{this->rd, rd};
+    const uint8_t* direct = lut->direct;
+    for (int y = 0; y < h; y++) {
+      int32_t* cur = out + size_t(y) * stride; const int32_t* up = cur - stride;
+      int32_t W, N, NW, NE, prev_grad = 0;
+      if (y) { N = up[0]; NE = w > 1 ? up[1] : N; W = N; NW = W; } else { N = NW = NE = 0; W = 0; }
+      int32_t ne_next = (y && w > 2) ? up[2] : NE;
+      for (int x = 0; x < w; x++) {
+        const int32_t ne_next2 = (y && x + 3 < w) ? up[x + 3] : 0;   // prefetch two ahead: independent of the symbol being decoded
+        const int32_t v = W - prev_grad; const uint32_t cl = direct[min(max(v, -128), 127) + 128];
+        const uint32_t tok = rd.ReadClusterAns(cv, cl);
+        const int32_t g = W + N - NW, lo = min(W, N), hi = max(W, N); const int32_t val = UnpackSignedDev(tok) + max(lo, min(hi, g));
+        cur[x] = val; prev_grad = g;
+        if (y) { NW = N; N = NE; NE = (x + 2 < w) ? ne_next : NE; ne_next = ne_next2; W = val; } else { W = val; N = val; NW = val; NE = val; }
+      }
+    }
+  }
+
   // Decodes one channel in raster order into out[y*stride + x]. wp_base: scratch for the weighted predictor (may be null when !uses_wp).
   __device__ void DecodeChannel(int chan, int stream_id, int32_t* out, size_t stride, int w, int h, int32_t* wp_base) {
     if (w <= 0 || h <= 0) return;
@@ -168,7 +190,8 @@ struct ModDecoder {
     BuildLut(root); const ChanLut& L = *lut;
     const bool sm = cv.AllShared() && !cv.use_prefix;
     if (wide || uses_wp) { if (L.ok) DecodeRows<long long, 1, false>(root, n, chan, stream_id, out, stride, w, h, wp_base); else DecodeRows<long long, 0, false>(root, n, chan, stream_id, out, stride, w, h, wp_base); }
-    else if (L.ok && sm && L.prop == 8 && L.predictor == 5) DecodeRows<int32_t, 2, true>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else if (L.ok && sm && L.prop == 8 && L.predictor == 5 && L.has_direct) DecodeRowsLean(out, stride, w, h);
+    else if (L.ok && L.prop == 8 && L.predictor == 5) DecodeRows<int32_t, 2, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
     else if (L.ok && sm) DecodeRows<int32_t, 1, true>(root, n, chan, stream_id, out, stride, w, h, wp_base);
     else if (L.ok) DecodeRows<int32_t, 1, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
     else DecodeRows<int32_t, 0, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
