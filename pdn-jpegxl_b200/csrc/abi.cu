@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <algorithm>
 #include <deque>
+#include <memory>
+#include <thread>
 #include <map>
 #include <chrono>
 #include <cstdio>
@@ -142,13 +144,13 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
   try {
     std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return DecoderStatus_DecodeError; }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
-    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 64)); int cur_dev = 0; cudaGetDevice(&cur_dev);
+    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 256)); int cur_dev = 0; cudaGetDevice(&cur_dev);
     // streams are created once per device and thread and reused by later batches (stream creation is not free)
     static thread_local std::map<int, std::vector<cudaStream_t>> stream_cache; std::vector<cudaStream_t>& all_streams = stream_cache[cur_dev];
     while (int(all_streams.size()) < nstreams + 1) { cudaStream_t s = nullptr; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaStreamCreate failed"); return DecoderStatus_DecodeError; } all_streams.push_back(s); }
     cudaStream_t copy_stream = all_streams[0]; std::vector<cudaStream_t> streams(all_streams.begin() + 1, all_streams.begin() + 1 + nstreams); void* pin = nullptr; size_t pin_bytes = 0;
-    struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; };
-    std::deque<InFlight> q;
+    const int batch_lanes = (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
+    struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; cudaStream_t stream = nullptr; };
     // device-resident inputs: the headers are parsed on the host, so fetch all files once through one pinned buffer (asynchronously, one sync)
     std::vector<size_t> in_off(count + 1, 0); const uint8_t* host_in = nullptr;
     if (!hostInputs) { for (int i = 0; i < count; i++) in_off[i + 1] = in_off[i] + ((dataSizes[i] + 63) & ~size_t(63));
@@ -158,24 +160,40 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
     // host outputs that are page-locked receive the pixels directly (no staging copy)
     std::vector<uint8_t> out_is_pinned(count, 0);
     if (hostOutputs) for (int i = 0; i < count; i++) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, outputs[i]) == cudaSuccess && at.type == cudaMemoryTypeHost) out_is_pinned[i] = 1; else cudaGetLastError(); }
-    auto retire = [&]() {
-      InFlight& f = q.front(); DecodeFinish(f.job, &f.res); DecoderStatus st = DecoderStatus(f.res.status);
+    const bool trace = getenv("JXLB200_TRACE") != nullptr; double acc_t[5] = {0, 0, 0, 0, 0}; double t_enq = 0, t_ret = 0; auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    // Three-phase pipeline per image (LF entropy | AC entropy | reconstruction + render): a phase is enqueued only once the image's
+    // stream has drained, so a kernel waiting on a 40 ms predecessor never sits at the head of a hardware queue shared with other
+    // streams (there are 32 queues, and up to 256 images in flight). q1/q2/q3 hold the images whose phase 1/2/3 is running.
+    std::deque<std::unique_ptr<InFlight>> q1, q2, q3; std::vector<cudaStream_t> free_streams(streams.rbegin(), streams.rend()); int next = 0, done = 0;
+    auto finish = [&](InFlight& f) {   // records the status of a finished or failed image
+      DecoderStatus st = DecoderStatus(f.res.status);
       if (st == DecoderStatus_Ok) { if (f.res.pixel_bytes > outputBytes[f.idx]) st = DecoderStatus_InvalidParameter; else if (!f.direct) memcpy(outputs[f.idx], f.res.pixels, f.res.pixel_bytes); }
       else if (first == DecoderStatus_Ok) SetErrorMessage(errorInfo, f.res.message);
+      if (trace) { const StageTimes& t = f.res.times; acc_t[0] += t.lf; acc_t[1] += t.ac; acc_t[2] += t.recon; acc_t[3] += t.filters + t.output; acc_t[4] += t.total; }
       if (statuses) statuses[f.idx] = st; if (st != DecoderStatus_Ok && first == DecoderStatus_Ok) first = st;
-      q.pop_front();
+      f.job.reset(); f.res.job.reset(); free_streams.push_back(f.stream); done++;
     };
-    const bool trace = getenv("JXLB200_TRACE") != nullptr; double t_enq = 0, t_ret = 0; auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    for (int i = 0; i < count; i++) {
-      if (int(q.size()) >= nstreams) { double t0 = now(); retire(); t_ret += now() - t0; }
-      double t0 = now();
-      q.emplace_back(); InFlight& f = q.back(); f.idx = i; DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i]; req.out_capacity = outputBytes[i];
-      if (hostInputs) req.data = datas[i]; else { req.data = host_in + in_off[i]; req.device_input = datas[i]; }
-      if (!hostOutputs) { req.out_device = outputs[i]; f.direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f.direct = true; }
-      f.job = DecodeEnqueue(req, streams[i % nstreams], &f.res); t_enq += now() - t0;
+    auto advance = [&]() {   // moves images whose current phase has drained to the next one (polling: a blocking wait on one stream would stall all others)
+      bool progressed = false; const size_t kWindow = 24;   // images finish roughly in order; look a little past the front of each queue
+      for (size_t k = 0; k < std::min(kWindow, q3.size());) { if (!DecodeStreamIdle(q3[k]->job)) { k++; continue; } InFlight& f = *q3[k]; DecodeFinish(f.job, &f.res); finish(f); q3.erase(q3.begin() + k); progressed = true; }
+      for (size_t k = 0; k < std::min(kWindow, q2.size());) { if (!DecodeStreamIdle(q2[k]->job)) { k++; continue; } std::unique_ptr<InFlight> f = std::move(q2[k]); q2.erase(q2.begin() + k); progressed = true; if (DecodeEnqueuePhase(f->job, 3, &f->res)) q3.push_back(std::move(f)); else finish(*f); }
+      for (size_t k = 0; k < std::min(kWindow, q1.size());) { if (!DecodeStreamIdle(q1[k]->job)) { k++; continue; } std::unique_ptr<InFlight> f = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true; if (DecodeEnqueuePhase(f->job, 2, &f->res)) q2.push_back(std::move(f)); else finish(*f); }
+      return progressed;
+    };
+    while (done < count) {
+      double t0 = now(); bool progressed = advance(); t_ret += now() - t0;
+      if (next < count && !free_streams.empty()) {
+        t0 = now(); const int i = next++;
+        std::unique_ptr<InFlight> f(new InFlight); f->idx = i; f->stream = free_streams.back(); free_streams.pop_back();
+        DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i]; req.out_capacity = outputBytes[i]; req.ac_lanes = batch_lanes;
+        if (hostInputs) req.data = datas[i]; else { req.data = host_in + in_off[i]; req.device_input = datas[i]; }
+        if (!hostOutputs) { req.out_device = outputs[i]; f->direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f->direct = true; }
+        f->job = DecodeEnqueue(req, f->stream, &f->res, true); t_enq += now() - t0;
+        if (f->job) q1.push_back(std::move(f)); else finish(*f);
+      } else if (!progressed) { t0 = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); t_ret += now() - t0; }
     }
-    { double t0 = now(); while (!q.empty()) retire(); t_ret += now() - t0; }
     if (trace) DumpHostTrace();
+    if (trace && count) fprintf(stderr, "[jxlb200] GPU ms/image under load: lf %.2f ac %.2f recon %.2f render %.2f total %.2f\n", acc_t[0] / count, acc_t[1] / count, acc_t[2] / count, acc_t[3] / count, acc_t[4] / count);
     if (trace) fprintf(stderr, "[jxlb200] batch of %d: host enqueue %.2f ms total (%.2f ms/image), retire/wait %.2f ms\n", count, t_enq, t_enq / std::max(count, 1), t_ret);
     if (pin) PinnedPut(pin, pin_bytes);
   } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }

@@ -14,6 +14,8 @@
 #include <mutex>
 #include <chrono>
 #include <atomic>
+#include <memory>
+#include <functional>
 #include <cstdio>
 
 namespace jxlgpu {
@@ -44,25 +46,40 @@ class Pool {
     if (e != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
     return p;
   }
-  void Put(void* p, size_t bytes) { if (!p) return; size_t sz = Round(bytes); std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; if (cached_ > limit_) TrimLocked(); }
+  void Put(void* p, size_t bytes) { if (!p) return; size_t sz = Round(bytes); std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; if (cached_ > Limit()) TrimLocked(); }
   void Trim() { std::lock_guard<std::mutex> lk(mu_); TrimLocked(); }
  private:
-  static size_t Round(size_t b) { size_t g = b < (1u << 20) ? 4096 : (size_t(1) << 20); return (b + g - 1) / g * g; }
+  // size classes: 4 KiB below 64 KiB, then eighths of a power of two, so that files of slightly different sizes share buckets
+  static size_t Round(size_t b) { if (b <= (1u << 16)) return (b + 4095) / 4096 * 4096; int k = 63 - __builtin_clzll(b); size_t g = size_t(1) << (k - 3); return (b + g - 1) / g * g; }
   void TrimLocked() { for (auto& kv : free_) for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } free_.clear(); cached_ = 0; }
-  bool pinned_; std::mutex mu_; std::map<size_t, std::vector<void*>> free_; size_t cached_ = 0; size_t limit_ = size_t(48) << 30;
+  size_t Limit() { if (!limit_) { size_t fr = 0, tot = 0; if (pinned_ || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); limit_ = size_t(32) << 30; } else limit_ = tot / 4 * 3; } return limit_; }
+  bool pinned_; std::mutex mu_; std::map<size_t, std::vector<void*>> free_; size_t cached_ = 0; size_t limit_ = 0;
 };
-static Pool& DevPool() { static Pool p(false); return p; }
+static Pool& DevPool() {   // one pool per device: a cached buffer must never cross devices
+  static std::mutex mu; static std::map<int, std::unique_ptr<Pool>> pools; int dev = 0; cudaGetDevice(&dev); std::lock_guard<std::mutex> lk(mu); auto& p = pools[dev]; if (!p) p.reset(new Pool(false)); return *p; }
 static Pool& HostPool() { static Pool p(true); return p; }
 void TrimPools() { DevPool().Trim(); HostPool().Trim(); }
 void* PinnedGet(size_t bytes) { return HostPool().Get(bytes ? bytes : 1); }
 void PinnedPut(void* p, size_t bytes) { HostPool().Put(p, bytes ? bytes : 1); }
 
-struct DevBuf { void* p = nullptr; size_t n = 0; bool host = false; void Alloc(size_t bytes, bool pinned = false) { Free(); host = pinned; n = bytes ? bytes : 1; p = (pinned ? HostPool() : DevPool()).Get(n); } void Free() { if (p) (host ? HostPool() : DevPool()).Put(p, n); p = nullptr; n = 0; } ~DevBuf() { Free(); } template <class T> T* as() const { return static_cast<T*>(p); } };
+struct DevBuf { void* p = nullptr; size_t n = 0; bool host = false; Pool* pool = nullptr; void Alloc(size_t bytes, bool pinned = false) { Free(); host = pinned; n = bytes ? bytes : 1; pool = pinned ? &HostPool() : &DevPool(); p = pool->Get(n); } void Free() { if (p) pool->Put(p, n); p = nullptr; n = 0; } ~DevBuf() { Free(); } template <class T> T* as() const { return static_cast<T*>(p); } };
 
 static const DTables* DeviceTables() {
   static std::mutex mu; static std::map<int, DTables*> per_dev; std::lock_guard<std::mutex> lk(mu); int dev = 0; CUDA_OK(cudaGetDevice(&dev));
   auto it = per_dev.find(dev); if (it != per_dev.end()) return it->second;
   std::unique_ptr<DTables> h(new DTables); FillDeviceTables(h.get()); DTables* d = nullptr; CUDA_OK(cudaMalloc(&d, sizeof(DTables))); CUDA_OK(cudaMemcpy(d, h.get(), sizeof(DTables), cudaMemcpyHostToDevice)); per_dev[dev] = d; return d;
+}
+
+// Per-device static blob: default dequantisation tables and natural coefficient orders (about 3 MB), uploaded once.
+struct StaticBlob { const uint8_t* dev = nullptr; uint32_t dq_off[kNumQuantTables]; uint32_t nat_off[kNumOrders]; };
+static const std::vector<float>& DefaultDequant(int t); static const std::vector<uint32_t>& NaturalOrderCached(int o);
+static const StaticBlob& DeviceStaticBlob() {
+  static std::mutex mu; static std::map<int, StaticBlob> per_dev; std::lock_guard<std::mutex> lk(mu); int dev = 0; CUDA_OK(cudaGetDevice(&dev));
+  auto it = per_dev.find(dev); if (it != per_dev.end()) return it->second;
+  StaticBlob sb; std::vector<uint8_t> b; auto add = [&](const void* p, size_t n) { size_t off = (b.size() + 15) & ~size_t(15); b.resize(off + n); memcpy(b.data() + off, p, n); return uint32_t(off) | kStaticBlobBit; };
+  for (int t = 0; t < kNumQuantTables; t++) { const std::vector<float>& d = DefaultDequant(t); sb.dq_off[t] = add(d.data(), d.size() * 4); }
+  for (int o = 0; o < kNumOrders; o++) { const std::vector<uint32_t>& n = NaturalOrderCached(o); sb.nat_off[o] = add(n.data(), n.size() * 4); }
+  uint8_t* d = nullptr; CUDA_OK(cudaMalloc(&d, b.size())); CUDA_OK(cudaMemcpy(d, b.data(), b.size(), cudaMemcpyHostToDevice)); sb.dev = d; return per_dev[dev] = sb;
 }
 
 static std::vector<uint8_t> BrotliDecompress(const uint8_t* data, size_t size) {
@@ -97,7 +114,7 @@ static ColorEncoding OutputEncoding(const ImageMetadata& m) {
 
 static Status ParseHeadersInto(const uint8_t* data, size_t size, Headers* h, ParsedInfo* info, std::string* msg) {
   int sig = SignatureCheck(data, size); if (sig == 0) return Status::InvalidFileSignature;
-  h->ci = ParseContainer(data, size); info->is_container = h->ci.is_container; const std::vector<uint8_t>& cs = h->ci.codestream;
+  h->ci = ParseContainer(data, size); info->is_container = h->ci.is_container; const ByteSpan& cs = h->ci.codestream;
   JXLG_CHECK(cs.size() >= 2 && cs[0] == 0xFF && cs[1] == 0x0A, "codestream signature");
   BitReader br(cs.data() + 2, cs.size() - 2); h->meta = ReadImageHeaders(br); const ImageMetadata& m = h->meta; h->frame_pos = 2 + br.pos / 8;
   // BASIC_INFO decisions, N/Decoder/JxlDecoder.cpp:461-561
@@ -185,18 +202,20 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 class DecodeJob {
  public:
   Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
-  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother;
+  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend;
+  std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false;
   cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
   bool has_tree = false; Tree tree; Code tree_code; GroupHeader gheader; size_t global_decoded = 0; uint64_t global_data_bitpos = 0; bool global_has_data = false;
   std::vector<Code> ac_codes; uint32_t hf_blob_mark = 0; uint32_t frame_uploads = 0; uint8_t* ext_out_device = nullptr; uint8_t* ext_out_pinned = nullptr;
   ~DecodeJob() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
 
   void Setup(const DecodeRequest& req);
+  void RunLf(const DecodeRequest& req); void RunAc(); void RunRender();
+  void Run(const DecodeRequest& req) { RunLf(req); RunAc(); RunRender(); }
   void ParseLfGlobal(BitReader& br);
   void ParseHfGlobal(BitReader& br);
   void AllocateAndUpload(const DecodeRequest& req);
   void UploadFrame();
-  void Run(const DecodeRequest& req);
 };
 
 void DecodeJob::ParseLfGlobal(BitReader& br) {
@@ -254,12 +273,12 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
 
 void DecodeJob::ParseHfGlobal(BitReader& br) {
   bool all_default = br.Bool();
-  for (int t = 0; t < kNumQuantTables; t++) { if (all_default) { const std::vector<float>& d = DefaultDequant(t); h.dq_off[t] = blob.Add(d.data(), d.size() * 4); } else { std::vector<float> d = ComputeDequantTable(t, ReadQuantEncodingHost(br, t)); h.dq_off[t] = blob.Add(d.data(), d.size() * 4); } }
+  const StaticBlob& sb = DeviceStaticBlob(); h.static_blob = sb.dev;
+  for (int t = 0; t < kNumQuantTables; t++) { if (all_default) h.dq_off[t] = sb.dq_off[t]; else { std::vector<float> d = ComputeDequantTable(t, ReadQuantEncodingHost(br, t)); h.dq_off[t] = blob.Add(d.data(), d.size() * 4); } }
   h.num_hf_presets = 1 + br.ReadBits(CeilLog2(fh.num_groups));
-  uint32_t nat_off[kNumOrders]; for (int o = 0; o < kNumOrders; o++) { const auto& n = NaturalOrderCached(o); nat_off[o] = blob.Add(n.data(), n.size() * 4); }
   ac_codes.resize(fh.passes.num_passes);
   for (uint32_t p = 0; p < fh.passes.num_passes; p++) {
-    uint32_t used = br.U32(Val(0x5F), Val(0x13), Val(0), Bits(13)); for (int i = 0; i < kNumOrders * 3; i++) h.order_off[p][i] = nat_off[i / 3];
+    uint32_t used = br.U32(Val(0x5F), Val(0x13), Val(0), Bits(13)); for (int i = 0; i < kNumOrders * 3; i++) h.order_off[p][i] = sb.nat_off[i / 3];
     if (used) { Code c = DecodeCode(br, 8); SymbolReader r(&c, &br);
       for (int o = 0; o < kNumOrders; o++) if (used >> o & 1) for (int chn = 0; chn < 3; chn++) { const auto& nat = NaturalOrderCached(o); size_t size = nat.size(); std::vector<uint32_t> perm = ReadPermutation(r, size / 64, size), out(size);
         for (size_t k = 0; k < size; k++) out[k] = nat[perm[k]]; h.order_off[p][o * 3 + chn] = blob.Add(out.data(), out.size() * 4); }
@@ -269,7 +288,7 @@ void DecodeJob::ParseHfGlobal(BitReader& br) {
 }
 
 void DecodeJob::Setup(const DecodeRequest& req) {
-  const ImageMetadata& m = hd.meta; const std::vector<uint8_t>& cs = hd.ci.codestream; size_t pos = hd.frame_pos;
+  const ImageMetadata& m = hd.meta; const ByteSpan& cs = hd.ci.codestream; size_t pos = hd.frame_pos;
   if (m.have_preview) { ImageMetadata pm = m; pm.xsize = m.preview_x; pm.ysize = m.preview_y; BitReader br(cs.data() + pos, cs.size() - pos); FrameHeader pf = ReadFrameHeader(br, pm); Toc t = ReadToc(br, pf); pos += br.pos / 8 + t.total; JXLG_CHECK(pos <= cs.size(), "preview frame truncated"); }
   BitReader br(cs.data() + pos, cs.size() - pos); fh = ReadFrameHeader(br, m);
   JXLG_CHECK(fh.frame_type == kFrameRegular || fh.frame_type == kFrameSkipProgressive, "reference-only / LF frames are not supported");
@@ -279,6 +298,7 @@ void DecodeJob::Setup(const DecodeRequest& req) {
   toc = ReadToc(br, fh); frame_off = pos + br.pos / 8; JXLG_CHECK(frame_off + toc.total <= cs.size(), "JxlDecoderProcessInput needs more input, but it already received the entire image.");
   info.frame_name = fh.name; info.bpp = double(cs.size()) * 8.0 / (double(m.xsize) * m.ysize);
   memset(&h, 0, sizeof(h)); bgra = req.bgra; device_output = req.device_output;
+  { int l = req.ac_lanes; static const int env_lanes = getenv("JXLB200_AC_LANES") ? atoi(getenv("JXLB200_AC_LANES")) : 0; if (env_lanes > 0) l = env_lanes; ac_lanes = 1; while (ac_lanes * 2 <= l && ac_lanes < 32) ac_lanes *= 2; }
   h.xsize = fh.xsize; h.ysize = fh.ysize; h.xb = fh.xblocks; h.yb = fh.yblocks; h.xpad = h.xb * 8; h.ypad = h.yb * 8; h.xt = (h.xb + 7) / 8; h.yt = (h.yb + 7) / 8; h.xgroups = fh.xgroups; h.ygroups = fh.ygroups; h.num_groups = fh.num_groups;
   h.xlfgroups = fh.xlfgroups; h.ylfgroups = fh.ylfgroups; h.num_lf_groups = fh.num_lf_groups; h.group_dim = fh.group_dim; h.num_passes = fh.passes.num_passes; h.encoding = fh.encoding; h.flags = uint32_t(fh.flags);
   for (uint32_t p = 0; p < h.num_passes; p++) { h.pass_shift[p] = p + 1 < h.num_passes ? fh.passes.shift[p] : 0;
@@ -320,13 +340,15 @@ void DecodeJob::Setup(const DecodeRequest& req) {
 void DecodeJob::UploadFrame() { if (!h_misc.p) h_misc.Alloc(2 * sizeof(DFrame) + 64, true); DFrame* slot = h_misc.as<DFrame>() + (frame_uploads++ & 1); *slot = h; CUDA_OK(cudaMemcpyAsync(d_frame.p, slot, sizeof(DFrame), cudaMemcpyHostToDevice, stream)); }
 
 void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
-  const std::vector<uint8_t>& cs = hd.ci.codestream; comp_size = cs.size();
+  const ByteSpan& cs = hd.ci.codestream; comp_size = cs.size();
   size_t cells = size_t(h.xb) * h.yb, px = size_t(h.xpad) * h.ypad, tiles = size_t(h.xt) * h.yt; bool vardct = h.encoding == 0;
   d_frame.Alloc(sizeof(DFrame)); d_err.Alloc(64); h_err.Alloc(64, true); d_gother.Alloc(size_t(h.num_groups) * 4);
   d_comp.Alloc(comp_size + 64);
   if (vardct) {
     d_lfq.Alloc(cells * 3 * 4); d_lf.Alloc(cells * 3 * 4); d_lf_tmp.Alloc(cells * 3 * 4); d_acs.Alloc(cells); d_qf.Alloc(cells); d_sharp.Alloc(cells); d_lfidx.Alloc(cells); d_ytox.Alloc(tiles); d_ytob.Alloc(tiles);
-    d_hfmeta.Alloc((size_t(h.num_lf_groups) * kHfMetaScratchInts + h.num_lf_groups) * 4); d_coeffs.Alloc(size_t(h.num_groups) * 3 * 65536 * 2); d_xyb.Alloc(px * 3 * 4); d_xyb_tmp.Alloc(px * 3 * 4); d_sigma.Alloc(cells * 4);
+    d_nz.Alloc(size_t(h.num_groups) * 3072); d_acend.Alloc(size_t(h.num_groups) * h.num_passes * 8);
+    d_hfmeta.Alloc((size_t(h.num_lf_groups) * kHfMetaScratchInts + h.num_lf_groups) * 4); d_coeffs.Alloc(size_t(h.num_groups) * 3 * 65536 * 2); d_xyb.Alloc(px * 3 * 4);
+    d_sigma.Alloc(cells * 4); if (!phased) d_xyb_tmp.Alloc(px * 3 * 4);   // phased (batch) jobs allocate xyb_tmp in RunRender, and only when the frame needs it
   }
   uint64_t mod_ints = 0; for (uint32_t i = 0; i < h.num_mod_channels; i++) mod_ints += uint64_t(h.mod_ch[i].w) * h.mod_ch[i].h; if (mod_ints) d_mod.Alloc(mod_ints * 4);
   if (h.uses_wp) d_wp.Alloc((size_t(h.num_lf_groups) + h.num_groups + 1) * 5 * 2 * (kMaxWpWidth + 2) * 4); else d_wp.Alloc(16);
@@ -339,7 +361,7 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   h.ytox = d_ytox.as<int8_t>(); h.ytob = d_ytob.as<int8_t>(); h.hfmeta_scratch = d_hfmeta.as<int32_t>(); h.coeffs = d_coeffs.as<int16_t>(); h.xyb = d_xyb.as<float>(); h.xyb_tmp = d_xyb_tmp.as<float>(); h.inv_sigma = d_sigma.as<float>();
   h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = req.out_device ? req.out_device : d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
   bool smooth = vardct && !(h.flags & kFlagSkipAdaptiveLfSmoothing) && h.xb > 2 && h.yb > 2; h.lf_src = smooth ? h.lf_tmp : h.lf;
-  h.group_other = d_gother.as<uint32_t>();
+  h.group_other = d_gother.as<uint32_t>(); h.nz_scratch = d_nz.as<uint8_t>(); h.ac_endpos = d_acend.as<uint64_t>();
   CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream)); CUDA_OK(cudaMemsetAsync(d_gother.p, 0, size_t(h.num_groups) * 4, stream));
   if (req.device_input && hd.ci.contiguous_offset != size_t(-1)) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input + hd.ci.contiguous_offset, comp_size, cudaMemcpyDeviceToDevice, stream));
   else { h_comp.Alloc(comp_size, true); memcpy(h_comp.p, cs.data(), comp_size); CUDA_OK(cudaMemcpyAsync(d_comp.p, h_comp.p, comp_size, cudaMemcpyHostToDevice, stream)); }   // pinned staging: a pageable source would serialise the stream
@@ -354,8 +376,9 @@ static const char* DevErrorText(uint32_t e) {
     default: return "device decode error"; }
 }
 
-void DecodeJob::Run(const DecodeRequest& req) {
-  const std::vector<uint8_t>& cs = hd.ci.codestream; const bool vardct = h.encoding == 0; const size_t nsec = toc.size.size(); const bool single = nsec == 1;
+// Phase 1: host parse of the global sections, uploads, the global Modular stream and the LF-group entropy kernel.
+void DecodeJob::RunLf(const DecodeRequest& req) {
+  const ByteSpan& cs = hd.ci.codestream; const bool vardct = h.encoding == 0; const size_t nsec = toc.size.size(); const bool single = nsec == 1;
   const size_t nlog = size_t(h.num_passes) * h.num_groups + h.num_lf_groups + 2;
   // host parse: LfGlobal (+ HfGlobal when it has its own section)
   double tt = NowMs();
@@ -365,10 +388,12 @@ void DecodeJob::Run(const DecodeRequest& req) {
   g_trace.t[3] += NowMs() - tt; tt = NowMs();
   {  // shared-memory budgets for the staged tables (host knows the exact sizes)
     auto code_bytes = [](const DCode& c) { return ((c.num_clusters * 4 + 15) & ~15u) + ((c.num_ctx + 15) & ~15u) + (c.use_prefix ? 0u : (((c.num_clusters << c.log_alpha) * 8 + 15) & ~15u)); };
-    uint32_t modb = has_tree ? code_bytes(h.mod_code) + ((h.tree_size * 16 + 15) & ~15u) : 0, acb = 0;
-    if (vardct && !single) for (uint32_t p = 0; p < h.num_passes; p++) acb = std::max(acb, code_bytes(h.ac_code[p]));
-    { static std::atomic<uint32_t> job_counter{0}; h.lf_cta_offset = (job_counter.fetch_add(1) * 4u) % 144u; }
-    h.lf_smem = std::min<uint32_t>(modb + 64, 96 * 1024); h.ac_smem = std::min<uint32_t>(acb + (h.num_mod_channels > h.first_group_channel ? modb : 0) + 64, 96 * 1024); if (single) h.ac_smem = 96 * 1024;
+    uint32_t modb = has_tree ? code_bytes(h.mod_code) + ((h.tree_size * 16 + 15) & ~15u) : 0;
+    { static std::atomic<uint32_t> lf_cursor{0}, ac_cursor{0};   // concurrent images start their few long-running CTAs on different SMs
+      h.lf_cta_offset = lf_cursor.fetch_add(h.num_lf_groups) % 148u; h.ac_cta_offset = vardct ? ac_cursor.fetch_add(uint32_t(AcCtas(h, ac_lanes))) % 148u : 0; }
+    h.lf_smem = std::min<uint32_t>(modb + 64, 96 * 1024); ac_budget = [this, code_bytes]() { uint32_t acb = 0; bool prefix = false; for (uint32_t p = 0; p < h.num_passes; p++) { acb = std::max(acb, code_bytes(h.ac_code[p])); prefix |= h.ac_code[p].use_prefix != 0; }
+      h.ac_smem = acb + 64; h.ac_fast = (!prefix && h.ac_smem <= 96 * 1024) ? 1 : 0; if (!h.ac_fast) h.ac_smem = 0; };
+    if (vardct && !single) ac_budget();
   }
   std::vector<uint64_t> sec(2 * nlog + 2, 0);
   for (size_t i = 0; i < nlog; i++) { size_t t = single ? 0 : i; sec[i] = base_bits + uint64_t(toc.offset[t]) * 8; sec[nlog + i] = base_bits + uint64_t(toc.offset[t] + toc.size[t]) * 8; }
@@ -387,16 +412,35 @@ void DecodeJob::Run(const DecodeRequest& req) {
     uint64_t pos[3] = {0, 0, 0}; CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
     uint32_t e = *h_err.as<uint32_t>(); JXLG_CHECK(e == 0, DevErrorText(e)); memcpy(pos, h_err.as<uint8_t>() + 16, 24);
     size_t byte = size_t(pos[1] / 8); JXLG_CHECK(byte <= cs.size(), "LF group ran past the end of the file");
-    BitReader hb(cs.data(), cs.size()); hb.pos = size_t(pos[1]); ParseHfGlobal(hb); JXLG_CHECK(!hb.overrun, "HfGlobal truncated"); uint64_t after = hb.pos;
+    BitReader hb(cs.data(), cs.size()); hb.pos = size_t(pos[1]); ParseHfGlobal(hb); JXLG_CHECK(!hb.overrun, "HfGlobal truncated"); uint64_t after = hb.pos; ac_budget();
     upload_blob(); { uint64_t* slot = reinterpret_cast<uint64_t*>(h_misc.as<uint8_t>() + 2 * sizeof(DFrame)) + 1; slot[0] = after; CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, slot, 8, cudaMemcpyHostToDevice, stream)); }
   }
+  g_trace.t[6] += NowMs() - tt;
+}
+
+// Phase 2: LF dequantisation (+ adaptive smoothing) and the AC / group-Modular entropy kernels.
+void DecodeJob::RunAc() {
+  const bool vardct = h.encoding == 0; const DFrame* d = d_frame.as<DFrame>(); double tt = NowMs();
   if (timed) cudaEventRecord(ev[1], stream);
   if (vardct) { bool smooth = h.lf_src == h.lf_tmp; LaunchLfDequant(d, h, smooth, stream); CountLaunch(smooth ? 2 : 1); }
-  for (uint32_t p = 0; p < h.num_passes; p++) { LaunchAcGroups(d, h, int(p), stream); CountLaunch(); }
+  if (vardct) CUDA_OK(cudaMemsetAsync(h.coeffs, 0, size_t(h.num_groups) * 3 * 65536 * 2, stream));
+  for (uint32_t p = 0; p < h.num_passes; p++) CountLaunch(LaunchAcGroups(d, h, int(p), ac_lanes, stream));
   if (timed) cudaEventRecord(ev[2], stream);
+  g_trace.t[6] += NowMs() - tt;
+}
+
+// Phase 3: dequant + IDCT, restoration filters, colour transform, pack, and the copy back to the host.
+void DecodeJob::RunRender() {
+  const bool vardct = h.encoding == 0; const DFrame* d = d_frame.as<DFrame>(); double tt = NowMs();
+  const bool unfused = getenv("JXLB200_UNFUSED") != nullptr;
+  if (vardct && !d_xyb_tmp.p) {   // phased job: the stream is idle here, so reading the LF kernel's flags back costs microseconds
+    CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    const bool big_blocks = h_err.as<uint32_t>()[12] != 0, filters = h.lpf.gab || h.lpf.epf_iters;
+    if (big_blocks || (filters && unfused)) { d_xyb_tmp.Alloc(size_t(h.xpad) * h.ypad * 3 * 4); h.xyb_tmp = d_xyb_tmp.as<float>(); UploadFrame(); }
+  }
   if (vardct) LaunchReconstruct(d, h, stream);
   if (timed) cudaEventRecord(ev[3], stream);
-  const bool unfused = getenv("JXLB200_UNFUSED") != nullptr; bool fused = false;
+  bool fused = false;
   if (h.num_rct) LaunchInverseRct(d, h, stream);
   if (vardct && !unfused) fused = LaunchFusedRender(d, h, stream);   // gaborish + EPF + colour + pack in one kernel
   if (vardct && !fused) LaunchFilters(d, h, stream);
@@ -409,18 +453,31 @@ void DecodeJob::Run(const DecodeRequest& req) {
   g_trace.t[6] += NowMs() - tt; g_trace.n++;
 }
 
-std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res) {
+std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res, bool lf_phase_only) {
   std::shared_ptr<DecodeJob> job;
   if (!req.data) { res->status = Status::NullParameter; return job; }
   try {
     std::string why; if (!CudaAvailable(&why)) { res->status = Status::DecodeError; res->message = why; return job; }
     job = std::make_shared<DecodeJob>(); job->stream = stream; double t0 = NowMs();
+    { static const bool batch_times = getenv("JXLB200_TRACE") != nullptr && atoi(getenv("JXLB200_TRACE")) >= 2; if (batch_times) { job->timed = true; for (int i = 0; i < 7; i++) cudaEventCreate(&job->ev[i]); } }
     res->status = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res->message); if (res->status != Status::Ok) { job.reset(); return job; }
-    g_trace.t[0] += NowMs() - t0; t0 = NowMs(); job->Setup(req); g_trace.t[1] += NowMs() - t0; job->Run(req); res->info = job->info;
+    g_trace.t[0] += NowMs() - t0; t0 = NowMs(); job->phased = lf_phase_only; job->Setup(req); g_trace.t[1] += NowMs() - t0; if (lf_phase_only) job->RunLf(req); else job->Run(req); res->info = job->info;
   } catch (const std::bad_alloc&) { res->status = Status::OutOfMemory; job.reset(); }
   catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); if (job) res->info = job->info; job.reset(); }
   return job;
 }
+
+// Phased enqueue (batches): phase 1 = DecodeEnqueue(..., lf_phase_only), then DecodeEnqueuePhase(job, 2) and (job, 3), each once
+// the stream has drained (DecodeStreamIdle), so that a queued dependent kernel never blocks a hardware queue shared with other streams.
+bool DecodeEnqueuePhase(std::shared_ptr<DecodeJob>& job, int phase, DecodeResult* res) {
+  if (!job) return false;
+  try { if (phase == 2) job->RunAc(); else job->RunRender(); return true; }
+  catch (const std::bad_alloc&) { res->status = Status::OutOfMemory; }
+  catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); res->info = job->info; }
+  cudaStreamSynchronize(job->stream); job.reset(); return false;
+}
+void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job) { if (job) cudaStreamSynchronize(job->stream); }
+bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job) { return !job || cudaStreamQuery(job->stream) != cudaErrorNotReady; }
 
 void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res) {
   if (!job) return;

@@ -1,9 +1,9 @@
 // pdn-jpegxl_b200 engine — entropy-decoding kernels (sm_100a).
 //   k_lf_group : one CTA per LF group (2048x2048 px): LF coefficients (Modular, 3 channels at 1/8 res),
 //                HF metadata (CfL maps, block strategies + hf multipliers, EPF sharpness), varblock placement.
-//   k_ac_group : one CTA per 256x256 AC group and pass: zero-fill + ANS/prefix coefficient decode with the
-//                context model of SURVEY.md A.8 "PassGroup AC decode", then the group's Modular channels
-//                (alpha / lossless colour).
+//   k_ac_vardct: AC coefficients of the 256x256 groups of one pass: ANS/prefix decode with the context model of
+//                SURVEY.md A.8 "PassGroup AC decode"; one lane per section, 1..32 sections per warp.
+//   k_mod_group: the groups' Modular channels (alpha / lossless colour).
 // A section is a serial bit stream (per-symbol adaptive contexts), so one thread is productive per CTA; the
 // other lanes zero-fill, stage tables and post-process. Throughput comes from the number of sections in
 // flight (192 AC groups for 12 MP, x batch). Replaces libjxl's DecodeGroup / ModularFrameDecoder work reached
@@ -40,6 +40,7 @@ __device__ void StageModDecoder(ModDecoder& md, const DFrame& f, uint8_t* dsm, u
   md.cv.Stage(dsm, cap, used, tid, nt); md.tree = static_cast<const DTreeNode*>(StageBytes(dsm, cap, used, md.tree, f.tree_size * 16, tid, nt));
 }
 
+template <bool kNarrow>
 __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame f) {
   // The first-wave CTA->SM mapping is deterministic, so concurrent images would stack their few LF CTAs on the same SMs:
   // each launch prepends `lf_cta_offset` empty CTAs to land on different SMs.
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame 
     if (ok) {
       md.rd.Init(md.cv); const int sid = 1 + g; size_t plane = size_t(f.xb) * f.yb;
       const int dst[3] = {1, 0, 2};   // stream channel order is Y, X, B (A.8 LfGroup)
-      for (int c = 0; c < 3; c++) md.DecodeChannel(c, sid, f.lfq + dst[c] * plane + size_t(cy0) * f.xb + cx0, f.xb, w, h, wp);
+      for (int c = 0; c < 3; c++) md.DecodeChannel<kNarrow>(c, sid, f.lfq + dst[c] * plane + size_t(cy0) * f.xb + cx0, f.xb, w, h, wp);
       if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
     }
     // (Modular LF-group channels — extra channels with dim_shift >= 3 — are rejected on the host.)
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame 
       ok = ReadGroupHeaderDev(md, f);
       if (ok) {
         md.rd.Init(md.cv); const int sid = 1 + 2 * int(f.num_lf_groups) + g;
-        md.DecodeChannel(0, sid, s_cflx, tw, tw, th, wp); md.DecodeChannel(1, sid, s_cflb, tw, tw, th, wp);
-        if (nb <= 65536u) { md.DecodeChannel(2, sid, s_info, nb, int(nb), 2, wp); md.DecodeChannel(3, sid, s_sharp, w, w, h, wp); } else md.rd.err = kErrHfMeta;
+        md.DecodeChannel<kNarrow>(0, sid, s_cflx, tw, tw, th, wp); md.DecodeChannel<kNarrow>(1, sid, s_cflb, tw, tw, th, wp);
+        if (nb <= 65536u) { md.DecodeChannel<kNarrow>(2, sid, s_info, nb, int(nb), 2, wp); md.DecodeChannel<kNarrow>(3, sid, s_sharp, w, w, h, wp); } else md.rd.err = kErrHfMeta;
         if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
       }
     }
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame 
       int32_t qf = max(0, min(255, s_info[nb + num]));
       for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { size_t p = o + size_t(iy) * f.xb + ix; if (f.acs[p] != 0xFF) e = kErrBlockBounds; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = uint8_t(qf); }
       f.acs[o] = uint8_t(s | 0x80); num++; if (s != 0) atomicAdd(f.group_other + ((cy0 + y) >> 5) * f.xgroups + ((cx0 + x) >> 5), 1u);
+      if (bw * bh >= 64) atomicOr(f.err + 12, 1u);   // a transform of 64x64 px or more: reconstruction needs the second plane set (xyb_tmp)
     }
     SetError(f.err, e);
   }
@@ -140,6 +142,7 @@ __global__ void k_lf_smooth(const DFrame* fp) {
 }
 
 // Decodes the group-local Modular channels (extra channels of VarDCT frames, everything of Modular frames).
+template <bool kNarrow>
 __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, int pass, bool* need_init) {
   const int gd = int(f.group_dim), gx = g % int(f.xgroups), gy = g / int(f.xgroups), x0 = gx * gd, y0 = gy * gd;
   int nch = 0;
@@ -152,85 +155,108 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth);
   for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
     int rx0 = x0 >> ch.hshift, ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) continue; int rw = min(gd >> ch.hshift, int(ch.w) - rx0), rh = min(gd >> ch.vshift, int(ch.h) - ry0); if (rw <= 0 || rh <= 0) continue;
-    md.DecodeChannel(k++, sid, f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, ch.w, rw, rh, wp); }
+    md.DecodeChannel<kNarrow>(k++, sid, f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, ch.w, rw, rh, wp); }
   if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
 }
 
-// AC coefficients of one 256x256 group and pass (A.8 "PassGroup AC decode"). kSmem: every code table is in shared memory.
+// AC coefficients of 256x256 groups (A.8 "PassGroup AC decode"), SIMT over independent sections.
+// Every section is a serial, adaptive-context bit stream, so one LANE walks one section; `lanes` (1..32) sections share a
+// warp. The walk is a flat one-symbol-per-iteration state machine (block/channel set-up and coefficient placement are the
+// divergent arms, the ANS step is the convergent one), so lanes at different blocks still share the instruction stream.
+// lanes = 1 gives the lowest single-image latency (192 warps for 12 MP); batches raise it so that the number of resident
+// sections is not capped by the register file (a lone lane still holds a full warp's registers).
+// kSmem: ANS code with every table staged in shared memory (the host checks sizes before choosing the instantiation).
+static const int kAcWarps = 4;
 template <bool kSmem>
-__device__ __noinline__ uint32_t DecodeAcCoeffs(const DFrame& f, SymReader& rd_io, const CodeView& cv_in, int pass, int g, int w, int h,
-                                                 uint8_t (*s_nz)[32 * 32], const uint8_t* s_acs, const uint8_t* s_qf, const uint8_t* s_lfidx) {
-  CodeView cv = cv_in; if (kSmem) cv.AssumeShared();
-  SymReader rd = rd_io;   // keep the reader state in registers (the by-reference copy lives in local memory)
-  struct WriteBack { SymReader& dst; SymReader& src; __device__ ~WriteBack() { dst = src; } } wb{rd_io, rd};
+__global__ void __launch_bounds__(32 * kAcWarps, 4) k_ac_vardct(const __grid_constant__ DFrame f, int pass, int lanes) {
+  if (blockIdx.x < f.ac_cta_offset) return;   // spreads concurrent images over different SMs (see k_lf_group)
+  extern __shared__ __align__(16) uint8_t dsm[]; __shared__ uint8_t s_freq[64], s_numnz[64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cta = int(blockIdx.x - f.ac_cta_offset);
+  CodeView cv; cv.Bind(f.blob, f.ac_code[pass]);
+  if (tid < 64) { s_freq[tid] = kFreqCtx[tid]; s_numnz[tid] = kNumNzCtx[tid]; }
+  if (kSmem) { uint32_t used = 0; cv.Stage(dsm, f.ac_smem, used, tid, 32 * kAcWarps); }
+  __syncthreads();
+  if (kSmem) cv.AssumeShared();
+  const int g = (cta * kAcWarps + warp) * lanes + lane;
+  if (lane >= lanes || g >= int(f.num_groups)) return;
+  const int xb = int(f.xb), cx0 = (g % int(f.xgroups)) * 32, cy0 = (g / int(f.xgroups)) * 32, w = min(32, xb - cx0), h = min(32, int(f.yb) - cy0);
+  const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
+  const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
+  const uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
+  SymReader rd; rd.br.Init(f.comp, start); rd.err = 0;
   uint32_t err = 0, bad_range = 0;
-  const uint32_t preset = rd.br.Read(CeilLog2Dev(f.num_hf_presets)); if (preset >= f.num_hf_presets) return kErrPreset;
+  const uint32_t preset = rd.br.Read(CeilLog2Dev(f.num_hf_presets));
+  if (preset >= f.num_hf_presets) { SetError(f.err, kErrPreset); return; }
   rd.Init(cv);
   const uint32_t nbctx = f.nb_block_ctx, ctx_offset = 495 * nbctx * preset, shift = f.pass_shift[pass], n_qf_thr = f.n_qf_thr, num_lf_ctxs = f.num_lf_ctxs;
-  const uint8_t* bmap = f.blob + f.bctx_map_off; int16_t* coef = f.coeffs + size_t(g) * 3 * 65536;
-  for (int by = 0; by < h; by++) for (int bx = 0; bx < w; bx++) {
-    const int cell = by * 32 + bx; const uint8_t a = s_acs[cell]; if (!(a & 0x80)) continue;
-    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); const uint32_t covered = uint32_t(bw * bh), log2c = 31 - __clz(covered), size = covered * 64; const int ord = StrategyOrder(s);
-    const uint32_t qf = uint32_t(s_qf[cell]) + 1; uint32_t qf_idx = 0; for (uint32_t t = 0; t < n_qf_thr; t++) qf_idx += qf > f.qf_thr[t];
-    const uint32_t lbw = 31 - __clz(uint32_t(bw)), bwm = uint32_t(bw) - 1;
-#pragma unroll 1
-    for (int ci = 0; ci < 3; ci++) {
-      const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; uint8_t* nzrow = s_nz[c];
+  const uint8_t* bmap = f.blob + f.bctx_map_off; int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; uint8_t* nzs = f.nz_scratch + size_t(g) * 3072;
+  int bx = -1, by = 0, ci = 2, cell = 0, ord = 0, bw = 1, bh = 1, c = 0;
+  uint32_t nz_left = 0, covered = 1, log2c = 0, size = 64, lbw = 0, bwm = 0, qf_idx = 0, lfi = 0, bctx = 0;
+  uint32_t k = 0, nzctx = 0, histo = 0, prev = 0; const uint32_t* order = nullptr; int16_t* cc = nullptr; uint8_t* nzrow = nzs;
+  for (;;) {
+    uint32_t ctx; const bool blk = nz_left == 0;
+    if (blk) {   // next (varblock, channel): number-of-nonzeros symbol
+      if (++ci == 3) {
+        ci = 0; bool found = false; uint32_t a = 0; size_t o = 0;
+        for (;;) { if (++bx >= w) { bx = 0; if (++by >= h) break; } o = size_t(cy0 + by) * xb + cx0 + bx; a = f.acs[o]; if (a & 0x80) { found = true; break; } }
+        if (!found) break;
+        const int s = a & 31; bw = CoveredX(s); bh = CoveredY(s); covered = uint32_t(bw * bh); log2c = 31 - __clz(covered); size = covered * 64; ord = StrategyOrder(s);
+        const uint32_t qf = uint32_t(f.hf_mul_m1[o]) + 1; qf_idx = 0; for (uint32_t t = 0; t < n_qf_thr; t++) qf_idx += qf > f.qf_thr[t];
+        lfi = f.lf_idx[o]; lbw = 31 - __clz(uint32_t(bw)); bwm = uint32_t(bw) - 1; cell = by * 32 + bx;
+      }
+      c = ci == 0 ? 1 : ci == 1 ? 0 : 2; nzrow = nzs + c * 1024;
       uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : nzrow[cell - 32]; else if (by == 0) pred = nzrow[cell - 1]; else pred = (uint32_t(nzrow[cell - 32]) + nzrow[cell - 1] + 1) >> 1;
-      uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u; idx = idx * 13 + ord; idx = idx * (n_qf_thr + 1) + qf_idx; idx = idx * num_lf_ctxs + s_lfidx[cell]; const uint32_t bctx = bmap[idx];
+      uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u; idx = idx * 13 + ord; idx = idx * (n_qf_thr + 1) + qf_idx; idx = idx * num_lf_ctxs + lfi; bctx = bmap[idx];
       uint32_t nzb = pred > 64 ? 64 : pred; nzb = nzb < 8 ? nzb : (nzb >= 64 ? 36 : 4 + nzb / 2);
-      uint32_t nz = kSmem ? rd.ReadAns(cv, ctx_offset + nzb * nbctx + bctx) : rd.Read(cv, ctx_offset + nzb * nbctx + bctx);
-      if (nz + covered > size) return kErrTooManyNz;
-      { const uint8_t v = uint8_t((nz + covered - 1) >> log2c); if (covered == 1) nzrow[cell] = v; else for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) nzrow[cell + iy * 32 + ix] = v; }
-      if (nz == 0) continue;
-      const uint32_t* order = reinterpret_cast<const uint32_t*>(f.blob + f.order_off[pass][ord * 3 + c]);
-      const uint32_t histo = ctx_offset + nbctx * 37 + 458 * bctx; uint32_t prev = nz > size / 16 ? 0 : 1; int16_t* cc = coef + c * 65536 + cell * 64;
-      uint32_t nzctx = uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) * 2 + histo; uint32_t k = covered;
-      do {
-        const uint32_t zc = nzctx + uint32_t(kFreqCtx[k >> log2c]) * 2 + prev; const uint32_t u = kSmem ? rd.ReadAns(cv, zc) : rd.Read(cv, zc); prev = u != 0;
-        if (u) {
-          int32_t v = int32_t(uint32_t(UnpackSignedDev(u)) << shift); const uint32_t p = order[k], j = p >> 6; const uint32_t addr = (((j >> lbw) << 5) + (j & bwm)) * 64 + (p & 63);
-          if (pass) v += cc[addr]; bad_range |= uint32_t(v + 32768) >> 16; cc[addr] = int16_t(v); nz--; nzctx = uint32_t(kNumNzCtx[(nz + covered - 1) >> log2c]) * 2 + histo;
-        }
-        k++;
-      } while (k < size && nz != 0);
-      if (nz != 0) return kErrNzMismatch;
+      ctx = ctx_offset + nzb * nbctx + bctx;
+    } else {
+      ctx = nzctx + uint32_t(s_freq[k >> log2c]) * 2 + prev;
+    }
+    const uint32_t u = kSmem ? rd.ReadAns(cv, ctx) : rd.Read(cv, ctx);
+    if (blk) {
+      if (u + covered > size) { err = kErrTooManyNz; break; }
+      const uint32_t v = (u + covered - 1) >> log2c;
+      if (covered == 1) nzrow[cell] = uint8_t(v); else for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) nzrow[cell + iy * 32 + ix] = uint8_t(v);
+      if (u) {
+        order = reinterpret_cast<const uint32_t*>(BlobAt(f, f.order_off[pass][ord * 3 + c])); histo = ctx_offset + nbctx * 37 + 458 * bctx; prev = u > size / 16 ? 0 : 1;
+        cc = coef + c * 65536 + cell * 64; nzctx = uint32_t(s_numnz[v]) * 2 + histo; k = covered; nz_left = u;
+      }
+    } else {
+      prev = u != 0;
+      if (u) {
+        int32_t v = int32_t(uint32_t(UnpackSignedDev(u)) << shift); const uint32_t p = order[k], j = p >> 6; const uint32_t addr = (((j >> lbw) << 5) + (j & bwm)) * 64 + (p & 63);
+        if (pass) v += cc[addr]; bad_range |= uint32_t(v + 32768) >> 16; cc[addr] = int16_t(v); nz_left--; nzctx = uint32_t(s_numnz[(nz_left + covered - 1) >> log2c]) * 2 + histo;
+      }
+      k++;
+      if (k >= size && nz_left) { err = kErrNzMismatch; break; }
     }
   }
-  if (!rd.FinalOk(cv)) err = kErrAnsFinal;
+  if (!err && !rd.FinalOk(cv)) err = kErrAnsFinal;
   if (!err && bad_range) err = kErrCoefRange;
   if (!err) err = rd.err;
-  return err;
+  const uint64_t pos = rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
+  f.ac_endpos[size_t(pass) * f.num_groups + g] = pos;
+  SetError(f.err, err);
 }
 
-// One CTA decodes kAcGroupsPerCta groups: warp w owns group blockIdx.x*kAcGroupsPerCta + w (lane 0 walks the bit stream, the
-// other lanes zero-fill and stage), and the warps share one shared-memory copy of the code tables.
-static const int kAcGroupsPerCta = 4;
-__global__ void __launch_bounds__(32 * kAcGroupsPerCta) k_ac_group(const __grid_constant__ DFrame f, int pass) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const int g = blockIdx.x * kAcGroupsPerCta + warp; const bool active = g < int(f.num_groups);
-  const int gx = active ? g % int(f.xgroups) : 0, gy = active ? g / int(f.xgroups) : 0;
-  __shared__ uint8_t s_nz_all[kAcGroupsPerCta][3][32 * 32]; __shared__ uint8_t s_acs_all[kAcGroupsPerCta][32 * 32], s_qf_all[kAcGroupsPerCta][32 * 32], s_lfidx_all[kAcGroupsPerCta][32 * 32];
-  __shared__ ChanLut sh_lut[kAcGroupsPerCta]; extern __shared__ __align__(16) uint8_t dsm[];
-  uint8_t (*s_nz)[32 * 32] = s_nz_all[warp]; uint8_t* s_acs = s_acs_all[warp]; uint8_t* s_qf = s_qf_all[warp]; uint8_t* s_lfidx = s_lfidx_all[warp];
-  const bool vardct = f.encoding == 0; int w = 0, h = 0;
-  ModDecoder md; BindModDecoder(md, f, &sh_lut[warp]); CodeView cv; uint32_t used = 0;
-  if (vardct) { cv.Bind(f.blob, f.ac_code[pass]); cv.Stage(dsm, f.ac_smem, used, tid, 32 * kAcGroupsPerCta); }
-  if (f.num_mod_channels > f.first_group_channel) StageModDecoder(md, f, dsm, f.ac_smem, used, tid, 32 * kAcGroupsPerCta);
-  if (vardct && active) {
-    const int cx0 = gx * 32, cy0 = gy * 32; w = min(32, int(f.xb) - cx0); h = min(32, int(f.yb) - cy0);
-    if (pass == 0) { int4* z = reinterpret_cast<int4*>(f.coeffs + size_t(g) * 3 * 65536); const int4 zero = make_int4(0, 0, 0, 0); for (int i = lane; i < 3 * 65536 * 2 / 16; i += 32) z[i] = zero; }
-    for (int i = lane; i < 32 * 32; i += 32) { int by = i >> 5, bx = i & 31; s_nz[0][i] = s_nz[1][i] = s_nz[2][i] = 0;
-      if (by < h && bx < w) { size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; s_acs[i] = f.acs[o]; s_qf[i] = f.hf_mul_m1[o]; s_lfidx[i] = f.lf_idx[o]; } else s_acs[i] = 0; }
-  }
+// Group-local Modular channels (alpha / extra channels of VarDCT frames, everything of Modular frames): warp w of a CTA owns
+// group blockIdx.x*kModGroupsPerCta + w, lane 0 walks the bit stream, and the warps share one staged copy of the tables.
+// In VarDCT frames the stream continues where the group's AC coefficients ended (ac_endpos, written by k_ac_vardct).
+static const int kModGroupsPerCta = 4;
+template <bool kNarrow>
+__global__ void __launch_bounds__(32 * kModGroupsPerCta) k_mod_group(const __grid_constant__ DFrame f, int pass) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const int g = blockIdx.x * kModGroupsPerCta + warp; const bool active = g < int(f.num_groups);
+  __shared__ ChanLut sh_lut[kModGroupsPerCta]; extern __shared__ __align__(16) uint8_t dsm[];
+  ModDecoder md; BindModDecoder(md, f, &sh_lut[warp]); uint32_t used = 0;
+  StageModDecoder(md, f, dsm, f.lf_smem, used, tid, 32 * kModGroupsPerCta);
   __syncthreads();
   if (lane != 0 || !active) return;
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
+  if (f.encoding == 0) start = f.ac_endpos[size_t(pass) * f.num_groups + g];
   md.rd.br.Init(f.comp, start);
-  uint32_t err = 0;
-  if (vardct) err = (cv.AllShared() && !cv.use_prefix) ? DecodeAcCoeffs<true>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx) : DecodeAcCoeffs<false>(f, md.rd, cv, pass, g, w, h, s_nz, s_acs, s_qf, s_lfidx);
-  if (!err) { bool need_init = true; md.rd.err = 0; DecodeModularGroupDev(md, f, g, pass, &need_init); err = md.rd.err; }
+  bool need_init = true; md.rd.err = 0; DecodeModularGroupDev<kNarrow>(md, f, g, pass, &need_init); uint32_t err = md.rd.err;
   uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
   SetError(f.err, err);
 }
@@ -253,12 +279,25 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
 }
 
 static void EnsureSmemAttr() { static bool done = false; if (done) return; done = true;
-  cudaFuncSetAttribute(k_lf_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
-void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (h.num_lf_groups) k_lf_group<<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); }
+  cudaFuncSetAttribute(k_lf_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
+void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (!h.num_lf_groups) return; const bool narrow = !h.uses_wp && !h.mod_wide;
+  if (narrow) k_lf_group<true><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); else k_lf_group<false><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); }
 void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st) {
   size_t plane = size_t(h.xb) * h.yb; unsigned blocks = unsigned((plane + 255) / 256); k_lf_dequant<<<blocks, 256, 0, st>>>(d); if (smooth) k_lf_smooth<<<blocks, 256, 0, st>>>(d);
 }
-void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st) { EnsureSmemAttr(); k_ac_group<<<(h.num_groups + kAcGroupsPerCta - 1) / kAcGroupsPerCta, 32 * kAcGroupsPerCta, h.ac_smem, st>>>(h, pass); }
+// Returns the number of kernels launched. `lanes`: sections per warp for the AC walk (power of two, 1..32).
+int AcCtas(const DFrame& h, int lanes) { const unsigned per_cta = unsigned(kAcWarps * lanes); return int((h.num_groups + per_cta - 1) / per_cta); }
+int LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, int lanes, cudaStream_t st) {
+  EnsureSmemAttr(); int n = 0;
+  if (h.encoding == 0) {
+    const unsigned per_cta = unsigned(kAcWarps * lanes), ctas = (h.num_groups + per_cta - 1) / per_cta;
+    if (h.ac_fast) k_ac_vardct<true><<<ctas + h.ac_cta_offset, 32 * kAcWarps, h.ac_smem, st>>>(h, pass, lanes); else k_ac_vardct<false><<<ctas + h.ac_cta_offset, 32 * kAcWarps, 0, st>>>(h, pass, lanes);
+    n++;
+  }
+  if (h.num_mod_channels > h.first_group_channel) { const unsigned ctas = (h.num_groups + kModGroupsPerCta - 1) / kModGroupsPerCta;
+    if (!h.uses_wp && !h.mod_wide) k_mod_group<true><<<ctas, 32 * kModGroupsPerCta, h.lf_smem, st>>>(h, pass); else k_mod_group<false><<<ctas, 32 * kModGroupsPerCta, h.lf_smem, st>>>(h, pass); n++; }
+  return n;
+}
 void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st) { EnsureSmemAttr(); k_modular_global<<<1, 32, h.lf_smem, st>>>(h, start_bitpos, num_channels); }
 
 }  // namespace jxlgpu

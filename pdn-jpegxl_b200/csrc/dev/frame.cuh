@@ -39,19 +39,23 @@ struct DFrame {
   uint32_t nb_block_ctx, num_lf_ctxs, n_lf_thr[3], n_qf_thr; int32_t lf_thr[3][15]; uint32_t qf_thr[15]; uint32_t bctx_map_off;
   uint32_t num_hf_presets; DCode mod_code; uint32_t has_tree, tree_off, tree_size, uses_wp; DCode ac_code[kMaxPasses]; uint32_t order_off[kMaxPasses][13 * 3];
   uint32_t dq_off[17];       // float[3*size] per quant table, byte offsets into blob
-  uint32_t lf_smem, ac_smem, lf_cta_offset; // dynamic shared memory budgets (bytes) for the table staging of k_lf_group / k_ac_group
+  uint32_t lf_smem, ac_smem, lf_cta_offset, ac_cta_offset, ac_fast; // dynamic shared memory budgets (bytes) for the table staging of k_lf_group / k_ac_group
   uint32_t sec_off;          // uint64 sec_bitpos[nsec] then uint64 sec_bitend[nsec], byte offset into blob
   uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8]; uint32_t mod_bitdepth, mod_wide; uint32_t num_rct; uint32_t rct_begin[4], rct_type[4];
   DLoopFilter lpf; DColor color; DOutput out;
   // device buffers
-  const uint8_t* comp; const uint8_t* blob;
+  const uint8_t* comp; const uint8_t* blob; const uint8_t* static_blob;
   int32_t* lfq; float* lf; float* lf_tmp; uint8_t* acs; uint8_t* hf_mul_m1; uint8_t* sharp; uint8_t* lf_idx; int8_t* ytox; int8_t* ytob; int32_t* hfmeta_scratch;
   const float* lf_src; const struct DTables* tables;
-  int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos; uint32_t* group_other;   // group_other[g]: number of varblocks in group g that are not plain DCT8
+  int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos; uint64_t* ac_endpos; uint8_t* nz_scratch; uint32_t* group_other;   // group_other[g]: number of varblocks in group g that are not plain DCT8
 };
 static const uint32_t kHfMetaScratchInts = 2 * 1024 + 2 * 65536 + 65536;
 
+// Offsets with the top bit set address the per-device static blob (default dequant tables, natural coefficient orders)
+// instead of the per-image blob: defaults are uploaded once per device, not once per image.
+static const uint32_t kStaticBlobBit = 0x80000000u;
 #ifdef __CUDACC__
+__device__ __forceinline__ const uint8_t* BlobAt(const DFrame& f, uint32_t off) { return (off & kStaticBlobBit) ? f.static_blob + (off & ~kStaticBlobBit) : f.blob + off; }
 __device__ __forceinline__ const uint64_t* SecBitPos(const DFrame& f) { return reinterpret_cast<const uint64_t*>(f.blob + f.sec_off); }
 #endif
 

@@ -6,7 +6,8 @@ namespace jxlgpu {
 // decode
 void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st);
 void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st);
-void LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, cudaStream_t st);
+int AcCtas(const DFrame& h, int lanes);
+int LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, int lanes, cudaStream_t st);
 void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st);
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st);       // dequant + CfL + LLF + inverse transforms
 void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st);           // gaborish + EPF (result in h.xyb)

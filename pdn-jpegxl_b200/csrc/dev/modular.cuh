@@ -116,10 +116,11 @@ struct ModDecoder {
   }
 
   // kMode 0: generic tree walk; 1: LUT fast path (any property/predictor); 2: LUT fast path specialised for property 8 + gradient predictor
-  template <typename T, int kMode, bool kSmem>
+  // kWp: the weighted predictor may be in use (only the wide instantiations carry its code and registers)
+  template <typename T, int kMode, bool kSmem, bool kWp>
   __device__ __noinline__ void DecodeRows(int root, DTreeNode n, int chan, int stream_id, int32_t* out, size_t stride, int w, int h, int32_t* wp_base) {
-    typedef ModMath<T> M; WPScratch ws; WPPred wo; wo.max_err = 0; if (this->uses_wp) { ws.Bind(wp_base, w); ws.Clear(); }
-    SymReader rd = this->rd; CodeView cv = this->cv; const DTreeNode* tree = this->tree; const DWPHeader wp = this->wp; const bool uses_wp = this->uses_wp; ChanLut* lut = this->lut;   // registers, not *this
+    typedef ModMath<T> M; WPScratch ws; WPPred wo; wo.max_err = 0; if (kWp && this->uses_wp) { ws.Bind(wp_base, w); ws.Clear(); }
+    SymReader rd = this->rd; CodeView cv = this->cv; const DTreeNode* tree = this->tree; const DWPHeader wp = this->wp; const bool uses_wp = kWp && this->uses_wp; ChanLut* lut = this->lut;   // registers, not *this
     struct WriteBack { SymReader& dst; SymReader& src; __device__ ~WriteBack() { dst = src; } } wb{this->rd, rd};
     __builtin_assume(__isShared(lut)); if (kSmem) cv.AssumeShared();
     const ChanLut& L = *lut; const int fprop = L.prop, fpred = L.predictor, fn = L.n; const bool direct = L.has_direct != 0;
@@ -181,6 +182,8 @@ struct ModDecoder {
   }
 
   // Decodes one channel in raster order into out[y*stride + x]. wp_base: scratch for the weighted predictor (may be null when !uses_wp).
+  // kNarrow: the caller guarantees !uses_wp && !wide (checked on the host), so the 64-bit / weighted-predictor code is not instantiated
+  template <bool kNarrow = false>
   __device__ void DecodeChannel(int chan, int stream_id, int32_t* out, size_t stride, int w, int h, int32_t* wp_base) {
     if (w <= 0 || h <= 0) return;
     // resolve static decisions (properties 0 = channel, 1 = stream id) at the top of the tree once per channel
@@ -189,12 +192,13 @@ struct ModDecoder {
     if (uses_wp && w > int(kMaxWpWidth)) { rd.err = kErrUnsupportedStream; return; }
     BuildLut(root); const ChanLut& L = *lut;
     const bool sm = cv.AllShared() && !cv.use_prefix;
-    if (wide || uses_wp) { if (L.ok) DecodeRows<long long, 1, false>(root, n, chan, stream_id, out, stride, w, h, wp_base); else DecodeRows<long long, 0, false>(root, n, chan, stream_id, out, stride, w, h, wp_base); }
+    if (!kNarrow && (wide || uses_wp)) { if (L.ok) DecodeRows<long long, 1, false, true>(root, n, chan, stream_id, out, stride, w, h, wp_base); else DecodeRows<long long, 0, false, true>(root, n, chan, stream_id, out, stride, w, h, wp_base); }
+    else if (wide || uses_wp) rd.err = kErrUnsupportedStream;
     else if (L.ok && sm && L.prop == 8 && L.predictor == 5 && L.has_direct) DecodeRowsLean(out, stride, w, h);
-    else if (L.ok && L.prop == 8 && L.predictor == 5) DecodeRows<int32_t, 2, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
-    else if (L.ok && sm) DecodeRows<int32_t, 1, true>(root, n, chan, stream_id, out, stride, w, h, wp_base);
-    else if (L.ok) DecodeRows<int32_t, 1, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
-    else DecodeRows<int32_t, 0, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else if (L.ok && L.prop == 8 && L.predictor == 5) DecodeRows<int32_t, 2, false, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else if (L.ok && sm) DecodeRows<int32_t, 1, true, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else if (L.ok) DecodeRows<int32_t, 1, false, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+    else DecodeRows<int32_t, 0, false, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
   }
 };
 #endif

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_reconstruct_dct8(const __grid_constant_
   const int g = blockIdx.x >> 2, quarter = blockIdx.x & 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = lane >> 3, r = lane & 7;
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
   __shared__ float s_dq[3 * 64]; __shared__ float s_t[8][4 * 72];
-  if (tid < 192) s_dq[tid] = reinterpret_cast<const float*>(f.blob + f.dq_off[0])[tid];
+  if (tid < 192) s_dq[tid] = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[0]))[tid];
   __syncthreads();
   const int by = quarter * 8 + warp; if (by >= h) return;
   const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; float* st = s_t[warp];
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
     const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
     const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw > 4 || bh > 4 || s == 0) continue;   // DCT8 is handled by k_reconstruct_dct8
-    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(f.blob + f.dq_off[QuantTableOf(s)]);
+    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[QuantTableOf(s)]));
     const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
     const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
     const bool plain = (s == 0) || (s >= 4 && s <= 11);
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
     const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
     const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw <= 4 && bh <= 4) continue;
-    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(f.blob + f.dq_off[QuantTableOf(s)]);
+    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[QuantTableOf(s)]));
     const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
     const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
     const size_t base = size_t(cy0 + by) * 8 * f.xpad + size_t(cx0 + bx) * 8;

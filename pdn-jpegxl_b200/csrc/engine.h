@@ -29,6 +29,7 @@ struct DecodeRequest {
   uint8_t* out_device = nullptr;    // optional: decode straight into this device buffer (out_capacity bytes)
   uint8_t* out_pinned = nullptr;    // optional: copy the pixels straight into this page-locked host buffer (out_capacity bytes)
   size_t out_capacity = 0;
+  int ac_lanes = 0;                 // AC sections walked per warp (power of two, 1..32); 0: 1 (lowest latency). Batches raise it for throughput.
 };
 
 struct StageTimes { float h2d = 0, lf = 0, ac = 0, recon = 0, filters = 0, output = 0, d2h = 0, total = 0; };
@@ -46,7 +47,10 @@ DecodeResult ParseInfo(const uint8_t* data, size_t size);
 // Full decode on the GPU. Fails loudly (DecodeError with a message) when no CUDA device is usable: there is no CPU fallback.
 DecodeResult DecodeOnGpu(const DecodeRequest& req);
 // Asynchronous variant for batches: enqueue everything on `stream`, return without synchronising. Finish() waits and reads the error word.
-std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res);
+std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res, bool lf_phase_only = false);
+bool DecodeEnqueuePhase(std::shared_ptr<DecodeJob>& job, int phase, DecodeResult* res);   // phase 2: AC entropy kernels, 3: reconstruction + render; false: job failed (res filled, job released)
+bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job);
+void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job);
 void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res);
 // stage dumps for parity tests (3 planes xpad*ypad floats or coefficient ints), copied to host
 bool DecodeDebugPlanes(const std::shared_ptr<DecodeJob>& job, int which, std::vector<float>* out, int* xpad, int* ypad);

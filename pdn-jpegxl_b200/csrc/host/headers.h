@@ -330,7 +330,15 @@ inline void WriteToc(BitWriter& bw, const std::vector<size_t>& sizes) {
 
 // ------------------------------------------------------------------ container (A.1)
 struct Box { char type[5]; const uint8_t* data; size_t size; };
-struct ContainerInfo { bool is_container = false; std::vector<uint8_t> codestream; std::vector<Box> boxes; size_t contiguous_offset = size_t(-1); /* file offset of the codestream when it is one contiguous range */ int parts = 0; };
+// The codestream bytes: a view into the caller's file buffer when they form one contiguous range (bare codestream, one jxlc box),
+// an owned concatenation only when the file splits them over several jxlp boxes.
+struct ByteSpan {
+  const uint8_t* p = nullptr; size_t n = 0; std::vector<uint8_t> own;
+  const uint8_t* data() const { return own.empty() ? p : own.data(); } size_t size() const { return own.empty() ? n : own.size(); } bool empty() const { return size() == 0; }
+  uint8_t operator[](size_t i) const { return data()[i]; }
+  void append(const uint8_t* d, size_t len) { if (!p && own.empty()) { p = d; n = len; return; } if (own.empty()) own.assign(p, p + n); own.insert(own.end(), d, d + len); }
+};
+struct ContainerInfo { bool is_container = false; ByteSpan codestream; std::vector<Box> boxes; size_t contiguous_offset = size_t(-1); /* file offset of the codestream when it is one contiguous range */ int parts = 0; };
 inline int SignatureCheck(const uint8_t* d, size_t n) {   // 0 invalid/not enough, 1 codestream, 2 container
   static const uint8_t sig[12] = {0, 0, 0, 0xC, 'J', 'X', 'L', ' ', 0xD, 0xA, 0x87, 0xA};
   if (n >= 2 && d[0] == 0xFF && d[1] == 0x0A) return 1;
@@ -339,15 +347,15 @@ inline int SignatureCheck(const uint8_t* d, size_t n) {   // 0 invalid/not enoug
 }
 inline ContainerInfo ParseContainer(const uint8_t* d, size_t n) {
   ContainerInfo c; int s = SignatureCheck(d, n); JXLG_CHECK(s != 0, "invalid signature");
-  if (s == 1) { c.codestream.assign(d, d + n); c.contiguous_offset = 0; c.parts = 1; return c; }
+  if (s == 1) { c.codestream.append(d, n); c.contiguous_offset = 0; c.parts = 1; return c; }
   c.is_container = true; size_t pos = 0; bool seen_last = false;
   while (pos + 8 <= n) {
     uint64_t size = (uint64_t(d[pos]) << 24) | (d[pos + 1] << 16) | (d[pos + 2] << 8) | d[pos + 3]; size_t hdr = 8; Box b; memcpy(b.type, d + pos + 4, 4); b.type[4] = 0;
     if (size == 1) { JXLG_CHECK(pos + 16 <= n, "box header truncated"); size = 0; for (int i = 0; i < 8; i++) size = (size << 8) | d[pos + 8 + i]; hdr = 16; }
     else if (size == 0) size = n - pos;
     JXLG_CHECK(size >= hdr && pos + size <= n, "box size"); b.data = d + pos + hdr; b.size = size - hdr;
-    if (!strcmp(b.type, "jxlc")) { c.codestream.insert(c.codestream.end(), b.data, b.data + b.size); c.contiguous_offset = size_t(b.data - d); c.parts++; }
-    else if (!strcmp(b.type, "jxlp")) { JXLG_CHECK(b.size >= 4 && !seen_last, "jxlp box"); if (b.data[0] & 0x80) seen_last = true; c.codestream.insert(c.codestream.end(), b.data + 4, b.data + b.size); c.contiguous_offset = size_t(b.data + 4 - d); c.parts++; }
+    if (!strcmp(b.type, "jxlc")) { c.codestream.append(b.data, b.size); c.contiguous_offset = size_t(b.data - d); c.parts++; }
+    else if (!strcmp(b.type, "jxlp")) { JXLG_CHECK(b.size >= 4 && !seen_last, "jxlp box"); if (b.data[0] & 0x80) seen_last = true; c.codestream.append(b.data + 4, b.size - 4); c.contiguous_offset = size_t(b.data + 4 - d); c.parts++; }
     c.boxes.push_back(b); pos += size;
   }
   JXLG_CHECK(!c.codestream.empty(), "container without codestream"); if (c.parts != 1) c.contiguous_offset = size_t(-1);
