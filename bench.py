@@ -35,9 +35,9 @@ def parse_args():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--width", type=int, default=4000)
     ap.add_argument("--height", type=int, default=3000)
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images (seeds 0..distinct-1), repeated to fill the batch")
-    ap.add_argument("--in-flight", type=int, default=16)
+    ap.add_argument("--in-flight", type=int, default=128)
     ap.add_argument("--cpu-sample", type=int, default=2, help="images in the bounded CPU-baseline sample")
     return ap.parse_args()
 

@@ -438,10 +438,12 @@ void DecodeJob::RunRender() {
     const bool big_blocks = h_err.as<uint32_t>()[12] != 0, filters = h.lpf.gab || h.lpf.epf_iters;
     if (big_blocks || (filters && unfused)) { d_xyb_tmp.Alloc(size_t(h.xpad) * h.ypad * 3 * 4); h.xyb_tmp = d_xyb_tmp.as<float>(); UploadFrame(); }
   }
-  if (vardct) LaunchReconstruct(d, h, stream);
+  static const int dbg_skip = getenv("JXLB200_DEBUG_SKIP") ? atoi(getenv("JXLB200_DEBUG_SKIP")) : 0;   // timing experiments only: 1 = no reconstruction, 2 = no render, 3 = neither
+  if (vardct && !(dbg_skip & 1)) LaunchReconstruct(d, h, stream);
   if (timed) cudaEventRecord(ev[3], stream);
   bool fused = false;
   if (h.num_rct) LaunchInverseRct(d, h, stream);
+  if (dbg_skip & 2) fused = true; else
   if (vardct && !unfused) fused = LaunchFusedRender(d, h, stream);   // gaborish + EPF + colour + pack in one kernel
   if (vardct && !fused) LaunchFilters(d, h, stream);
   if (timed) cudaEventRecord(ev[4], stream);

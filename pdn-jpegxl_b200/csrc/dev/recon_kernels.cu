@@ -269,16 +269,19 @@ __global__ void k_inverse_rct(const DFrame* fp, uint32_t begin_c, uint32_t type)
 }
 
 // ------------------------------------------------------------------ output
+// a^e for a >= 0 through the SFU (lg2 + ex2): relative error of a few 1e-7 here (|e * log2 a| < 16), far inside the 1-LSB / 1e-4 bounds
+// of the output formats; libm powf costs ~70 instructions per call and was 29 % of the fused kernel's issue slots (profiles/).
+__device__ __forceinline__ float PowSfu(float a, float e) { return a > 0.f ? exp2f(e * __log2f(a)) : 0.f; }
 __device__ __forceinline__ float TfFromLinearDev(float v, uint32_t tf, float gamma, float intensity_target) {
   float a = fabsf(v), r;
   switch (tf) {
-    case 0: r = powf(a, gamma); break;
+    case 0: r = PowSfu(a, gamma); break;
     case 8: r = a; break;
-    case 13: r = a <= 0.0031308f ? 12.92f * a : 1.055f * powf(a, 1.0f / 2.4f) - 0.055f; break;
-    case 1: r = a < 0.018f ? 4.5f * a : 1.099f * powf(a, 0.45f) - 0.099f; break;
+    case 13: r = a <= 0.0031308f ? 12.92f * a : 1.055f * PowSfu(a, 1.0f / 2.4f) - 0.055f; break;
+    case 1: r = a < 0.018f ? 4.5f * a : 1.099f * PowSfu(a, 0.45f) - 0.099f; break;
     case 16: { const float m1 = 2610.0f / 16384, m2 = 2523.0f / 4096 * 128, c1 = 3424.0f / 4096, c2 = 2413.0f / 4096 * 32, c3 = 2392.0f / 4096 * 32;
       float yv = fminf(1.0f, a * intensity_target / 10000.0f); float p = powf(yv, m1); r = powf((c1 + c2 * p) / (1.0f + c3 * p), m2); break; }
-    case 17: r = powf(a, 1.0f / 2.6f); break;
+    case 17: r = PowSfu(a, 1.0f / 2.6f); break;
     default: r = a; break;
   }
   return v < 0 ? -r : r;
@@ -358,45 +361,104 @@ __global__ void k_output(const __grid_constant__ DFrame f, const float* __restri
 template <int GAB, int EPF>
 __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DFrame f) {
   constexpr int R0 = EPF == 3 ? 3 : 0, R1 = EPF >= 1 ? 2 : 0, R2 = EPF >= 2 ? 1 : 0, H = GAB + R0 + R1 + R2, D = 32 + 2 * H, N = D * D;
-  extern __shared__ float rs[]; float* A = rs; float* Bf = rs + 3 * N;
+  extern __shared__ float rs[]; float* A = rs; float* Bf = rs + 3 * N; float* Mh = rs + 6 * N; float* Mv = rs + 7 * N; float* s_is = rs + (EPF ? 8 : 6) * N;   // s_is: 8x8 blocks of 1/sigma
   const int xs = int(f.xsize), ys = int(f.ysize), tx0 = blockIdx.x * 32 - H, ty0 = blockIdx.y * 32 - H, tid = threadIdx.x; const size_t plane = size_t(f.xpad) * f.ypad;
-  for (int i = tid; i < N; i += 256) { const int ly = i / D, lx = i - ly * D; const size_t at = size_t(MirrorDev(ty0 + ly, ys)) * f.xpad + MirrorDev(tx0 + lx, xs);
-    A[i] = f.xyb[at]; A[N + i] = f.xyb[plane + at]; A[2 * N + i] = f.xyb[2 * plane + at]; }
+  const int bx0 = max(tx0, 0) >> 3, by0 = max(ty0, 0) >> 3;
+  if (EPF && tid < 64) { const int by = by0 + (tid >> 3), bx = bx0 + (tid & 7); s_is[tid] = (by < int(f.yb) && bx < int(f.xb)) ? f.inv_sigma[size_t(by) * f.xb + bx] : 0.f; }
+  {  // tile + halo: a thread owns one column (mirrored x resolved once) and every (256/D)-th row
+    constexpr int S = 256 / D; const int lx = tid % D, gx = MirrorDev(tx0 + lx, xs);
+    if (tid < S * D) for (int ly = tid / D; ly < D; ly += S) { const size_t at = size_t(MirrorDev(ty0 + ly, ys)) * f.xpad + gx; const int i = ly * D + lx;
+      A[i] = f.xyb[at]; A[N + i] = f.xyb[plane + at]; A[2 * N + i] = f.xyb[2 * plane + at]; }
+  }
   __syncthreads();
   int off = 0;   // valid region of the current buffer is [off, D-off)^2
   float* src = A; float* dst = Bf;
-  if (GAB) {
-    off += 1; const int n = D - 2 * off;
-    for (int i = tid; i < n * n; i += 256) { const int y = off + i / n, x = off + i % n; const int p = y * D + x;
+  if (GAB) {   // column strips: a thread walks down its column with a rolling 3x3 window per channel (3 shared loads per sample instead of 9)
+    off += 1; constexpr int n = D - 2, S = 256 / n, R = (n + S - 1) / S;
+    if (tid < n * S) {
+      const int x = off + tid % n, y0 = off + (tid / n) * R, y1 = min(y0 + R, off + n);
 #pragma unroll
-      for (int c = 0; c < 3; c++) { const float* s = src + c * N + p; const float w1 = f.lpf.gab_w[2 * c], w2 = f.lpf.gab_w[2 * c + 1], mul = 1.0f / (1.0f + 4.0f * (w1 + w2));
-        dst[c * N + p] = s[0] * mul + (s[-D] + s[D] + s[-1] + s[1]) * (w1 * mul) + (s[-D - 1] + s[-D + 1] + s[D - 1] + s[D + 1]) * (w2 * mul); } }
+      for (int c = 0; c < 3; c++) {
+        const float* s = src + c * N + x; float* d = dst + c * N + x; const float w1 = f.lpf.gab_w[2 * c], w2 = f.lpf.gab_w[2 * c + 1], mul = 1.0f / (1.0f + 4.0f * (w1 + w2)), m1 = w1 * mul, m2 = w2 * mul;
+        float a0 = s[(y0 - 1) * D - 1], a1 = s[(y0 - 1) * D], a2 = s[(y0 - 1) * D + 1], b0 = s[y0 * D - 1], b1 = s[y0 * D], b2 = s[y0 * D + 1];
+#pragma unroll
+        for (int k = 0; k < R; k++) { const int y = y0 + k; if (y >= y1) break; const float c0 = s[(y + 1) * D - 1], c1 = s[(y + 1) * D], c2 = s[(y + 1) * D + 1];
+          d[y * D] = b1 * mul + (a1 + c1 + b0 + b2) * m1 + (a0 + a2 + c0 + c2) * m2; a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2; }
+      }
+    }
     __syncthreads(); float* t = src; src = dst; dst = t;
   }
 #pragma unroll
   for (int pass = 0; pass < 3; pass++) {
     const int r = pass == 0 ? R0 : pass == 1 ? R1 : R2; if (r == 0) continue;
     off += r; const int n = D - 2 * off;
-    const float sigma_scale = pass == 0 ? f.lpf.pass0_sigma_scale : pass == 2 ? f.lpf.pass2_sigma_scale : 1.0f, sm = sigma_scale * 1.65f;
-    for (int i = tid; i < n * n; i += 256) {
-      const int y = off + i / n, x = off + i % n, p = y * D + x; const int gy = MirrorDev(ty0 + y, ys), gx = MirrorDev(tx0 + x, xs);
-      const float is = f.inv_sigma[size_t(gy >> 3) * f.xb + (gx >> 3)];
-      if (is < -3.90524291751269967465540850526868f) { dst[p] = src[p]; dst[N + p] = src[N + p]; dst[2 * N + p] = src[2 * N + p]; continue; }
-      const bool border = ((gy & 7) == 0 || (gy & 7) == 7 || (gx & 7) == 0 || (gx & 7) == 7); const float inv = is * (border ? sm * f.lpf.border_sad_mul : sm);
-      float wsum = 1.0f, acc0 = src[p], acc1 = src[N + p], acc2 = src[2 * N + p];
-      const int nn = pass == 0 ? 12 : 4;
-      const int d12[12] = {-2 * D, -D - 1, -D, -D + 1, -2, -1, 1, 2, D - 1, D, D + 1, 2 * D}; const int d4[4] = {-D, -1, 1, D};
+    const float sigma_scale = pass == 0 ? f.lpf.pass0_sigma_scale : pass == 2 ? f.lpf.pass2_sigma_scale : 1.0f, sm = sigma_scale * 1.65f, smb = sm * f.lpf.border_sad_mul;
+    const float cs0 = f.lpf.epf_channel_scale[0], cs1 = f.lpf.epf_channel_scale[1], cs2 = f.lpf.epf_channel_scale[2];
+    if (pass == 1) {
+      // The 5-tap-cross SAD towards a 4-neighbour is a sum of five adjacent-sample differences, so two maps of channel-weighted
+      // |horizontal| and |vertical| differences are built once, and a pixel reads 16 map entries instead of 120 samples.
+      { const int lo = off - 2, m = D - 2 * lo - 1;
+        for (int i = tid; i < m * m; i += 256) { const int q = (lo + i / m) * D + lo + i % m; const float a0 = src[q], a1 = src[N + q], a2 = src[2 * N + q];
+          Mh[q] = fabsf(src[q + 1] - a0) * cs0 + fabsf(src[N + q + 1] - a1) * cs1 + fabsf(src[2 * N + q + 1] - a2) * cs2;
+          Mv[q] = fabsf(src[q + D] - a0) * cs0 + fabsf(src[N + q + D] - a1) * cs1 + fabsf(src[2 * N + q + D] - a2) * cs2; } }
+      __syncthreads();
+      constexpr int n1 = D - 2 * (GAB + R0 + R1), S = 256 / n1, R = (n1 + S - 1) / S;
+      if (tid < n * S) {   // column strips with rolling registers: 16 shared loads per pixel
+        const int x = off + tid % n, y0 = off + (tid / n) * R, y1 = min(y0 + R, off + n); const int gx = MirrorDev(tx0 + x, xs); const bool xborder = (gx & 7) == 0 || (gx & 7) == 7; const int isx = (gx >> 3) - bx0;
+        float h[3][4], v[4][3], pu[3], pl[3], pc[3], pr[3], pd[3];
 #pragma unroll
-      for (int k = 0; k < nn; k++) {
-        const int d = pass == 0 ? d12[k] : d4[k]; float sad = 0.f;
+        for (int rr = 0; rr < 3; rr++) for (int j = 0; j < 4; j++) h[rr][j] = Mh[(y0 - 1 + rr) * D + x - 2 + j];
 #pragma unroll
-        for (int c = 0; c < 3; c++) { const float* s = src + c * N + p; float sc;
-          if (pass == 2) sc = fabsf(s[d] - s[0]);
-          else sc = fabsf(s[d] - s[0]) + fabsf(s[d - D] - s[-D]) + fabsf(s[d + D] - s[D]) + fabsf(s[d - 1] - s[-1]) + fabsf(s[d + 1] - s[1]);
-          sad += sc * f.lpf.epf_channel_scale[c]; }
-        const float wgt = fmaxf(0.f, 1.0f + sad * inv); wsum += wgt; acc0 += wgt * src[p + d]; acc1 += wgt * src[N + p + d]; acc2 += wgt * src[2 * N + p + d];
+        for (int rr = 0; rr < 4; rr++) for (int j = 0; j < 3; j++) v[rr][j] = Mv[(y0 - 2 + rr) * D + x - 1 + j];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const float* s = src + c * N + y0 * D + x; pu[c] = s[-D]; pl[c] = s[-1]; pc[c] = s[0]; pr[c] = s[1]; pd[c] = s[D]; }
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          const int y = y0 + k; if (y >= y1) break;
+          const int p = y * D + x, gy = MirrorDev(ty0 + y, ys); const float is = s_is[((gy >> 3) - by0) * 8 + isx];
+          if (is < -3.90524291751269967465540850526868f) { dst[p] = pc[0]; dst[N + p] = pc[1]; dst[2 * N + p] = pc[2]; }
+          else {
+            const bool border = xborder || (gy & 7) == 0 || (gy & 7) == 7; const float inv = is * (border ? smb : sm);
+            const float sad_u = v[1][1] + v[0][1] + v[2][1] + v[1][0] + v[1][2];   // neighbour (y-1, x)
+            const float sad_l = h[1][1] + h[0][1] + h[2][1] + h[1][0] + h[1][2];   // neighbour (y, x-1)
+            const float sad_r = h[1][2] + h[0][2] + h[2][2] + h[1][1] + h[1][3];   // neighbour (y, x+1)
+            const float sad_d = v[2][1] + v[1][1] + v[3][1] + v[2][0] + v[2][2];   // neighbour (y+1, x)
+            const float wu = fmaxf(0.f, 1.0f + sad_u * inv), wl = fmaxf(0.f, 1.0f + sad_l * inv), wr = fmaxf(0.f, 1.0f + sad_r * inv), wd = fmaxf(0.f, 1.0f + sad_d * inv);
+            const float iw = 1.0f / (1.0f + wu + wl + wr + wd);
+#pragma unroll
+            for (int c = 0; c < 3; c++) dst[c * N + p] = (pc[c] + wu * pu[c] + wl * pl[c] + wr * pr[c] + wd * pd[c]) * iw;
+          }
+          if (y + 1 < y1) {   // roll the window one row down
+#pragma unroll
+            for (int j = 0; j < 4; j++) { h[0][j] = h[1][j]; h[1][j] = h[2][j]; h[2][j] = Mh[(y + 2) * D + x - 2 + j]; }
+#pragma unroll
+            for (int j = 0; j < 3; j++) { v[0][j] = v[1][j]; v[1][j] = v[2][j]; v[2][j] = v[3][j]; v[3][j] = Mv[(y + 2) * D + x - 1 + j]; }
+#pragma unroll
+            for (int c = 0; c < 3; c++) { const float* s = src + c * N + (y + 1) * D + x; pu[c] = pc[c]; pc[c] = pd[c]; pl[c] = s[-1]; pr[c] = s[1]; pd[c] = s[D]; }
+          }
+        }
       }
-      const float iw = 1.0f / wsum; dst[p] = acc0 * iw; dst[N + p] = acc1 * iw; dst[2 * N + p] = acc2 * iw;
+    } else {
+      for (int i = tid; i < n * n; i += 256) {
+        const int y = off + i / n, x = off + i % n, p = y * D + x; const int gy = MirrorDev(ty0 + y, ys), gx = MirrorDev(tx0 + x, xs);
+        const float is = s_is[((gy >> 3) - by0) * 8 + (gx >> 3) - bx0];
+        if (is < -3.90524291751269967465540850526868f) { dst[p] = src[p]; dst[N + p] = src[N + p]; dst[2 * N + p] = src[2 * N + p]; continue; }
+        const bool border = ((gy & 7) == 0 || (gy & 7) == 7 || (gx & 7) == 0 || (gx & 7) == 7); const float inv = is * (border ? smb : sm);
+        float wsum = 1.0f, acc0 = src[p], acc1 = src[N + p], acc2 = src[2 * N + p];
+        const int nn = pass == 0 ? 12 : 4;
+        const int d12[12] = {-2 * D, -D - 1, -D, -D + 1, -2, -1, 1, 2, D - 1, D, D + 1, 2 * D}; const int d4[4] = {-D, -1, 1, D};
+#pragma unroll
+        for (int k = 0; k < nn; k++) {
+          const int d = pass == 0 ? d12[k] : d4[k]; float sad = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; c++) { const float* s = src + c * N + p; float sc;
+            if (pass == 2) sc = fabsf(s[d] - s[0]);
+            else sc = fabsf(s[d] - s[0]) + fabsf(s[d - D] - s[-D]) + fabsf(s[d + D] - s[D]) + fabsf(s[d - 1] - s[-1]) + fabsf(s[d + 1] - s[1]);
+            sad += sc * (c == 0 ? cs0 : c == 1 ? cs1 : cs2); }
+          const float wgt = fmaxf(0.f, 1.0f + sad * inv); wsum += wgt; acc0 += wgt * src[p + d]; acc1 += wgt * src[N + p + d]; acc2 += wgt * src[2 * N + p + d];
+        }
+        const float iw = 1.0f / wsum; dst[p] = acc0 * iw; dst[N + p] = acc1 * iw; dst[2 * N + p] = acc2 * iw;
+      }
     }
     __syncthreads(); float* t = src; src = dst; dst = t;
   }
@@ -437,8 +499,8 @@ void LaunchGaborishPlanes(const DFrame* d, const DFrame& h, const float* src, fl
 const float* FilteredPlanes(const DFrame& h) { int n = (h.lpf.gab ? 1 : 0) + (h.lpf.epf_iters == 3 ? 3 : int(h.lpf.epf_iters)); return (n & 1) ? h.xyb_tmp : h.xyb; }
 // gaborish + EPF + colour in one pass over the frame (VarDCT frames with at least one restoration filter)
 template <int GAB, int EPF> static void LaunchRenderT(const DFrame& h, cudaStream_t st) {
-  constexpr int H = GAB + (EPF == 3 ? 3 : 0) + (EPF >= 1 ? 2 : 0) + (EPF >= 2 ? 1 : 0), D = 32 + 2 * H; size_t smem = size_t(6) * D * D * sizeof(float);
-  static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_render<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr = true; }
+  constexpr int H = GAB + (EPF == 3 ? 3 : 0) + (EPF >= 1 ? 2 : 0) + (EPF >= 2 ? 1 : 0), D = 32 + 2 * H; size_t smem = (size_t(EPF ? 8 : 6) * D * D + 64) * sizeof(float);
+  cudaFuncSetAttribute(k_render<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   dim3 grid((h.xsize + 31) / 32, (h.ysize + 31) / 32); k_render<GAB, EPF><<<grid, 256, smem, st>>>(h); CountLaunch();
 }
 bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st) {
