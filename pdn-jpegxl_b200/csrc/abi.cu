@@ -151,12 +151,16 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
     cudaStream_t copy_stream = all_streams[0]; std::vector<cudaStream_t> streams(all_streams.begin() + 1, all_streams.begin() + 1 + nstreams); void* pin = nullptr; size_t pin_bytes = 0;
     const int batch_lanes = (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
     struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; cudaStream_t stream = nullptr; };
-    // device-resident inputs: the headers are parsed on the host, so fetch all files once through one pinned buffer (asynchronously, one sync)
     std::vector<size_t> in_off(count + 1, 0); const uint8_t* host_in = nullptr;
+    // Device-resident inputs: the headers are parsed on the host, so every file comes back once through one pinned buffer. The copies
+    // are queued up front on their own stream, one event per file, and a file is only waited for when its turn to be parsed comes.
+    std::vector<cudaEvent_t> in_ready;
+    struct EventGuard { std::vector<cudaEvent_t>& v; ~EventGuard() { for (cudaEvent_t e : v) cudaEventDestroy(e); } } in_ready_guard{in_ready};
     if (!hostInputs) { for (int i = 0; i < count; i++) in_off[i + 1] = in_off[i] + ((dataSizes[i] + 63) & ~size_t(63));
-      pin_bytes = in_off[count] + 64; pin = PinnedGet(pin_bytes);
-      for (int i = 0; i < count; i++) cudaMemcpyAsync(static_cast<uint8_t*>(pin) + in_off[i], datas[i], dataSizes[i], cudaMemcpyDeviceToHost, copy_stream);
-      if (cudaStreamSynchronize(copy_stream) != cudaSuccess) { SetErrorMessage(errorInfo, "cannot read device inputs"); return DecoderStatus_DecodeError; } host_in = static_cast<uint8_t*>(pin); }
+      pin_bytes = in_off[count] + 64; pin = PinnedGet(pin_bytes); in_ready.resize(count, nullptr);
+      for (int i = 0; i < count; i++) { cudaMemcpyAsync(static_cast<uint8_t*>(pin) + in_off[i], datas[i], dataSizes[i], cudaMemcpyDeviceToHost, copy_stream);
+        if (cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(in_ready[i], copy_stream) != cudaSuccess) { SetErrorMessage(errorInfo, "cannot read device inputs"); if (pin) PinnedPut(pin, pin_bytes); return DecoderStatus_DecodeError; } }
+      host_in = static_cast<uint8_t*>(pin); }
     // host outputs that are page-locked receive the pixels directly (no staging copy)
     std::vector<uint8_t> out_is_pinned(count, 0);
     if (hostOutputs) for (int i = 0; i < count; i++) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, outputs[i]) == cudaSuccess && at.type == cudaMemoryTypeHost) out_is_pinned[i] = 1; else cudaGetLastError(); }
@@ -186,7 +190,7 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
         t0 = now(); const int i = next++;
         std::unique_ptr<InFlight> f(new InFlight); f->idx = i; f->stream = free_streams.back(); free_streams.pop_back();
         DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i]; req.out_capacity = outputBytes[i]; req.ac_lanes = batch_lanes;
-        if (hostInputs) req.data = datas[i]; else { req.data = host_in + in_off[i]; req.device_input = datas[i]; }
+        if (hostInputs) req.data = datas[i]; else { cudaEventSynchronize(in_ready[i]); req.data = host_in + in_off[i]; req.device_input = datas[i]; }
         if (!hostOutputs) { req.out_device = outputs[i]; f->direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f->direct = true; }
         f->job = DecodeEnqueue(req, f->stream, &f->res, true); t_enq += now() - t0;
         if (f->job) q1.push_back(std::move(f)); else finish(*f);

@@ -271,7 +271,8 @@ __global__ void k_inverse_rct(const DFrame* fp, uint32_t begin_c, uint32_t type)
 // ------------------------------------------------------------------ output
 // a^e for a >= 0 through the SFU (lg2 + ex2): relative error of a few 1e-7 here (|e * log2 a| < 16), far inside the 1-LSB / 1e-4 bounds
 // of the output formats; libm powf costs ~70 instructions per call and was 29 % of the fused kernel's issue slots (profiles/).
-__device__ __forceinline__ float PowSfu(float a, float e) { return a > 0.f ? exp2f(e * __log2f(a)) : 0.f; }
+__device__ __forceinline__ float PowSfu(float a, float e) {   // lg2(0) = -inf -> ex2(-inf) = +0: no branch needed for a == 0 (e > 0)
+  float l, r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(a)); asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * e)); return r; }
 __device__ __forceinline__ float TfFromLinearDev(float v, uint32_t tf, float gamma, float intensity_target) {
   float a = fabsf(v), r;
   switch (tf) {
@@ -317,11 +318,18 @@ __device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float
     float gm[3] = {Y + X, Y - X, B}, mix[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) { float v = gm[c] - f.color.opsin_bias_cbrt[c]; mix[c] = v * v * v + f.color.opsin_bias[c]; }
-    float lin[3];
+    float lin[6];
 #pragma unroll
     for (int c = 0; c < 3; c++) lin[c] = (f.color.opsin_inv[3 * c] * mix[0] + f.color.opsin_inv[3 * c + 1] * mix[1] + f.color.opsin_inv[3 * c + 2] * mix[2]) * f.color.itscale;
 #pragma unroll
-    for (int c = 0; c < 3; c++) rgb[c] = TfFromLinearDev(f.color.to_target[3 * c] * lin[0] + f.color.to_target[3 * c + 1] * lin[1] + f.color.to_target[3 * c + 2] * lin[2], f.color.tf, f.color.gamma, f.color.intensity_target);
+    for (int c = 0; c < 3; c++) lin[c + 3] = f.color.to_target[3 * c] * lin[0] + f.color.to_target[3 * c + 1] * lin[1] + f.color.to_target[3 * c + 2] * lin[2];
+    if (f.color.tf == 13) {   // sRGB curve, the common case: branch-free per channel
+#pragma unroll
+      for (int c = 0; c < 3; c++) { const float v = lin[c + 3], a = fabsf(v), r = a <= 0.0031308f ? 12.92f * a : 1.055f * PowSfu(a, 1.0f / 2.4f) - 0.055f; rgb[c] = v < 0 ? -r : r; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; c++) rgb[c] = TfFromLinearDev(lin[c + 3], f.color.tf, f.color.gamma, f.color.intensity_target);
+    }
   } else {
     const uint32_t nc = f.color.num_color;
     for (uint32_t c = 0; c < 3; c++) { const DModChannel& ch = f.mod_ch[c < nc ? c : nc - 1]; rgb[c] = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(y) * ch.w + x], o.bits, o.exp_bits); }
