@@ -467,7 +467,7 @@ def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, widt
     return data
 
 
-def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None):
+def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None, raise_on_error=True):
     """Host path: datas = list of bytes, out_arrays = list of writable numpy arrays. Device path: device_inputs/device_outputs = lists of int pointers."""
     n = len(datas) if device_inputs is None else len(device_inputs)
     ptrs = (C.c_void_p * n)()
@@ -493,7 +493,7 @@ def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16
     statuses = (C.c_int32 * n)()
     ei = ErrorInfo()
     st = _lib.JxlB200DecodeBatch(device, n, ptrs, lens, outs, olens, int(bgra), int(device_inputs is None), int(device_outputs is None), max_in_flight, statuses, C.byref(ei))
-    if st != 0:
+    if st != 0 and raise_on_error:
         raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
     return list(statuses)
 

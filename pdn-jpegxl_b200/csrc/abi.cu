@@ -164,7 +164,7 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
     // host outputs that are page-locked receive the pixels directly (no staging copy)
     std::vector<uint8_t> out_is_pinned(count, 0);
     if (hostOutputs) for (int i = 0; i < count; i++) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, outputs[i]) == cudaSuccess && at.type == cudaMemoryTypeHost) out_is_pinned[i] = 1; else cudaGetLastError(); }
-    const bool trace = getenv("JXLB200_TRACE") != nullptr; double acc_t[5] = {0, 0, 0, 0, 0}; double t_enq = 0, t_ret = 0; auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const bool trace = getenv("JXLB200_TRACE") != nullptr; double acc_t[5] = {0, 0, 0, 0, 0}; double t_enq = 0, t_ret = 0, t_idle = 0; auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     // Three-phase pipeline per image (LF entropy | AC entropy | reconstruction + render): a phase is enqueued only once the image's
     // stream has drained, so a kernel waiting on a 40 ms predecessor never sits at the head of a hardware queue shared with other
     // streams (there are 32 queues, and up to 256 images in flight). q1/q2/q3 hold the images whose phase 1/2/3 is running.
@@ -194,11 +194,11 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
         if (!hostOutputs) { req.out_device = outputs[i]; f->direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f->direct = true; }
         f->job = DecodeEnqueue(req, f->stream, &f->res, true); t_enq += now() - t0;
         if (f->job) q1.push_back(std::move(f)); else finish(*f);
-      } else if (!progressed) { t0 = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); t_ret += now() - t0; }
+      } else if (!progressed) { t0 = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); t_idle += now() - t0; }
     }
     if (trace) DumpHostTrace();
     if (trace && count) fprintf(stderr, "[jxlb200] GPU ms/image under load: lf %.2f ac %.2f recon %.2f render %.2f total %.2f\n", acc_t[0] / count, acc_t[1] / count, acc_t[2] / count, acc_t[3] / count, acc_t[4] / count);
-    if (trace) fprintf(stderr, "[jxlb200] batch of %d: host enqueue %.2f ms total (%.2f ms/image), retire/wait %.2f ms\n", count, t_enq, t_enq / std::max(count, 1), t_ret);
+    if (trace) fprintf(stderr, "[jxlb200] batch of %d: host parse + LF phase %.2f ms (%.2f ms/image), polling + later phases + retire %.2f ms, idle (GPU-bound) %.2f ms\n", count, t_enq, t_enq / std::max(count, 1), t_ret, t_idle);
     if (pin) PinnedPut(pin, pin_bytes);
   } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
   return first;

@@ -361,7 +361,7 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   h.ytox = d_ytox.as<int8_t>(); h.ytob = d_ytob.as<int8_t>(); h.hfmeta_scratch = d_hfmeta.as<int32_t>(); h.coeffs = d_coeffs.as<int16_t>(); h.xyb = d_xyb.as<float>(); h.xyb_tmp = d_xyb_tmp.as<float>(); h.inv_sigma = d_sigma.as<float>();
   h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = req.out_device ? req.out_device : d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
   bool smooth = vardct && !(h.flags & kFlagSkipAdaptiveLfSmoothing) && h.xb > 2 && h.yb > 2; h.lf_src = smooth ? h.lf_tmp : h.lf;
-  h.group_other = d_gother.as<uint32_t>(); h.nz_scratch = d_nz.as<uint8_t>(); h.ac_endpos = d_acend.as<uint64_t>();
+  memset(h_err.p, 0, 64); h.host_flags = h_err.as<uint32_t>() + 12; h.group_other = d_gother.as<uint32_t>(); h.nz_scratch = d_nz.as<uint8_t>(); h.ac_endpos = d_acend.as<uint64_t>();
   CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream)); CUDA_OK(cudaMemsetAsync(d_gother.p, 0, size_t(h.num_groups) * 4, stream));
   if (req.device_input && hd.ci.contiguous_offset != size_t(-1)) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input + hd.ci.contiguous_offset, comp_size, cudaMemcpyDeviceToDevice, stream));
   else { h_comp.Alloc(comp_size, true); memcpy(h_comp.p, cs.data(), comp_size); CUDA_OK(cudaMemcpyAsync(d_comp.p, h_comp.p, comp_size, cudaMemcpyHostToDevice, stream)); }   // pinned staging: a pageable source would serialise the stream
@@ -432,10 +432,10 @@ void DecodeJob::RunAc() {
 // Phase 3: dequant + IDCT, restoration filters, colour transform, pack, and the copy back to the host.
 void DecodeJob::RunRender() {
   const bool vardct = h.encoding == 0; const DFrame* d = d_frame.as<DFrame>(); double tt = NowMs();
-  const bool unfused = getenv("JXLB200_UNFUSED") != nullptr;
-  if (vardct && !d_xyb_tmp.p) {   // phased job: the stream is idle here, so reading the LF kernel's flags back costs microseconds
-    CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
-    const bool big_blocks = h_err.as<uint32_t>()[12] != 0, filters = h.lpf.gab || h.lpf.epf_iters;
+  static const bool unfused = getenv("JXLB200_UNFUSED") != nullptr;
+  if (vardct && !d_xyb_tmp.p) {   // phased job: the LF phase has drained, its flag word is already in host memory
+    const bool big_blocks = h_err.as<volatile uint32_t>()[12] != 0;   // written by k_lf_group straight into this page-locked word
+    const bool filters = h.lpf.gab || h.lpf.epf_iters;
     if (big_blocks || (filters && unfused)) { d_xyb_tmp.Alloc(size_t(h.xpad) * h.ypad * 3 * 4); h.xyb_tmp = d_xyb_tmp.as<float>(); UploadFrame(); }
   }
   static const int dbg_skip = getenv("JXLB200_DEBUG_SKIP") ? atoi(getenv("JXLB200_DEBUG_SKIP")) : 0;   // timing experiments only: 1 = no reconstruction, 2 = no render, 3 = neither

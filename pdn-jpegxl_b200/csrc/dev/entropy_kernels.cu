@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame 
       int32_t qf = max(0, min(255, s_info[nb + num]));
       for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { size_t p = o + size_t(iy) * f.xb + ix; if (f.acs[p] != 0xFF) e = kErrBlockBounds; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = uint8_t(qf); }
       f.acs[o] = uint8_t(s | 0x80); num++; if (s != 0) atomicAdd(f.group_other + ((cy0 + y) >> 5) * f.xgroups + ((cx0 + x) >> 5), 1u);
-      if (bw * bh >= 64) atomicOr(f.err + 12, 1u);   // a transform of 64x64 px or more: reconstruction needs the second plane set (xyb_tmp)
+      if (bw * bh >= 64) { atomicOr(f.err + 12, 1u); *reinterpret_cast<volatile uint32_t*>(f.host_flags) = 1u; }   // host_flags: page-locked host word, read by the host once this kernel has drained   // a transform of 64x64 px or more: reconstruction needs the second plane set (xyb_tmp)
     }
     SetError(f.err, e);
   }
@@ -278,7 +278,7 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
   SetError(f.err, md.rd.err);
 }
 
-static void EnsureSmemAttr() { static bool done = false; if (done) return; done = true;
+static void EnsureSmemAttr() { static bool done[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (done[dev & 63]) return; done[dev & 63] = true;   // function attributes are per device
   cudaFuncSetAttribute(k_lf_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
 void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (!h.num_lf_groups) return; const bool narrow = !h.uses_wp && !h.mod_wide;
   if (narrow) k_lf_group<true><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); else k_lf_group<false><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); }

@@ -488,8 +488,8 @@ __global__ void k_output_int(const DFrame* fp) {
 }
 
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st) {
-  static bool attr = false; size_t smem = size_t(kReconWarps) * 3072 * sizeof(float);
-  if (!attr) { cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr = true; }
+  static bool attr[64] = {false}; size_t smem = size_t(kReconWarps) * 3072 * sizeof(float); int dev = 0; cudaGetDevice(&dev);
+  if (!attr[dev & 63]) { cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; }
   k_reconstruct_dct8<<<h.num_groups * 4, 256, 0, st>>>(h); k_reconstruct<<<h.num_groups, kReconWarps * 32, smem, st>>>(d); CountLaunch(2);
 }
 // Runs gaborish + EPF; ping-pongs between xyb and xyb_tmp. Returns the buffer holding the result.
@@ -508,7 +508,7 @@ const float* FilteredPlanes(const DFrame& h) { int n = (h.lpf.gab ? 1 : 0) + (h.
 // gaborish + EPF + colour in one pass over the frame (VarDCT frames with at least one restoration filter)
 template <int GAB, int EPF> static void LaunchRenderT(const DFrame& h, cudaStream_t st) {
   constexpr int H = GAB + (EPF == 3 ? 3 : 0) + (EPF >= 1 ? 2 : 0) + (EPF >= 2 ? 1 : 0), D = 32 + 2 * H; size_t smem = (size_t(EPF ? 8 : 6) * D * D + 64) * sizeof(float);
-  cudaFuncSetAttribute(k_render<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  { static bool attr[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (!attr[dev & 63]) { cudaFuncSetAttribute(k_render<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; } }
   dim3 grid((h.xsize + 31) / 32, (h.ysize + 31) / 32); k_render<GAB, EPF><<<grid, 256, smem, st>>>(h); CountLaunch();
 }
 bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st) {

@@ -162,3 +162,33 @@ def test_batch_matches_single_decodes(gpu, oracle):
     assert st == [0] * 6
     for f, o in zip(files, outs):
         assert np.array_equal(o, _decode_gpu(gpu, f).layer_data.color)
+
+
+def test_batch_pipeline_mixed_content(gpu, oracle):
+    """The three-phase batch pipeline with 8 sections per warp (count >= 8), on files that exercise its lazy paths: 64x64+ transforms
+    (second plane set allocated only when the LF kernel reports them), multi-group frames, alpha, and a lossless Modular frame."""
+    imgs, files = [], []
+    for i, strat in enumerate([0, 21, 24, 26, 5, 18, 0, 22, 4, 25]):
+        img = oracle.synthetic_image(600 + 16 * i, 520, seed=40 + i)
+        files.append(oracle.encode(img, effort=3, force_strategy=strat))
+    rgba = oracle.synthetic_image(520, 300, seed=77, channels=4)
+    files.append(oracle.encode(rgba, effort=7))
+    files.append(oracle.encode(oracle.synthetic_image(300, 280, seed=78), lossless=True))
+    singles = []
+    for f in files:   # the batch writes the interleaved buffer LoadImage hands to setLayerData: colour channels, then alpha
+        ld = _decode_gpu(gpu, f).layer_data
+        singles.append(ld.color if ld.transparency is None else np.concatenate([ld.color, ld.transparency[..., None]], axis=2))
+    outs = [np.zeros_like(s) for s in singles]
+    st = gpu.decode_batch(files, outs, max_in_flight=12)
+    assert st == [0] * len(files)
+    for o, s in zip(outs, singles):
+        assert np.array_equal(o, s)
+    # one broken file must not disturb its neighbours
+    bad = list(files); bad[3] = files[3][: len(files[3]) // 2]
+    outs2 = [np.zeros_like(s) for s in singles]
+    st2 = gpu.decode_batch(bad, outs2, max_in_flight=12, raise_on_error=False) if "raise_on_error" in gpu.decode_batch.__code__.co_varnames else None
+    if st2 is not None:
+        assert st2[3] != 0 and all(s == 0 for i, s in enumerate(st2) if i != 3)
+        for i, (o, s) in enumerate(zip(outs2, singles)):
+            if i != 3:
+                assert np.array_equal(o, s)
