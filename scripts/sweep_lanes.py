@@ -25,7 +25,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"lanes": os.environ.get("JXLB200_AC_LANES"), "in_flight": inflight, "batch": B, "mp_s": B * W * H / 1e6 / dt, "ms_per_image": dt * 1e3 / B}))
     sys.exit(0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-for lanes, infl in [(8, 128), (8, 128), (16, 192)]:
+for lanes, infl in [(8, 128), (8, 192), (8, 256), (16, 256), (4, 256)]:
     env = dict(os.environ, JXLB200_AC_LANES=str(lanes))
     r = subprocess.run([sys.executable, __file__, "child", str(B), str(infl)], env=env, capture_output=True, text=True)
     print("\n".join(r.stdout.strip().splitlines()[-2:]) if r.stdout.strip() else "FAILED " + r.stderr[-400:], flush=True)
