@@ -1,6 +1,7 @@
 // ORACLE — test infrastructure only (see jxlo_bits.h header). PARITY UNPINNED.
 // C API over the oracle for ctypes (tests/, __graft_entry__.smoke(), bench.py cpu_baseline).
 #include "jxlo_encoder.h"
+#include "jxlo_icc.h"
 #include <dlfcn.h>
 
 namespace jxlo {
@@ -13,9 +14,6 @@ std::vector<uint8_t> BrotliDecompress(const uint8_t* data, size_t size) {
   }
   throw Error("brob box: brotli stream invalid or too large");
 }
-// ICC stream: not restated yet (SURVEY A.3 [L]); files that signal want_icc are rejected by the oracle.
-std::vector<uint8_t> ReadIccStream(BitReader&) { throw Error("ICC streams are not supported by the oracle yet"); }
-void WriteIccStream(BitWriter&, const std::vector<uint8_t>&) { throw Error("ICC streams are not supported by the oracle yet"); }
 }  // namespace jxlo
 
 using namespace jxlo;
@@ -28,6 +26,7 @@ struct jxlo_encode_params {
   int32_t bits; int32_t exp_bits; int32_t color_space; int32_t white_point; int32_t primaries; int32_t tf; int32_t intent; float intensity_target; int32_t premultiplied; int32_t black_channel;
 };
 
+static thread_local std::vector<uint8_t> g_next_icc;
 static void SetErr(char* err, size_t n, const char* msg) { if (err && n) { strncpy(err, msg, n - 1); err[n - 1] = 0; } }
 
 void jxlo_default_params(jxlo_encode_params* p) {
@@ -45,10 +44,27 @@ int jxlo_encode(const void* pixels, int is_float, uint32_t width, uint32_t heigh
     p.ce.primaries = uint32_t(cp->primaries); p.ce.tf = uint32_t(cp->tf); p.ce.intent = uint32_t(cp->intent); p.intensity_target = cp->intensity_target; p.premultiplied = cp->premultiplied != 0; p.black_channel = cp->black_channel != 0;
     EncodeInput in; in.width = width; in.height = height; in.num_color = num_color; in.has_alpha = has_alpha != 0; if (is_float) in.f32 = static_cast<const float*>(pixels); else in.u8 = static_cast<const uint8_t*>(pixels);
     in.exif = exif; in.exif_size = exif_size; in.xmp = xmp; in.xmp_size = xmp_size;
+    std::vector<uint8_t> icc; icc.swap(g_next_icc); in.icc = icc.data(); in.icc_size = icc.size();
     std::vector<uint8_t> v = EncodeImage(in, p); *out = static_cast<uint8_t*>(malloc(v.size() ? v.size() : 1)); memcpy(*out, v.data(), v.size()); *out_size = v.size(); return 0;
   } catch (const std::exception& e) { SetErr(err, errlen, e.what()); return 1; }
 }
 void jxlo_free(void* p) { free(p); }
+// ICC profile attached to the NEXT jxlo_encode call of this thread (keeps jxlo_encode's signature stable); cleared by that call.
+void jxlo_set_next_icc(const uint8_t* icc, size_t n) { g_next_icc.assign(icc, icc + n); }
+// ICC stream codec alone (bit stream as it sits in the codestream after ImageMetadata)
+int jxlo_icc_stream_write(const uint8_t* icc, size_t n, uint8_t** out, size_t* out_size, char* err, size_t errlen) {
+  try { BitWriter bw; WriteIccStream(bw, std::vector<uint8_t>(icc, icc + n)); std::vector<uint8_t> b = bw.Finish(); *out = static_cast<uint8_t*>(malloc(b.size() ? b.size() : 1)); memcpy(*out, b.data(), b.size()); *out_size = b.size(); return 0; }
+  catch (const std::exception& e) { SetErr(err, errlen, e.what()); return 1; }
+}
+int jxlo_icc_stream_read(const uint8_t* data, size_t n, uint8_t** out, size_t* out_size, char* err, size_t errlen) {
+  try { BitReader br(data, n); std::vector<uint8_t> v = ReadIccStream(br); JXLO_CHECK(!br.overrun, "ICC stream truncated"); *out = static_cast<uint8_t*>(malloc(v.size() ? v.size() : 1)); memcpy(*out, v.data(), v.size()); *out_size = v.size(); return 0; }
+  catch (const std::exception& e) { SetErr(err, errlen, e.what()); return 1; }
+}
+// Replays a hand-written predicted-ICC byte string (commands + data) through the predictor only: lets the tests exercise every command.
+int jxlo_icc_unpredict(const uint8_t* enc, size_t n, uint8_t** out, size_t* out_size, char* err, size_t errlen) {
+  try { std::vector<uint8_t> v = UnpredictIcc(std::vector<uint8_t>(enc, enc + n)); *out = static_cast<uint8_t*>(malloc(v.size() ? v.size() : 1)); memcpy(*out, v.data(), v.size()); *out_size = v.size(); return 0; }
+  catch (const std::exception& e) { SetErr(err, errlen, e.what()); return 1; }
+}
 
 struct jxlo_image { DecodedImage img; };
 
@@ -64,6 +80,7 @@ void jxlo_image_info(const jxlo_image* i, int32_t* info) {
 }
 const uint8_t* jxlo_image_pixels(const jxlo_image* i, size_t* n) { *n = i->img.pixels.size(); return i->img.pixels.data(); }
 const char* jxlo_image_name(const jxlo_image* i, size_t* n) { *n = i->img.frame_name.size(); return i->img.frame_name.data(); }
+const uint8_t* jxlo_image_icc(const jxlo_image* i, size_t* n) { *n = i->img.meta.icc.size(); return i->img.meta.icc.data(); }
 const uint8_t* jxlo_image_exif(const jxlo_image* i, size_t* n) { *n = i->img.exif.size(); return i->img.exif.data(); }
 const uint8_t* jxlo_image_xmp(const jxlo_image* i, int k, size_t* n) { *n = i->img.xmp[k].size(); return i->img.xmp[k].data(); }
 // which: 0 idct, 1 gab, 2 epf (3 planes xpad*ypad floats), 3 lf (3 planes xb*yb); returns element count

@@ -9,6 +9,8 @@
 #include "host/headers.h"
 #include "host/modular_host.h"
 #include "host/vardct_tables.h"
+#define JXLG_ICC_DEFINE_STREAM_FUNCS
+#include "host/icc.h"
 #include <dlfcn.h>
 #include <map>
 #include <mutex>
@@ -89,8 +91,6 @@ static std::vector<uint8_t> BrotliDecompress(const uint8_t* data, size_t size) {
   for (size_t cap = std::max<size_t>(size * 8, 1 << 16); cap <= (size_t(1) << 31); cap *= 4) { std::vector<uint8_t> out(cap); size_t n = cap; if (fn(size, data, &n, out.data()) == 1) { out.resize(n); return out; } }
   throw Error("brob box: brotli stream invalid or too large");
 }
-std::vector<uint8_t> ReadIccStream(BitReader&) { throw Error("ICC-stream colour profiles are not supported yet"); }
-void WriteIccStream(BitWriter&, const std::vector<uint8_t>&) { throw Error("ICC-stream colour profiles are not supported yet"); }
 
 // ---------------------------------------------------------------- pass 1: info + metadata
 struct Headers { ContainerInfo ci; ImageMetadata meta; size_t frame_pos = 0; /* byte offset of the first frame in the codestream */ };
@@ -135,6 +135,8 @@ static Status ParseHeadersInto(const uint8_t* data, size_t size, Headers* h, Par
   if (m.orientation >= 5) std::swap(info->width, info->height);
   // COLOR_ENCODING, :562-686 — the profile reported is the one describing the delivered samples
   ColorEncoding out_ce = OutputEncoding(m); info->known_profile = KnownProfileOf(out_ce); if (m.ce.want_icc && !m.xyb_encoded) info->icc = m.icc;
+  // encodings libjxl can express but the 8 known enums cannot (custom primaries / white point, pure gamma, DCI): synthesised ICC
+  if (info->known_profile < 0 && info->icc.empty() && !out_ce.want_icc) info->icc = SynthesizeIcc(out_ce);
   // BOX events, :687-784: first Exif box only, every xml box, brob decompressed; container files only
   for (const Box& b : h->ci.boxes) {
     const uint8_t* p = b.data; size_t n = b.size; char type[5]; memcpy(type, b.type, 5); std::vector<uint8_t> tmp;
@@ -295,6 +297,7 @@ void DecodeJob::Setup(const DecodeRequest& req) {
   JXLG_CHECK(fh.upsampling == 1, "upsampling is not supported"); JXLG_CHECK(!fh.do_ycbcr, "YCbCr (JPEG-recompressed) frames are not supported");
   JXLG_CHECK(!fh.have_crop || (fh.x0 == 0 && fh.y0 == 0 && fh.width == m.xsize && fh.height == m.ysize), "cropped frames are not supported");
   JXLG_CHECK(fh.passes.num_passes <= uint32_t(kMaxPasses), "too many passes");
+  JXLG_CHECK(fh.encoding != 0 || m.xyb_encoded, "VarDCT frames that are not XYB-encoded are not supported");
   toc = ReadToc(br, fh); frame_off = pos + br.pos / 8; JXLG_CHECK(frame_off + toc.total <= cs.size(), "JxlDecoderProcessInput needs more input, but it already received the entire image.");
   info.frame_name = fh.name; info.bpp = double(cs.size()) * 8.0 / (double(m.xsize) * m.ysize);
   memset(&h, 0, sizeof(h)); bgra = req.bgra; device_output = req.device_output;

@@ -11,6 +11,7 @@ struct DEncFrame {
   uint32_t xsize, ysize, stride, xpad, ypad, xb, yb, xgroups, ygroups, num_groups, gray, alpha, alpha_plane, hf_mul;
   float inv_gs, xm, bm, kx, kb, lf_fac[3], cfl_x_lf, cfl_b_lf, quant_bias[4];
   float* xyb; int32_t* planes; float* lf; int32_t* lfq; int16_t* coeffs; uint8_t* nz; const float* dequant8; const uint16_t* order8; const DTables* tables;
+  const float* src_lut; float src_matrix[9]; uint32_t has_src_profile, pad0;   // ICC-described source: per-channel tone LUT [3][256] + matrix to linear sRGB (null / 0: sRGB input)
   uint2* tokens; uint64_t ac_token_off; uint32_t* ac_token_count; uint8_t* stream_bytes; uint64_t* stream_bits;
 };
 struct DEncModStream { uint32_t x0, y0, w, h, kind, pad; uint64_t token_off; };

@@ -26,7 +26,11 @@ __global__ void k_enc_scan(const uint8_t* __restrict__ bgra, uint32_t w, uint32_
 __global__ void k_enc_to_xyb(const DEncFrame* ep, const uint8_t* __restrict__ bgra) {
   const DEncFrame& e = *ep; int xx = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y * blockDim.y + threadIdx.y; if (xx >= int(e.xpad) || yy >= int(e.ypad)) return;
   int x = min(xx, int(e.xsize) - 1), y = min(yy, int(e.ysize) - 1); uchar4 p = *reinterpret_cast<const uchar4*>(bgra + size_t(y) * e.stride + size_t(x) * 4);
-  float r = kSrgbLut[e.gray ? p.x : p.z], g = kSrgbLut[e.gray ? p.x : p.y], b = kSrgbLut[p.x];   // gray takes the B channel (N/Encoder/PixelFormatConversion.cpp:34)
+  float r, g, b;
+  if (e.has_src_profile) {   // matrix/TRC ICC source: tone curves from the profile, then its colorants -> linear sRGB (what libjxl's CMS step does)
+    const float lr = e.src_lut[p.z], lg = e.src_lut[256 + p.y], lb = e.src_lut[512 + p.x]; const float* m = e.src_matrix;
+    r = m[0] * lr + m[1] * lg + m[2] * lb; g = m[3] * lr + m[4] * lg + m[5] * lb; b = m[6] * lr + m[7] * lg + m[8] * lb;
+  } else { r = kSrgbLut[e.gray ? p.x : p.z]; g = kSrgbLut[e.gray ? p.x : p.y]; b = kSrgbLut[p.x]; }   // gray takes the B channel (N/Encoder/PixelFormatConversion.cpp:34)
   const float bias = 0.0037930732552754493f, cb = cbrtf(bias);
   float m0 = 0.30f * r + 0.622f * g + 0.078f * b + bias, m1 = 0.23f * r + 0.692f * g + 0.078f * b + bias, m2 = 0.24342268924547819f * r + 0.20476744424496821f * g + 0.55180986650955360f * b + bias;
   float g0 = cbrtf(fmaxf(m0, 0.f)) - cb, g1 = cbrtf(fmaxf(m1, 0.f)) - cb, g2 = cbrtf(fmaxf(m2, 0.f)) - cb;

@@ -11,6 +11,7 @@
 #include "host/headers.h"
 #include "host/modular_host.h"
 #include "host/vardct_tables.h"
+#include "host/icc.h"
 #include <map>
 #include <mutex>
 #include <cmath>
@@ -116,9 +117,15 @@ EncodeResult EncodeOnGpu(const EncodeRequest& req) {
     d_flags.Alloc(16); CUDA_OK(cudaMemsetAsync(d_flags.p, 0, 16, st)); EncLaunchScan(d_bgra, xs, ys, req.stride, d_flags.as<uint32_t>(), st);
     uint32_t flags = 0; CUDA_OK(cudaMemcpyAsync(&flags, d_flags.p, 4, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
     const bool is_gray = !(flags & 1) && req.icc_size == 0, has_alpha = (flags & 2) != 0; res.pixel_format = is_gray ? (has_alpha ? 1 : 0) : (has_alpha ? 3 : 2);
-    JXLG_CHECK(req.icc_size == 0, "ICC-stream colour profiles are not supported yet");
     // ---- headers
     ImageMetadata m; m.xsize = xs; m.ysize = ys; m.xyb_encoded = !lossless; m.ce.intent = 0; if (is_gray) m.ce.color_space = kCsGray;   // sRGB, perceptual intent (N/Encoder/JxlEncoder.cpp:269-282)
+    // ICC profile given (N/Encoder/JxlEncoder.cpp:258-262): the codestream carries it as an ICC stream. Lossless keeps the samples as they are;
+    // lossy needs the source -> XYB mapping, which libjxl gets from a CMS and the engine reads from a matrix/TRC profile directly.
+    IccMatrixTrc src_profile; bool has_src_profile = false;
+    if (req.icc_size) {
+      m.ce.want_icc = true; m.icc.assign(req.icc, req.icc + req.icc_size);
+      if (!lossless) { std::string why; JXLG_CHECK(ParseMatrixTrcIcc(req.icc, req.icc_size, &src_profile, &why), why + " — lossy encoding of this profile needs a CMS, which the engine does not have"); has_src_profile = true; }
+    }
     if (has_alpha) { ExtraChannelInfo a; a.type = kEcAlpha; m.ec.push_back(a); }
     const int num_ec = has_alpha ? 1 : 0, ncolor = is_gray ? 1 : 3;
     FrameHeader fh; fh.encoding = lossless ? 1 : 0; fh.ec_upsampling.assign(num_ec, 1); fh.ec_blending.assign(num_ec, BlendingInfo());
@@ -133,6 +140,7 @@ EncodeResult EncodeOnGpu(const EncodeRequest& req) {
     for (int kind = 0; kind < 3; kind++) for (int c = 0; c < 8; c++) for (int b = 0; b < 11; b++) { int stream = kind == 0 ? 1 : kind == 1 ? int(1 + 3 * nlf + 17) : 0; leaf_lut[(kind * 8 + c) * 11 + b] = uint16_t(LeafFor(tree, c, stream, 1, kProp8Rep[b]).leaf_id); }
     // ---- device frame
     DEncFrame e; memset(&e, 0, sizeof(e)); e.xsize = xs; e.ysize = ys; e.stride = req.stride; e.xb = fh.xblocks; e.yb = fh.yblocks; e.xpad = e.xb * 8; e.ypad = e.yb * 8; e.xgroups = fh.xgroups; e.ygroups = fh.ygroups; e.num_groups = ng; e.gray = is_gray; e.alpha = has_alpha;
+    Buf d_srclut; if (has_src_profile) { d_srclut.Alloc(sizeof(src_profile.lut)); CUDA_OK(cudaMemcpyAsync(d_srclut.p, src_profile.lut, sizeof(src_profile.lut), cudaMemcpyHostToDevice, st)); e.src_lut = d_srclut.as<float>(); e.has_src_profile = 1; for (int i = 0; i < 9; i++) e.src_matrix[i] = float(src_profile.to_linear_srgb[i]); }
     e.tables = EncDeviceTables(); const size_t npx = size_t(xs) * ys, ppx = size_t(e.xpad) * e.ypad, cells = size_t(e.xb) * e.yb;
     const int nplanes = lossless ? ncolor + num_ec : num_ec; e.alpha_plane = lossless ? uint32_t(ncolor) : 0;
     uint32_t global_scale = 1, quant_lf = 16; float q_ac = 1;
@@ -165,7 +173,7 @@ EncodeResult EncodeOnGpu(const EncodeRequest& req) {
     // ---- pixels -> planes / XYB -> DCT + quant
     if (lossless) EncLaunchToPlanes(de, e, d_bgra, st);
     else {
-      EncLaunchToXyb(de, e, d_bgra, st);
+      EncLaunchToXyb(de, e, d_bgra, st);   // e.src_lut / e.src_matrix were filled above when an ICC source profile is in use
       if (fh.lf.gab) {   // approximate inverse gaborish: two Van Cittert iterations against the decoder's own kernel (padded frame, mirrored edges)
         d_tmp1.Alloc(ppx * 12); d_tmp2.Alloc(ppx * 12); d_gabframe.Alloc(sizeof(DFrame)); DFrame gf; memset(&gf, 0, sizeof(gf)); gf.xsize = e.xpad; gf.ysize = e.ypad; gf.xpad = e.xpad; gf.ypad = e.ypad; gf.lpf.gab = 1; memcpy(gf.lpf.gab_w, fh.lf.gab_w, sizeof(gf.lpf.gab_w));
         CUDA_OK(cudaMemcpyAsync(d_gabframe.p, &gf, sizeof(gf), cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(d_tmp1.p, d_xyb.p, ppx * 12, cudaMemcpyDeviceToDevice, st));

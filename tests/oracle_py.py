@@ -46,7 +46,7 @@ def lib():
         L.jxlo_image_free.argtypes = [C.c_void_p]
         L.jxlo_free.argtypes = [C.c_void_p]
         L.jxlo_image_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
-        for n in ("jxlo_image_pixels", "jxlo_image_name", "jxlo_image_exif"):
+        for n in ("jxlo_image_pixels", "jxlo_image_name", "jxlo_image_exif", "jxlo_image_icc"):
             getattr(L, n).argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
             getattr(L, n).restype = C.c_void_p
         L.jxlo_image_xmp.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
@@ -55,6 +55,9 @@ def lib():
         L.jxlo_image_stage_f32.restype = C.c_size_t
         L.jxlo_image_stage_coeffs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.jxlo_image_stage_coeffs.restype = C.c_size_t
+        L.jxlo_set_next_icc.argtypes = [C.c_char_p, C.c_size_t]
+        for n in ("jxlo_icc_stream_write", "jxlo_icc_stream_read", "jxlo_icc_unpredict"):
+            getattr(L, n).argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
         L.jxlo_signature_check.argtypes = [C.c_void_p, C.c_size_t]
         L.jxlo_transform_to_pixels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlo_transform_from_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -83,7 +86,7 @@ class OracleError(RuntimeError):
     pass
 
 
-def encode(pixels, num_color=None, has_alpha=None, exif=b"", xmp=b"", **kw):
+def encode(pixels, num_color=None, has_alpha=None, exif=b"", xmp=b"", icc=b"", **kw):
     """pixels: HxWxC uint8 or float32 array (C = colour [+black] [+alpha])."""
     a = np.ascontiguousarray(pixels)
     if a.ndim == 2:
@@ -102,6 +105,8 @@ def encode(pixels, num_color=None, has_alpha=None, exif=b"", xmp=b"", **kw):
     out = C.c_void_p()
     n = C.c_size_t()
     err = C.create_string_buffer(512)
+    if icc:
+        lib().jxlo_set_next_icc(bytes(icc), len(icc))
     rc = lib().jxlo_encode(a.ctypes.data, int(is_float), w, h, num_color, int(has_alpha), C.byref(p), exif, len(exif), xmp, len(xmp),
                            C.byref(out), C.byref(n), err, 512)
     if rc:
@@ -109,6 +114,27 @@ def encode(pixels, num_color=None, has_alpha=None, exif=b"", xmp=b"", **kw):
     data = C.string_at(out, n.value)
     lib().jxlo_free(out)
     return data
+
+
+def _icc_call(fn, data):
+    out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
+    if fn(bytes(data), len(data), C.byref(out), C.byref(n), err, 512):
+        raise OracleError(err.value.decode())
+    r = C.string_at(out, n.value)
+    lib().jxlo_free(out)
+    return r
+
+
+def icc_stream_write(icc):
+    return _icc_call(lib().jxlo_icc_stream_write, icc)
+
+
+def icc_stream_read(data):
+    return _icc_call(lib().jxlo_icc_stream_read, data)
+
+
+def icc_unpredict(enc):
+    return _icc_call(lib().jxlo_icc_unpredict, enc)
 
 
 _DT = {0: np.uint8, 1: np.uint16, 2: np.float16, 3: np.float32}
@@ -137,6 +163,8 @@ def decode(data, threads=1, keep_stages=False):
         d.pixels = raw.reshape(d.height, d.width, -1).copy()
         p = lib().jxlo_image_name(img, C.byref(n))
         d.name = C.string_at(p, n.value) if n.value else b""
+        p = lib().jxlo_image_icc(img, C.byref(n))
+        d.icc = C.string_at(p, n.value) if n.value else None
         p = lib().jxlo_image_exif(img, C.byref(n))
         d.exif = C.string_at(p, n.value) if d.has_exif else None
         d.xmp = []

@@ -152,3 +152,96 @@ def test_orientation_and_16bit_float_outputs(oracle):
     assert dh.sample_type == 2 and dh.pixels.dtype == np.float16
     df = oracle.decode(oracle.encode(f, bits=32, exp_bits=8, effort=3))
     assert df.sample_type == 3 and df.pixels.dtype == np.float32 and oracle.psnr(df.pixels * 255.0, img) > 30
+
+
+# ---------------------------------------------------------------- ICC profile stream (SURVEY A.3 "ICC stream")
+def _varint(v):
+    out = bytearray()
+    while v > 127:
+        out.append((v & 127) | 128)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_icc_stream_round_trip(oracle):
+    import icc_util
+    rng = np.random.default_rng(5)
+    profiles = [icc_util.make_matrix_icc(icc_util.P3_PRIMS, gamma=2.2), icc_util.make_matrix_icc(icc_util.ADOBE_PRIMS, gamma=2.19921875, curve="curv1"),
+                icc_util.make_matrix_icc(icc_util.SRGB_PRIMS, gamma=2.4, curve="table"), bytes(rng.integers(0, 256, 1, dtype=np.uint8)),
+                bytes(rng.integers(0, 256, 127, dtype=np.uint8)), bytes(rng.integers(0, 256, 128, dtype=np.uint8)), bytes(rng.integers(0, 256, 5000, dtype=np.uint8))]
+    for icc in profiles:
+        stream = oracle.icc_stream_write(icc)
+        assert oracle.icc_stream_read(stream) == icc
+    # the predicted header makes a real profile's first 128 bytes nearly free
+    real = profiles[0]
+    assert len(oracle.icc_stream_write(real)) < len(real)
+
+
+def test_icc_predictor_commands(oracle):
+    """Hand-written command streams through the predictor: tag-table shortcuts (TRC / XYZ triples, named tags, explicit offsets), type
+    keywords, the XYZ command, shuffled and N-th order predicted runs. Expected bytes are computed here, independently of the C++."""
+    import struct
+    header = bytearray(128)
+    header[8] = 4; header[12:16] = b"mntr"; header[16:20] = b"RGB "; header[20:24] = b"XYZ "; header[36:40] = b"acsp"
+    header[68:80] = bytes([0, 0, 0xF6, 0xD6, 0, 1, 0, 0, 0, 0, 0xD3, 0x2D])
+    # expected profile: header (with a few deviations from the prediction), tag table of 8 tags, then content
+    # (the implicit offset of the first tag is 128 + 12 * numtags: the predictor does not count the 4-byte tag count)
+    want_tags = [(b"desc", 128 + 8 * 12, 40), (b"rTRC", 264, 16), (b"gTRC", 264, 16), (b"bTRC", 264, 16), (b"rXYZ", 280, 20), (b"gXYZ", 300, 20), (b"bXYZ", 320, 20), (b"ABCD", 1000, 7)]
+    content = b"mluc" + b"\0" * 4 + bytes(range(32))                                        # type keyword command + raw insert
+    content += b"XYZ " + b"\0" * 4 + bytes(range(100, 112))                                  # XYZ command
+    ramp16 = b"".join(struct.pack(">H", 1000 + 37 * i) for i in range(24))                   # order-1, width-2 predictable ramp
+    content += ramp16
+    shuf_src = bytes(range(200, 216))                                                        # shuffle-4 run
+    content += shuf_src
+    total = 128 + 4 + 12 * len(want_tags) + len(content)
+    hdr = bytearray(header); hdr[0:4] = struct.pack(">I", total); hdr[4:8] = b"lcms"; hdr[40:44] = b"APPL"; hdr[80:84] = b"lcms"; hdr[100] = 9
+    expected = bytes(hdr) + struct.pack(">I", len(want_tags)) + b"".join(s + struct.pack(">II", o, n) for s, o, n in want_tags) + content
+
+    # --- encode by hand
+    pred = bytearray(header); pred[0:4] = struct.pack(">I", total)
+    data = bytearray()
+    for i in range(128):
+        if i == 8:
+            pred[80:84] = hdr[4:8]
+        if i == 41 and hdr[40] == ord("A"):
+            pred[41:44] = b"PPL"
+        data.append((hdr[i] - pred[i]) & 255)
+    cmds = bytearray()
+    cmds += _varint(len(want_tags) + 1)
+    cmds += bytes([4 + 12 | 128]) + _varint(40)                     # 'desc' (string index 12), implicit offset, explicit size
+    cmds += bytes([2 | 128]) + _varint(16)                          # TRC triple, implicit offset (= 224 + 40), explicit size
+    cmds += bytes([3])                                              # XYZ triple: offset = prev start + prev size, size 20 implied
+    cmds += bytes([1 | 64 | 128]) + _varint(1000) + _varint(7)      # unknown tag: keyword from the data stream, explicit offset + size
+    data += b"ABCD"
+    cmds += bytes([0])                                              # end of tag list
+    cmds += bytes([16 + 3])                                         # type keyword 'mluc' + 4 zero bytes
+    cmds += bytes([1]) + _varint(32); data += bytes(range(32))     # insert
+    cmds += bytes([10]); data += bytes(range(100, 112))             # XYZ
+    # predicted run: width 2 (flags bits 0-1 = 1), order 1 (bits 2-3 = 1), default stride = width; residuals then byte-plane split
+    first = ramp16[:4]
+    cmds += bytes([1]) + _varint(4); data += first
+    resid = bytearray()
+    vals = [1000 + 37 * i for i in range(24)]
+    prevbytes = bytes(expected[: expected.index(ramp16) + 4])
+    out_so_far = bytearray(prevbytes)
+    for i in range(2, 24):
+        p1 = (out_so_far[-2] << 8) | out_so_far[-1]; p2 = (out_so_far[-4] << 8) | out_so_far[-3]
+        pr = (2 * p1 - p2) & 0xFFFF
+        hi, lo = (vals[i] >> 8) & 255, vals[i] & 255
+        resid += bytes([(hi - (pr >> 8)) & 255, (lo - (pr & 255)) & 255])
+        out_so_far += bytes([hi, lo])
+    n = len(resid); planes = bytes(resid[0::2]) + bytes(resid[1::2])   # encoder side of Shuffle(width 2)
+    cmds += bytes([4, 1 | (1 << 2)]) + _varint(n); data += planes
+    cmds += bytes([3]) + _varint(16); data += bytes(shuf_src[0::4]) + bytes(shuf_src[1::4]) + bytes(shuf_src[2::4]) + bytes(shuf_src[3::4])
+    enc = _varint(total) + _varint(len(cmds)) + bytes(cmds) + bytes(data)
+    got = oracle.icc_unpredict(enc)
+    assert got == expected
+
+
+def test_icc_profile_travels_through_the_codestream(oracle):
+    import icc_util
+    icc = icc_util.make_matrix_icc(icc_util.P3_PRIMS, gamma=2.2)
+    img = oracle.synthetic_image(96, 64, seed=9)
+    d = oracle.decode(oracle.encode(img, lossless=True, icc=icc))
+    assert d.icc == icc and d.known_profile == -1 and np.array_equal(d.pixels, img)
