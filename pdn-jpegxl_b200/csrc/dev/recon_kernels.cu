@@ -90,39 +90,54 @@ __device__ constexpr float kCos8[64] = {1.000000000e+00f, 1.000000000e+00f, 1.00
 __global__ void __launch_bounds__(256) k_reconstruct_dct8(const __grid_constant__ DFrame f) {
   const int g = blockIdx.x >> 2, quarter = blockIdx.x & 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = lane >> 3, r = lane & 7;
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
-  __shared__ float s_dq[3 * 64]; __shared__ float s_t[8][4 * 72];
+  __shared__ float s_dq[3 * 64]; __shared__ float s_t[8][3][4 * 72];   // per warp: [channel][block][72]: two __syncwarp per iteration instead of six
   if (tid < 192) s_dq[tid] = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[0]))[tid];
   __syncthreads();
   const int by = quarter * 8 + warp; if (by >= h) return;
-  const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; float* st = s_t[warp];
+  const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536;
   const size_t tile_row = size_t((cy0 + by) >> 3) * f.xt;
+  // Software pipeline: everything iteration it+1 reads from global memory (3 x 16 B of coefficients, the cell's strategy / multiplier,
+  // the tile's CfL factors, the LF samples) is requested before iteration it is transformed, so a lane keeps ~60 B in flight instead
+  // of waiting for one dependent load at a time (ncu r01: long-scoreboard stall 6.5 per issue, 29 % of the HBM roofline).
+  struct Pre { int4 raw[3]; float lf[3]; int acs, hf, tx, tb; };
+  auto fetch = [&](int it, Pre& p) {
+    const int bx = it * 4 + b; p.raw[0] = p.raw[1] = p.raw[2] = make_int4(0, 0, 0, 0); p.lf[0] = p.lf[1] = p.lf[2] = 0.f; p.acs = 0; p.hf = 0; p.tx = 0; p.tb = 0;
+    if (bx < w) {
+      const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx, tile = tile_row + ((cx0 + bx) >> 3); const int16_t* cp = coef + (by * 32 + bx) * 64 + r * 8;
+      p.raw[0] = __ldcs(reinterpret_cast<const int4*>(cp)); p.raw[1] = __ldcs(reinterpret_cast<const int4*>(cp + 65536)); p.raw[2] = __ldcs(reinterpret_cast<const int4*>(cp + 2 * 65536));
+      p.acs = f.acs[o]; p.hf = f.hf_mul_m1[o]; p.tx = f.ytox[tile]; p.tb = f.ytob[tile];
+      if (r == 0) { p.lf[0] = f.lf_src[o]; p.lf[1] = f.lf_src[lfplane + o]; p.lf[2] = f.lf_src[2 * lfplane + o]; }
+    }
+  };
+  Pre cur; fetch(0, cur);
 #pragma unroll 1
   for (int it = 0; it < 8; it++) {
-    const int bx = it * 4 + b; const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const bool valid = bx < w && f.acs[o] == 0x80;   // strategy 0 (DCT8), first (only) cell
-    float scale = 0.f, kx = 0.f, kb = 0.f;
-    if (valid) { scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = tile_row + ((cx0 + bx) >> 3); kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor; kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor; }
-    float y8[8];
+    Pre nxt; if (it + 1 < 8) fetch(it + 1, nxt); else nxt = cur;
+    const int bx = it * 4 + b; const bool valid = bx < w && cur.acs == 0x80;   // strategy 0 (DCT8), first (only) cell
+    const float scale = f.inv_gs / float(cur.hf + 1), kx = f.base_x + float(cur.tx) * f.inv_color_factor, kb = f.base_b + float(cur.tb) * f.inv_color_factor;
+    float y8[8]; float (*st)[4 * 72] = s_t[warp];
 #pragma unroll
-    for (int ci = 0; ci < 3; ci++) {
+    for (int ci = 0; ci < 3; ci++) {   // phase A: dequantise + CfL, transform along the storage row, park T[hf = r][y] in shared memory
       const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; float v[8];
-      int4 raw = make_int4(0, 0, 0, 0); if (valid) raw = *reinterpret_cast<const int4*>(coef + c * 65536 + (by * 32 + bx) * 64 + r * 8);
+      const int4 raw = valid ? cur.raw[c] : make_int4(0, 0, 0, 0);
       const int q[8] = {int(short(raw.x & 0xffff)), raw.x >> 16, int(short(raw.y & 0xffff)), raw.y >> 16, int(short(raw.z & 0xffff)), raw.z >> 16, int(short(raw.w & 0xffff)), raw.w >> 16};
       const float mulc = c == 1 ? scale : c == 0 ? scale * f.xm : scale * f.bm, kc = c == 0 ? kx : kb, b1 = f.quant_bias[c], b3 = f.quant_bias[3];
 #pragma unroll
       for (int j = 0; j < 8; j++) { float a = AdjustQuantBiasDev(q[j], b1, b3) * s_dq[c * 64 + r * 8 + j] * mulc; if (c == 1) y8[j] = a; else a += kc * y8[j]; v[j] = a; }
-      if (valid && r == 0) v[0] = f.lf_src[c * lfplane + o];   // LLF of an 8x8 block is the LF sample itself
-      // storage row r holds S[hf = r][vf = 0..7]: transform along vf -> T[hf = r][y]
+      if (valid && r == 0) v[0] = cur.lf[c];   // LLF of an 8x8 block is the LF sample itself
       float t[8];
 #pragma unroll
       for (int y = 0; y < 8; y++) { float a = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) a = fmaf(v[j], kCos8[j * 8 + y], a); t[y] = a; }
-      __syncwarp();
-      *reinterpret_cast<float4*>(st + b * 72 + r * 8) = make_float4(t[0], t[1], t[2], t[3]); *reinterpret_cast<float4*>(st + b * 72 + r * 8 + 4) = make_float4(t[4], t[5], t[6], t[7]);
-      __syncwarp();
+      *reinterpret_cast<float4*>(st[c] + b * 72 + r * 8) = make_float4(t[0], t[1], t[2], t[3]); *reinterpret_cast<float4*>(st[c] + b * 72 + r * 8 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 3; c++) {   // phase B: lane (b, y = r) gathers T[hf][y], transforms along hf, writes one 32-byte pixel row segment
       float u[8];
 #pragma unroll
-      for (int hf = 0; hf < 8; hf++) u[hf] = st[b * 72 + hf * 8 + r];   // lane (b, y = r) gathers T[hf][y]
+      for (int hf = 0; hf < 8; hf++) u[hf] = st[c][b * 72 + hf * 8 + r];
       float px[8];
 #pragma unroll
       for (int x = 0; x < 8; x++) { float a = 0.f;
@@ -130,6 +145,8 @@ __global__ void __launch_bounds__(256) k_reconstruct_dct8(const __grid_constant_
         for (int hf = 0; hf < 8; hf++) a = fmaf(u[hf], kCos8[hf * 8 + x], a); px[x] = a; }
       if (valid) { float* out = f.xyb + c * plane + (size_t(cy0 + by) * 8 + r) * f.xpad + size_t(cx0 + bx) * 8; *reinterpret_cast<float4*>(out) = make_float4(px[0], px[1], px[2], px[3]); *reinterpret_cast<float4*>(out + 4) = make_float4(px[4], px[5], px[6], px[7]); }
     }
+    __syncwarp();
+    cur = nxt;
   }
 }
 
