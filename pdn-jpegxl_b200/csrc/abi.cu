@@ -144,12 +144,14 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
   try {
     std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return DecoderStatus_DecodeError; }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
-    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 256)); int cur_dev = 0; cudaGetDevice(&cur_dev);
+    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 256)); int cur_dev = 0; cudaGetDevice(&cur_dev);   // maxInFlight counts streams (bundles) in flight
     // streams are created once per device and thread and reused by later batches (stream creation is not free)
     static thread_local std::map<int, std::vector<cudaStream_t>> stream_cache; std::vector<cudaStream_t>& all_streams = stream_cache[cur_dev];
     while (int(all_streams.size()) < nstreams + 1) { cudaStream_t s = nullptr; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaStreamCreate failed"); return DecoderStatus_DecodeError; } all_streams.push_back(s); }
     cudaStream_t copy_stream = all_streams[0]; std::vector<cudaStream_t> streams(all_streams.begin() + 1, all_streams.begin() + 1 + nstreams); void* pin = nullptr; size_t pin_bytes = 0;
     const int batch_lanes = (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
+    static const int env_bundle = getenv("JXLB200_BUNDLE") ? atoi(getenv("JXLB200_BUNDLE")) : 0;
+    const int bundle_size = std::max(1, std::min(env_bundle > 0 ? env_bundle : ((count >= 64 && nstreams >= 32) ? 2 : 1), kMaxBundle));   // images per stream / per entropy launch
     struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; cudaStream_t stream = nullptr; };
     std::vector<size_t> in_off(count + 1, 0); const uint8_t* host_in = nullptr;
     // Device-resident inputs: the headers are parsed on the host, so every file comes back once through one pinned buffer. The copies
@@ -167,33 +169,47 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
     const bool trace = getenv("JXLB200_TRACE") != nullptr; double acc_t[5] = {0, 0, 0, 0, 0}; double t_enq = 0, t_ret = 0, t_idle = 0; auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     // Three-phase pipeline per image (LF entropy | AC entropy | reconstruction + render): a phase is enqueued only once the image's
     // stream has drained, so a kernel waiting on a 40 ms predecessor never sits at the head of a hardware queue shared with other
-    // streams (there are 32 queues, and up to 256 images in flight). q1/q2/q3 hold the images whose phase 1/2/3 is running.
-    std::deque<std::unique_ptr<InFlight>> q1, q2, q3; std::vector<cudaStream_t> free_streams(streams.rbegin(), streams.rend()); int next = 0, done = 0;
+    // streams (there are 32 queues). Images travel in bundles of `bundle_size` that share a stream and whose LF / AC entropy kernels
+    // are one multi-image launch each: the device holds at most 128 resident grids, and an image keeps one for ~70 ms.
+    // q1/q2/q3 hold the bundles whose phase 1/2/3 is running.
+    struct Bundle { std::vector<std::unique_ptr<InFlight>> items; cudaStream_t stream = nullptr; };
+    std::deque<std::unique_ptr<Bundle>> q1, q2, q3; std::vector<cudaStream_t> free_streams(streams.rbegin(), streams.rend()); int next = 0, done = 0;
     auto finish = [&](InFlight& f) {   // records the status of a finished or failed image
       DecoderStatus st = DecoderStatus(f.res.status);
       if (st == DecoderStatus_Ok) { if (f.res.pixel_bytes > outputBytes[f.idx]) st = DecoderStatus_InvalidParameter; else if (!f.direct) memcpy(outputs[f.idx], f.res.pixels, f.res.pixel_bytes); }
       else if (first == DecoderStatus_Ok) SetErrorMessage(errorInfo, f.res.message);
       if (trace) { const StageTimes& t = f.res.times; acc_t[0] += t.lf; acc_t[1] += t.ac; acc_t[2] += t.recon; acc_t[3] += t.filters + t.output; acc_t[4] += t.total; }
       if (statuses) statuses[f.idx] = st; if (st != DecoderStatus_Ok && first == DecoderStatus_Ok) first = st;
-      f.job.reset(); f.res.job.reset(); free_streams.push_back(f.stream); done++;
+      f.job.reset(); f.res.job.reset(); done++;
     };
-    auto advance = [&]() {   // moves images whose current phase has drained to the next one (polling: a blocking wait on one stream would stall all others)
-      bool progressed = false; const size_t kWindow = 24;   // images finish roughly in order; look a little past the front of each queue
-      for (size_t k = 0; k < std::min(kWindow, q3.size());) { if (!DecodeStreamIdle(q3[k]->job)) { k++; continue; } InFlight& f = *q3[k]; DecodeFinish(f.job, &f.res); finish(f); q3.erase(q3.begin() + k); progressed = true; }
-      for (size_t k = 0; k < std::min(kWindow, q2.size());) { if (!DecodeStreamIdle(q2[k]->job)) { k++; continue; } std::unique_ptr<InFlight> f = std::move(q2[k]); q2.erase(q2.begin() + k); progressed = true; if (DecodeEnqueuePhase(f->job, 3, &f->res)) q3.push_back(std::move(f)); else finish(*f); }
-      for (size_t k = 0; k < std::min(kWindow, q1.size());) { if (!DecodeStreamIdle(q1[k]->job)) { k++; continue; } std::unique_ptr<InFlight> f = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true; if (DecodeEnqueuePhase(f->job, 2, &f->res)) q2.push_back(std::move(f)); else finish(*f); }
+    auto idle = [](const Bundle& b) { return cudaStreamQuery(b.stream) != cudaErrorNotReady; };
+    auto jobs_of = [](Bundle& b) { std::vector<std::shared_ptr<DecodeJob>> v; for (auto& it : b.items) v.push_back(it->job); return v; };
+    auto next_phase = [&](Bundle& b, int phase) {   // enqueue `phase` for every image of the bundle; images that fail are finished and dropped
+      for (size_t k = 0; k < b.items.size();) { InFlight& f = *b.items[k]; if (DecodeEnqueuePhase(f.job, phase, &f.res)) k++; else { finish(f); b.items.erase(b.items.begin() + k); } }
+      if (phase == 2) DecodeBundleLaunch(jobs_of(b), 2);
+    };
+    auto advance = [&]() {   // moves bundles whose current phase has drained to the next one (polling: a blocking wait on one stream would stall all others)
+      bool progressed = false; const size_t kWindow = 24;   // bundles finish roughly in order; look a little past the front of each queue
+      for (size_t k = 0; k < std::min(kWindow, q3.size());) { if (!idle(*q3[k])) { k++; continue; } Bundle& b = *q3[k]; for (auto& f : b.items) { DecodeFinish(f->job, &f->res); finish(*f); } free_streams.push_back(b.stream); q3.erase(q3.begin() + k); progressed = true; }
+      for (size_t k = 0; k < std::min(kWindow, q2.size());) { if (!idle(*q2[k])) { k++; continue; } std::unique_ptr<Bundle> b = std::move(q2[k]); q2.erase(q2.begin() + k); progressed = true; next_phase(*b, 3); if (b->items.empty()) free_streams.push_back(b->stream); else q3.push_back(std::move(b)); }
+      for (size_t k = 0; k < std::min(kWindow, q1.size());) { if (!idle(*q1[k])) { k++; continue; } std::unique_ptr<Bundle> b = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true; next_phase(*b, 2); if (b->items.empty()) free_streams.push_back(b->stream); else q2.push_back(std::move(b)); }
       return progressed;
     };
     while (done < count) {
       double t0 = now(); bool progressed = advance(); t_ret += now() - t0;
       if (next < count && !free_streams.empty()) {
-        t0 = now(); const int i = next++;
-        std::unique_ptr<InFlight> f(new InFlight); f->idx = i; f->stream = free_streams.back(); free_streams.pop_back();
-        DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i]; req.out_capacity = outputBytes[i]; req.ac_lanes = batch_lanes;
-        if (hostInputs) req.data = datas[i]; else { cudaEventSynchronize(in_ready[i]); req.data = host_in + in_off[i]; req.device_input = datas[i]; }
-        if (!hostOutputs) { req.out_device = outputs[i]; f->direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f->direct = true; }
-        f->job = DecodeEnqueue(req, f->stream, &f->res, true); t_enq += now() - t0;
-        if (f->job) q1.push_back(std::move(f)); else finish(*f);
+        t0 = now(); std::unique_ptr<Bundle> b(new Bundle); b->stream = free_streams.back(); free_streams.pop_back();
+        for (int k = 0; k < bundle_size && next < count; k++) {
+          const int i = next++; std::unique_ptr<InFlight> f(new InFlight); f->idx = i; f->stream = b->stream;
+          DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i]; req.out_capacity = outputBytes[i]; req.ac_lanes = batch_lanes;
+          if (hostInputs) req.data = datas[i]; else { cudaEventSynchronize(in_ready[i]); req.data = host_in + in_off[i]; req.device_input = datas[i]; }
+          if (!hostOutputs) { req.out_device = outputs[i]; f->direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f->direct = true; }
+          f->job = DecodeEnqueue(req, b->stream, &f->res, true, bundle_size > 1);
+          if (f->job) b->items.push_back(std::move(f)); else finish(*f);
+        }
+        if (bundle_size > 1) DecodeBundleLaunch(jobs_of(*b), 1);
+        t_enq += now() - t0;
+        if (b->items.empty()) free_streams.push_back(b->stream); else q1.push_back(std::move(b));
       } else if (!progressed) { t0 = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); t_idle += now() - t0; }
     }
     if (trace) DumpHostTrace();

@@ -206,6 +206,7 @@ class DecodeJob {
   Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
   DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend;
   std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false;
+  bool defer_entropy = false, lf_pending = false, ac_pending = false;   // bundle mode: the LF / AC entropy launch is left to DecodeBundleLaunch*
   cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
   bool has_tree = false; Tree tree; Code tree_code; GroupHeader gheader; size_t global_decoded = 0; uint64_t global_data_bitpos = 0; bool global_has_data = false;
   std::vector<Code> ac_codes; uint32_t hf_blob_mark = 0; uint32_t frame_uploads = 0; uint8_t* ext_out_device = nullptr; uint8_t* ext_out_pinned = nullptr;
@@ -409,7 +410,7 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
   // global Modular stream
   if (global_has_data) { LaunchModularGlobal(d, h, after_lfglobal, uint32_t(global_decoded), stream); CountLaunch(); }
   else if (single) { uint64_t* slot = reinterpret_cast<uint64_t*>(h_misc.as<uint8_t>() + 2 * sizeof(DFrame)); slot[0] = after_lfglobal; CUDA_OK(cudaMemcpyAsync(h.end_bitpos, slot, 8, cudaMemcpyHostToDevice, stream)); }
-  if (vardct) { LaunchLfGroups(d, h, stream); CountLaunch(); }
+  if (vardct) { if (defer_entropy && !single) lf_pending = true; else { LaunchLfGroups(d, h, stream); CountLaunch(); } }
   else if (single) { /* Modular frame, single section: LF group and HfGlobal parts are empty; groups continue where the global stream ended */ CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, h.end_bitpos, 8, cudaMemcpyDeviceToDevice, stream)); }
   if (single && vardct) {   // HfGlobal follows the LF group in the same bit stream: need its end position on the host
     uint64_t pos[3] = {0, 0, 0}; CUDA_OK(cudaMemcpyAsync(h_err.p, d_err.p, 64, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
@@ -427,7 +428,8 @@ void DecodeJob::RunAc() {
   if (timed) cudaEventRecord(ev[1], stream);
   if (vardct) { bool smooth = h.lf_src == h.lf_tmp; LaunchLfDequant(d, h, smooth, stream); CountLaunch(smooth ? 2 : 1); }
   if (vardct) CUDA_OK(cudaMemsetAsync(h.coeffs, 0, size_t(h.num_groups) * 3 * 65536 * 2, stream));
-  for (uint32_t p = 0; p < h.num_passes; p++) CountLaunch(LaunchAcGroups(d, h, int(p), ac_lanes, stream));
+  if (defer_entropy && vardct && h.num_passes == 1 && h.ac_fast && !(h.num_mod_channels > h.first_group_channel)) ac_pending = true;
+  else for (uint32_t p = 0; p < h.num_passes; p++) CountLaunch(LaunchAcGroups(d, h, int(p), ac_lanes, stream));
   if (timed) cudaEventRecord(ev[2], stream);
   g_trace.t[6] += NowMs() - tt;
 }
@@ -458,7 +460,7 @@ void DecodeJob::RunRender() {
   g_trace.t[6] += NowMs() - tt; g_trace.n++;
 }
 
-std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res, bool lf_phase_only) {
+std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res, bool lf_phase_only, bool defer_entropy) {
   std::shared_ptr<DecodeJob> job;
   if (!req.data) { res->status = Status::NullParameter; return job; }
   try {
@@ -466,7 +468,7 @@ std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t 
     job = std::make_shared<DecodeJob>(); job->stream = stream; double t0 = NowMs();
     { static const bool batch_times = getenv("JXLB200_TRACE") != nullptr && atoi(getenv("JXLB200_TRACE")) >= 2; if (batch_times) { job->timed = true; for (int i = 0; i < 7; i++) cudaEventCreate(&job->ev[i]); } }
     res->status = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res->message); if (res->status != Status::Ok) { job.reset(); return job; }
-    g_trace.t[0] += NowMs() - t0; t0 = NowMs(); job->phased = lf_phase_only; job->Setup(req); g_trace.t[1] += NowMs() - t0; if (lf_phase_only) job->RunLf(req); else job->Run(req); res->info = job->info;
+    g_trace.t[0] += NowMs() - t0; t0 = NowMs(); job->phased = lf_phase_only; job->defer_entropy = defer_entropy && lf_phase_only; job->Setup(req); g_trace.t[1] += NowMs() - t0; if (lf_phase_only) job->RunLf(req); else job->Run(req); res->info = job->info;
   } catch (const std::bad_alloc&) { res->status = Status::OutOfMemory; job.reset(); }
   catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); if (job) res->info = job->info; job.reset(); }
   return job;
@@ -480,6 +482,24 @@ bool DecodeEnqueuePhase(std::shared_ptr<DecodeJob>& job, int phase, DecodeResult
   catch (const std::bad_alloc&) { res->status = Status::OutOfMemory; }
   catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); res->info = job->info; }
   cudaStreamSynchronize(job->stream); job.reset(); return false;
+}
+// Bundle mode: the jobs share one stream and were enqueued with defer_entropy; their pending LF (phase 1) or AC (phase 2) entropy kernels
+// go out as multi-image launches of up to kMaxBundle frames each.
+void DecodeBundleLaunch(const std::vector<std::shared_ptr<DecodeJob>>& jobs, int phase) {
+  for (int kind = 0; kind < 2; kind++) {   // LF: narrow / wide Modular kernels; AC: one kind
+    DFrameSet set; set.n = 0; cudaStream_t st = nullptr; int lanes = 1;
+    auto flush = [&]() { if (!set.n) return; if (phase == 1) LaunchLfGroupsMulti(set, kind == 0, st); else LaunchAcGroupsMulti(set, lanes, st); CountLaunch(); set.n = 0; };
+    for (const auto& j : jobs) {
+      if (!j) continue;
+      if (phase == 1) { if (!j->lf_pending || LfNarrow(j->h) != (kind == 0)) continue; }
+      else { if (kind == 1 || !j->ac_pending) continue; if (set.n && j->ac_lanes != lanes) flush(); lanes = j->ac_lanes; }
+      if (set.n == 0) { set.first[0] = 0; set.cta_offset = phase == 1 ? j->h.lf_cta_offset : j->h.ac_cta_offset; st = j->stream; }
+      set.f[set.n] = j->h; set.first[set.n + 1] = set.first[set.n] + (phase == 1 ? j->h.num_lf_groups : uint32_t(AcCtas(j->h, j->ac_lanes))); set.n++;
+      if (phase == 1) j->lf_pending = false; else j->ac_pending = false;
+      if (set.n == uint32_t(kMaxBundle)) flush();
+    }
+    flush();
+  }
 }
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job) { if (job) cudaStreamSynchronize(job->stream); }
 bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job) { return !job || cudaStreamQuery(job->stream) != cudaErrorNotReady; }

@@ -41,11 +41,8 @@ __device__ void StageModDecoder(ModDecoder& md, const DFrame& f, uint8_t* dsm, u
 }
 
 template <bool kNarrow>
-__global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame f) {
-  // The first-wave CTA->SM mapping is deterministic, so concurrent images would stack their few LF CTAs on the same SMs:
-  // each launch prepends `lf_cta_offset` empty CTAs to land on different SMs.
-  if (blockIdx.x < f.lf_cta_offset) return;
-  const int g = int(blockIdx.x - f.lf_cta_offset), lane = threadIdx.x;
+__device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
+  const int lane = threadIdx.x;
   const int gx = g % int(f.xlfgroups), gy = g / int(f.xlfgroups), cx0 = gx * 256, cy0 = gy * 256;
   const int w = min(256, int(f.xb) - cx0), h = min(256, int(f.yb) - cy0), tw = (w + 7) / 8, th = (h + 7) / 8;
   int32_t* scratch = f.hfmeta_scratch + size_t(g) * kHfMetaScratchInts;
@@ -116,6 +113,21 @@ __global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame 
   }
 }
 
+// The first-wave CTA->SM mapping is deterministic, so concurrent images would stack their few LF CTAs on the same SMs:
+// each launch prepends `lf_cta_offset` empty CTAs to land on different SMs.
+template <bool kNarrow>
+__global__ void __launch_bounds__(32) k_lf_group(const __grid_constant__ DFrame f) {
+  if (blockIdx.x < f.lf_cta_offset) return;
+  LfGroupBody<kNarrow>(f, int(blockIdx.x - f.lf_cta_offset));
+}
+// Several images per launch (DFrameSet): the image is found from the CTA index.
+template <bool kNarrow>
+__global__ void __launch_bounds__(32) k_lf_group_multi(const __grid_constant__ DFrameSet s) {
+  if (blockIdx.x < s.cta_offset) return;
+  const uint32_t cta = blockIdx.x - s.cta_offset; uint32_t img = 0; while (img + 1 < s.n && cta >= s.first[img + 1]) img++;
+  LfGroupBody<kNarrow>(s.f[img], int(cta - s.first[img]));
+}
+
 // LF dequantisation + chroma-from-luma + block-context LF index (A.8 "Dequant", BlockCtxMap)
 __global__ void k_lf_dequant(const DFrame* fp) {
   const DFrame& f = *fp; size_t plane = size_t(f.xb) * f.yb; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= plane) return;
@@ -168,10 +180,9 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
 // kSmem: ANS code with every table staged in shared memory (the host checks sizes before choosing the instantiation).
 static const int kAcWarps = 4;
 template <bool kSmem>
-__global__ void __launch_bounds__(32 * kAcWarps, 4) k_ac_vardct(const __grid_constant__ DFrame f, int pass, int lanes) {
-  if (blockIdx.x < f.ac_cta_offset) return;   // spreads concurrent images over different SMs (see k_lf_group)
+__device__ __forceinline__ void AcVardctBody(const DFrame& f, const int pass, const int lanes, const int cta) {
   extern __shared__ __align__(16) uint8_t dsm[]; __shared__ uint8_t s_freq[64], s_numnz[64];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cta = int(blockIdx.x - f.ac_cta_offset);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   CodeView cv; cv.Bind(f.blob, f.ac_code[pass]);
   if (tid < 64) { s_freq[tid] = kFreqCtx[tid]; s_numnz[tid] = kNumNzCtx[tid]; }
   if (kSmem) { uint32_t used = 0; cv.Stage(dsm, f.ac_smem, used, tid, 32 * kAcWarps); }
@@ -239,6 +250,18 @@ __global__ void __launch_bounds__(32 * kAcWarps, 4) k_ac_vardct(const __grid_con
   SetError(f.err, err);
 }
 
+template <bool kSmem>
+__global__ void __launch_bounds__(32 * kAcWarps, 4) k_ac_vardct(const __grid_constant__ DFrame f, int pass, int lanes) {
+  if (blockIdx.x < f.ac_cta_offset) return;   // spreads concurrent images over different SMs (see k_lf_group)
+  AcVardctBody<kSmem>(f, pass, lanes, int(blockIdx.x - f.ac_cta_offset));
+}
+template <bool kSmem>
+__global__ void __launch_bounds__(32 * kAcWarps, 4) k_ac_vardct_multi(const __grid_constant__ DFrameSet s, int lanes) {   // pass 0 of single-pass frames
+  if (blockIdx.x < s.cta_offset) return;
+  const uint32_t cta = blockIdx.x - s.cta_offset; uint32_t img = 0; while (img + 1 < s.n && cta >= s.first[img + 1]) img++;
+  AcVardctBody<kSmem>(s.f[img], 0, lanes, int(cta - s.first[img]));
+}
+
 // Group-local Modular channels (alpha / extra channels of VarDCT frames, everything of Modular frames): warp w of a CTA owns
 // group blockIdx.x*kModGroupsPerCta + w, lane 0 walks the bit stream, and the warps share one staged copy of the tables.
 // In VarDCT frames the stream continues where the group's AC coefficients ended (ac_endpos, written by k_ac_vardct).
@@ -279,9 +302,21 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
 }
 
 static void EnsureSmemAttr() { static bool done[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (done[dev & 63]) return; done[dev & 63] = true;   // function attributes are per device
+  cudaFuncSetAttribute(k_lf_group_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   cudaFuncSetAttribute(k_lf_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
 void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (!h.num_lf_groups) return; const bool narrow = !h.uses_wp && !h.mod_wide;
   if (narrow) k_lf_group<true><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); else k_lf_group<false><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); }
+// Bundle launches (JxlB200DecodeBatch): the images of `set` share one stream; all must be VarDCT, multi-section, of the same kind
+// (narrow Modular path for LF; single pass + shared-memory ANS tables for AC) — the caller checks with BundleCompatible*.
+bool LfNarrow(const DFrame& h) { return !h.uses_wp && !h.mod_wide; }
+void LaunchLfGroupsMulti(const DFrameSet& set, bool narrow, cudaStream_t st) {
+  EnsureSmemAttr(); uint32_t smem = 0; for (uint32_t i = 0; i < set.n; i++) smem = std::max(smem, set.f[i].lf_smem); const unsigned grid = set.first[set.n] + set.cta_offset;
+  if (narrow) k_lf_group_multi<true><<<grid, 32, smem, st>>>(set); else k_lf_group_multi<false><<<grid, 32, smem, st>>>(set);
+}
+void LaunchAcGroupsMulti(const DFrameSet& set, int lanes, cudaStream_t st) {   // every frame: encoding 0, num_passes 1, ac_fast
+  EnsureSmemAttr(); uint32_t smem = 0; for (uint32_t i = 0; i < set.n; i++) smem = std::max(smem, set.f[i].ac_smem);
+  k_ac_vardct_multi<true><<<set.first[set.n] + set.cta_offset, 32 * kAcWarps, smem, st>>>(set, lanes);
+}
 void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st) {
   size_t plane = size_t(h.xb) * h.yb; unsigned blocks = unsigned((plane + 255) / 256); k_lf_dequant<<<blocks, 256, 0, st>>>(d); if (smooth) k_lf_smooth<<<blocks, 256, 0, st>>>(d);
 }

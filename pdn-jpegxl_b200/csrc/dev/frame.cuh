@@ -49,6 +49,11 @@ struct DFrame {
   const float* lf_src; const struct DTables* tables;
   int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos; uint64_t* ac_endpos; uint8_t* nz_scratch; uint32_t* host_flags; uint32_t* group_other;   // group_other[g]: number of varblocks in group g that are not plain DCT8
 };
+// A bundle of images decoded by one launch of an entropy kernel (batches): passed by value like DFrame (4 x 3.4 KB of the 32 KB
+// parameter space). CTA `first[i]` .. `first[i+1]-1` (after `cta_offset` empty CTAs) belong to image i. Raises the number of images
+// in flight past the 128-resident-grid limit of the device.
+static const int kMaxBundle = 4;
+struct DFrameSet { uint32_t n, cta_offset; uint32_t first[kMaxBundle + 1]; uint32_t pad; DFrame f[kMaxBundle]; };
 static const uint32_t kHfMetaScratchInts = 2 * 1024 + 2 * 65536 + 65536;
 
 // Offsets with the top bit set address the per-device static blob (default dequant tables, natural coefficient orders)

@@ -7,6 +7,9 @@ namespace jxlgpu {
 void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st);
 void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st);
 int AcCtas(const DFrame& h, int lanes);
+bool LfNarrow(const DFrame& h);
+void LaunchLfGroupsMulti(const DFrameSet& set, bool narrow, cudaStream_t st);
+void LaunchAcGroupsMulti(const DFrameSet& set, int lanes, cudaStream_t st);
 int LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, int lanes, cudaStream_t st);
 void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st);
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st);       // dequant + CfL + LLF + inverse transforms

@@ -47,7 +47,8 @@ DecodeResult ParseInfo(const uint8_t* data, size_t size);
 // Full decode on the GPU. Fails loudly (DecodeError with a message) when no CUDA device is usable: there is no CPU fallback.
 DecodeResult DecodeOnGpu(const DecodeRequest& req);
 // Asynchronous variant for batches: enqueue everything on `stream`, return without synchronising. Finish() waits and reads the error word.
-std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res, bool lf_phase_only = false);
+std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t stream, DecodeResult* res, bool lf_phase_only = false, bool defer_entropy = false);
+void DecodeBundleLaunch(const std::vector<std::shared_ptr<DecodeJob>>& jobs, int phase);   // phase 1: pending LF launches, 2: pending AC launches (jobs share one stream)
 bool DecodeEnqueuePhase(std::shared_ptr<DecodeJob>& job, int phase, DecodeResult* res);   // phase 2: AC entropy kernels, 3: reconstruction + render; false: job failed (res filled, job released)
 bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job);
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job);
