@@ -125,8 +125,10 @@ def test_golden_files(gpu, oracle):
 
 @pytest.mark.parametrize("kw,dtype,tol", [
     (dict(bits=16), np.uint16, 1.0 / 255),                                   # u16 output
-    (dict(bits=16, exp_bits=5), np.float16, 2e-3),                            # f16 output
-    (dict(bits=32, exp_bits=8), np.float32, 1e-4),                            # f32 output: <= 1e-4 relative (north_star)
+    (dict(bits=16, exp_bits=5), np.float16, 1e-3),                            # f16 output: one half-precision ulp (2^-10) — a rounding flip
+    (dict(bits=32, exp_bits=8), np.float32, 1e-4),                            # f32 output: <= 1e-4 relative (north_star); measured 1.1e-5
+    (dict(bits=32, exp_bits=8, primaries=9, tf=16, intensity_target=1000.0), np.float32, 5e-4),   # f32 PQ: the PQ curve (exponent 78.8) amplifies
+                                                                              # fp32 summation-order differences of the IDCT; measured 2.3e-4 relative, 1.4e-5 absolute
     (dict(bits=16, primaries=9, tf=16, intensity_target=1000.0), np.uint16, 1.0 / 255),   # Rec.2020 PQ HDR, gab + EPF
     (dict(bits=16, primaries=11), np.uint16, 1.0 / 255),                      # Display P3
     (dict(bits=32, exp_bits=8, tf=8), np.float32, 1e-4),                      # linear sRGB float
@@ -142,7 +144,7 @@ def test_hdr_and_high_bit_depth_outputs(gpu, oracle, kw, dtype, tol):
         assert int(np.abs(got.astype(np.int64) - ref.astype(np.int64)).max()) <= 257      # <= 1 LSB at 8-bit precision
     else:
         a, b = got.astype(np.float64), ref.astype(np.float64)
-        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.05)) <= tol * 20 if dtype == np.float16 else np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.05)) <= 2e-3
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3)) <= tol            # relative, with a floor of 1e-3 for samples near zero
 
 
 @pytest.mark.parametrize("orientation", [2, 3, 4, 5, 6, 7, 8])
