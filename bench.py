@@ -297,6 +297,12 @@ def main():
             line["roofline"] = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peak, "unit": "GB/s", "frac": d["frac"], "traffic": None,
                                 "peak_source": peak_src, "share_of_decode": d["ms"] / max(acc.get("total", 1e-9), 1e-9),
                                 "note": "dominant kernel of a single-image decode; entropy decode is a serial bit stream per section, so its HBM fraction is tiny by nature — ns/symbol is the relevant figure (DESIGN.md)"}
+        # DRAM traffic per launch from the one `ncu --set full` capture of these kernels at this frame size (profiles/r01_ncu_render.md)
+        if W * H == 4000 * 3000:
+            if "recon" in stages:
+                stages["recon"]["traffic"] = 74.7e6 + 90.1e6
+            if "filters" in stages and stage_bytes["filters"] == 15.0:
+                stages["filters"]["traffic"] = 144.9e6 + 36.1e6
         line["stage_rooflines"] = {k: v for k, v in stages.items() if k in ("recon", "filters", "output")}
         line["single_image_ms"] = acc
         try:
