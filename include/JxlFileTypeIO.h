@@ -93,6 +93,16 @@ JXLFT_API DecoderStatus JXLFT_CALL JxlB200LoadImageBgra(const uint8_t* data, siz
  * width, height, DecoderImageFormat, ImageChannelRepresentation, hasTransparency, numChannels, KnownColorProfile or -1, isContainer. */
 JXLFT_API DecoderStatus JXLFT_CALL JxlB200PeekInfo(const uint8_t* data, size_t dataSize, int32_t* info, ErrorInfo* errorInfo);
 
+/* Band decode (BASELINE config 5, SURVEY §8e "gigapixel"): one rank's share of a frame that is sharded by group rows. JxlB200BandLayout
+ * reports layout[4] = {width, height, group size in pixels (256 for VarDCT), number of group rows}; JxlB200DecodeBand decodes group rows
+ * [groupRowBegin, groupRowEnd) on device `device` (-1: current) and writes image rows [groupRowBegin*groupDim, min(groupRowEnd*groupDim,
+ * height)) to `out`, interleaved and tightly packed as LoadImage hands them to setLayerData (BGRA32 when bgra != 0); *rows receives the
+ * row count. No exchange between ranks: each reconstructs one extra group row on either side (the 7-pixel filter halo). The image must
+ * not carry an orientation other than identity. */
+JXLFT_API DecoderStatus JXLFT_CALL JxlB200BandLayout(const uint8_t* data, size_t dataSize, int32_t* layout, ErrorInfo* errorInfo);
+JXLFT_API DecoderStatus JXLFT_CALL JxlB200DecodeBand(int32_t device, const uint8_t* data, size_t dataSize, uint32_t groupRowBegin, uint32_t groupRowEnd,
+                                                      uint8_t* out, size_t outBytes, int32_t bgra, int32_t* rows, ErrorInfo* errorInfo);
+
 /* Batch decode (BASELINE config 3): `count` independent files, each decoded by the full single-image pipeline on its own
  * CUDA stream of device `device`; outputs[i] (host memory, outputBytes[i] bytes, interleaved as LoadImage delivers, or
  * BGRA32 when bgra != 0) are filled on return. statuses[i] receives a DecoderStatus per file. Returns the first non-Ok

@@ -87,6 +87,10 @@ _lib.SaveImage.restype = C.c_int32
 _lib.JxlB200LoadImageBgra.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
 _lib.JxlB200LoadImageBgra.restype = C.c_int32
 _lib.JxlB200PeekInfo.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200BandLayout.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200BandLayout.restype = C.c_int32
+_lib.JxlB200DecodeBand.argtypes = [C.c_int32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200DecodeBand.restype = C.c_int32
 _lib.JxlB200PeekInfo.restype = C.c_int32
 _lib.JxlB200DecodeBatch.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
@@ -465,6 +469,45 @@ def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, widt
     data = C.string_at(out, n.value)
     _lib.JxlB200Free(out)
     return data
+
+
+def band_layout(data):
+    """(width, height, group size in pixels, number of group rows) of the first frame — what a caller shards over."""
+    b = bytes(data)
+    lay = (C.c_int32 * 4)()
+    ei = ErrorInfo()
+    st = _lib.JxlB200BandLayout(b, len(b), lay, C.byref(ei))
+    if st != 0:
+        raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
+    return tuple(lay)
+
+
+def band_partition(num_group_rows, world):
+    """Contiguous group-row ranges per rank: rank r decodes rows [begin, end); ranks beyond the row count get (0, 0)."""
+    base, extra = divmod(num_group_rows, world)
+    out, at = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((at, at + n) if n else (0, 0))
+        at += n
+    return out
+
+
+def decode_band(data, group_row_begin, group_row_end, bgra=False, device=-1):
+    """Decodes group rows [begin, end) of the frame on `device`; returns the H_band x W x C array of those image rows."""
+    b = bytes(data)
+    info = peek_info(b)
+    w, _, gdim, _ = band_layout(b)
+    nch = 4 if bgra else info["num_channels"] + (1 if info["format"] == "Cmyk" else 0)
+    dtype = np.uint8 if bgra else _DTYPES[info["representation"]]
+    rows_cap = (group_row_end - group_row_begin) * gdim
+    out = np.empty((rows_cap, w, nch), dtype)
+    rows = C.c_int32()
+    ei = ErrorInfo()
+    st = _lib.JxlB200DecodeBand(device, b, len(b), group_row_begin, group_row_end, out.ctypes.data, out.nbytes, int(bgra), C.byref(rows), C.byref(ei))
+    if st != 0:
+        raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
+    return out[: rows.value]
 
 
 def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None, raise_on_error=True):

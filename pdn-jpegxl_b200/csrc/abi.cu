@@ -137,6 +137,29 @@ DecoderStatus JxlB200LoadImageBgra(const uint8_t* data, size_t dataSize, uint8_t
   return DecoderStatus_Ok;
 }
 
+// Band decode: one rank's share of a frame sharded by group rows (SURVEY §8e "gigapixel": AC-group row ranges per GPU, no collective —
+// each rank reconstructs one extra group row on either side instead of exchanging a halo). layout4 = {width, height, group size in
+// pixels, number of group rows}. Rows [groupRowBegin*groupDim, min(groupRowEnd*groupDim, height)) are written to `out`, interleaved
+// and tightly packed exactly as LoadImage would hand them to setLayerData.
+DecoderStatus JxlB200BandLayout(const uint8_t* data, size_t dataSize, int32_t* layout4, ErrorInfo* errorInfo) {
+  if (!data || !layout4) return DecoderStatus_NullParameter;
+  ParsedInfo pi; std::string msg; Status st = DecodeBandLayout(data, dataSize, &pi, &msg);
+  if (st != Status::Ok) { SetErrorMessage(errorInfo, msg); return DecoderStatus(st); }
+  layout4[0] = int32_t(pi.width); layout4[1] = int32_t(pi.height); layout4[2] = int32_t(pi.group_dim); layout4[3] = int32_t(pi.num_group_rows); return DecoderStatus_Ok;
+}
+DecoderStatus JxlB200DecodeBand(int32_t device, const uint8_t* data, size_t dataSize, uint32_t groupRowBegin, uint32_t groupRowEnd, uint8_t* out, size_t outBytes, int32_t bgra, int32_t* rows, ErrorInfo* errorInfo) {
+  if (!data || !out) return DecoderStatus_NullParameter;
+  try {
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
+    if (groupRowBegin >= groupRowEnd) { SetErrorMessage(errorInfo, "band decode: empty group-row range"); return DecoderStatus_InvalidParameter; }
+    DecodeRequest req; req.data = data; req.size = dataSize; req.bgra = bgra != 0; req.band_begin = groupRowBegin; req.band_end = groupRowEnd; DecodeResult res = DecodeOnGpu(req); g_last_times = res.times;
+    if (res.status != Status::Ok) { SetErrorMessage(errorInfo, res.message); return DecoderStatus(res.status); }
+    if (outBytes < res.pixel_bytes) { SetErrorMessage(errorInfo, "band buffer too small"); return DecoderStatus_InvalidParameter; }
+    memcpy(out, res.pixels, res.pixel_bytes); if (rows) *rows = int32_t(res.out_height);
+  } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
+  return DecoderStatus_Ok;
+}
+
 DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes, uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
                                  int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, DecoderStatus* statuses, ErrorInfo* errorInfo) {
   if (!datas || !dataSizes || !outputs || !outputBytes || count < 0) return DecoderStatus_NullParameter;

@@ -305,6 +305,12 @@ void DecodeJob::Setup(const DecodeRequest& req) {
   { int l = req.ac_lanes; static const int env_lanes = getenv("JXLB200_AC_LANES") ? atoi(getenv("JXLB200_AC_LANES")) : 0; if (env_lanes > 0) l = env_lanes; ac_lanes = 1; while (ac_lanes * 2 <= l && ac_lanes < 32) ac_lanes *= 2; }
   h.xsize = fh.xsize; h.ysize = fh.ysize; h.xb = fh.xblocks; h.yb = fh.yblocks; h.xpad = h.xb * 8; h.ypad = h.yb * 8; h.xt = (h.xb + 7) / 8; h.yt = (h.yb + 7) / 8; h.xgroups = fh.xgroups; h.ygroups = fh.ygroups; h.num_groups = fh.num_groups;
   h.xlfgroups = fh.xlfgroups; h.ylfgroups = fh.ylfgroups; h.num_lf_groups = fh.num_lf_groups; h.group_dim = fh.group_dim; h.num_passes = fh.passes.num_passes; h.encoding = fh.encoding; h.flags = uint32_t(fh.flags);
+  info.group_dim = h.group_dim; info.num_group_rows = h.ygroups;
+  if (req.band_begin || req.band_end) {
+    JXLG_CHECK(req.band_begin < req.band_end && req.band_end <= h.ygroups, "band decode: group-row range out of bounds"); JXLG_CHECK(m.orientation == 1, "band decode needs identity orientation");
+    h.band_on = 1; h.out_g0 = req.band_begin; h.out_g1 = req.band_end; h.comp_g0 = req.band_begin ? req.band_begin - 1 : 0; h.comp_g1 = std::min(h.ygroups, req.band_end + 1);
+    h.out_y0 = h.out_g0 * h.group_dim; h.out_y1 = std::min(h.ysize, h.out_g1 * h.group_dim);
+  }
   for (uint32_t p = 0; p < h.num_passes; p++) { h.pass_shift[p] = p + 1 < h.num_passes ? fh.passes.shift[p] : 0;
     int min_shift = 3, max_shift = 2; for (uint32_t i = 0;; i++) { for (uint32_t j = 0; j < fh.passes.num_ds; j++) if (i == fh.passes.last_pass[j]) min_shift = FloorLog2(fh.passes.downsample[j]); if (i + 1 == h.num_passes) min_shift = 0; if (i == p) break; max_shift = min_shift - 1; }
     h.pass_min_shift[p] = min_shift; h.pass_max_shift[p] = max_shift; }
@@ -357,7 +363,7 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   uint64_t mod_ints = 0; for (uint32_t i = 0; i < h.num_mod_channels; i++) mod_ints += uint64_t(h.mod_ch[i].w) * h.mod_ch[i].h; if (mod_ints) d_mod.Alloc(mod_ints * 4);
   if (h.uses_wp) d_wp.Alloc((size_t(h.num_lf_groups) + h.num_groups + 1) * 5 * 2 * (kMaxWpWidth + 2) * 4); else d_wp.Alloc(16);
   const DOutput& o = h.out; size_t bps = o.sample_type == 0 ? 1 : o.sample_type == 3 ? 4 : 2; size_t chans = bgra ? 4 : (o.num_channels + (o.black_plane >= 0 ? 1 : 0)); if (bgra) bps = 1;
-  out_bytes = size_t(o.out_w) * o.out_h * chans * bps;
+  out_bytes = size_t(o.out_w) * (h.band_on ? h.out_y1 - h.out_y0 : o.out_h) * chans * bps;
   if (req.out_device || req.out_pinned) JXLG_CHECK(req.out_capacity >= out_bytes, "output buffer too small");
   if (!req.out_device) d_out.Alloc(out_bytes); if (!device_output && !req.out_pinned) h_out.Alloc(out_bytes, true);
   ext_out_device = req.out_device; ext_out_pinned = req.out_pinned;
@@ -501,6 +507,13 @@ void DecodeBundleLaunch(const std::vector<std::shared_ptr<DecodeJob>>& jobs, int
     flush();
   }
 }
+// Band layout of the first frame (host-only parse): group size in pixels and the number of group rows a caller can shard over.
+Status DecodeBandLayout(const uint8_t* data, size_t size, ParsedInfo* info, std::string* message) {
+  if (!data) return Status::NullParameter;
+  try { DecodeJob job; Status st = ParseHeadersInto(data, size, &job.hd, &job.info, message); if (st != Status::Ok) return st; DecodeRequest req; req.data = data; req.size = size; job.Setup(req); *info = job.info; return Status::Ok; }
+  catch (const std::bad_alloc&) { return Status::OutOfMemory; }
+  catch (const std::exception& e) { if (message) *message = e.what(); return Status::DecodeError; }
+}
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job) { if (job) cudaStreamSynchronize(job->stream); }
 bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job) { return !job || cudaStreamQuery(job->stream) != cudaErrorNotReady; }
 
@@ -510,7 +523,7 @@ void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res) {
   if (e != cudaSuccess) { res->status = Status::DecodeError; res->message = std::string("CUDA: ") + cudaGetErrorString(e); return; }
   uint32_t de = *job->h_err.as<uint32_t>();
   if (de) { res->status = Status::DecodeError; res->message = DevErrorText(de); return; }
-  res->info = job->info; res->pixels = job->device_output ? job->h.out_px : (job->ext_out_pinned ? job->ext_out_pinned : job->h_out.as<uint8_t>()); res->pixel_bytes = job->out_bytes; res->out_width = job->h.out.out_w; res->out_height = job->h.out.out_h; res->job = job;
+  res->info = job->info; res->pixels = job->device_output ? job->h.out_px : (job->ext_out_pinned ? job->ext_out_pinned : job->h_out.as<uint8_t>()); res->pixel_bytes = job->out_bytes; res->out_width = job->h.out.out_w; res->out_height = job->h.band_on ? job->h.out_y1 - job->h.out_y0 : job->h.out.out_h; res->job = job;
   if (job->timed) { auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, job->ev[a], job->ev[b]); return t; };
     res->times.lf = ms(0, 1); res->times.ac = ms(1, 2); res->times.recon = ms(2, 3); res->times.filters = ms(3, 4); res->times.output = ms(4, 5); res->times.d2h = ms(5, 6); res->times.total = ms(0, 6); }
 }

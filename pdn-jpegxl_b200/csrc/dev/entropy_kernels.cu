@@ -43,6 +43,10 @@ __device__ void StageModDecoder(ModDecoder& md, const DFrame& f, uint8_t* dsm, u
 template <bool kNarrow>
 __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
   const int lane = threadIdx.x;
+  if (f.band_on) {   // band decode: only the LF groups that cover the block rows of the band (+1 row each side for smoothing / LLF context)
+    const int r0 = (g / int(f.xlfgroups)) * 256, r1 = r0 + 256, need0 = int(f.comp_g0 * (f.group_dim >> 3)) - 1, need1 = int(f.comp_g1 * (f.group_dim >> 3)) + 1;
+    if (r1 <= need0 || r0 >= need1) return;
+  }
   const int gx = g % int(f.xlfgroups), gy = g / int(f.xlfgroups), cx0 = gx * 256, cy0 = gy * 256;
   const int w = min(256, int(f.xb) - cx0), h = min(256, int(f.yb) - cy0), tw = (w + 7) / 8, th = (h + 7) / 8;
   int32_t* scratch = f.hfmeta_scratch + size_t(g) * kHfMetaScratchInts;
@@ -189,7 +193,7 @@ __device__ __forceinline__ void AcVardctBody(const DFrame& f, const int pass, co
   __syncthreads();
   if (kSmem) cv.AssumeShared();
   const int g = (cta * kAcWarps + warp) * lanes + lane;
-  if (lane >= lanes || g >= int(f.num_groups)) return;
+  if (lane >= lanes || g >= int(f.num_groups) || !GroupInBand(f, g)) return;
   const int xb = int(f.xb), cx0 = (g % int(f.xgroups)) * 32, cy0 = (g / int(f.xgroups)) * 32, w = min(32, xb - cx0), h = min(32, int(f.yb) - cy0);
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(32 * kModGroupsPerCta) k_mod_group(const __gri
   ModDecoder md; BindModDecoder(md, f, &sh_lut[warp]); uint32_t used = 0;
   StageModDecoder(md, f, dsm, f.lf_smem, used, tid, 32 * kModGroupsPerCta);
   __syncthreads();
-  if (lane != 0 || !active) return;
+  if (lane != 0 || !active || !GroupInBand(f, g)) return;
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];

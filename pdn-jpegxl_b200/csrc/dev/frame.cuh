@@ -33,6 +33,9 @@ struct DTables { float cosines[1 + 4 + 16 + 64 + 256 + 1024 + 4096 + 16384 + 655
 __host__ __device__ inline uint32_t CosOff(int log2n) { const uint32_t o[9] = {0, 1, 5, 21, 85, 341, 1365, 5461, 21845}; return o[log2n]; }
 
 struct DFrame {
+  // Band decode (one rank's share of a frame that is sharded by group rows): output rows [out_y0, out_y1) = group rows
+  // [out_g0, out_g1); entropy decode + reconstruction run on group rows [comp_g0, comp_g1) (one extra row each side: the filters' halo).
+  uint32_t band_on, out_g0, out_g1, comp_g0, comp_g1, out_y0, out_y1, band_pad;
   uint32_t xsize, ysize, xb, yb, xpad, ypad, xt, yt, xgroups, ygroups, num_groups, xlfgroups, ylfgroups, num_lf_groups, group_dim, num_passes, encoding, flags;
   uint32_t pass_shift[kMaxPasses]; int32_t pass_min_shift[kMaxPasses], pass_max_shift[kMaxPasses];
   float lf_fac[3], cfl_x_lf, cfl_b_lf, inv_gs, xm, bm, base_x, base_b, inv_color_factor, quant_bias[4], quant_scale;
@@ -61,6 +64,7 @@ static const uint32_t kHfMetaScratchInts = 2 * 1024 + 2 * 65536 + 65536;
 static const uint32_t kStaticBlobBit = 0x80000000u;
 #ifdef __CUDACC__
 __device__ __forceinline__ const uint8_t* BlobAt(const DFrame& f, uint32_t off) { return (off & kStaticBlobBit) ? f.static_blob + (off & ~kStaticBlobBit) : f.blob + off; }
+__device__ __forceinline__ bool GroupInBand(const DFrame& f, int g) { if (!f.band_on) return true; const uint32_t gy = uint32_t(g) / f.xgroups; return gy >= f.comp_g0 && gy < f.comp_g1; }
 __device__ __forceinline__ const uint64_t* SecBitPos(const DFrame& f) { return reinterpret_cast<const uint64_t*>(f.blob + f.sec_off); }
 #endif
 

@@ -90,6 +90,7 @@ __device__ constexpr float kCos8[64] = {1.000000000e+00f, 1.000000000e+00f, 1.00
 __global__ void __launch_bounds__(256) k_reconstruct_dct8(const __grid_constant__ DFrame f) {
   const int g = blockIdx.x >> 2, quarter = blockIdx.x & 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = lane >> 3, r = lane & 7;
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
+  if (!GroupInBand(f, g)) return;
   __shared__ float s_dq[3 * 64]; __shared__ float s_t[8][3][4 * 72];   // per warp: [channel][block][72]: two __syncwarp per iteration instead of six
   if (tid < 192) s_dq[tid] = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[0]))[tid];
   __syncthreads();
@@ -154,7 +155,7 @@ static const int kReconWarps = 8;
 // dynamic smem per warp: Sy[1024] Sc[1024] T[1024] floats
 __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* fp) {
   const DFrame& f = *fp; const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (f.group_other[g] == 0) return;   // every varblock of this group is a DCT8: k_reconstruct_dct8 did all the work
+  if (!GroupInBand(f, g) || f.group_other[g] == 0) return;   // every varblock of this group is a DCT8: k_reconstruct_dct8 did all the work
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
   extern __shared__ float smem[]; float* Sy = smem + warp * 3072; float* Sc = Sy + 1024; float* T = Sc + 1024;
   const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const DTables& tb = *f.tables;
@@ -325,7 +326,7 @@ __device__ __forceinline__ size_t OrientedIndex(const DFrame& f, int x, int y) {
   const int W = int(f.xsize), H = int(f.ysize); int ox, oy;
   switch (f.out.orientation) { case 2: ox = W - 1 - x; oy = y; break; case 3: ox = W - 1 - x; oy = H - 1 - y; break; case 4: ox = x; oy = H - 1 - y; break;
     case 5: ox = y; oy = x; break; case 6: ox = H - 1 - y; oy = x; break; case 7: ox = H - 1 - y; oy = W - 1 - x; break; case 8: ox = y; oy = W - 1 - x; break; default: ox = x; oy = y; }
-  return size_t(oy) * f.out.out_w + ox;
+  return size_t(oy - int(f.out_y0)) * f.out.out_w + ox;   // out_y0: first output row of a band decode (0 otherwise; bands need orientation 1)
 }
 
 // Colour + sample conversion + store of one pixel. For VarDCT frames (X,Y,B) are the filtered XYB samples.
@@ -373,6 +374,7 @@ __device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float
 
 __global__ void k_output(const __grid_constant__ DFrame f, const float* __restrict__ xyb) {
   const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+  if (f.band_on && (y < int(f.out_y0) || y >= int(f.out_y1))) return;
   float X = 0.f, Y = 0.f, B = 0.f;
   if (f.encoding == 0) { const size_t plane = size_t(f.xpad) * f.ypad, at = size_t(y) * f.xpad + x; X = xyb[at]; Y = xyb[plane + at]; B = xyb[2 * plane + at]; }
   OutputPixel(f, x, y, X, Y, B);
@@ -386,6 +388,7 @@ __global__ void k_output(const __grid_constant__ DFrame f, const float* __restri
 template <int GAB, int EPF>
 __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DFrame f) {
   constexpr int R0 = EPF == 3 ? 3 : 0, R1 = EPF >= 1 ? 2 : 0, R2 = EPF >= 2 ? 1 : 0, H = GAB + R0 + R1 + R2, D = 32 + 2 * H, N = D * D;
+  if (f.band_on && (blockIdx.y * 32 + 32 <= f.out_y0 || blockIdx.y * 32 >= f.out_y1)) return;   // band decode: tiles outside the band
   extern __shared__ float rs[]; float* A = rs; float* Bf = rs + 3 * N; float* Mh = rs + 6 * N; float* Mv = rs + 7 * N; float* s_is = rs + (EPF ? 8 : 6) * N;   // s_is: 8x8 blocks of 1/sigma
   const int xs = int(f.xsize), ys = int(f.ysize), tx0 = blockIdx.x * 32 - H, ty0 = blockIdx.y * 32 - H, tid = threadIdx.x; const size_t plane = size_t(f.xpad) * f.ypad;
   const int bx0 = max(tx0, 0) >> 3, by0 = max(ty0, 0) >> 3;
@@ -488,12 +491,14 @@ __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DFrame f
     __syncthreads(); float* t = src; src = dst; dst = t;
   }
   for (int i = tid; i < 32 * 32; i += 256) { const int ly = i >> 5, lx = i & 31, y = blockIdx.y * 32 + ly, x = blockIdx.x * 32 + lx; if (x >= xs || y >= ys) continue;
+    if (f.band_on && (y < int(f.out_y0) || y >= int(f.out_y1))) continue;
     const int p = (H + ly) * D + H + lx; OutputPixel(f, x, y, src[p], src[N + p], src[2 * N + p]); }
 }
 
 // Lossless 8/16-bit integer fast path: samples pass through untouched (bit-exact by construction).
 __global__ void k_output_int(const DFrame* fp) {
   const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
+  if (f.band_on && (y < int(f.out_y0) || y >= int(f.out_y1))) return;
   const DOutput& o = f.out; const size_t oi = OrientedIndex(f, x, y); const uint32_t nc = f.color.num_color; int32_t v[4]; uint32_t n = 0;
   for (uint32_t c = 0; c < o.color_channels; c++) { const DModChannel& ch = f.mod_ch[c < nc ? c : nc - 1]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }
   if (o.alpha_plane >= 0) { const DModChannel& ch = f.mod_ch[o.alpha_plane]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }

@@ -14,7 +14,8 @@ namespace jxlgpu {
 enum class Status : int32_t { Ok = 0, NullParameter, InvalidParameter, OutOfMemory, HasAnimation, HasMultipleFrames, ImageDimensionExceedsInt32, UnsupportedChannelFormat,
                               CreateLayerError, CreateMetadataError, DecodeError, MetadataError, InvalidFileSignature };
 
-struct ParsedInfo {   // what pass 1 of the reference reports (N/Decoder/JxlDecoder.cpp:412-793)
+struct ParsedInfo {
+  uint32_t group_dim = 0, num_group_rows = 0;   // frame group size in pixels and number of group rows (band decode layout)   // what pass 1 of the reference reports (N/Decoder/JxlDecoder.cpp:412-793)
   uint32_t width = 0, height = 0; int format = 1; int sample_type = 0; bool has_alpha = false; int num_channels = 3;
   int known_profile = -1; std::vector<uint8_t> icc; bool is_container = false; bool has_exif = false; std::vector<uint8_t> exif; std::vector<std::vector<uint8_t>> xmp;
   std::string frame_name; double bpp = 0;
@@ -29,6 +30,7 @@ struct DecodeRequest {
   uint8_t* out_device = nullptr;    // optional: decode straight into this device buffer (out_capacity bytes)
   uint8_t* out_pinned = nullptr;    // optional: copy the pixels straight into this page-locked host buffer (out_capacity bytes)
   size_t out_capacity = 0;
+  uint32_t band_begin = 0, band_end = 0;   // band decode: output only group rows [band_begin, band_end) of the frame (0,0 = whole frame); needs orientation 1
   int ac_lanes = 0;                 // AC sections walked per warp (power of two, 1..32); 0: 1 (lowest latency). Batches raise it for throughput.
 };
 
@@ -52,6 +54,7 @@ void DecodeBundleLaunch(const std::vector<std::shared_ptr<DecodeJob>>& jobs, int
 bool DecodeEnqueuePhase(std::shared_ptr<DecodeJob>& job, int phase, DecodeResult* res);   // phase 2: AC entropy kernels, 3: reconstruction + render; false: job failed (res filled, job released)
 bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job);
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job);
+Status DecodeBandLayout(const uint8_t* data, size_t size, ParsedInfo* info, std::string* message);
 void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res);
 // stage dumps for parity tests (3 planes xpad*ypad floats or coefficient ints), copied to host
 bool DecodeDebugPlanes(const std::shared_ptr<DecodeJob>& job, int which, std::vector<float>* out, int* xpad, int* ypad);

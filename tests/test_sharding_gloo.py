@@ -44,3 +44,41 @@ def test_two_rank_sharding_covers_all_files_once():
     assert sorted(i for s in gathered for i in s) == list(range(11))
     assert gathered[0] == [0, 2, 4, 6, 8, 10] and gathered[1] == [1, 3, 5, 7, 9]
     assert tmax == 15.0 and units == 11.0
+
+
+def _band_worker(rank, world, port, data, out):
+    """Gigapixel-style sharding of ONE frame: every rank parses the layout from the same file bytes (host only, no GPU
+    needed), takes its contiguous group-row range, and the host stitches the bands by row offset. No collective carries pixel data."""
+    sys.path.insert(0, ROOT)
+    import pkgload
+    P = pkgload.load()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w, h, gdim, rows = P.band_layout(data)
+    begin, end = P.band_partition(rows, world)[rank]
+    mine = (begin * gdim, min(end * gdim, h)) if end > begin else (0, 0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (rank, begin, end, mine))
+    if rank == 0:
+        out.put(((w, h, gdim, rows), gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_band_sharding_of_one_frame():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py as O
+    data = O.encode(O.synthetic_image(300, 1100, seed=4), effort=3)      # 2 x 5 groups of 256 px
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_band_worker, args=(r, 2, port, data, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    layout, gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert layout == (300, 1100, 256, 5)
+    assert gathered == [(0, 0, 3, (0, 768)), (1, 3, 5, (768, 1100))]       # contiguous, disjoint, covering every image row
