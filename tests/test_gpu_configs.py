@@ -1,5 +1,6 @@
 """-m gpu tests at the full sizes of BASELINE.json's configs 2 and 4 (config 1 / 3 are the small-size and batch tests of
-test_gpu_decode.py / bench.py; config 5, the sharded gigapixel frame, is not built — DESIGN.md §7)."""
+test_gpu_decode.py / bench.py; config 5, the gigapixel frame sharded by group rows, is covered at test size by
+test_band_decode_stitches_to_the_full_frame and at full size by scripts/gigapixel_bands.py — DESIGN.md §7)."""
 import io
 
 import numpy as np
