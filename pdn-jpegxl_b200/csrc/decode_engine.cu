@@ -522,6 +522,7 @@ void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res) {
   cudaError_t e = cudaStreamSynchronize(job->stream);
   if (e != cudaSuccess) { res->status = Status::DecodeError; res->message = std::string("CUDA: ") + cudaGetErrorString(e); return; }
   uint32_t de = *job->h_err.as<uint32_t>();
+  { static const bool dbg = getenv("JXLB200_TRACE") != nullptr; if (dbg && job->timed) fprintf(stderr, "[jxlb200] LF group 0: LF coefficients %u kcycles, HF metadata %u kcycles\n", job->h_err.as<uint32_t>()[13], job->h_err.as<uint32_t>()[14]); }
   if (de) { res->status = Status::DecodeError; res->message = DevErrorText(de); return; }
   res->info = job->info; res->pixels = job->device_output ? job->h.out_px : (job->ext_out_pinned ? job->ext_out_pinned : job->h_out.as<uint8_t>()); res->pixel_bytes = job->out_bytes; res->out_width = job->h.out.out_w; res->out_height = job->h.band_on ? job->h.out_y1 - job->h.out_y0 : job->h.out.out_h; res->job = job;
   if (job->timed) { auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, job->ev[a], job->ev[b]); return t; };

@@ -103,7 +103,8 @@ struct SymReader {
     return sym;
   }
   // hybrid-uint tail for tokens >= split (info: packed per-cluster word)
-  __device__ __noinline__ uint32_t HybridSlow(uint32_t info, uint32_t t) { DHybrid h; h.split_exp = uint8_t(info & 0xff); h.msb = uint8_t((info >> 8) & 15); h.lsb = uint8_t((info >> 12) & 15); return Hybrid(h, t); }
+  // (must inline: a non-inlined member call takes the address of the reader and forces its whole state — ANS state, bit buffer — into local memory)
+  __device__ __forceinline__ uint32_t HybridSlow(uint32_t info, uint32_t t) { DHybrid h; h.split_exp = uint8_t(info & 0xff); h.msb = uint8_t((info >> 8) & 15); h.lsb = uint8_t((info >> 12) & 15); return Hybrid(h, t); }
   __device__ __forceinline__ uint32_t ReadClusterAns(const CodeView& cv, uint32_t cl) {
     const uint32_t info = cv.info[cl]; uint32_t t = info >> 16; if (t == 0xffffu) t = ReadTokenAns(cv, cl);
     if (t < (1u << (info & 0xff))) return t;

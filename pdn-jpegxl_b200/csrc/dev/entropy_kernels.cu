@@ -64,11 +64,13 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
     f.hfmeta_scratch[size_t(f.num_lf_groups) * kHfMetaScratchInts + g] = int32_t(extra_prec);
     bool ok = ReadGroupHeaderDev(md, f);
     if (ok) {
-      md.rd.Init(md.cv); const int sid = 1 + g; size_t plane = size_t(f.xb) * f.yb;
+      md.rd.Init(md.cv); const int sid = 1 + g; size_t plane = size_t(f.xb) * f.yb; const long long dbg_t0 = clock64();
       const int dst[3] = {1, 0, 2};   // stream channel order is Y, X, B (A.8 LfGroup)
       for (int c = 0; c < 3; c++) md.DecodeChannel<kNarrow>(c, sid, f.lfq + dst[c] * plane + size_t(cy0) * f.xb + cx0, f.xb, w, h, wp);
       if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
+      if (g == 0) f.err[13] = uint32_t((clock64() - dbg_t0) >> 10);   // debug: kilo-cycles spent on the LF coefficients of LF group 0
     }
+    const long long dbg_t1 = clock64();
     // (Modular LF-group channels — extra channels with dim_shift >= 3 — are rejected on the host.)
     if (ok && !md.rd.err) {
       uint32_t nb = md.rd.br.Read(CeilLog2Dev(uint32_t(w * h))) + 1; sh_nb = nb;
@@ -80,6 +82,7 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
         if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
       }
     }
+    if (g == 0) f.err[14] = uint32_t((clock64() - dbg_t1) >> 10);   // debug: kilo-cycles spent on its HF metadata
     uint64_t pos = md.rd.br.BitPos(); if (pos > end) md.rd.err = md.rd.err ? md.rd.err : kErrOverrun;
     if (single) f.end_bitpos[1] = pos;
     SetError(f.err, md.rd.err); sh_ok = (ok && !md.rd.err) ? 1 : 0;

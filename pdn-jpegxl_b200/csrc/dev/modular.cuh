@@ -65,7 +65,8 @@ __device__ __forceinline__ void WPUpdate(WPScratch& s, const WPPred& o, long lon
 // Per-channel lookup table for the common case of an MA subtree that tests a single dynamic property with uniform
 // leaves (predictor fixed, offset 0, multiplier 1): context cluster = lut[#thresholds below the property value].
 // When every threshold lies in [-128, 126] the lookup is a direct 256-entry table on the clamped property value.
-struct ChanLut { int32_t thr[32]; uint16_t cluster[33]; uint8_t direct[256]; int32_t n, prop, predictor, ok, has_direct; };
+struct ChanLut { int32_t thr[32]; uint16_t cluster[33]; uint8_t direct[256]; int32_t n, prop, predictor, ok, has_direct;
+  uint2 dinfo[256]; };   // dinfo[v+128] = {info word of the cluster for property value v, byte offset of its alias rows}: one LDS.64 replaces direct[] -> info[] -> address math
 
 // T = int32_t when all sums of four samples fit 32 bits (bit depth <= 20), else int64_t (libjxl's pixel_type_w).
 template <typename T> struct ModMath {
@@ -111,7 +112,8 @@ struct ModDecoder {
     for (int i = 1; i < L.n; i++) if (L.thr[i] < L.thr[i - 1]) return;
     if (L.prop < 0) L.prop = 2;   // single leaf: any property, zero thresholds
     bool direct = true; for (int i = 0; i < L.n; i++) if (L.thr[i] < -128 || L.thr[i] > 126) direct = false;
-    if (direct) { for (int v = -128; v <= 127; v++) { int cnt = 0; for (int i = 0; i < L.n; i++) cnt += v > L.thr[i]; L.direct[v + 128] = uint8_t(L.cluster[cnt]); } L.has_direct = 1; }
+    if (direct) { for (int v = -128; v <= 127; v++) { int cnt = 0; for (int i = 0; i < L.n; i++) cnt += v > L.thr[i]; const uint32_t cl = L.cluster[cnt]; L.direct[v + 128] = uint8_t(cl);
+        L.dinfo[v + 128] = make_uint2(cv.info[cl], (cl << cv.log_alpha) * 8u); } L.has_direct = 1; }
     L.ok = 1;
   }
 
@@ -162,23 +164,47 @@ struct ModDecoder {
   // Lean path: ANS code with every table in shared memory, no weighted predictor, int32 samples, gradient predictor,
   // context = direct LUT of property 8 (previous residual). This is the LF-coefficient / alpha / lossless hot loop.
   __device__ __noinline__ void DecodeRowsLean(int32_t* out, size_t stride, int w, int h) {
-    SymReader rd = this->rd; CodeView cv = this->cv; ChanLut* lut = this->lut; __builtin_assume(__isShared(lut)); cv.AssumeShared();
-    struct WriteBack { SymReader& dst; SymReader& src; __device__ ~WriteBack() { dst = src; } } wb{this->rd, rd};
-    const uint8_t* direct = lut->direct;
-    for (int y = 0; y < h; y++) {
-      int32_t* cur = out + size_t(y) * stride; const int32_t* up = cur - stride;
-      int32_t W, N, NW, NE, prev_grad = 0;
-      if (y) { N = up[0]; NE = w > 1 ? up[1] : N; W = N; NW = W; } else { N = NW = NE = 0; W = 0; }
-      int32_t ne_next = (y && w > 2) ? up[2] : NE;
+    CodeView cv = this->cv; ChanLut* lut = this->lut; __builtin_assume(__isShared(lut)); cv.AssumeShared();
+    // reader state in plain locals (nothing may take the reader's address here, or it all moves to local memory)
+    BitRd br = this->rd.br; uint32_t state = this->rd.state, err = this->rd.err;
+    const uint2* dinfo = lut->dinfo; const uint8_t* alias_bytes = reinterpret_cast<const uint8_t*>(cv.alias);
+    const uint32_t log_entry = 12 - cv.log_alpha, pos_mask = (1u << log_entry) - 1;
+    // One symbol: context word di = dinfo[clamp(W - prev_grad)] -> token -> residual. A single warp issues at best one instruction
+    // every other cycle, so the loop is written for instruction count: the gradient predictor and property 8 only need W, N and NW,
+    // i.e. ONE load per pixel (the next N, requested a full iteration early), and row 0 (no row above) has its own loop.
+    auto symbol = [&](int32_t ctxv) -> int32_t {
+      const uint2 di = dinfo[min(max(ctxv, -128), 127) + 128]; const uint32_t info = di.x;
+      uint32_t tok = info >> 16;
+      if (tok == 0xffffu) {   // ANS step (clusters with a single symbol carry it in the info word instead)
+        const uint32_t idx = state & 0xfff, i = idx >> log_entry, pos = idx & pos_mask;
+        const DAlias e = *reinterpret_cast<const DAlias*>(alias_bytes + di.y + i * 8u);
+        const bool g = pos >= (e.x & 0xffu); tok = g ? ((e.x >> 8) & 0xffu) : i;
+        const uint32_t s1 = (g ? (e.y >> 16) : (e.y & 0xffffu)) * (state >> 12) + (g ? (e.x >> 16) : 0u) + pos;
+        const bool refill = s1 < 65536u; state = refill ? ((s1 << 16) | (br.Peek32() & 0xffffu)) : s1;   // branch-free renormalisation
+        if (refill) br.Skip(16);
+      }
+      if (tok >= (1u << (info & 0xff))) {   // hybrid-uint tail (rare for LF residuals)
+        DHybrid hc; hc.split_exp = uint8_t(info & 0xff); hc.msb = uint8_t((info >> 8) & 15); hc.lsb = uint8_t((info >> 12) & 15);
+        const uint32_t split = 1u << hc.split_exp, n = hc.split_exp - (hc.msb + hc.lsb) + ((tok - split) >> (hc.msb + hc.lsb));
+        if (n >= 32) { err = err ? err : kErrHybrid; tok = 0; }
+        else { const uint32_t low = tok & ((1u << hc.lsb) - 1); const uint32_t t2 = tok >> hc.lsb; const uint32_t hi = (t2 & ((1u << hc.msb) - 1)) | (1u << hc.msb); tok = (((hi << n) | br.Read(int(n))) << hc.lsb) | low; }
+      }
+      return UnpackSignedDev(tok);
+    };
+    { int32_t W = 0, prev_grad = 0;   // row 0: N = NW = W, so the gradient is W itself
+      for (int x = 0; x < w; x++) { const int32_t val = symbol(W - prev_grad) + W; out[x] = val; prev_grad = W; W = val; } }
+    for (int y = 1; y < h; y++) {
+      int32_t* __restrict__ cur = out + size_t(y) * stride; const int32_t* __restrict__ up = cur - stride;
+      int32_t N = up[0], NW = N, W = N, prev_grad = 0; const int last = w - 1;
+#pragma unroll 2
       for (int x = 0; x < w; x++) {
-        const int32_t ne_next2 = (y && x + 3 < w) ? up[x + 3] : 0;   // prefetch two ahead: independent of the symbol being decoded
-        const int32_t v = W - prev_grad; const uint32_t cl = direct[min(max(v, -128), 127) + 128];
-        const uint32_t tok = rd.ReadClusterAns(cv, cl);
-        const int32_t g = W + N - NW, lo = min(W, N), hi = max(W, N); const int32_t val = UnpackSignedDev(tok) + max(lo, min(hi, g));
-        cur[x] = val; prev_grad = g;
-        if (y) { NW = N; N = NE; NE = (x + 2 < w) ? ne_next : NE; ne_next = ne_next2; W = val; } else { W = val; N = val; NW = val; NE = val; }
+        const int32_t n_next = up[min(x + 1, last)];   // independent of the symbol being decoded: its latency hides behind the ANS step
+        const int32_t res = symbol(W - prev_grad);
+        const int32_t g = W + N - NW, val = res + max(min(W, N), min(max(W, N), g));
+        cur[x] = val; prev_grad = g; NW = N; N = n_next; W = val;
       }
     }
+    this->rd.br = br; this->rd.state = state; this->rd.err = err;
   }
 
   // Decodes one channel in raster order into out[y*stride + x]. wp_base: scratch for the weighted predictor (may be null when !uses_wp).
