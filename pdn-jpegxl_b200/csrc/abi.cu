@@ -218,6 +218,7 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
       for (size_t k = 0; k < std::min(kWindow, q1.size());) { if (!idle(*q1[k])) { k++; continue; } std::unique_ptr<Bundle> b = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true; next_phase(*b, 2); if (b->items.empty()) free_streams.push_back(b->stream); else q2.push_back(std::move(b)); }
       return progressed;
     };
+    bool reserved = false;
     while (done < count) {
       double t0 = now(); bool progressed = advance(); t_ret += now() - t0;
       if (next < count && !free_streams.empty()) {
@@ -228,6 +229,7 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
           if (hostInputs) req.data = datas[i]; else { cudaEventSynchronize(in_ready[i]); req.data = host_in + in_off[i]; req.device_input = datas[i]; }
           if (!hostOutputs) { req.out_device = outputs[i]; f->direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f->direct = true; }
           f->job = DecodeEnqueue(req, b->stream, &f->res, true, bundle_size > 1);
+          if (f->job && !reserved) { reserved = true; DecodeReservePools(f->job, size_t(std::min(count, nstreams * bundle_size)) - 1); }   // the first image tells the buffer sizes of the batch
           if (f->job) b->items.push_back(std::move(f)); else finish(*f);
         }
         if (bundle_size > 1) DecodeBundleLaunch(jobs_of(*b), 1);
@@ -235,7 +237,7 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
         if (b->items.empty()) free_streams.push_back(b->stream); else q1.push_back(std::move(b));
       } else if (!progressed) { t0 = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); t_idle += now() - t0; }
     }
-    if (trace) DumpHostTrace();
+    if (trace) { DumpHostTrace(); DumpPoolStats(); }
     if (trace && count) fprintf(stderr, "[jxlb200] GPU ms/image under load: lf %.2f ac %.2f recon %.2f render %.2f total %.2f\n", acc_t[0] / count, acc_t[1] / count, acc_t[2] / count, acc_t[3] / count, acc_t[4] / count);
     if (trace) fprintf(stderr, "[jxlb200] batch of %d: host parse + LF phase %.2f ms (%.2f ms/image), polling + later phases + retire %.2f ms, idle (GPU-bound) %.2f ms\n", count, t_enq, t_enq / std::max(count, 1), t_ret, t_idle);
     if (pin) PinnedPut(pin, pin_bytes);

@@ -43,24 +43,35 @@ class Pool {
   explicit Pool(bool pinned) : pinned_(pinned) {}
   void* Get(size_t bytes) {
     size_t sz = Round(bytes); { std::lock_guard<std::mutex> lk(mu_); auto it = free_.find(sz); if (it != free_.end() && !it->second.empty()) { void* p = it->second.back(); it->second.pop_back(); cached_ -= sz; return p; } }
-    void* p = nullptr; cudaError_t e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz);
+    misses_++; { std::lock_guard<std::mutex> lk(mu_); miss_sizes_[sz]++; } void* p = nullptr; cudaError_t e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz);
     if (e != cudaSuccess) { cudaGetLastError(); Trim(); e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz); }
     if (e != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
     return p;
   }
   void Put(void* p, size_t bytes) { if (!p) return; size_t sz = Round(bytes); std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; if (cached_ > Limit()) TrimLocked(); }
   void Trim() { std::lock_guard<std::mutex> lk(mu_); TrimLocked(); }
+  // Makes sure `count` buffers of this size class are cached (batch start: the first image tells the sizes; allocating them one
+  // by one while the GPU is busy stalls the enqueue thread for milliseconds each and takes many batches to converge).
+  void Reserve(size_t bytes, size_t count) {
+    const size_t sz = Round(bytes); size_t have; { std::lock_guard<std::mutex> lk(mu_); have = free_[sz].size(); }
+    for (; have < count; have++) { if (cached_ + sz > Limit()) return; void* p = nullptr; cudaError_t e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz); if (e != cudaSuccess) { cudaGetLastError(); return; }
+      std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; }
+  }
  private:
-  // size classes: 4 KiB below 64 KiB, then eighths of a power of two, so that files of slightly different sizes share buckets
-  static size_t Round(size_t b) { if (b <= (1u << 16)) return (b + 4095) / 4096 * 4096; int k = 63 - __builtin_clzll(b); size_t g = size_t(1) << (k - 3); return (b + g - 1) / g * g; }
-  void TrimLocked() { for (auto& kv : free_) for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } free_.clear(); cached_ = 0; }
+  // size classes: powers of two from 4 KiB up to 16 MiB (files of different sizes then share every small bucket, so the first image of
+  // a batch can reserve for all of them), eighths of a power of two above (the big planes, whose size depends on the dimensions only)
+  static size_t Round(size_t b) { if (b <= 4096) return 4096; int k = 63 - __builtin_clzll(b - 1); if (b <= (size_t(16) << 20)) return size_t(2) << k; k = 63 - __builtin_clzll(b); size_t g = size_t(1) << (k - 3); return (b + g - 1) / g * g; }
+  void TrimLocked() { trims_++; for (auto& kv : free_) for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } free_.clear(); cached_ = 0; }
   size_t Limit() { if (!limit_) { size_t fr = 0, tot = 0; if (pinned_ || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); limit_ = size_t(32) << 30; } else limit_ = tot / 4 * 3; } return limit_; }
+  public: size_t misses_ = 0, trims_ = 0; std::map<size_t, size_t> miss_sizes_; std::string MissReport() { std::lock_guard<std::mutex> lk(mu_); std::string r; for (auto& kv : miss_sizes_) { r += " " + std::to_string(kv.first >> 10) + "K:" + std::to_string(kv.second) + "(free " + std::to_string(free_[kv.first].size()) + ")"; } return r; } size_t Cached() const { return cached_; }
+ private:
   bool pinned_; std::mutex mu_; std::map<size_t, std::vector<void*>> free_; size_t cached_ = 0; size_t limit_ = 0;
 };
 static Pool& DevPool() {   // one pool per device: a cached buffer must never cross devices
   static std::mutex mu; static std::map<int, std::unique_ptr<Pool>> pools; int dev = 0; cudaGetDevice(&dev); std::lock_guard<std::mutex> lk(mu); auto& p = pools[dev]; if (!p) p.reset(new Pool(false)); return *p; }
 static Pool& HostPool() { static Pool p(true); return p; }
 void TrimPools() { DevPool().Trim(); HostPool().Trim(); }
+void DumpPoolStats() { Pool& d = DevPool(); Pool& h = HostPool(); fprintf(stderr, "[jxlb200] pools: device misses %zu trims %zu cached %.1f GB; pinned misses %zu trims %zu cached %.2f GB\n", d.misses_, d.trims_, d.Cached() / 1e9, h.misses_, h.trims_, h.Cached() / 1e9); fprintf(stderr, "[jxlb200] device miss sizes:%s\n", d.MissReport().c_str()); }
 void* PinnedGet(size_t bytes) { return HostPool().Get(bytes ? bytes : 1); }
 void PinnedPut(void* p, size_t bytes) { HostPool().Put(p, bytes ? bytes : 1); }
 
@@ -214,6 +225,8 @@ class DecodeJob {
 
   void Setup(const DecodeRequest& req);
   void RunLf(const DecodeRequest& req); void RunAc(); void RunRender();
+  void ReservePools(size_t count) { DevBuf* all[] = {&d_frame, &d_blob, &d_comp, &d_lfq, &d_lf, &d_lf_tmp, &d_acs, &d_qf, &d_sharp, &d_lfidx, &d_ytox, &d_ytob, &d_hfmeta, &d_coeffs, &d_xyb, &d_xyb_tmp, &d_sigma, &d_mod, &d_wp, &d_out, &d_err, &h_out, &h_err, &h_comp, &h_blob, &h_misc, &d_gother, &d_nz, &d_acend};
+    for (DevBuf* b : all) if (b->p && b->pool) b->pool->Reserve(b->n, count); }
   void Run(const DecodeRequest& req) { RunLf(req); RunAc(); RunRender(); }
   void ParseLfGlobal(BitReader& br);
   void ParseHfGlobal(BitReader& br);
@@ -514,6 +527,7 @@ Status DecodeBandLayout(const uint8_t* data, size_t size, ParsedInfo* info, std:
   catch (const std::bad_alloc&) { return Status::OutOfMemory; }
   catch (const std::exception& e) { if (message) *message = e.what(); return Status::DecodeError; }
 }
+void DecodeReservePools(const std::shared_ptr<DecodeJob>& job, size_t count) { if (job) job->ReservePools(count); }
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job) { if (job) cudaStreamSynchronize(job->stream); }
 bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job) { return !job || cudaStreamQuery(job->stream) != cudaErrorNotReady; }
 

@@ -53,6 +53,8 @@ std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t 
 void DecodeBundleLaunch(const std::vector<std::shared_ptr<DecodeJob>>& jobs, int phase);   // phase 1: pending LF launches, 2: pending AC launches (jobs share one stream)
 bool DecodeEnqueuePhase(std::shared_ptr<DecodeJob>& job, int phase, DecodeResult* res);   // phase 2: AC entropy kernels, 3: reconstruction + render; false: job failed (res filled, job released)
 bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job);
+void DumpPoolStats();
+void DecodeReservePools(const std::shared_ptr<DecodeJob>& job, size_t count);   // pre-populate the caching pools with `count` more sets of this job's buffers
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job);
 Status DecodeBandLayout(const uint8_t* data, size_t size, ParsedInfo* info, std::string* message);
 void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res);
