@@ -103,6 +103,10 @@ JXLFT_API DecoderStatus JXLFT_CALL JxlB200BandLayout(const uint8_t* data, size_t
 JXLFT_API DecoderStatus JXLFT_CALL JxlB200DecodeBand(int32_t device, const uint8_t* data, size_t dataSize, uint32_t groupRowBegin, uint32_t groupRowEnd,
                                                       uint8_t* out, size_t outBytes, int32_t bgra, int32_t* rows, ErrorInfo* errorInfo);
 
+/* The engine caches device and page-locked buffers between calls (cudaMalloc costs more than a decode). This returns them to the
+ * driver; call it when a burst of work is over. */
+JXLFT_API void JXLFT_CALL JxlB200ReleaseMemory(void);
+
 /* Batch decode (BASELINE config 3): `count` independent files, each decoded by the full single-image pipeline on its own
  * CUDA stream of device `device`; outputs[i] (host memory, outputBytes[i] bytes, interleaved as LoadImage delivers, or
  * BGRA32 when bgra != 0) are filled on return. statuses[i] receives a DecoderStatus per file. Returns the first non-Ok

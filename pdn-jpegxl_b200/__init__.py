@@ -77,7 +77,7 @@ class IOCallbacks(C.Structure):
 
 EXPORTS = ["GetLibJxlVersion", "LoadImage", "SaveImage", "JxlB200LoadImageBgra", "JxlB200PeekInfo", "JxlB200DecodeBatch", "JxlB200EncodeToMemory",
            "JxlB200Free", "JxlB200LastStageTimes", "JxlB200KernelLaunchCount", "JxlB200DebugDecodeStage", "JxlB200CudaAvailable", "JxlB200BandLayout",
-           "JxlB200DecodeBand"]
+           "JxlB200DecodeBand", "JxlB200ReleaseMemory"]
 
 _lib.GetLibJxlVersion.restype = C.c_uint32
 _lib.LoadImage.argtypes = [C.POINTER(DecoderCallbacks), C.c_void_p, C.c_size_t, C.POINTER(ErrorInfo)]
@@ -470,6 +470,11 @@ def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, widt
     data = C.string_at(out, n.value)
     _lib.JxlB200Free(out)
     return data
+
+
+def release_memory():
+    """Returns the engine's cached device / page-locked buffers to the driver."""
+    _lib.JxlB200ReleaseMemory()
 
 
 def band_layout(data):

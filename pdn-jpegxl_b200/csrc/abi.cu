@@ -257,6 +257,9 @@ EncoderStatus JxlB200EncodeToMemory(const BitmapData* bitmap, const EncoderOptio
   return EncoderStatus_Ok;
 }
 void JxlB200Free(void* p) { free(p); }
+// Returns the cached device and page-locked buffers of the calling thread's current device to the driver (after a large batch the
+// pools hold one buffer set per image that was in flight).
+void JxlB200ReleaseMemory(void) { try { cudaDeviceSynchronize(); TrimPools(); } catch (...) {} }
 
 void JxlB200LastStageTimes(float* ms8) { if (!ms8) return; const StageTimes& t = g_last_times; ms8[0] = t.h2d; ms8[1] = t.lf; ms8[2] = t.ac; ms8[3] = t.recon; ms8[4] = t.filters; ms8[5] = t.output; ms8[6] = t.d2h; ms8[7] = t.total; }
 int64_t JxlB200KernelLaunchCount(void) { return LaunchCount(); }
