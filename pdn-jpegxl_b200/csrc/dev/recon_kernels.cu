@@ -330,9 +330,8 @@ __device__ __forceinline__ size_t OrientedIndex(const DFrame& f, int x, int y) {
 }
 
 // Colour + sample conversion + store of one pixel. For VarDCT frames (X,Y,B) are the filtered XYB samples.
-__device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float X, float Y, float B) {
-  const DOutput& o = f.out; float rgb[3];
-  if (f.encoding == 0) {
+// XYB -> target-encoded RGB of one VarDCT sample (shared by every output path, so they agree bit for bit)
+__device__ __forceinline__ void XybToRgbDev(const DFrame& f, float X, float Y, float B, float rgb[3]) {
     float gm[3] = {Y + X, Y - X, B}, mix[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) { float v = gm[c] - f.color.opsin_bias_cbrt[c]; mix[c] = v * v * v + f.color.opsin_bias[c]; }
@@ -348,7 +347,11 @@ __device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float
 #pragma unroll
       for (int c = 0; c < 3; c++) rgb[c] = TfFromLinearDev(lin[c + 3], f.color.tf, f.color.gamma, f.color.intensity_target);
     }
-  } else {
+}
+__device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float X, float Y, float B) {
+  const DOutput& o = f.out; float rgb[3];
+  if (f.encoding == 0) XybToRgbDev(f, X, Y, B, rgb);
+  else {
     const uint32_t nc = f.color.num_color;
     for (uint32_t c = 0; c < 3; c++) { const DModChannel& ch = f.mod_ch[c < nc ? c : nc - 1]; rgb[c] = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(y) * ch.w + x], o.bits, o.exp_bits); }
   }
@@ -385,7 +388,9 @@ __global__ void k_output(const __grid_constant__ DFrame f, const float* __restri
 // the mirrored halo reproduces the mirrored filtered image), the passes ping-pong between two shared buffers, and the last
 // buffer goes straight through the colour transform to the output image: 12 B/px read + 3-4 B/px written instead of
 // 24 B/px per pass. SURVEY.md A.10; replaces libjxl's render pipeline stages reached from N/Decoder/JxlDecoder.cpp:252.
-template <int GAB, int EPF>
+// FAST: plain RGB8 output (3 colour channels, no alpha / CMYK / BGRA, identity orientation, rows 4-byte aligned): the tile's bytes are
+// packed in shared memory and leave as 32-bit words, 96 contiguous bytes per row, instead of three byte stores per pixel.
+template <int GAB, int EPF, bool FAST>
 __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DFrame f) {
   constexpr int R0 = EPF == 3 ? 3 : 0, R1 = EPF >= 1 ? 2 : 0, R2 = EPF >= 2 ? 1 : 0, H = GAB + R0 + R1 + R2, D = 32 + 2 * H, N = D * D;
   if (f.band_on && (blockIdx.y * 32 + 32 <= f.out_y0 || blockIdx.y * 32 >= f.out_y1)) return;   // band decode: tiles outside the band
@@ -490,6 +495,19 @@ __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DFrame f
     }
     __syncthreads(); float* t = src; src = dst; dst = t;
   }
+  if (FAST) {
+    uint8_t* sb = reinterpret_cast<uint8_t*>(dst);   // the other plane buffer is free after the last pass: 32 rows x 96 bytes
+    for (int i = tid; i < 32 * 32; i += 256) { const int ly = i >> 5, lx = i & 31, p = (H + ly) * D + H + lx; float rgb[3]; XybToRgbDev(f, src[p], src[N + p], src[2 * N + p], rgb);
+#pragma unroll
+      for (int c = 0; c < 3; c++) sb[ly * 96 + lx * 3 + c] = uint8_t(__float2int_rn(fminf(1.f, fmaxf(0.f, rgb[c])) * 255.0f)); }
+    __syncthreads();
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, nbytes = min(32, xs - x0) * 3;
+    for (int i = tid; i < 32 * 24; i += 256) { const int ly = i / 24, b0 = (i - ly * 24) * 4, y = y0 + ly; if (y >= ys || b0 >= nbytes) continue;
+      if (f.band_on && (y < int(f.out_y0) || y >= int(f.out_y1))) continue;
+      uint8_t* row = f.out_px + (size_t(y - int(f.out_y0)) * xs + x0) * 3;
+      if (b0 + 4 <= nbytes) *reinterpret_cast<uint32_t*>(row + b0) = *reinterpret_cast<const uint32_t*>(sb + ly * 96 + b0); else for (int b = b0; b < nbytes; b++) row[b] = sb[ly * 96 + b]; }
+    return;
+  }
   for (int i = tid; i < 32 * 32; i += 256) { const int ly = i >> 5, lx = i & 31, y = blockIdx.y * 32 + ly, x = blockIdx.x * 32 + lx; if (x >= xs || y >= ys) continue;
     if (f.band_on && (y < int(f.out_y0) || y >= int(f.out_y1))) continue;
     const int p = (H + ly) * D + H + lx; OutputPixel(f, x, y, src[p], src[N + p], src[2 * N + p]); }
@@ -530,8 +548,13 @@ const float* FilteredPlanes(const DFrame& h) { int n = (h.lpf.gab ? 1 : 0) + (h.
 // gaborish + EPF + colour in one pass over the frame (VarDCT frames with at least one restoration filter)
 template <int GAB, int EPF> static void LaunchRenderT(const DFrame& h, cudaStream_t st) {
   constexpr int H = GAB + (EPF == 3 ? 3 : 0) + (EPF >= 1 ? 2 : 0) + (EPF >= 2 ? 1 : 0), D = 32 + 2 * H; size_t smem = (size_t(EPF ? 8 : 6) * D * D + 64) * sizeof(float);
-  { static bool attr[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (!attr[dev & 63]) { cudaFuncSetAttribute(k_render<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; } }
-  dim3 grid((h.xsize + 31) / 32, (h.ysize + 31) / 32); k_render<GAB, EPF><<<grid, 256, smem, st>>>(h); CountLaunch();
+  { static bool attr[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (!attr[dev & 63]) { cudaFuncSetAttribute(k_render<GAB, EPF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cudaFuncSetAttribute(k_render<GAB, EPF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; } }
+  const DOutput& o = h.out;
+  const bool fast = !o.bgra && o.sample_type == 0 && o.num_channels == 3 && o.color_channels == 3 && o.alpha_plane < 0 && o.black_plane < 0 && !o.premultiplied && o.orientation == 1 &&
+                    (size_t(h.xsize) * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(h.out_px) & 3) == 0;
+  dim3 grid((h.xsize + 31) / 32, (h.ysize + 31) / 32);
+  if (fast) k_render<GAB, EPF, true><<<grid, 256, smem, st>>>(h); else k_render<GAB, EPF, false><<<grid, 256, smem, st>>>(h);
+  CountLaunch();
 }
 bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st) {
   if (h.encoding != 0 || (!h.lpf.gab && !h.lpf.epf_iters)) return false;
