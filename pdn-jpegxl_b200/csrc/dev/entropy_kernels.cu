@@ -98,7 +98,7 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
   __syncwarp();
   // ---- varblock placement: raster scan, each block at the first uncovered cell (A.8 LfGroup)
   const uint32_t nb = sh_nb; bool all1 = nb == uint32_t(w * h);
-  if (all1) for (uint32_t i = lane; i < nb; i += 32) { int32_t s = s_info[i]; if (s < 0 || s >= 27 || CoveredX(s) != 1 || CoveredY(s) != 1) all1 = false; }
+  if (all1) for (uint32_t i = lane; i < nb; i += 32) { int32_t s = s_info[i]; if (s < 0 || s >= 27 || (CoveredXLog2Dev(s) | CoveredYLog2Dev(s)) != 0) all1 = false; }
   all1 = __all_sync(0xffffffffu, all1);
   if (all1) {   // common case (only 8x8 strategies): block i sits in cell i, fully parallel
     for (uint32_t i = lane; i < nb; i += 32) { const int yy = cy0 + int(i / w), xx = cx0 + int(i % w); size_t o = size_t(yy) * f.xb + xx; f.acs[o] = uint8_t(s_info[i] | 0x80); f.hf_mul_m1[o] = uint8_t(max(0, min(255, s_info[nb + i])));
@@ -109,7 +109,7 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
       size_t o = size_t(cy0 + y) * f.xb + cx0 + x; if (f.acs[o] != 0xFF) continue;
       if (num >= nb) { e = kErrHfMeta; break; }
       int32_t s = s_info[num]; if (s < 0 || s >= 27) { e = kErrBadStrategy; break; }
-      int bw = CoveredX(s), bh = CoveredY(s);
+      int bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s);
       if (x + bw > w || y + bh > h || (x & 31) + bw > 32 || (y & 31) + bh > 32) { e = kErrBlockBounds; break; }
       int32_t qf = max(0, min(255, s_info[nb + num]));
       for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { size_t p = o + size_t(iy) * f.xb + ix; if (f.acs[p] != 0xFF) e = kErrBlockBounds; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = uint8_t(qf); }
@@ -218,9 +218,9 @@ __device__ __forceinline__ void AcVardctBody(const DFrame& f, const int pass, co
         ci = 0; bool found = false; uint32_t a = 0; size_t o = 0;
         for (;;) { if (++bx >= w) { bx = 0; if (++by >= h) break; } o = size_t(cy0 + by) * xb + cx0 + bx; a = f.acs[o]; if (a & 0x80) { found = true; break; } }
         if (!found) break;
-        const int s = a & 31; bw = CoveredX(s); bh = CoveredY(s); covered = uint32_t(bw * bh); log2c = 31 - __clz(covered); size = covered * 64; ord = StrategyOrder(s);
+        const int s = min(int(a & 31), 26); lbw = CoveredXLog2Dev(s); const uint32_t lbh = CoveredYLog2Dev(s); bw = 1 << lbw; bh = 1 << lbh; log2c = lbw + lbh; covered = 1u << log2c; size = covered * 64; ord = int(StrategyOrderDev(s));
         const uint32_t qf = uint32_t(f.hf_mul_m1[o]) + 1; qf_idx = 0; for (uint32_t t = 0; t < n_qf_thr; t++) qf_idx += qf > f.qf_thr[t];
-        lfi = f.lf_idx[o]; lbw = 31 - __clz(uint32_t(bw)); bwm = uint32_t(bw) - 1; cell = by * 32 + bx;
+        lfi = f.lf_idx[o]; bwm = uint32_t(bw) - 1; cell = by * 32 + bx;
       }
       c = ci == 0 ? 1 : ci == 1 ? 0 : 2; nzrow = nzs + c * 1024;
       uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : nzrow[cell - 32]; else if (by == 0) pred = nzrow[cell - 1]; else pred = (uint32_t(nzrow[cell - 32]) + nzrow[cell - 1] + 1) >> 1;

@@ -64,6 +64,12 @@ static const uint32_t kHfMetaScratchInts = 2 * 1024 + 2 * 65536 + 65536;
 static const uint32_t kStaticBlobBit = 0x80000000u;
 #ifdef __CUDACC__
 __device__ __forceinline__ const uint8_t* BlobAt(const DFrame& f, uint32_t off) { return (off & kStaticBlobBit) ? f.static_blob + (off & ~kStaticBlobBit) : f.blob + off; }
+// The strategy tables as packed nibbles (27 entries in two 64-bit immediates): register arithmetic only. The array forms below are
+// rebuilt on the stack at every call site when the index is a run-time value (ncu/SASS: 98 STL + 84 LDL in the AC block set-up).
+__device__ __forceinline__ uint32_t NibbleAt(uint64_t lo, uint64_t hi, int s) { return uint32_t(((s < 16 ? lo : hi) >> ((s & 15) * 4)) & 15u); }
+__device__ __forceinline__ uint32_t CoveredXLog2Dev(int s) { return NibbleAt(0x212010210000ull, 0x54543432300ull, s); }
+__device__ __forceinline__ uint32_t CoveredYLog2Dev(int s) { return NibbleAt(0x120201210000ull, 0x45534423300ull, s); }
+__device__ __forceinline__ uint32_t StrategyOrderDev(int s) { return NibbleAt(0x1111665544321110ull, 0xccbaa988711ull, s); }
 __device__ __forceinline__ bool GroupInBand(const DFrame& f, int g) { if (!f.band_on) return true; const uint32_t gy = uint32_t(g) / f.xgroups; return gy >= f.comp_g0 && gy < f.comp_g1; }
 __device__ __forceinline__ const uint64_t* SecBitPos(const DFrame& f) { return reinterpret_cast<const uint64_t*>(f.blob + f.sec_off); }
 #endif

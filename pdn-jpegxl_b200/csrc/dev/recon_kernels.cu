@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
   for (int cell = warp; cell < 1024; cell += kReconWarps) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
     const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
-    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw > 4 || bh > 4 || s == 0) continue;   // DCT8 is handled by k_reconstruct_dct8
+    const int s = min(int(a & 31), 26), bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s); if (bw > 4 || bh > 4 || s == 0) continue;   // DCT8 is handled by k_reconstruct_dct8
     const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[QuantTableOf(s)]));
     const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
     const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
   for (int cell = 0; cell < 1024; cell++) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
     const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
-    const int s = a & 31, bw = CoveredX(s), bh = CoveredY(s); if (bw <= 4 && bh <= 4) continue;
+    const int s = min(int(a & 31), 26), bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s); if (bw <= 4 && bh <= 4) continue;
     const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[QuantTableOf(s)]));
     const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
     const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
