@@ -27,6 +27,10 @@ METRIC = "decode MP/s (lossy VarDCT, 12 MP 8-bit)"
 UNIT = "MP/s"
 
 
+WORKLOAD = ("batch of %d synthetic %dx%d RGB8 VarDCT d=1.0 e=7 files per GPU (%d distinct seeds, encoded by the engine's SaveImage path), "
+            "decoded to interleaved RGB8; files sharded across ranks, no collective")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,7 +147,8 @@ def run_reference(args):
     # cpu_baseline() includes one warm-up decode per call; report the timed sample rate it measured
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%dx%d RGB8 VarDCT d=1.0 decode on the host CPU; each step a bounded sample of %d images" % (args.width, args.height, per_step), "mp_per_step": mp_step},
+            "config": {"workload": WORKLOAD % (args.batch, args.width, args.height, args.distinct), "mp_per_step": mp_step,
+                       "sample": "the same files decoded on the host CPU; each step a bounded sample of %d images" % per_step},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -256,7 +261,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "batch of %d synthetic %dx%d RGB8 VarDCT d=1.0 e=7 files per GPU (%d distinct seeds, encoded by the engine's SaveImage path), decoded to interleaved RGB8; files sharded across ranks, no collective" % (B, W, H, args.distinct),
+            "config": {"workload": WORKLOAD % (B, W, H, args.distinct),
                        "mp_per_step_per_gpu": mp_step, "bpp": 8.0 * comp_bytes / (B * W * H), "in_flight": args.in_flight,
                        "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % ((comp_bytes + B * out_bytes_one) / 1e6)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": comp_bytes, "d2h_bytes_per_step": B * out_bytes_one, "ms_per_step": ms_host / args.steps, "host_buffers": "page-locked" if host_pinned else "pageable"},
