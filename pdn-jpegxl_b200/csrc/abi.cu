@@ -172,7 +172,7 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
     static thread_local std::map<int, std::vector<cudaStream_t>> stream_cache; std::vector<cudaStream_t>& all_streams = stream_cache[cur_dev];
     while (int(all_streams.size()) < nstreams + 1) { cudaStream_t s = nullptr; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaStreamCreate failed"); return DecoderStatus_DecodeError; } all_streams.push_back(s); }
     cudaStream_t copy_stream = all_streams[0]; std::vector<cudaStream_t> streams(all_streams.begin() + 1, all_streams.begin() + 1 + nstreams); void* pin = nullptr; size_t pin_bytes = 0;
-    const int batch_lanes = (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
+    const int batch_lanes = (count >= 64 && nstreams >= 32) ? 16 : (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
     static const int env_bundle = getenv("JXLB200_BUNDLE") ? atoi(getenv("JXLB200_BUNDLE")) : 0;
     const int bundle_size = std::max(1, std::min(env_bundle > 0 ? env_bundle : ((count >= 64 && nstreams >= 32) ? 2 : 1), kMaxBundle));   // images per stream / per entropy launch
     struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; cudaStream_t stream = nullptr; };
