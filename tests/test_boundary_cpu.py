@@ -119,3 +119,54 @@ def test_shard_indices(pkg):
     files = list(range(10))
     shards = [pkg.shard_indices(len(files), r, 4) for r in range(4)]
     assert sorted(i for s in shards for i in s) == files and shards[1] == [1, 5, 9]
+
+
+def test_colour_profile_callbacks_without_gpu(pkg):
+    """Pass 1 of LoadImage (headers + metadata callbacks, N/Decoder/JxlDecoder.cpp:412-793) is host code: even without a CUDA device the
+    profile callbacks fire before the decode fails. setKnownColorProfile xor setIccProfile; embedded ICC streams come back byte for
+    byte; enum encodings outside the 8 known profiles get a synthesised matrix/TRC profile."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    import oracle_py as O
+    import icc_util
+    ok, _ = pkg.cuda_available()
+    img = O.synthetic_image(64, 48, seed=1)
+
+    def load(data):
+        im = pkg.DecoderImage()
+        try:
+            pkg.JpegXLNative.LoadImage(data, im)
+        except pkg.FormatException:
+            assert not ok          # only acceptable when there is no GPU: the engine has no CPU fallback
+        return im
+
+    icc = icc_util.make_matrix_icc(icc_util.ADOBE_PRIMS, gamma=2.19921875, curve="curv1")
+    im = load(O.encode(img, lossless=True, icc=icc))
+    assert (im.width, im.height) == (64, 48) and im.icc_profile == icc and im.known_color_profile is None
+    im = load(O.encode(img, lossless=True))
+    assert im.known_color_profile == "Srgb" and im.icc_profile is None
+    im = load(O.encode(img, lossless=True, primaries=11, tf=1))           # P3 primaries + Rec.709 curve: not one of the 8 enums
+    assert im.known_color_profile is None and im.icc_profile is not None
+    p = icc_util.parse_icc(im.icc_profile)
+    assert p["size"] == len(im.icc_profile) and p["space"] == b"RGB " and p["pcs"] == b"XYZ " and p["cls"] == b"mntr"
+    want = icc_util.adapt_to_d50(0.3127, 0.3290) @ icc_util.rgb_to_xyz(icc_util.P3_PRIMS, 0.3127, 0.3290)
+    got = np.stack([icc_util.xyz_of(p["tags"][s]) for s in (b"rXYZ", b"gXYZ", b"bXYZ")], axis=1)
+    assert np.abs(got - want).max() < 2e-4
+    t, params = icc_util.para_of(p["tags"][b"rTRC"])
+    assert t == 3 and np.allclose(params, [1 / 0.45, 1 / 1.099, 0.099 / 1.099, 1 / 4.5, 0.081], atol=2e-4)
+    im = load(O.encode(img, lossless=True, primaries=9, tf=16))          # Rec.2020 PQ is a known enum
+    assert im.known_color_profile == "Rec2020PQ"
+
+
+def test_band_layout_and_partition_are_host_only(pkg):
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import oracle_py as O
+    data = O.encode(O.synthetic_image(520, 700, seed=2), effort=3)
+    assert pkg.band_layout(data) == (520, 700, 256, 3)
+    data = O.encode(O.synthetic_image(300, 300, seed=3, channels=4), lossless=True)
+    w, h, gdim, rows = pkg.band_layout(data)
+    assert (w, h) == (300, 300) and gdim in (128, 256, 512, 1024) and rows == -(-300 // gdim)
+    assert pkg.band_partition(128, 8) == [(16 * r, 16 * r + 16) for r in range(8)]      # BASELINE config 5: rows [16r, 16r+16) on GPU r
+    assert pkg.band_partition(5, 2) == [(0, 3), (3, 5)] and pkg.band_partition(1, 3) == [(0, 1), (0, 0), (0, 0)]
