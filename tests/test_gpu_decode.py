@@ -213,3 +213,16 @@ def test_band_decode_stitches_to_the_full_frame(gpu, oracle, kw):
     assert np.array_equal(np.concatenate(parts, axis=0), full)
     with pytest.raises(gpu.FormatException):
         gpu.decode_band(data, 0, rows + 1)
+
+
+def test_large_batch_uses_bundles_and_wide_warps(gpu, oracle):
+    """64+ files with 32+ streams is the configuration bench.py measures: two images per entropy launch and 16 AC sections per warp.
+    Every output must equal the single-image decode of the same file."""
+    distinct = [oracle.encode(oracle.synthetic_image(600 + 40 * i, 520, seed=90 + i), effort=7 if i % 2 else 3) for i in range(5)]
+    singles = [_decode_gpu(gpu, f).layer_data.color for f in distinct]
+    files = [distinct[i % 5] for i in range(70)]
+    outs = [np.zeros_like(singles[i % 5]) for i in range(70)]
+    st = gpu.decode_batch(files, outs, max_in_flight=40)
+    assert st == [0] * 70
+    for i, o in enumerate(outs):
+        assert np.array_equal(o, singles[i % 5]), i
