@@ -107,6 +107,11 @@ JXLFT_API DecoderStatus JXLFT_CALL JxlB200DecodeBand(int32_t device, const uint8
  * driver; call it when a burst of work is over. */
 JXLFT_API void JXLFT_CALL JxlB200ReleaseMemory(void);
 
+/* Host-only diagnostic: the colorant matrix (profile RGB, linear -> linear sRGB, 9 floats) and the three tone curves sampled at v/255
+ * (768 floats) that SaveImage derives from a matrix/TRC ICC profile for lossy encoding. Returns 1 on success, 0 (with a message) when the
+ * profile is not a matrix/TRC RGB profile. */
+JXLFT_API int32_t JXLFT_CALL JxlB200DebugParseIcc(const uint8_t* icc, size_t iccSize, float* matrix9, float* lut768, ErrorInfo* errorInfo);
+
 /* Batch decode (BASELINE config 3): `count` independent files, each decoded by the full single-image pipeline on its own
  * CUDA stream of device `device`; outputs[i] (host memory, outputBytes[i] bytes, interleaved as LoadImage delivers, or
  * BGRA32 when bgra != 0) are filled on return. statuses[i] receives a DecoderStatus per file. Returns the first non-Ok

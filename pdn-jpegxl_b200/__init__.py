@@ -77,7 +77,7 @@ class IOCallbacks(C.Structure):
 
 EXPORTS = ["GetLibJxlVersion", "LoadImage", "SaveImage", "JxlB200LoadImageBgra", "JxlB200PeekInfo", "JxlB200DecodeBatch", "JxlB200EncodeToMemory",
            "JxlB200Free", "JxlB200LastStageTimes", "JxlB200KernelLaunchCount", "JxlB200DebugDecodeStage", "JxlB200CudaAvailable", "JxlB200BandLayout",
-           "JxlB200DecodeBand", "JxlB200ReleaseMemory"]
+           "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc"]
 
 _lib.GetLibJxlVersion.restype = C.c_uint32
 _lib.LoadImage.argtypes = [C.POINTER(DecoderCallbacks), C.c_void_p, C.c_size_t, C.POINTER(ErrorInfo)]
@@ -470,6 +470,19 @@ def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, widt
     data = C.string_at(out, n.value)
     _lib.JxlB200Free(out)
     return data
+
+
+def debug_parse_icc(icc):
+    """(3x3 matrix profile-RGB-linear -> linear sRGB, 3x256 tone curves) the encoder derives from a matrix/TRC ICC profile, or raises."""
+    b = bytes(icc)
+    m = (C.c_float * 9)()
+    lut = (C.c_float * 768)()
+    ei = ErrorInfo()
+    _lib.JxlB200DebugParseIcc.restype = C.c_int32
+    _lib.JxlB200DebugParseIcc.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(ErrorInfo)]
+    if not _lib.JxlB200DebugParseIcc(b, len(b), m, lut, C.byref(ei)):
+        raise FormatException("EncodeError", _message(ei) or "unsupported ICC profile")
+    return np.array(m, dtype=np.float64).reshape(3, 3), np.array(lut, dtype=np.float64).reshape(3, 256)
 
 
 def release_memory():

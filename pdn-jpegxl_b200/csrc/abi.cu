@@ -7,6 +7,7 @@
 #include "../../include/JxlFileTypeIO.h"
 #include "engine.h"
 #include "dev/kernels.h"
+#include "host/icc.h"
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
@@ -257,6 +258,14 @@ EncoderStatus JxlB200EncodeToMemory(const BitmapData* bitmap, const EncoderOptio
   return EncoderStatus_Ok;
 }
 void JxlB200Free(void* p) { free(p); }
+// Host-only: what the encoder reads out of a matrix/TRC ICC profile (SaveImage with metadata->iccProfile, lossy): matrix9 = profile RGB
+// (linear) -> linear sRGB, lut768 = the three tone curves sampled at v/255. Returns 0 and a message when the profile cannot be used.
+int32_t JxlB200DebugParseIcc(const uint8_t* icc, size_t iccSize, float* matrix9, float* lut768, ErrorInfo* errorInfo) {
+  if (!icc || !matrix9 || !lut768) return 0;
+  try { IccMatrixTrc m; std::string why; if (!ParseMatrixTrcIcc(icc, iccSize, &m, &why)) { SetErrorMessage(errorInfo, why); return 0; }
+    for (int i = 0; i < 9; i++) matrix9[i] = float(m.to_linear_srgb[i]); memcpy(lut768, m.lut, sizeof(m.lut)); return 1; }
+  catch (...) { return 0; }
+}
 // Returns the cached device and page-locked buffers of the calling thread's current device to the driver (after a large batch the
 // pools hold one buffer set per image that was in flight).
 void JxlB200ReleaseMemory(void) { try { cudaDeviceSynchronize(); TrimPools(); } catch (...) {} }

@@ -170,3 +170,44 @@ def test_band_layout_and_partition_are_host_only(pkg):
     assert (w, h) == (300, 300) and gdim in (128, 256, 512, 1024) and rows == -(-300 // gdim)
     assert pkg.band_partition(128, 8) == [(16 * r, 16 * r + 16) for r in range(8)]      # BASELINE config 5: rows [16r, 16r+16) on GPU r
     assert pkg.band_partition(5, 2) == [(0, 3), (3, 5)] and pkg.band_partition(1, 3) == [(0, 1), (0, 0), (0, 0)]
+
+
+def test_matrix_trc_icc_reading_for_lossy_encode(pkg):
+    """What SaveImage derives from an ICC source profile when it has to reach XYB without a CMS (host code, no GPU needed): the colorant
+    matrix to linear sRGB and the three tone curves, for 'para' types 0 and 3, a one-entry 'curv' gamma and a sampled 'curv' table."""
+    import struct, sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    import icc_util
+    v = np.arange(256) / 255.0
+    to_srgb = lambda prims: np.linalg.inv(icc_util.rgb_to_xyz(icc_util.SRGB_PRIMS, 0.3127, 0.3290)) @ icc_util.rgb_to_xyz(prims, 0.3127, 0.3290)
+    for curve, gamma in (("para", 2.2), ("curv1", 2.19921875), ("table", 2.4)):
+        m, lut = pkg.debug_parse_icc(icc_util.make_matrix_icc(icc_util.P3_PRIMS, gamma=gamma, curve=curve))
+        assert np.abs(m - to_srgb(icc_util.P3_PRIMS)).max() < 2e-3            # s15Fixed16 colorants + Bradford round trip
+        assert np.abs(lut - (v ** gamma)[None, :]).max() < (2e-4 if curve != "table" else 2e-3)
+    # an sRGB profile with the parametric sRGB curve (type 3) must come out as the identity matrix and the sRGB decoding curve
+    icc = bytearray(icc_util.make_matrix_icc(icc_util.SRGB_PRIMS, gamma=2.4, curve="para"))
+    p = icc_util.parse_icc(bytes(icc))
+    para3 = b"para" + b"\0" * 4 + struct.pack(">HH", 3, 0) + b"".join(icc_util.s15(x) for x in (2.4, 1 / 1.055, 0.055 / 1.055, 1 / 12.92, 0.04045))
+    # rebuild the profile with the longer curve element appended at the end and the three TRC tags pointing at it
+    n = struct.unpack(">I", icc[128:132])[0]
+    off = len(icc)
+    icc += para3
+    for i in range(n):
+        e = 132 + 12 * i
+        if icc[e + 1: e + 4] == b"TRC":
+            icc[e + 4: e + 12] = struct.pack(">II", off, len(para3))
+    icc[0:4] = struct.pack(">I", len(icc))
+    m, lut = pkg.debug_parse_icc(bytes(icc))
+    assert np.abs(m - np.eye(3)).max() < 2e-3
+    srgb = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+    assert np.abs(lut - srgb[None, :]).max() < 3e-4
+    # profiles the engine must refuse for lossy encoding
+    bad = bytearray(icc_util.make_matrix_icc(icc_util.P3_PRIMS)); bad[16:20] = b"CMYK"
+    with pytest.raises(pkg.FormatException):
+        pkg.debug_parse_icc(bytes(bad))
+    bad = bytearray(icc_util.make_matrix_icc(icc_util.P3_PRIMS)); bad[20:24] = b"Lab "
+    with pytest.raises(pkg.FormatException):
+        pkg.debug_parse_icc(bytes(bad))
+    with pytest.raises(pkg.FormatException):
+        pkg.debug_parse_icc(b"\0" * 64)
