@@ -211,3 +211,24 @@ def test_matrix_trc_icc_reading_for_lossy_encode(pkg):
         pkg.debug_parse_icc(bytes(bad))
     with pytest.raises(pkg.FormatException):
         pkg.debug_parse_icc(b"\0" * 64)
+
+
+def test_synthesised_profile_reads_back(pkg):
+    """The profile the decoder synthesises for an enum encoding (P3 primaries, Rec.709 curve) fed to the encoder-side reader gives back the
+    P3 -> sRGB matrix and the 709 decoding curve: the two host-side halves of the colour-profile handling agree with each other."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    import oracle_py as O
+    import icc_util
+    im = pkg.DecoderImage()
+    try:
+        pkg.JpegXLNative.LoadImage(O.encode(O.synthetic_image(32, 32, seed=5), lossless=True, primaries=11, tf=1), im)
+    except pkg.FormatException:
+        assert not pkg.cuda_available()[0]
+    m, lut = pkg.debug_parse_icc(im.icc_profile)
+    want = np.linalg.inv(icc_util.rgb_to_xyz(icc_util.SRGB_PRIMS, 0.3127, 0.3290)) @ icc_util.rgb_to_xyz(icc_util.P3_PRIMS, 0.3127, 0.3290)
+    assert np.abs(m - want).max() < 2e-3
+    v = np.arange(256) / 255.0
+    bt709 = np.where(v < 0.081, v / 4.5, ((v + 0.099) / 1.099) ** (1 / 0.45))
+    assert np.abs(lut - bt709[None, :]).max() < 3e-4
