@@ -69,8 +69,9 @@ inline uint32_t StreamIdModularGroup(const FrameHeader& f, uint32_t pass, uint32
 inline void DecodeLfGlobal(FrameState& fs, BitReader& br) {
   const FrameHeader& fh = fs.fh; const ImageMetadata& m = fs.meta;
   JXLO_CHECK(!(fh.flags & (kFlagPatches | kFlagSplines | kFlagNoise)), "patches/splines/noise are not supported");
+  // LfChannelDequantization comes first for EVERY frame encoding (Modular frames carry it too, unused)
+  if (!br.Bool()) for (int c = 0; c < 3; c++) { fs.lf_dequant[c] = br.F16() * (1.0f / 128.0f); JXLO_CHECK(fs.lf_dequant[c] >= 1e-8f, "lf dequant"); }
   if (fh.encoding == 0) {
-    if (!br.Bool()) for (int c = 0; c < 3; c++) { fs.lf_dequant[c] = br.F16() * (1.0f / 128.0f); JXLO_CHECK(fs.lf_dequant[c] >= 1e-8f, "lf dequant"); }
     fs.q.global_scale = br.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193));
     fs.q.quant_lf = br.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));
     if (!br.Bool()) {

@@ -262,7 +262,8 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
 
   // ---- sections
   { BitWriter& bw = sw.Get(0);   // LfGlobal
-    if (!p.lossless) { bw.Bool(true); bw.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193), pl.q.global_scale); bw.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1), pl.q.quant_lf); bw.Bool(true); bw.Bool(true); }
+    bw.Bool(true);   /* LfChannelDequantization all_default: present for Modular frames too */
+    if (!p.lossless) { bw.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193), pl.q.global_scale); bw.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1), pl.q.quant_lf); bw.Bool(true); bw.Bool(true); }
     bw.Bool(true); WriteCode(bw, tree_code); WriteTokens(bw, tree_code, tree_tokens); WriteCode(bw, mcode);
     if (!gimg.ch.empty()) { WriteGroupHeader(bw, gheader); if (global_n) WriteTokens(bw, mcode, global_tokens); } }
   GroupHeader plain; plain.use_global_tree = true;

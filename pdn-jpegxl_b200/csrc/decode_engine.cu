@@ -238,9 +238,10 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
   const ImageMetadata& m = hd.meta;
   JXLG_CHECK(!(fh.flags & (kFlagPatches | kFlagSplines | kFlagNoise)), "patches/splines/noise are not supported");
   float lf_dequant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256}; uint32_t global_scale = 1, quant_lf = 16; BlockCtxMap bctx; uint32_t color_factor = 84; float base_x = 0.f, base_b = 1.f; int32_t xlf = 0, blf = 0;
+  // LfChannelDequantization is read for every frame encoding: Modular frames carry the bundle too (unused there)
+  if (!br.Bool()) for (int c = 0; c < 3; c++) { lf_dequant[c] = br.F16() * (1.0f / 128.0f); JXLG_CHECK(lf_dequant[c] >= 1e-8f, "lf dequant"); }
   if (fh.encoding == 0) {
     JXLG_CHECK(!(fh.flags & kFlagUseLfFrame), "LF frames are not supported");
-    if (!br.Bool()) for (int c = 0; c < 3; c++) { lf_dequant[c] = br.F16() * (1.0f / 128.0f); JXLG_CHECK(lf_dequant[c] >= 1e-8f, "lf dequant"); }
     global_scale = br.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193)); quant_lf = br.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1));
     if (!br.Bool()) {
       bctx.num_lf_ctxs = 1; for (int j = 0; j < 3; j++) { uint32_t n = br.ReadBits(4); bctx.lf_thr[j].resize(n); for (auto& t : bctx.lf_thr[j]) t = UnpackSigned(br.U32(Bits(4), BitsOffset(8, 16), BitsOffset(16, 272), BitsOffset(32, 65808))); bctx.num_lf_ctxs *= n + 1; }
@@ -462,7 +463,11 @@ void DecodeJob::RunRender() {
     const bool filters = h.lpf.gab || h.lpf.epf_iters;
     if (big_blocks || (filters && unfused)) { d_xyb_tmp.Alloc(size_t(h.xpad) * h.ypad * 3 * 4); h.xyb_tmp = d_xyb_tmp.as<float>(); UploadFrame(); }
   }
-  static const int dbg_skip = getenv("JXLB200_DEBUG_SKIP") ? atoi(getenv("JXLB200_DEBUG_SKIP")) : 0;   // timing experiments only: 1 = no reconstruction, 2 = no render, 3 = neither
+#ifdef JXLB200_DEBUG   // timing experiments only (never in release builds: skipped stages leave invalid pixels): 1 = no reconstruction, 2 = no render, 3 = neither
+  static const int dbg_skip = getenv("JXLB200_DEBUG_SKIP") ? atoi(getenv("JXLB200_DEBUG_SKIP")) : 0;
+#else
+  const int dbg_skip = 0;
+#endif
   if (vardct && !(dbg_skip & 1)) LaunchReconstruct(d, h, stream);
   if (timed) cudaEventRecord(ev[3], stream);
   bool fused = false;

@@ -218,7 +218,8 @@ EncodeResult EncodeOnGpu(const EncodeRequest& req) {
     std::vector<BitWriter> secw(single ? 1 : nsec); auto W = [&](size_t i) -> BitWriter& { return single ? secw[0] : secw[i]; };
     GroupHeader plain; plain.use_global_tree = true; GroupHeader gheader = plain; if (lossless && ncolor == 3) { Transform t; t.id = 0; t.begin_c = 0; t.rct_type = 6; gheader.transforms.push_back(t); }
     { BitWriter& bw = W(0);
-      if (!lossless) { bw.Bool(true); bw.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193), global_scale); bw.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1), quant_lf); bw.Bool(true); bw.Bool(true); }
+      bw.Bool(true);   /* LfChannelDequantization all_default: present for Modular frames too */
+      if (!lossless) { bw.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193), global_scale); bw.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1), quant_lf); bw.Bool(true); bw.Bool(true); }
       bw.Bool(true); WriteCode(bw, tree_code); WriteTokens(bw, tree_code, tree_tokens); WriteCode(bw, mcode);
       if (nplanes > 0) { WriteGroupHeader(bw, gheader); if (global_has_modular) { const DEncStream& s = m_streams[first_group_stream]; AppendBits(bw, &bytes[s.byte_off], bits_m[first_group_stream]); } } }
     for (uint32_t g = 0; g < nlf; g++) { BitWriter& bw = W(1 + g); if (lossless) continue;

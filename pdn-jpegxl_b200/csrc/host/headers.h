@@ -208,7 +208,8 @@ inline void DeriveFrameDims(FrameHeader& f, const ImageMetadata& m) {
 }
 inline BlendingInfo ReadBlending(BitReader& br, bool have_ec, bool partial) {
   BlendingInfo b; b.mode = br.U32(Val(0), Val(1), Val(2), BitsOffset(2, 3)); JXLG_CHECK(b.mode <= 4, "blend mode");
-  if (have_ec && (b.mode == 2 || b.mode == 3)) { b.alpha_channel = br.U32(Val(0), Val(1), Val(2), BitsOffset(3, 3)); b.clamp = br.Bool(); }
+  if (have_ec && (b.mode == 2 || b.mode == 3)) b.alpha_channel = br.U32(Val(0), Val(1), Val(2), BitsOffset(3, 3));
+  if ((have_ec && (b.mode == 2 || b.mode == 3)) || b.mode == 4) b.clamp = br.Bool();
   if (b.mode != 0 || partial) b.source = br.ReadBits(2);
   return b;
 }
@@ -353,7 +354,7 @@ inline ContainerInfo ParseContainer(const uint8_t* d, size_t n) {
     uint64_t size = (uint64_t(d[pos]) << 24) | (d[pos + 1] << 16) | (d[pos + 2] << 8) | d[pos + 3]; size_t hdr = 8; Box b; memcpy(b.type, d + pos + 4, 4); b.type[4] = 0;
     if (size == 1) { JXLG_CHECK(pos + 16 <= n, "box header truncated"); size = 0; for (int i = 0; i < 8; i++) size = (size << 8) | d[pos + 8 + i]; hdr = 16; }
     else if (size == 0) size = n - pos;
-    JXLG_CHECK(size >= hdr && pos + size <= n, "box size"); b.data = d + pos + hdr; b.size = size - hdr;
+    JXLG_CHECK(size >= hdr && size <= uint64_t(n - pos), "box size");   /* written so that a 64-bit extended size cannot wrap: pos always advances by at least hdr */ b.data = d + pos + hdr; b.size = size - hdr;
     if (!strcmp(b.type, "jxlc")) { c.codestream.append(b.data, b.size); c.contiguous_offset = size_t(b.data - d); c.parts++; }
     else if (!strcmp(b.type, "jxlp")) { JXLG_CHECK(b.size >= 4 && !seen_last, "jxlp box"); if (b.data[0] & 0x80) seen_last = true; c.codestream.append(b.data + 4, b.size - 4); c.contiguous_offset = size_t(b.data + 4 - d); c.parts++; }
     c.boxes.push_back(b); pos += size;
