@@ -139,7 +139,7 @@ inline ImageMetadata ReadImageHeaders(BitReader& br) {
     if (m.cw_mask & 1) { m.up2.resize(15); for (auto& v : m.up2) v = br.F16(); }
     if (m.cw_mask & 2) { m.up4.resize(55); for (auto& v : m.up4) v = br.F16(); }
     if (m.cw_mask & 4) { m.up8.resize(210); for (auto& v : m.up8) v = br.F16(); }
-    br.Extensions();
+    // (CustomTransformData carries no extensions field)
   }
   if (m.ce.want_icc) m.icc = ReadIccStream(br);
   br.ZeroPadToByte();
@@ -319,7 +319,10 @@ inline Toc ReadToc(BitReader& br, const FrameHeader& f) {
   std::vector<size_t> sizes(n); for (auto& s : sizes) s = br.U32(Bits(10), BitsOffset(14, 1024), BitsOffset(22, 17408), BitsOffset(30, 4211712));
   br.ZeroPadToByte(); JXLO_CHECK(!br.overrun, "TOC truncated");
   t.offset.assign(n, 0); t.size.assign(n, 0); size_t pos = 0;
-  for (size_t i = 0; i < n; i++) { size_t logical = perm.empty() ? i : perm[i]; t.offset[logical] = pos; t.size[logical] = sizes[i]; pos += sizes[i]; }
+  // Sizes are coded in file order; the permutation maps a LOGICAL section to its file slot (libjxl's writer stores section i at
+  // slot permutation[i], and its reader takes offsets[permutation[i]] for section i).
+  std::vector<size_t> slot_pos(n); for (size_t i = 0; i < n; i++) { slot_pos[i] = pos; pos += sizes[i]; }
+  for (size_t i = 0; i < n; i++) { size_t slot = perm.empty() ? i : perm[i]; t.offset[i] = slot_pos[slot]; t.size[i] = sizes[slot]; }
   t.total = pos; return t;
 }
 inline void WriteToc(BitWriter& bw, const std::vector<size_t>& sizes) {

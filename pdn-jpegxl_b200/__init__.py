@@ -186,6 +186,7 @@ class DecoderLayerData:
         ncolor = {"Gray": 1, "Rgb": 3, "Cmyk": 4}[fmt]
         nch = ncolor + (1 if has_transparency else 0)
         arr = np.frombuffer(pixels, dtype=_DTYPES[representation]).reshape(height, width, nch)
+        self.interleaved = arr   # the native buffer as handed to setLayerData (tests compare it with the oracle's pixels)
         if fmt == "Cmyk" and representation != 0:
             raise FormatException("DecodeError", "unsupported CMYK channel representation")
         color = arr[..., :ncolor]

@@ -1,0 +1,133 @@
+"""Files assembled by the independent bit-level writer (tests/jxl_spec_writer.py) and the pixels each must decode to.
+
+Every case exercises codestream syntax that the oracle's and the product's readers share text for (SizeHeader forms,
+ImageMetadata fields, FrameHeader, TOC with and without a permutation, entropy-code headers, alias tables, prefix codes,
+MA trees, RCT, container boxes, a DC-only VarDCT frame). Used by the CPU tests (oracle + host-only PeekInfo) and by the
+GPU tests (LoadImage through the C ABI).
+"""
+import numpy as np
+
+import jxl_spec_writer as W
+
+
+def _planes(arr):
+    """HxWxC array -> list of C channels, each a list of rows of Python ints."""
+    a = np.asarray(arr)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    return [[[int(v) for v in row] for row in a[:, :, c]] for c in range(a.shape[2])]
+
+
+def _img(h, w, c, seed, lo=0, hi=255, smooth=True):
+    rng = np.random.default_rng(seed)
+    if not smooth:
+        return rng.integers(lo, hi + 1, size=(h, w, c)).astype(np.int64)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * (3 + k) + yy * (5 - k) + 17 * k) % (hi - lo + 1) for k in range(c)], axis=2)
+    noise = rng.integers(-6, 7, size=(h, w, c))
+    return np.clip(base + noise + lo, lo, hi).astype(np.int64)
+
+
+def cases():
+    """-> list of (name, file bytes, expected pixels (HxWxC, dtype of the reference's output), expected info dict)"""
+    out = []
+
+    # 1. gray 8-bit, "small" SizeHeader with an aspect ratio, single gradient leaf, flat 256-symbol ANS (trivial alias table)
+    g = _img(24, 32, 1, seed=1)          # 32 = 24 * 4 / 3: ratio 3
+    out.append(("gray8_small_ratio", W.modular_image(_planes(g), gray=True), g.astype(np.uint8), dict(width=32, height=24, format="Gray", num_channels=1)))
+
+    # 2. RGB 8-bit, explicit U32 sizes (not a multiple of 8), frame name, no RCT, random (noisy) content
+    a = _img(13, 21, 3, seed=2, smooth=False)
+    out.append(("rgb8_u32_size_named", W.modular_image(_planes(a), name=b"layer one"), a.astype(np.uint8), dict(width=21, height=13, format="Rgb", num_channels=3, name=b"layer one")))
+
+    # 3. RGB + 8-bit alpha (default ExtraChannelInfo), YCgCo RCT (type 6), tree splitting on property 0 (channel) and 9 (gradient)
+    a = _img(16, 16, 4, seed=3)
+    tree = W.Split(0, 2, W.Leaf(0, 1), W.Split(9, 40, W.Leaf(1, 5), W.Leaf(2, 4)))
+    out.append(("rgba8_rct6_tree", W.modular_image(_planes(a), alpha_bits=8, tree=tree, rct=(0, 6)), a.astype(np.uint8), dict(width=16, height=16, format="Rgb", num_channels=4, has_transparency=True)))
+
+    # 4. non-power-of-two flat ANS alphabet (needs the alias construction), 6-bit table, two-symbol and single-symbol clusters.
+    #    Leaves are numbered in breadth-first order: ctx 0 = channel 0 (flat 40-symbol alphabet, hybrid config 5/1/1),
+    #    ctx 1 = channel 2 (constant: single-symbol distribution), ctx 2 = channel 1 (two residual values: two-symbol distribution)
+    h, w = 12, 20
+    rng = np.random.default_rng(4)
+    c0 = rng.integers(0, 64, size=(h, w))
+    c1 = np.zeros((h, w), np.int64) + 77
+    c1[:, 1::2] += 1
+    c2 = np.zeros((h, w), np.int64) + 200
+    a = np.stack([c0, c1, c2], axis=2)
+    tree = W.Split(0, 0, W.Split(0, 1, W.Leaf(1, 0, offset=200), W.Leaf(2, 0, offset=77)), W.Leaf(0, 0))
+    code = W.EntropyCode([0, 1, 2], [("flat", 40), ("single", 0), ("two", 0, 2, 1365)], hybrids=[W.Hybrid(5, 1, 1), W.Hybrid(4, 2, 0), W.Hybrid(0, 0, 0)], log_alpha=6)
+    out.append(("rgb8_alias_tables", W.modular_image(_planes(a), tree=tree, data_code=code), a.astype(np.uint8), dict(width=w, height=h, format="Rgb", num_channels=3)))
+
+    # 5. simple prefix codes (2, 3 and 4 symbols) and leaf multipliers: ctx 0 = channel 0 (4 levels x 60), ctx 1 = channel 2 (2 levels x 255),
+    #    ctx 2 = channel 1 (3 levels x 100)
+    rng = np.random.default_rng(5)
+    a = np.stack([rng.integers(0, 4, size=(9, 14)) * 60, rng.integers(0, 3, size=(9, 14)) * 100, rng.integers(0, 2, size=(9, 14)) * 255], axis=2)
+    tree = W.Split(0, 0, W.Split(0, 1, W.Leaf(1, 0, multiplier=255), W.Leaf(2, 0, multiplier=100)), W.Leaf(0, 0, multiplier=60))
+    code = W.EntropyCode([0, 1, 2], [(0, 2, 4, 6), (0, 2), (0, 2, 4)], hybrids=[W.Hybrid(4, 1, 0)] * 3, use_prefix=True)
+    out.append(("rgb8_prefix_codes", W.modular_image(_planes(a), tree=tree, data_code=code), a.astype(np.uint8), dict(width=14, height=9, format="Rgb", num_channels=3)))
+
+    # 6. 16-bit RGB with 16-bit premultiplied alpha and orientation 6 (output is rotated); hybrid-uint tails in use
+    a = _img(10, 18, 4, seed=6, hi=65535)
+    a[..., 3] = np.maximum(a[..., 3], 30000)
+    f = W.modular_image(_planes(a), bits=16, alpha_bits=16, orientation=6, alpha_associated=True,
+                        data_code=W.EntropyCode([0], [("flat", 100)], hybrids=[W.Hybrid(4, 2, 0)], log_alpha=7))   # 100 symbols over 128 buckets: alias redirects
+    out.append(("rgba16_orient6_premul", f, ("premul16", a), dict(width=10, height=18, format="Rgb", num_channels=4, representation=1, has_transparency=True)))
+
+    # 7. multi-group frame (group size 128) with a real TOC, every group its own section
+    a = _img(150, 200, 3, seed=7)
+    out.append(("rgb8_multigroup_toc", W.modular_image(_planes(a), group_size_shift=0), a.astype(np.uint8), dict(width=200, height=150, format="Rgb", num_channels=3)))
+
+    # 8. the same with the sections stored in a permuted order (TOC permutation, Lehmer-coded)
+    nsec = 1 + 1 + 1 + 4
+    order = [0, 1, 2, 6, 4, 3, 5]
+    out.append(("rgb8_permuted_toc", W.modular_image(_planes(a), group_size_shift=0, toc_permutation=order), a.astype(np.uint8), dict(width=200, height=150, format="Rgb", num_channels=3)))
+    assert len(order) == nsec
+
+    # 9. CMYK: black extra channel (+ alpha), 8-bit; the reference inverts C, M, Y, K (N/Decoder/JxlDecoder.cpp:159-215)
+    a = _img(11, 15, 5, seed=9, smooth=False)
+    ecs = [dict(type=W.EC_BLACK, bits=8, name=b"K")]
+    f = W.modular_image(_planes(a), alpha_bits=8, extra=ecs)          # channel order in the file: R,G,B(=C,M,Y), alpha, black
+    want = np.concatenate([255 - a[..., 0:3], 255 - a[..., 4:5], a[..., 3:4]], axis=2).astype(np.uint8)
+    out.append(("cmyka8", f, want, dict(width=15, height=11, format="Cmyk", num_channels=4, has_transparency=True)))
+    return out
+
+
+def containerised():
+    """Container-level variants of case 2: jxlp split with metadata boxes between the parts, a jxll level box."""
+    name, cs, px, info = cases()[1]
+    exif = b"\x00\x00\x00\x00II*\x00\x08\x00\x00\x00\x00\x00"
+    xmp = b"<x:xmpmeta xmlns:x='adobe:ns:meta/'/>"
+    return [
+        ("jxlc_with_boxes", W.container(cs, boxes=[(b"Exif", exif), (b"xml ", xmp)], level=5), px, exif, [xmp]),
+        ("jxlp_split", W.container(cs, boxes=[(b"Exif", exif), (b"xml ", xmp), (b"xml ", xmp + b"2")], split_at=len(cs) // 3), px, exif, [xmp, xmp + b"2"]),
+    ]
+
+
+# ---- DC-only VarDCT frame: expected pixels from the published constants, computed here in float64
+OPSIN_INV = np.array([[11.031566901960783, -9.866943921568629, -0.16462299647058826],
+                      [-3.254147380392157, 4.418770392156863, -0.16462299647058826],
+                      [-3.6588512862745097, 2.7129230470588235, 1.9459282392156863]])
+OPSIN_BIAS = 0.0037930732552754493
+
+
+def vardct_dc_case(seed=11, xb=9, yb=7, xsize=70, ysize=52):
+    rng = np.random.default_rng(seed)
+    gs, qlf = 32768, 64
+    yy, xx = np.mgrid[0:yb, 0:xb]
+    qy = (40 + 6 * xx + 3 * yy + rng.integers(-3, 4, size=(yb, xb))).astype(np.int64)      # Y in about [0.2, 0.7]
+    qx = rng.integers(-6, 7, size=(yb, xb)).astype(np.int64)
+    qb = rng.integers(-20, 21, size=(yb, xb)).astype(np.int64)
+    f = W.vardct_dc_only([_planes(qx)[0], _planes(qy)[0], _planes(qb)[0]], xsize, ysize, global_scale=gs, quant_lf=qlf)
+    inv = 65536.0 / gs / qlf
+    Y = qy * (inv / 512)
+    X = qx * (inv / 4096)             # default chroma-from-luma: X gets 0 * Y, B gets 1 * Y
+    B = qb * (inv / 256) + Y
+    cb = np.cbrt(OPSIN_BIAS)
+    mix = np.stack([(Y + X + cb) ** 3 - OPSIN_BIAS, (Y - X + cb) ** 3 - OPSIN_BIAS, (B + cb) ** 3 - OPSIN_BIAS], axis=-1)
+    lin = mix @ OPSIN_INV.T
+    a = np.abs(lin)
+    srgb = np.where(a <= 0.0031308, 12.92 * a, 1.055 * np.power(a, 1 / 2.4) - 0.055) * np.sign(lin)
+    block = np.clip(srgb, 0, 1) * 255.0
+    full = np.repeat(np.repeat(block, 8, axis=0), 8, axis=1)[:ysize, :xsize]
+    return f, full      # float expected values: compare with |decoded - expected| <= 0.5 + eps
