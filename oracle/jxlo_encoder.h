@@ -17,6 +17,7 @@ struct EncodeParams {
   int force_strategy = -1;                // tile the frame with this AC strategy where it fits
   bool use_prefix = false; bool container = true; int modular_group_shift = 1; uint32_t orientation = 1; std::string frame_name;
   bool skip_lf_smoothing = false; int threads = 1;
+  int num_passes = 1, pass_shift = 1;     // 2 passes: pass 0 carries the quantised coefficients >> pass_shift, pass 1 the remainder (progressive files)
   // source description for non-8-bit sources (tests of 16-bit / float / HDR output paths)
   BitDepth bd; ColorEncoding ce; float intensity_target = 255.f; bool premultiplied = false; bool black_channel = false;
 };
@@ -120,6 +121,8 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
     if (epf < 0) { epf = 0; if (p.effort >= 5) { const float thr[3] = {0.7f, 1.5f, 4.0f}; for (float t : thr) if (p.distance >= t) epf++; } }
     fh.lf.gab = gab != 0; fh.lf.epf_iters = uint32_t(epf); if (p.skip_lf_smoothing) fh.flags |= kFlagSkipAdaptiveLfSmoothing;
   }
+  JXLO_CHECK(p.num_passes == 1 || p.num_passes == 2, "num_passes"); fh.passes.num_passes = uint32_t(p.num_passes); if (p.num_passes == 2) fh.passes.shift[0] = uint32_t(p.pass_shift);
+  const uint32_t np = fh.passes.num_passes;
   DeriveFrameDims(fh, m);
   const uint32_t nlf = fh.num_lf_groups, ng = fh.num_groups; const size_t nsec = NumTocEntries(fh);
   SectionWriter sw(nsec);
@@ -143,11 +146,11 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
     int gx = int(g % fh.xgroups), gy = int(g / fh.xgroups); ModularImage gi; gi.bitdepth = gimg.bitdepth;
     for (size_t c = global_n; c < gimg.ch.size(); c++) { const Channel& fc = gimg.ch[c]; int x0 = gx * gd, y0 = gy * gd; if (x0 >= fc.w || y0 >= fc.h) continue; int w = std::min(gd, fc.w - x0), h = std::min(gd, fc.h - y0);
       Channel ch(w, h); for (int y = 0; y < h; y++) memcpy(ch.row(y), fc.row(y0 + y) + x0, sizeof(int32_t) * size_t(w)); gi.ch.push_back(std::move(ch)); }
-    if (gi.ch.empty()) return; mg_present[g] = 1; ModularTokenize(gi, 0, gi.ch.size(), StreamIdModularGroup(fh, 0, uint32_t(g)), tree, &mg_tokens[g]);
+    if (gi.ch.empty()) return; mg_present[g] = 1; ModularTokenize(gi, 0, gi.ch.size(), StreamIdModularGroup(fh, np - 1, uint32_t(g)), tree, &mg_tokens[g]);   // shift-0 channels belong to the last pass
   });
 
   // ---- VarDCT analysis
-  VarDctPlan pl; std::vector<std::vector<Token>> lf_tokens(nlf), hfmeta_tokens(nlf), ac_tokens(ng); std::vector<uint32_t> hfmeta_nb(nlf, 0);
+  VarDctPlan pl; std::vector<std::vector<Token>> lf_tokens(nlf), hfmeta_tokens(nlf), ac_tokens(size_t(ng) * np); std::vector<uint32_t> hfmeta_nb(nlf, 0);
   if (!p.lossless) {
     pl.xb = int(fh.xblocks); pl.yb = int(fh.yblocks); pl.xpad = pl.xb * 8; pl.ypad = pl.yb * 8; pl.xt = (pl.xb + 7) / 8; pl.yt = (pl.yb + 7) / 8;
     Plane xyb[3]; for (auto& pln : xyb) pln = Plane(pl.xpad, pl.ypad);
@@ -217,7 +220,7 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
           int fx = 0, fb = 0; if (syy > 1e-12) { fx = int(std::lrint(84.0 * (sxy / syy))); fb = int(std::lrint(84.0 * (sby / syy - 1.0))); }
           pl.ytox[size_t(ty) * pl.xt + tx] = int8_t(std::max(-128, std::min(127, fx))); pl.ytob[size_t(ty) * pl.xt + tx] = int8_t(std::max(-128, std::min(127, fb))); }
       }
-      ColorCorrelation cc; std::vector<uint16_t> nzs[3]; for (auto& v : nzs) v.assign(32 * 32, 0); std::vector<Token>& out = ac_tokens[g];
+      ColorCorrelation cc; std::vector<uint16_t> nzs_all[2][3]; for (auto& a : nzs_all) for (auto& v : a) v.assign(32 * 32, 0);
       for (const Blk& b : blocks) {
         size_t o = size_t(cy0 + b.by) * pl.xb + cx0 + b.bx; int s = b.s, bw = kCoveredX[s], bh = kCoveredY[s]; uint32_t covered = uint32_t(bw * bh), log2c = uint32_t(FloorLog2(covered)), size = covered * 64; int ord = kStrategyOrder[s], t = kQuantTableOf[s];
         int SW = std::max(bw, bh) * 8, lr = std::min(bw, bh), lc = std::max(bw, bh);
@@ -226,6 +229,9 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
         for (uint32_t k = 0; k < size; k++) { int r = int(k) / SW, c2 = int(k) % SW; if (r < lr && c2 < lc) continue;
           float sy = dq[size + k] * scale; q[1][k] = QuantizeCoef(b.co[1][k], 1.0f / sy); float ydq = AdjustQuantBias(q[1][k], qbias[1], qbias[3]) * sy;
           q[0][k] = QuantizeCoef(b.co[0][k] - kx * ydq, 1.0f / (dq[k] * scale * xm)); q[2][k] = QuantizeCoef(b.co[2][k] - kb * ydq, 1.0f / (dq[2 * size + k] * scale * bm)); }
+        std::vector<int32_t> qfull[3] = {q[0], q[1], q[2]};
+        for (uint32_t pass = 0; pass < np; pass++) { std::vector<Token>& out = ac_tokens[size_t(pass) * ng + g]; std::vector<uint16_t>* nzs = nzs_all[pass];
+        if (np == 2) for (int c = 0; c < 3; c++) for (uint32_t k = 0; k < size; k++) { int32_t hi = qfull[c][k] >> p.pass_shift; q[c][k] = pass == 0 ? hi : qfull[c][k] - (hi << p.pass_shift); }
         for (int ci = 0; ci < 3; ci++) { int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; const std::vector<uint32_t>& order = natural[ord];
           uint32_t nz = 0; for (uint32_t k = covered; k < size; k++) nz += q[c][order[k]] != 0;
           uint32_t pred; { uint16_t* z = nzs[c].data(); int by = b.by, bx = b.bx; if (bx == 0) pred = by == 0 ? 32 : z[(by - 1) * 32 + bx]; else if (by == 0) pred = z[by * 32 + bx - 1]; else pred = (uint32_t(z[(by - 1) * 32 + bx]) + z[by * 32 + bx - 1] + 1) / 2; }
@@ -233,6 +239,7 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
           { uint16_t v = uint16_t((nz + covered - 1) >> log2c); for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) nzs[c][(b.by + iy) * 32 + b.bx + ix] = v; }
           uint32_t histo = nbctx * kNonZeroBuckets + kZeroDensityContextCount * bc, prev = nz > size / 16 ? 0 : 1;
           for (uint32_t k = covered; k < size && nz != 0; k++) { int32_t v = q[c][order[k]]; out.push_back({histo + ZeroDensityContext(nz, k, covered, log2c, prev), PackSigned(v)}); prev = v != 0; nz -= prev; } }
+        }
       }
     });
     // LF quantisation + tokens, HF metadata tokens (per LF group)
@@ -257,8 +264,8 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
   // ---- entropy codes
   std::vector<const std::vector<Token>*> mstreams; mstreams.push_back(&global_tokens); for (auto& t : lf_tokens) mstreams.push_back(&t); for (auto& t : hfmeta_tokens) mstreams.push_back(&t); for (auto& t : mg_tokens) mstreams.push_back(&t);
   EncCode tree_code = BuildCode({&tree_tokens}, 6, topt); EncCode mcode = BuildCode(mstreams, NumLeaves(tree), mopt);
-  EncCode ac_code; BlockCtxMap bctx0;
-  if (!p.lossless) { std::vector<const std::vector<Token>*> as; for (auto& t : ac_tokens) as.push_back(&t); EncOptions aopt; aopt.cfg = HybridCfg{4, 2, 0}; aopt.use_prefix = p.use_prefix; aopt.max_clusters = 64; ac_code = BuildCode(as, size_t(495) * bctx0.num_ctxs, aopt); }
+  EncCode ac_code[2]; BlockCtxMap bctx0;
+  if (!p.lossless) for (uint32_t pass = 0; pass < np; pass++) { std::vector<const std::vector<Token>*> as; for (uint32_t g = 0; g < ng; g++) as.push_back(&ac_tokens[size_t(pass) * ng + g]); EncOptions aopt; aopt.cfg = HybridCfg{4, 2, 0}; aopt.use_prefix = p.use_prefix; aopt.max_clusters = 64; ac_code[pass] = BuildCode(as, size_t(495) * bctx0.num_ctxs, aopt); }
 
   // ---- sections
   { BitWriter& bw = sw.Get(0);   // LfGlobal
@@ -272,10 +279,10 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
       int gx = int(g % fh.xlfgroups), gy = int(g / fh.xlfgroups), w = std::min(256, pl.xb - gx * 256), h = std::min(256, pl.yb - gy * 256);
       bw.Write(CeilLog2(uint64_t(w) * h), hfmeta_nb[g] - 1); WriteGroupHeader(bw, plain); WriteTokens(bw, mcode, hfmeta_tokens[g]); } }
   { BitWriter& bw = sw.Get(1 + nlf);   // HfGlobal
-    if (!p.lossless) { bw.Bool(true); bw.Write(CeilLog2(ng), 0); bw.U32(Val(0x5F), Val(0x13), Val(0), Bits(13), 0); WriteCode(bw, ac_code); } }
-  for (uint32_t g = 0; g < ng; g++) { BitWriter& bw = sw.Get(2 + nlf + g);
-    if (!p.lossless) WriteTokens(bw, ac_code, ac_tokens[g]);
-    if (mg_present[g]) { WriteGroupHeader(bw, plain); WriteTokens(bw, mcode, mg_tokens[g]); } }
+    if (!p.lossless) { bw.Bool(true); bw.Write(CeilLog2(ng), 0); for (uint32_t pass = 0; pass < np; pass++) { bw.U32(Val(0x5F), Val(0x13), Val(0), Bits(13), 0); WriteCode(bw, ac_code[pass]); } } }
+  for (uint32_t pass = 0; pass < np; pass++) for (uint32_t g = 0; g < ng; g++) { BitWriter& bw = sw.Get(2 + nlf + size_t(pass) * ng + g);
+    if (!p.lossless) WriteTokens(bw, ac_code[pass], ac_tokens[size_t(pass) * ng + g]);
+    if (mg_present[g] && pass + 1 == np) { WriteGroupHeader(bw, plain); WriteTokens(bw, mcode, mg_tokens[g]); } }
 
   // ---- assemble codestream
   BitWriter cs; cs.Write(16, 0x0AFF); WriteImageHeaders(cs, m); WriteFrameHeader(cs, fh, m);

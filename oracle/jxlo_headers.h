@@ -278,7 +278,9 @@ inline void WriteFrameHeader(BitWriter& bw, const FrameHeader& f, const ImageMet
   bw.U32(Val(1), Val(2), Val(4), Val(8), 1); for (size_t i = 0; i < m.ec.size(); i++) bw.U32(Val(1), Val(2), Val(4), Val(8), 1);
   if (f.encoding == 1) bw.Write(2, f.group_size_shift);
   if (f.encoding == 0 && m.xyb_encoded) { bw.Write(3, f.x_qm_scale); bw.Write(3, f.b_qm_scale); }
-  bw.U32(Val(1), Val(2), Val(3), BitsOffset(3, 4), 1);   // single pass
+  bw.U32(Val(1), Val(2), Val(3), BitsOffset(3, 4), f.passes.num_passes);
+  if (f.passes.num_passes != 1) { bw.U32(Val(0), Val(1), Val(2), BitsOffset(1, 3), f.passes.num_ds); for (uint32_t i = 0; i + 1 < f.passes.num_passes; i++) bw.Write(2, f.passes.shift[i]);
+    for (uint32_t i = 0; i < f.passes.num_ds; i++) bw.U32(Val(1), Val(2), Val(4), Val(8), f.passes.downsample[i]); for (uint32_t i = 0; i < f.passes.num_ds; i++) bw.U32(Val(0), Val(1), Val(2), Bits(3), f.passes.last_pass[i]); }
   bw.Bool(false);                                         // no crop
   bw.U32(Val(0), Val(1), Val(2), BitsOffset(2, 3), 0); for (size_t i = 0; i < m.ec.size(); i++) bw.U32(Val(0), Val(1), Val(2), BitsOffset(2, 3), 0);
   bw.Bool(true);                                          // is_last

@@ -445,8 +445,12 @@ def load_image_bgra(data):
     return out
 
 
-def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, width=None, height=None, stride=None):
-    if device_ptr is None:
+def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, width=None, height=None, stride=None, host_array=None):
+    """host_array: a 2-D uint8 array of `height` rows of `stride` bytes (BitmapData with stride > 4*width, N/Common.h:17-23)."""
+    if host_array is not None:
+        assert host_array.dtype == np.uint8 and host_array.flags.c_contiguous and host_array.shape == (height, stride)
+        bitmap = BitmapData(host_array.ctypes.data, width, height, stride)
+    elif device_ptr is None:
         surf = np.ascontiguousarray(surface_bgra, dtype=np.uint8)
         h, w, _ = surf.shape
         bitmap = BitmapData(surf.ctypes.data, w, h, surf.strides[0])

@@ -28,7 +28,7 @@ class EncodeParams(C.Structure):
     _fields_ = [("distance", C.c_float)] + [(n, C.c_int32) for n in (
         "effort", "lossless", "gab", "epf", "varblocks", "cfl", "adaptive_quant", "force_strategy", "use_prefix", "container",
         "modular_group_shift", "orientation", "skip_lf_smoothing", "threads", "bits", "exp_bits", "color_space", "white_point",
-        "primaries", "tf", "intent")] + [("intensity_target", C.c_float), ("premultiplied", C.c_int32), ("black_channel", C.c_int32)]
+        "primaries", "tf", "intent")] + [("intensity_target", C.c_float), ("premultiplied", C.c_int32), ("black_channel", C.c_int32), ("num_passes", C.c_int32), ("pass_shift", C.c_int32)]
 
 
 _lib = None
