@@ -17,6 +17,8 @@
 #include <map>
 #include <chrono>
 #include <cstdio>
+#include <mutex>
+#include <stdexcept>
 
 using namespace jxlgpu;
 
@@ -161,76 +163,129 @@ DecoderStatus JxlB200DecodeBand(int32_t device, const uint8_t* data, size_t data
   return DecoderStatus_Ok;
 }
 
-DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes, uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
-                                 int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, DecoderStatus* statuses, ErrorInfo* errorInfo) {
-  if (!datas || !dataSizes || !outputs || !outputBytes || count < 0) return DecoderStatus_NullParameter;
-  DecoderStatus first = DecoderStatus_Ok;
+// One shard of a batch: images [begin, end) of the caller's arrays, decoded by the three-phase pipeline below on `nstreams` streams owned
+// by this shard. Runs on its own host thread (see JxlB200DecodeBatch): the enqueue work of an image (header parse, table building,
+// ~40 CUDA calls) costs more host time than the image costs the GPU, so one enqueue thread caps a batch at about 1.2 images/ms.
+struct BatchArgs {
+  int32_t device, count; const uint8_t* const* datas; const size_t* dataSizes; uint8_t* const* outputs; const size_t* outputBytes;
+  int32_t bgra, hostInputs, hostOutputs; DecoderStatus* statuses;
+};
+struct ShardResult { DecoderStatus first = DecoderStatus_Ok; std::string message; };
+
+// Streams are created once per (device, shard slot) and reused by later batches (stream creation is not free).
+static std::vector<cudaStream_t>& ShardStreams(int device, int slot, int want) {
+  static std::mutex mu; static std::map<std::pair<int, int>, std::vector<cudaStream_t>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  std::vector<cudaStream_t>& v = cache[std::make_pair(device, slot)];
+  while (int(v.size()) < want) {
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) throw std::runtime_error("cudaStreamCreate failed");
+    v.push_back(st);
+  }
+  return v;
+}
+
+static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int nstreams, int batch_lanes, int bundle_size, size_t reserve_sets, ShardResult* out) {
+  const int count = end - begin;
+  if (count <= 0) return;
+  void* pin = nullptr; size_t pin_bytes = 0;
+  std::vector<cudaEvent_t> in_ready;
+  struct EventGuard { std::vector<cudaEvent_t>& v; ~EventGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); } } in_ready_guard{in_ready};
+  std::vector<uint8_t> finished(size_t(count), 0);
+  auto record = [&](int idx, DecoderStatus st, const std::string& msg) {
+    if (a.statuses) a.statuses[idx] = st;
+    finished[size_t(idx - begin)] = 1;
+    if (st != DecoderStatus_Ok && out->first == DecoderStatus_Ok) { out->first = st; out->message = msg; }
+  };
   try {
-    std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return DecoderStatus_DecodeError; }
-    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
-    int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 256)); int cur_dev = 0; cudaGetDevice(&cur_dev);   // maxInFlight counts streams (bundles) in flight
-    // streams are created once per device and thread and reused by later batches (stream creation is not free)
-    static thread_local std::map<int, std::vector<cudaStream_t>> stream_cache; std::vector<cudaStream_t>& all_streams = stream_cache[cur_dev];
-    while (int(all_streams.size()) < nstreams + 1) { cudaStream_t s = nullptr; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaStreamCreate failed"); return DecoderStatus_DecodeError; } all_streams.push_back(s); }
-    cudaStream_t copy_stream = all_streams[0]; std::vector<cudaStream_t> streams(all_streams.begin() + 1, all_streams.begin() + 1 + nstreams); void* pin = nullptr; size_t pin_bytes = 0;
-    const int batch_lanes = (count >= 64 && nstreams >= 32) ? 16 : (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
-    static const int env_bundle = getenv("JXLB200_BUNDLE") ? atoi(getenv("JXLB200_BUNDLE")) : 0;
-    const int bundle_size = std::max(1, std::min(env_bundle > 0 ? env_bundle : ((count >= 64 && nstreams >= 32) ? 2 : 1), kMaxBundle));   // images per stream / per entropy launch
-    struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; cudaStream_t stream = nullptr; };
-    std::vector<size_t> in_off(count + 1, 0); const uint8_t* host_in = nullptr;
+    if (a.device >= 0 && cudaSetDevice(a.device) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed");
+    int cur_dev = 0; cudaGetDevice(&cur_dev);
+    std::vector<cudaStream_t>& all_streams = ShardStreams(cur_dev, slot, nstreams + 1);
+    cudaStream_t copy_stream = all_streams[0];
+    std::vector<cudaStream_t> free_streams(all_streams.rbegin(), all_streams.rbegin() + nstreams);
+    struct InFlight { int idx; std::shared_ptr<DecodeJob> job; DecodeResult res; bool direct = false; };
+    std::vector<size_t> in_off(size_t(count) + 1, 0); const uint8_t* host_in = nullptr;
     // Device-resident inputs: the headers are parsed on the host, so every file comes back once through one pinned buffer. The copies
     // are queued up front on their own stream, one event per file, and a file is only waited for when its turn to be parsed comes.
-    std::vector<cudaEvent_t> in_ready;
-    struct EventGuard { std::vector<cudaEvent_t>& v; ~EventGuard() { for (cudaEvent_t e : v) cudaEventDestroy(e); } } in_ready_guard{in_ready};
-    if (!hostInputs) { for (int i = 0; i < count; i++) in_off[i + 1] = in_off[i] + ((dataSizes[i] + 63) & ~size_t(63));
-      pin_bytes = in_off[count] + 64; pin = PinnedGet(pin_bytes); in_ready.resize(count, nullptr);
-      for (int i = 0; i < count; i++) { cudaMemcpyAsync(static_cast<uint8_t*>(pin) + in_off[i], datas[i], dataSizes[i], cudaMemcpyDeviceToHost, copy_stream);
-        if (cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(in_ready[i], copy_stream) != cudaSuccess) { SetErrorMessage(errorInfo, "cannot read device inputs"); if (pin) PinnedPut(pin, pin_bytes); return DecoderStatus_DecodeError; } }
-      host_in = static_cast<uint8_t*>(pin); }
+    if (!a.hostInputs) {
+      for (int i = 0; i < count; i++) in_off[i + 1] = in_off[i] + ((a.dataSizes[begin + i] + 63) & ~size_t(63));
+      pin_bytes = in_off[count] + 64; pin = PinnedGet(pin_bytes); in_ready.resize(size_t(count), nullptr);
+      for (int i = 0; i < count; i++) {
+        cudaMemcpyAsync(static_cast<uint8_t*>(pin) + in_off[i], a.datas[begin + i], a.dataSizes[begin + i], cudaMemcpyDeviceToHost, copy_stream);
+        if (cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(in_ready[i], copy_stream) != cudaSuccess)
+          throw std::runtime_error("cannot read device inputs");
+      }
+      host_in = static_cast<uint8_t*>(pin);
+    }
     // host outputs that are page-locked receive the pixels directly (no staging copy)
-    std::vector<uint8_t> out_is_pinned(count, 0);
-    if (hostOutputs) for (int i = 0; i < count; i++) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, outputs[i]) == cudaSuccess && at.type == cudaMemoryTypeHost) out_is_pinned[i] = 1; else cudaGetLastError(); }
-    const bool trace = getenv("JXLB200_TRACE") != nullptr; double acc_t[5] = {0, 0, 0, 0, 0}; double t_enq = 0, t_ret = 0, t_idle = 0; auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    std::vector<uint8_t> out_is_pinned(size_t(count), 0);
+    if (a.hostOutputs) for (int i = 0; i < count; i++) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, a.outputs[begin + i]) == cudaSuccess && at.type == cudaMemoryTypeHost) out_is_pinned[i] = 1; else cudaGetLastError();
+    }
+    const bool trace = getenv("JXLB200_TRACE") != nullptr; double t_enq = 0, t_ret = 0, t_idle = 0;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     // Three-phase pipeline per image (LF entropy | AC entropy | reconstruction + render): a phase is enqueued only once the image's
     // stream has drained, so a kernel waiting on a 40 ms predecessor never sits at the head of a hardware queue shared with other
     // streams (there are 32 queues). Images travel in bundles of `bundle_size` that share a stream and whose LF / AC entropy kernels
     // are one multi-image launch each: the device holds at most 128 resident grids, and an image keeps one for ~70 ms.
     // q1/q2/q3 hold the bundles whose phase 1/2/3 is running.
     struct Bundle { std::vector<std::unique_ptr<InFlight>> items; cudaStream_t stream = nullptr; };
-    std::deque<std::unique_ptr<Bundle>> q1, q2, q3; std::vector<cudaStream_t> free_streams(streams.rbegin(), streams.rend()); int next = 0, done = 0;
+    std::deque<std::unique_ptr<Bundle>> q1, q2, q3; int next = 0, done = 0;
     auto finish = [&](InFlight& f) {   // records the status of a finished or failed image
       DecoderStatus st = DecoderStatus(f.res.status);
-      if (st == DecoderStatus_Ok) { if (f.res.pixel_bytes > outputBytes[f.idx]) st = DecoderStatus_InvalidParameter; else if (!f.direct) memcpy(outputs[f.idx], f.res.pixels, f.res.pixel_bytes); }
-      else if (first == DecoderStatus_Ok) SetErrorMessage(errorInfo, f.res.message);
-      if (trace) { const StageTimes& t = f.res.times; acc_t[0] += t.lf; acc_t[1] += t.ac; acc_t[2] += t.recon; acc_t[3] += t.filters + t.output; acc_t[4] += t.total; }
-      if (statuses) statuses[f.idx] = st; if (st != DecoderStatus_Ok && first == DecoderStatus_Ok) first = st;
+      if (st == DecoderStatus_Ok) {
+        if (f.res.pixel_bytes > a.outputBytes[f.idx]) st = DecoderStatus_InvalidParameter;
+        else if (!f.direct) memcpy(a.outputs[f.idx], f.res.pixels, f.res.pixel_bytes);
+      }
+      record(f.idx, st, f.res.message);
       f.job.reset(); f.res.job.reset(); done++;
     };
     auto idle = [](const Bundle& b) { return cudaStreamQuery(b.stream) != cudaErrorNotReady; };
     auto jobs_of = [](Bundle& b) { std::vector<std::shared_ptr<DecodeJob>> v; for (auto& it : b.items) v.push_back(it->job); return v; };
     auto next_phase = [&](Bundle& b, int phase) {   // enqueue `phase` for every image of the bundle; images that fail are finished and dropped
-      for (size_t k = 0; k < b.items.size();) { InFlight& f = *b.items[k]; if (DecodeEnqueuePhase(f.job, phase, &f.res)) k++; else { finish(f); b.items.erase(b.items.begin() + k); } }
+      for (size_t k = 0; k < b.items.size();) {
+        InFlight& f = *b.items[k];
+        if (DecodeEnqueuePhase(f.job, phase, &f.res)) k++; else { finish(f); b.items.erase(b.items.begin() + k); }
+      }
       if (phase == 2) DecodeBundleLaunch(jobs_of(b), 2);
     };
     auto advance = [&]() {   // moves bundles whose current phase has drained to the next one (polling: a blocking wait on one stream would stall all others)
       bool progressed = false; const size_t kWindow = 24;   // bundles finish roughly in order; look a little past the front of each queue
-      for (size_t k = 0; k < std::min(kWindow, q3.size());) { if (!idle(*q3[k])) { k++; continue; } Bundle& b = *q3[k]; for (auto& f : b.items) { DecodeFinish(f->job, &f->res); finish(*f); } free_streams.push_back(b.stream); q3.erase(q3.begin() + k); progressed = true; }
-      for (size_t k = 0; k < std::min(kWindow, q2.size());) { if (!idle(*q2[k])) { k++; continue; } std::unique_ptr<Bundle> b = std::move(q2[k]); q2.erase(q2.begin() + k); progressed = true; next_phase(*b, 3); if (b->items.empty()) free_streams.push_back(b->stream); else q3.push_back(std::move(b)); }
-      for (size_t k = 0; k < std::min(kWindow, q1.size());) { if (!idle(*q1[k])) { k++; continue; } std::unique_ptr<Bundle> b = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true; next_phase(*b, 2); if (b->items.empty()) free_streams.push_back(b->stream); else q2.push_back(std::move(b)); }
+      for (size_t k = 0; k < std::min(kWindow, q3.size());) {
+        if (!idle(*q3[k])) { k++; continue; }
+        Bundle& b = *q3[k];
+        for (auto& f : b.items) { DecodeFinish(f->job, &f->res); finish(*f); }
+        free_streams.push_back(b.stream); q3.erase(q3.begin() + k); progressed = true;
+      }
+      for (size_t k = 0; k < std::min(kWindow, q2.size());) {
+        if (!idle(*q2[k])) { k++; continue; }
+        std::unique_ptr<Bundle> b = std::move(q2[k]); q2.erase(q2.begin() + k); progressed = true;
+        next_phase(*b, 3);
+        if (b->items.empty()) free_streams.push_back(b->stream); else q3.push_back(std::move(b));
+      }
+      for (size_t k = 0; k < std::min(kWindow, q1.size());) {
+        if (!idle(*q1[k])) { k++; continue; }
+        std::unique_ptr<Bundle> b = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true;
+        next_phase(*b, 2);
+        if (b->items.empty()) free_streams.push_back(b->stream); else q2.push_back(std::move(b));
+      }
       return progressed;
     };
-    bool reserved = false;
+    bool reserved = reserve_sets == 0;
     while (done < count) {
       double t0 = now(); bool progressed = advance(); t_ret += now() - t0;
       if (next < count && !free_streams.empty()) {
-        t0 = now(); std::unique_ptr<Bundle> b(new Bundle); b->stream = free_streams.back(); free_streams.pop_back();
+        t0 = now();
+        std::unique_ptr<Bundle> b(new Bundle); b->stream = free_streams.back(); free_streams.pop_back();
         for (int k = 0; k < bundle_size && next < count; k++) {
-          const int i = next++; std::unique_ptr<InFlight> f(new InFlight); f->idx = i; f->stream = b->stream;
-          DecodeRequest req; req.bgra = bgra != 0; req.device_output = !hostOutputs; req.size = dataSizes[i]; req.out_capacity = outputBytes[i]; req.ac_lanes = batch_lanes;
-          if (hostInputs) req.data = datas[i]; else { cudaEventSynchronize(in_ready[i]); req.data = host_in + in_off[i]; req.device_input = datas[i]; }
-          if (!hostOutputs) { req.out_device = outputs[i]; f->direct = true; } else if (out_is_pinned[i]) { req.out_pinned = outputs[i]; f->direct = true; }
+          const int li = next++, i = begin + li;
+          std::unique_ptr<InFlight> f(new InFlight); f->idx = i;
+          DecodeRequest req; req.bgra = a.bgra != 0; req.device_output = !a.hostOutputs; req.size = a.dataSizes[i]; req.out_capacity = a.outputBytes[i]; req.ac_lanes = batch_lanes;
+          if (a.hostInputs) req.data = a.datas[i]; else { cudaEventSynchronize(in_ready[li]); req.data = host_in + in_off[li]; req.device_input = a.datas[i]; }
+          if (!a.hostOutputs) { req.out_device = a.outputs[i]; f->direct = true; } else if (out_is_pinned[li]) { req.out_pinned = a.outputs[i]; f->direct = true; }
           f->job = DecodeEnqueue(req, b->stream, &f->res, true, bundle_size > 1);
-          if (f->job && !reserved) { reserved = true; DecodeReservePools(f->job, size_t(std::min(count, nstreams * bundle_size)) - 1); }   // the first image tells the buffer sizes of the batch
+          if (f->job && !reserved) { reserved = true; DecodeReservePools(f->job, reserve_sets); }   // the first image tells the buffer sizes of the batch
           if (f->job) b->items.push_back(std::move(f)); else finish(*f);
         }
         if (bundle_size > 1) DecodeBundleLaunch(jobs_of(*b), 1);
@@ -238,12 +293,47 @@ DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* c
         if (b->items.empty()) free_streams.push_back(b->stream); else q1.push_back(std::move(b));
       } else if (!progressed) { t0 = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); t_idle += now() - t0; }
     }
-    if (trace) { DumpHostTrace(); DumpPoolStats(); }
-    if (trace && count) fprintf(stderr, "[jxlb200] GPU ms/image under load: lf %.2f ac %.2f recon %.2f render %.2f total %.2f\n", acc_t[0] / count, acc_t[1] / count, acc_t[2] / count, acc_t[3] / count, acc_t[4] / count);
-    if (trace) fprintf(stderr, "[jxlb200] batch of %d: host parse + LF phase %.2f ms (%.2f ms/image), polling + later phases + retire %.2f ms, idle (GPU-bound) %.2f ms\n", count, t_enq, t_enq / std::max(count, 1), t_ret, t_idle);
-    if (pin) PinnedPut(pin, pin_bytes);
+    if (trace) { DumpHostTrace(); if (slot == 0) DumpPoolStats(); }
+    if (trace) fprintf(stderr, "[jxlb200] shard %d, %d images: host parse + LF phase %.2f ms (%.2f ms/image), polling + later phases + retire %.2f ms, idle (GPU-bound) %.2f ms\n", slot, count, t_enq, t_enq / std::max(count, 1), t_ret, t_idle);
+  } catch (const std::exception& e) {
+    // Work may still be running on this shard's streams and writing into caller-owned buffers: wait for it before returning them.
+    cudaDeviceSynchronize(); cudaGetLastError();
+    const DecoderStatus st = dynamic_cast<const std::bad_alloc*>(&e) ? DecoderStatus_OutOfMemory : DecoderStatus_DecodeError;
+    for (int i = begin; i < end; i++) if (!finished[size_t(i - begin)]) record(i, st, e.what());
+  } catch (...) {
+    cudaDeviceSynchronize(); cudaGetLastError();
+    for (int i = begin; i < end; i++) if (!finished[size_t(i - begin)]) record(i, DecoderStatus_DecodeError, "batch decode failed");
+  }
+  if (pin) PinnedPut(pin, pin_bytes);
+}
+
+DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes, uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
+                                 int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, DecoderStatus* statuses, ErrorInfo* errorInfo) {
+  if (!datas || !dataSizes || !outputs || !outputBytes || count < 0) return DecoderStatus_NullParameter;
+  try {
+    std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return DecoderStatus_DecodeError; }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
+    const int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 256));   // maxInFlight counts streams (bundles) in flight
+    const int batch_lanes = (count >= 64 && nstreams >= 32) ? 16 : (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
+    static const int env_bundle = getenv("JXLB200_BUNDLE") ? atoi(getenv("JXLB200_BUNDLE")) : 0;
+    const int bundle_size = std::max(1, std::min(env_bundle > 0 ? env_bundle : ((count >= 64 && nstreams >= 32) ? 2 : 1), kMaxBundle));   // images per stream / per entropy launch
+    // Host threads: the per-image enqueue work is split over `shards` threads, each with its own share of the streams.
+    const int env_threads = getenv("JXLB200_HOST_THREADS") ? atoi(getenv("JXLB200_HOST_THREADS")) : 0;   // read per call (cheap): lets a caller tune it between batches
+    int hw = int(std::thread::hardware_concurrency()); if (hw <= 0) hw = 4;
+    int shards = env_threads > 0 ? env_threads : std::min(4, std::max(1, hw / 2));
+    shards = std::max(1, std::min(std::min(shards, nstreams / 8), count / 16));   // small batches keep the single-thread path
+    BatchArgs a{device, count, datas, dataSizes, outputs, outputBytes, bgra, hostInputs, hostOutputs, statuses};
+    std::vector<ShardResult> results; results.resize(size_t(shards)); std::vector<std::thread> threads;
+    const size_t reserve_sets = size_t(std::min(count, nstreams * bundle_size)) - (count > 0 ? 1 : 0);
+    for (int k = 0; k < shards; k++) {
+      const int i0 = int(int64_t(count) * k / shards), i1 = int(int64_t(count) * (k + 1) / shards), ns = nstreams * (k + 1) / shards - nstreams * k / shards;
+      auto fn = [&, k, i0, i1, ns]() { RunBatchShard(a, k, i0, i1, std::max(1, ns), batch_lanes, bundle_size, k == 0 ? reserve_sets : 0, &results[size_t(k)]); };
+      if (k + 1 < shards) threads.emplace_back(fn); else fn();   // the calling thread runs the last shard
+    }
+    for (auto& t : threads) t.join();
+    for (size_t k = 0; k < results.size(); k++) if (results[k].first != DecoderStatus_Ok) { SetErrorMessage(errorInfo, results[k].message); return results[k].first; }
   } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
-  return first;
+  return DecoderStatus_Ok;
 }
 
 EncoderStatus JxlB200EncodeToMemory(const BitmapData* bitmap, const EncoderOptions* options, const EncoderImageMetadata* metadata, int32_t deviceInput, uint8_t** out, size_t* outSize, ErrorInfo* errorInfo) {
