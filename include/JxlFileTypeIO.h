@@ -122,6 +122,17 @@ JXLFT_API DecoderStatus JXLFT_CALL JxlB200DecodeBatch(int32_t device, int32_t co
                                                        int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight,
                                                        DecoderStatus* statuses, ErrorInfo* errorInfo);
 
+/* Asynchronous form of JxlB200DecodeBatch: Submit starts the batch on internal host threads and returns at once (NULL + message on an
+ * immediate failure); Wait blocks until every file is done, fills statuses[count] (may be NULL), frees the handle and returns the first
+ * non-Ok status. The data, output and size arrays are copied by Submit; the buffers they point to must stay valid until Wait returns.
+ * Several batches may be in flight on one device: a caller that submits the next batch before waiting for the previous one keeps the
+ * GPU busy across the fill / drain of each batch (bench.py pipelines half-batches this way). */
+typedef struct JxlB200Batch JxlB200Batch;
+JXLFT_API JxlB200Batch* JXLFT_CALL JxlB200DecodeBatchSubmit(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes,
+                                                            uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
+                                                            int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, ErrorInfo* errorInfo);
+JXLFT_API DecoderStatus JXLFT_CALL JxlB200DecodeBatchWait(JxlB200Batch* batch, DecoderStatus* statuses, ErrorInfo* errorInfo);
+
 /* Encode a BGRA32 surface to a .jxl file in memory (same pipeline as SaveImage, no callbacks). *out is malloc'ed; free it
  * with JxlB200Free. deviceInput != 0: scan0 is a device pointer. Returns an EncoderStatus. */
 JXLFT_API EncoderStatus JXLFT_CALL JxlB200EncodeToMemory(const BitmapData* bitmap, const EncoderOptions* options, const EncoderImageMetadata* metadata,

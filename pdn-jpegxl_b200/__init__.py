@@ -77,7 +77,7 @@ class IOCallbacks(C.Structure):
 
 EXPORTS = ["GetLibJxlVersion", "LoadImage", "SaveImage", "JxlB200LoadImageBgra", "JxlB200PeekInfo", "JxlB200DecodeBatch", "JxlB200EncodeToMemory",
            "JxlB200Free", "JxlB200LastStageTimes", "JxlB200KernelLaunchCount", "JxlB200DebugDecodeStage", "JxlB200CudaAvailable", "JxlB200BandLayout",
-           "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc"]
+           "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc", "JxlB200DecodeBatchSubmit", "JxlB200DecodeBatchWait"]
 
 _lib.GetLibJxlVersion.restype = C.c_uint32
 _lib.LoadImage.argtypes = [C.POINTER(DecoderCallbacks), C.c_void_p, C.c_size_t, C.POINTER(ErrorInfo)]
@@ -96,6 +96,11 @@ _lib.JxlB200PeekInfo.restype = C.c_int32
 _lib.JxlB200DecodeBatch.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
 _lib.JxlB200DecodeBatch.restype = C.c_int32
+_lib.JxlB200DecodeBatchSubmit.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ErrorInfo)]
+_lib.JxlB200DecodeBatchSubmit.restype = C.c_void_p
+_lib.JxlB200DecodeBatchWait.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200DecodeBatchWait.restype = C.c_int32
 _lib.JxlB200EncodeToMemory.argtypes = [C.POINTER(BitmapData), C.POINTER(EncoderOptionsNative), C.POINTER(EncoderImageMetadataNative), C.c_int32,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ErrorInfo)]
 _lib.JxlB200EncodeToMemory.restype = C.c_int32
@@ -534,8 +539,25 @@ def decode_band(data, group_row_begin, group_row_end, bgra=False, device=-1):
     return out[: rows.value]
 
 
-def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None, raise_on_error=True):
-    """Host path: datas = list of bytes, out_arrays = list of writable numpy arrays. Device path: device_inputs/device_outputs = lists of int pointers."""
+class BatchHandle:
+    """A batch in flight (JxlB200DecodeBatchSubmit). Keeps the input bytes alive until wait()."""
+
+    def __init__(self, handle, n, keep):
+        self.handle, self.n, self.keep = handle, n, keep
+
+    def wait(self, raise_on_error=True):
+        statuses = (C.c_int32 * self.n)()
+        ei = ErrorInfo()
+        st = _lib.JxlB200DecodeBatchWait(self.handle, statuses, C.byref(ei))
+        self.handle, self.keep = None, None
+        if st != 0 and raise_on_error:
+            raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
+        return list(statuses)
+
+
+def decode_batch_submit(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None):
+    """Starts a batch and returns a BatchHandle at once. Host path: datas = list of bytes, out_arrays = list of writable numpy arrays.
+    Device path: device_inputs/device_outputs = lists of int pointers. The buffers must stay valid until handle.wait() returns."""
     n = len(datas) if device_inputs is None else len(device_inputs)
     ptrs = (C.c_void_p * n)()
     lens = (C.c_size_t * n)()
@@ -557,12 +579,16 @@ def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16
         else:
             outs[i] = device_outputs[i]
             olens[i] = out_sizes[i]
-    statuses = (C.c_int32 * n)()
     ei = ErrorInfo()
-    st = _lib.JxlB200DecodeBatch(device, n, ptrs, lens, outs, olens, int(bgra), int(device_inputs is None), int(device_outputs is None), max_in_flight, statuses, C.byref(ei))
-    if st != 0 and raise_on_error:
-        raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
-    return list(statuses)
+    h = _lib.JxlB200DecodeBatchSubmit(device, n, ptrs, lens, outs, olens, int(bgra), int(device_inputs is None), int(device_outputs is None), max_in_flight, C.byref(ei))
+    if not h:
+        raise FormatException("DecodeError", _message(ei) or "batch submit failed")
+    return BatchHandle(h, n, keep)
+
+
+def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None, raise_on_error=True):
+    """Synchronous batch decode (submit + wait)."""
+    return decode_batch_submit(datas, out_arrays, bgra, device, max_in_flight, device_inputs, device_outputs, sizes, out_sizes).wait(raise_on_error)
 
 
 def last_stage_times():

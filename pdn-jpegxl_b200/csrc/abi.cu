@@ -223,7 +223,7 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
       cudaPointerAttributes at;
       if (cudaPointerGetAttributes(&at, a.outputs[begin + i]) == cudaSuccess && at.type == cudaMemoryTypeHost) out_is_pinned[i] = 1; else cudaGetLastError();
     }
-    const bool trace = getenv("JXLB200_TRACE") != nullptr; double t_enq = 0, t_ret = 0, t_idle = 0;
+    const bool trace = getenv("JXLB200_TRACE") != nullptr; double t_enq = 0, t_ret = 0, t_idle = 0, acc_t[5] = {0, 0, 0, 0, 0};
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     // Three-phase pipeline per image (LF entropy | AC entropy | reconstruction + render): a phase is enqueued only once the image's
     // stream has drained, so a kernel waiting on a 40 ms predecessor never sits at the head of a hardware queue shared with other
@@ -239,6 +239,7 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
         else if (!f.direct) memcpy(a.outputs[f.idx], f.res.pixels, f.res.pixel_bytes);
       }
       record(f.idx, st, f.res.message);
+      if (trace) { const StageTimes& t = f.res.times; acc_t[0] += t.lf; acc_t[1] += t.ac; acc_t[2] += t.recon; acc_t[3] += t.filters + t.output; acc_t[4] += t.total; }
       f.job.reset(); f.res.job.reset(); done++;
     };
     auto idle = [](const Bundle& b) { return cudaStreamQuery(b.stream) != cudaErrorNotReady; };
@@ -294,6 +295,7 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
       } else if (!progressed) { t0 = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); t_idle += now() - t0; }
     }
     if (trace) { DumpHostTrace(); if (slot == 0) DumpPoolStats(); }
+    if (trace && acc_t[4] > 0) fprintf(stderr, "[jxlb200] shard %d GPU ms/image under load (JXLB200_TRACE=2 events): lf %.2f ac %.2f recon %.2f render %.2f total %.2f\n", slot, acc_t[0] / count, acc_t[1] / count, acc_t[2] / count, acc_t[3] / count, acc_t[4] / count);
     if (trace) fprintf(stderr, "[jxlb200] shard %d, %d images: host parse + LF phase %.2f ms (%.2f ms/image), polling + later phases + retire %.2f ms, idle (GPU-bound) %.2f ms\n", slot, count, t_enq, t_enq / std::max(count, 1), t_ret, t_idle);
   } catch (const std::exception& e) {
     // Work may still be running on this shard's streams and writing into caller-owned buffers: wait for it before returning them.
@@ -307,33 +309,67 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
   if (pin) PinnedPut(pin, pin_bytes);
 }
 
-DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes, uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
-                                 int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, DecoderStatus* statuses, ErrorInfo* errorInfo) {
-  if (!datas || !dataSizes || !outputs || !outputBytes || count < 0) return DecoderStatus_NullParameter;
+// A batch in flight: owns copies of the caller's pointer arrays, the per-file statuses and the shard threads.
+struct JxlB200Batch {
+  std::vector<const uint8_t*> datas; std::vector<size_t> sizes; std::vector<uint8_t*> outputs; std::vector<size_t> out_bytes;
+  std::vector<DecoderStatus> statuses; std::vector<ShardResult> results; std::vector<std::thread> threads; std::vector<int> slots; BatchArgs args;
+};
+// Stream sets are leased per shard so that two batches in flight on one device never share a stream.
+static std::mutex g_slot_mu; static std::vector<uint8_t> g_slot_busy;
+static int AcquireSlot() { std::lock_guard<std::mutex> lk(g_slot_mu); for (size_t i = 0; i < g_slot_busy.size(); i++) if (!g_slot_busy[i]) { g_slot_busy[i] = 1; return int(i); } g_slot_busy.push_back(1); return int(g_slot_busy.size()) - 1; }
+static void ReleaseSlot(int slot) { std::lock_guard<std::mutex> lk(g_slot_mu); g_slot_busy[size_t(slot)] = 0; }
+
+JxlB200Batch* JxlB200DecodeBatchSubmit(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes, uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
+                                       int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, ErrorInfo* errorInfo) {
+  if (!datas || !dataSizes || !outputs || !outputBytes || count < 0) { SetErrorMessage(errorInfo, "null parameter"); return nullptr; }
   try {
-    std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return DecoderStatus_DecodeError; }
-    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return DecoderStatus_InvalidParameter; }
+    std::string why; if (!CudaAvailable(&why)) { SetErrorMessage(errorInfo, why); return nullptr; }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return nullptr; }
+    std::unique_ptr<JxlB200Batch> b(new JxlB200Batch);
+    b->datas.assign(datas, datas + count); b->sizes.assign(dataSizes, dataSizes + count); b->outputs.assign(outputs, outputs + count); b->out_bytes.assign(outputBytes, outputBytes + count);
+    b->statuses.assign(size_t(count), DecoderStatus_Ok);
     const int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 256));   // maxInFlight counts streams (bundles) in flight
     const int batch_lanes = (count >= 64 && nstreams >= 32) ? 16 : (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
-    static const int env_bundle = getenv("JXLB200_BUNDLE") ? atoi(getenv("JXLB200_BUNDLE")) : 0;
+    const int env_bundle = getenv("JXLB200_BUNDLE") ? atoi(getenv("JXLB200_BUNDLE")) : 0;
     const int bundle_size = std::max(1, std::min(env_bundle > 0 ? env_bundle : ((count >= 64 && nstreams >= 32) ? 2 : 1), kMaxBundle));   // images per stream / per entropy launch
     // Host threads: the per-image enqueue work is split over `shards` threads, each with its own share of the streams.
     const int env_threads = getenv("JXLB200_HOST_THREADS") ? atoi(getenv("JXLB200_HOST_THREADS")) : 0;   // read per call (cheap): lets a caller tune it between batches
     int hw = int(std::thread::hardware_concurrency()); if (hw <= 0) hw = 4;
     int shards = env_threads > 0 ? env_threads : std::min(4, std::max(1, hw / 2));
-    shards = std::max(1, std::min(std::min(shards, nstreams / 8), count / 16));   // small batches keep the single-thread path
-    BatchArgs a{device, count, datas, dataSizes, outputs, outputBytes, bgra, hostInputs, hostOutputs, statuses};
-    std::vector<ShardResult> results; results.resize(size_t(shards)); std::vector<std::thread> threads;
+    shards = std::max(1, std::min(std::min(shards, nstreams / 8), count / 16));   // small batches keep a single enqueue thread
+    b->args = BatchArgs{device, count, b->datas.data(), b->sizes.data(), b->outputs.data(), b->out_bytes.data(), bgra, hostInputs, hostOutputs, b->statuses.data()};
+    b->results.resize(size_t(shards));
     const size_t reserve_sets = size_t(std::min(count, nstreams * bundle_size)) - (count > 0 ? 1 : 0);
+    JxlB200Batch* raw = b.get();
     for (int k = 0; k < shards; k++) {
       const int i0 = int(int64_t(count) * k / shards), i1 = int(int64_t(count) * (k + 1) / shards), ns = nstreams * (k + 1) / shards - nstreams * k / shards;
-      auto fn = [&, k, i0, i1, ns]() { RunBatchShard(a, k, i0, i1, std::max(1, ns), batch_lanes, bundle_size, k == 0 ? reserve_sets : 0, &results[size_t(k)]); };
-      if (k + 1 < shards) threads.emplace_back(fn); else fn();   // the calling thread runs the last shard
+      const int slot = AcquireSlot(); b->slots.push_back(slot);
+      b->threads.emplace_back([raw, k, slot, i0, i1, ns, batch_lanes, bundle_size, reserve_sets]() {
+        RunBatchShard(raw->args, slot, i0, i1, std::max(1, ns), batch_lanes, bundle_size, k == 0 ? reserve_sets : 0, &raw->results[size_t(k)]);
+      });
     }
-    for (auto& t : threads) t.join();
-    for (size_t k = 0; k < results.size(); k++) if (results[k].first != DecoderStatus_Ok) { SetErrorMessage(errorInfo, results[k].message); return results[k].first; }
-  } catch (const std::bad_alloc&) { return DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); return DecoderStatus_DecodeError; } catch (...) { return DecoderStatus_DecodeError; }
+    return b.release();
+  } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); } catch (...) {}
+  return nullptr;
+}
+
+DecoderStatus JxlB200DecodeBatchWait(JxlB200Batch* batch, DecoderStatus* statuses, ErrorInfo* errorInfo) {
+  if (!batch) return DecoderStatus_NullParameter;
+  std::unique_ptr<JxlB200Batch> b(batch);
+  for (auto& t : b->threads) if (t.joinable()) t.join();
+  for (int slot : b->slots) ReleaseSlot(slot);
+  if (statuses) for (size_t i = 0; i < b->statuses.size(); i++) statuses[i] = b->statuses[i];
+  for (size_t k = 0; k < b->results.size(); k++) if (b->results[k].first != DecoderStatus_Ok) { SetErrorMessage(errorInfo, b->results[k].message); return b->results[k].first; }
   return DecoderStatus_Ok;
+}
+
+DecoderStatus JxlB200DecodeBatch(int32_t device, int32_t count, const uint8_t* const* datas, const size_t* dataSizes, uint8_t* const* outputs, const size_t* outputBytes, int32_t bgra,
+                                 int32_t hostInputs, int32_t hostOutputs, int32_t maxInFlight, DecoderStatus* statuses, ErrorInfo* errorInfo) {
+  if (!datas || !dataSizes || !outputs || !outputBytes || count < 0) return DecoderStatus_NullParameter;
+  ErrorInfo local; local.errorMessage[0] = 0;
+  JxlB200Batch* b = JxlB200DecodeBatchSubmit(device, count, datas, dataSizes, outputs, outputBytes, bgra, hostInputs, hostOutputs, maxInFlight, &local);
+  if (!b) { SetErrorMessage(errorInfo, local.errorMessage); return std::string(local.errorMessage) == "cudaSetDevice failed" ? DecoderStatus_InvalidParameter : DecoderStatus_DecodeError; }
+  return JxlB200DecodeBatchWait(b, statuses, errorInfo);
 }
 
 EncoderStatus JxlB200EncodeToMemory(const BitmapData* bitmap, const EncoderOptions* options, const EncoderImageMetadata* metadata, int32_t deviceInput, uint8_t** out, size_t* outSize, ErrorInfo* errorInfo) {

@@ -316,7 +316,7 @@ void DecodeJob::Setup(const DecodeRequest& req) {
   toc = ReadToc(br, fh); frame_off = pos + br.pos / 8; JXLG_CHECK(frame_off + toc.total <= cs.size(), "JxlDecoderProcessInput needs more input, but it already received the entire image.");
   info.frame_name = fh.name; info.bpp = double(cs.size()) * 8.0 / (double(m.xsize) * m.ysize);
   memset(&h, 0, sizeof(h)); bgra = req.bgra; device_output = req.device_output;
-  { int l = req.ac_lanes; static const int env_lanes = getenv("JXLB200_AC_LANES") ? atoi(getenv("JXLB200_AC_LANES")) : 0; if (env_lanes > 0) l = env_lanes; ac_lanes = 1; while (ac_lanes * 2 <= l && ac_lanes < 32) ac_lanes *= 2; }
+  { int l = req.ac_lanes; const int env_lanes = getenv("JXLB200_AC_LANES") ? atoi(getenv("JXLB200_AC_LANES")) : 0; if (env_lanes > 0) l = env_lanes; ac_lanes = 1; while (ac_lanes * 2 <= l && ac_lanes < 32) ac_lanes *= 2; }
   h.xsize = fh.xsize; h.ysize = fh.ysize; h.xb = fh.xblocks; h.yb = fh.yblocks; h.xpad = h.xb * 8; h.ypad = h.yb * 8; h.xt = (h.xb + 7) / 8; h.yt = (h.yb + 7) / 8; h.xgroups = fh.xgroups; h.ygroups = fh.ygroups; h.num_groups = fh.num_groups;
   h.xlfgroups = fh.xlfgroups; h.ylfgroups = fh.ylfgroups; h.num_lf_groups = fh.num_lf_groups; h.group_dim = fh.group_dim; h.num_passes = fh.passes.num_passes; h.encoding = fh.encoding; h.flags = uint32_t(fh.flags);
   info.group_dim = h.group_dim; info.num_group_rows = h.ygroups;
@@ -418,6 +418,7 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
     h.lf_smem = std::min<uint32_t>(modb + 64, 96 * 1024); ac_budget = [this, code_bytes]() { uint32_t acb = 0; bool prefix = false; for (uint32_t p = 0; p < h.num_passes; p++) { acb = std::max(acb, code_bytes(h.ac_code[p])); prefix |= h.ac_code[p].use_prefix != 0; }
       h.ac_smem = acb + 64; h.ac_fast = (!prefix && h.ac_smem <= 96 * 1024) ? 1 : 0; if (!h.ac_fast) h.ac_smem = 0; };
     if (vardct && !single) ac_budget();
+    { static const bool tr = getenv("JXLB200_TRACE") != nullptr; static std::atomic<int> shown{0}; if (tr && shown.fetch_add(1) < 2) fprintf(stderr, "[jxlb200] table staging: lf_smem %u B, ac_smem %u B (ac_fast %u), AC clusters %u, log_alpha %u\n", h.lf_smem, h.ac_smem, h.ac_fast, h.ac_code[0].num_clusters, h.ac_code[0].log_alpha); }
   }
   std::vector<uint64_t> sec(2 * nlog + 2, 0);
   for (size_t i = 0; i < nlog; i++) { size_t t = single ? 0 : i; sec[i] = base_bits + uint64_t(toc.offset[t]) * 8; sec[nlog + i] = base_bits + uint64_t(toc.offset[t] + toc.size[t]) * 8; }

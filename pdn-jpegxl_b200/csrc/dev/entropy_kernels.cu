@@ -10,6 +10,8 @@
 // from N/Decoder/JxlDecoder.cpp:252.
 #include "frame.cuh"
 #include "kernels.h"
+#include <cstdlib>
+#include <algorithm>
 
 namespace jxlgpu {
 
@@ -185,17 +187,22 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
 // lanes = 1 gives the lowest single-image latency (192 warps for 12 MP); batches raise it so that the number of resident
 // sections is not capped by the register file (a lone lane still holds a full warp's registers).
 // kSmem: ANS code with every table staged in shared memory (the host checks sizes before choosing the instantiation).
-static const int kAcWarps = 4;
+// Warps per CTA: the code tables are staged once per CTA, and the CTAs resident on an SM are capped by that shared memory (a
+// 60 KB table set allows 3). Wide CTAs (12 warps = a whole 12 MP image at 16 sections per warp) share one copy between 12 warps, so
+// a batch keeps 24 AC warps resident per SM instead of 12; single-image decodes keep small CTAs that spread over more SMs.
+static const int kAcMaxWarps = 12;
+static const uint32_t kAcBatchSmem = 0;   // bytes of shared memory a batch-mode AC CTA asks for at least (0: only what its tables need)
+static inline int AcWarpsFor(int lanes) { return lanes >= 8 ? kAcMaxWarps : 4; }
 template <bool kSmem>
 __device__ __forceinline__ void AcVardctBody(const DFrame& f, const int pass, const int lanes, const int cta) {
   extern __shared__ __align__(16) uint8_t dsm[]; __shared__ uint8_t s_freq[64], s_numnz[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   CodeView cv; cv.Bind(f.blob, f.ac_code[pass]);
   if (tid < 64) { s_freq[tid] = kFreqCtx[tid]; s_numnz[tid] = kNumNzCtx[tid]; }
-  if (kSmem) { uint32_t used = 0; cv.Stage(dsm, f.ac_smem, used, tid, 32 * kAcWarps); }
+  if (kSmem) { uint32_t used = 0; cv.Stage(dsm, f.ac_smem, used, tid, int(blockDim.x)); }
   __syncthreads();
   if (kSmem) cv.AssumeShared();
-  const int g = (cta * kAcWarps + warp) * lanes + lane;
+  const int g = (cta * int(blockDim.x >> 5) + warp) * lanes + lane;
   if (lane >= lanes || g >= int(f.num_groups) || !GroupInBand(f, g)) return;
   const int xb = int(f.xb), cx0 = (g % int(f.xgroups)) * 32, cy0 = (g / int(f.xgroups)) * 32, w = min(32, xb - cx0), h = min(32, int(f.yb) - cy0);
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
@@ -258,12 +265,12 @@ __device__ __forceinline__ void AcVardctBody(const DFrame& f, const int pass, co
 }
 
 template <bool kSmem>
-__global__ void __launch_bounds__(32 * kAcWarps, 4) k_ac_vardct(const __grid_constant__ DFrame f, int pass, int lanes) {
+__global__ void __launch_bounds__(32 * kAcMaxWarps, 2) k_ac_vardct(const __grid_constant__ DFrame f, int pass, int lanes) {
   if (blockIdx.x < f.ac_cta_offset) return;   // spreads concurrent images over different SMs (see k_lf_group)
   AcVardctBody<kSmem>(f, pass, lanes, int(blockIdx.x - f.ac_cta_offset));
 }
 template <bool kSmem>
-__global__ void __launch_bounds__(32 * kAcWarps, 4) k_ac_vardct_multi(const __grid_constant__ DFrameSet s, int lanes) {   // pass 0 of single-pass frames
+__global__ void __launch_bounds__(32 * kAcMaxWarps, 2) k_ac_vardct_multi(const __grid_constant__ DFrameSet s, int lanes) {   // pass 0 of single-pass frames
   if (blockIdx.x < s.cta_offset) return;
   const uint32_t cta = blockIdx.x - s.cta_offset; uint32_t img = 0; while (img + 1 < s.n && cta >= s.first[img + 1]) img++;
   AcVardctBody<kSmem>(s.f[img], 0, lanes, int(cta - s.first[img]));
@@ -309,7 +316,7 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
 }
 
 static void EnsureSmemAttr() { static bool done[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (done[dev & 63]) return; done[dev & 63] = true;   // function attributes are per device
-  cudaFuncSetAttribute(k_lf_group_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(k_lf_group_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_lf_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
 void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (!h.num_lf_groups) return; const bool narrow = !h.uses_wp && !h.mod_wide;
   if (narrow) k_lf_group<true><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); else k_lf_group<false><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); }
@@ -322,18 +329,21 @@ void LaunchLfGroupsMulti(const DFrameSet& set, bool narrow, cudaStream_t st) {
 }
 void LaunchAcGroupsMulti(const DFrameSet& set, int lanes, cudaStream_t st) {   // every frame: encoding 0, num_passes 1, ac_fast
   EnsureSmemAttr(); uint32_t smem = 0; for (uint32_t i = 0; i < set.n; i++) smem = std::max(smem, set.f[i].ac_smem);
-  k_ac_vardct_multi<true><<<set.first[set.n] + set.cta_offset, 32 * kAcWarps, smem, st>>>(set, lanes);
+  // Occupancy cap: a padded shared-memory request bounds the AC CTAs resident per SM, which leaves registers and shared memory for the
+  // tile kernels (reconstruction, render) of images that are further along (they otherwise queue behind ~70 ms entropy CTAs).
+  { const char* e = getenv("JXLB200_AC_SMEM_KB"); const uint32_t pad = e ? uint32_t(atoi(e)) * 1024u : kAcBatchSmem; if (lanes >= 8) smem = std::max(smem, std::min(pad, 200u * 1024u)); }
+  k_ac_vardct_multi<true><<<set.first[set.n] + set.cta_offset, 32 * AcWarpsFor(lanes), smem, st>>>(set, lanes);
 }
 void LaunchLfDequant(const DFrame* d, const DFrame& h, bool smooth, cudaStream_t st) {
   size_t plane = size_t(h.xb) * h.yb; unsigned blocks = unsigned((plane + 255) / 256); k_lf_dequant<<<blocks, 256, 0, st>>>(d); if (smooth) k_lf_smooth<<<blocks, 256, 0, st>>>(d);
 }
 // Returns the number of kernels launched. `lanes`: sections per warp for the AC walk (power of two, 1..32).
-int AcCtas(const DFrame& h, int lanes) { const unsigned per_cta = unsigned(kAcWarps * lanes); return int((h.num_groups + per_cta - 1) / per_cta); }
+int AcCtas(const DFrame& h, int lanes) { const unsigned per_cta = unsigned(AcWarpsFor(lanes) * lanes); return int((h.num_groups + per_cta - 1) / per_cta); }
 int LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, int lanes, cudaStream_t st) {
   EnsureSmemAttr(); int n = 0;
   if (h.encoding == 0) {
-    const unsigned per_cta = unsigned(kAcWarps * lanes), ctas = (h.num_groups + per_cta - 1) / per_cta;
-    if (h.ac_fast) k_ac_vardct<true><<<ctas + h.ac_cta_offset, 32 * kAcWarps, h.ac_smem, st>>>(h, pass, lanes); else k_ac_vardct<false><<<ctas + h.ac_cta_offset, 32 * kAcWarps, 0, st>>>(h, pass, lanes);
+    const unsigned nw = unsigned(AcWarpsFor(lanes)), per_cta = nw * unsigned(lanes), ctas = (h.num_groups + per_cta - 1) / per_cta;
+    if (h.ac_fast) k_ac_vardct<true><<<ctas + h.ac_cta_offset, 32 * nw, h.ac_smem, st>>>(h, pass, lanes); else k_ac_vardct<false><<<ctas + h.ac_cta_offset, 32 * nw, 0, st>>>(h, pass, lanes);
     n++;
   }
   if (h.num_mod_channels > h.first_group_channel) { const unsigned ctas = (h.num_groups + kModGroupsPerCta - 1) / kModGroupsPerCta;

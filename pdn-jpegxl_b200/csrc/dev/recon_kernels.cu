@@ -83,70 +83,116 @@ __device__ void LlfFromLf(const DFrame& f, int c, int cy, int cx, const float* l
 // c[k*8+i] = ck * cos((2i+1) k pi / 16), c0 = 1, ck = sqrt(2) (A.9 scaling: inverse is the plain DCT-III sum)
 __device__ constexpr float kCos8[64] = {1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, 1.387039845e+00f, 1.175875602e+00f, 7.856949584e-01f, 2.758993793e-01f, -2.758993793e-01f, -7.856949584e-01f, -1.175875602e+00f, -1.387039845e+00f, 1.306562965e+00f, 5.411961001e-01f, -5.411961001e-01f, -1.306562965e+00f, -1.306562965e+00f, -5.411961001e-01f, 5.411961001e-01f, 1.306562965e+00f, 1.175875602e+00f, -2.758993793e-01f, -1.387039845e+00f, -7.856949584e-01f, 7.856949584e-01f, 1.387039845e+00f, 2.758993793e-01f, -1.175875602e+00f, 1.000000000e+00f, -1.000000000e+00f, -1.000000000e+00f, 1.000000000e+00f, 1.000000000e+00f, -1.000000000e+00f, -1.000000000e+00f, 1.000000000e+00f, 7.856949584e-01f, -1.387039845e+00f, 2.758993793e-01f, 1.175875602e+00f, -1.175875602e+00f, -2.758993793e-01f, 1.387039845e+00f, -7.856949584e-01f, 5.411961001e-01f, -1.306562965e+00f, 1.306562965e+00f, -5.411961001e-01f, -5.411961001e-01f, 1.306562965e+00f, -1.306562965e+00f, 5.411961001e-01f, 2.758993793e-01f, -7.856949584e-01f, 1.175875602e+00f, -1.387039845e+00f, 1.387039845e+00f, -1.175875602e+00f, 7.856949584e-01f, -2.758993793e-01f};
 
-// Dequant + chroma-from-luma + LLF + 8x8 IDCT for every DCT8 varblock. One warp handles 4 horizontally adjacent cells per
-// iteration: lane (b = lane>>3, r = lane&7) loads storage row r of block b (one 16-byte load: 8 int16 coefficients, the
-// 4 blocks are 512 contiguous bytes), transforms along the row in registers, transposes through 1.1 KB of padded shared
-// memory and writes one 32-byte pixel row segment; a warp writes 8 rows x 128 contiguous bytes per channel.
-__global__ void __launch_bounds__(256) k_reconstruct_dct8(const __grid_constant__ DFrame f) {
-  const int g = blockIdx.x >> 2, quarter = blockIdx.x & 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = lane >> 3, r = lane & 7;
-  const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
-  if (!GroupInBand(f, g)) return;
-  __shared__ float s_dq[3 * 64]; __shared__ float s_t[8][3][4 * 72];   // per warp: [channel][block][72]: two __syncwarp per iteration instead of six
+// 8-point inverse DCT in the codestream's scaling (y[n] = X0 + sqrt2 * sum_k X[k] cos((2n+1) k pi / 16)) as an even/odd split:
+// 34 flops instead of the 64 of the matrix form (kCos8 rows 1,3,5,7 are +-{k1,k3,k5,k7}, rows 2,6 are +-{1.3066, 0.5412}, row 4 is +-1).
+__device__ __forceinline__ void Idct8(const float X[8], float y[8]) {
+  const float k1 = 1.387039845e+00f, k3 = 1.175875602e+00f, k5 = 7.856949584e-01f, k7 = 2.758993793e-01f, r2 = 1.306562965e+00f, r6 = 5.411961001e-01f;
+  const float a0 = X[0] + X[4], a1 = X[0] - X[4];
+  const float b0 = fmaf(r2, X[2], r6 * X[6]), b1 = fmaf(r6, X[2], -r2 * X[6]);
+  const float e0 = a0 + b0, e3 = a0 - b0, e1 = a1 + b1, e2 = a1 - b1;
+  const float o0 = fmaf(k1, X[1], fmaf(k3, X[3], fmaf(k5, X[5], k7 * X[7])));
+  const float o1 = fmaf(k3, X[1], fmaf(-k7, X[3], fmaf(-k1, X[5], -k5 * X[7])));
+  const float o2 = fmaf(k5, X[1], fmaf(-k1, X[3], fmaf(k7, X[5], k3 * X[7])));
+  const float o3 = fmaf(k7, X[1], fmaf(-k5, X[3], fmaf(k3, X[5], -k1 * X[7])));
+  y[0] = e0 + o0; y[7] = e0 - o0; y[1] = e1 + o1; y[6] = e1 - o1; y[2] = e2 + o2; y[5] = e2 - o2; y[3] = e3 + o3; y[4] = e3 - o3;
+}
+
+// Dequant + chroma-from-luma + LLF + 8x8 IDCT for every DCT8 varblock. A work item is one row of 32 cells of a 256x256 group; a CTA of
+// 8 warps walks items with a grid stride (persistent: the grid is a multiple of the SM count).
+//   phase A  thread (cell, storage row r): one 16-byte load per channel (8 int16 coefficients; a cell's 3 x 128 bytes are contiguous, a
+//            warp reads 16 cells x 2 rows = full 32-byte sectors), dequantise + CfL in registers, 8-point IDCT along the row, two
+//            STS.128 into a [cell][68] transposition buffer. Warps own a row PAIR, so the high-frequency pairs, which are all zero in
+//            most cells, skip the arithmetic warp-uniformly.
+//   phase B  thread (channel, half of the pixel rows, cell): eight LDS.128 (four pixel rows of the column-transformed block), four
+//            8-point IDCTs, and per pixel row two float4 stores: a warp writes 32 cells x 32 bytes = 1 KB contiguous per pixel row.
+// The buffer is double-buffered, so an item costs one __syncthreads. Everything the next item reads from global memory is requested
+// before the current one is transformed. 6 B/px read (int16 coefficients) + 12 B/px written (fp32 XYB) = 18 algorithmic bytes per pixel.
+static const int kD8Stride = 68;   // floats per cell in the transposition buffer: 64 + 4, so 8 consecutive cells hit 8 different 16-byte bank groups
+__global__ void __launch_bounds__(256, 3) k_reconstruct_dct8(const __grid_constant__ DFrame f, const int num_items) {
+  extern __shared__ __align__(16) float s_t_raw[];   // [2 buffers][3 channels][32 cells * kD8Stride] (dynamic: 51 KB)
+  float (*s_t)[3][32 * kD8Stride] = reinterpret_cast<float (*)[3][32 * kD8Stride]>(s_t_raw);
+  __shared__ __align__(16) float s_dq[192];
+  __shared__ uint8_t s_valid[2][32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bxA = (warp >> 2) * 16 + (lane & 15), rA = (warp & 3) * 2 + (lane >> 4);   // phase A role
+  const int cB = warp % 3, yhalf = warp / 3;                                            // phase B role (warps 0..5), cell = lane
   if (tid < 192) s_dq[tid] = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[0]))[tid];
   __syncthreads();
-  const int by = quarter * 8 + warp; if (by >= h) return;
-  const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536;
-  const size_t tile_row = size_t((cy0 + by) >> 3) * f.xt;
-  // Software pipeline: everything iteration it+1 reads from global memory (3 x 16 B of coefficients, the cell's strategy / multiplier,
-  // the tile's CfL factors, the LF samples) is requested before iteration it is transformed, so a lane keeps ~60 B in flight instead
-  // of waiting for one dependent load at a time (ncu r01: long-scoreboard stall 6.5 per issue, 29 % of the HBM roofline).
+  const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb;
   struct Pre { int4 raw[3]; float lf[3]; int acs, hf, tx, tb; };
-  auto fetch = [&](int it, Pre& p) {
-    const int bx = it * 4 + b; p.raw[0] = p.raw[1] = p.raw[2] = make_int4(0, 0, 0, 0); p.lf[0] = p.lf[1] = p.lf[2] = 0.f; p.acs = 0; p.hf = 0; p.tx = 0; p.tb = 0;
-    if (bx < w) {
-      const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx, tile = tile_row + ((cx0 + bx) >> 3); const int16_t* cp = coef + (by * 32 + bx) * 64 + r * 8;
-      p.raw[0] = __ldcs(reinterpret_cast<const int4*>(cp)); p.raw[1] = __ldcs(reinterpret_cast<const int4*>(cp + 65536)); p.raw[2] = __ldcs(reinterpret_cast<const int4*>(cp + 2 * 65536));
-      p.acs = f.acs[o]; p.hf = f.hf_mul_m1[o]; p.tx = f.ytox[tile]; p.tb = f.ytob[tile];
-      if (r == 0) { p.lf[0] = f.lf_src[o]; p.lf[1] = f.lf_src[lfplane + o]; p.lf[2] = f.lf_src[2 * lfplane + o]; }
-    }
+  auto geometry = [&](int item, int& cx0, int& cy0, int& by, int& w) -> bool {
+    const int g = item >> 5; by = item & 31; const int gx = g % int(f.xgroups), gy = g / int(f.xgroups); cx0 = gx * 32; cy0 = gy * 32;
+    w = min(32, int(f.xb) - cx0); return by < min(32, int(f.yb) - cy0) && GroupInBand(f, g);
   };
-  Pre cur; fetch(0, cur);
+  auto fetch = [&](int item, Pre& p) {
+    p.raw[0] = p.raw[1] = p.raw[2] = make_int4(0, 0, 0, 0); p.lf[0] = p.lf[1] = p.lf[2] = 0.f; p.acs = 0; p.hf = 0; p.tx = 0; p.tb = 0;
+    int cx0, cy0, by, w; if (item >= num_items || !geometry(item, cx0, cy0, by, w) || bxA >= w) return;
+    const size_t o = size_t(cy0 + by) * f.xb + cx0 + bxA, tile = size_t((cy0 + by) >> 3) * f.xt + ((cx0 + bxA) >> 3);
+    const int16_t* cp = f.coeffs + size_t(item >> 5) * 3 * 65536 + (by * 32 + bxA) * 64 + rA * 8;
+    p.raw[0] = __ldcs(reinterpret_cast<const int4*>(cp)); p.raw[1] = __ldcs(reinterpret_cast<const int4*>(cp + 65536)); p.raw[2] = __ldcs(reinterpret_cast<const int4*>(cp + 2 * 65536));
+    p.acs = f.acs[o]; p.hf = f.hf_mul_m1[o]; p.tx = f.ytox[tile]; p.tb = f.ytob[tile];
+    if (rA == 0) { p.lf[0] = f.lf_src[o]; p.lf[1] = f.lf_src[lfplane + o]; p.lf[2] = f.lf_src[2 * lfplane + o]; }
+  };
+  Pre cur; fetch(blockIdx.x, cur);
+  int buf = 0;
 #pragma unroll 1
-  for (int it = 0; it < 8; it++) {
-    Pre nxt; if (it + 1 < 8) fetch(it + 1, nxt); else nxt = cur;
-    const int bx = it * 4 + b; const bool valid = bx < w && cur.acs == 0x80;   // strategy 0 (DCT8), first (only) cell
-    const float scale = f.inv_gs / float(cur.hf + 1), kx = f.base_x + float(cur.tx) * f.inv_color_factor, kb = f.base_b + float(cur.tb) * f.inv_color_factor;
-    float y8[8]; float (*st)[4 * 72] = s_t[warp];
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x, buf ^= 1) {
+    Pre nxt; fetch(item + int(gridDim.x), nxt);
+    int cx0, cy0, by, w; const bool row_ok = geometry(item, cx0, cy0, by, w);
+    if (!row_ok) { cur = nxt; continue; }   // uniform over the CTA
+    // ---- phase A
+    const bool valid = bxA < w && cur.acs == 0x80;   // strategy 0 (DCT8), first (only) cell
+    if (rA == 0) s_valid[buf][bxA] = valid ? 1 : 0;
+    const bool any = valid && (((cur.raw[0].x | cur.raw[0].y | cur.raw[0].z | cur.raw[0].w | cur.raw[1].x | cur.raw[1].y | cur.raw[1].z | cur.raw[1].w | cur.raw[2].x | cur.raw[2].y | cur.raw[2].z | cur.raw[2].w) != 0) || rA == 0);
+    const bool warp_any = __any_sync(0xffffffffu, any);   // voted by every lane, before the lanes of other strategies drop out
+    if (valid) {
+      const float scale = f.inv_gs / float(cur.hf + 1), kx = f.base_x + float(cur.tx) * f.inv_color_factor, kb = f.base_b + float(cur.tb) * f.inv_color_factor;
+      float* dst = &s_t[buf][0][bxA * kD8Stride + rA * 8];
+      if (!warp_any) {   // the whole row pair of these 16 cells is zero: the row transform of zeros is zeros
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int ci = 0; ci < 3; ci++) {   // phase A: dequantise + CfL, transform along the storage row, park T[hf = r][y] in shared memory
-      const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; float v[8];
-      const int4 raw = valid ? cur.raw[c] : make_int4(0, 0, 0, 0);
-      const int q[8] = {int(short(raw.x & 0xffff)), raw.x >> 16, int(short(raw.y & 0xffff)), raw.y >> 16, int(short(raw.z & 0xffff)), raw.z >> 16, int(short(raw.w & 0xffff)), raw.w >> 16};
-      const float mulc = c == 1 ? scale : c == 0 ? scale * f.xm : scale * f.bm, kc = c == 0 ? kx : kb, b1 = f.quant_bias[c], b3 = f.quant_bias[3];
+        for (int c = 0; c < 3; c++) { *reinterpret_cast<float4*>(dst + c * 32 * kD8Stride) = z; *reinterpret_cast<float4*>(dst + c * 32 * kD8Stride + 4) = z; }
+      } else {
+        float y8[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) { float a = AdjustQuantBiasDev(q[j], b1, b3) * s_dq[c * 64 + r * 8 + j] * mulc; if (c == 1) y8[j] = a; else a += kc * y8[j]; v[j] = a; }
-      if (valid && r == 0) v[0] = cur.lf[c];   // LLF of an 8x8 block is the LF sample itself
-      float t[8];
+        for (int ci = 0; ci < 3; ci++) {
+          const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; float v[8], t[8];
+          const int4 raw = cur.raw[c];
+          const int q[8] = {int(short(raw.x & 0xffff)), raw.x >> 16, int(short(raw.y & 0xffff)), raw.y >> 16, int(short(raw.z & 0xffff)), raw.z >> 16, int(short(raw.w & 0xffff)), raw.w >> 16};
+          const float mulc = c == 1 ? scale : c == 0 ? scale * f.xm : scale * f.bm, kc = c == 0 ? kx : kb, b1 = f.quant_bias[c], b3 = f.quant_bias[3];
+          const float4 d0 = *reinterpret_cast<const float4*>(&s_dq[c * 64 + rA * 8]), d1 = *reinterpret_cast<const float4*>(&s_dq[c * 64 + rA * 8 + 4]);
+          const float dq[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-      for (int y = 0; y < 8; y++) { float a = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; j++) a = fmaf(v[j], kCos8[j * 8 + y], a); t[y] = a; }
-      *reinterpret_cast<float4*>(st[c] + b * 72 + r * 8) = make_float4(t[0], t[1], t[2], t[3]); *reinterpret_cast<float4*>(st[c] + b * 72 + r * 8 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+          for (int j = 0; j < 8; j++) {
+            const float qf = float(q[j]);   // quantisation-bias adjustment: 0 -> 0, +-1 -> +-b1, else q - b3 / q
+            const float adj = fabsf(qf) >= 1.5f ? qf - __fdividef(b3, qf) : qf * b1;
+            float a = adj * dq[j] * mulc; if (c == 1) y8[j] = a; else a = fmaf(kc, y8[j], a); v[j] = a;
+          }
+          if (rA == 0) v[0] = cur.lf[c];   // LLF of an 8x8 block is the LF sample itself
+          Idct8(v, t);
+          *reinterpret_cast<float4*>(dst + c * 32 * kD8Stride) = make_float4(t[0], t[1], t[2], t[3]);
+          *reinterpret_cast<float4*>(dst + c * 32 * kD8Stride + 4) = make_float4(t[4], t[5], t[6], t[7]);
+        }
+      }
     }
-    __syncwarp();
+    __syncthreads();
+    // ---- phase B
+    if (warp < 6 && lane < w && s_valid[buf][lane]) {
+      const float* src = &s_t[buf][cB][lane * kD8Stride + yhalf * 4];
+      float4 in[8];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {   // phase B: lane (b, y = r) gathers T[hf][y], transforms along hf, writes one 32-byte pixel row segment
-      float u[8];
+      for (int hf = 0; hf < 8; hf++) in[hf] = *reinterpret_cast<const float4*>(src + hf * 8);
+      float* out = f.xyb + cB * plane + (size_t(cy0 + by) * 8 + yhalf * 4) * f.xpad + size_t(cx0 + lane) * 8;
 #pragma unroll
-      for (int hf = 0; hf < 8; hf++) u[hf] = st[c][b * 72 + hf * 8 + r];
-      float px[8];
+      for (int yy = 0; yy < 4; yy++) {
+        float X[8], px[8];
 #pragma unroll
-      for (int x = 0; x < 8; x++) { float a = 0.f;
-#pragma unroll
-        for (int hf = 0; hf < 8; hf++) a = fmaf(u[hf], kCos8[hf * 8 + x], a); px[x] = a; }
-      if (valid) { float* out = f.xyb + c * plane + (size_t(cy0 + by) * 8 + r) * f.xpad + size_t(cx0 + bx) * 8; *reinterpret_cast<float4*>(out) = make_float4(px[0], px[1], px[2], px[3]); *reinterpret_cast<float4*>(out + 4) = make_float4(px[4], px[5], px[6], px[7]); }
+        for (int hf = 0; hf < 8; hf++) X[hf] = yy == 0 ? in[hf].x : yy == 1 ? in[hf].y : yy == 2 ? in[hf].z : in[hf].w;
+        Idct8(X, px);
+        __stcs(reinterpret_cast<float4*>(out + size_t(yy) * f.xpad), make_float4(px[0], px[1], px[2], px[3]));
+        __stcs(reinterpret_cast<float4*>(out + size_t(yy) * f.xpad + 4), make_float4(px[4], px[5], px[6], px[7]));
+      }
     }
-    __syncwarp();
     cur = nxt;
   }
 }
@@ -530,7 +576,10 @@ __global__ void k_output_int(const DFrame* fp) {
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st) {
   static bool attr[64] = {false}; size_t smem = size_t(kReconWarps) * 3072 * sizeof(float); int dev = 0; cudaGetDevice(&dev);
   if (!attr[dev & 63]) { cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; }
-  k_reconstruct_dct8<<<h.num_groups * 4, 256, 0, st>>>(h); k_reconstruct<<<h.num_groups, kReconWarps * 32, smem, st>>>(d); CountLaunch(2);
+  { const int items = int(h.num_groups) * 32; const int grid = std::min(items, 148 * 3); const size_t d8smem = size_t(2) * 3 * 32 * kD8Stride * sizeof(float);
+    static bool attr8[64] = {false}; if (!attr8[dev & 63]) { cudaFuncSetAttribute(k_reconstruct_dct8, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d8smem)); attr8[dev & 63] = true; }
+    k_reconstruct_dct8<<<grid, 256, d8smem, st>>>(h, items); }
+  k_reconstruct<<<h.num_groups, kReconWarps * 32, smem, st>>>(d); CountLaunch(2);
 }
 // Runs gaborish + EPF; ping-pongs between xyb and xyb_tmp. Returns the buffer holding the result.
 void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {

@@ -17,11 +17,15 @@ def step(infl):
     st = P.decode_batch(None, device=0, max_in_flight=infl, device_inputs=[t.data_ptr() for t in dev_in], device_outputs=[t.data_ptr() for t in dev_out], sizes=[t.numel() for t in dev_in], out_sizes=[W * H * 3] * B)
     assert all(s == 0 for s in st)
 configs = [(1, 128), (2, 128), (4, 128), (8, 128), (4, 256), (8, 256)] if len(sys.argv) < 3 else [tuple(int(v) for v in c.split(":")) for c in sys.argv[2:]]
-for threads, infl in configs:
+for cfg in configs:
+    threads, infl = cfg[0], cfg[1]
     os.environ["JXLB200_HOST_THREADS"] = str(threads)
+    os.environ["JXLB200_AC_LANES"] = str(cfg[2]) if len(cfg) > 2 else "0"
+    os.environ["JXLB200_BUNDLE"] = str(cfg[3]) if len(cfg) > 3 else "0"
+    os.environ["JXLB200_AC_SMEM_KB"] = str(cfg[4]) if len(cfg) > 4 else "0"
     for _ in range(3): step(infl)
     torch.cuda.synchronize(); ts = []
     for _ in range(4):
         t = time.time(); step(infl); torch.cuda.synchronize(); ts.append(time.time() - t)
     dt = sum(ts) / len(ts)
-    print(json.dumps({"host_threads": threads, "in_flight": infl, "batch": B, "mp_s": round(B * W * H / 1e6 / dt), "ms_per_image": round(dt * 1e3 / B, 3), "step_ms": [round(x * 1e3) for x in ts]}), flush=True)
+    print(json.dumps({"host_threads": threads, "in_flight": infl, "lanes": os.environ["JXLB200_AC_LANES"], "bundle": os.environ["JXLB200_BUNDLE"], "ac_smem_kb": os.environ["JXLB200_AC_SMEM_KB"], "batch": B, "mp_s": round(B * W * H / 1e6 / dt), "ms_per_image": round(dt * 1e3 / B, 3), "step_ms": [round(x * 1e3) for x in ts]}), flush=True)
