@@ -232,6 +232,8 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
     // q1/q2/q3 hold the bundles whose phase 1/2/3 is running.
     struct Bundle { std::vector<std::unique_ptr<InFlight>> items; cudaStream_t stream = nullptr; };
     std::deque<std::unique_ptr<Bundle>> q1, q2, q3; int next = 0, done = 0;
+    const double t_start = now(); double ph_first[3] = {-1, -1, -1}, ph_last[3] = {0, 0, 0};   // trace: when the first / last bundle left phase 1, 2, 3
+    auto stamp = [&](int ph) { const double t = now() - t_start; if (ph_first[ph] < 0) ph_first[ph] = t; ph_last[ph] = t; };
     auto finish = [&](InFlight& f) {   // records the status of a finished or failed image
       DecoderStatus st = DecoderStatus(f.res.status);
       if (st == DecoderStatus_Ok) {
@@ -257,17 +259,17 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
         if (!idle(*q3[k])) { k++; continue; }
         Bundle& b = *q3[k];
         for (auto& f : b.items) { DecodeFinish(f->job, &f->res); finish(*f); }
-        free_streams.push_back(b.stream); q3.erase(q3.begin() + k); progressed = true;
+        free_streams.push_back(b.stream); q3.erase(q3.begin() + k); progressed = true; stamp(2);
       }
       for (size_t k = 0; k < std::min(kWindow, q2.size());) {
         if (!idle(*q2[k])) { k++; continue; }
-        std::unique_ptr<Bundle> b = std::move(q2[k]); q2.erase(q2.begin() + k); progressed = true;
+        std::unique_ptr<Bundle> b = std::move(q2[k]); q2.erase(q2.begin() + k); progressed = true; stamp(1);
         next_phase(*b, 3);
         if (b->items.empty()) free_streams.push_back(b->stream); else q3.push_back(std::move(b));
       }
       for (size_t k = 0; k < std::min(kWindow, q1.size());) {
         if (!idle(*q1[k])) { k++; continue; }
-        std::unique_ptr<Bundle> b = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true;
+        std::unique_ptr<Bundle> b = std::move(q1[k]); q1.erase(q1.begin() + k); progressed = true; stamp(0);
         next_phase(*b, 2);
         if (b->items.empty()) free_streams.push_back(b->stream); else q2.push_back(std::move(b));
       }
@@ -296,6 +298,7 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
     }
     if (trace) { DumpHostTrace(); if (slot == 0) DumpPoolStats(); }
     if (trace && acc_t[4] > 0) fprintf(stderr, "[jxlb200] shard %d GPU ms/image under load (JXLB200_TRACE=2 events): lf %.2f ac %.2f recon %.2f render %.2f total %.2f\n", slot, acc_t[0] / count, acc_t[1] / count, acc_t[2] / count, acc_t[3] / count, acc_t[4] / count);
+    if (trace) fprintf(stderr, "[jxlb200] shard %d phase exits, ms after shard start (first .. last bundle): LF %.1f .. %.1f, AC %.1f .. %.1f, tiles %.1f .. %.1f\n", slot, ph_first[0], ph_last[0], ph_first[1], ph_last[1], ph_first[2], ph_last[2]);
     if (trace) fprintf(stderr, "[jxlb200] shard %d, %d images: host parse + LF phase %.2f ms (%.2f ms/image), polling + later phases + retire %.2f ms, idle (GPU-bound) %.2f ms\n", slot, count, t_enq, t_enq / std::max(count, 1), t_ret, t_idle);
   } catch (const std::exception& e) {
     // Work may still be running on this shard's streams and writing into caller-owned buffers: wait for it before returning them.

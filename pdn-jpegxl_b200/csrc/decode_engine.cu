@@ -351,6 +351,7 @@ void DecodeJob::Setup(const DecodeRequest& req) {
       for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) { double v = 0; for (int k = 0; k < 3; k++) v += Bi[3 * r + k] * A[3 * k + cc]; c.to_target[3 * r + cc] = float(v); }
     }
   }
+  for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) { double v = 0; for (int k = 0; k < 3; k++) v += double(c.to_target[3 * r + k]) * double(c.opsin_inv[3 * k + cc]); c.mix_to_target[3 * r + cc] = float(v * double(c.itscale)); }
   // output description
   DOutput& o = h.out; o.sample_type = uint32_t(info.sample_type); o.num_channels = uint32_t(info.num_channels); o.color_channels = uint32_t(m.num_color_channels()); o.orientation = m.orientation; o.bgra = bgra ? 1 : 0;
   o.out_w = m.orientation >= 5 ? fh.ysize : fh.xsize; o.out_h = m.orientation >= 5 ? fh.xsize : fh.ysize; o.bits = m.bd.bits; o.exp_bits = m.bd.exp_bits;

@@ -15,7 +15,8 @@ struct DLoopFilter {
   uint32_t gab, epf_iters; float gab_w[6]; float epf_sharp_lut[8]; float epf_channel_scale[3]; float epf_quant_mul, pass0_sigma_scale, pass2_sigma_scale, border_sad_mul, sigma_for_modular;
 };
 struct DColor {
-  float opsin_inv[9]; float opsin_bias[3]; float opsin_bias_cbrt[3]; float itscale; float intensity_target; float to_target[9];   // linear sRGB -> target primaries
+  float opsin_inv[9]; float opsin_bias[3]; float opsin_bias_cbrt[3]; float itscale; float intensity_target; float mix_to_target[9];   // to_target * opsin_inv * itscale, folded on the host: one 3x3 product per pixel
+  float to_target[9];   // linear sRGB -> target primaries
   uint32_t tf; float gamma; uint32_t xyb_encoded; uint32_t num_color;   // tf: host ColorEncoding tf enum, 0 = pure gamma (gamma = exponent)
 };
 struct DOutput {

@@ -10,9 +10,12 @@
 #include "frame.cuh"
 #include "kernels.h"
 #include "enc_frame.cuh"
+#include "idct_tables.inc"
 #include <atomic>
 #include <cuda_fp16.h>
+#include <cuda.h>
 #include <cmath>
+#include <cstdlib>
 
 namespace jxlgpu {
 
@@ -95,6 +98,64 @@ __device__ __forceinline__ void Idct8(const float X[8], float y[8]) {
   const float o2 = fmaf(k5, X[1], fmaf(-k1, X[3], fmaf(k7, X[5], k3 * X[7])));
   const float o3 = fmaf(k7, X[1], fmaf(-k5, X[3], fmaf(k3, X[5], -k1 * X[7])));
   y[0] = e0 + o0; y[7] = e0 - o0; y[1] = e1 + o1; y[6] = e1 - o1; y[2] = e2 + o2; y[5] = e2 - o2; y[3] = e3 + o3; y[4] = e3 - o3;
+}
+
+// N-point inverse DCT (N = 8, 16, 32) on register arrays by the even/odd recursion: the even-indexed coefficients are an N/2-point
+// IDCT, the odd ones an (N/2)x(N/2) product with compile-time constants (FFMA immediates after unrolling): 114 flops for N = 16 and
+// 402 for N = 32 instead of N^2, and no cosine-table loads.
+template <int N> struct IdctN;
+template <> struct IdctN<8> { static __device__ __forceinline__ void Run(const float* X, float* y) { Idct8(X, y); } };
+template <> struct IdctN<16> { static __device__ __forceinline__ void Run(const float* X, float* y) {
+  float e[8], ye[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = X[2 * i];
+  Idct8(e, ye);
+#pragma unroll
+  for (int n = 0; n < 8; n++) { float o = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o = fmaf(kOdd16[i][n], X[2 * i + 1], o);
+    y[n] = ye[n] + o; y[15 - n] = ye[n] - o; } } };
+template <> struct IdctN<32> { static __device__ __forceinline__ void Run(const float* X, float* y) {
+  float e[16], ye[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) e[i] = X[2 * i];
+  IdctN<16>::Run(e, ye);
+#pragma unroll
+  for (int n = 0; n < 16; n++) { float o = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) o = fmaf(kOdd32[i][n], X[2 * i + 1], o);
+    y[n] = ye[n] + o; y[31 - n] = ye[n] - o; } } };
+
+// Both passes of a separable SW x SH inverse transform for one warp. S holds the dequantised block in storage layout (SH rows of SW
+// coefficients, row stride STR = SW + 4 floats so that LDS.128 by 8 consecutive rows is conflict-free), T is scratch of the same shape.
+// Pass 1: lane r transforms storage row r (SW-point IDCT in registers). Pass 2: lane j transforms column j (SH-point) and writes
+// pixels: a contiguous run of SH floats per lane when the block is at least as tall as wide, one coalesced row per step otherwise.
+template <int SW, int SH>
+__device__ __forceinline__ void InverseSeparable(const float* S, float* T, float* out, size_t xpad, bool tall, int lane) {
+  constexpr int STR = SW + 4;
+  if (lane < SH) {
+    float X[SW], y[SW];
+#pragma unroll
+    for (int k = 0; k < SW; k += 4) { const float4 v = *reinterpret_cast<const float4*>(S + lane * STR + k); X[k] = v.x; X[k + 1] = v.y; X[k + 2] = v.z; X[k + 3] = v.w; }
+    IdctN<SW>::Run(X, y);
+#pragma unroll
+    for (int k = 0; k < SW; k += 4) *reinterpret_cast<float4*>(T + lane * STR + k) = make_float4(y[k], y[k + 1], y[k + 2], y[k + 3]);
+  }
+  __syncwarp();
+  if (lane < SW) {
+    float X[SH], y[SH];
+#pragma unroll
+    for (int r = 0; r < SH; r++) X[r] = T[r * STR + lane];
+    IdctN<SH>::Run(X, y);
+    if (tall) {   // long axis vertical: lane = pixel row, y[] runs along x
+#pragma unroll
+      for (int i = 0; i < SH; i += 4) *reinterpret_cast<float4*>(out + size_t(lane) * xpad + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+    } else {      // long axis horizontal: lane = pixel column, y[] runs along y
+#pragma unroll
+      for (int i = 0; i < SH; i++) out[size_t(i) * xpad + lane] = y[i];
+    }
+  }
+  __syncwarp();
 }
 
 // Dequant + chroma-from-luma + LLF + 8x8 IDCT for every DCT8 varblock. A work item is one row of 32 cells of a 256x256 group; a CTA of
@@ -198,38 +259,41 @@ __global__ void __launch_bounds__(256, 3) k_reconstruct_dct8(const __grid_consta
 }
 
 static const int kReconWarps = 8;
-// dynamic smem per warp: Sy[1024] Sc[1024] T[1024] floats
+static const int kReconWarpFloats = 3 * 32 * 36;   // dynamic smem per warp: Sy, Sc, T
 __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* fp) {
   const DFrame& f = *fp; const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (!GroupInBand(f, g) || f.group_other[g] == 0) return;   // every varblock of this group is a DCT8: k_reconstruct_dct8 did all the work
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
-  extern __shared__ float smem[]; float* Sy = smem + warp * 3072; float* Sc = Sy + 1024; float* T = Sc + 1024;
+  extern __shared__ __align__(16) float smem[]; float* Sy = smem + warp * kReconWarpFloats; float* Sc = Sy + 32 * 36; float* T = Sc + 32 * 36;   // per warp: Sy, Sc, T of 32 rows x (32 + 4) floats
   const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const DTables& tb = *f.tables;
-  // ---- small varblocks (both sides <= 32 px): one warp per block
+  // ---- small varblocks (both sides <= 32 px): one warp per block. Separable DCTs of 8/16/32 points run as register-resident straight-line
+  // code (InverseSeparable); the 8x8 special transforms (IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4) are rare and stay with lane 0.
   for (int cell = warp; cell < 1024; cell += kReconWarps) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
     const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
     const int s = min(int(a & 31), 26), bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s); if (bw > 4 || bh > 4 || s == 0) continue;   // DCT8 is handled by k_reconstruct_dct8
-    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W); const float* dq = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[QuantTableOf(s)]));
+    const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W), STR = (s >= 4 && s <= 11) ? SW + 4 : SW; const float* dq = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[QuantTableOf(s)]));
     const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
     const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
-    const bool plain = (s == 0) || (s >= 4 && s <= 11);
+    const bool plain = s >= 4 && s <= 11; const int lsw = Log2Dev(SW);
     for (int c3 = 0; c3 < 3; c3++) {
       const int c = c3 == 0 ? 1 : c3 == 1 ? 0 : 2; float* S = c == 1 ? Sy : Sc;
       const float mulc = c == 1 ? scale : c == 0 ? scale * f.xm : scale * f.bm, kc = c == 0 ? kx : kb, b1 = f.quant_bias[c], b3 = f.quant_bias[3];
-      for (int p = lane; p < size; p += 32) { int q = coef[c * 65536 + CoefAddr(by, bx, bw, uint32_t(p))]; float v = AdjustQuantBiasDev(q, b1, b3) * dq[c * size + p] * mulc; if (c != 1) v += kc * Sy[p]; S[p] = v; }
+      for (int p = lane; p < size; p += 32) { const int sp = (p >> lsw) * STR + (p & (SW - 1)); int q = coef[c * 65536 + CoefAddr(by, bx, bw, uint32_t(p))];
+        float v = AdjustQuantBiasDev(q, b1, b3) * dq[c * size + p] * mulc; if (c != 1) v += kc * Sy[sp]; S[sp] = v; }
       __syncwarp();
-      LlfFromLf(f, c, bh, bw, f.lf_src + c * lfplane + o, int(f.xb), S, SW, lane, 32);
+      LlfFromLf(f, c, bh, bw, f.lf_src + c * lfplane + o, int(f.xb), S, STR, lane, 32);
       __syncwarp();
       float* out = f.xyb + c * plane + size_t(cy0 + by) * 8 * f.xpad + size_t(cx0 + bx) * 8;
       if (plain) {
-        const float* cl = tb.cosines + CosOff(Log2Dev(SW)); const float* cs = tb.cosines + CosOff(Log2Dev(SH));
-        for (int idx = lane; idx < SH * SW; idx += 32) { int r = idx / SW, j = idx % SW; float acc = 0; for (int k = 0; k < SW; k++) acc += S[r * SW + k] * cl[k * SW + j]; T[idx] = acc; }
-        __syncwarp();
-        for (int idx = lane; idx < SH * SW; idx += 32) { int i = idx / SW, j = idx % SW; float acc = 0; for (int r = 0; r < SH; r++) acc += T[r * SW + j] * cs[r * SH + i];
-          if (H >= W) out[size_t(j) * f.xpad + i] = acc; else out[size_t(i) * f.xpad + j] = acc; }
+        const bool tall = H >= W;
+        if (SW == 16 && SH == 16) InverseSeparable<16, 16>(S, T, out, f.xpad, tall, lane);
+        else if (SW == 32 && SH == 32) InverseSeparable<32, 32>(S, T, out, f.xpad, tall, lane);
+        else if (SW == 16 && SH == 8) InverseSeparable<16, 8>(S, T, out, f.xpad, tall, lane);
+        else if (SW == 32 && SH == 8) InverseSeparable<32, 8>(S, T, out, f.xpad, tall, lane);
+        else InverseSeparable<32, 16>(S, T, out, f.xpad, tall, lane);
       } else if (s >= 14 && s <= 17) { if (lane == 0) SetError(f.err, kErrBadStrategy); }
-      else if (lane == 0) SpecialTransform8x8(s, S, out, f.xpad, tb.cosines + CosOff(2), tb.cosines + CosOff(3));
+      else if (lane == 0) SpecialTransform8x8(s, S, out, f.xpad, tb.cosines + CosOff(2), tb.cosines + CosOff(3));   // 8x8 block, unpadded rows (STR = 8)
       __syncwarp();
     }
   }
@@ -381,11 +445,9 @@ __device__ __forceinline__ void XybToRgbDev(const DFrame& f, float X, float Y, f
     float gm[3] = {Y + X, Y - X, B}, mix[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) { float v = gm[c] - f.color.opsin_bias_cbrt[c]; mix[c] = v * v * v + f.color.opsin_bias[c]; }
-    float lin[6];
+    float lin[6];   // lin[3..5]: linear light in the target primaries (opsin inverse, intensity scale and primaries change are one matrix)
 #pragma unroll
-    for (int c = 0; c < 3; c++) lin[c] = (f.color.opsin_inv[3 * c] * mix[0] + f.color.opsin_inv[3 * c + 1] * mix[1] + f.color.opsin_inv[3 * c + 2] * mix[2]) * f.color.itscale;
-#pragma unroll
-    for (int c = 0; c < 3; c++) lin[c + 3] = f.color.to_target[3 * c] * lin[0] + f.color.to_target[3 * c + 1] * lin[1] + f.color.to_target[3 * c + 2] * lin[2];
+    for (int c = 0; c < 3; c++) lin[c + 3] = fmaf(f.color.mix_to_target[3 * c], mix[0], fmaf(f.color.mix_to_target[3 * c + 1], mix[1], f.color.mix_to_target[3 * c + 2] * mix[2]));
     if (f.color.tf == 13) {   // sRGB curve, the common case: branch-free per channel
 #pragma unroll
       for (int c = 0; c < 3; c++) { const float v = lin[c + 3], a = fabsf(v), r = a <= 0.0031308f ? 12.92f * a : 1.055f * PowSfu(a, 1.0f / 2.4f) - 0.055f; rgb[c] = v < 0 ? -r : r; }
@@ -559,6 +621,226 @@ __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DFrame f
     const int p = (H + ly) * D + H + lx; OutputPixel(f, x, y, src[p], src[N + p], src[2 * N + p]); }
 }
 
+// ------------------------------------------------------------------ fused render, wide-tile version
+// gaborish + EPF pass 1 (+ pass 2) + XYB -> RGB8 for the common output (RGB8, identity orientation) with 64x32 output tiles and
+// vector shared-memory accesses. Same arithmetic as k_render; what changes is the work per instruction:
+//   * 64x32 tiles: halo overhead (70x38)/(64x32) = 1.30 instead of 1.41 for 32x32, and rows of 72 floats so that every row starts
+//     16-byte aligned (x = -4 sits in column 0): interior tiles are loaded with aligned float4 loads, filters read LDS.128;
+//   * gaborish: a thread owns (channel, 4 columns, 9 rows) with a rolling three-row window: 3 shared loads per 4 outputs;
+//   * EPF: the 5-tap-cross SADs are sums of channel-weighted |horizontal| / |vertical| difference maps Dh, Dv built once; a thread
+//     filters a 4x2 patch and builds the cross sums of its patch from LDS.128 rows, ~6 shared loads per pixel instead of 16;
+//   * colour + pack in registers, 12 contiguous bytes per thread and row.
+// Buffers: A[3][38][72] (raw XYB; later Dh = A[0], Dv = A[1]), B[3][38][72] (after gaborish). Row r <-> y = ty0 - 3 + r, column c <-> x = tx0 - 4 + c.
+static const int kRfS = 72, kRfRows = 38, kRfPlane = kRfS * kRfRows;
+static const int kRfBuf = (3 * kRfPlane * 4 + 127) / 128 * 128 / 4;   // floats per three-plane buffer, padded so that every buffer starts 128-byte aligned (TMA destination)
+__device__ __forceinline__ bool WideTileInterior(const DFrame& f, int tx0, int ty0) { return tx0 >= 4 && tx0 + 68 <= int(f.xsize) && ty0 >= 3 && ty0 + 35 <= int(f.ysize); }
+// tile + halo -> A with mirrored image borders (the slow path of border tiles; interior tiles use float4 loads or TMA)
+__device__ __forceinline__ void WideTileFillMirrored(const DFrame& f, float* A, int tx0, int ty0, int tid) {
+  const int xs = int(f.xsize), ys = int(f.ysize); const size_t plane = size_t(f.xpad) * f.ypad;
+  for (int i = tid; i < 3 * kRfRows * kRfS; i += 256) { const int c = i / kRfPlane, rem = i - c * kRfPlane, r = rem / kRfS, col = rem - r * kRfS;
+    A[i] = f.xyb[c * plane + size_t(MirrorDev(ty0 - 3 + r, ys)) * f.xpad + MirrorDev(tx0 - 4 + col, xs)]; }
+}
+// Stages 1-3 on a tile whose raw samples sit in A (visible to every thread). Ends with the pixel stores; the caller synchronises before
+// A or B are written again.
+template <int EPF, bool BGRA>
+__device__ __forceinline__ void WideTileStages(const DFrame& f, float* A, float* B, const float* s_is, const int tx0, const int ty0, const int tid) {
+  static_assert(EPF == 1, "pass 2 is handled by k_render");
+  const int xs = int(f.xsize), ys = int(f.ysize);
+  // ---- stage 1: gaborish A -> B on rows 1..36 (y = -2..33); thread = (channel, quad column, 9-row strip)
+  if (tid < 216) {
+    const int c = tid / 72, rem = tid - c * 72, q = rem % 18, strip = rem / 18, r0 = 1 + strip * 9;
+    const float w1 = f.lpf.gab_w[2 * c], w2 = f.lpf.gab_w[2 * c + 1], m0 = 1.0f / (1.0f + 4.0f * (w1 + w2)), m1 = w1 * m0, m2 = w2 * m0;
+    const float* src = A + c * kRfPlane + 4 * q; float* dst = B + c * kRfPlane + 4 * q; const int lo = q == 0 ? 0 : -1, hi = q == 17 ? 3 : 4;
+    auto load = [&](int r, float4& v, float4& sd) { const float* p = src + r * kRfS; v = *reinterpret_cast<const float4*>(p); const float L = p[lo], R = p[hi];
+      sd = make_float4(L + v.y, v.x + v.z, v.y + v.w, v.z + R); };
+    float4 c0, s0, c1, s1, c2, s2; load(r0 - 1, c0, s0); load(r0, c1, s1);
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      load(r0 + k + 1, c2, s2);
+      float4 o;
+      o.x = c1.x * m0 + (c0.x + c2.x + s1.x) * m1 + (s0.x + s2.x) * m2; o.y = c1.y * m0 + (c0.y + c2.y + s1.y) * m1 + (s0.y + s2.y) * m2;
+      o.z = c1.z * m0 + (c0.z + c2.z + s1.z) * m1 + (s0.z + s2.z) * m2; o.w = c1.w * m0 + (c0.w + c2.w + s1.w) * m1 + (s0.w + s2.w) * m2;
+      *reinterpret_cast<float4*>(dst + (r0 + k) * kRfS) = o; c0 = c1; s0 = s1; c1 = c2; s1 = s2;
+    }
+  }
+  __syncthreads();
+  // ---- stage 2: difference maps from B: Dh(r, c) = sum_ch scale * |B(r, c+1) - B(r, c)| -> A[0], Dv(r, c) = sum_ch scale * |B(r+1, c) - B(r, c)| -> A[1], rows 1..35
+  if (tid < 252) {
+    const int q = tid % 18, part = tid / 18, r0 = 1 + (part < 7 ? part * 3 : 21 + (part - 7) * 2), nr = part < 7 ? 3 : 2, hi = q == 17 ? 3 : 4;
+    const float cs[3] = {f.lpf.epf_channel_scale[0], f.lpf.epf_channel_scale[1], f.lpf.epf_channel_scale[2]};
+    float4 cur[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) cur[c] = *reinterpret_cast<const float4*>(B + c * kRfPlane + r0 * kRfS + 4 * q);
+    for (int k = 0; k < nr; k++) {
+      const int r = r0 + k; float4 dh = make_float4(0.f, 0.f, 0.f, 0.f), dv = dh;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float* p = B + c * kRfPlane + r * kRfS + 4 * q; const float R = p[hi]; const float4 nx = *reinterpret_cast<const float4*>(p + kRfS), v = cur[c];
+        dh.x = fmaf(fabsf(v.y - v.x), cs[c], dh.x); dh.y = fmaf(fabsf(v.z - v.y), cs[c], dh.y); dh.z = fmaf(fabsf(v.w - v.z), cs[c], dh.z); dh.w = fmaf(fabsf(R - v.w), cs[c], dh.w);
+        dv.x = fmaf(fabsf(nx.x - v.x), cs[c], dv.x); dv.y = fmaf(fabsf(nx.y - v.y), cs[c], dv.y); dv.z = fmaf(fabsf(nx.z - v.z), cs[c], dv.z); dv.w = fmaf(fabsf(nx.w - v.w), cs[c], dv.w);
+        cur[c] = nx;
+      }
+      *reinterpret_cast<float4*>(A + r * kRfS + 4 * q) = dh; *reinterpret_cast<float4*>(A + kRfPlane + r * kRfS + 4 * q) = dv;
+    }
+  }
+  __syncthreads();
+  // ---- stage 3: EPF pass 1 on a 4x2 patch per thread, then colour + pack
+  const int px = tid & 15, py = tid >> 4, col = 4 + 4 * px, r0 = 3 + 2 * py;   // patch: columns col..col+3 (x = 4 px ..), rows r0, r0+1 (y = 2 py, 2 py + 1)
+  const float* Dh = A; const float* Dv = A + kRfPlane;
+  float outv[3][2][4];
+  {
+    const float is = s_is[(py >> 2) * 8 + (px >> 1)];
+    if (is < -3.90524291751269967465540850526868f) {
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) { const float4 v = *reinterpret_cast<const float4*>(B + c * kRfPlane + (r0 + j) * kRfS + col); outv[c][j][0] = v.x; outv[c][j][1] = v.y; outv[c][j][2] = v.z; outv[c][j][3] = v.w; }
+    } else {
+      // cross sums Ch(r, c) = Dh(r-1,c) + Dh(r,c) + Dh(r+1,c) + Dh(r,c-1) + Dh(r,c+1) at columns col-1..col+3, rows r0, r0+1:
+      // SAD towards the right neighbour of pixel (r, c) is Ch(r, c), towards the left neighbour Ch(r, c-1)
+      float hrow[4][5];   // Dh rows r0-1..r0+2, columns col-1..col+3
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const float* p = Dh + (r0 - 1 + k) * kRfS + col; const float4 v = *reinterpret_cast<const float4*>(p); hrow[k][0] = p[-1]; hrow[k][1] = v.x; hrow[k][2] = v.y; hrow[k][3] = v.z; hrow[k][4] = v.w; }
+      float Ch[2][5];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const float* p = Dh + (r0 + j) * kRfS + col; const float l2 = p[-2], r4 = p[4];
+#pragma unroll
+        for (int i = 0; i < 5; i++) { const float left = i == 0 ? l2 : hrow[j + 1][i - 1], right = i == 4 ? r4 : hrow[j + 1][i + 1]; Ch[j][i] = hrow[j][i] + hrow[j + 1][i] + hrow[j + 2][i] + left + right; }
+      }
+      // Cv(r, c) = Dv(r-1,c) + Dv(r,c) + Dv(r+1,c) + Dv(r,c-1) + Dv(r,c+1) at rows r0-1..r0+1, columns col..col+3:
+      // SAD towards the lower neighbour of pixel (r, c) is Cv(r, c), towards the upper neighbour Cv(r-1, c)
+      float vrow[5][4];   // Dv rows r0-2..r0+2
+#pragma unroll
+      for (int k = 0; k < 5; k++) { const float4 v = *reinterpret_cast<const float4*>(Dv + (r0 - 2 + k) * kRfS + col); vrow[k][0] = v.x; vrow[k][1] = v.y; vrow[k][2] = v.z; vrow[k][3] = v.w; }
+      float Cv[3][4];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const float* p = Dv + (r0 - 1 + j) * kRfS + col; const float l1 = p[-1], r4 = p[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float left = i == 0 ? l1 : vrow[j + 1][i - 1], right = i == 3 ? r4 : vrow[j + 1][i + 1]; Cv[j][i] = vrow[j][i] + vrow[j + 1][i] + vrow[j + 2][i] + left + right; }
+      }
+      const float sm = 1.65f, smb = sm * f.lpf.border_sad_mul;   // pass 1 has sigma scale 1
+      float wl[2][4], wr[2][4], wu[2][4], wd[2][4], iw[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int xm = (4 * px + i) & 7, ym = (2 * py + j) & 7; const bool border = xm == 0 || xm == 7 || ym == 0 || ym == 7; const float inv = is * (border ? smb : sm);
+          wr[j][i] = fmaxf(0.f, fmaf(Ch[j][i + 1], inv, 1.0f)); wl[j][i] = fmaxf(0.f, fmaf(Ch[j][i], inv, 1.0f));
+          wd[j][i] = fmaxf(0.f, fmaf(Cv[j + 1][i], inv, 1.0f)); wu[j][i] = fmaxf(0.f, fmaf(Cv[j][i], inv, 1.0f));
+          iw[j][i] = __fdividef(1.0f, 1.0f + wu[j][i] + wl[j][i] + wr[j][i] + wd[j][i]);   // MUFU.RCP: the sum is in [1, 5]
+        }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float prow[4][6];   // B rows r0-1..r0+2, columns col-1..col+4 (the corner entries of the outer rows are not used)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const float* p = B + c * kRfPlane + (r0 - 1 + k) * kRfS + col; const float4 v = *reinterpret_cast<const float4*>(p); prow[k][1] = v.x; prow[k][2] = v.y; prow[k][3] = v.z; prow[k][4] = v.w;
+          if (k == 1 || k == 2) { prow[k][0] = p[-1]; prow[k][5] = p[4]; } }
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            outv[c][j][i] = (prow[j + 1][i + 1] + wu[j][i] * prow[j][i + 1] + wl[j][i] * prow[j + 1][i] + wr[j][i] * prow[j + 1][i + 2] + wd[j][i] * prow[j + 2][i + 1]) * iw[j][i];
+      }
+    }
+  }
+  // ---- colour + pack: 4 pixels = 12 bytes per row (RGB8) or one 16-byte store (BGRA32 surface, A = 255: S/JpegXLLoad.cs:219-249 with an opaque layer)
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int y = ty0 + 2 * py + j, x = tx0 + 4 * px; uint32_t b[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float rgb[3]; XybToRgbDev(f, outv[0][j][i], outv[1][j][i], outv[2][j][i], rgb);
+#pragma unroll
+      for (int c = 0; c < 3; c++) b[3 * i + c] = uint32_t(__float2int_rn(fminf(1.f, fmaxf(0.f, rgb[c])) * 255.0f)); }
+    if (y >= ys || x >= xs) continue;
+    if (f.band_on && (y < int(f.out_y0) || y >= int(f.out_y1))) continue;
+    if (BGRA) {
+      uint32_t* row4 = reinterpret_cast<uint32_t*>(f.out_px) + size_t(y - int(f.out_y0)) * xs + x; uint32_t v[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) v[i] = b[3 * i + 2] | (b[3 * i + 1] << 8) | (b[3 * i] << 16) | 0xff000000u;
+      if (x + 4 <= xs && (xs & 3) == 0) *reinterpret_cast<uint4*>(row4) = make_uint4(v[0], v[1], v[2], v[3]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (x + i < xs) row4[i] = v[i];
+      }
+      continue;
+    }
+    uint8_t* row = f.out_px + (size_t(y - int(f.out_y0)) * xs + x) * 3;
+    if (x + 4 <= xs && (reinterpret_cast<uintptr_t>(row) & 3) == 0) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(row);
+      w[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); w[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24); w[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) if (x + i < xs) { row[3 * i] = uint8_t(b[3 * i]); row[3 * i + 1] = uint8_t(b[3 * i + 1]); row[3 * i + 2] = uint8_t(b[3 * i + 2]); }
+    }
+  }
+}
+
+// Front-end 1: one CTA per tile, the tile is loaded by the threads themselves (aligned float4 loads for interior tiles).
+template <int EPF, bool BGRA>
+__global__ void __launch_bounds__(256, 2) k_render_wide(const __grid_constant__ DFrame f) {
+  extern __shared__ __align__(128) float rw[];
+  float* A = rw; float* B = rw + kRfBuf; __shared__ float s_is[32];
+  const int tid = threadIdx.x, tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 32;
+  if (f.band_on && (ty0 + 32 <= int(f.out_y0) || ty0 >= int(f.out_y1))) return;
+  const size_t plane = size_t(f.xpad) * f.ypad;
+  if (tid < 32) { const int by = (ty0 >> 3) + (tid >> 3), bx = (tx0 >> 3) + (tid & 7); s_is[tid] = (by < int(f.yb) && bx < int(f.xb)) ? f.inv_sigma[size_t(by) * f.xb + bx] : 0.f; }
+  if (WideTileInterior(f, tx0, ty0)) {
+    for (int i = tid; i < 3 * kRfRows * 18; i += 256) { const int c = i / (kRfRows * 18), rem = i - c * kRfRows * 18, r = rem / 18, q = rem - r * 18;
+      reinterpret_cast<float4*>(A)[i] = __ldg(reinterpret_cast<const float4*>(f.xyb + c * plane + size_t(ty0 - 3 + r) * f.xpad + tx0 - 4) + q); }
+  } else WideTileFillMirrored(f, A, tx0, ty0, tid);
+  __syncthreads();
+  WideTileStages<EPF, BGRA>(f, A, B, s_is, tx0, ty0, tid);
+}
+
+// Front-end 2 (the default): persistent CTAs, two per SM, that walk the tiles with a grid stride; the raw 72x38x3 box of the NEXT tile is
+// fetched by one TMA operation (cp.async.bulk.tensor.3d, completion on an mbarrier) into the second raw buffer while the current tile is
+// filtered, so no warp ever waits on HBM latency inside the stages. Border tiles (mirrored samples: TMA can only zero-fill) are loaded
+// by the threads. The A/B against front-end 1 is in profiles/ (JXLB200_RENDER_TMA=0 selects front-end 1).
+__device__ __forceinline__ uint32_t SmemU32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+template <int EPF, bool BGRA>
+__global__ void __launch_bounds__(256, 2) k_render_wide_tma(const __grid_constant__ DFrame f, const __grid_constant__ CUtensorMap tmap, const int ntx, const int ntiles) {
+  extern __shared__ __align__(128) float rw[];
+  float* B = rw + 2 * kRfBuf;   // raw buffers: rw + b * kRfBuf, b = 0, 1
+  __shared__ __align__(8) unsigned long long bar[2]; __shared__ float s_is[32];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(SmemU32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(SmemU32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto tile_xy = [&](int t, int& tx0, int& ty0) { tx0 = (t % ntx) * 64; ty0 = (t / ntx) * 32; };
+  auto in_band = [&](int ty0) { return !f.band_on || !(ty0 + 32 <= int(f.out_y0) || ty0 >= int(f.out_y1)); };
+  auto issue = [&](int t, int b) {   // one thread: arm the barrier with the box size and start the bulk copy
+    int tx0, ty0; tile_xy(t, tx0, ty0);
+    if (tid != 0 || !in_band(ty0) || !WideTileInterior(f, tx0, ty0)) return;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last written through the generic proxy (difference maps)
+    const uint32_t bytes = 3u * kRfPlane * 4u, mb = SmemU32(&bar[b]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(SmemU32(rw + b * kRfBuf)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(mb), "r"(tx0 - 4), "r"(ty0 - 3), "r"(0) : "memory");
+  };
+  uint32_t phase_bits = 0u;   // bit b: parity of buffer b's barrier
+  int t = blockIdx.x; if (t < ntiles) issue(t, 0);
+  for (int b = 0; t < ntiles; t += int(gridDim.x), b ^= 1) {
+    if (t + int(gridDim.x) < ntiles) issue(t + int(gridDim.x), b ^ 1);
+    int tx0, ty0; tile_xy(t, tx0, ty0);
+    if (!in_band(ty0)) continue;   // uniform over the CTA; no copy was issued for this tile
+    float* A = rw + b * kRfBuf;
+    if (tid < 32) { const int by = (ty0 >> 3) + (tid >> 3), bx = (tx0 >> 3) + (tid & 7); s_is[tid] = (by < int(f.yb) && bx < int(f.xb)) ? f.inv_sigma[size_t(by) * f.xb + bx] : 0.f; }
+    if (WideTileInterior(f, tx0, ty0)) {
+      const uint32_t mb = SmemU32(&bar[b]), ph = (phase_bits >> b) & 1u; uint32_t ok = 0;
+      while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mb), "r"(ph) : "memory");
+      phase_bits ^= 1u << b;
+    } else WideTileFillMirrored(f, A, tx0, ty0, tid);
+    __syncthreads();
+    WideTileStages<EPF, BGRA>(f, A, B, s_is, tx0, ty0, tid);
+    __syncthreads();   // every read of A / B is done before the next copy lands in A's partner and before B is rewritten
+  }
+}
+
 // Lossless 8/16-bit integer fast path: samples pass through untouched (bit-exact by construction).
 __global__ void k_output_int(const DFrame* fp) {
   const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
@@ -574,7 +856,7 @@ __global__ void k_output_int(const DFrame* fp) {
 }
 
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st) {
-  static bool attr[64] = {false}; size_t smem = size_t(kReconWarps) * 3072 * sizeof(float); int dev = 0; cudaGetDevice(&dev);
+  static bool attr[64] = {false}; size_t smem = size_t(kReconWarps) * kReconWarpFloats * sizeof(float); int dev = 0; cudaGetDevice(&dev);
   if (!attr[dev & 63]) { cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; }
   { const int items = int(h.num_groups) * 32; const int grid = std::min(items, 148 * 3); const size_t d8smem = size_t(2) * 3 * 32 * kD8Stride * sizeof(float);
     static bool attr8[64] = {false}; if (!attr8[dev & 63]) { cudaFuncSetAttribute(k_reconstruct_dct8, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d8smem)); attr8[dev & 63] = true; }
@@ -594,15 +876,41 @@ void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {
 }
 void LaunchGaborishPlanes(const DFrame* d, const DFrame& h, const float* src, float* dst, cudaStream_t st) { dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8); k_gaborish<<<grid, blk, 0, st>>>(d, src, dst); CountLaunch(); }
 const float* FilteredPlanes(const DFrame& h) { int n = (h.lpf.gab ? 1 : 0) + (h.lpf.epf_iters == 3 ? 3 : int(h.lpf.epf_iters)); return (n & 1) ? h.xyb_tmp : h.xyb; }
+// TMA descriptor of the three XYB planes as one rank-3 fp32 tensor {xpad, ypad, 3}, box {72, 38, 3}: one bulk copy fetches a whole
+// tile-plus-halo into the dense [plane][row][72] layout the filters read. The driver entry point is looked up at run time (no libcuda link).
+static bool EncodeXybTensorMap(const DFrame& h, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = []() -> EncodeFn { void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; } return reinterpret_cast<EncodeFn>(p); }();
+  if (!fn || h.xpad < 72 || h.ypad < 38) return false;
+  const cuuint64_t gdim[3] = {h.xpad, h.ypad, 3}, gstride[2] = {cuuint64_t(h.xpad) * 4, cuuint64_t(h.xpad) * h.ypad * 4}; const cuuint32_t box[3] = {kRfS, kRfRows, 3}, es[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h.xyb, gdim, gstride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // gaborish + EPF + colour in one pass over the frame (VarDCT frames with at least one restoration filter)
 template <int GAB, int EPF> static void LaunchRenderT(const DFrame& h, cudaStream_t st) {
   constexpr int H = GAB + (EPF == 3 ? 3 : 0) + (EPF >= 1 ? 2 : 0) + (EPF >= 2 ? 1 : 0), D = 32 + 2 * H; size_t smem = (size_t(EPF ? 8 : 6) * D * D + 64) * sizeof(float);
   { static bool attr[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (!attr[dev & 63]) { cudaFuncSetAttribute(k_render<GAB, EPF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cudaFuncSetAttribute(k_render<GAB, EPF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; } }
   const DOutput& o = h.out;
-  const bool fast = !o.bgra && o.sample_type == 0 && o.num_channels == 3 && o.color_channels == 3 && o.alpha_plane < 0 && o.black_plane < 0 && !o.premultiplied && o.orientation == 1 &&
-                    (size_t(h.xsize) * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(h.out_px) & 3) == 0;
+  const bool rgb8 = !o.bgra && o.sample_type == 0 && o.num_channels == 3 && o.color_channels == 3 && o.alpha_plane < 0 && o.black_plane < 0 && !o.premultiplied && o.orientation == 1;
+  const bool fast = rgb8 && (size_t(h.xsize) * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(h.out_px) & 3) == 0;
   dim3 grid((h.xsize + 31) / 32, (h.ysize + 31) / 32);
-  if (fast) k_render<GAB, EPF, true><<<grid, 256, smem, st>>>(h); else k_render<GAB, EPF, false><<<grid, 256, smem, st>>>(h);
+  static const bool no_wide = getenv("JXLB200_NO_WIDE_RENDER") != nullptr;
+  // opaque BGRA32 surface of an 8-bit RGB image (JxlB200LoadImageBgra, BASELINE config 2): the same kernel with a 16-byte store per 4 pixels
+  const bool fast_bgra = o.bgra && o.color_channels == 3 && o.alpha_plane < 0 && o.black_plane < 0 && !o.premultiplied && o.orientation == 1 && (reinterpret_cast<uintptr_t>(h.out_px) & 15) == 0;
+  if ((rgb8 || fast_bgra) && GAB == 1 && EPF == 1 && !no_wide) {   // rows that are not 4-byte aligned fall back to byte stores inside the kernel
+    const size_t wsmem = size_t(2) * kRfBuf * sizeof(float), tsmem = size_t(3) * kRfBuf * sizeof(float);
+    { static bool wattr[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (!wattr[dev & 63]) {
+        cudaFuncSetAttribute(k_render_wide<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wsmem)); cudaFuncSetAttribute(k_render_wide<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wsmem));
+        cudaFuncSetAttribute(k_render_wide_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tsmem)); cudaFuncSetAttribute(k_render_wide_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tsmem)); wattr[dev & 63] = true; } }
+    const dim3 wgrid((h.xsize + 63) / 64, (h.ysize + 31) / 32);
+    static const bool use_tma = !(getenv("JXLB200_RENDER_TMA") && atoi(getenv("JXLB200_RENDER_TMA")) == 0);
+    CUtensorMap tmap;
+    if (use_tma && EncodeXybTensorMap(h, &tmap)) {
+      const int ntiles = int(wgrid.x * wgrid.y), grid1 = std::min(ntiles, 148 * 2);
+      if (fast_bgra) k_render_wide_tma<1, true><<<grid1, 256, tsmem, st>>>(h, tmap, int(wgrid.x), ntiles); else k_render_wide_tma<1, false><<<grid1, 256, tsmem, st>>>(h, tmap, int(wgrid.x), ntiles);
+    } else if (fast_bgra) k_render_wide<1, true><<<wgrid, 256, wsmem, st>>>(h); else k_render_wide<1, false><<<wgrid, 256, wsmem, st>>>(h);
+  } else if (fast) k_render<GAB, EPF, true><<<grid, 256, smem, st>>>(h); else k_render<GAB, EPF, false><<<grid, 256, smem, st>>>(h);
   CountLaunch();
 }
 bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st) {
