@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstdio>
 #include <mutex>
+#include <atomic>
 #include <stdexcept>
 
 using namespace jxlgpu;
@@ -171,6 +172,9 @@ struct BatchArgs {
   int32_t bgra, hostInputs, hostOutputs; DecoderStatus* statuses;
 };
 struct ShardResult { DecoderStatus first = DecoderStatus_Ok; std::string message; };
+// Set once the caching pools of a device hold a full batch's buffer sets: until then only shard 0 enqueues (it reserves the sets when
+// its first image is parsed); the other shards would otherwise race it with one cudaMalloc per buffer while the GPU is busy.
+static std::atomic<int> g_pools_warm[64];
 
 // Streams are created once per (device, shard slot) and reused by later batches (stream creation is not free).
 static std::vector<cudaStream_t>& ShardStreams(int device, int slot, int want) {
@@ -287,8 +291,9 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
           DecodeRequest req; req.bgra = a.bgra != 0; req.device_output = !a.hostOutputs; req.size = a.dataSizes[i]; req.out_capacity = a.outputBytes[i]; req.ac_lanes = batch_lanes;
           if (a.hostInputs) req.data = a.datas[i]; else { cudaEventSynchronize(in_ready[li]); req.data = host_in + in_off[li]; req.device_input = a.datas[i]; }
           if (!a.hostOutputs) { req.out_device = a.outputs[i]; f->direct = true; } else if (out_is_pinned[li]) { req.out_pinned = a.outputs[i]; f->direct = true; }
+          if (reserve_sets == 0 && a.count >= 32) for (int spin = 0; spin < 40000 && !g_pools_warm[cur_dev & 63].load(); spin++) std::this_thread::sleep_for(std::chrono::microseconds(50));   // at most 2 s, first batch only
           f->job = DecodeEnqueue(req, b->stream, &f->res, true, bundle_size > 1);
-          if (f->job && !reserved) { reserved = true; DecodeReservePools(f->job, reserve_sets); }   // the first image tells the buffer sizes of the batch
+          if (!reserved) { reserved = true; if (f->job) DecodeReservePools(f->job, reserve_sets); g_pools_warm[cur_dev & 63].store(1); }   // the first image tells the buffer sizes of the batch
           if (f->job) b->items.push_back(std::move(f)); else finish(*f);
         }
         if (bundle_size > 1) DecodeBundleLaunch(jobs_of(*b), 1);
@@ -397,7 +402,7 @@ int32_t JxlB200DebugParseIcc(const uint8_t* icc, size_t iccSize, float* matrix9,
 }
 // Returns the cached device and page-locked buffers of the calling thread's current device to the driver (after a large batch the
 // pools hold one buffer set per image that was in flight).
-void JxlB200ReleaseMemory(void) { try { cudaDeviceSynchronize(); TrimPools(); } catch (...) {} }
+void JxlB200ReleaseMemory(void) { try { cudaDeviceSynchronize(); TrimPools(); for (auto& w : g_pools_warm) w.store(0); } catch (...) {} }
 
 void JxlB200LastStageTimes(float* ms8) { if (!ms8) return; const StageTimes& t = g_last_times; ms8[0] = t.h2d; ms8[1] = t.lf; ms8[2] = t.ac; ms8[3] = t.recon; ms8[4] = t.filters; ms8[5] = t.output; ms8[6] = t.d2h; ms8[7] = t.total; }
 int64_t JxlB200KernelLaunchCount(void) { return LaunchCount(); }

@@ -60,8 +60,8 @@ class Pool {
  private:
   // size classes: powers of two from 4 KiB up to 16 MiB (files of different sizes then share every small bucket, so the first image of
   // a batch can reserve for all of them), eighths of a power of two above (the big planes, whose size depends on the dimensions only)
-  static size_t Round(size_t b) { if (b <= 4096) return 4096; int k = 63 - __builtin_clzll(b - 1); if (b <= (size_t(16) << 20)) return size_t(2) << k; k = 63 - __builtin_clzll(b); size_t g = size_t(1) << (k - 3); return (b + g - 1) / g * g; }
-  void TrimLocked() { trims_++; for (auto& kv : free_) for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } free_.clear(); cached_ = 0; }
+  public: static size_t Round(size_t b) { if (b <= 4096) return 4096; int k = 63 - __builtin_clzll(b - 1); if (b <= (size_t(16) << 20)) return size_t(2) << k; k = 63 - __builtin_clzll(b); size_t g = size_t(1) << (k - 3); return (b + g - 1) / g * g; }
+  private: void TrimLocked() { trims_++; for (auto& kv : free_) for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } free_.clear(); cached_ = 0; }
   size_t Limit() { if (!limit_) { size_t fr = 0, tot = 0; if (pinned_ || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); limit_ = size_t(32) << 30; } else limit_ = tot / 4 * 3; } return limit_; }
   public: size_t misses_ = 0, trims_ = 0; std::map<size_t, size_t> miss_sizes_; std::string MissReport() { std::lock_guard<std::mutex> lk(mu_); std::string r; for (auto& kv : miss_sizes_) { r += " " + std::to_string(kv.first >> 10) + "K:" + std::to_string(kv.second) + "(free " + std::to_string(free_[kv.first].size()) + ")"; } return r; } size_t Cached() const { return cached_; }
  private:
@@ -226,7 +226,10 @@ class DecodeJob {
   void Setup(const DecodeRequest& req);
   void RunLf(const DecodeRequest& req); void RunAc(); void RunRender();
   void ReservePools(size_t count) { DevBuf* all[] = {&d_frame, &d_blob, &d_comp, &d_lfq, &d_lf, &d_lf_tmp, &d_acs, &d_qf, &d_sharp, &d_lfidx, &d_ytox, &d_ytob, &d_hfmeta, &d_coeffs, &d_xyb, &d_xyb_tmp, &d_sigma, &d_mod, &d_wp, &d_out, &d_err, &h_out, &h_err, &h_comp, &h_blob, &h_misc, &d_gother, &d_nz, &d_acend};
-    for (DevBuf* b : all) if (b->p && b->pool) b->pool->Reserve(b->n, count); }
+    // several buffers of a job share a size class (the small ones all round to 4 KiB): reserve count x multiplicity per class
+    std::map<std::pair<Pool*, size_t>, size_t> mult;
+    for (DevBuf* b : all) if (b->p && b->pool) mult[std::make_pair(b->pool, Pool::Round(b->n))]++;
+    for (auto& kv : mult) kv.first.first->Reserve(kv.first.second, count * kv.second); }
   void Run(const DecodeRequest& req) { RunLf(req); RunAc(); RunRender(); }
   void ParseLfGlobal(BitReader& br);
   void ParseHfGlobal(BitReader& br);
@@ -416,7 +419,8 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
     uint32_t modb = has_tree ? code_bytes(h.mod_code) + ((h.tree_size * 16 + 15) & ~15u) : 0;
     { static std::atomic<uint32_t> lf_cursor{0}, ac_cursor{0};   // concurrent images start their few long-running CTAs on different SMs
       h.lf_cta_offset = lf_cursor.fetch_add(h.num_lf_groups) % 148u; h.ac_cta_offset = vardct ? ac_cursor.fetch_add(uint32_t(AcCtas(h, ac_lanes))) % 148u : 0; }
-    h.lf_smem = std::min<uint32_t>(modb + 64, 96 * 1024); ac_budget = [this, code_bytes]() { uint32_t acb = 0; bool prefix = false; for (uint32_t p = 0; p < h.num_passes; p++) { acb = std::max(acb, code_bytes(h.ac_code[p])); prefix |= h.ac_code[p].use_prefix != 0; }
+    // + the transposed alias table of the speculative LF loop (32 slots x 8 bytes per alias entry), when it stays small
+    { const uint32_t spec = has_tree && !h.mod_code.use_prefix ? (256u << h.mod_code.log_alpha) : 0u; h.lf_smem = std::min<uint32_t>(modb + 64 + (spec <= 64 * 1024 ? spec + 16 : 0), 96 * 1024); } ac_budget = [this, code_bytes]() { uint32_t acb = 0; bool prefix = false; for (uint32_t p = 0; p < h.num_passes; p++) { acb = std::max(acb, code_bytes(h.ac_code[p])); prefix |= h.ac_code[p].use_prefix != 0; }
       h.ac_smem = acb + 64; h.ac_fast = (!prefix && h.ac_smem <= 96 * 1024) ? 1 : 0; if (!h.ac_fast) h.ac_smem = 0; };
     if (vardct && !single) ac_budget();
     { static const bool tr = getenv("JXLB200_TRACE") != nullptr; static std::atomic<int> shown{0}; if (tr && shown.fetch_add(1) < 2) fprintf(stderr, "[jxlb200] table staging: lf_smem %u B, ac_smem %u B (ac_fast %u), AC clusters %u, log_alpha %u\n", h.lf_smem, h.ac_smem, h.ac_fast, h.ac_code[0].num_clusters, h.ac_code[0].log_alpha); }

@@ -53,22 +53,45 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
   const int w = min(256, int(f.xb) - cx0), h = min(256, int(f.yb) - cy0), tw = (w + 7) / 8, th = (h + 7) / 8;
   int32_t* scratch = f.hfmeta_scratch + size_t(g) * kHfMetaScratchInts;
   int32_t* s_cflx = scratch; int32_t* s_cflb = scratch + 1024; int32_t* s_info = scratch + 2048; int32_t* s_sharp = scratch + 2048 + 2 * 65536;
-  __shared__ uint32_t sh_nb, sh_ok; __shared__ ChanLut sh_lut; extern __shared__ __align__(16) uint8_t dsm[];
-  ModDecoder md; BindModDecoder(md, f, &sh_lut); { uint32_t used = 0; StageModDecoder(md, f, dsm, f.lf_smem, used, lane, 32); }
+  __shared__ uint32_t sh_nb, sh_ok, sh_hdr_ok; __shared__ ChanLut sh_lut; __shared__ LeanSpecPrep sh_prep; extern __shared__ __align__(16) uint8_t dsm[];
+  uint32_t used = 0;
+  ModDecoder md; BindModDecoder(md, f, &sh_lut); StageModDecoder(md, f, dsm, f.lf_smem, used, lane, 32);
   __syncthreads();
+  // room left in the dynamic shared memory for the transposed alias table of the speculative loop (DecodeRowsLeanSpec)
+  const uint32_t spec_off = (used + 15u) & ~15u, spec_bytes = f.lf_smem > spec_off ? f.lf_smem - spec_off : 0u;
+  const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
+  const uint64_t end = single ? sec[nsec] : sec[nsec + 1 + g];
+  int32_t* wp = f.wp_scratch + size_t(g) * WPScratchInts(kMaxWpWidth);
+  const size_t plane = size_t(f.xb) * f.yb; const int lf_sid = 1 + g; long long dbg_t0 = 0;
+  // ---- part A (lane 0): section start, LF-coefficient sub-bitstream header
   if (lane == 0) {
     sh_ok = 0; sh_nb = 0;
-    const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
-    uint64_t start = single ? f.end_bitpos[0] : sec[1 + g]; uint64_t end = single ? sec[nsec] : sec[nsec + 1 + g];
+    const uint64_t start = single ? f.end_bitpos[0] : sec[1 + g];
     md.rd.br.Init(f.comp, start);
-    int32_t* wp = f.wp_scratch + size_t(g) * WPScratchInts(kMaxWpWidth);
     uint32_t extra_prec = md.rd.br.Read(2);
     f.hfmeta_scratch[size_t(f.num_lf_groups) * kHfMetaScratchInts + g] = int32_t(extra_prec);
-    bool ok = ReadGroupHeaderDev(md, f);
+    const bool ok = ReadGroupHeaderDev(md, f);
+    if (ok) md.rd.Init(md.cv);
+    sh_hdr_ok = ok ? 1 : 0; dbg_t0 = clock64();
+  }
+  __syncwarp();
+  // ---- part B (whole warp): the three LF-coefficient channels; stream channel order is Y, X, B (A.8 LfGroup)
+  if (sh_hdr_ok) {
+    for (int c = 0; c < 3; c++) {
+      const int dstc = c == 0 ? 1 : c == 1 ? 0 : 2; int32_t* dst = f.lfq + dstc * plane + size_t(cy0) * f.xb + cx0;
+      if (lane == 0) { sh_prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(c, lf_sid, sh_prep, spec_bytes))) md.DecodeChannel<kNarrow>(c, lf_sid, dst, f.xb, w, h, wp); }
+      __syncwarp();
+      if (sh_prep.ok) {   // uniform: written by lane 0 before the barrier
+        DecodeRowsLeanSpec(sh_prep, reinterpret_cast<const uint8_t*>(md.cv.alias), md.cv.log_alpha, reinterpret_cast<uint2*>(dsm + spec_off), dst, f.xb, w, h, lane);
+        if (lane == 0) md.FinishLeanSpec(sh_prep);
+      }
+      __syncwarp();
+    }
+  }
+  // ---- part C (lane 0): HF metadata
+  if (lane == 0) {
+    bool ok = sh_hdr_ok != 0;
     if (ok) {
-      md.rd.Init(md.cv); const int sid = 1 + g; size_t plane = size_t(f.xb) * f.yb; const long long dbg_t0 = clock64();
-      const int dst[3] = {1, 0, 2};   // stream channel order is Y, X, B (A.8 LfGroup)
-      for (int c = 0; c < 3; c++) md.DecodeChannel<kNarrow>(c, sid, f.lfq + dst[c] * plane + size_t(cy0) * f.xb + cx0, f.xb, w, h, wp);
       if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
       if (g == 0) f.err[13] = uint32_t((clock64() - dbg_t0) >> 10);   // debug: kilo-cycles spent on the LF coefficients of LF group 0
     }

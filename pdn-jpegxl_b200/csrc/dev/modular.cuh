@@ -90,6 +90,10 @@ template <typename T> struct ModMath {
   }
 };
 
+// Hand-over between the lane that parses (lane 0) and the warp-collective speculative loop (DecodeRowsLeanSpec): reader state, the
+// distinct clusters ("slots", at most 32: one per lane) this channel's contexts can select, and the context value -> slot map.
+struct LeanSpecPrep { BitRd br; uint32_t state, err, K, ok; uint32_t slot_info[32], slot_alias_off[32]; uint8_t slot_of[256]; };
+
 struct ModDecoder {
   SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; ChanLut* lut;   // lut: per-decoding-thread scratch (shared memory)
 
@@ -134,6 +138,9 @@ struct ModDecoder {
       if (kMode == 1 && fpred == 0 && !uses_wp && (fn == 0 || fprop == 2)) {   // zero-entropy row: the context cluster has a single symbol and the predictor is Zero
         int cnt = 0; for (int i = 0; i < fn; i++) cnt += y > L.thr[i]; const uint32_t info = cv.info[L.cluster[cnt]]; const uint32_t t = info >> 16;
         if (t != 0xffffu && t < (1u << (info & 0xff))) { const int32_t cval = UnpackSignedDev(t); for (int x = 0; x < w; x++) cur[x] = cval; continue; }
+        // one cluster for the whole row and no prediction: the samples do not depend on each other, only the ANS state chain is serial
+        // (HF metadata of frames with variable blocks: strategies and quantiser multipliers are coded this way)
+        { const uint32_t cl = L.cluster[cnt]; for (int x = 0; x < w; x++) cur[x] = UnpackSignedDev(rd.ReadCluster(cv, cl)); continue; }
       }
       for (int x = 0; x < w; x++) {
         const T nee_next = (y && x + 3 < w) ? T(up[x + 3]) : T(0);   // issued early: independent of the symbol being decoded
@@ -207,6 +214,25 @@ struct ModDecoder {
     this->rd.br = br; this->rd.state = state; this->rd.err = err;
   }
 
+  // Lane 0: decides whether channel `chan` can take the warp-collective loop (same conditions as DecodeRowsLean plus: at most 32
+  // distinct clusters, transposed alias table fits `spec_bytes`), and if so fills P. Returns P.ok.
+  __device__ bool PrepareLeanSpec(int chan, int stream_id, LeanSpecPrep& P, uint32_t spec_bytes) {
+    P.ok = 0;
+    int root = 0; DTreeNode n = tree[0];
+    while (n.x == 0 || n.x == 1) { int v = n.x == 0 ? chan : stream_id; root = v > n.y ? n.z : n.w; n = tree[root]; }
+    if (wide || uses_wp || cv.use_prefix || !cv.AllShared() || spec_bytes < (256u << cv.log_alpha)) return false;
+    BuildLut(root); const ChanLut& L = *lut;
+    if (!(L.ok && L.prop == 8 && L.predictor == 5 && L.has_direct)) return false;
+    uint32_t K = 0;
+    for (int v = 0; v < 256; v++) {
+      const uint2 di = L.dinfo[v]; uint32_t k = 0; while (k < K && P.slot_alias_off[k] != di.y) k++;
+      if (k == K) { if (K == 32) return false; P.slot_alias_off[K] = di.y; P.slot_info[K] = di.x; K++; }
+      P.slot_of[v] = uint8_t(k);
+    }
+    P.K = K; P.br = rd.br; P.state = rd.state; P.err = rd.err; P.ok = 1; return true;
+  }
+  __device__ void FinishLeanSpec(const LeanSpecPrep& P) { rd.br = P.br; rd.state = P.state; rd.err = P.err; }
+
   // Decodes one channel in raster order into out[y*stride + x]. wp_base: scratch for the weighted predictor (may be null when !uses_wp).
   // kNarrow: the caller guarantees !uses_wp && !wide (checked on the host), so the 64-bit / weighted-predictor code is not instantiated
   template <bool kNarrow = false>
@@ -227,6 +253,76 @@ struct ModDecoder {
     else DecodeRows<int32_t, 0, false, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
   }
 };
+
+// Warp-collective form of ModDecoder::DecodeRowsLean (ANS, gradient predictor, context = property 8 through a direct LUT). The serial
+// chain of one symbol is  previous sample -> context -> cluster -> alias entry of (cluster, state) -> token + next state -> sample.
+// Here every lane k < K decodes the CURRENT state under the assumption that the cluster is slot k (its own row of a transposed alias
+// table: conflict-free LDS.64), while the context of the symbol is still being derived from the previous sample; two shuffles then pick
+// the lane whose assumption was right. The alias lookup and the state arithmetic leave the critical path, which drops from ~280 to
+// ~110 cycles per symbol. All lanes carry identical copies of the bit reader and of the neighbourhood; lane 0 stores the samples.
+// T: [1 << log_alpha][32] uint2 in shared memory (built here from the staged alias rows).
+static __device__ __noinline__ void DecodeRowsLeanSpec(LeanSpecPrep& P, const uint8_t* alias_bytes, uint32_t log_alpha, uint2* T, int32_t* out, size_t stride, int w, int h, int lane) {
+  __builtin_assume(__isShared(T)); __builtin_assume(__isShared(&P));
+  const uint32_t K = P.K, nent = 1u << log_alpha;
+  for (uint32_t idx = uint32_t(lane); idx < nent * 32u; idx += 32u) { const uint32_t i = idx >> 5, k = idx & 31u;
+    T[idx] = k < K ? *reinterpret_cast<const uint2*>(alias_bytes + P.slot_alias_off[k] + i * 8u) : make_uint2(0u, 0u); }
+  const uint32_t my_info = P.slot_info[uint32_t(lane) < K ? lane : 0]; const bool my_const = (my_info >> 16) != 0xffffu; const uint32_t my_split = 1u << (my_info & 0xffu);
+  BitRd br = P.br; uint32_t state = P.state, err = P.err;
+  __syncwarp();
+  const uint32_t log_entry = 12 - log_alpha, pos_mask = (1u << log_entry) - 1; const uint8_t* slot_of = P.slot_of;
+  auto symbol = [&](int32_t ctxv) -> int32_t {
+    const uint32_t slot = slot_of[min(max(ctxv, -128), 127) + 128];
+    const uint32_t idx = state & 0xfff, i = idx >> log_entry, pos = idx & pos_mask;
+    const uint2 e = T[(i << 5) + uint32_t(lane)];
+    const bool g = pos >= (e.x & 0xffu);
+    const uint32_t s1 = (g ? (e.y >> 16) : (e.y & 0xffffu)) * (state >> 12) + (g ? (e.x >> 16) : 0u) + pos;
+    const bool refill = s1 < 65536u;
+    uint32_t cand_state = refill ? ((s1 << 16) | (br.Peek32() & 0xffffu)) : s1;
+    uint32_t cand = (g ? ((e.x >> 8) & 0xffu) : i) | (refill ? 0x100u : 0u);
+    if (my_const) { cand = my_info >> 16; cand_state = state; }   // single-symbol cluster: no bits read, state unchanged
+    if ((cand & 0xffu) >= my_split) cand |= 0x200u;                // token has a hybrid-uint tail
+    const uint32_t sel = __shfl_sync(0xffffffffu, cand, int(slot));
+    state = __shfl_sync(0xffffffffu, cand_state, int(slot));
+    if (sel & 0x100u) br.Skip(16);
+    uint32_t tok = sel & 0xffu;
+    if (sel & 0x200u) {   // rare for LF residuals; uniform over the warp
+      const uint32_t info = __shfl_sync(0xffffffffu, my_info, int(slot));
+      const uint32_t se = info & 0xff, msb = (info >> 8) & 15, lsb = (info >> 12) & 15, split = 1u << se, n = se - (msb + lsb) + ((tok - split) >> (msb + lsb));
+      if (n >= 32) { err = err ? err : kErrHybrid; tok = 0; }
+      else { const uint32_t low = tok & ((1u << lsb) - 1); const uint32_t t2 = tok >> lsb; const uint32_t hi = (t2 & ((1u << msb) - 1)) | (1u << msb); tok = (((hi << n) | br.Read(int(n))) << lsb) | low; }
+    }
+    return UnpackSignedDev(tok);
+  };
+  // Rows move through registers in chunks of 32 samples: lane j keeps sample x0 + j of the row being decoded (one coalesced 128-byte
+  // store per chunk) and sample x0 + j of the row above (one coalesced load per chunk, issued a whole chunk ahead of its first use:
+  // at ~120 cycles per symbol a load issued one symbol ahead would sit on the critical path). Neighbours come from shuffles that do not
+  // depend on the symbol being decoded.
+  { int32_t W = 0, prev_grad = 0;   // row 0: N = NW = W, so the gradient is W itself
+    for (int x0 = 0; x0 < w; x0 += 32) { const int cnt = min(32, w - x0); int32_t mine = 0;
+      for (int j = 0; j < cnt; j++) { const int32_t val = symbol(W - prev_grad) + W; if (lane == j) mine = val; prev_grad = W; W = val; }
+      if (lane < cnt) out[x0 + lane] = mine; } }
+  for (int y = 1; y < h; y++) {
+    int32_t* cur = out + size_t(y) * stride; const int32_t* up = cur - stride; const int last = w - 1;
+    __syncwarp();   // row y-1 is stored
+    int32_t upc = up[min(lane, last)];
+    int32_t N = __shfl_sync(0xffffffffu, upc, 0), NW = N, W = N, prev_grad = 0;
+    for (int x0 = 0; x0 < w; x0 += 32) {
+      const int32_t upn = up[min(x0 + 32 + lane, last)]; const int cnt = min(32, w - x0); int32_t mine = 0;
+      for (int j = 0; j < cnt; j++) {
+        const int32_t n_next = __shfl_sync(0xffffffffu, j + 1 < 32 ? upc : upn, (j + 1) & 31);   // row above at min(x + 1, last)
+        const int32_t res = symbol(W - prev_grad);
+        const int32_t g = W + N - NW, val = res + max(min(W, N), min(max(W, N), g));
+        if (lane == j) mine = val;
+        prev_grad = g; NW = N; N = n_next; W = val;
+      }
+      if (lane < cnt) cur[x0 + lane] = mine;
+      upc = upn;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) { P.br = br; P.state = state; P.err = err; }
+  __syncwarp();
+}
 #endif
 
 }  // namespace jxlgpu
