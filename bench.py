@@ -38,9 +38,13 @@ UNIT = "MP/s"
 WORKLOADS = {
     "dct8": dict(enc=dict(effort=7, distance=1.0, varblocks=0, cfl=0, adaptive_quant=0),
                  label="DCT8-only VarDCT d=1.0 (every block 8x8, no chroma-from-luma, one quantiser), gaborish + EPFx1, fixed gradient MA tree for LF, ANS, one pass"),
-    "mixed": dict(enc=dict(effort=7, distance=1.0),
-                  label="VarDCT d=1.0 with variable blocks (DCT8 / 8x16 / 16x16 / 32x32), chroma-from-luma and adaptive quantisation, gaborish + EPFx1, fixed gradient MA tree for LF, ANS, one pass"),
+    "mixed": dict(enc=dict(effort=7, distance=1.0, varblock_scale=4.0, varblock_pattern=1),
+                  label="VarDCT d=1.0 with variable blocks (DCT8 / DCT8x16 / DCT16x16 / DCT32x32 in a fixed mix per 64x64 tile; measured area shares in workloads.mixed.block_mix), "
+                        "chroma-from-luma and adaptive quantisation, gaborish + EPFx1, fixed gradient MA tree for LF, ANS, one pass"),
 }
+
+
+BLOCK_MIX = {}   # workload -> share of the frame area per AC strategy, measured by the encoder that wrote the files
 
 
 def parse_args():
@@ -71,7 +75,11 @@ def _make_one(job):
     import oracle_py as O
     from synth import synthetic_image
     img = synthetic_image(w, h, seed=seed)
-    return seed, [O.encode(img, threads=2, **enc) for enc in encs]
+    files, mixes = [], []
+    for enc in encs:
+        files.append(O.encode(img, threads=2, **enc))
+        mixes.append(O.last_encode_strategy_cells())   # cells per AC strategy: says what the file really contains
+    return seed, files, mixes
 
 
 def make_files(args, seeds, names):
@@ -86,7 +94,11 @@ def make_files(args, seeds, names):
             res = pool.map(_make_one, jobs)
     else:
         res = [_make_one(j) for j in jobs]
-    return {n: {seed: files[k] for seed, files in res} for k, n in enumerate(names)}
+    names_s = {0: "DCT8", 4: "DCT16x16", 5: "DCT32x32", 6: "DCT16x8", 7: "DCT8x16"}
+    for k, n in enumerate(names):
+        tot = [sum(m[k][i] for _, _, m in res) for i in range(27)]
+        BLOCK_MIX[n] = {names_s.get(i, "strategy%d" % i): round(v / max(sum(tot), 1), 3) for i, v in enumerate(tot) if v}
+    return {n: {seed: files[k] for seed, files, _ in res} for k, n in enumerate(names)}
 
 
 class ClockSampler(threading.Thread):
@@ -338,7 +350,8 @@ def main():
     if mixed is not None:
         line["workloads"] = {"dct8": {"value": head["value"], "bpp": 8.0 * comp_bytes / (B * W * H), "what": WORKLOADS["dct8"]["label"]},
                              "mixed": {"value": mixed["value"], "bpp": 8.0 * mixed["comp_bytes"] / (B * W * H), "ms_per_step": mixed["ms_dev"] / max(2, args.steps // 2),
-                                       "ratio_to_dct8": mixed["value"] / head["value"], "what": WORKLOADS["mixed"]["label"]}}
+                                       "ratio_to_dct8": mixed["value"] / head["value"], "what": WORKLOADS["mixed"]["label"], "block_mix": BLOCK_MIX.get("mixed")}}
+        line["workloads"]["dct8"]["block_mix"] = BLOCK_MIX.get("dct8")
 
     if rank == 0:
         # per-kernel durations of one decode, CUDA events on the stream the kernels are launched on (engine StageTimes)

@@ -9,6 +9,7 @@
 #include "jxlo_image.h"
 
 namespace jxlo {
+inline int64_t* LastEncodeStrategyCells() { static thread_local int64_t cells[27]; return cells; }   // cells covered per AC strategy in the last EncodeImage call of this thread
 
 struct EncodeParams {
   float distance = 1.0f; int effort = 7; bool lossless = false;
@@ -17,6 +18,8 @@ struct EncodeParams {
   int force_strategy = -1;                // tile the frame with this AC strategy where it fits
   bool use_prefix = false; bool container = true; int modular_group_shift = 1; uint32_t orientation = 1; std::string frame_name;
   bool skip_lf_smoothing = false; int threads = 1;
+  int varblock_pattern = 0;               // 1: modulate varblock_scale per 64x64 tile by {0, 0.55, 1, 2.75} (a fixed four-way mix of block sizes)
+  float varblock_scale = 1.0f;            // multiplies the smoothness thresholds of the varblock merge (bench: a frame with a known share of large blocks)
   int num_passes = 1, pass_shift = 1;     // 2 passes: pass 0 carries the quantised coefficients >> pass_shift, pass 1 the remainder (progressive files)
   // source description for non-8-bit sources (tests of 16-bit / float / HDR output paths)
   BitDepth bd; ColorEncoding ce; float intensity_target = 255.f; bool premultiplied = false; bool black_channel = false;
@@ -186,11 +189,12 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
       float step_y = (1.0f / 560.0f) * inv_gs / float(base_qf);
       auto smooth = [&](int by, int bx, int n, float thr) { if (by + n > pl.yb || bx + n > pl.xb) return false; for (int iy = 0; iy < n; iy++) for (int ix = 0; ix < n; ix++) if (act[size_t(by + iy) * pl.xb + bx + ix] > thr * step_y) return false; return true; };
       for (int by = 0; by < pl.yb; by += 4) for (int bx = 0; bx < pl.xb; bx += 4) {
-        if (smooth(by, bx, 4, 6.0f)) { place(by, bx, kDCT32); continue; }
+        static const float kPat[4] = {0.f, 0.55f, 1.0f, 2.75f}; const float vs = p.varblock_scale * (p.varblock_pattern ? kPat[((bx / 8) + 2 * (by / 8)) & 3] : 1.0f);
+        if (smooth(by, bx, 4, 6.0f * vs)) { place(by, bx, kDCT32); continue; }
         for (int sy = 0; sy < 4; sy += 2) for (int sx = 0; sx < 4; sx += 2) {
           int y0 = by + sy, x0 = bx + sx; if (y0 >= pl.yb || x0 >= pl.xb) continue;
-          if (smooth(y0, x0, 2, 14.0f)) { place(y0, x0, kDCT16); continue; }
-          if (x0 + 1 < pl.xb) { for (int r = 0; r < 2 && y0 + r < pl.yb; r++) if (act[size_t(y0 + r) * pl.xb + x0] < 24.0f * step_y && act[size_t(y0 + r) * pl.xb + x0 + 1] < 24.0f * step_y) place(y0 + r, x0, kDCT8x16); }
+          if (smooth(y0, x0, 2, 14.0f * vs)) { place(y0, x0, kDCT16); continue; }
+          if (x0 + 1 < pl.xb) { for (int r = 0; r < 2 && y0 + r < pl.yb; r++) if (act[size_t(y0 + r) * pl.xb + x0] < 24.0f * vs * step_y && act[size_t(y0 + r) * pl.xb + x0 + 1] < 24.0f * vs * step_y) place(y0 + r, x0, kDCT8x16); }
         }
       }
     }
@@ -201,6 +205,7 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
         float mulq = std::pow(float(mean) / (a / n + 1e-4f), 0.2f); mulq = std::min(1.35f, std::max(0.75f, mulq)); int qf = std::max(1, std::min(255, int(std::lrintf(base_qf * mulq))));
         for (int iy = 0; iy < kCoveredY[s]; iy++) for (int ix = 0; ix < kCoveredX[s]; ix++) pl.hf_mul[o + size_t(iy) * pl.xb + ix] = qf; }
     }
+    { int64_t* st = LastEncodeStrategyCells(); for (int i = 0; i < 27; i++) st[i] = 0; for (size_t i = 0; i < ncell; i++) st[pl.strategy[i]]++; }
     // dequant tables + natural orders
     std::vector<std::vector<float>> dequant(kNumQuantTables); for (int t = 0; t < kNumQuantTables; t++) dequant[t] = ComputeDequantTable(t, LibraryEncoding(t));
     std::vector<std::vector<uint32_t>> natural(kNumOrders); for (int o = 0; o < kNumOrders; o++) { int s = kOrderStrategy[o]; natural[o] = NaturalOrder(std::min(kCoveredX[s], kCoveredY[s]), std::max(kCoveredX[s], kCoveredY[s])); }

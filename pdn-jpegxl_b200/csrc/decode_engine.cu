@@ -46,26 +46,29 @@ class Pool {
     misses_++; { std::lock_guard<std::mutex> lk(mu_); miss_sizes_[sz]++; } void* p = nullptr; cudaError_t e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz);
     if (e != cudaSuccess) { cudaGetLastError(); Trim(); e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz); }
     if (e != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+    { std::lock_guard<std::mutex> lk(mu_); total_[sz]++; }
     return p;
   }
   void Put(void* p, size_t bytes) { if (!p) return; size_t sz = Round(bytes); std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; if (cached_ > Limit()) TrimLocked(); }
   void Trim() { std::lock_guard<std::mutex> lk(mu_); TrimLocked(); }
   // Makes sure `count` buffers of this size class are cached (batch start: the first image tells the sizes; allocating them one
   // by one while the GPU is busy stalls the enqueue thread for milliseconds each and takes many batches to converge).
+  // `count` is the number of buffers of this class the pool must OWN (free or handed out): other threads take buffers while a
+  // reservation runs, so counting only the free ones would allocate a fresh set on every batch.
   void Reserve(size_t bytes, size_t count) {
-    const size_t sz = Round(bytes); size_t have; { std::lock_guard<std::mutex> lk(mu_); have = free_[sz].size(); }
+    const size_t sz = Round(bytes); size_t have; { std::lock_guard<std::mutex> lk(mu_); have = total_[sz]; }
     for (; have < count; have++) { if (cached_ + sz > Limit()) return; void* p = nullptr; cudaError_t e = pinned_ ? cudaHostAlloc(&p, sz, cudaHostAllocDefault) : cudaMalloc(&p, sz); if (e != cudaSuccess) { cudaGetLastError(); return; }
-      std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; }
+      std::lock_guard<std::mutex> lk(mu_); free_[sz].push_back(p); cached_ += sz; total_[sz]++; }
   }
  private:
   // size classes: powers of two from 4 KiB up to 16 MiB (files of different sizes then share every small bucket, so the first image of
   // a batch can reserve for all of them), eighths of a power of two above (the big planes, whose size depends on the dimensions only)
   public: static size_t Round(size_t b) { if (b <= 4096) return 4096; int k = 63 - __builtin_clzll(b - 1); if (b <= (size_t(16) << 20)) return size_t(2) << k; k = 63 - __builtin_clzll(b); size_t g = size_t(1) << (k - 3); return (b + g - 1) / g * g; }
-  private: void TrimLocked() { trims_++; for (auto& kv : free_) for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } free_.clear(); cached_ = 0; }
+  private: void TrimLocked() { trims_++; for (auto& kv : free_) { for (void* p : kv.second) { if (pinned_) cudaFreeHost(p); else cudaFree(p); } total_[kv.first] -= std::min(total_[kv.first], kv.second.size()); } free_.clear(); cached_ = 0; }
   size_t Limit() { if (!limit_) { size_t fr = 0, tot = 0; if (pinned_ || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); limit_ = size_t(32) << 30; } else limit_ = tot / 4 * 3; } return limit_; }
   public: size_t misses_ = 0, trims_ = 0; std::map<size_t, size_t> miss_sizes_; std::string MissReport() { std::lock_guard<std::mutex> lk(mu_); std::string r; for (auto& kv : miss_sizes_) { r += " " + std::to_string(kv.first >> 10) + "K:" + std::to_string(kv.second) + "(free " + std::to_string(free_[kv.first].size()) + ")"; } return r; } size_t Cached() const { return cached_; }
  private:
-  bool pinned_; std::mutex mu_; std::map<size_t, std::vector<void*>> free_; size_t cached_ = 0; size_t limit_ = 0;
+  bool pinned_; std::mutex mu_; std::map<size_t, std::vector<void*>> free_; std::map<size_t, size_t> total_; size_t cached_ = 0; size_t limit_ = 0;
 };
 static Pool& DevPool() {   // one pool per device: a cached buffer must never cross devices
   static std::mutex mu; static std::map<int, std::unique_ptr<Pool>> pools; int dev = 0; cudaGetDevice(&dev); std::lock_guard<std::mutex> lk(mu); auto& p = pools[dev]; if (!p) p.reset(new Pool(false)); return *p; }
@@ -216,7 +219,7 @@ class DecodeJob {
  public:
   Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
   DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend;
-  std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false;
+  std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false; size_t coeffs_bytes = 0, xyb_row_shift = 0;
   bool defer_entropy = false, lf_pending = false, ac_pending = false;   // bundle mode: the LF / AC entropy launch is left to DecodeBundleLaunch*
   cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
   bool has_tree = false; Tree tree; Code tree_code; GroupHeader gheader; size_t global_decoded = 0; uint64_t global_data_bitpos = 0; bool global_has_data = false;
@@ -229,7 +232,7 @@ class DecodeJob {
     // several buffers of a job share a size class (the small ones all round to 4 KiB): reserve count x multiplicity per class
     std::map<std::pair<Pool*, size_t>, size_t> mult;
     for (DevBuf* b : all) if (b->p && b->pool) mult[std::make_pair(b->pool, Pool::Round(b->n))]++;
-    for (auto& kv : mult) kv.first.first->Reserve(kv.first.second, count * kv.second); }
+    for (auto& kv : mult) kv.first.first->Reserve(kv.first.second, (count + 1) * kv.second); }
   void Run(const DecodeRequest& req) { RunLf(req); RunAc(); RunRender(); }
   void ParseLfGlobal(BitReader& br);
   void ParseHfGlobal(BitReader& br);
@@ -369,13 +372,19 @@ void DecodeJob::UploadFrame() { if (!h_misc.p) h_misc.Alloc(2 * sizeof(DFrame) +
 
 void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   const ByteSpan& cs = hd.ci.codestream; comp_size = cs.size();
+  // Band decode (one rank's share of a huge frame): the big per-pixel buffers — coefficients, XYB planes, non-zero counts — are allocated
+  // for the band's group rows only (comp_g0 .. comp_g1: the band plus one halo row each side), not for the frame. The kernels keep
+  // addressing by absolute group / pixel row, so the descriptor carries bases shifted back by the band's first group / row.
+  const size_t band_g0 = h.band_on ? size_t(h.comp_g0) * h.xgroups : 0, band_groups = h.band_on ? size_t(h.comp_g1 - h.comp_g0) * h.xgroups : h.num_groups;
+  const size_t band_y0 = h.band_on ? size_t(h.comp_g0) * h.group_dim : 0;
+  if (h.band_on && h.encoding == 0) h.ypad = uint32_t(std::min<size_t>(h.ypad, size_t(h.comp_g1) * h.group_dim) - band_y0);   // rows per plane = plane stride of the kernels
   size_t cells = size_t(h.xb) * h.yb, px = size_t(h.xpad) * h.ypad, tiles = size_t(h.xt) * h.yt; bool vardct = h.encoding == 0;
   d_frame.Alloc(sizeof(DFrame)); d_err.Alloc(64); h_err.Alloc(64, true); d_gother.Alloc(size_t(h.num_groups) * 4);
   d_comp.Alloc(comp_size + 64);
   if (vardct) {
     d_lfq.Alloc(cells * 3 * 4); d_lf.Alloc(cells * 3 * 4); d_lf_tmp.Alloc(cells * 3 * 4); d_acs.Alloc(cells); d_qf.Alloc(cells); d_sharp.Alloc(cells); d_lfidx.Alloc(cells); d_ytox.Alloc(tiles); d_ytob.Alloc(tiles);
-    d_nz.Alloc(size_t(h.num_groups) * 3072); d_acend.Alloc(size_t(h.num_groups) * h.num_passes * 8);
-    d_hfmeta.Alloc((size_t(h.num_lf_groups) * kHfMetaScratchInts + h.num_lf_groups) * 4); d_coeffs.Alloc(size_t(h.num_groups) * 3 * 65536 * 2); d_xyb.Alloc(px * 3 * 4);
+    d_nz.Alloc(band_groups * 3072); d_acend.Alloc(size_t(h.num_groups) * h.num_passes * 8);
+    d_hfmeta.Alloc((size_t(h.num_lf_groups) * kHfMetaScratchInts + h.num_lf_groups) * 4); d_coeffs.Alloc(band_groups * 3 * 65536 * 2); coeffs_bytes = band_groups * 3 * 65536 * 2; d_xyb.Alloc(px * 3 * 4);
     d_sigma.Alloc(cells * 4); if (!phased) d_xyb_tmp.Alloc(px * 3 * 4);   // phased (batch) jobs allocate xyb_tmp in RunRender, and only when the frame needs it
   }
   uint64_t mod_ints = 0; for (uint32_t i = 0; i < h.num_mod_channels; i++) mod_ints += uint64_t(h.mod_ch[i].w) * h.mod_ch[i].h; if (mod_ints) d_mod.Alloc(mod_ints * 4);
@@ -386,10 +395,10 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   if (!req.out_device) d_out.Alloc(out_bytes); if (!device_output && !req.out_pinned) h_out.Alloc(out_bytes, true);
   ext_out_device = req.out_device; ext_out_pinned = req.out_pinned;
   h.comp = d_comp.as<uint8_t>(); h.lfq = d_lfq.as<int32_t>(); h.lf = d_lf.as<float>(); h.lf_tmp = d_lf_tmp.as<float>(); h.acs = d_acs.as<uint8_t>(); h.hf_mul_m1 = d_qf.as<uint8_t>(); h.sharp = d_sharp.as<uint8_t>(); h.lf_idx = d_lfidx.as<uint8_t>();
-  h.ytox = d_ytox.as<int8_t>(); h.ytob = d_ytob.as<int8_t>(); h.hfmeta_scratch = d_hfmeta.as<int32_t>(); h.coeffs = d_coeffs.as<int16_t>(); h.xyb = d_xyb.as<float>(); h.xyb_tmp = d_xyb_tmp.as<float>(); h.inv_sigma = d_sigma.as<float>();
+  h.ytox = d_ytox.as<int8_t>(); h.ytob = d_ytob.as<int8_t>(); h.hfmeta_scratch = d_hfmeta.as<int32_t>(); h.coeffs = d_coeffs.as<int16_t>() - band_g0 * 3 * 65536; h.xyb = d_xyb.as<float>() - band_y0 * h.xpad; h.xyb_tmp = d_xyb_tmp.p ? d_xyb_tmp.as<float>() - band_y0 * h.xpad : nullptr; xyb_row_shift = band_y0 * h.xpad; h.inv_sigma = d_sigma.as<float>();
   h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = req.out_device ? req.out_device : d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
   bool smooth = vardct && !(h.flags & kFlagSkipAdaptiveLfSmoothing) && h.xb > 2 && h.yb > 2; h.lf_src = smooth ? h.lf_tmp : h.lf;
-  memset(h_err.p, 0, 64); h.host_flags = h_err.as<uint32_t>() + 12; h.group_other = d_gother.as<uint32_t>(); h.nz_scratch = d_nz.as<uint8_t>(); h.ac_endpos = d_acend.as<uint64_t>();
+  memset(h_err.p, 0, 64); h.host_flags = h_err.as<uint32_t>() + 12; h.group_other = d_gother.as<uint32_t>(); h.nz_scratch = d_nz.as<uint8_t>() - band_g0 * 3072; h.ac_endpos = d_acend.as<uint64_t>();
   CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream)); CUDA_OK(cudaMemsetAsync(d_gother.p, 0, size_t(h.num_groups) * 4, stream));
   if (req.device_input && hd.ci.contiguous_offset != size_t(-1)) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input + hd.ci.contiguous_offset, comp_size, cudaMemcpyDeviceToDevice, stream));
   else { h_comp.Alloc(comp_size, true); memcpy(h_comp.p, cs.data(), comp_size); CUDA_OK(cudaMemcpyAsync(d_comp.p, h_comp.p, comp_size, cudaMemcpyHostToDevice, stream)); }   // pinned staging: a pageable source would serialise the stream
@@ -453,7 +462,7 @@ void DecodeJob::RunAc() {
   const bool vardct = h.encoding == 0; const DFrame* d = d_frame.as<DFrame>(); double tt = NowMs();
   if (timed) cudaEventRecord(ev[1], stream);
   if (vardct) { bool smooth = h.lf_src == h.lf_tmp; LaunchLfDequant(d, h, smooth, stream); CountLaunch(smooth ? 2 : 1); }
-  if (vardct) CUDA_OK(cudaMemsetAsync(h.coeffs, 0, size_t(h.num_groups) * 3 * 65536 * 2, stream));
+  if (vardct) CUDA_OK(cudaMemsetAsync(d_coeffs.p, 0, coeffs_bytes, stream));
   if (defer_entropy && vardct && h.num_passes == 1 && h.ac_fast && !(h.num_mod_channels > h.first_group_channel)) ac_pending = true;
   else for (uint32_t p = 0; p < h.num_passes; p++) CountLaunch(LaunchAcGroups(d, h, int(p), ac_lanes, stream));
   if (timed) cudaEventRecord(ev[2], stream);
@@ -463,11 +472,11 @@ void DecodeJob::RunAc() {
 // Phase 3: dequant + IDCT, restoration filters, colour transform, pack, and the copy back to the host.
 void DecodeJob::RunRender() {
   const bool vardct = h.encoding == 0; const DFrame* d = d_frame.as<DFrame>(); double tt = NowMs();
-  static const bool unfused = getenv("JXLB200_UNFUSED") != nullptr;
+  static const bool unfused_env = getenv("JXLB200_UNFUSED") != nullptr; const bool unfused = unfused_env && !h.band_on;   // the unfused filter kernels walk the whole frame: not for band buffers
   if (vardct && !d_xyb_tmp.p) {   // phased job: the LF phase has drained, its flag word is already in host memory
     const bool big_blocks = h_err.as<volatile uint32_t>()[12] != 0;   // written by k_lf_group straight into this page-locked word
     const bool filters = h.lpf.gab || h.lpf.epf_iters;
-    if (big_blocks || (filters && unfused)) { d_xyb_tmp.Alloc(size_t(h.xpad) * h.ypad * 3 * 4); h.xyb_tmp = d_xyb_tmp.as<float>(); UploadFrame(); }
+    if (big_blocks || (filters && unfused)) { d_xyb_tmp.Alloc(size_t(h.xpad) * h.ypad * 3 * 4); h.xyb_tmp = d_xyb_tmp.as<float>() - xyb_row_shift; UploadFrame(); }
   }
 #ifdef JXLB200_DEBUG   // timing experiments only (never in release builds: skipped stages leave invalid pixels): 1 = no reconstruction, 2 = no render, 3 = neither
   static const int dbg_skip = getenv("JXLB200_DEBUG_SKIP") ? atoi(getenv("JXLB200_DEBUG_SKIP")) : 0;

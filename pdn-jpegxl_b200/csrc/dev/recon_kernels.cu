@@ -261,14 +261,14 @@ __global__ void __launch_bounds__(256, 3) k_reconstruct_dct8(const __grid_consta
 static const int kReconWarps = 8;
 static const int kReconWarpFloats = 3 * 32 * 36;   // dynamic smem per warp: Sy, Sc, T
 __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* fp) {
-  const DFrame& f = *fp; const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const DFrame& f = *fp; const int g = blockIdx.x >> 2, quarter = blockIdx.x & 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;   // four CTAs share a group's small varblocks
   if (!GroupInBand(f, g) || f.group_other[g] == 0) return;   // every varblock of this group is a DCT8: k_reconstruct_dct8 did all the work
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
   extern __shared__ __align__(16) float smem[]; float* Sy = smem + warp * kReconWarpFloats; float* Sc = Sy + 32 * 36; float* T = Sc + 32 * 36;   // per warp: Sy, Sc, T of 32 rows x (32 + 4) floats
   const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const DTables& tb = *f.tables;
   // ---- small varblocks (both sides <= 32 px): one warp per block. Separable DCTs of 8/16/32 points run as register-resident straight-line
   // code (InverseSeparable); the 8x8 special transforms (IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4) are rare and stay with lane 0.
-  for (int cell = warp; cell < 1024; cell += kReconWarps) {
+  for (int cell = warp + kReconWarps * quarter; cell < 1024; cell += 4 * kReconWarps) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
     const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
     const int s = min(int(a & 31), 26), bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s); if (bw > 4 || bh > 4 || s == 0) continue;   // DCT8 is handled by k_reconstruct_dct8
@@ -279,7 +279,20 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
     for (int c3 = 0; c3 < 3; c3++) {
       const int c = c3 == 0 ? 1 : c3 == 1 ? 0 : 2; float* S = c == 1 ? Sy : Sc;
       const float mulc = c == 1 ? scale : c == 0 ? scale * f.xm : scale * f.bm, kc = c == 0 ? kx : kb, b1 = f.quant_bias[c], b3 = f.quant_bias[3];
-      for (int p = lane; p < size; p += 32) { const int sp = (p >> lsw) * STR + (p & (SW - 1)); int q = coef[c * 65536 + CoefAddr(by, bx, bw, uint32_t(p))];
+      if (plain) {   // 8 coefficients per lane and step: one 16-byte coefficient load, two 16-byte table loads, two STS.128
+        for (int p8 = lane * 8; p8 < size; p8 += 256) {
+          const int j = p8 >> 6, sp = (p8 >> lsw) * STR + (p8 & (SW - 1));
+          const int4 raw = *reinterpret_cast<const int4*>(coef + c * 65536 + ((by + j / bw) * 32 + bx + j % bw) * 64 + (p8 & 63));
+          const float4 d0 = *reinterpret_cast<const float4*>(dq + c * size + p8), d1 = *reinterpret_cast<const float4*>(dq + c * size + p8 + 4);
+          const int q[8] = {int(short(raw.x & 0xffff)), raw.x >> 16, int(short(raw.y & 0xffff)), raw.y >> 16, int(short(raw.z & 0xffff)), raw.z >> 16, int(short(raw.w & 0xffff)), raw.w >> 16};
+          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w}; float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) { const float qf = float(q[k]); const float adj = fabsf(qf) >= 1.5f ? qf - __fdividef(b3, qf) : qf * b1; v[k] = adj * dd[k] * mulc; }
+          if (c != 1) { const float4 y0 = *reinterpret_cast<const float4*>(Sy + sp), y1 = *reinterpret_cast<const float4*>(Sy + sp + 4);
+            v[0] = fmaf(kc, y0.x, v[0]); v[1] = fmaf(kc, y0.y, v[1]); v[2] = fmaf(kc, y0.z, v[2]); v[3] = fmaf(kc, y0.w, v[3]); v[4] = fmaf(kc, y1.x, v[4]); v[5] = fmaf(kc, y1.y, v[5]); v[6] = fmaf(kc, y1.z, v[6]); v[7] = fmaf(kc, y1.w, v[7]); }
+          *reinterpret_cast<float4*>(S + sp) = make_float4(v[0], v[1], v[2], v[3]); *reinterpret_cast<float4*>(S + sp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      } else for (int p = lane; p < size; p += 32) { const int sp = (p >> lsw) * STR + (p & (SW - 1)); int q = coef[c * 65536 + CoefAddr(by, bx, bw, uint32_t(p))];
         float v = AdjustQuantBiasDev(q, b1, b3) * dq[c * size + p] * mulc; if (c != 1) v += kc * Sy[sp]; S[sp] = v; }
       __syncwarp();
       LlfFromLf(f, c, bh, bw, f.lf_src + c * lfplane + o, int(f.xb), S, STR, lane, 32);
@@ -298,7 +311,8 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
     }
   }
   __syncthreads();
-  // ---- large varblocks (a side >= 64 px): the whole CTA per block, staged through the XYB planes themselves
+  // ---- large varblocks (a side >= 64 px): the whole CTA per block, staged through the XYB planes themselves (first of the group's four CTAs)
+  if (quarter != 0) return;
   const int NT = kReconWarps * 32;
   for (int cell = 0; cell < 1024; cell++) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
@@ -861,7 +875,7 @@ void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st) {
   { const int items = int(h.num_groups) * 32; const int grid = std::min(items, 148 * 3); const size_t d8smem = size_t(2) * 3 * 32 * kD8Stride * sizeof(float);
     static bool attr8[64] = {false}; if (!attr8[dev & 63]) { cudaFuncSetAttribute(k_reconstruct_dct8, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d8smem)); attr8[dev & 63] = true; }
     k_reconstruct_dct8<<<grid, 256, d8smem, st>>>(h, items); }
-  k_reconstruct<<<h.num_groups, kReconWarps * 32, smem, st>>>(d); CountLaunch(2);
+  k_reconstruct<<<h.num_groups * 4, kReconWarps * 32, smem, st>>>(d); CountLaunch(2);
 }
 // Runs gaborish + EPF; ping-pongs between xyb and xyb_tmp. Returns the buffer holding the result.
 void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {
@@ -906,7 +920,7 @@ template <int GAB, int EPF> static void LaunchRenderT(const DFrame& h, cudaStrea
     const dim3 wgrid((h.xsize + 63) / 64, (h.ysize + 31) / 32);
     static const bool use_tma = !(getenv("JXLB200_RENDER_TMA") && atoi(getenv("JXLB200_RENDER_TMA")) == 0);
     CUtensorMap tmap;
-    if (use_tma && EncodeXybTensorMap(h, &tmap)) {
+    if (use_tma && !h.band_on && EncodeXybTensorMap(h, &tmap)) {   // band decodes address the planes through a shifted base: thread loads
       const int ntiles = int(wgrid.x * wgrid.y), grid1 = std::min(ntiles, 148 * 2);
       if (fast_bgra) k_render_wide_tma<1, true><<<grid1, 256, tsmem, st>>>(h, tmap, int(wgrid.x), ntiles); else k_render_wide_tma<1, false><<<grid1, 256, tsmem, st>>>(h, tmap, int(wgrid.x), ntiles);
     } else if (fast_bgra) k_render_wide<1, true><<<wgrid, 256, wsmem, st>>>(h); else k_render_wide<1, false><<<wgrid, 256, wsmem, st>>>(h);

@@ -41,6 +41,12 @@ if dist is not None:
 t = time.time(); outs = [P.decode_band(data, a, b, device=local) for a, b in mine if b > a]; torch.cuda.synchronize(); dt = time.time() - t
 if dist is not None:
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt = float(tt.item())
+free_b, total_b = torch.cuda.mem_get_info()
+used = torch.tensor([float(total_b - free_b)], dtype=torch.float64, device="cuda")
+if dist is not None:
+    dist.all_reduce(used, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("device memory in use per rank after the band decode (buffers + caching pools, max over ranks): %.2f GB" % (float(used.item()) / 1e9), flush=True)
 if rank == 0:
     halo = sum((min(b + 1, rows) - max(a - 1, 0)) for a, b in parts if b > a) / rows - 1.0
     print("decode as %d bands (%s): %.2f s = %.0f MP/s; redundant reconstruction %.1f %%; bytes exchanged between ranks: 0" % (nb, "one per rank" if world > 1 else "sequential on one GPU", dt, mp / dt, 100 * halo), flush=True)

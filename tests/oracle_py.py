@@ -28,7 +28,7 @@ class EncodeParams(C.Structure):
     _fields_ = [("distance", C.c_float)] + [(n, C.c_int32) for n in (
         "effort", "lossless", "gab", "epf", "varblocks", "cfl", "adaptive_quant", "force_strategy", "use_prefix", "container",
         "modular_group_shift", "orientation", "skip_lf_smoothing", "threads", "bits", "exp_bits", "color_space", "white_point",
-        "primaries", "tf", "intent")] + [("intensity_target", C.c_float), ("premultiplied", C.c_int32), ("black_channel", C.c_int32), ("num_passes", C.c_int32), ("pass_shift", C.c_int32)]
+        "primaries", "tf", "intent")] + [("intensity_target", C.c_float), ("premultiplied", C.c_int32), ("black_channel", C.c_int32), ("num_passes", C.c_int32), ("pass_shift", C.c_int32), ("varblock_scale", C.c_float), ("varblock_pattern", C.c_int32)]
 
 
 _lib = None
@@ -114,6 +114,13 @@ def encode(pixels, num_color=None, has_alpha=None, exif=b"", xmp=b"", icc=b"", *
     data = C.string_at(out, n.value)
     lib().jxlo_free(out)
     return data
+
+
+def last_encode_strategy_cells():
+    """Cells (8x8 units) covered per AC strategy in the last encode() of this thread."""
+    out = (C.c_int64 * 27)()
+    lib().jxlo_last_encode_strategy_cells(out)
+    return list(out)
 
 
 def _icc_call(fn, data):
