@@ -169,10 +169,9 @@ DecodeResult ParseInfo(const uint8_t* data, size_t size) {
 
 // ---------------------------------------------------------------- blob builder
 struct Blob {
-  std::vector<uint8_t> b;
+  std::vector<uint8_t> b; bool uses_lz77 = false;   // some code of this frame is LZ77-enabled: the kernels need their windows
   uint32_t Add(const void* p, size_t n, size_t align = 16) { size_t o = (b.size() + align - 1) / align * align; b.resize(o + n); if (n) memcpy(&b[o], p, n); JXLG_CHECK(b.size() < (size_t(1) << 31), "table blob too large"); return uint32_t(o); }
   DCode AddCode(const Code& c) {
-    JXLG_CHECK(!c.lz77, "LZ77-enabled entropy streams are not supported by the GPU decoder yet");
     DCode d; memset(&d, 0, sizeof(d)); d.num_ctx = uint32_t(c.ctx_map.size()); d.num_clusters = uint32_t(c.cfg.size()); d.log_alpha = uint32_t(c.log_alpha); d.use_prefix = c.use_prefix;
     d.ctx_map_off = Add(c.ctx_map.data(), c.ctx_map.size()); std::vector<DHybrid> cfg(c.cfg.size()); for (size_t i = 0; i < cfg.size(); i++) cfg[i] = DHybrid{uint8_t(c.cfg[i].split_exp), uint8_t(c.cfg[i].msb), uint8_t(c.cfg[i].lsb), 0};
     d.cfg_off = Add(cfg.data(), cfg.size() * sizeof(DHybrid));
@@ -181,6 +180,8 @@ struct Blob {
       if (!c.use_prefix) { for (size_t sy = 0; sy < c.ans[k].freq.size(); sy++) if (c.ans[k].freq[sy] == kAnsTab) cs = uint32_t(sy); } else if (c.prefix[k].max_len == 0) cs = uint32_t(c.prefix[k].single);
       info[k] = c.cfg[k].split_exp | (c.cfg[k].msb << 8) | (c.cfg[k].lsb << 12) | (cs << 16); }
     d.info_off = Add(info.data(), info.size() * 4);
+    if (c.lz77) { d.lz77 = 1; d.lz_min_symbol = c.lz_min_symbol; d.lz_min_length = c.lz_min_length; d.lz_len_info = c.lz_len_cfg.split_exp | (c.lz_len_cfg.msb << 8) | (c.lz_len_cfg.lsb << 12);
+      d.lz_dist_cluster = c.ctx_map.back(); uses_lz77 = true; }
     if (!c.use_prefix) {
       size_t ts = size_t(1) << c.log_alpha; std::vector<DAlias> al(c.ans.size() * ts);
       for (size_t k = 0; k < c.ans.size(); k++) { const AnsTable& t = c.ans[k]; for (size_t i = 0; i < ts; i++) al[k * ts + i] = PackAlias(t.cutoff[i], t.right[i], t.off1[i], t.freq[i], t.freq[t.right[i]]); }
@@ -218,7 +219,7 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 class DecodeJob {
  public:
   Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
-  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend;
+  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend, d_lz;
   std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false; size_t coeffs_bytes = 0, xyb_row_shift = 0;
   bool defer_entropy = false, lf_pending = false, ac_pending = false;   // bundle mode: the LF / AC entropy launch is left to DecodeBundleLaunch*
   cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
@@ -399,6 +400,8 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
   h.mod_planes = d_mod.as<int32_t>(); h.wp_scratch = d_wp.as<int32_t>(); h.out_px = req.out_device ? req.out_device : d_out.as<uint8_t>(); h.err = d_err.as<uint32_t>(); h.end_bitpos = reinterpret_cast<uint64_t*>(d_err.as<uint8_t>() + 16); h.tables = DeviceTables();
   bool smooth = vardct && !(h.flags & kFlagSkipAdaptiveLfSmoothing) && h.xb > 2 && h.yb > 2; h.lf_src = smooth ? h.lf_tmp : h.lf;
   memset(h_err.p, 0, 64); h.host_flags = h_err.as<uint32_t>() + 12; h.group_other = d_gother.as<uint32_t>(); h.nz_scratch = d_nz.as<uint8_t>() - band_g0 * 3072; h.ac_endpos = d_acend.as<uint64_t>();
+  h.lz_window = nullptr;
+  if (blob.uses_lz77) { d_lz.Alloc((size_t(std::max(h.num_lf_groups, h.num_groups)) + 1) * (size_t(1) << 20) * 4); h.lz_window = d_lz.as<uint32_t>(); }
   CUDA_OK(cudaMemsetAsync(d_err.p, 0, 64, stream)); CUDA_OK(cudaMemsetAsync(d_gother.p, 0, size_t(h.num_groups) * 4, stream));
   if (req.device_input && hd.ci.contiguous_offset != size_t(-1)) CUDA_OK(cudaMemcpyAsync(d_comp.p, req.device_input + hd.ci.contiguous_offset, comp_size, cudaMemcpyDeviceToDevice, stream));
   else { h_comp.Alloc(comp_size, true); memcpy(h_comp.p, cs.data(), comp_size); CUDA_OK(cudaMemcpyAsync(d_comp.p, h_comp.p, comp_size, cudaMemcpyHostToDevice, stream)); }   // pinned staging: a pageable source would serialise the stream
@@ -430,6 +433,7 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
       h.lf_cta_offset = lf_cursor.fetch_add(h.num_lf_groups) % 148u; h.ac_cta_offset = vardct ? ac_cursor.fetch_add(uint32_t(AcCtas(h, ac_lanes))) % 148u : 0; }
     // + the transposed alias table of the speculative LF loop (32 slots x 8 bytes per alias entry), when it stays small
     { const uint32_t spec = has_tree && !h.mod_code.use_prefix ? (256u << h.mod_code.log_alpha) : 0u; h.lf_smem = std::min<uint32_t>(modb + 64 + (spec <= 64 * 1024 ? spec + 16 : 0), 96 * 1024); } ac_budget = [this, code_bytes]() { uint32_t acb = 0; bool prefix = false; for (uint32_t p = 0; p < h.num_passes; p++) { acb = std::max(acb, code_bytes(h.ac_code[p])); prefix |= h.ac_code[p].use_prefix != 0; }
+      for (uint32_t p = 0; p < h.num_passes; p++) prefix |= h.ac_code[p].lz77 != 0;   // LZ77 streams take the generic reader too
       h.ac_smem = acb + 64; h.ac_fast = (!prefix && h.ac_smem <= 96 * 1024) ? 1 : 0; if (!h.ac_fast) h.ac_smem = 0; };
     if (vardct && !single) ac_budget();
     { static const bool tr = getenv("JXLB200_TRACE") != nullptr; static std::atomic<int> shown{0}; if (tr && shown.fetch_add(1) < 2) fprintf(stderr, "[jxlb200] table staging: lf_smem %u B, ac_smem %u B (ac_fast %u), AC clusters %u, log_alpha %u\n", h.lf_smem, h.ac_smem, h.ac_fast, h.ac_code[0].num_clusters, h.ac_code[0].log_alpha); }

@@ -20,6 +20,9 @@ struct DCode {
   uint32_t prefix_off;    // uint32[2*num_clusters] {lut byte offset, max_len} (prefix)
   uint32_t info_off;      // uint32[num_clusters]: split_exp[0,8) | msb[8,12) | lsb[12,16) | const symbol[16,32) (0xffff: none). A constant
                           // symbol is the only symbol of a zero-entropy cluster: decoding it reads no bits and leaves the ANS state unchanged.
+  // LZ77 (C.2.5): tokens >= lz_min_symbol start a copy of lz_min_length + hybrid(lz_len_info, token - lz_min_symbol) earlier values; the
+  // distance is coded with cluster lz_dist_cluster (the cluster of the extra context the map carries when LZ77 is on).
+  uint32_t lz77, lz_min_symbol, lz_min_length, lz_len_info, lz_dist_cluster;
 };
 // alias entry as two 32-bit words: x = cutoff[0,8) | right[8,16) | off1[16,32); y = freq0[0,16) | freq1[16,32)
 struct DAlias { uint32_t x, y; };
@@ -62,8 +65,9 @@ __device__ __forceinline__ const void* StageBytes(uint8_t* dsm, uint32_t cap, ui
 }
 
 struct CodeView {   // resolved pointers (generic address space: shared or global)
-  const uint8_t* ctx_map; const DHybrid* cfg; const DAlias* alias; const uint32_t* prefix_desc; const uint32_t* info; const uint8_t* blob; uint32_t log_alpha, use_prefix, num_ctx, num_clusters;
+  const uint8_t* ctx_map; const DHybrid* cfg; const DAlias* alias; const uint32_t* prefix_desc; const uint32_t* info; const uint8_t* blob; uint32_t log_alpha, use_prefix, num_ctx, num_clusters, lz77, lz_min_symbol, lz_min_length, lz_len_info, lz_dist_cluster;
   __device__ __forceinline__ void Bind(const uint8_t* blob_, const DCode& c) {
+    lz77 = c.lz77; lz_min_symbol = c.lz_min_symbol; lz_min_length = c.lz_min_length; lz_len_info = c.lz_len_info; lz_dist_cluster = c.lz_dist_cluster;
     blob = blob_; ctx_map = blob_ + c.ctx_map_off; cfg = reinterpret_cast<const DHybrid*>(blob_ + c.cfg_off); alias = reinterpret_cast<const DAlias*>(blob_ + c.alias_off);
     prefix_desc = reinterpret_cast<const uint32_t*>(blob_ + c.prefix_off); info = reinterpret_cast<const uint32_t*>(blob_ + c.info_off); log_alpha = c.log_alpha; use_prefix = c.use_prefix; num_ctx = c.num_ctx; num_clusters = c.num_clusters;
   }
@@ -78,9 +82,11 @@ struct CodeView {   // resolved pointers (generic address space: shared or globa
   }
 };
 
+static const uint32_t kLzWindow = 1u << 20;   // values an LZ77 copy can reach back (per stream)
 struct SymReader {
   BitRd br; uint32_t state; uint32_t err;
-  __device__ __forceinline__ void Init(const CodeView& cv) { err = 0; state = cv.use_prefix ? 0 : br.Read(32); }
+  uint32_t* win = nullptr; uint32_t num_to_copy = 0, copy_pos = 0, num_decoded = 0;   // LZ77 state; win: kLzWindow values in global memory
+  __device__ __forceinline__ void Init(const CodeView& cv) { err = 0; state = cv.use_prefix ? 0 : br.Read(32); num_to_copy = 0; copy_pos = 0; num_decoded = 0; }
   __device__ __forceinline__ uint32_t ReadToken(const CodeView& cv, uint32_t cluster) {
     if (cv.use_prefix) {
       uint32_t lut_off = cv.prefix_desc[2 * cluster], max_len = cv.prefix_desc[2 * cluster + 1]; const uint32_t* lut = reinterpret_cast<const uint32_t*>(cv.blob + lut_off);
@@ -124,6 +130,34 @@ struct SymReader {
     DHybrid h; h.split_exp = uint8_t(info & 0xff); h.msb = uint8_t((info >> 8) & 15); h.lsb = uint8_t((info >> 12) & 15); return Hybrid(h, t);
   }
   __device__ __forceinline__ uint32_t Read(const CodeView& cv, uint32_t ctx) { return ReadCluster(cv, cv.ctx_map[ctx]); }
+  // The reader of LZ77-enabled codes. dist_mult: widest channel of a Modular sub-bitstream (distance symbols below 120 then index a table
+  // of (dx, dy) offsets), 0 for the other streams.
+  __device__ __noinline__ uint32_t ReadLz(const CodeView& cv, uint32_t ctx, uint32_t dist_mult) {
+    const uint32_t mask = kLzWindow - 1;
+    if (!win) { err = err ? err : kErrUnsupportedStream; return 0; }
+    if (num_to_copy == 0) {
+      const uint32_t cl = cv.ctx_map[ctx], info = cv.info[cl]; uint32_t tok = info >> 16; if (tok == 0xffffu) tok = ReadToken(cv, cl);
+      if (tok < cv.lz_min_symbol) {   // literal
+        uint32_t r = tok; if (tok >= (1u << (info & 0xff))) r = HybridSlow(info, tok);
+        win[(num_decoded++) & mask] = r; return r;
+      }
+      const uint32_t lt = tok - cv.lz_min_symbol; uint32_t len = lt; if (lt >= (1u << (cv.lz_len_info & 0xff))) len = HybridSlow(cv.lz_len_info, lt);
+      num_to_copy = len + cv.lz_min_length;
+      const uint32_t dcl = cv.lz_dist_cluster, dinfo = cv.info[dcl]; uint32_t dtok = dinfo >> 16; if (dtok == 0xffffu) dtok = ReadToken(cv, dcl);
+      uint32_t distance = dtok; if (dtok >= (1u << (dinfo & 0xff))) distance = HybridSlow(dinfo, dtok);
+      if (dist_mult == 0) distance++;
+      else if (distance < 120) {   // special distances: (dx, dy) pairs in a fixed order, offset = dx + width * dy, at least 1
+        const int8_t kdx[120] = {0,1,1,-1,0,2,1,-1,2,-2,2,-2,0,3,1,-1,3,-3,2,-2,3,-3,0,4,1,-1,4,-4,3,-3,2,-2,4,-4,0,3,-3,4,-4,5,1,-1,5,-5,2,-2,5,-5,4,-4,3,-3,5,-5,0,6,1,-1,6,-6,2,-2,6,-6,4,-4,5,-5,3,-3,6,-6,0,7,1,-1,5,-5,7,-7,4,-4,6,-6,2,-2,7,-7,3,-3,7,-7,5,-5,6,-6,8,4,-4,7,-7,8,8,6,-6,8,5,-5,7,-7,8,6,-6,7,-7,8,7,-7,8,8};
+        const int8_t kdy[120] = {1,0,1,1,2,0,2,2,1,1,2,2,3,0,3,3,1,1,3,3,2,2,4,0,4,4,1,1,3,3,4,4,2,2,5,4,4,3,3,0,5,5,1,1,5,5,2,2,4,4,5,5,3,3,6,0,6,6,1,1,6,6,2,2,5,5,4,4,6,6,3,3,7,0,7,7,5,5,1,1,6,6,4,4,7,7,2,2,7,7,3,3,6,6,5,5,0,7,7,4,4,1,2,6,6,3,7,7,5,5,4,7,7,6,6,5,7,7,6,7};
+        const int off = int(kdx[distance]) + int(dist_mult) * int(kdy[distance]); distance = off < 1 ? 1u : uint32_t(off);
+      } else distance -= 119;
+      distance = min(distance, min(num_decoded, kLzWindow));
+      copy_pos = num_decoded - distance;
+      if (distance == 0) { const uint32_t n = min(num_to_copy, kLzWindow); for (uint32_t i = 0; i < n; i++) win[i] = 0; }
+      if (num_to_copy < cv.lz_min_length) { err = err ? err : kErrHybrid; num_to_copy = 0; return 0; }
+    }
+    const uint32_t r = win[(copy_pos++) & mask]; num_to_copy--; win[(num_decoded++) & mask] = r; return r;
+  }
   __device__ __forceinline__ bool FinalOk(const CodeView& cv) const { return cv.use_prefix || state == 0x130000u; }
 };
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
   if (lane == 0) {
     sh_ok = 0; sh_nb = 0;
     const uint64_t start = single ? f.end_bitpos[0] : sec[1 + g];
-    md.rd.br.Init(f.comp, start);
+    md.rd.br.Init(f.comp, start); if (f.lz_window) md.rd.win = f.lz_window + size_t(g) * kLzWindow; md.dist_mult = uint32_t(w);
     uint32_t extra_prec = md.rd.br.Read(2);
     f.hfmeta_scratch[size_t(f.num_lf_groups) * kHfMetaScratchInts + g] = int32_t(extra_prec);
     const bool ok = ReadGroupHeaderDev(md, f);
@@ -101,7 +101,7 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
       uint32_t nb = md.rd.br.Read(CeilLog2Dev(uint32_t(w * h))) + 1; sh_nb = nb;
       ok = ReadGroupHeaderDev(md, f);
       if (ok) {
-        md.rd.Init(md.cv); const int sid = 1 + 2 * int(f.num_lf_groups) + g;
+        md.rd.Init(md.cv); const int sid = 1 + 2 * int(f.num_lf_groups) + g; md.dist_mult = uint32_t(max(max(tw, w), int(min(nb, 65536u))));
         md.DecodeChannel<kNarrow>(0, sid, s_cflx, tw, tw, th, wp); md.DecodeChannel<kNarrow>(1, sid, s_cflb, tw, tw, th, wp);
         if (nb <= 65536u) { md.DecodeChannel<kNarrow>(2, sid, s_info, nb, int(nb), 2, wp); md.DecodeChannel<kNarrow>(3, sid, s_sharp, w, w, h, wp); } else md.rd.err = kErrHfMeta;
         if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
@@ -195,6 +195,9 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   if (nch == 0) return;
   if (!ReadGroupHeaderDev(md, f)) return;
   md.rd.Init(md.cv); *need_init = false;
+  { uint32_t dm = 0; for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
+      int rx0 = x0 >> ch.hshift, ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) continue; int rw = min(gd >> ch.hshift, int(ch.w) - rx0), rh = min(gd >> ch.vshift, int(ch.h) - ry0); if (rw > 0 && rh > 0) dm = max(dm, uint32_t(rw)); }
+    md.dist_mult = dm; }
   const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g; int k = 0;
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth);
   for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
@@ -231,7 +234,7 @@ __device__ __forceinline__ void AcVardctBody(const DFrame& f, const int pass, co
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
   const uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
-  SymReader rd; rd.br.Init(f.comp, start); rd.err = 0;
+  SymReader rd; rd.br.Init(f.comp, start); rd.err = 0; if (f.lz_window) rd.win = f.lz_window + size_t(g) * kLzWindow;
   uint32_t err = 0, bad_range = 0;
   const uint32_t preset = rd.br.Read(CeilLog2Dev(f.num_hf_presets));
   if (preset >= f.num_hf_presets) { SetError(f.err, kErrPreset); return; }
@@ -260,7 +263,7 @@ __device__ __forceinline__ void AcVardctBody(const DFrame& f, const int pass, co
     } else {
       ctx = nzctx + uint32_t(s_freq[k >> log2c]) * 2 + prev;
     }
-    const uint32_t u = kSmem ? rd.ReadAns(cv, ctx) : rd.Read(cv, ctx);
+    const uint32_t u = kSmem ? rd.ReadAns(cv, ctx) : (cv.lz77 ? rd.ReadLz(cv, ctx, 0) : rd.Read(cv, ctx));
     if (blk) {
       if (u + covered > size) { err = kErrTooManyNz; break; }
       const uint32_t v = (u + covered - 1) >> log2c;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(32 * kModGroupsPerCta) k_mod_group(const __gri
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
   if (f.encoding == 0) start = f.ac_endpos[size_t(pass) * f.num_groups + g];
-  md.rd.br.Init(f.comp, start);
+  md.rd.br.Init(f.comp, start); if (f.lz_window) md.rd.win = f.lz_window + size_t(g) * kLzWindow;
   bool need_init = true; md.rd.err = 0; DecodeModularGroupDev<kNarrow>(md, f, g, pass, &need_init); uint32_t err = md.rd.err;
   uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
   SetError(f.err, err);
@@ -330,6 +333,8 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
   md.rd.br.Init(f.comp, start_bitpos);
   // header already parsed on the host (it carries the global transforms); the ANS state word follows
   md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12;
+  if (f.lz_window) md.rd.win = f.lz_window + size_t(max(f.num_lf_groups, f.num_groups)) * kLzWindow;
+  { uint32_t dm = 0; for (uint32_t c = 0; c < num_channels; c++) dm = max(dm, f.mod_ch[c].w); md.dist_mult = dm; }
   md.rd.Init(md.cv);
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + f.num_groups) * WPScratchInts(kMaxWpWidth);
   for (uint32_t c = 0; c < num_channels; c++) { const DModChannel& ch = f.mod_ch[c]; md.DecodeChannel(int(c), 0, f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), wp); }

@@ -51,7 +51,7 @@ struct DFrame {
   const uint8_t* comp; const uint8_t* blob; const uint8_t* static_blob;
   int32_t* lfq; float* lf; float* lf_tmp; uint8_t* acs; uint8_t* hf_mul_m1; uint8_t* sharp; uint8_t* lf_idx; int8_t* ytox; int8_t* ytob; int32_t* hfmeta_scratch;
   const float* lf_src; const struct DTables* tables;
-  int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos; uint64_t* ac_endpos; uint8_t* nz_scratch; uint32_t* host_flags; uint32_t* group_other;   // group_other[g]: number of varblocks in group g that are not plain DCT8
+  int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos; uint64_t* ac_endpos; uint8_t* nz_scratch; uint32_t* host_flags; uint32_t* lz_window;   /* LZ77 windows: kLzWindow values per stream (slots: LF group g | group g | last: global), null when no code uses LZ77 */ uint32_t* group_other;   // group_other[g]: number of varblocks in group g that are not plain DCT8
 };
 // A bundle of images decoded by one launch of an entropy kernel (batches): passed by value like DFrame (4 x 3.4 KB of the 32 KB
 // parameter space). CTA `first[i]` .. `first[i+1]-1` (after `cta_offset` empty CTAs) belong to image i. Raises the number of images

@@ -95,7 +95,7 @@ template <typename T> struct ModMath {
 struct LeanSpecPrep { BitRd br; uint32_t state, err, K, ok; uint32_t slot_info[32], slot_alias_off[32]; uint8_t slot_of[256]; };
 
 struct ModDecoder {
-  SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; ChanLut* lut;   // lut: per-decoding-thread scratch (shared memory)
+  SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; uint32_t dist_mult = 0; /* LZ77: widest channel of the sub-bitstream */ ChanLut* lut;   // lut: per-decoding-thread scratch (shared memory)
 
   // In-order walk of the subtree under `root` (<= branch first): ascending thresholds, leaves per interval.
   __device__ void BuildLut(int root) {
@@ -155,7 +155,7 @@ struct ModDecoder {
         } else {
           DTreeNode nd = n;
           while (nd.x >= 0) { int32_t v = int32_t(M::PropValue(nd.x, chan, stream_id, x, y, N, W, NW, NE, NN, WW, prev_grad, wo.max_err, &rd.err)); nd = tree[v > nd.y ? nd.z : nd.w]; }
-          tok = rd.Read(cv, uint32_t(nd.y) >> 4); pred = M::Prediction(nd.y & 15, N, W, NW, NE, NN, WW, NEE, wpred); offset = nd.z; mult = uint32_t(nd.w);
+          tok = cv.lz77 ? rd.ReadLz(cv, uint32_t(nd.y) >> 4, this->dist_mult) : rd.Read(cv, uint32_t(nd.y) >> 4); pred = M::Prediction(nd.y & 15, N, W, NW, NE, NN, WW, NEE, wpred); offset = nd.z; mult = uint32_t(nd.w);
         }
         const int32_t val = kMode != 0 ? int32_t(T(UnpackSignedDev(tok)) + pred) : int32_t((long long)UnpackSignedDev(tok) * (long long)mult + offset + (long long)pred);
         cur[x] = val;
@@ -220,7 +220,7 @@ struct ModDecoder {
     P.ok = 0;
     int root = 0; DTreeNode n = tree[0];
     while (n.x == 0 || n.x == 1) { int v = n.x == 0 ? chan : stream_id; root = v > n.y ? n.z : n.w; n = tree[root]; }
-    if (wide || uses_wp || cv.use_prefix || !cv.AllShared() || spec_bytes < (256u << cv.log_alpha)) return false;
+    if (wide || uses_wp || cv.use_prefix || cv.lz77 || !cv.AllShared() || spec_bytes < (256u << cv.log_alpha)) return false;
     BuildLut(root); const ChanLut& L = *lut;
     if (!(L.ok && L.prop == 8 && L.predictor == 5 && L.has_direct)) return false;
     uint32_t K = 0;
@@ -243,6 +243,12 @@ struct ModDecoder {
     while (n.x == 0 || n.x == 1) { int v = n.x == 0 ? chan : stream_id; root = v > n.y ? n.z : n.w; n = tree[root]; }
     if (uses_wp && w > int(kMaxWpWidth)) { rd.err = kErrUnsupportedStream; return; }
     BuildLut(root); const ChanLut& L = *lut;
+    if (cv.lz77) {   // LZ77 streams: every value goes through the window, so only the generic tree walk reads them
+      if (!kNarrow && (wide || uses_wp)) DecodeRows<long long, 0, false, true>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+      else if (wide || uses_wp) rd.err = kErrUnsupportedStream;
+      else DecodeRows<int32_t, 0, false, false>(root, n, chan, stream_id, out, stride, w, h, wp_base);
+      return;
+    }
     const bool sm = cv.AllShared() && !cv.use_prefix;
     if (!kNarrow && (wide || uses_wp)) { if (L.ok) DecodeRows<long long, 1, false, true>(root, n, chan, stream_id, out, stride, w, h, wp_base); else DecodeRows<long long, 0, false, true>(root, n, chan, stream_id, out, stride, w, h, wp_base); }
     else if (wide || uses_wp) rd.err = kErrUnsupportedStream;

@@ -346,8 +346,10 @@ class EntropyCode:
     """One clustered entropy code. Each cluster is ("flat", n) | ("single", sym) | ("two", s0, s1, p0) for ANS, or a tuple of
     1..4 symbols for a simple prefix code. ctx_map maps context -> cluster."""
 
-    def __init__(self, ctx_map, clusters, hybrids=None, use_prefix=False, log_alpha=None):
-        self.ctx_map, self.clusters, self.use_prefix = list(ctx_map), list(clusters), use_prefix
+    def __init__(self, ctx_map, clusters, hybrids=None, use_prefix=False, log_alpha=None, lz77=None):
+        """lz77: None or dict(min_symbol, min_length, len_hybrid=Hybrid(..)): ctx_map then carries one extra entry, the cluster of the
+        distance context; stream items may be ("copy", length, distance_symbol) triples (C.2.5)."""
+        self.ctx_map, self.clusters, self.use_prefix, self.lz77 = list(ctx_map), list(clusters), use_prefix, lz77
         self.log_alpha = 15 if use_prefix else (log_alpha if log_alpha is not None else 8)
         assert use_prefix or 5 <= self.log_alpha <= 8
         self.hybrids = hybrids or [Hybrid(4, 2, 0)] * len(clusters)   # the syntax's customary default configuration
@@ -394,7 +396,11 @@ class EntropyCode:
         return codes
 
     def write_header(self, b):
-        b.bool(False)                                   # lz77.enabled
+        b.bool(self.lz77 is not None)                   # lz77.enabled
+        if self.lz77 is not None:
+            b.u32((("val", 224), ("val", 512), ("val", 4096), ("bo", 15, 8)), self.lz77["min_symbol"])
+            b.u32((("val", 3), ("val", 4), ("bo", 2, 5), ("bo", 8, 9)), self.lz77["min_length"])
+            self.lz77["len_hybrid"].write(b, 8)         # the length configuration is always coded against log_alpha_size 8
         if len(self.ctx_map) > 1:
             nbits = ceil_log2(len(self.clusters))
             assert nbits <= 3
@@ -447,9 +453,20 @@ class EntropyCode:
     def write_stream(self, b, items):
         """items: list of (context, value). Writes the ANS state + symbols (or the prefix codes) with the hybrid-uint extra bits."""
         toks = []
-        for ctx, v in items:
+        for it in items:
+            if it[0] == "copy":                          # (copy, context of the symbol that would have been coded here, length, distance symbol)
+                _, ctx, length, dist_sym = it
+                cl = self.ctx_map[ctx]
+                t, nb, ex = self.lz77["len_hybrid"].encode(length - self.lz77["min_length"])
+                toks.append((cl, self.lz77["min_symbol"] + t, nb, ex))
+                dcl = self.ctx_map[-1]                   # the distance context is the last one
+                t, nb, ex = self.hybrids[dcl].encode(dist_sym)
+                toks.append((dcl, t, nb, ex))
+                continue
+            ctx, v = it
             cl = self.ctx_map[ctx]
             t, nb, ex = self.hybrids[cl].encode(v)
+            assert self.lz77 is None or t < self.lz77["min_symbol"]
             toks.append((cl, t, nb, ex))
         if self.use_prefix:
             for cl, t, nb, ex in toks:
@@ -589,6 +606,24 @@ def modular_items(root, channels, stream_id=0):
     return items
 
 
+def rle_copies(items, min_length, dist_sym):
+    """Replaces runs of equal (context, value) pairs by one literal plus a copy of distance 1 (`dist_sym` is the distance SYMBOL that means
+    "one sample back": 1 in Modular streams, where symbols below 120 index the special-distance table and entry 1 is (dx, dy) = (1, 0))."""
+    out, i = [], 0
+    while i < len(items):
+        j = i
+        while j + 1 < len(items) and items[j + 1][1] == items[i][1]:
+            j += 1
+        run = j - i + 1
+        out.append(items[i])
+        if run - 1 >= min_length:
+            out.append(("copy", items[i + 1][0], run - 1, dist_sym))
+        else:
+            out += items[i + 1:j + 1]
+        i = j + 1
+    return out
+
+
 def group_header(b, transforms=()):
     b.bool(True)       # use_global_tree
     b.bool(True)       # default weighted-predictor parameters
@@ -619,7 +654,7 @@ def container(codestream, boxes=(), split_at=None, level=None):
 
 
 def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_code=None, rct=None, name=b"", orientation=1,
-                  small_size=True, group_size_shift=1, toc_permutation=None, alpha_associated=False, extra=None):
+                  small_size=True, group_size_shift=1, toc_permutation=None, alpha_associated=False, extra=None, rle=None):
     """A lossless Modular frame. channels: colour planes (1 or 3) + optional alpha + optional `extra` channels, each a list of rows.
     tree/data_code default to a single gradient-predictor leaf over a flat 256-symbol ANS code. Images larger than one group are
     written with a real multi-section TOC (each group its own section); toc_permutation reorders the sections in the file."""
@@ -655,8 +690,9 @@ def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_co
     if rct:
         planes = forward_rct(planes, rct[0], rct[1])
     fits = w <= gdim and h <= gdim
+    pack = (lambda it: rle_copies(it, rle[0], rle[1])) if rle else (lambda it: it)   # rle = (min run to replace, distance symbol)
     if fits:
-        code.write_stream(g, modular_items(tree, planes, 0))
+        code.write_stream(g, pack(modular_items(tree, planes, 0)))
     if ngroups == 1:
         sections = [g.bytes()]
     else:
@@ -667,7 +703,7 @@ def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_co
             if not fits:
                 group_header(s)
                 sub = [[row[x0:x0 + gdim] for row in ch[y0:y0 + gdim]] for ch in planes]
-                code.write_stream(s, modular_items(tree, sub, 1 + 3 * nlf + 17 + gi))
+                code.write_stream(s, pack(modular_items(tree, sub, 1 + 3 * nlf + 17 + gi)))
             sections.append(s.bytes())
     # toc_permutation lists the logical section indices in the order they are stored in the file. The TOC codes the sizes in FILE
     # order plus the permutation that maps a logical section to its file slot.

@@ -90,6 +90,14 @@ def cases():
     f = W.modular_image(_planes(a), alpha_bits=8, extra=ecs)          # channel order in the file: R,G,B(=C,M,Y), alpha, black
     want = np.concatenate([255 - a[..., 0:3], 255 - a[..., 4:5], a[..., 3:4]], axis=2).astype(np.uint8)
     out.append(("cmyka8", f, want, dict(width=15, height=11, format="Cmyk", num_channels=4, has_transparency=True)))
+    # 10. LZ77: long runs of equal residuals become (length, distance 1) copies; ANS with a 256-symbol alphabet so that length tokens
+    #     (min_symbol 224 + ...) fit; the distance context is one extra entry of the context map. Single group and multi-group.
+    for nm, (hh, ww), shift in (("rgb8_lz77_runs", (40, 64), 1), ("rgb8_lz77_multigroup", (150, 200), 0)):
+        yy, xx = np.mgrid[0:hh, 0:ww]
+        a = np.stack([(xx // 16) * 9 + (yy // 8) * 3, np.where((xx > ww // 3) & (yy > hh // 4), 200, 17), (yy // 5) * 7 % 256], axis=2).astype(np.int64) % 256
+        code = W.EntropyCode([0, 1], [("flat", 256), ("flat", 32)], hybrids=[W.Hybrid(4, 2, 0), W.Hybrid(4, 1, 0)], log_alpha=8,
+                             lz77=dict(min_symbol=224, min_length=3, len_hybrid=W.Hybrid(2, 0, 0)))
+        out.append((nm, W.modular_image(_planes(a), data_code=code, rle=(3, 1), group_size_shift=shift), a.astype(np.uint8), dict(width=ww, height=hh, format="Rgb", num_channels=3)))
     return out
 
 
