@@ -138,8 +138,8 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
       if (x + bw > w || y + bh > h || (x & 31) + bw > 32 || (y & 31) + bh > 32) { e = kErrBlockBounds; break; }
       int32_t qf = max(0, min(255, s_info[nb + num]));
       for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { size_t p = o + size_t(iy) * f.xb + ix; if (f.acs[p] != 0xFF) e = kErrBlockBounds; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = uint8_t(qf); }
-      f.acs[o] = uint8_t(s | 0x80); num++; if (s != 0) atomicAdd(f.group_other + ((cy0 + y) >> 5) * f.xgroups + ((cx0 + x) >> 5), 1u);
-      if (bw * bh >= 64) { atomicOr(f.err + 12, 1u); *reinterpret_cast<volatile uint32_t*>(f.host_flags) = 1u; }   // host_flags: page-locked host word, read by the host once this kernel has drained   // a transform of 64x64 px or more: reconstruction needs the second plane set (xyb_tmp)
+      f.acs[o] = uint8_t(s | 0x80); num++; if (s != 0) atomicAdd(f.group_other + ((cy0 + y) >> 5) * f.xgroups + ((cx0 + x) >> 5), 1u + ((bw > 4 || bh > 4) ? 0x10000u : 0u));   // low half: non-DCT8 varblocks, high half: those of 64 px and more
+      if (bw > 4 || bh > 4) { atomicOr(f.err + 12, 1u); *reinterpret_cast<volatile uint32_t*>(f.host_flags) = 1u; }   // host_flags: page-locked host word, read by the host once this kernel has drained   // a transform of 64x64 px or more: reconstruction needs the second plane set (xyb_tmp)
     }
     SetError(f.err, e);
   }

@@ -268,10 +268,18 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
   const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const DTables& tb = *f.tables;
   // ---- small varblocks (both sides <= 32 px): one warp per block. Separable DCTs of 8/16/32 points run as register-resident straight-line
   // code (InverseSeparable); the 8x8 special transforms (IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4) are rare and stay with lane 0.
-  for (int cell = warp + kReconWarps * quarter; cell < 1024; cell += 4 * kReconWarps) {
-    const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
-    const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx; const uint8_t a = f.acs[o]; if (!(a & 0x80)) continue;
-    const int s = min(int(a & 31), 26), bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s); if (bw > 4 || bh > 4 || s == 0) continue;   // DCT8 is handled by k_reconstruct_dct8
+  // A warp owns one row of 32 cells: the lanes read the row's strategy bytes with one coalesced load and vote which cells start a small
+  // non-DCT8 varblock (a serial scan would pay one dependent global load per cell), then the warp works through the set bits.
+  const int by = quarter * kReconWarps + warp;
+  uint32_t my_a = 0;
+  if (by < h && lane < w) my_a = f.acs[size_t(cy0 + by) * f.xb + cx0 + lane];
+  { const int ms = min(int(my_a & 31), 26); const bool cand = (my_a & 0x80) && ms != 0 && CoveredXLog2Dev(ms) <= 2 && CoveredYLog2Dev(ms) <= 2; if (!cand) my_a = 0; }
+  uint32_t todo = __ballot_sync(0xffffffffu, my_a != 0);
+  while (todo) {
+    const int bx = __ffs(int(todo)) - 1; todo &= todo - 1;
+    const uint32_t a = __shfl_sync(0xffffffffu, my_a, bx);
+    const size_t o = size_t(cy0 + by) * f.xb + cx0 + bx;
+    const int s = min(int(a & 31), 26), bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s);
     const int size = bw * bh * 64, H = bh * 8, W = bw * 8, SW = max(H, W), SH = min(H, W), STR = (s >= 4 && s <= 11) ? SW + 4 : SW; const float* dq = reinterpret_cast<const float*>(BlobAt(f, f.dq_off[QuantTableOf(s)]));
     const float scale = f.inv_gs / float(int(f.hf_mul_m1[o]) + 1); const size_t tile = size_t((cy0 + by) / 8) * f.xt + (cx0 + bx) / 8;
     const float kx = f.base_x + float(f.ytox[tile]) * f.inv_color_factor, kb = f.base_b + float(f.ytob[tile]) * f.inv_color_factor;
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
   }
   __syncthreads();
   // ---- large varblocks (a side >= 64 px): the whole CTA per block, staged through the XYB planes themselves (first of the group's four CTAs)
-  if (quarter != 0) return;
+  if (quarter != 0 || (f.group_other[g] >> 16) == 0) return;   // high half of group_other: number of varblocks with a side of 64 px or more
   const int NT = kReconWarps * 32;
   for (int cell = 0; cell < 1024; cell++) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;
