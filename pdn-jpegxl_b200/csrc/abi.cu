@@ -337,9 +337,13 @@ JxlB200Batch* JxlB200DecodeBatchSubmit(int32_t device, int32_t count, const uint
     b->datas.assign(datas, datas + count); b->sizes.assign(dataSizes, dataSizes + count); b->outputs.assign(outputs, outputs + count); b->out_bytes.assign(outputBytes, outputBytes + count);
     b->statuses.assign(size_t(count), DecoderStatus_Ok);
     const int nstreams = std::max(1, std::min(maxInFlight > 0 ? maxInFlight : 16, 256));   // maxInFlight counts streams (bundles) in flight
-    const int batch_lanes = (count >= 64 && nstreams >= 32) ? 16 : (count >= 8 && nstreams >= 8) ? 8 : 1;   // enough images in flight: trade per-image AC latency for resident sections
+    // AC sections per warp: more lanes = fewer resident warps and instructions per section, but a longer walk (16 / 24 / 31 / 41 ms for
+    // 1 / 4 / 8 / 16 lanes on a 12 MP image). Large batches are bound by issue slots and take 16; small ones (a rank's share of a
+    // sharded batch) are bound by the walk itself and take just enough lanes to keep every section resident at once.
+    const int env_lanes = getenv("JXLB200_BATCH_LANES") ? atoi(getenv("JXLB200_BATCH_LANES")) : 0;
+    const int batch_lanes = env_lanes > 0 ? env_lanes : nstreams < 8 ? 1 : count >= 192 ? 16 : count >= 96 ? 8 : count >= 48 ? 4 : count >= 24 ? 2 : 1;
     const int env_bundle = getenv("JXLB200_BUNDLE") ? atoi(getenv("JXLB200_BUNDLE")) : 0;
-    const int bundle_size = std::max(1, std::min(env_bundle > 0 ? env_bundle : ((count >= 64 && nstreams >= 32) ? 2 : 1), kMaxBundle));   // images per stream / per entropy launch
+    const int bundle_size = std::max(1, std::min(env_bundle > 0 ? env_bundle : ((count > nstreams && nstreams >= 32) ? 2 : 1), kMaxBundle));   // images per stream / per entropy launch: only when the batch has more images than streams
     // Host threads: the per-image enqueue work is split over `shards` threads, each with its own share of the streams.
     const int env_threads = getenv("JXLB200_HOST_THREADS") ? atoi(getenv("JXLB200_HOST_THREADS")) : 0;   // read per call (cheap): lets a caller tune it between batches
     int hw = int(std::thread::hardware_concurrency()); if (hw <= 0) hw = 4;
