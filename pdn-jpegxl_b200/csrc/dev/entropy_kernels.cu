@@ -128,20 +128,47 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
   if (all1) {   // common case (only 8x8 strategies): block i sits in cell i, fully parallel
     for (uint32_t i = lane; i < nb; i += 32) { const int yy = cy0 + int(i / w), xx = cx0 + int(i % w); size_t o = size_t(yy) * f.xb + xx; f.acs[o] = uint8_t(s_info[i] | 0x80); f.hf_mul_m1[o] = uint8_t(max(0, min(255, s_info[nb + i])));
       if (s_info[i] != 0) atomicAdd(f.group_other + (yy >> 5) * f.xgroups + (xx >> 5), 1u); }
-  } else if (lane == 0) {
-    uint32_t num = 0, e = 0;
-    for (int y = 0; y < h && !e; y++) for (int x = 0; x < w; x++) {
-      size_t o = size_t(cy0 + y) * f.xb + cx0 + x; if (f.acs[o] != 0xFF) continue;
-      if (num >= nb) { e = kErrHfMeta; break; }
-      int32_t s = s_info[num]; if (s < 0 || s >= 27) { e = kErrBadStrategy; break; }
-      int bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s);
-      if (x + bw > w || y + bh > h || (x & 31) + bw > 32 || (y & 31) + bh > 32) { e = kErrBlockBounds; break; }
-      int32_t qf = max(0, min(255, s_info[nb + num]));
-      for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { size_t p = o + size_t(iy) * f.xb + ix; if (f.acs[p] != 0xFF) e = kErrBlockBounds; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = uint8_t(qf); }
-      f.acs[o] = uint8_t(s | 0x80); num++; if (s != 0) atomicAdd(f.group_other + ((cy0 + y) >> 5) * f.xgroups + ((cx0 + x) >> 5), 1u + ((bw > 4 || bh > 4) ? 0x10000u : 0u));   // low half: non-DCT8 varblocks, high half: those of 64 px and more
-      if (bw > 4 || bh > 4) { atomicOr(f.err + 12, 1u); *reinterpret_cast<volatile uint32_t*>(f.host_flags) = 1u; }   // host_flags: page-locked host word, read by the host once this kernel has drained   // a transform of 64x64 px or more: reconstruction needs the second plane set (xyb_tmp)
+  } else {
+    // Mixed strategies. Pass 1 (lane 0): walk the blocks in order against a coverage bitmap in shared memory (one bit per cell: the next free
+    // cell is a find-first-set on a word, not a chain of dependent global loads) and note each block's first cell in the upper bits of its
+    // s_info entry. Pass 2 (all lanes): fill the strategy / multiplier maps block by block.
+    __shared__ uint32_t cov[256][8];
+    for (int idx = lane; idx < 256 * 8; idx += 32) { const int row = idx >> 3, k = idx & 7, lo = k * 32;
+      cov[row][k] = row >= h ? 0xffffffffu : (w >= lo + 32 ? 0u : (w <= lo ? 0xffffffffu : (0xffffffffu << (w - lo)))); }   // cells outside the group count as covered
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t e = 0; int y = 0, x = 0;
+      for (uint32_t num = 0; num < nb && !e; num++) {
+        for (;;) {   // first uncovered cell at or after (y, x)
+          if (y >= h) { e = kErrHfMeta; break; }
+          const uint32_t free_bits = ~(cov[y][x >> 5] | ((1u << (x & 31)) - 1u));
+          if (free_bits) { x = (x & ~31) + __ffs(int(free_bits)) - 1; break; }
+          x = (x & ~31) + 32; if (x >= w) { x = 0; y++; }
+        }
+        if (e) break;
+        const int32_t s = s_info[num]; if (s < 0 || s >= 27) { e = kErrBadStrategy; break; }
+        const int bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s);
+        if (x + bw > w || y + bh > h || (x & 31) + bw > 32 || (y & 31) + bh > 32) { e = kErrBlockBounds; break; }
+        const uint32_t m = (bw == 32 ? 0xffffffffu : ((1u << bw) - 1u)) << (x & 31);
+        for (int iy = 0; iy < bh; iy++) { if (cov[y + iy][x >> 5] & m) e = kErrBlockBounds; cov[y + iy][x >> 5] |= m; }
+        s_info[num] = s | (x << 8) | (y << 16);
+        if (bw > 4 || bh > 4) { atomicOr(f.err + 12, 1u); *reinterpret_cast<volatile uint32_t*>(f.host_flags) = 1u; }   // host_flags: page-locked host word, read by the host once this kernel has drained: a transform of 64 px or more needs the second plane set (xyb_tmp)
+        x += bw; if (x >= w) { x = 0; y++; }
+      }
+      SetError(f.err, e);
     }
-    SetError(f.err, e);
+    __syncwarp();
+    uint32_t bad_cov = 0;   // every cell must be covered once the blocks are placed
+    for (int idx = lane; idx < h * 8; idx += 32) if (cov[idx >> 3][idx & 7] != 0xffffffffu) bad_cov = kErrHfMeta;
+    if (bad_cov) SetError(f.err, bad_cov);
+    for (uint32_t i = lane; i < nb; i += 32) {
+      const int32_t info = s_info[i]; const int s = info & 0xff, x = (info >> 8) & 0xff, y = (info >> 16) & 0xff; if (s >= 27) continue;
+      const int bw = 1 << CoveredXLog2Dev(s), bh = 1 << CoveredYLog2Dev(s); if (x + bw > w || y + bh > h) continue;   // (pass 1 stopped on an error: entries beyond it are unplaced)
+      const uint8_t qf = uint8_t(max(0, min(255, s_info[nb + i]))); const size_t o = size_t(cy0 + y) * f.xb + cx0 + x;
+      for (int iy = 0; iy < bh; iy++) for (int ix = 0; ix < bw; ix++) { const size_t p = o + size_t(iy) * f.xb + ix; f.acs[p] = uint8_t(s); f.hf_mul_m1[p] = qf; }
+      f.acs[o] = uint8_t(s | 0x80);
+      if (s != 0) atomicAdd(f.group_other + ((cy0 + y) >> 5) * f.xgroups + ((cx0 + x) >> 5), 1u + ((bw > 4 || bh > 4) ? 0x10000u : 0u));   // low half: non-DCT8 varblocks, high half: those of 64 px and more
+    }
   }
 }
 

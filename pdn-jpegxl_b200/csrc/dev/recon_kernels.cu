@@ -318,9 +318,9 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
       __syncwarp();
     }
   }
+  if (quarter != 0 || (f.group_other[g] >> 16) == 0) return;   // high half of group_other: number of varblocks with a side of 64 px or more (uniform over the CTA, so no barrier is skipped by part of it)
   __syncthreads();
   // ---- large varblocks (a side >= 64 px): the whole CTA per block, staged through the XYB planes themselves (first of the group's four CTAs)
-  if (quarter != 0 || (f.group_other[g] >> 16) == 0) return;   // high half of group_other: number of varblocks with a side of 64 px or more
   const int NT = kReconWarps * 32;
   for (int cell = 0; cell < 1024; cell++) {
     const int by = cell >> 5, bx = cell & 31; if (by >= h || bx >= w) continue;

@@ -226,3 +226,24 @@ def test_large_batch_uses_bundles_and_wide_warps(gpu, oracle):
     assert st == [0] * 70
     for i, o in enumerate(outs):
         assert np.array_equal(o, singles[i % 5]), i
+
+
+def test_two_batches_in_flight_through_submit_and_wait(gpu, oracle):
+    """JxlB200DecodeBatchSubmit / Wait: a second batch submitted before the first is waited for; both deliver the single-image pixels,
+    a corrupt file only fails its own status."""
+    files = [oracle.encode(oracle.synthetic_image(320 + 16 * i, 240, seed=40 + i), effort=7 if i % 2 else 3) for i in range(4)]
+    singles = [_decode_gpu(gpu, f).layer_data.color for f in files]
+    a_files, b_files = [files[i % 4] for i in range(40)], [files[(i + 1) % 4] for i in range(36)]
+    b_files[5] = b_files[5][: len(b_files[5]) // 2]                      # truncated: DecodeError for this one only
+    a_out = [np.zeros_like(singles[i % 4]) for i in range(40)]
+    b_out = [np.zeros_like(singles[(i + 1) % 4]) for i in range(36)]
+    ha = gpu.decode_batch_submit(a_files, a_out, max_in_flight=32)
+    hb = gpu.decode_batch_submit(b_files, b_out, max_in_flight=32)
+    sb = hb.wait(raise_on_error=False)
+    sa = ha.wait()
+    assert sa == [0] * 40 and sb[5] == gpu.DECODER_STATUS.index("DecodeError") and all(s == 0 for k, s in enumerate(sb) if k != 5)
+    for i in range(40):
+        assert np.array_equal(a_out[i], singles[i % 4]), i
+    for i in range(36):
+        if i != 5:
+            assert np.array_equal(b_out[i], singles[(i + 1) % 4]), i
