@@ -140,7 +140,7 @@ struct ModDecoder {
         if (t != 0xffffu && t < (1u << (info & 0xff))) { const int32_t cval = UnpackSignedDev(t); for (int x = 0; x < w; x++) cur[x] = cval; continue; }
         // one cluster for the whole row and no prediction: the samples do not depend on each other, only the ANS state chain is serial
         // (HF metadata of frames with variable blocks: strategies and quantiser multipliers are coded this way)
-        { const uint32_t cl = L.cluster[cnt]; for (int x = 0; x < w; x++) cur[x] = UnpackSignedDev(rd.ReadCluster(cv, cl)); continue; }
+        { const uint32_t cl = L.cluster[cnt]; for (int x = 0; x < w; x++) cur[x] = UnpackSignedDev(kSmem ? rd.ReadClusterAns(cv, cl) : rd.ReadCluster(cv, cl)); continue; }
       }
       for (int x = 0; x < w; x++) {
         const T nee_next = (y && x + 3 < w) ? T(up[x + 3]) : T(0);   // issued early: independent of the symbol being decoded

@@ -259,12 +259,16 @@ __global__ void __launch_bounds__(256, 3) k_reconstruct_dct8(const __grid_consta
 }
 
 static const int kReconWarps = 8;
-static const int kReconWarpFloats = 3 * 32 * 36;   // dynamic smem per warp: Sy, Sc, T
-__global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* fp) {
+// Two instantiations, launched one after the other: kSide = 16 takes the varblocks whose longer side is at most 16 px (DCT16x16, 16x8, 8x16 and
+// the 8x8 special transforms: up to 85 registers, 3.8 KB of shared memory per warp, 3 CTAs per SM), kSide = 32 the 32-px ones and the >= 64-px pass
+// (128 registers for the 32-point IDCT, 2 CTAs per SM). One kernel for both ran everything at the occupancy of the widest transform.
+template <int kSide>
+__global__ void __launch_bounds__(kReconWarps * 32, kSide == 16 ? 3 : 2) k_reconstruct(const DFrame* fp) {
   const DFrame& f = *fp; const int g = blockIdx.x >> 2, quarter = blockIdx.x & 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;   // four CTAs share a group's small varblocks
   if (!GroupInBand(f, g) || f.group_other[g] == 0) return;   // every varblock of this group is a DCT8: k_reconstruct_dct8 did all the work
   const int gx = g % int(f.xgroups), gy = g / int(f.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(f.xb) - cx0), h = min(32, int(f.yb) - cy0);
-  extern __shared__ __align__(16) float smem[]; float* Sy = smem + warp * kReconWarpFloats; float* Sc = Sy + 32 * 36; float* T = Sc + 32 * 36;   // per warp: Sy, Sc, T of 32 rows x (32 + 4) floats
+  constexpr int kBuf = kSide * (kSide + 4);   // floats per buffer: kSide rows of kSide + 4
+  extern __shared__ __align__(16) float smem[]; float* Sy = smem + warp * 3 * kBuf; float* Sc = Sy + kBuf; float* T = Sc + kBuf;   // per warp: Sy, Sc, T
   const int16_t* coef = f.coeffs + size_t(g) * 3 * 65536; const size_t plane = size_t(f.xpad) * f.ypad, lfplane = size_t(f.xb) * f.yb; const DTables& tb = *f.tables;
   // ---- small varblocks (both sides <= 32 px): one warp per block. Separable DCTs of 8/16/32 points run as register-resident straight-line
   // code (InverseSeparable); the 8x8 special transforms (IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4) are rare and stay with lane 0.
@@ -273,7 +277,8 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
   const int by = quarter * kReconWarps + warp;
   uint32_t my_a = 0;
   if (by < h && lane < w) my_a = f.acs[size_t(cy0 + by) * f.xb + cx0 + lane];
-  { const int ms = min(int(my_a & 31), 26); const bool cand = (my_a & 0x80) && ms != 0 && CoveredXLog2Dev(ms) <= 2 && CoveredYLog2Dev(ms) <= 2; if (!cand) my_a = 0; }
+  { const int ms = min(int(my_a & 31), 26); const uint32_t lx = CoveredXLog2Dev(ms), ly = CoveredYLog2Dev(ms); const bool wide32 = lx == 2 || ly == 2;
+    const bool cand = (my_a & 0x80) && ms != 0 && lx <= 2 && ly <= 2 && wide32 == (kSide == 32); if (!cand) my_a = 0; }
   uint32_t todo = __ballot_sync(0xffffffffu, my_a != 0);
   while (todo) {
     const int bx = __ffs(int(todo)) - 1; todo &= todo - 1;
@@ -308,17 +313,16 @@ __global__ void __launch_bounds__(kReconWarps * 32) k_reconstruct(const DFrame* 
       float* out = f.xyb + c * plane + size_t(cy0 + by) * 8 * f.xpad + size_t(cx0 + bx) * 8;
       if (plain) {
         const bool tall = H >= W;
-        if (SW == 16 && SH == 16) InverseSeparable<16, 16>(S, T, out, f.xpad, tall, lane);
-        else if (SW == 32 && SH == 32) InverseSeparable<32, 32>(S, T, out, f.xpad, tall, lane);
-        else if (SW == 16 && SH == 8) InverseSeparable<16, 8>(S, T, out, f.xpad, tall, lane);
-        else if (SW == 32 && SH == 8) InverseSeparable<32, 8>(S, T, out, f.xpad, tall, lane);
+        if (kSide == 16) { if (SH == 16) InverseSeparable<16, 16>(S, T, out, f.xpad, tall, lane); else InverseSeparable<16, 8>(S, T, out, f.xpad, tall, lane); }
+        else if (SH == 32) InverseSeparable<32, 32>(S, T, out, f.xpad, tall, lane);
+        else if (SH == 8) InverseSeparable<32, 8>(S, T, out, f.xpad, tall, lane);
         else InverseSeparable<32, 16>(S, T, out, f.xpad, tall, lane);
       } else if (s >= 14 && s <= 17) { if (lane == 0) SetError(f.err, kErrBadStrategy); }
       else if (lane == 0) SpecialTransform8x8(s, S, out, f.xpad, tb.cosines + CosOff(2), tb.cosines + CosOff(3));   // 8x8 block, unpadded rows (STR = 8)
       __syncwarp();
     }
   }
-  if (quarter != 0 || (f.group_other[g] >> 16) == 0) return;   // high half of group_other: number of varblocks with a side of 64 px or more (uniform over the CTA, so no barrier is skipped by part of it)
+  if (kSide != 32 || quarter != 0 || (f.group_other[g] >> 16) == 0) return;   // high half of group_other: number of varblocks with a side of 64 px or more (uniform over the CTA, so no barrier is skipped by part of it)
   __syncthreads();
   // ---- large varblocks (a side >= 64 px): the whole CTA per block, staged through the XYB planes themselves (first of the group's four CTAs)
   const int NT = kReconWarps * 32;
@@ -878,12 +882,12 @@ __global__ void k_output_int(const DFrame* fp) {
 }
 
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st) {
-  static bool attr[64] = {false}; size_t smem = size_t(kReconWarps) * kReconWarpFloats * sizeof(float); int dev = 0; cudaGetDevice(&dev);
-  if (!attr[dev & 63]) { cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr[dev & 63] = true; }
+  static bool attr[64] = {false}; const size_t smem16 = size_t(kReconWarps) * 3 * 16 * 20 * sizeof(float), smem32 = size_t(kReconWarps) * 3 * 32 * 36 * sizeof(float); int dev = 0; cudaGetDevice(&dev);
+  if (!attr[dev & 63]) { cudaFuncSetAttribute(k_reconstruct<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem32)); attr[dev & 63] = true; }
   { const int items = int(h.num_groups) * 32; const int grid = std::min(items, 148 * 3); const size_t d8smem = size_t(2) * 3 * 32 * kD8Stride * sizeof(float);
     static bool attr8[64] = {false}; if (!attr8[dev & 63]) { cudaFuncSetAttribute(k_reconstruct_dct8, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d8smem)); attr8[dev & 63] = true; }
     k_reconstruct_dct8<<<grid, 256, d8smem, st>>>(h, items); }
-  k_reconstruct<<<h.num_groups * 4, kReconWarps * 32, smem, st>>>(d); CountLaunch(2);
+  k_reconstruct<16><<<h.num_groups * 4, kReconWarps * 32, smem16, st>>>(d); k_reconstruct<32><<<h.num_groups * 4, kReconWarps * 32, smem32, st>>>(d); CountLaunch(3);
 }
 // Runs gaborish + EPF; ping-pongs between xyb and xyb_tmp. Returns the buffer holding the result.
 void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st) {
