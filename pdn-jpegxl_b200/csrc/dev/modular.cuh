@@ -275,11 +275,15 @@ static __device__ __noinline__ void DecodeRowsLeanSpec(LeanSpecPrep& P, const ui
   const uint32_t my_info = P.slot_info[uint32_t(lane) < K ? lane : 0]; const bool my_const = (my_info >> 16) != 0xffffu; const uint32_t my_split = 1u << (my_info & 0xffu);
   BitRd br = P.br; uint32_t state = P.state, err = P.err;
   __syncwarp();
-  const uint32_t log_entry = 12 - log_alpha, pos_mask = (1u << log_entry) - 1; const uint8_t* slot_of = P.slot_of;
+  const uint32_t log_entry = 12 - log_alpha, pos_mask = (1u << log_entry) - 1;
+  // Software pipeline across symbols: the warp issues in order and the loop has a back edge, so the alias entry of the NEXT symbol is
+  // requested as soon as the new ANS state exists (right after the shuffle), not at the top of the next iteration: its shared-memory
+  // latency then runs beside the unpack / predict / store tail of the current symbol.
+  const uint8_t* slot_of = P.slot_of; const uint2* Tl = T + lane;
+  uint2 e = Tl[((state & 0xfff) >> log_entry) << 5];
   auto symbol = [&](int32_t ctxv) -> int32_t {
     const uint32_t slot = slot_of[min(max(ctxv, -128), 127) + 128];
     const uint32_t idx = state & 0xfff, i = idx >> log_entry, pos = idx & pos_mask;
-    const uint2 e = T[(i << 5) + uint32_t(lane)];
     const bool g = pos >= (e.x & 0xffu);
     const uint32_t s1 = (g ? (e.y >> 16) : (e.y & 0xffffu)) * (state >> 12) + (g ? (e.x >> 16) : 0u) + pos;
     const bool refill = s1 < 65536u;
@@ -289,6 +293,7 @@ static __device__ __noinline__ void DecodeRowsLeanSpec(LeanSpecPrep& P, const ui
     if ((cand & 0xffu) >= my_split) cand |= 0x200u;                // token has a hybrid-uint tail
     const uint32_t sel = __shfl_sync(0xffffffffu, cand, int(slot));
     state = __shfl_sync(0xffffffffu, cand_state, int(slot));
+    e = Tl[((state & 0xfff) >> log_entry) << 5];
     if (sel & 0x100u) br.Skip(16);
     uint32_t tok = sel & 0xffu;
     if (sel & 0x200u) {   // rare for LF residuals; uniform over the warp
