@@ -432,7 +432,9 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
     { static std::atomic<uint32_t> lf_cursor{0}, ac_cursor{0};   // concurrent images start their few long-running CTAs on different SMs
       h.lf_cta_offset = lf_cursor.fetch_add(h.num_lf_groups) % 148u; h.ac_cta_offset = vardct ? ac_cursor.fetch_add(uint32_t(AcCtas(h, ac_lanes))) % 148u : 0; }
     // + the transposed alias table of the speculative LF loop (32 slots x 8 bytes per alias entry), when it stays small
-    { const uint32_t spec = has_tree && !h.mod_code.use_prefix ? (256u << h.mod_code.log_alpha) : 0u; h.lf_smem = std::min<uint32_t>(modb + 64 + (spec <= 64 * 1024 ? spec + 16 : 0), 96 * 1024); } ac_budget = [this, code_bytes]() { uint32_t acb = 0; bool prefix = false; for (uint32_t p = 0; p < h.num_passes; p++) { acb = std::max(acb, code_bytes(h.ac_code[p])); prefix |= h.ac_code[p].use_prefix != 0; }
+    { static const bool no_spec = getenv("JXLB200_NO_SPEC") != nullptr;   // A/B switch: without room for the transposed alias table the kernels take the one-lane loop
+      const uint32_t spec = has_tree && !h.mod_code.use_prefix && !no_spec ? (256u << h.mod_code.log_alpha) : 0u; const uint32_t copies = h.num_mod_channels > h.first_group_channel ? 4u : 1u;   // k_mod_group: one table per warp, 4 warps per CTA
+      h.lf_smem = std::min<uint32_t>(modb + 64 + (spec * copies <= 64 * 1024 ? spec * copies + 64 : (spec <= 64 * 1024 ? spec + 16 : 0)), 96 * 1024); } ac_budget = [this, code_bytes]() { uint32_t acb = 0; bool prefix = false; for (uint32_t p = 0; p < h.num_passes; p++) { acb = std::max(acb, code_bytes(h.ac_code[p])); prefix |= h.ac_code[p].use_prefix != 0; }
       for (uint32_t p = 0; p < h.num_passes; p++) prefix |= h.ac_code[p].lz77 != 0;   // LZ77 streams take the generic reader too
       h.ac_smem = acb + 64; h.ac_fast = (!prefix && h.ac_smem <= 96 * 1024) ? 1 : 0; if (!h.ac_fast) h.ac_smem = 0; };
     if (vardct && !single) ac_budget();

@@ -212,25 +212,36 @@ __global__ void k_lf_smooth(const DFrame* fp) {
   for (int c = 0; c < 3; c++) f.lf_tmp[c * plane + i] = (sm[c] - mc[c]) * factor + mc[c];
 }
 
-// Decodes the group-local Modular channels (extra channels of VarDCT frames, everything of Modular frames).
+// Decodes the group-local Modular channels (extra channels of VarDCT frames, everything of Modular frames). Warp-collective: lane 0 owns the
+// bit stream and parses; channels that qualify run through the speculative loop with every lane (DecodeRowsLeanSpec), the others on lane 0.
+// `prep` / `flag` are this warp's shared-memory words, `T` its room for the transposed alias table (spec_bytes bytes, may be 0).
 template <bool kNarrow>
-__device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, int pass, bool* need_init) {
+__device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, int pass, int lane, LeanSpecPrep& prep, volatile uint32_t* flag, uint2* T, uint32_t spec_bytes) {
   const int gd = int(f.group_dim), gx = g % int(f.xgroups), gy = g / int(f.xgroups), x0 = gx * gd, y0 = gy * gd;
-  int nch = 0;
-  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
-    int rx0 = x0 >> ch.hshift, ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) continue; int rw = min(gd >> ch.hshift, int(ch.w) - rx0), rh = min(gd >> ch.vshift, int(ch.h) - ry0); if (rw > 0 && rh > 0) nch++; }
+  // the channels of this group and pass (every lane derives the same list from the frame descriptor)
+  auto region = [&](uint32_t c, int& rx0, int& ry0, int& rw, int& rh) -> bool {
+    const DModChannel& ch = f.mod_ch[c]; const int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) return false;
+    rx0 = x0 >> ch.hshift; ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) return false;
+    rw = min(gd >> ch.hshift, int(ch.w) - rx0); rh = min(gd >> ch.vshift, int(ch.h) - ry0); return rw > 0 && rh > 0;
+  };
+  int nch = 0; uint32_t dm = 0;
+  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { int rx0, ry0, rw, rh; if (region(c, rx0, ry0, rw, rh)) { nch++; dm = max(dm, uint32_t(rw)); } }
   if (nch == 0) return;
-  if (!ReadGroupHeaderDev(md, f)) return;
-  md.rd.Init(md.cv); *need_init = false;
-  { uint32_t dm = 0; for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
-      int rx0 = x0 >> ch.hshift, ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) continue; int rw = min(gd >> ch.hshift, int(ch.w) - rx0), rh = min(gd >> ch.vshift, int(ch.h) - ry0); if (rw > 0 && rh > 0) dm = max(dm, uint32_t(rw)); }
-    md.dist_mult = dm; }
+  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f); if (ok) { md.rd.Init(md.cv); md.dist_mult = dm; } *flag = ok ? 1u : 0u; }
+  __syncwarp();
+  if (!*flag) return;
   const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g; int k = 0;
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth);
-  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { const DModChannel& ch = f.mod_ch[c]; int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) continue;
-    int rx0 = x0 >> ch.hshift, ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) continue; int rw = min(gd >> ch.hshift, int(ch.w) - rx0), rh = min(gd >> ch.vshift, int(ch.h) - ry0); if (rw <= 0 || rh <= 0) continue;
-    md.DecodeChannel<kNarrow>(k++, sid, f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, ch.w, rw, rh, wp); }
-  if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
+  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) {
+    int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
+    const DModChannel& ch = f.mod_ch[c]; int32_t* dst = f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0;
+    if (lane == 0) { prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(k, sid, prep, spec_bytes))) md.DecodeChannel<kNarrow>(k, sid, dst, ch.w, rw, rh, wp); }
+    __syncwarp();
+    if (prep.ok) { DecodeRowsLeanSpec(prep, reinterpret_cast<const uint8_t*>(md.cv.alias), md.cv.log_alpha, T, dst, ch.w, rw, rh, lane); if (lane == 0) md.FinishLeanSpec(prep); }
+    __syncwarp();
+    k++;
+  }
+  if (lane == 0 && !md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
 }
 
 // AC coefficients of 256x256 groups (A.8 "PassGroup AC decode"), SIMT over independent sections.
@@ -336,18 +347,22 @@ static const int kModGroupsPerCta = 4;
 template <bool kNarrow>
 __global__ void __launch_bounds__(32 * kModGroupsPerCta) k_mod_group(const __grid_constant__ DFrame f, int pass) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const int g = blockIdx.x * kModGroupsPerCta + warp; const bool active = g < int(f.num_groups);
-  __shared__ ChanLut sh_lut[kModGroupsPerCta]; extern __shared__ __align__(16) uint8_t dsm[];
+  __shared__ ChanLut sh_lut[kModGroupsPerCta]; __shared__ LeanSpecPrep sh_prep[kModGroupsPerCta]; __shared__ uint32_t sh_flag[kModGroupsPerCta]; extern __shared__ __align__(16) uint8_t dsm[];
   ModDecoder md; BindModDecoder(md, f, &sh_lut[warp]); uint32_t used = 0;
   StageModDecoder(md, f, dsm, f.lf_smem, used, tid, 32 * kModGroupsPerCta);
   __syncthreads();
-  if (lane != 0 || !active || !GroupInBand(f, g)) return;
+  if (!active || !GroupInBand(f, g)) return;   // whole warps leave; inside a warp every lane stays (the speculative loop is warp-collective)
+  // each warp's share of the dynamic shared memory left after the staged tables: room for its transposed alias table
+  const uint32_t spec_off = (used + 15u) & ~15u, spec_all = f.lf_smem > spec_off ? f.lf_smem - spec_off : 0u, spec_bytes = (spec_all / kModGroupsPerCta) & ~15u;
+  uint2* T = reinterpret_cast<uint2*>(dsm + spec_off + size_t(warp) * spec_bytes);
   const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
   const uint32_t sidx = 2 + f.num_lf_groups + uint32_t(pass) * f.num_groups + g;
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
   if (f.encoding == 0) start = f.ac_endpos[size_t(pass) * f.num_groups + g];
   md.rd.br.Init(f.comp, start); if (f.lz_window) md.rd.win = f.lz_window + size_t(g) * kLzWindow;
-  bool need_init = true; md.rd.err = 0; DecodeModularGroupDev<kNarrow>(md, f, g, pass, &need_init); uint32_t err = md.rd.err;
-  uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
+  md.rd.err = 0; DecodeModularGroupDev<kNarrow>(md, f, g, pass, lane, sh_prep[warp], &sh_flag[warp], T, spec_bytes);
+  if (lane != 0) return;
+  uint32_t err = md.rd.err; uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
   SetError(f.err, err);
 }
 
