@@ -89,6 +89,12 @@ JXLFT_API EncoderStatus JXLFT_CALL SaveImage(const BitmapData* bitmap, const Enc
  * caller learns from JxlB200PeekInfo. Returns a DecoderStatus. */
 JXLFT_API DecoderStatus JXLFT_CALL JxlB200LoadImageBgra(const uint8_t* data, size_t dataSize, uint8_t* surface, size_t surfaceBytes,
                                                          int32_t* width, int32_t* height, ErrorInfo* errorInfo);
+/* Decode into the two bitmaps a layer is made of, fusing the managed repack of I/DecoderLayerData.cs:26-125 (Set*ImageData, :127-992)
+ * and I/TransparencyMapping.cs:18-32: `color` receives Rgb24 / Rgb48 / Rgb48Half / Rgb96Float pixels (gray replicated into R, G, B) or
+ * Cmyk32, `transparency` (may be NULL for images without alpha) the Alpha8 bitmap; both tightly packed. info[6] receives width, height,
+ * DecoderImageFormat, ImageChannelRepresentation, hasTransparency and the channel count of the colour bitmap. */
+JXLFT_API DecoderStatus JXLFT_CALL JxlB200LoadImageLayers(const uint8_t* data, size_t dataSize, uint8_t* color, size_t colorBytes,
+                                                           uint8_t* transparency, size_t transparencyBytes, int32_t* info, ErrorInfo* errorInfo);
 /* Header-only pass (pass 1 of DecoderReadImage, N/Decoder/JxlDecoder.cpp:412-793) without callbacks. info[8] receives:
  * width, height, DecoderImageFormat, ImageChannelRepresentation, hasTransparency, numChannels, KnownColorProfile or -1, isContainer. */
 JXLFT_API DecoderStatus JXLFT_CALL JxlB200PeekInfo(const uint8_t* data, size_t dataSize, int32_t* info, ErrorInfo* errorInfo);

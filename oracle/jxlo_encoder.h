@@ -68,7 +68,9 @@ inline float TfToLinear(float v, const ColorEncoding& ce, float intensity_target
     case kTf709: r = a < 0.081f ? a / 4.5f : std::pow((a + 0.099f) / 1.099f, 1.0f / 0.45f); break;
     case kTfPQ: { const double m1 = 2610.0 / 16384, m2 = 2523.0 / 4096 * 128, c1 = 3424.0 / 4096, c2 = 2413.0 / 4096 * 32, c3 = 2392.0 / 4096 * 32;
       double p = std::pow(double(a), 1.0 / m2); double num = std::max(p - c1, 0.0), den = c2 - c3 * p; r = float(std::pow(num / den, 1.0 / m1) * 10000.0 / intensity_target); break; }
-    case kTfDCI: r = std::pow(a, 2.6f); break; default: throw Error("unsupported source transfer function");
+    case kTfDCI: r = std::pow(a, 2.6f); break;
+    case kTfHLG: { const double ha = 0.17883277, hb = 0.28466892, hc = 0.55991073; r = a <= 0.5f ? float(double(a) * a / 3.0) : float((std::exp((a - hc) / ha) + hb) / 12.0); break; }
+    default: throw Error("unsupported source transfer function");
   }
   return v < 0 ? -r : r;
 }
@@ -112,7 +114,9 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
   // integer view of a sample for Modular coding (lossless colour, and extra channels always)
   auto isample = [&](int x, int y, int c) -> int32_t {
     size_t i = (size_t(y) * xs + x) * C + c; if (in.u8) return in.u8[i];
-    if (p.bd.float_sample) { JXLO_CHECK(p.bd.bits == 32 && p.bd.exp_bits == 8, "float lossless source must be binary32"); int32_t v; memcpy(&v, &in.f32[i], 4); return v; }
+    if (p.bd.float_sample) {
+      if (p.bd.bits == 16 && p.bd.exp_bits == 5) return int32_t(BitWriter::FloatToHalf(in.f32[i]));   // binary16: the half's bit pattern is the Modular sample
+      JXLO_CHECK(p.bd.bits == 32 && p.bd.exp_bits == 8, "float lossless source must be binary32 or binary16"); int32_t v; memcpy(&v, &in.f32[i], 4); return v; }
     return int32_t(std::lrintf(std::min(1.f, std::max(0.f, in.f32[i])) * float((1u << p.bd.bits) - 1)));
   };
   if (in.u8) JXLO_CHECK(!p.bd.float_sample && p.bd.bits == 8, "u8 input requires an 8-bit stream");

@@ -164,7 +164,7 @@ inline DecodedImage DecodeImage(const uint8_t* data, size_t size, const DecodeOp
   auto ec_sample = [&](int ec, int x, int y) -> float { const Channel& ch = fs.gimg.ch[ec_base + ec]; int s = int(m.ec[ec].dim_shift); return IntToFloatSample(ch.row(std::min(y >> s, ch.h - 1))[std::min(x >> s, ch.w - 1)], m.ec[ec].bd); };
   // output colour transform (Appendix C-1: default output encoding of a freshly reset decoder)
   bool to_target = m.xyb_encoded && !m.ce.want_icc; ColorEncoding target = to_target ? m.ce : ColorEncoding(); if (m.xyb_encoded && m.ce.want_icc && m.ce.color_space == kCsGray) target.color_space = kCsGray;
-  if (to_target && !target.have_gamma && (target.tf == kTfUnknown || target.tf == kTfHLG)) { target = ColorEncoding(); target.color_space = m.ce.color_space; }
+  if (to_target && !target.have_gamma && target.tf == kTfUnknown) { target = ColorEncoding(); target.color_space = m.ce.color_space; }
   float mat[9]; LinearSrgbToTarget(target, mat); float itscale = 255.0f / m.tm.intensity_target;
   int C = info.num_channels, cc = m.num_color_channels(); size_t bps = BytesPerSample(info.sample_type), bpp = bps * C;
   out.width = uint32_t(xs); out.height = uint32_t(ys); out.pixels.assign(size_t(xs) * ys * bpp, 0);

@@ -124,6 +124,9 @@ inline float TfFromLinear(float v, const ColorEncoding& ce, float intensity_targ
     case kTfPQ: { const double m1 = 2610.0 / 16384, m2 = 2523.0 / 4096 * 128, c1 = 3424.0 / 4096, c2 = 2413.0 / 4096 * 32, c3 = 2392.0 / 4096 * 32;
       double yv = std::min(1.0, double(a) * intensity_target / 10000.0); double p = std::pow(yv, m1); r = float(std::pow((c1 + c2 * p) / (1 + c3 * p), m2)); break; }
     case kTfDCI: r = std::pow(a, 1.0f / 2.6f); break;
+    // ARIB STD-B67 OETF on the nominal range [0, 1] (12 E = the 0..12 scene range); an HLG-tagged file comes back in its own encoding, so no
+    // OOTF is involved (display light is only derived when the output encoding differs from the file's, which the reference never asks for)
+    case kTfHLG: { const double ha = 0.17883277, hb = 0.28466892, hc = 0.55991073; r = a <= 1.0f / 12 ? float(std::sqrt(3.0 * a)) : float(ha * std::log(12.0 * a - hb) + hc); break; }
     default: throw Error("unsupported transfer function for output");
   }
   return v < 0 ? -r : r;

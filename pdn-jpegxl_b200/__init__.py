@@ -77,7 +77,7 @@ class IOCallbacks(C.Structure):
 
 EXPORTS = ["GetLibJxlVersion", "LoadImage", "SaveImage", "JxlB200LoadImageBgra", "JxlB200PeekInfo", "JxlB200DecodeBatch", "JxlB200EncodeToMemory",
            "JxlB200Free", "JxlB200LastStageTimes", "JxlB200KernelLaunchCount", "JxlB200DebugDecodeStage", "JxlB200CudaAvailable", "JxlB200BandLayout",
-           "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc", "JxlB200DecodeBatchSubmit", "JxlB200DecodeBatchWait"]
+           "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc", "JxlB200DecodeBatchSubmit", "JxlB200DecodeBatchWait", "JxlB200LoadImageLayers"]
 
 _lib.GetLibJxlVersion.restype = C.c_uint32
 _lib.LoadImage.argtypes = [C.POINTER(DecoderCallbacks), C.c_void_p, C.c_size_t, C.POINTER(ErrorInfo)]
@@ -88,6 +88,8 @@ _lib.SaveImage.restype = C.c_int32
 _lib.JxlB200LoadImageBgra.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
 _lib.JxlB200LoadImageBgra.restype = C.c_int32
 _lib.JxlB200PeekInfo.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200LoadImageLayers.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+_lib.JxlB200LoadImageLayers.restype = C.c_int32
 _lib.JxlB200BandLayout.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
 _lib.JxlB200BandLayout.restype = C.c_int32
 _lib.JxlB200DecodeBand.argtypes = [C.c_int32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
@@ -448,6 +450,25 @@ def load_image_bgra(data):
     if st != 0:
         raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
     return out
+
+
+def load_image_layers(data):
+    """JxlB200LoadImageLayers: the colour bitmap and the Alpha8 bitmap of I/DecoderLayerData.cs, split on the GPU. Returns (color, transparency | None)."""
+    info = peek_info(data)
+    buf = bytes(data)
+    if info["format"] == "Cmyk" and info["representation"] != 0:
+        raise FormatException("UnsupportedChannelFormat", "unsupported CMYK channel representation")
+    ch = 4 if info["format"] == "Cmyk" else 3
+    color = np.empty((info["height"], info["width"], ch), _DTYPES[info["representation"]])
+    alpha = np.empty((info["height"], info["width"]), np.uint8) if info["has_transparency"] else None
+    got = (C.c_int32 * 6)()
+    ei = ErrorInfo()
+    st = _lib.JxlB200LoadImageLayers(buf, len(buf), color.ctypes.data, color.nbytes, alpha.ctypes.data if alpha is not None else None,
+                                     alpha.nbytes if alpha is not None else 0, got, C.byref(ei))
+    if st != 0:
+        raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
+    assert (got[0], got[1], got[5]) == (info["width"], info["height"], ch)
+    return color, alpha
 
 
 def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, width=None, height=None, stride=None, host_array=None):

@@ -141,6 +141,33 @@ DecoderStatus JxlB200LoadImageBgra(const uint8_t* data, size_t dataSize, uint8_t
   return DecoderStatus_Ok;
 }
 
+// The managed layer repack as a GPU epilogue (I/DecoderLayerData.cs:26-125 and its eighteen Set*ImageData variants): the decoder's
+// interleaved output stays on the device, k_split_layers writes the colour bitmap (Rgb24 / Rgb48 / Rgb48Half / Rgb96Float with gray
+// replicated, Cmyk32) and the Alpha8 transparency bitmap, and only those two cross PCIe.
+DecoderStatus JxlB200LoadImageLayers(const uint8_t* data, size_t dataSize, uint8_t* color, size_t colorBytes, uint8_t* transparency, size_t transparencyBytes,
+                                     int32_t* info6, ErrorInfo* errorInfo) {
+  if (!data || !color) return DecoderStatus_NullParameter;
+  void* d_color = nullptr; void* d_alpha = nullptr; DecoderStatus rc = DecoderStatus_Ok;
+  try {
+    DecodeRequest req; req.data = data; req.size = dataSize; req.device_output = true; DecodeResult res = DecodeOnGpu(req); g_last_times = res.times;
+    if (res.status != Status::Ok) { SetErrorMessage(errorInfo, res.message); return DecoderStatus(res.status); }
+    const ParsedInfo& pi = res.info; const size_t npix = size_t(res.out_width) * res.out_height; const size_t bps = pi.sample_type == 0 ? 1 : pi.sample_type == 3 ? 4 : 2;
+    if (pi.format == 2 && pi.sample_type != 0) { SetErrorMessage(errorInfo, "unsupported CMYK channel representation"); return DecoderStatus_UnsupportedChannelFormat; }   // I/DecoderLayerData.cs:127-162
+    const size_t dst_ch = pi.format == 2 ? 4 : 3, need_color = npix * dst_ch * bps, need_alpha = pi.has_alpha ? npix : 0;
+    if (info6) { info6[0] = int32_t(res.out_width); info6[1] = int32_t(res.out_height); info6[2] = pi.format; info6[3] = pi.sample_type; info6[4] = pi.has_alpha ? 1 : 0; info6[5] = int32_t(dst_ch); }
+    if (colorBytes < need_color || (pi.has_alpha && (!transparency || transparencyBytes < need_alpha))) { SetErrorMessage(errorInfo, "layer buffers too small"); return DecoderStatus_InvalidParameter; }
+    if (cudaMalloc(&d_color, need_color ? need_color : 1) != cudaSuccess || cudaMalloc(&d_alpha, need_alpha ? need_alpha : 1) != cudaSuccess) { rc = DecoderStatus_OutOfMemory; }
+    else {
+      LaunchSplitLayers(res.pixels, d_color, static_cast<uint8_t*>(d_alpha), npix, pi.format, pi.sample_type, pi.has_alpha, 0);
+      cudaError_t e = cudaMemcpy(color, d_color, need_color, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess && need_alpha) e = cudaMemcpy(transparency, d_alpha, need_alpha, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { SetErrorMessage(errorInfo, std::string("CUDA: ") + cudaGetErrorString(e)); rc = DecoderStatus_DecodeError; }
+    }
+  } catch (const std::bad_alloc&) { rc = DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); rc = DecoderStatus_DecodeError; } catch (...) { rc = DecoderStatus_DecodeError; }
+  if (d_color) cudaFree(d_color); if (d_alpha) cudaFree(d_alpha);
+  return rc;
+}
+
 // Band decode: one rank's share of a frame sharded by group rows (SURVEY §8e "gigapixel": AC-group row ranges per GPU, no collective —
 // each rank reconstructs one extra group row on either side instead of exchanging a halo). layout4 = {width, height, group size in
 // pixels, number of group rows}. Rows [groupRowBegin*groupDim, min(groupRowEnd*groupDim, height)) are written to `out`, interleaved

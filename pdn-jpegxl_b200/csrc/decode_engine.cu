@@ -122,7 +122,7 @@ static int KnownProfileOf(const ColorEncoding& c) {   // N/Decoder/JxlDecoder.cp
 // Output encoding of the samples (Appendix C-1): original enum encoding when expressible without a CMS, else sRGB.
 static ColorEncoding OutputEncoding(const ImageMetadata& m) {
   ColorEncoding t; if (!m.xyb_encoded) return m.ce;
-  bool ok = !m.ce.want_icc && (m.ce.have_gamma || (m.ce.tf != kTfUnknown && m.ce.tf != kTfHLG)) && m.ce.color_space != kCsXYB && m.ce.color_space != kCsUnknown;
+  bool ok = !m.ce.want_icc && (m.ce.have_gamma || m.ce.tf != kTfUnknown) && m.ce.color_space != kCsXYB && m.ce.color_space != kCsUnknown;
   if (ok) return m.ce; t.color_space = m.ce.color_space == kCsGray ? kCsGray : kCsRGB; t.intent = 0; return t;
 }
 
@@ -271,7 +271,7 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
     tree = DecodeTree(br, limit); tree_code = DecodeCode(br, NumLeaves(tree));
     std::vector<DTreeNode> nodes(tree.size()); uint32_t uses_wp = 0;
     for (size_t i = 0; i < tree.size(); i++) { const TreeNode& n = tree[i];
-      if (n.property >= 0) { nodes[i] = make_int4(n.property, n.splitval, n.lchild, n.rchild); if (n.property == 15) uses_wp = 1; JXLG_CHECK(n.property < 16, "MA-tree properties of previous channels are not supported by the GPU decoder yet"); }
+      if (n.property >= 0) { nodes[i] = make_int4(n.property, n.splitval, n.lchild, n.rchild); if (n.property == 15) uses_wp = 1; JXLG_CHECK(n.property < 16 + 4 * 4, "MA-tree properties of more than four previous channels are not supported by the GPU decoder"); }
       else { nodes[i] = make_int4(-1, (n.leaf_id << 4) | n.predictor, n.offset, int(n.multiplier)); if (n.predictor == 6) uses_wp = 1; } }
     h.tree_off = blob.Add(nodes.data(), nodes.size() * sizeof(DTreeNode)); h.tree_size = uint32_t(nodes.size()); h.uses_wp = uses_wp; h.mod_code = blob.AddCode(tree_code);
   }

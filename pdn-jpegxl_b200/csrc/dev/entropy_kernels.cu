@@ -79,7 +79,7 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
   if (sh_hdr_ok) {
     for (int c = 0; c < 3; c++) {
       const int dstc = c == 0 ? 1 : c == 1 ? 0 : 2; int32_t* dst = f.lfq + dstc * plane + size_t(cy0) * f.xb + cx0;
-      if (lane == 0) { sh_prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(c, lf_sid, sh_prep, spec_bytes))) md.DecodeChannel<kNarrow>(c, lf_sid, dst, f.xb, w, h, wp); }
+      if (lane == 0) { if (c == 0) md.ResetChannels(); md.NoteChannel(dst, f.xb, w, h, 3, 3); sh_prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(c, lf_sid, sh_prep, spec_bytes))) md.DecodeChannel<kNarrow>(c, lf_sid, dst, f.xb, w, h, wp); }
       __syncwarp();
       if (sh_prep.ok) {   // uniform: written by lane 0 before the barrier
         DecodeRowsLeanSpec(sh_prep, reinterpret_cast<const uint8_t*>(md.cv.alias), md.cv.log_alpha, reinterpret_cast<uint2*>(dsm + spec_off), dst, f.xb, w, h, lane);
@@ -102,8 +102,9 @@ __device__ __forceinline__ void LfGroupBody(const DFrame& f, const int g) {
       ok = ReadGroupHeaderDev(md, f);
       if (ok) {
         md.rd.Init(md.cv); const int sid = 1 + 2 * int(f.num_lf_groups) + g; md.dist_mult = uint32_t(max(max(tw, w), int(min(nb, 65536u))));
-        md.DecodeChannel<kNarrow>(0, sid, s_cflx, tw, tw, th, wp); md.DecodeChannel<kNarrow>(1, sid, s_cflb, tw, tw, th, wp);
-        if (nb <= 65536u) { md.DecodeChannel<kNarrow>(2, sid, s_info, nb, int(nb), 2, wp); md.DecodeChannel<kNarrow>(3, sid, s_sharp, w, w, h, wp); } else md.rd.err = kErrHfMeta;
+        md.ResetChannels();
+        md.NoteChannel(s_cflx, tw, tw, th, 3, 3); md.DecodeChannel<kNarrow>(0, sid, s_cflx, tw, tw, th, wp); md.NoteChannel(s_cflb, tw, tw, th, 3, 3); md.DecodeChannel<kNarrow>(1, sid, s_cflb, tw, tw, th, wp);
+        if (nb <= 65536u) { md.NoteChannel(s_info, nb, int(nb), 2, 0, 0); md.DecodeChannel<kNarrow>(2, sid, s_info, nb, int(nb), 2, wp); md.NoteChannel(s_sharp, w, w, h, 0, 0); md.DecodeChannel<kNarrow>(3, sid, s_sharp, w, w, h, wp); } else md.rd.err = kErrHfMeta;
         if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
       }
     }
@@ -235,7 +236,7 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) {
     int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
     const DModChannel& ch = f.mod_ch[c]; int32_t* dst = f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0;
-    if (lane == 0) { prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(k, sid, prep, spec_bytes))) md.DecodeChannel<kNarrow>(k, sid, dst, ch.w, rw, rh, wp); }
+    if (lane == 0) { if (k == 0) md.ResetChannels(); md.NoteChannel(dst, ch.w, rw, rh, int(ch.hshift), int(ch.vshift)); prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(k, sid, prep, spec_bytes))) md.DecodeChannel<kNarrow>(k, sid, dst, ch.w, rw, rh, wp); }
     __syncwarp();
     if (prep.ok) { DecodeRowsLeanSpec(prep, reinterpret_cast<const uint8_t*>(md.cv.alias), md.cv.log_alpha, T, dst, ch.w, rw, rh, lane); if (lane == 0) md.FinishLeanSpec(prep); }
     __syncwarp();
@@ -379,7 +380,8 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
   { uint32_t dm = 0; for (uint32_t c = 0; c < num_channels; c++) dm = max(dm, f.mod_ch[c].w); md.dist_mult = dm; }
   md.rd.Init(md.cv);
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + f.num_groups) * WPScratchInts(kMaxWpWidth);
-  for (uint32_t c = 0; c < num_channels; c++) { const DModChannel& ch = f.mod_ch[c]; md.DecodeChannel(int(c), 0, f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), wp); }
+  md.ResetChannels();
+  for (uint32_t c = 0; c < num_channels; c++) { const DModChannel& ch = f.mod_ch[c]; md.NoteChannel(f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), int(ch.hshift), int(ch.vshift)); md.DecodeChannel(int(c), 0, f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), wp); }
   if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
   f.end_bitpos[0] = md.rd.br.BitPos();
   SetError(f.err, md.rd.err);

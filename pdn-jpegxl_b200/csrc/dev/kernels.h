@@ -17,6 +17,7 @@ void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st);          
 bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st);       // gaborish + EPF + colour fused (returns false when not applicable)
 void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st);
 void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st);            // colour transform + sample conversion + interleave (+BGRA)
+void LaunchSplitLayers(const void* src, void* color, uint8_t* alpha, size_t npix, int format, int sample_type, bool has_alpha, cudaStream_t st);   // I/DecoderLayerData.cs repack
 void FillDeviceTables(DTables* host_tables);
 int LaunchCount();                                                                 // kernels launched by this process so far (bench gpu_launches)
 void CountLaunch(int n = 1);

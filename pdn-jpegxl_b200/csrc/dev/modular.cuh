@@ -95,7 +95,24 @@ template <typename T> struct ModMath {
 struct LeanSpecPrep { BitRd br; uint32_t state, err, K, ok; uint32_t slot_info[32], slot_alias_off[32]; uint8_t slot_of[256]; };
 
 struct ModDecoder {
-  SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; uint32_t dist_mult = 0; /* LZ77: widest channel of the sub-bitstream */ ChanLut* lut;   // lut: per-decoding-thread scratch (shared memory)
+  SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; uint32_t dist_mult = 0; /* LZ77: widest channel of the sub-bitstream */ ChanLut* lut;
+  // Earlier channels of the same sub-bitstream with the geometry of the channel being decoded, nearest first (MA-tree properties 16 + 4k .. 19 + 4k:
+  // |v|, v, |v - g|, v - g of that channel's sample at the same position, g its clamped gradient). The caller keeps the list (NoteChannel).
+  static const int kMaxRefs = 4; const int32_t* ref_p[kMaxRefs]; size_t ref_stride[kMaxRefs]; int ref_n = 0;
+  struct Seen { const int32_t* p; size_t stride; int w, h, hs, vs; }; Seen seen[8]; int num_seen = 0;
+  __device__ void ResetChannels() { num_seen = 0; ref_n = 0; }
+  // call before decoding a channel: selects its reference channels among those noted so far, then notes the channel itself
+  __device__ void NoteChannel(const int32_t* p, size_t stride, int w, int h, int hs, int vs) {
+    ref_n = 0; for (int j = num_seen - 1; j >= 0 && ref_n < kMaxRefs; j--) if (seen[j].w == w && seen[j].h == h && seen[j].hs == hs && seen[j].vs == vs) { ref_p[ref_n] = seen[j].p; ref_stride[ref_n] = seen[j].stride; ref_n++; }
+    if (num_seen < 8) { seen[num_seen].p = p; seen[num_seen].stride = stride; seen[num_seen].w = w; seen[num_seen].h = h; seen[num_seen].hs = hs; seen[num_seen].vs = vs; num_seen++; }
+  }
+  __device__ __forceinline__ int32_t RefProp(int p, int x, int y) const {
+    const int k = (p - 16) >> 2, which = (p - 16) & 3; if (k >= ref_n) return 0;   // fewer matching channels than the tree asks for: the property reads 0
+    const int32_t* rp = ref_p[k] + size_t(y) * ref_stride[k]; const long long v = rp[x];
+    const long long rW = x ? rp[x - 1] : 0, rN = y ? rp[x - ptrdiff_t(ref_stride[k])] : rW, rNW = (x && y) ? rp[x - 1 - ptrdiff_t(ref_stride[k])] : rW;
+    const long long lo = min(rW, rN), hi = max(rW, rN), g = max(lo, min(hi, rW + rN - rNW)), d = v - g;
+    return int32_t(which == 0 ? (v < 0 ? -v : v) : which == 1 ? v : which == 2 ? (d < 0 ? -d : d) : d);
+  }   // lut: per-decoding-thread scratch (shared memory)
 
   // In-order walk of the subtree under `root` (<= branch first): ascending thresholds, leaves per interval.
   __device__ void BuildLut(int root) {
@@ -154,7 +171,7 @@ struct ModDecoder {
           tok = rd.ReadCluster(cv, cl); pred = kMode == 2 ? M::Gradient(N, W, NW) : M::Prediction(fpred, N, W, NW, NE, NN, WW, NEE, wpred);
         } else {
           DTreeNode nd = n;
-          while (nd.x >= 0) { int32_t v = int32_t(M::PropValue(nd.x, chan, stream_id, x, y, N, W, NW, NE, NN, WW, prev_grad, wo.max_err, &rd.err)); nd = tree[v > nd.y ? nd.z : nd.w]; }
+          while (nd.x >= 0) { int32_t v = nd.x >= 16 ? this->RefProp(nd.x, x, y) : int32_t(M::PropValue(nd.x, chan, stream_id, x, y, N, W, NW, NE, NN, WW, prev_grad, wo.max_err, &rd.err)); nd = tree[v > nd.y ? nd.z : nd.w]; }
           tok = cv.lz77 ? rd.ReadLz(cv, uint32_t(nd.y) >> 4, this->dist_mult) : rd.Read(cv, uint32_t(nd.y) >> 4); pred = M::Prediction(nd.y & 15, N, W, NW, NE, NN, WW, NEE, wpred); offset = nd.z; mult = uint32_t(nd.w);
         }
         const int32_t val = kMode != 0 ? int32_t(T(UnpackSignedDev(tok)) + pred) : int32_t((long long)UnpackSignedDev(tok) * (long long)mult + offset + (long long)pred);

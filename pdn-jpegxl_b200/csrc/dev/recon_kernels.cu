@@ -434,9 +434,11 @@ __device__ __forceinline__ float TfFromLinearDev(float v, uint32_t tf, float gam
     case 8: r = a; break;
     case 13: r = a <= 0.0031308f ? 12.92f * a : 1.055f * PowSfu(a, 1.0f / 2.4f) - 0.055f; break;
     case 1: r = a < 0.018f ? 4.5f * a : 1.099f * PowSfu(a, 0.45f) - 0.099f; break;
-    case 16: { const float m1 = 2610.0f / 16384, m2 = 2523.0f / 4096 * 128, c1 = 3424.0f / 4096, c2 = 2413.0f / 4096 * 32, c3 = 2392.0f / 4096 * 32;
-      float yv = fminf(1.0f, a * intensity_target / 10000.0f); float p = powf(yv, m1); r = powf((c1 + c2 * p) / (1.0f + c3 * p), m2); break; }
+    // PQ in double: the outer exponent (78.84) multiplies every fp32 rounding of the ratio by ~80, which alone is 1e-5..1e-4 relative on the code value
+    case 16: { const double m1 = 2610.0 / 16384, m2 = 2523.0 / 4096 * 128, c1 = 3424.0 / 4096, c2 = 2413.0 / 4096 * 32, c3 = 2392.0 / 4096 * 32;
+      const double yv = fmin(1.0, double(a) * double(intensity_target) / 10000.0); const double p = pow(yv, m1); r = float(pow((c1 + c2 * p) / (1.0 + c3 * p), m2)); break; }
     case 17: r = PowSfu(a, 1.0f / 2.6f); break;
+    case 18: r = a <= 1.0f / 12 ? sqrtf(3.0f * a) : 0.17883277f * logf(12.0f * a - 0.28466892f) + 0.55991073f; break;   // HLG OETF (ARIB STD-B67), no OOTF: the file's own encoding
     default: r = a; break;
   }
   return v < 0 ? -r : r;

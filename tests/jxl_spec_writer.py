@@ -597,9 +597,23 @@ def modular_items(root, channels, stream_id=0):
                     props[8] = W - (Wl + Nl - NWl)
                 else:
                     props[8] = W
+                # properties 16 + 4k .. 19 + 4k: the k-th previous channel of the same size (nearest first): |v|, v, |v - g|, v - g with g the
+                # clamped gradient of that channel at the same position (H.4.1)
+                k = 0
+                for cj in range(ci - 1, -1, -1):
+                    r = channels[cj]
+                    if len(r) != h or len(r[0]) != w:
+                        continue
+                    v = r[y][x]
+                    rW = r[y][x - 1] if x else 0
+                    rN = r[y - 1][x] if y else rW
+                    rNW = r[y - 1][x - 1] if x and y else rW
+                    g = max(min(rW, rN), min(max(rW, rN), rW + rN - rNW))
+                    props[16 + 4 * k], props[17 + 4 * k], props[18 + 4 * k], props[19 + 4 * k] = abs(v), v, abs(v - g), v - g
+                    k += 1
                 n = root
                 while isinstance(n, Split):
-                    n = n.gt if props[n.prop] > n.value else n.le
+                    n = n.gt if props.get(n.prop, 0) > n.value else n.le
                 r = ch[y][x] - predict(n.predictor, W, N, NW, NE, NN, WW, NEE) - n.offset
                 assert r % n.multiplier == 0, "sample not representable with this leaf's multiplier"
                 items.append((n.ctx, pack_signed(r // n.multiplier)))

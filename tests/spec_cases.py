@@ -98,6 +98,22 @@ def cases():
         code = W.EntropyCode([0, 1], [("flat", 256), ("flat", 32)], hybrids=[W.Hybrid(4, 2, 0), W.Hybrid(4, 1, 0)], log_alpha=8,
                              lz77=dict(min_symbol=224, min_length=3, len_hybrid=W.Hybrid(2, 0, 0)))
         out.append((nm, W.modular_image(_planes(a), data_code=code, rle=(3, 1), group_size_shift=shift), a.astype(np.uint8), dict(width=ww, height=hh, format="Rgb", num_channels=3)))
+    # 11. MA-tree properties of previous channels: channel 1 splits on the value of channel 0 (property 17), channel 2 on channel 1's
+    #     gradient residual (property 19) and on channel 0's absolute value (property 20 = second previous channel); no RCT, 2 groups
+    a = _img(140, 130, 3, seed=12)
+    a[..., 1] = (a[..., 0] * 3 // 4 + a[..., 1] // 8) % 256
+    tree = W.Split(0, 0, W.Split(0, 1, W.Split(19, 2, W.Leaf(2, 5), W.Split(20, 90, W.Leaf(5, 4), W.Leaf(6, 1))), W.Split(17, 100, W.Leaf(3, 5), W.Leaf(4, 2))), W.Leaf(0, 5))
+    # breadth-first leaf order: root; [gt Split(ch>1?), le Leaf0]; then [Split(19), Split(17)]; then [Leaf2?...]: renumber by construction below
+    def renumber(root):
+        k = 0
+        for n in W.tree_nodes_bfs(root):
+            if isinstance(n, W.Leaf):
+                n.ctx = k
+                k += 1
+        return k
+    nl = renumber(tree)
+    code = W.EntropyCode(list(range(nl)), [("flat", 64)] * nl, hybrids=[W.Hybrid(4, 2, 0)] * nl, log_alpha=6) if nl <= 8 else None
+    out.append(("rgb8_prev_channel_props", W.modular_image(_planes(a), tree=tree, data_code=code, group_size_shift=0), a.astype(np.uint8), dict(width=130, height=140, format="Rgb", num_channels=3)))
     return out
 
 

@@ -144,3 +144,37 @@ def test_save_image_with_padded_stride_matches_the_reference_repack(gpu, oracle,
     d = oracle.decode(data)
     assert d.pixels.shape == want.shape and np.array_equal(d.pixels, want), kind
     assert np.array_equal(_decode_gpu(gpu, data).layer_data.interleaved, want)
+
+
+@pytest.mark.parametrize("colors,alpha", [(1, False), (1, True), (3, False), (3, True)])
+@pytest.mark.parametrize("kw,dtype", [(dict(lossless=1), np.uint8), (dict(lossless=1, bits=16), np.uint16), (dict(effort=3, bits=16, exp_bits=5), np.float16), (dict(lossless=1, bits=16, exp_bits=5), np.float16),
+                                      (dict(lossless=1, bits=32, exp_bits=8), np.float32), (dict(effort=5, bits=32, exp_bits=8), np.float32)])
+def test_layer_bitmaps_on_the_gpu_match_the_managed_repack(gpu, oracle, colors, alpha, kw, dtype):
+    """JxlB200LoadImageLayers == LoadImage + DecoderLayerData's Set{Gray,GrayAlpha,Rgb,Rgba}{UInt8,UInt16,Float16,Float32}ImageData
+    (I/DecoderLayerData.cs:245-992): gray replicated into RGB, alpha through TransparencyMapping.ToEightBit — bit for bit."""
+    img = oracle.synthetic_image(150, 90, seed=3 + colors, channels=4)
+    src = np.concatenate([img[..., :colors]] + ([img[..., 3:4]] if alpha else []), axis=2)
+    src = src if dtype == np.uint8 else src.astype(np.float32) / 255.0
+    data = oracle.encode(src, num_color=colors, has_alpha=alpha, **kw)
+    image = _decode_gpu(gpu, data)
+    layer = image.layer_data
+    color, transparency = gpu.load_image_layers(data)
+    assert color.dtype == dtype and color.shape == (90, 150, 3)
+    assert np.array_equal(color.view(np.uint8), layer.color.view(np.uint8))
+    if alpha:
+        assert transparency.dtype == np.uint8 and np.array_equal(transparency, layer.transparency)
+        assert len(np.unique(transparency)) > 50
+    else:
+        assert transparency is None
+
+
+@pytest.mark.parametrize("alpha", [False, True])
+def test_cmyk_layer_bitmaps_on_the_gpu(gpu, oracle, alpha):
+    """SetCmykUInt8ImageData / SetCmykAlphaUInt8ImageData (I/DecoderLayerData.cs:164-243) after the native K merge."""
+    img = oracle.synthetic_image(120, 80, seed=15, channels=4)
+    src = np.concatenate([img, img[..., :1][:, ::-1]], axis=2) if alpha else img
+    data = oracle.encode(src, num_color=3, has_alpha=alpha, lossless=1, black_channel=1)
+    layer = _decode_gpu(gpu, data).layer_data
+    color, transparency = gpu.load_image_layers(data)
+    assert color.shape == (80, 120, 4) and np.array_equal(color, layer.color)
+    assert (transparency is None) == (not alpha) and (not alpha or np.array_equal(transparency, layer.transparency))
