@@ -145,6 +145,29 @@ JXLFT_API EncoderStatus JXLFT_CALL JxlB200EncodeToMemory(const BitmapData* bitma
                                                           int32_t deviceInput, uint8_t** out, size_t* outSize, ErrorInfo* errorInfo);
 JXLFT_API void JXLFT_CALL JxlB200Free(void* p);
 
+/* Sharded encode (BASELINE config 5, SURVEY §8e "Encode sharding"; the reference hands the whole frame to libjxl in one process,
+ * N/Encoder/JxlEncoder.cpp:128,367). A frame is cut into bands of whole LF-group rows (2048 pixel rows; the last band takes the rest);
+ * each band is encoded by its own session, normally one per GPU / process:
+ *   Create    band = the band's rows of the frame (width = frame width, height = rows of the band, scan0 = first row HANDED OVER, which is
+ *             haloTop rows before the band's first row; haloTop = min(8, firstRow), haloBottom = min(8, rows of the frame below the band):
+ *             the neighbouring bands' pixels the inverse-gaborish stencil reaches). Uploads and scans -> *bandFlags.
+ *   Tokenize  frameFlags = OR of all bands' flags (the GetOutputPixelFormat decision of N/Encoder/JxlEncoder.cpp:33-77 is per frame)
+ *             -> this band's token histograms (malloc'ed, histWords 64-bit counters; free with JxlB200Free).
+ *   Finish    frameHist = element-wise SUM of all bands' histograms -> this band's sections as one opaque blob (free with JxlB200Free).
+ * JxlB200AssembleBands then builds the file from the blobs of all bands (any order) on one rank. Two reductions (4 bytes, a few MB) are
+ * the only exchange between ranks; the file is bit-identical to SaveImage's for the same frame. Returns NULL / an EncoderStatus. */
+typedef struct JxlB200BandEncoder JxlB200BandEncoder;
+JXLFT_API JxlB200BandEncoder* JXLFT_CALL JxlB200BandEncoderCreate(int32_t device, const BitmapData* band, uint32_t frameHeight, uint32_t firstRow, uint32_t haloTop,
+                                                                   uint32_t haloBottom, const EncoderOptions* options, const EncoderImageMetadata* metadata,
+                                                                   int32_t deviceInput, uint32_t* bandFlags, ErrorInfo* errorInfo);
+JXLFT_API EncoderStatus JXLFT_CALL JxlB200BandEncoderTokenize(JxlB200BandEncoder* enc, uint32_t frameFlags, uint64_t** hist, size_t* histWords, ErrorInfo* errorInfo);
+JXLFT_API EncoderStatus JXLFT_CALL JxlB200BandEncoderFinish(JxlB200BandEncoder* enc, const uint64_t* frameHist, size_t histWords, uint8_t** sections,
+                                                             size_t* sectionBytes, float* deviceMs, ErrorInfo* errorInfo);
+JXLFT_API void JXLFT_CALL JxlB200BandEncoderDestroy(JxlB200BandEncoder* enc);
+JXLFT_API EncoderStatus JXLFT_CALL JxlB200AssembleBands(uint32_t width, uint32_t height, const EncoderOptions* options, const EncoderImageMetadata* metadata,
+                                                         uint32_t frameFlags, const uint64_t* frameHist, size_t histWords, const uint8_t* const* bandSections,
+                                                         const size_t* bandSectionBytes, int32_t bandCount, uint8_t** out, size_t* outSize, ErrorInfo* errorInfo);
+
 /* Instrumentation for bench.py / tests: per-stage device times (ms) of the last single-image decode on this thread
  * (h2d, lf, ac, recon, filters, output, d2h, total), number of kernels launched by this process, and raw stage dumps of
  * one decode for parity tests (which: 0 = planes in the XYB buffer, 1 = planes in the ping-pong buffer, 3 = LF planes;

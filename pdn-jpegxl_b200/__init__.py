@@ -77,7 +77,8 @@ class IOCallbacks(C.Structure):
 
 EXPORTS = ["GetLibJxlVersion", "LoadImage", "SaveImage", "JxlB200LoadImageBgra", "JxlB200PeekInfo", "JxlB200DecodeBatch", "JxlB200EncodeToMemory",
            "JxlB200Free", "JxlB200LastStageTimes", "JxlB200KernelLaunchCount", "JxlB200DebugDecodeStage", "JxlB200CudaAvailable", "JxlB200BandLayout",
-           "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc", "JxlB200DecodeBatchSubmit", "JxlB200DecodeBatchWait", "JxlB200LoadImageLayers"]
+           "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc", "JxlB200DecodeBatchSubmit", "JxlB200DecodeBatchWait", "JxlB200LoadImageLayers",
+           "JxlB200BandEncoderCreate", "JxlB200BandEncoderTokenize", "JxlB200BandEncoderFinish", "JxlB200BandEncoderDestroy", "JxlB200AssembleBands"]
 
 _lib.GetLibJxlVersion.restype = C.c_uint32
 _lib.LoadImage.argtypes = [C.POINTER(DecoderCallbacks), C.c_void_p, C.c_size_t, C.POINTER(ErrorInfo)]
@@ -471,6 +472,20 @@ def load_image_layers(data):
     return color, alpha
 
 
+def _native_metadata(metadata):
+    """EncoderImageMetadata (N/Encoder/JxlEncoderTypes.h:35-42) from the Python-side metadata; returns it with the buffers to keep alive."""
+    meta = EncoderImageMetadataNative()
+    keep = []
+    if metadata is not None:
+        for field, size, b in (("exif", "exifSize", metadata.exif), ("iccProfile", "iccProfileSize", metadata.icc), ("xmp", "xmpSize", metadata.xmp)):
+            if b:
+                arr = (C.c_uint8 * len(b)).from_buffer_copy(b)
+                keep.append(arr)
+                setattr(meta, field, C.cast(arr, C.c_void_p))
+                setattr(meta, size, len(b))
+    return meta, keep
+
+
 def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, width=None, height=None, stride=None, host_array=None):
     """host_array: a 2-D uint8 array of `height` rows of `stride` bytes (BitmapData with stride > 4*width, N/Common.h:17-23)."""
     if host_array is not None:
@@ -483,15 +498,7 @@ def encode_to_memory(surface_bgra, options, metadata=None, device_ptr=None, widt
     else:
         bitmap = BitmapData(device_ptr, width, height, stride)
     opts = EncoderOptionsNative(options.distance, options.effort, options.lossless)
-    meta = EncoderImageMetadataNative()
-    keep = []
-    if metadata is not None:
-        for field, size, b in (("exif", "exifSize", metadata.exif), ("iccProfile", "iccProfileSize", metadata.icc), ("xmp", "xmpSize", metadata.xmp)):
-            if b:
-                arr = (C.c_uint8 * len(b)).from_buffer_copy(b)
-                keep.append(arr)
-                setattr(meta, field, C.cast(arr, C.c_void_p))
-                setattr(meta, size, len(b))
+    meta, keep = _native_metadata(metadata)
     out = C.c_void_p()
     n = C.c_size_t()
     ei = ErrorInfo()
@@ -558,6 +565,157 @@ def decode_band(data, group_row_begin, group_row_end, bgra=False, device=-1):
     if st != 0:
         raise FormatException(DECODER_STATUS[st], _message(ei) or DECODER_STATUS[st])
     return out[: rows.value]
+
+
+# ---- sharded encode (SURVEY §8e "Encode sharding"): bands of whole LF-group rows, one session per band / GPU
+ENC_BAND_ROWS = 2048   # one LF-group row: 8 groups of 256 px
+
+
+def encode_band_partition(height, world):
+    """Contiguous bands of whole LF-group rows per rank: [(first_row, row_count)]; ranks beyond the LF-group rows get (0, 0)."""
+    lf_rows = -(-height // ENC_BAND_ROWS)
+    out = []
+    for begin, end in band_partition(lf_rows, world):
+        y0, y1 = begin * ENC_BAND_ROWS, min(end * ENC_BAND_ROWS, height)
+        out.append((y0, y1 - y0) if end > begin else (0, 0))
+    return out
+
+
+def band_rows_with_halo(height, first_row, rows):
+    """(first row to hand over, halo_top, halo_bottom) for a band: 8 rows of each neighbour (fewer at the end of the frame)."""
+    halo_top = min(8, first_row)
+    halo_bottom = min(8, height - (first_row + rows))
+    return first_row - halo_top, halo_top, halo_bottom
+
+
+_lib.JxlB200BandEncoderCreate.argtypes = [C.c_int32, C.POINTER(BitmapData), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(EncoderOptionsNative),
+                                          C.POINTER(EncoderImageMetadataNative), C.c_int32, C.POINTER(C.c_uint32), C.POINTER(ErrorInfo)]
+_lib.JxlB200BandEncoderCreate.restype = C.c_void_p
+_lib.JxlB200BandEncoderTokenize.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ErrorInfo)]
+_lib.JxlB200BandEncoderTokenize.restype = C.c_int32
+_lib.JxlB200BandEncoderFinish.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_float), C.POINTER(ErrorInfo)]
+_lib.JxlB200BandEncoderFinish.restype = C.c_int32
+_lib.JxlB200BandEncoderDestroy.argtypes = [C.c_void_p]
+_lib.JxlB200BandEncoderDestroy.restype = None
+_lib.JxlB200AssembleBands.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(EncoderOptionsNative), C.POINTER(EncoderImageMetadataNative), C.c_uint32, C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ErrorInfo)]
+_lib.JxlB200AssembleBands.restype = C.c_int32
+
+
+def _enc_check(st, ei):
+    if st != 0:
+        raise FormatException(ENCODER_STATUS[st], _message(ei) or ENCODER_STATUS[st])
+
+
+class BandEncoder:
+    """One band of a frame on one GPU (JxlB200BandEncoder*). `rows_bgra`: the rows handed over, halo rows included (H x W x 4 uint8)."""
+
+    def __init__(self, rows_bgra, frame_height, first_row, halo_top, halo_bottom, options, device=-1):
+        self._rows = np.ascontiguousarray(rows_bgra, dtype=np.uint8)
+        h, w, _ = self._rows.shape
+        bitmap = BitmapData(self._rows.ctypes.data, w, h - halo_top - halo_bottom, self._rows.strides[0])
+        self._opts = EncoderOptionsNative(options.distance, options.effort, options.lossless)
+        flags, ei = C.c_uint32(), ErrorInfo()
+        self._h = _lib.JxlB200BandEncoderCreate(device, C.byref(bitmap), frame_height, first_row, halo_top, halo_bottom, C.byref(self._opts), None, 0, C.byref(flags), C.byref(ei))
+        if not self._h:
+            raise FormatException("EncodeError", _message(ei) or "band encoder")
+        self.flags = int(flags.value)
+        self.device_ms = 0.0
+
+    def tokenize(self, frame_flags):
+        p, n, ei = C.c_void_p(), C.c_size_t(), ErrorInfo()
+        _enc_check(_lib.JxlB200BandEncoderTokenize(self._h, frame_flags, C.byref(p), C.byref(n), C.byref(ei)), ei)
+        hist = np.frombuffer(C.string_at(p, n.value * 8), dtype=np.uint64).copy()
+        _lib.JxlB200Free(p)
+        return hist
+
+    def finish(self, frame_hist):
+        hist = np.ascontiguousarray(frame_hist, dtype=np.uint64)
+        p, n, ms, ei = C.c_void_p(), C.c_size_t(), C.c_float(), ErrorInfo()
+        _enc_check(_lib.JxlB200BandEncoderFinish(self._h, hist.ctypes.data, hist.size, C.byref(p), C.byref(n), C.byref(ms), C.byref(ei)), ei)
+        blob = C.string_at(p, n.value)
+        _lib.JxlB200Free(p)
+        self.device_ms = float(ms.value)
+        return blob
+
+    def close(self):
+        if self._h:
+            _lib.JxlB200BandEncoderDestroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def assemble_bands(width, height, options, frame_flags, frame_hist, blobs, metadata=None):
+    opts = EncoderOptionsNative(options.distance, options.effort, options.lossless)
+    hist = np.ascontiguousarray(frame_hist, dtype=np.uint64)
+    keep = [bytes(b) for b in blobs]
+    ptrs = (C.c_void_p * len(keep))(*[C.cast(C.c_char_p(b), C.c_void_p) for b in keep])
+    sizes = (C.c_size_t * len(keep))(*[len(b) for b in keep])
+    meta, hold = _native_metadata(metadata)
+    out, n, ei = C.c_void_p(), C.c_size_t(), ErrorInfo()
+    _enc_check(_lib.JxlB200AssembleBands(width, height, C.byref(opts), C.byref(meta), frame_flags, hist.ctypes.data, hist.size, ptrs, sizes, len(keep),
+                                         C.byref(out), C.byref(n), C.byref(ei)), ei)
+    data = C.string_at(out, n.value)
+    _lib.JxlB200Free(out)
+    del hold
+    return data
+
+
+def encode_in_bands(surface_bgra, options, num_bands, devices=None, metadata=None):
+    """The sharded encoder driven from ONE process (tests; a single host that owns several GPUs): band i runs on devices[i % len]."""
+    surf = np.ascontiguousarray(surface_bgra, dtype=np.uint8)
+    h, w, _ = surf.shape
+    encs = []
+    for i, (y0, rows) in enumerate(encode_band_partition(h, num_bands)):
+        if rows == 0:
+            continue
+        first, ht, hb = band_rows_with_halo(h, y0, rows)
+        dev = -1 if not devices else devices[i % len(devices)]
+        encs.append(BandEncoder(surf[first:y0 + rows + hb], h, y0, ht, hb, options, device=dev))
+    flags = 0
+    for e in encs:
+        flags |= e.flags
+    hists = [e.tokenize(flags) for e in encs]
+    total = np.sum(np.stack(hists), axis=0, dtype=np.uint64)
+    blobs = [e.finish(total) for e in encs]
+    for e in encs:
+        e.close()
+    return assemble_bands(w, h, options, flags, total, blobs, metadata)
+
+
+def encode_band_distributed(rows_bgra, width, height, first_row, rows, options, dist, device=-1, metadata=None, dst=0):
+    """One rank's part of a sharded encode under torch.distributed (one process per GPU): this rank's band (rows handed over with their
+    halo), two reductions (flags: MAX of bit fields via OR-able ints; histograms: SUM), a gather of the section blobs to `dst`, which
+    returns the file (other ranks return None). Ranks with no rows (rows == 0) only take part in the reductions."""
+    import torch
+    enc = None
+    if rows:
+        _, ht, hb = band_rows_with_halo(height, first_row, rows)
+        enc = BandEncoder(rows_bgra, height, first_row, ht, hb, options, device=device)
+    bits = torch.tensor([(enc.flags >> 0) & 1, (enc.flags >> 1) & 1] if enc else [0, 0], dtype=torch.int64)
+    dist.all_reduce(bits, op=dist.ReduceOp.MAX)
+    flags = int(bits[0].item()) | (int(bits[1].item()) << 1)
+    words = torch.tensor([0], dtype=torch.int64)
+    hist = enc.tokenize(flags) if enc else None
+    if hist is not None:
+        words[0] = hist.size
+    dist.all_reduce(words, op=dist.ReduceOp.MAX)
+    t = torch.zeros(int(words.item()), dtype=torch.int64)
+    if hist is not None:
+        t += torch.from_numpy(hist.astype(np.int64))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    total = t.numpy().astype(np.uint64)
+    blob = enc.finish(total) if enc else b""
+    ms = enc.device_ms if enc else 0.0
+    if enc:
+        enc.close()
+    gathered = [None] * dist.get_world_size() if dist.get_rank() == dst else None
+    dist.gather_object(blob, gathered, dst=dst)
+    if dist.get_rank() != dst:
+        return None, ms
+    return assemble_bands(width, height, options, flags, total, [b for b in gathered if b], metadata), ms
 
 
 class BatchHandle:

@@ -433,6 +433,57 @@ int32_t JxlB200DebugParseIcc(const uint8_t* icc, size_t iccSize, float* matrix9,
 }
 // Returns the cached device and page-locked buffers of the calling thread's current device to the driver (after a large batch the
 // pools hold one buffer set per image that was in flight).
+// ---- sharded encode (BASELINE config 5, SURVEY §8e "Encode sharding"): one band session per GPU, see encode_engine.cu
+struct JxlB200BandEncoder { BandSession* s = nullptr; int device = -1; };
+static void* CopyOut(const void* p, size_t n) { void* m = malloc(n ? n : 1); if (!m) throw std::bad_alloc(); if (n) memcpy(m, p, n); return m; }
+static EncodeRequest BandRequest(const BitmapData* b, const EncoderOptions* o, const EncoderImageMetadata* md) {
+  EncodeRequest req; req.bgra = b->scan0; req.width = b->width; req.height = b->height; req.stride = b->stride; req.distance = o->distance; req.effort = o->effort; req.lossless = o->lossless;
+  if (md) { req.exif = md->exif; req.exif_size = md->exifSize; req.icc = md->iccProfile; req.icc_size = md->iccProfileSize; req.xmp = md->xmp; req.xmp_size = md->xmpSize; }
+  return req;
+}
+JxlB200BandEncoder* JxlB200BandEncoderCreate(int32_t device, const BitmapData* band, uint32_t frameHeight, uint32_t firstRow, uint32_t haloTop, uint32_t haloBottom,
+                                             const EncoderOptions* options, const EncoderImageMetadata* metadata, int32_t deviceInput, uint32_t* bandFlags, ErrorInfo* errorInfo) {
+  if (!band || !band->scan0 || !options || !bandFlags) { SetErrorMessage(errorInfo, "null parameter"); return nullptr; }
+  try {
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { SetErrorMessage(errorInfo, "cudaSetDevice failed"); return nullptr; }
+    EncodeRequest req = BandRequest(band, options, metadata); req.device_input = deviceInput != 0;
+    req.frame_height = frameHeight; req.band_y0 = firstRow; req.halo_top = haloTop; req.halo_bottom = haloBottom;
+    EncStatus st = EncStatus::Ok; std::string msg; BandSession* s = BandEncoderCreate(req, bandFlags, &st, &msg);
+    if (!s) { SetErrorMessage(errorInfo, msg.empty() ? "band encoder: out of memory" : msg); return nullptr; }
+    JxlB200BandEncoder* h = new JxlB200BandEncoder; h->s = s; h->device = device; return h;
+  } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); } catch (...) {}
+  return nullptr;
+}
+EncoderStatus JxlB200BandEncoderTokenize(JxlB200BandEncoder* enc, uint32_t frameFlags, uint64_t** hist, size_t* histWords, ErrorInfo* errorInfo) {
+  if (!enc || !hist || !histWords) return EncoderStatus_NullParameter;
+  try {
+    if (enc->device >= 0) cudaSetDevice(enc->device);
+    std::vector<uint64_t> h; std::string msg; EncStatus st = BandEncoderTokenize(enc->s, frameFlags, &h, &msg);
+    if (st != EncStatus::Ok) { SetErrorMessage(errorInfo, msg); return EncoderStatus(st); }
+    *hist = static_cast<uint64_t*>(CopyOut(h.data(), h.size() * 8)); *histWords = h.size(); return EncoderStatus_Ok;
+  } catch (const std::bad_alloc&) { return EncoderStatus_OutOfMemory; } catch (...) { return EncoderStatus_EncodeError; }
+}
+EncoderStatus JxlB200BandEncoderFinish(JxlB200BandEncoder* enc, const uint64_t* frameHist, size_t histWords, uint8_t** sections, size_t* sectionBytes, float* deviceMs, ErrorInfo* errorInfo) {
+  if (!enc || !frameHist || !sections || !sectionBytes) return EncoderStatus_NullParameter;
+  try {
+    if (enc->device >= 0) cudaSetDevice(enc->device);
+    std::vector<uint8_t> blob; std::string msg; EncStatus st = BandEncoderFinish(enc->s, frameHist, histWords, &blob, deviceMs, &msg);
+    if (st != EncStatus::Ok) { SetErrorMessage(errorInfo, msg); return EncoderStatus(st); }
+    *sections = static_cast<uint8_t*>(CopyOut(blob.data(), blob.size())); *sectionBytes = blob.size(); return EncoderStatus_Ok;
+  } catch (const std::bad_alloc&) { return EncoderStatus_OutOfMemory; } catch (...) { return EncoderStatus_EncodeError; }
+}
+void JxlB200BandEncoderDestroy(JxlB200BandEncoder* enc) { if (!enc) return; try { if (enc->device >= 0) cudaSetDevice(enc->device); BandEncoderDestroy(enc->s); } catch (...) {} delete enc; }
+EncoderStatus JxlB200AssembleBands(uint32_t width, uint32_t height, const EncoderOptions* options, const EncoderImageMetadata* metadata, uint32_t frameFlags, const uint64_t* frameHist, size_t histWords,
+                                   const uint8_t* const* bandSections, const size_t* bandSectionBytes, int32_t bandCount, uint8_t** out, size_t* outSize, ErrorInfo* errorInfo) {
+  if (!options || !frameHist || !bandSections || !bandSectionBytes || !out || !outSize || bandCount <= 0) return EncoderStatus_NullParameter;
+  try {
+    BitmapData whole{nullptr, width, height, width * 4}; EncodeRequest req = BandRequest(&whole, options, metadata);
+    std::vector<uint8_t> file; std::string msg; EncStatus st = AssembleBands(req, frameFlags, frameHist, histWords, bandSections, bandSectionBytes, size_t(bandCount), &file, &msg);
+    if (st != EncStatus::Ok) { SetErrorMessage(errorInfo, msg); return EncoderStatus(st); }
+    *out = static_cast<uint8_t*>(CopyOut(file.data(), file.size())); *outSize = file.size(); return EncoderStatus_Ok;
+  } catch (const std::bad_alloc&) { return EncoderStatus_OutOfMemory; } catch (...) { return EncoderStatus_EncodeError; }
+}
+
 void JxlB200ReleaseMemory(void) { try { cudaDeviceSynchronize(); TrimPools(); for (auto& w : g_pools_warm) w.store(0); } catch (...) {} }
 
 void JxlB200LastStageTimes(float* ms8) { if (!ms8) return; const StageTimes& t = g_last_times; ms8[0] = t.h2d; ms8[1] = t.lf; ms8[2] = t.ac; ms8[3] = t.recon; ms8[4] = t.filters; ms8[5] = t.output; ms8[6] = t.d2h; ms8[7] = t.total; }

@@ -10,6 +10,10 @@ static const uint32_t kMaxAcTokensPerGroup = 3 * 1024 * 64;  // 3 channels x 102
 struct DEncFrame {
   uint32_t xsize, ysize, stride, xpad, ypad, xb, yb, xgroups, ygroups, num_groups, gray, alpha, alpha_plane, hf_mul;
   float inv_gs, xm, bm, kx, kb, lf_fac[3], cfl_x_lf, cfl_b_lf, quant_bias[4];
+  // XYB planes cover `ext_rows` rows: `ext_top` halo rows, the ypad rows of the frame (or of this band of it), halo rows below. A whole frame has no
+  // halo (ext_top = 0, ext_rows = ypad). Source rows are clamped to [src_row_min, src_row_max] (relative to the first row of the band): the rows
+  // the caller handed over, so that a band's halo holds the neighbouring band's pixels and the bottom padding repeats the frame's last row.
+  uint32_t ext_top, ext_rows; int32_t src_row_min, src_row_max;
   float* xyb; int32_t* planes; float* lf; int32_t* lfq; int16_t* coeffs; uint8_t* nz; const float* dequant8; const uint16_t* order8; const DTables* tables;
   const float* src_lut; float src_matrix[9]; uint32_t has_src_profile, pad0;   // ICC-described source: per-channel tone LUT [3][256] + matrix to linear sRGB (null / 0: sRGB input)
   uint2* tokens; uint64_t ac_token_off; uint32_t* ac_token_count; uint8_t* stream_bytes; uint64_t* stream_bits;

@@ -24,8 +24,10 @@ __global__ void k_enc_scan(const uint8_t* __restrict__ bgra, uint32_t w, uint32_
 }
 
 __global__ void k_enc_to_xyb(const DEncFrame* ep, const uint8_t* __restrict__ bgra) {
-  const DEncFrame& e = *ep; int xx = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y * blockDim.y + threadIdx.y; if (xx >= int(e.xpad) || yy >= int(e.ypad)) return;
-  int x = min(xx, int(e.xsize) - 1), y = min(yy, int(e.ysize) - 1); uchar4 p = *reinterpret_cast<const uchar4*>(bgra + size_t(y) * e.stride + size_t(x) * 4);
+  // yy counts rows of the extended plane (halo rows first); `bgra` points at the first row of the band itself, halo rows lie before it
+  const DEncFrame& e = *ep; int xx = blockIdx.x * blockDim.x + threadIdx.x, ye = blockIdx.y * blockDim.y + threadIdx.y; if (xx >= int(e.xpad) || ye >= int(e.ext_rows)) return;
+  const int yy = ye - int(e.ext_top);
+  int x = min(xx, int(e.xsize) - 1), y = max(e.src_row_min, min(yy, e.src_row_max)); uchar4 p = *reinterpret_cast<const uchar4*>(bgra + ptrdiff_t(y) * ptrdiff_t(e.stride) + size_t(x) * 4);
   float r, g, b;
   if (e.has_src_profile) {   // matrix/TRC ICC source: tone curves from the profile, then its colorants -> linear sRGB (what libjxl's CMS step does)
     const float lr = e.src_lut[p.z], lg = e.src_lut[256 + p.y], lb = e.src_lut[512 + p.x]; const float* m = e.src_matrix;
@@ -34,8 +36,8 @@ __global__ void k_enc_to_xyb(const DEncFrame* ep, const uint8_t* __restrict__ bg
   const float bias = 0.0037930732552754493f, cb = cbrtf(bias);
   float m0 = 0.30f * r + 0.622f * g + 0.078f * b + bias, m1 = 0.23f * r + 0.692f * g + 0.078f * b + bias, m2 = 0.24342268924547819f * r + 0.20476744424496821f * g + 0.55180986650955360f * b + bias;
   float g0 = cbrtf(fmaxf(m0, 0.f)) - cb, g1 = cbrtf(fmaxf(m1, 0.f)) - cb, g2 = cbrtf(fmaxf(m2, 0.f)) - cb;
-  size_t plane = size_t(e.xpad) * e.ypad, at = size_t(yy) * e.xpad + xx; e.xyb[at] = 0.5f * (g0 - g1); e.xyb[plane + at] = 0.5f * (g0 + g1); e.xyb[2 * plane + at] = g2;
-  if (e.alpha && xx < int(e.xsize) && yy < int(e.ysize)) e.planes[size_t(e.alpha_plane) * e.xsize * e.ysize + size_t(yy) * e.xsize + xx] = p.w;
+  size_t plane = size_t(e.xpad) * e.ext_rows, at = size_t(ye) * e.xpad + xx; e.xyb[at] = 0.5f * (g0 - g1); e.xyb[plane + at] = 0.5f * (g0 + g1); e.xyb[2 * plane + at] = g2;
+  if (e.alpha && xx < int(e.xsize) && yy >= 0 && yy < int(e.ysize)) e.planes[size_t(e.alpha_plane) * e.xsize * e.ysize + size_t(yy) * e.xsize + xx] = p.w;
 }
 
 __global__ void k_enc_to_planes(const DEncFrame* ep, const uint8_t* __restrict__ bgra) {
@@ -54,11 +56,11 @@ __global__ void k_enc_sharpen(float* __restrict__ cur, const float* __restrict__
 __global__ void __launch_bounds__(64) k_enc_dct8(const DEncFrame* ep) {
   const DEncFrame& e = *ep; int cell = blockIdx.x * blockDim.x + threadIdx.x; if (cell >= int(e.xb * e.yb)) return;
   int cy = cell / int(e.xb), cx = cell % int(e.xb); int g = (cy >> 5) * int(e.xgroups) + (cx >> 5); int by = cy & 31, bx = cx & 31;
-  const float* cos8 = e.tables->cosines + CosOff(3); const float* dq = e.dequant8; size_t plane = size_t(e.xpad) * e.ypad, lfplane = size_t(e.xb) * e.yb;
+  const float* cos8 = e.tables->cosines + CosOff(3); const float* dq = e.dequant8; size_t plane = size_t(e.xpad) * e.ext_rows, lfplane = size_t(e.xb) * e.yb;
   float scale = e.inv_gs / float(e.hf_mul); float ydq[64]; uint32_t nzc[3];
 #pragma unroll 1
   for (int ci = 0; ci < 3; ci++) {
-    const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; const float* px = e.xyb + c * plane + size_t(cy) * 8 * e.xpad + size_t(cx) * 8; float t[64], S[64];
+    const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; const float* px = e.xyb + c * plane + (size_t(e.ext_top) + size_t(cy) * 8) * e.xpad + size_t(cx) * 8; float t[64], S[64];
     // rows: t[y][hf] = (1/8) sum_x px[y][x] cos[hf][x]
     for (int y = 0; y < 8; y++) { float v[8]; for (int x = 0; x < 8; x++) v[x] = px[size_t(y) * e.xpad + x]; for (int k = 0; k < 8; k++) { float a = 0; for (int x = 0; x < 8; x++) a += v[x] * cos8[k * 8 + x]; t[y * 8 + k] = a * 0.125f; } }
     // columns: F[vf][hf]; storage (square block) S[hf][vf]
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(32) k_enc_ans(const DEncFrame* ep, const DEncS
 }
 
 void EncLaunchScan(const uint8_t* bgra, uint32_t w, uint32_t h, uint32_t stride, uint32_t* flags, cudaStream_t st) { dim3 grid((w + 255) / 256, h); k_enc_scan<<<grid, 256, 0, st>>>(bgra, w, h, stride, flags); CountLaunch(); }
-void EncLaunchToXyb(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st) { dim3 blk(32, 8), grid((h.xpad + 31) / 32, (h.ypad + 7) / 8); k_enc_to_xyb<<<grid, blk, 0, st>>>(d, bgra); CountLaunch(); }
+void EncLaunchToXyb(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st) { dim3 blk(32, 8), grid((h.xpad + 31) / 32, (h.ext_rows + 7) / 8); k_enc_to_xyb<<<grid, blk, 0, st>>>(d, bgra); CountLaunch(); }
 void EncLaunchToPlanes(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st) { dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8); k_enc_to_planes<<<grid, blk, 0, st>>>(d, bgra); CountLaunch(); }
 void EncLaunchSharpen(float* cur, const float* orig, const float* blur, size_t n, cudaStream_t st) { k_enc_sharpen<<<unsigned((n + 255) / 256), 256, 0, st>>>(cur, orig, blur, n); CountLaunch(); }
 void EncLaunchDct8(const DEncFrame* d, const DEncFrame& h, cudaStream_t st) { uint32_t cells = h.xb * h.yb; k_enc_dct8<<<(cells + 63) / 64, 64, 0, st>>>(d); k_enc_lf_quant<<<(cells + 255) / 256, 256, 0, st>>>(d); CountLaunch(2); }

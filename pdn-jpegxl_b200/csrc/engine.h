@@ -74,9 +74,20 @@ struct EncodeRequest {
   float distance = 1.0f; int effort = 7; bool lossless = false;
   const uint8_t* exif = nullptr; size_t exif_size = 0; const uint8_t* icc = nullptr; size_t icc_size = 0; const uint8_t* xmp = nullptr; size_t xmp_size = 0;
   bool device_input = false;   // bgra points at device memory (bench)
+  // Band of a larger frame (sharded encode): `height` rows starting at frame row band_y0 of a frame_height-row frame; `bgra` points at
+  // the first of halo_top rows that precede the band's own rows, halo_bottom rows follow them. frame_height == 0: the bitmap is the whole frame.
+  uint32_t frame_height = 0, band_y0 = 0, halo_top = 0, halo_bottom = 0;
 };
 enum class EncStatus : int32_t { Ok = 0, NullParameter, OutOfMemory, UserCanceled, EncodeError, WriteError };
 struct EncodeResult { EncStatus status = EncStatus::Ok; std::string message; std::vector<uint8_t> file; StageTimes times; int pixel_format = 2; /* 0 Gray 1 GrayAlpha 2 Rgb 3 Rgba */ };
 EncodeResult EncodeOnGpu(const EncodeRequest& req);
+// Sharded encode: one session per band (one per GPU), three steps with two small reductions between them, then AssembleBands on one rank.
+struct BandSession;
+BandSession* BandEncoderCreate(const EncodeRequest& band, uint32_t* band_flags, EncStatus* status, std::string* message);
+EncStatus BandEncoderTokenize(BandSession* s, uint32_t frame_flags, std::vector<uint64_t>* band_hist, std::string* message);
+EncStatus BandEncoderFinish(BandSession* s, const uint64_t* frame_hist, size_t words, std::vector<uint8_t>* sections, float* device_ms, std::string* message);
+void BandEncoderDestroy(BandSession* s);
+EncStatus AssembleBands(const EncodeRequest& frame, uint32_t frame_flags, const uint64_t* frame_hist, size_t words, const uint8_t* const* blobs, const size_t* sizes, size_t count,
+                        std::vector<uint8_t>* file, std::string* message);
 
 }  // namespace jxlgpu

@@ -93,3 +93,35 @@ def test_write_error_is_sticky(gpu, oracle):
     img = oracle.synthetic_image(64, 64, seed=3)
     with pytest.raises(IOError):
         gpu.JpegXLSave.Save(_bgra(img), Broken())
+
+
+@pytest.mark.parametrize("ch,kw,bands", [(3, dict(quality=90, effort=3), 3), (3, dict(quality=90, effort=7), 2), (4, dict(quality=75, effort=7), 3),
+                                         (4, dict(lossless=True), 3), (1, dict(quality=90, effort=5), 8)])
+def test_banded_encode_is_bit_identical_to_save_image(gpu, oracle, ch, kw, bands):
+    """Sharded encode: bands of whole LF-group rows, each through its own JxlB200BandEncoder session, flags OR-ed and histograms
+    summed between the steps. The assembled file must be the file SaveImage writes for the whole frame — including with gaborish on
+    (effort >= 5), where a band needs its neighbours' rows for the inverse-gaborish stencil — and must decode."""
+    w, h = 520, 4500                                      # 3 LF-group rows: bands of 2048, 2048 and 404 rows
+    img = oracle.synthetic_image(w, h, seed=31 + ch, channels=ch)
+    surface = _bgra(img)
+    opts = gpu.EncoderOptions(**kw)
+    whole = gpu.encode_to_memory(surface, opts)
+    banded = gpu.encode_in_bands(surface, opts, bands)
+    assert banded == whole
+    image = gpu.DecoderImage()
+    gpu.JpegXLNative.LoadImage(banded, image)
+    got = image.layer_data.color[..., :min(ch, 3)]
+    src = img[..., :3] if ch >= 3 else img[..., :1]
+    if kw.get("lossless"):
+        assert np.array_equal(got, src) and np.array_equal(image.layer_data.transparency, img[..., 3])
+    else:
+        assert oracle.psnr(got[..., :src.shape[2]], src) > 26.0
+
+
+def test_band_encoder_rejects_misaligned_bands(gpu, oracle):
+    img = _bgra(oracle.synthetic_image(300, 2500, seed=2))
+    opts = gpu.EncoderOptions(quality=90, effort=3)
+    with pytest.raises(gpu.FormatException, match="multiple of 2048"):
+        gpu.BandEncoder(img[1000:2500], 2500, 1000, 0, 0, opts)           # a band must start on an LF-group row
+    with pytest.raises(gpu.FormatException, match="halo"):
+        gpu.BandEncoder(img[2048:2500], 2500, 2048, 0, 0, opts)           # and bring the 8 rows above it
