@@ -685,34 +685,35 @@ def encode_in_bands(surface_bgra, options, num_bands, devices=None, metadata=Non
     return assemble_bands(w, h, options, flags, total, blobs, metadata)
 
 
-def encode_band_distributed(rows_bgra, width, height, first_row, rows, options, dist, device=-1, metadata=None, dst=0):
+def encode_band_distributed(rows_bgra, width, height, first_row, rows, options, dist, device=-1, metadata=None, dst=0, group=None):
     """One rank's part of a sharded encode under torch.distributed (one process per GPU): this rank's band (rows handed over with their
     halo), two reductions (flags: MAX of bit fields via OR-able ints; histograms: SUM), a gather of the section blobs to `dst`, which
-    returns the file (other ranks return None). Ranks with no rows (rows == 0) only take part in the reductions."""
+    returns the file (other ranks return None). Ranks with no rows (rows == 0) only take part in the reductions. The tensors are host
+    tensors: `group` must be a group with a CPU backend (gloo) when the default group is NCCL-only."""
     import torch
     enc = None
     if rows:
         _, ht, hb = band_rows_with_halo(height, first_row, rows)
         enc = BandEncoder(rows_bgra, height, first_row, ht, hb, options, device=device)
     bits = torch.tensor([(enc.flags >> 0) & 1, (enc.flags >> 1) & 1] if enc else [0, 0], dtype=torch.int64)
-    dist.all_reduce(bits, op=dist.ReduceOp.MAX)
+    dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
     flags = int(bits[0].item()) | (int(bits[1].item()) << 1)
     words = torch.tensor([0], dtype=torch.int64)
     hist = enc.tokenize(flags) if enc else None
     if hist is not None:
         words[0] = hist.size
-    dist.all_reduce(words, op=dist.ReduceOp.MAX)
+    dist.all_reduce(words, op=dist.ReduceOp.MAX, group=group)
     t = torch.zeros(int(words.item()), dtype=torch.int64)
     if hist is not None:
         t += torch.from_numpy(hist.astype(np.int64))
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     total = t.numpy().astype(np.uint64)
     blob = enc.finish(total) if enc else b""
     ms = enc.device_ms if enc else 0.0
     if enc:
         enc.close()
     gathered = [None] * dist.get_world_size() if dist.get_rank() == dst else None
-    dist.gather_object(blob, gathered, dst=dst)
+    dist.gather_object(blob, gathered, dst=dst, group=group)
     if dist.get_rank() != dst:
         return None, ms
     return assemble_bands(width, height, options, flags, total, [b for b in gathered if b], metadata), ms

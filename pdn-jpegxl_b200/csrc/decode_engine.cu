@@ -218,7 +218,7 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 // ---------------------------------------------------------------- the job
 class DecodeJob {
  public:
-  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false;
+  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false; uint64_t mod_total_ints = 0;   /* int32 samples of all Modular planes: coded channels + the outputs of palette expansions */
   DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend, d_lz;
   std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false; size_t coeffs_bytes = 0, xyb_row_shift = 0;
   bool defer_entropy = false, lf_pending = false, ac_pending = false;   // bundle mode: the LF / AC entropy launch is left to DecodeBundleLaunch*
@@ -280,19 +280,53 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
   std::vector<DModChannel> ch;
   if (fh.encoding == 1) { JXLG_CHECK(!m.xyb_encoded, "XYB-encoded Modular frames are not supported"); int nc = m.ce.color_space == kCsGray ? 1 : 3; for (int c = 0; c < nc; c++) ch.push_back(DModChannel{fh.xsize, fh.ysize, 0, 0, 0}); }
   for (size_t i = 0; i < m.ec.size(); i++) { JXLG_CHECK(fh.ec_upsampling[i] == 1, "upsampling is not supported"); uint32_t s = m.ec[i].dim_shift; ch.push_back(DModChannel{DivCeil(fh.xsize, 1u << s), DivCeil(fh.ysize, 1u << s), s, s, 0}); }
-  JXLG_CHECK(ch.size() <= 8, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size()); h.num_rct = 0; h.first_group_channel = 0; global_has_data = false;
-  uint64_t off = 0; for (auto& c : ch) { c.plane_off = off; off += uint64_t(c.w) * c.h; } for (size_t i = 0; i < ch.size(); i++) h.mod_ch[i] = ch[i];
+  JXLG_CHECK(ch.size() <= 8, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size()); h.num_ops = 0; h.first_group_channel = 0; global_has_data = false; mod_total_ints = 0;
   h.mod_bitdepth = m.bd.bits; { uint32_t mb = m.bd.bits; for (const auto& e : m.ec) mb = std::max(mb, e.bd.bits); h.mod_wide = (mb > 20 || !m.modular_16bit) ? 1 : 0; }
+  const size_t num_image_channels = ch.size();
   if (!ch.empty()) {
     gheader = ReadGroupHeader(br);
-    for (const Transform& t : gheader.transforms) { JXLG_CHECK(t.id == 0, "palette / squeeze transforms are not supported by the GPU decoder yet"); JXLG_CHECK(t.begin_c + 3 <= ch.size() && h.num_rct < 4, "RCT channel range");
-      JXLG_CHECK(ch[t.begin_c].w == ch[t.begin_c + 1].w && ch[t.begin_c].w == ch[t.begin_c + 2].w && ch[t.begin_c].h == ch[t.begin_c + 1].h && ch[t.begin_c].h == ch[t.begin_c + 2].h, "RCT channel sizes");
-      h.rct_begin[h.num_rct] = t.begin_c; h.rct_type[h.num_rct] = t.rct_type; h.num_rct++; }
-    size_t c = 0; for (; c < ch.size(); c++) if (ch[c].w > fh.group_dim || ch[c].h > fh.group_dim) break;
+    // ---- the channel list as coded: the forward side of every transform (libjxl's MetaApply)
+    int nb_meta = 0;
+    for (const Transform& t : gheader.transforms) {
+      JXLG_CHECK(t.id != 2, "squeeze transforms are not supported by the GPU decoder yet");
+      if (t.id == 0) { JXLG_CHECK(t.begin_c + 3 <= ch.size(), "RCT channel range"); continue; }
+      const uint32_t end_c = t.begin_c + t.num_c - 1; JXLG_CHECK(t.num_c >= 1 && t.num_c <= 4 && end_c < ch.size(), "palette channel range");
+      for (uint32_t c = t.begin_c + 1; c <= end_c; c++) JXLG_CHECK(ch[c].w == ch[t.begin_c].w && ch[c].h == ch[t.begin_c].h && ch[c].hshift == ch[t.begin_c].hshift && ch[c].vshift == ch[t.begin_c].vshift, "palette channel sizes");
+      if (int(t.begin_c) < nb_meta) { JXLG_CHECK(int(end_c) < nb_meta, "palette across the meta-channel boundary"); nb_meta += 2 - int(t.num_c); } else nb_meta += 1;
+      ch.erase(ch.begin() + t.begin_c + 1, ch.begin() + end_c + 1);
+      ch.insert(ch.begin(), DModChannel{t.nb_colors + t.nb_deltas, t.num_c, 0, 0, 0});   // the palette itself: one row per colour channel, always coded in the global section
+    }
+    JXLG_CHECK(ch.size() <= 8, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size());
+  }
+  uint64_t off = 0; for (auto& c : ch) { c.plane_off = off; off += uint64_t(c.w) * c.h; } for (size_t i = 0; i < ch.size(); i++) h.mod_ch[i] = ch[i];
+  if (!ch.empty()) {
+    // ---- which of them the global section holds: meta channels always, then every channel up to the first one larger than a group
+    int nb_meta = 0; for (const Transform& t : gheader.transforms) if (t.id == 1) { if (int(t.begin_c) < nb_meta) nb_meta += 2 - int(t.num_c); else nb_meta += 1; }
+    size_t c = 0; for (; c < ch.size(); c++) if (int(c) >= nb_meta && (ch[c].w > fh.group_dim || ch[c].h > fh.group_dim)) break;
     global_decoded = c; h.first_group_channel = uint32_t(c);
     size_t nonempty = 0; for (size_t i = 0; i < c; i++) if (ch[i].w && ch[i].h) nonempty++;
     if (nonempty) { JXLG_CHECK(gheader.use_global_tree && has_tree, "local MA trees are not supported by the GPU decoder yet"); global_has_data = true; }
+    // ---- the inverse transforms as device ops, last transform first; `cur` follows the channel list back to the image's own channels
+    std::vector<DModChannel> cur = ch;
+    for (size_t ti = gheader.transforms.size(); ti-- > 0;) {
+      const Transform& t = gheader.transforms[ti]; JXLG_CHECK(h.num_ops < 4, "too many Modular transforms"); DModOp& op = h.ops[h.num_ops++]; memset(&op, 0, sizeof(op));
+      if (t.id == 0) {
+        JXLG_CHECK(t.begin_c + 3 <= cur.size(), "RCT channel range"); const DModChannel& a = cur[t.begin_c];
+        for (int k = 1; k < 3; k++) JXLG_CHECK(cur[t.begin_c + k].w == a.w && cur[t.begin_c + k].h == a.h, "RCT channel sizes");
+        op.kind = 0; op.rct_type = t.rct_type; op.w = a.w; op.h = a.h; for (int k = 0; k < 3; k++) op.p[k] = cur[t.begin_c + k].plane_off;
+      } else {
+        JXLG_CHECK(t.begin_c + 1 < cur.size(), "palette channel range"); const DModChannel pal = cur[0], idx = cur[t.begin_c + 1];
+        JXLG_CHECK(pal.h == t.num_c && pal.w == t.nb_colors + t.nb_deltas, "palette geometry"); JXLG_CHECK(t.nb_deltas == 0 || t.predictor != 6, "delta palettes with the weighted predictor are not supported");
+        op.kind = 1; op.num_c = t.num_c; op.pal_w = pal.w; op.nb_deltas = t.nb_deltas; op.predictor = t.predictor; op.w = idx.w; op.h = idx.h; op.p[0] = idx.plane_off; op.p[1] = pal.plane_off;
+        cur.erase(cur.begin()); std::vector<DModChannel> outs;
+        for (uint32_t k = 0; k < t.num_c; k++) { DModChannel o = idx; o.plane_off = off; off += uint64_t(idx.w) * idx.h; op.out[k] = o.plane_off; outs.push_back(o); }
+        cur.erase(cur.begin() + t.begin_c); cur.insert(cur.begin() + t.begin_c, outs.begin(), outs.end());
+      }
+    }
+    JXLG_CHECK(cur.size() == num_image_channels, "Modular transforms do not restore the channel list");
+    for (size_t i = 0; i < cur.size(); i++) h.out_ch[i] = cur[i];
   }
+  mod_total_ints = off;
 }
 
 void DecodeJob::ParseHfGlobal(BitReader& br) {
@@ -388,7 +422,7 @@ void DecodeJob::AllocateAndUpload(const DecodeRequest& req) {
     d_hfmeta.Alloc((size_t(h.num_lf_groups) * kHfMetaScratchInts + h.num_lf_groups) * 4); d_coeffs.Alloc(band_groups * 3 * 65536 * 2); coeffs_bytes = band_groups * 3 * 65536 * 2; d_xyb.Alloc(px * 3 * 4);
     d_sigma.Alloc(cells * 4); if (!phased) d_xyb_tmp.Alloc(px * 3 * 4);   // phased (batch) jobs allocate xyb_tmp in RunRender, and only when the frame needs it
   }
-  uint64_t mod_ints = 0; for (uint32_t i = 0; i < h.num_mod_channels; i++) mod_ints += uint64_t(h.mod_ch[i].w) * h.mod_ch[i].h; if (mod_ints) d_mod.Alloc(mod_ints * 4);
+  uint64_t mod_ints = mod_total_ints; if (mod_ints) d_mod.Alloc(mod_ints * 4);
   if (h.uses_wp) d_wp.Alloc((size_t(h.num_lf_groups) + h.num_groups + 1) * 5 * 2 * (kMaxWpWidth + 2) * 4); else d_wp.Alloc(16);
   const DOutput& o = h.out; size_t bps = o.sample_type == 0 ? 1 : o.sample_type == 3 ? 4 : 2; size_t chans = bgra ? 4 : (o.num_channels + (o.black_plane >= 0 ? 1 : 0)); if (bgra) bps = 1;
   out_bytes = size_t(o.out_w) * (h.band_on ? h.out_y1 - h.out_y0 : o.out_h) * chans * bps;
@@ -413,6 +447,7 @@ static const char* DevErrorText(uint32_t e) {
     case kErrTooManyNz: return "too many non-zero coefficients"; case kErrNzMismatch: return "non-zero count mismatch"; case kErrUnsupportedStream: return "unsupported Modular stream geometry"; case kErrCoefRange: return "coefficient exceeds 16 bits";
     case kErrHfMeta: return "HF metadata inconsistent"; case kErrLocalTree: return "local MA trees are not supported by the GPU decoder yet"; case kErrGroupTransform: return "per-group Modular transforms are not supported by the GPU decoder yet";
     case kErrHybrid: return "hybrid integer too large"; case kErrPrefix: return "invalid prefix code"; case kErrCflRange: return "CfL factor out of range"; case kErrSharpness: return "EPF sharpness out of range"; case kErrPreset: return "invalid HF preset"; case kErrRefProps: return "unsupported MA-tree property";
+    case kErrPaletteDelta: return "delta-palette entries (negative palette indices) are not supported";
     default: return "device decode error"; }
 }
 
@@ -492,7 +527,7 @@ void DecodeJob::RunRender() {
   if (vardct && !(dbg_skip & 1)) LaunchReconstruct(d, h, stream);
   if (timed) cudaEventRecord(ev[3], stream);
   bool fused = false;
-  if (h.num_rct) LaunchInverseRct(d, h, stream);
+  if (h.num_ops) LaunchInverseRct(d, h, stream);
   if (dbg_skip & 2) fused = true; else
   if (vardct && !unfused) fused = LaunchFusedRender(d, h, stream);   // gaborish + EPF + colour + pack in one kernel
   if (vardct && !fused) LaunchFilters(d, h, stream);

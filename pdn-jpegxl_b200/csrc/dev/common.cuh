@@ -32,7 +32,7 @@ __host__ __device__ inline DAlias PackAlias(uint32_t cutoff, uint32_t right, uin
 
 enum DevError : uint32_t {
   kErrNone = 0, kErrOverrun = 1, kErrAnsFinal = 2, kErrBadStrategy = 3, kErrBlockBounds = 4, kErrTooManyNz = 5, kErrNzMismatch = 6, kErrUnsupportedStream = 7,
-  kErrCoefRange = 8, kErrHfMeta = 9, kErrLocalTree = 10, kErrGroupTransform = 11, kErrHybrid = 12, kErrPrefix = 13, kErrCflRange = 14, kErrSharpness = 15, kErrPreset = 16, kErrRefProps = 17,
+  kErrCoefRange = 8, kErrHfMeta = 9, kErrLocalTree = 10, kErrGroupTransform = 11, kErrHybrid = 12, kErrPrefix = 13, kErrCflRange = 14, kErrSharpness = 15, kErrPreset = 16, kErrRefProps = 17, kErrPaletteDelta = 18,
 };
 
 #ifdef __CUDACC__

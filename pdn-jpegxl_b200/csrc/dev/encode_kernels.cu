@@ -112,48 +112,117 @@ __device__ __constant__ uint8_t kFreqCtxE[64] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 __device__ __constant__ uint8_t kNumNzCtxE[64] = {0, 0, 31, 62, 62, 93, 93, 93, 93, 123, 123, 123, 123, 152, 152, 152, 152, 152, 152, 152, 152, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180,
   206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
 
-// AC tokenisation for DCT8-only frames (default block-context map: 15 contexts, order id 0).
-__global__ void __launch_bounds__(32) k_enc_ac_tokens(const DEncFrame* ep) {
-  const DEncFrame& e = *ep; int g = blockIdx.x * blockDim.x + threadIdx.x; if (g >= int(e.num_groups)) return;
-  int gx = g % int(e.xgroups), gy = g / int(e.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(e.xb) - cx0), h = min(32, int(e.yb) - cy0); size_t lfplane = size_t(e.xb) * e.yb;
-  uint2* out = e.tokens + e.ac_token_off + size_t(g) * kMaxAcTokensPerGroup; uint32_t n = 0; const uint32_t nbctx = 15; const uint8_t bctx_of[3] = {7, 0, 7};   // default map, order 0: Y->0, X->7, B->7 (A.8)
-  const uint16_t* order = e.order8;
-  for (int by = 0; by < h; by++) for (int bx = 0; bx < w; bx++) {
-    size_t cell = size_t(cy0 + by) * e.xb + cx0 + bx;
-    for (int ci = 0; ci < 3; ci++) {
-      int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; const uint8_t* nzp = e.nz + c * lfplane; uint32_t nz = nzp[cell];
-      uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : nzp[cell - e.xb]; else if (by == 0) pred = nzp[cell - 1]; else pred = (uint32_t(nzp[cell - e.xb]) + nzp[cell - 1] + 1) >> 1;
-      uint32_t nzb = pred < 8 ? pred : (pred >= 64 ? 36 : 4 + pred / 2); uint32_t bc = bctx_of[c];
-      MakeToken(nzb * nbctx + bc, nz, 4, 2, out + n++);
-      const int16_t* co = e.coeffs + (size_t(g) * 3 + c) * 65536 + (size_t(by) * 32 + bx) * 64; uint32_t histo = nbctx * 37 + 458 * bc, prev = nz > 4 ? 0 : 1;
-      for (uint32_t k = 1; k < 64 && nz != 0; k++) { int32_t v = co[order[k]]; uint32_t zctx = (uint32_t(kNumNzCtxE[nz]) + kFreqCtxE[k]) * 2 + prev; MakeToken(histo + zctx, PackSignedDev(v), 4, 2, out + n++); prev = v != 0; nz -= prev; }
+// AC tokenisation for DCT8-only frames (default block-context map: 15 contexts, order id 0). One CTA per 256x256 group, one thread per
+// 8x8 block: a block's token count is known from its coefficients alone (1 + the scan position of the last non-zero coefficient, per
+// channel), so a CTA-wide exclusive scan in raster order gives every block its place in the group's token stream and all blocks are
+// written at once. (r01: one THREAD per group walked its 1024 blocks serially.)
+__global__ void __launch_bounds__(1024) k_enc_ac_tokens(const DEncFrame* ep) {
+  const DEncFrame& e = *ep; const int g = blockIdx.x;
+  const int gx = g % int(e.xgroups), gy = g / int(e.xgroups), cx0 = gx * 32, cy0 = gy * 32, w = min(32, int(e.xb) - cx0), h = min(32, int(e.yb) - cy0); const size_t lfplane = size_t(e.xb) * e.yb;
+  const int tid = threadIdx.x, by = tid >> 5, bx = tid & 31, lane = tid & 31, warp = tid >> 5; const bool active = by < h && bx < w;
+  const uint32_t nbctx = 15; const uint8_t bctx_of[3] = {7, 0, 7};   // default map, order 0: Y->0, X->7, B->7 (A.8)
+  const uint16_t* order = e.order8; const size_t cell = size_t(cy0 + by) * e.xb + cx0 + bx;
+  __shared__ uint32_t warp_total[32];
+  // ---- count: per channel, the scan position of the last non-zero coefficient (0: the block has none)
+  uint32_t last[3] = {0, 0, 0}, cnt = 0;
+  if (active) {
+#pragma unroll 1
+    for (int c = 0; c < 3; c++) {
+      if (e.nz[c * lfplane + cell]) { const int16_t* co = e.coeffs + (size_t(g) * 3 + c) * 65536 + (size_t(by) * 32 + bx) * 64; int k = 63; while (k > 0 && co[order[k]] == 0) k--; last[c] = uint32_t(k); }
+      cnt += 1 + last[c];
     }
   }
-  e.ac_token_count[g] = n;
-}
-
-__global__ void k_enc_histogram(const uint2* __restrict__ tokens, const DEncStream* streams, uint32_t* hist) {
-  const DEncStream s = streams[blockIdx.y]; uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= s.count) return;
-  uint32_t t = tokens[s.token_off + i].x; atomicAdd(hist + size_t(t & 0xffff) * kEncAlphabet + ((t >> 16) & 0xff), 1u);
-}
-
-// ANS writer (A.6 "ANS symbol read" mirrored): reverse pass computes the state chain, forward pass packs the bits.
-__global__ void __launch_bounds__(32) k_enc_ans(const DEncFrame* ep, const DEncStream* streams, uint32_t nstreams, const DEncCode* code) {
-  const DEncFrame& e = *ep; uint32_t si = blockIdx.x * blockDim.x + threadIdx.x; if (si >= nstreams) return; const DEncStream s = streams[si];
-  uint2* tk = e.tokens + s.token_off; uint32_t state = 0x130000u;
-  const uint8_t* ctx_map = code->ctx_map; const uint16_t* freq = code->freq; const uint16_t* start = code->start; const uint16_t* rev = code->rev;
-  for (uint32_t i = s.count; i-- > 0;) {
-    uint32_t t = tk[i].x, cl = ctx_map[t & 0xffff], sym = (t >> 16) & 0xff; uint32_t f = freq[cl * kEncAlphabet + sym], flush = 0;
-    if ((state >> 20) >= f) { flush = 0x10000u | (state & 0xffff); state >>= 16; }
-    state = ((state / f) << 12) + rev[cl * 4096 + start[cl * kEncAlphabet + sym] + (state % f)];
-    tk[i].x = (t & 0x3f000000u) | flush;   // keep nbits, replace ctx/symbol by the flush word
+  // ---- exclusive scan over the CTA in raster order
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+  if (lane == 31) warp_total[warp] = incl;
+  __syncthreads();
+  if (warp == 0) { uint32_t v = warp_total[lane], iv = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, iv, d); if (lane >= d) iv += u; }
+    warp_total[lane] = iv - v; if (lane == 31) e.ac_token_count[g] = iv; }
+  __syncthreads();
+  if (!active) return;
+  uint2* out = e.tokens + e.ac_token_off + size_t(g) * kMaxAcTokensPerGroup + warp_total[warp] + (incl - cnt);
+  // ---- emit: channels in the order Y, X, B
+#pragma unroll 1
+  for (int ci = 0; ci < 3; ci++) {
+    const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; const uint8_t* nzp = e.nz + c * lfplane; uint32_t nz = nzp[cell];
+    uint32_t pred; if (bx == 0) pred = by == 0 ? 32 : nzp[cell - e.xb]; else if (by == 0) pred = nzp[cell - 1]; else pred = (uint32_t(nzp[cell - e.xb]) + nzp[cell - 1] + 1) >> 1;
+    const uint32_t nzb = pred < 8 ? pred : (pred >= 64 ? 36 : 4 + pred / 2), bc = bctx_of[c];
+    MakeToken(nzb * nbctx + bc, nz, 4, 2, out++);
+    const int16_t* co = e.coeffs + (size_t(g) * 3 + c) * 65536 + (size_t(by) * 32 + bx) * 64; const uint32_t histo = nbctx * 37 + 458 * bc; uint32_t prev = nz > 4 ? 0 : 1;
+    for (uint32_t k = 1; k <= last[c]; k++) { const int32_t v = co[order[k]]; const uint32_t zctx = (uint32_t(kNumNzCtxE[nz]) + kFreqCtxE[k]) * 2 + prev; MakeToken(histo + zctx, PackSignedDev(v), 4, 2, out++); prev = v != 0; nz -= prev; }
   }
-  uint8_t* out = e.stream_bytes + s.byte_off; uint64_t acc = state; int nb = 32; size_t pos = 0;
-  auto put = [&](uint32_t v, int n) { acc |= uint64_t(v) << nb; nb += n; while (nb >= 8) { out[pos++] = uint8_t(acc); acc >>= 8; nb -= 8; } };
-  put(0, 0);
-  for (uint32_t i = 0; i < s.count; i++) { uint2 t = tk[i]; if (t.x & 0x10000u) put(t.x & 0xffff, 16); int n = int((t.x >> 24) & 0x3f); if (n) put(t.y, n); }
-  uint64_t bits = uint64_t(pos) * 8 + nb; if (nb) out[pos++] = uint8_t(acc);
-  e.stream_bits[si] = bits;
+}
+
+// Token histograms. Neighbouring tokens of a stream mostly share their (context, symbol) pair (runs of zeros in one context), so a warp first
+// groups its lanes by key and one lane per group adds the group's size: same-address atomics, which serialise in L2, drop several-fold.
+__global__ void k_enc_histogram(const uint2* __restrict__ tokens, const DEncStream* streams, uint32_t* hist) {
+  const DEncStream s = streams[blockIdx.y]; const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; const bool valid = i < s.count;
+  const uint32_t t = valid ? tokens[s.token_off + i].x : 0xffffffffu; const uint32_t key = valid ? (t & 0x00ffffffu) : 0xffffffffu;   // ctx[0,16) | symbol[16,24)
+  const uint32_t peers = __match_any_sync(0xffffffffu, key); const int leader = __ffs(peers) - 1;
+  if (valid && int(threadIdx.x & 31) == leader) atomicAdd(hist + size_t(key & 0xffff) * kEncAlphabet + (key >> 16), uint32_t(__popc(peers)));
+}
+
+// ANS writer (A.6 "ANS symbol read" mirrored), one WARP per section stream. The state chain is serial (token i needs the state after token
+// i + 1), but everything around it is not:
+//   reverse pass: the lanes load 32 tokens at once and look up cluster, frequency, reciprocal and reverse-table base for them; then the warp
+//                 steps through the 32 tokens with the state held redundantly in every lane (shuffles hand out token k's operands), so a step
+//                 is a reciprocal multiply + one dependent table load, not five dependent global loads;
+//   forward pass: lengths (16 flush bits + extra bits) are prefix-summed across the warp, every lane ORs its bits into a shared-memory
+//                 window, whole words go to HBM with coalesced stores.
+// (r01: one THREAD per stream: 32 lanes of a warp walked 32 different streams with scattered loads, 70 ms per launch at 12 MP.)
+__global__ void __launch_bounds__(128) k_enc_ans(const DEncFrame* ep, const DEncStream* streams, uint32_t nstreams, const DEncCode* code, uint32_t bits_off) {
+  const DEncFrame& e = *ep; const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; const uint32_t si = blockIdx.x * 4 + warp;
+  __shared__ uint32_t window[4][56];
+  if (si >= nstreams) return;   // whole warps leave; only __syncwarp below
+  const DEncStream s = streams[si]; uint2* tk = e.tokens + s.token_off; const uint32_t count = s.count; uint32_t state = 0x130000u;
+  const uint8_t* ctx_map = code->ctx_map; const uint16_t* freq = code->freq; const uint16_t* start = code->start; const uint16_t* rev = code->rev;
+  // One step of the chain for token k of the chunk: the operands come from lane k, the state is uniform across the warp. Both candidates of
+  // the quotient (with and without the 16-bit flush) are started before the flush decision is known.
+  auto step = [&](int k, uint32_t f, uint32_t m, uint32_t rb, uint32_t& myflush) {
+    const uint32_t fk = __shfl_sync(0xffffffffu, f, k), mk = __shfl_sync(0xffffffffu, m, k), rk = __shfl_sync(0xffffffffu, rb, k);
+    const bool fl = (state >> 20) >= fk; const uint32_t flush = fl ? (0x10000u | (state & 0xffff)) : 0u, x = fl ? (state >> 16) : state;
+    uint32_t q = __umulhi(x, mk), r = x - q * fk; if (r >= fk) { q++; r -= fk; } if (r >= fk) { q++; r -= fk; }
+    state = (q << 12) + rev[rk + r];
+    if (lane == k) myflush = flush;
+  };
+  for (int64_t base = count ? int64_t((count - 1) & ~31u) : -1; base >= 0; base -= 32) {
+    const uint32_t i = uint32_t(base) + lane; const bool valid = i < count; uint32_t t = 0, f = 1, rb = 0;
+    if (valid) { t = tk[i].x; const uint32_t cl = ctx_map[t & 0xffff], sym = (t >> 16) & 0xff; f = freq[cl * kEncAlphabet + sym]; rb = cl * 4096 + start[cl * kEncAlphabet + sym]; }
+    const uint32_t m = 0xffffffffu / max(f, 1u);   // floor((2^32 - 1) / f): umulhi(state, m) is state / f or up to 2 less
+    uint32_t myflush = 0; const int kmax = int(min(uint32_t(31), count - 1 - uint32_t(base)));
+    if (kmax == 31) {   // full chunk: straight-line code, so the shuffles of later tokens issue while a table load is in flight
+#pragma unroll
+      for (int k = 31; k >= 0; k--) step(k, f, m, rb, myflush);
+    } else for (int k = kmax; k >= 0; k--) step(k, f, m, rb, myflush);
+    if (valid) tk[i].x = (t & 0x3f000000u) | myflush;   // keep nbits, replace ctx / symbol by the flush word
+  }
+  __syncwarp();
+  // ---- forward: the final state first (32 bits), then per token [16 flush bits][extra bits]
+  uint32_t* out = reinterpret_cast<uint32_t*>(e.stream_bytes + s.byte_off); uint32_t* win = window[warp];
+  if (lane == 0) out[0] = state;
+  uint64_t pos = 32; uint32_t carry = 0;   // bits written so far; the partial last word
+  for (uint32_t base = 0; base < count; base += 32) {
+    const uint32_t i = base + lane; uint32_t len = 0; uint64_t val = 0;
+    if (i < count) { const uint2 t = tk[i]; const uint32_t nb = (t.x >> 24) & 0x3f; if (t.x & 0x10000u) { val = (t.x & 0xffff) | (uint64_t(t.y) << 16); len = 16 + nb; } else { val = t.y; len = nb; } }
+    uint32_t incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), lead = uint32_t(pos & 31), at = lead + incl - len;
+    win[lane] = lane == 0 ? carry : 0; if (lane < 24) win[32 + lane] = 0;
+    __syncwarp();
+    if (len) { const uint32_t wd = at >> 5, sh = at & 31; const uint64_t lo = val << sh; atomicOr(&win[wd], uint32_t(lo)); const uint32_t mid = uint32_t(lo >> 32); if (mid) atomicOr(&win[wd + 1], mid);
+      if (sh + len > 64) atomicOr(&win[wd + 2], uint32_t(val >> (64 - sh))); }
+    __syncwarp();
+    const uint32_t filled = lead + total, nfull = filled >> 5; uint32_t* dst = out + (pos >> 5);
+    for (uint32_t j = lane; j < nfull; j += 32) dst[j] = win[j];
+    carry = win[nfull]; pos += total;
+    __syncwarp();
+  }
+  if (lane == 0) { if (pos & 31) out[pos >> 5] = carry; e.stream_bits[bits_off + si] = pos; }
 }
 
 void EncLaunchScan(const uint8_t* bgra, uint32_t w, uint32_t h, uint32_t stride, uint32_t* flags, cudaStream_t st) { dim3 grid((w + 255) / 256, h); k_enc_scan<<<grid, 256, 0, st>>>(bgra, w, h, stride, flags); CountLaunch(); }
@@ -164,10 +233,10 @@ void EncLaunchDct8(const DEncFrame* d, const DEncFrame& h, cudaStream_t st) { ui
 void EncLaunchModTokens(const DEncFrame* d, const DEncModStream* streams, uint32_t nstreams, uint32_t max_tokens, const int32_t* planes, uint32_t pw, uint32_t ph, uint32_t nch, const uint16_t* leaf_lut, cudaStream_t st) {
   if (!nstreams || !max_tokens) return; dim3 grid((max_tokens + 255) / 256, nstreams); k_enc_mod_tokens<<<grid, 256, 0, st>>>(d, streams, planes, pw, ph, nch, leaf_lut); CountLaunch();
 }
-void EncLaunchAcTokens(const DEncFrame* d, const DEncFrame& h, cudaStream_t st) { k_enc_ac_tokens<<<(h.num_groups + 31) / 32, 32, 0, st>>>(d); CountLaunch(); }
+void EncLaunchAcTokens(const DEncFrame* d, const DEncFrame& h, cudaStream_t st) { if (!h.num_groups) return; k_enc_ac_tokens<<<h.num_groups, 1024, 0, st>>>(d); CountLaunch(); }
 void EncLaunchHistogram(const uint2* tokens, const DEncStream* streams, uint32_t nstreams, uint32_t max_count, uint32_t* hist, cudaStream_t st) {
   if (!nstreams || !max_count) return; dim3 grid((max_count + 255) / 256, nstreams); k_enc_histogram<<<grid, 256, 0, st>>>(tokens, streams, hist); CountLaunch();
 }
-void EncLaunchAns(const DEncFrame* d, const DEncStream* streams, uint32_t nstreams, const DEncCode* code, cudaStream_t st) { if (!nstreams) return; k_enc_ans<<<(nstreams + 31) / 32, 32, 0, st>>>(d, streams, nstreams, code); CountLaunch(); }
+void EncLaunchAns(const DEncFrame* d, const DEncStream* streams, uint32_t nstreams, const DEncCode* code, uint32_t bits_off, cudaStream_t st) { if (!nstreams) return; k_enc_ans<<<(nstreams + 3) / 4, 128, 0, st>>>(d, streams, nstreams, code, bits_off); CountLaunch(); }
 
 }  // namespace jxlgpu

@@ -27,6 +27,10 @@ struct DOutput {
   uint32_t alpha_bits, alpha_exp_bits, black_bits, bits, exp_bits;
 };
 struct DModChannel { uint32_t w, h, hshift, vshift; uint64_t plane_off; };   // plane_off: int32 element offset into DFrame::mod_planes
+// One inverse transform of the global Modular image, in the order the kernels run them (the reverse of the order the file lists them).
+// kind 0 RCT: planes p[0..2] of n samples, in place. kind 1 Palette: index plane p[0] (w x h) and palette plane p[1] (pal_w entries per row,
+// one row per output channel) expand into num_c new planes out[0..num_c) — out of place, the index plane is read by every output channel.
+struct DModOp { uint32_t kind, rct_type, num_c, pal_w, nb_deltas, predictor, w, h; uint64_t p[3]; uint64_t out[4]; };
 
 // Per-device constant tables (built once): scaled DCT cosines c[k*N+i] = ck*cos((2i+1)k*pi/2N) for N = 1..256 and
 // the LF->LLF resample scales. cos_off[log2 N] is the float offset of the N x N table.
@@ -45,7 +49,9 @@ struct DFrame {
   uint32_t dq_off[17];       // float[3*size] per quant table, byte offsets into blob
   uint32_t lf_smem, ac_smem, lf_cta_offset, ac_cta_offset, ac_fast; // dynamic shared memory budgets (bytes) for the table staging of k_lf_group / k_ac_group
   uint32_t sec_off;          // uint64 sec_bitpos[nsec] then uint64 sec_bitend[nsec], byte offset into blob
-  uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8]; uint32_t mod_bitdepth, mod_wide; uint32_t num_rct; uint32_t rct_begin[4], rct_type[4];
+  uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8];   // the channels as CODED (after the file's forward transforms): what the entropy kernels fill
+  DModChannel out_ch[8];   // the image's own channels (colour, then extra channels) after the inverse transforms: what the output kernels read
+  uint32_t mod_bitdepth, mod_wide; uint32_t num_ops, ops_pad; DModOp ops[4];
   DLoopFilter lpf; DColor color; DOutput out;
   // device buffers
   const uint8_t* comp; const uint8_t* blob; const uint8_t* static_blob;

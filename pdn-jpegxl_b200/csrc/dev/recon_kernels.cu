@@ -412,14 +412,47 @@ __global__ void k_epf(const DFrame* fp, const float* __restrict__ src, float* __
 }
 
 // ------------------------------------------------------------------ inverse RCT on the global Modular image
-__global__ void k_inverse_rct(const DFrame* fp, uint32_t begin_c, uint32_t type) {
-  const DFrame& f = *fp; const DModChannel& c0 = f.mod_ch[begin_c]; size_t n = size_t(c0.w) * c0.h; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
-  int32_t* p0 = f.mod_planes + f.mod_ch[begin_c].plane_off; int32_t* p1 = f.mod_planes + f.mod_ch[begin_c + 1].plane_off; int32_t* p2 = f.mod_planes + f.mod_ch[begin_c + 2].plane_off;
+__global__ void k_inverse_rct(const DFrame* fp, uint32_t op_index) {
+  const DFrame& f = *fp; const DModOp& op = f.ops[op_index]; const uint32_t type = op.rct_type; const size_t n = size_t(op.w) * op.h; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
+  int32_t* p0 = f.mod_planes + op.p[0]; int32_t* p1 = f.mod_planes + op.p[1]; int32_t* p2 = f.mod_planes + op.p[2];
   uint32_t perm = type / 7, k = type % 7; int32_t A = p0[i], B = p1[i], C = p2[i], o[3];
   if (k == 6) { int32_t t = A - (C >> 1); int32_t G = C + t; int32_t Bl = t - (B >> 1); int32_t R = Bl + B; o[0] = R; o[1] = G; o[2] = Bl; }
   else { int32_t D = A, E = B, F = C; if (k & 1) F += A; if ((k >> 1) == 1) E += A; if ((k >> 1) == 2) E += (A + F) >> 1; o[0] = D; o[1] = E; o[2] = F; }
   int32_t r[3]; r[perm % 3] = o[0]; r[(perm + 1 + perm / 3) % 3] = o[1]; r[(perm + 2 - perm / 3) % 3] = o[2];
   p0[i] = r[0]; p1[i] = r[1]; p2[i] = r[2];
+}
+
+// ------------------------------------------------------------------ inverse Palette on the global Modular image (SURVEY.md A.7 "Palette")
+// Index -> colour: explicit entries [0, pal_w), then the implicit 4x4x4 cube (64 entries, offset by 2^(bitdepth-3)) and the implicit 5x5x5
+// cube. Negative indices address the 72-entry delta palette, whose table is not available offline: they raise kErrPaletteDelta.
+__device__ __forceinline__ int32_t PaletteValue(const int32_t* pal_row, int index, int c, int pal_w, int bitdepth, uint32_t* err) {
+  if (index < 0) { SetError(err, kErrPaletteDelta); return 0; }
+  if (index < pal_w) return pal_row[index];
+  if (c > 2) return 0;
+  const long long maxv = (1ll << bitdepth) - 1;
+  if (index < pal_w + 64) { const int i2 = index - pal_w, div = c == 0 ? 1 : c == 1 ? 4 : 16; return int32_t((((long long)((i2 / div) % 4) * maxv) >> 2) + (1ll << max(0, bitdepth - 3))); }
+  const int i2 = index - pal_w - 64, div = c == 0 ? 1 : c == 1 ? 5 : 25; return int32_t(((long long)((i2 / div) % 5) * maxv) >> 2);
+}
+// Pure gather: one thread per sample and output channel (blockIdx.y). Used when the palette has no delta entries.
+__global__ void k_inverse_palette(const DFrame* fp, uint32_t op_index) {
+  const DFrame& f = *fp; const DModOp& op = f.ops[op_index]; const size_t n = size_t(op.w) * op.h; const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
+  const int c = blockIdx.y; const int32_t* idx = f.mod_planes + op.p[0]; const int32_t* pal = f.mod_planes + op.p[1] + size_t(c) * op.pal_w;
+  f.mod_planes[op.out[c] + i] = PaletteValue(pal, idx[i], c, int(op.pal_w), int(f.mod_bitdepth), f.err);
+}
+// Palettes with delta entries (index < nb_deltas: the entry is ADDED to a prediction from the already reconstructed neighbours of the same
+// output channel): serial in raster order, one thread per output channel. A rare path (lossy-palette files); correctness only.
+__global__ void k_inverse_palette_delta(const DFrame* fp, uint32_t op_index) {
+  const DFrame& f = *fp; const DModOp& op = f.ops[op_index]; const int c = blockIdx.x; if (threadIdx.x) return;
+  const int32_t* idx = f.mod_planes + op.p[0]; const int32_t* pal = f.mod_planes + op.p[1] + size_t(c) * op.pal_w; int32_t* out = f.mod_planes + op.out[c]; const int w = int(op.w), h = int(op.h);
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+    const int index = idx[size_t(y) * w + x]; int32_t v = PaletteValue(pal, index, c, int(op.pal_w), int(f.mod_bitdepth), f.err);
+    if (index >= 0 && index < int(op.nb_deltas)) {
+      const int32_t* p = out + size_t(y) * w + x;
+      const long long W = x ? p[-1] : (y ? p[-w] : 0), N = y ? p[-w] : W, NW = (x && y) ? p[-w - 1] : W, NE = (y && x + 1 < w) ? p[-w + 1] : N, NN = y > 1 ? p[-2 * w] : N, WW = x > 1 ? p[-2] : W, NEE = (y && x + 2 < w) ? p[-w + 2] : NE;
+      v = int32_t(v + ModMath<long long>::Prediction(int(op.predictor), N, W, NW, NE, NN, WW, NEE, 0));
+    }
+    out[size_t(y) * w + x] = v;
+  }
 }
 
 // ------------------------------------------------------------------ output
@@ -489,10 +522,10 @@ __device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float
   if (f.encoding == 0) XybToRgbDev(f, X, Y, B, rgb);
   else {
     const uint32_t nc = f.color.num_color;
-    for (uint32_t c = 0; c < 3; c++) { const DModChannel& ch = f.mod_ch[c < nc ? c : nc - 1]; rgb[c] = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(y) * ch.w + x], o.bits, o.exp_bits); }
+    for (uint32_t c = 0; c < 3; c++) { const DModChannel& ch = f.out_ch[c < nc ? c : nc - 1]; rgb[c] = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(y) * ch.w + x], o.bits, o.exp_bits); }
   }
   float a = 1.0f;
-  if (o.alpha_plane >= 0) { const DModChannel& ch = f.mod_ch[o.alpha_plane]; int sx = min(x >> ch.hshift, int(ch.w) - 1), sy = min(y >> ch.vshift, int(ch.h) - 1); a = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(sy) * ch.w + sx], o.alpha_bits, o.alpha_exp_bits); }
+  if (o.alpha_plane >= 0) { const DModChannel& ch = f.out_ch[o.alpha_plane]; int sx = min(x >> ch.hshift, int(ch.w) - 1), sy = min(y >> ch.vshift, int(ch.h) - 1); a = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(sy) * ch.w + sx], o.alpha_bits, o.alpha_exp_bits); }
   if (o.premultiplied) { float mul = 1.0f / fmaxf(1.0f / 67108864.0f, a); rgb[0] *= mul; rgb[1] *= mul; rgb[2] *= mul; }
   const size_t oi = OrientedIndex(f, x, y);
   if (o.bgra) {   // BGRA32 surface: B,G,R from the 8-bit conversion, A = alpha plane mapped to 8 bits (I/TransparencyMapping.cs:19-32) or 255
@@ -503,7 +536,7 @@ __device__ __forceinline__ void OutputPixel(const DFrame& f, int x, int y, float
   }
   const uint32_t bps = o.sample_type == 0 ? 1 : o.sample_type == 3 ? 4 : 2; uint8_t* dst = f.out_px + oi * size_t(bps) * (o.num_channels + (o.black_plane >= 0 ? 1 : 0));
   if (o.black_plane >= 0) {   // CMYK merge, N/Decoder/JxlDecoder.cpp:159-215 (u8 only): 255 - C,M,Y,K then optional A
-    const DModChannel& ch = f.mod_ch[o.black_plane]; float k = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(min(y >> ch.vshift, int(ch.h) - 1)) * ch.w + min(x >> ch.hshift, int(ch.w) - 1)], o.black_bits, 0);
+    const DModChannel& ch = f.out_ch[o.black_plane]; float k = IntToFloatSampleDev(f.mod_planes[ch.plane_off + size_t(min(y >> ch.vshift, int(ch.h) - 1)) * ch.w + min(x >> ch.hshift, int(ch.w) - 1)], o.black_bits, 0);
     uint8_t t[4]; for (int c = 0; c < 3; c++) StoreSampleDev(&t[c], 0, rgb[c]); StoreSampleDev(&t[3], 0, k);
     for (int c = 0; c < 4; c++) dst[c] = uint8_t(0xff - t[c]); if (o.alpha_plane >= 0) StoreSampleDev(dst + 4, 0, a); return;
   }
@@ -874,8 +907,8 @@ __global__ void k_output_int(const DFrame* fp) {
   const DFrame& f = *fp; const int xs = int(f.xsize), ys = int(f.ysize); const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= xs || y >= ys) return;
   if (f.band_on && (y < int(f.out_y0) || y >= int(f.out_y1))) return;
   const DOutput& o = f.out; const size_t oi = OrientedIndex(f, x, y); const uint32_t nc = f.color.num_color; int32_t v[4]; uint32_t n = 0;
-  for (uint32_t c = 0; c < o.color_channels; c++) { const DModChannel& ch = f.mod_ch[c < nc ? c : nc - 1]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }
-  if (o.alpha_plane >= 0) { const DModChannel& ch = f.mod_ch[o.alpha_plane]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }
+  for (uint32_t c = 0; c < o.color_channels; c++) { const DModChannel& ch = f.out_ch[c < nc ? c : nc - 1]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }
+  if (o.alpha_plane >= 0) { const DModChannel& ch = f.out_ch[o.alpha_plane]; v[n++] = f.mod_planes[ch.plane_off + size_t(y) * ch.w + x]; }
   const int32_t mx = o.sample_type == 0 ? 255 : 65535;
   if (o.bgra) { uint8_t r8 = uint8_t(min(max(v[0], 0), 255)), g8 = o.color_channels == 1 ? r8 : uint8_t(min(max(v[1], 0), 255)), b8 = o.color_channels == 1 ? r8 : uint8_t(min(max(v[2], 0), 255)); uint8_t a8 = o.alpha_plane >= 0 ? uint8_t(min(max(v[n - 1], 0), 255)) : 255;
     reinterpret_cast<uint32_t*>(f.out_px)[oi] = uint32_t(b8) | (uint32_t(g8) << 8) | (uint32_t(r8) << 16) | (uint32_t(a8) << 24); return; }
@@ -952,13 +985,19 @@ bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st) {
   }
   return true;
 }
-void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st) {
-  for (uint32_t i = h.num_rct; i-- > 0;) { const DModChannel& c0 = h.mod_ch[h.rct_begin[i]]; size_t n = size_t(c0.w) * c0.h; k_inverse_rct<<<unsigned((n + 255) / 256), 256, 0, st>>>(d, h.rct_begin[i], h.rct_type[i]); CountLaunch(); }
+void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st) {   // every inverse transform of the global Modular image, in execution order
+  for (uint32_t i = 0; i < h.num_ops; i++) {
+    const DModOp& op = h.ops[i]; const size_t n = size_t(op.w) * op.h; if (!n) continue;
+    if (op.kind == 0) k_inverse_rct<<<unsigned((n + 255) / 256), 256, 0, st>>>(d, i);
+    else if (op.nb_deltas == 0) k_inverse_palette<<<dim3(unsigned((n + 255) / 256), op.num_c), 256, 0, st>>>(d, i);
+    else k_inverse_palette_delta<<<op.num_c, 32, 0, st>>>(d, i);
+    CountLaunch();
+  }
 }
 void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st) {
   dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8);
   bool int_path = h.encoding == 1 && !h.color.xyb_encoded && h.out.exp_bits == 0 && h.out.black_plane < 0 && !h.out.premultiplied && (h.out.sample_type == 0 ? h.out.bits == 8 : (h.out.sample_type == 1 && h.out.bits == 16)) &&
-                  (h.out.alpha_plane < 0 || (h.out.alpha_bits == h.out.bits && h.out.alpha_exp_bits == 0 && h.mod_ch[h.out.alpha_plane].hshift == 0));
+                  (h.out.alpha_plane < 0 || (h.out.alpha_bits == h.out.bits && h.out.alpha_exp_bits == 0 && h.out_ch[h.out.alpha_plane].hshift == 0));
   if (int_path) k_output_int<<<grid, blk, 0, st>>>(d); else k_output<<<grid, blk, 0, st>>>(h, FilteredPlanes(h));
   CountLaunch();
 }

@@ -342,10 +342,16 @@ std::vector<BandSection> BandEncoder::Finish(const std::vector<uint64_t>& frame_
     Timer t(st, &device_ms);
     DeviceEncCode dm, da; UploadEncCode(codes.mcode, &dm, st); if (!lossless) UploadEncCode(codes.acode, &da, st);
     const DEncFrame* de = d_e.as<DEncFrame>(); const DEncStream* d_m = d_streams.as<DEncStream>(); const DEncStream* d_a = d_m + m_streams.size();
-    EncLaunchAns(de, d_m, uint32_t(m_streams.size()), dm.desc.as<DEncCode>(), st);
-    if (!m_streams.empty()) CUDA_OK(cudaMemcpyAsync(bits_m.data(), e.stream_bits, bits_m.size() * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    if (!lossless) { EncLaunchAns(de, d_a, ng, da.desc.as<DEncCode>(), st); CUDA_OK(cudaMemcpyAsync(bits_a.data(), e.stream_bits, size_t(ng) * 8, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); }
+    // the Modular streams (few and long: an LF group is one serial stream of 196 608 tokens) and the AC streams (many) are independent: two CUDA streams
+    cudaStream_t st2 = nullptr; cudaEvent_t ready = nullptr, done2 = nullptr; CUDA_OK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking)); cudaEventCreateWithFlags(&ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&done2, cudaEventDisableTiming);
+    cudaEventRecord(ready, st); cudaStreamWaitEvent(st2, ready, 0);
+    const uint32_t nm = uint32_t(m_streams.size());
+    EncLaunchAns(de, d_m, nm, dm.desc.as<DEncCode>(), 0, st);
+    if (!lossless) EncLaunchAns(de, d_a, ng, da.desc.as<DEncCode>(), nm, st2);
+    cudaEventRecord(done2, st2); cudaStreamWaitEvent(st, done2, 0);
+    if (nm) CUDA_OK(cudaMemcpyAsync(bits_m.data(), e.stream_bits, size_t(nm) * 8, cudaMemcpyDeviceToHost, st));
+    if (!lossless) CUDA_OK(cudaMemcpyAsync(bits_a.data(), e.stream_bits + nm, size_t(ng) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st)); cudaStreamDestroy(st2); cudaEventDestroy(ready); cudaEventDestroy(done2);
     if (byte_cursor) CUDA_OK(cudaMemcpyAsync(bytes.data(), d_bytes.p, byte_cursor, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
   }
   std::vector<BandSection> out;

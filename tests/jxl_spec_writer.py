@@ -575,8 +575,9 @@ def predict(pred, W, N, NW, NE, NN, WW, NEE):
     raise NotImplementedError(pred)
 
 
-def modular_items(root, channels, stream_id=0):
-    """Residual tokens of `channels` (list of 2-D integer lists) under the MA tree: [(context, packed residual)]."""
+def modular_items(root, channels, stream_id=0, first_channel=0):
+    """Residual tokens of `channels` (list of 2-D integer lists) under the MA tree: [(context, packed residual)]. first_channel: index of
+    channels[0] in the image's channel list (property 0) when the list is a tail of it (group sections skip the meta channels)."""
     items = []
     for ci, ch in enumerate(channels):
         h, w = len(ch), len(ch[0]) if ch else 0
@@ -589,7 +590,7 @@ def modular_items(root, channels, stream_id=0):
                 NN = ch[y - 2][x] if y > 1 else N
                 WW = ch[y][x - 2] if x > 1 else W
                 NEE = ch[y - 1][x + 2] if y and x + 2 < w else NE
-                props = {0: ci, 1: stream_id, 2: y, 3: x, 4: abs(N), 5: abs(W), 6: N, 7: W, 9: W + N - NW, 10: W - NW, 11: NW - N, 12: N - NE, 13: N - NN, 14: W - WW}
+                props = {0: ci + first_channel, 1: stream_id, 2: y, 3: x, 4: abs(N), 5: abs(W), 6: N, 7: W, 9: W + N - NW, 10: W - NW, 11: NW - N, 12: N - NE, 13: N - NN, 14: W - WW}
                 if x:   # property 8: W minus the gradient prediction error context of the pixel to the left
                     Wl = ch[y][x - 2] if x > 1 else (ch[y - 1][x - 1] if y else 0)
                     Nl = ch[y - 1][x - 1] if y else Wl
@@ -642,11 +643,57 @@ def group_header(b, transforms=()):
     b.bool(True)       # use_global_tree
     b.bool(True)       # default weighted-predictor parameters
     b.u32((("val", 0), ("val", 1), ("bo", 4, 2), ("bo", 8, 18)), len(transforms))
+    begin_c = (("bits", 3), ("bo", 6, 8), ("bo", 10, 72), ("bo", 13, 1096))
     for t in transforms:
-        assert t[0] == "rct"
-        b.u(2, 0)
-        b.u32((("bits", 3), ("bo", 6, 8), ("bo", 10, 72), ("bo", 13, 1096)), t[1])         # begin_c
-        b.u32((("val", 6), ("bits", 2), ("bo", 4, 2), ("bo", 6, 10)), t[2])                # rct_type
+        if t[0] == "rct":
+            b.u(2, 0)
+            b.u32(begin_c, t[1])
+            b.u32((("val", 6), ("bits", 2), ("bo", 4, 2), ("bo", 6, 10)), t[2])                # rct_type
+        else:
+            assert t[0] == "palette"                                                           # ("palette", begin_c, num_c, nb_colours, nb_deltas, predictor)
+            b.u(2, 1)
+            b.u32(begin_c, t[1])
+            b.u32((("val", 1), ("val", 3), ("val", 4), ("bo", 13, 1)), t[2])
+            b.u32((("bo", 8, 0), ("bo", 10, 256), ("bo", 12, 1280), ("bo", 16, 5376)), t[3])
+            b.u32((("val", 0), ("bo", 8, 1), ("bo", 10, 257), ("bo", 16, 1281)), t[4])
+            b.u(4, t[5])
+
+
+def implicit_palette_index(pixel, bits=8):
+    """Index offset (relative to the end of the explicit palette) of a colour of the implicit cubes (H.6.3), or None: first the 4x4x4 cube
+    whose levels are ((k * max) >> 2) + 2^(bits-3), then the 5x5x5 cube with levels (k * max) >> 2."""
+    maxv = (1 << bits) - 1
+    small = [((k * maxv) >> 2) + (1 << max(0, bits - 3)) for k in range(4)]
+    large = [(k * maxv) >> 2 for k in range(5)]
+    if len(pixel) == 3 and all(v in small for v in pixel):
+        return small.index(pixel[0]) + 4 * small.index(pixel[1]) + 16 * small.index(pixel[2])
+    if len(pixel) == 3 and all(v in large for v in pixel):
+        return 64 + large.index(pixel[0]) + 5 * large.index(pixel[1]) + 25 * large.index(pixel[2])
+    return None
+
+
+def forward_palette(planes, begin, num_c, colors, bits=8, deltas=(), predictor=0, delta_mask=None):
+    """-> (palette plane: num_c rows of len(deltas) + len(colors) entries, index plane). A pixel takes the index of its colour among `colors`
+    (offset by the delta entries, which come first), else an implicit-cube index. Where delta_mask[y][x] is an int d, the pixel is coded as
+    delta entry d: it must equal prediction + deltas[d] in every channel (the caller builds the image that way)."""
+    h, w = len(planes[begin]), len(planes[begin][0])
+    nd = len(deltas)
+    lut = {tuple(c): nd + i for i, c in enumerate(colors)}
+    idx = [[0] * w for _ in range(h)]
+    for y in range(h):
+        for x in range(w):
+            px = tuple(planes[begin + c][y][x] for c in range(num_c))
+            if delta_mask is not None and delta_mask[y][x] is not None:
+                idx[y][x] = delta_mask[y][x]
+                continue
+            if px in lut:
+                idx[y][x] = lut[px]
+            else:
+                k = implicit_palette_index(px, bits)
+                assert k is not None, "colour %r is neither in the palette nor in the implicit cubes" % (px,)
+                idx[y][x] = nd + len(colors) + k
+    pal = [[d[c] for d in deltas] + [col[c] for col in colors] for c in range(num_c)]
+    return pal, idx
 
 
 # ----------------------------------------------------------------------------- whole files
@@ -668,10 +715,12 @@ def container(codestream, boxes=(), split_at=None, level=None):
 
 
 def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_code=None, rct=None, name=b"", orientation=1,
-                  small_size=True, group_size_shift=1, toc_permutation=None, alpha_associated=False, extra=None, rle=None):
+                  small_size=True, group_size_shift=1, toc_permutation=None, alpha_associated=False, extra=None, rle=None, palette=None):
     """A lossless Modular frame. channels: colour planes (1 or 3) + optional alpha + optional `extra` channels, each a list of rows.
     tree/data_code default to a single gradient-predictor leaf over a flat 256-symbol ANS code. Images larger than one group are
-    written with a real multi-section TOC (each group its own section); toc_permutation reorders the sections in the file."""
+    written with a real multi-section TOC (each group its own section); toc_permutation reorders the sections in the file.
+    palette = dict(begin, num_c, colors, deltas=(), predictor=0, delta_mask=None): a Palette transform (after the RCT, if any): the palette
+    becomes meta channel 0, coded in the global section whatever its size; the index channel takes the place of the colour channels."""
     h, w = len(channels[0]), len(channels[0][0])
     ncolor = 1 if gray else 3
     ecs = []
@@ -699,14 +748,23 @@ def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_co
     code = data_code or EntropyCode([0] * nleaf, [("flat", 256)], log_alpha=8)
     code.write_header(g)
     transforms = [("rct", rct[0], rct[1])] if rct else []
+    if palette:
+        transforms.append(("palette", palette["begin"], palette["num_c"], len(palette["colors"]), len(palette.get("deltas", ())), palette.get("predictor", 0)))
     group_header(g, transforms)
     planes = [[list(r) for r in ch] for ch in channels]
     if rct:
         planes = forward_rct(planes, rct[0], rct[1])
+    nb_meta = 0
+    if palette:
+        pal, idx = forward_palette(planes, palette["begin"], palette["num_c"], palette["colors"], bits, palette.get("deltas", ()), palette.get("predictor", 0), palette.get("delta_mask"))
+        planes = [pal] + planes[:palette["begin"]] + [idx] + planes[palette["begin"] + palette["num_c"]:]
+        nb_meta = 1
     fits = w <= gdim and h <= gdim
     pack = (lambda it: rle_copies(it, rle[0], rle[1])) if rle else (lambda it: it)   # rle = (min run to replace, distance symbol)
     if fits:
         code.write_stream(g, pack(modular_items(tree, planes, 0)))
+    elif nb_meta:
+        code.write_stream(g, pack(modular_items(tree, planes[:nb_meta], 0)))         # meta channels live in the global section
     if ngroups == 1:
         sections = [g.bytes()]
     else:
@@ -716,8 +774,8 @@ def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_co
             s = Bits()
             if not fits:
                 group_header(s)
-                sub = [[row[x0:x0 + gdim] for row in ch[y0:y0 + gdim]] for ch in planes]
-                code.write_stream(s, pack(modular_items(tree, sub, 1 + 3 * nlf + 17 + gi)))
+                sub = [[row[x0:x0 + gdim] for row in ch[y0:y0 + gdim]] for ch in planes[nb_meta:]]
+                code.write_stream(s, pack(modular_items(tree, sub, 1 + 3 * nlf + 17 + gi)))   # channels are numbered from 0 inside a group section
             sections.append(s.bytes())
     # toc_permutation lists the logical section indices in the order they are stored in the file. The TOC codes the sizes in FILE
     # order plus the permutation that maps a logical section to its file slot.

@@ -114,7 +114,51 @@ def cases():
     nl = renumber(tree)
     code = W.EntropyCode(list(range(nl)), [("flat", 64)] * nl, hybrids=[W.Hybrid(4, 2, 0)] * nl, log_alpha=6) if nl <= 8 else None
     out.append(("rgb8_prev_channel_props", W.modular_image(_planes(a), tree=tree, data_code=code, group_size_shift=0), a.astype(np.uint8), dict(width=130, height=140, format="Rgb", num_channels=3)))
+    # 12. Palette (H.6.3): 37 explicit colours + colours of both implicit cubes; the palette is meta channel 0, the index channel replaces R,G,B.
+    #     Single group; then 3 x 2 groups of 128 px (palette in the global section, index channel in the group sections); then with an
+    #     alpha channel behind the palettised colour channels and an RCT applied before the palette.
+    rng = np.random.default_rng(13)
+    explicit = [tuple(int(v) for v in rng.integers(0, 256, size=3)) for _ in range(37)]
+    cube = [(32, 95, 159), (223, 223, 32), (0, 63, 255), (191, 127, 0), (255, 255, 255), (95, 95, 95)]      # 4x4x4 levels 32/95/159/223, 5x5x5 levels 0/63/127/191/255
+    def paletted(hh, ww, seed):
+        r = np.random.default_rng(seed)
+        pick = r.integers(0, len(explicit) + len(cube), size=(hh, ww))
+        pick = np.where(r.random((hh, ww)) < 0.7, np.roll(pick, 1, axis=1), pick)                           # some horizontal coherence
+        table = np.array(explicit + cube, dtype=np.int64)
+        return table[pick]
+    a = paletted(90, 120, 1)
+    tree = W.Split(0, 0, W.Leaf(0, 1), W.Leaf(1, 0))                                                        # ctx 0: indices (channel > 0, predictor W), ctx 1: the palette rows (predictor Zero)
+    code = W.EntropyCode([0, 1], [("flat", 128), ("flat", 256)], hybrids=[W.Hybrid(4, 2, 0), W.Hybrid(4, 2, 0)], log_alpha=8)
+    pal = dict(begin=0, num_c=3, colors=explicit)
+    out.append(("rgb8_palette", W.modular_image(_planes(a), tree=tree, data_code=code, palette=pal), a.astype(np.uint8), dict(width=120, height=90, format="Rgb", num_channels=3)))
+    a = paletted(200, 300, 2)
+    out.append(("rgb8_palette_groups", W.modular_image(_planes(a), tree=tree, data_code=code, palette=pal, group_size_shift=0), a.astype(np.uint8), dict(width=300, height=200, format="Rgb", num_channels=3)))
+    a = np.concatenate([paletted(70, 50, 3), _img(70, 50, 1, seed=14)], axis=2)
+    tree3 = W.Split(0, 1, W.Leaf(0, 5), W.Split(0, 0, W.Leaf(1, 1), W.Leaf(2, 0)))                          # BFS: alpha (gradient), indices (W), palette (Zero)
+    renumber(tree3)
+    code3 = W.EntropyCode([0, 1, 2], [("flat", 256), ("flat", 128), ("flat", 256)], hybrids=[W.Hybrid(4, 2, 0)] * 3, log_alpha=8)
+    out.append(("rgba8_palette_alpha", W.modular_image(_planes(a), alpha_bits=8, tree=tree3, data_code=code3, palette=pal), a.astype(np.uint8), dict(width=50, height=70, format="Rgb", num_channels=4, has_transparency=True)))
+    # 13. Palette with delta entries: the first two entries are deltas added to the W prediction of the reconstructed channel (H.6.3): a
+    #     horizontal ramp is "previous pixel + (1, 2, 3)" / "previous pixel + (-2, 0, 1)" after an explicit first column
+    hh, ww = 24, 40
+    deltas = [(1, 2, 3), (-2, 0, 1)]
+    a = np.zeros((hh, ww, 3), dtype=np.int64)
+    mask = [[None] * ww for _ in range(hh)]
+    starts = [tuple(int(v) for v in rng.integers(60, 120, size=3)) for _ in range(5)]
+    for y in range(hh):
+        a[y, 0] = starts[y % 5]
+        for x in range(1, ww):
+            if (x * 7 + y * 3) % 11 == 0:
+                a[y, x] = starts[(x + y) % 5]
+            else:
+                d = (x + y) % 2
+                a[y, x] = a[y, x - 1] + np.array(deltas[d])
+                mask[y][x] = d
+    assert a.min() >= 0 and a.max() <= 255
+    pald = dict(begin=0, num_c=3, colors=starts, deltas=deltas, predictor=1, delta_mask=mask)
+    out.append(("rgb8_palette_deltas", W.modular_image(_planes(a), tree=tree, data_code=code, palette=pald), a.astype(np.uint8), dict(width=ww, height=hh, format="Rgb", num_channels=3)))
     return out
+
 
 
 def containerised():
