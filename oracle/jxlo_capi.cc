@@ -24,6 +24,7 @@ struct jxlo_encode_params {
   float distance; int32_t effort; int32_t lossless; int32_t gab; int32_t epf; int32_t varblocks; int32_t cfl; int32_t adaptive_quant; int32_t force_strategy;
   int32_t use_prefix; int32_t container; int32_t modular_group_shift; int32_t orientation; int32_t skip_lf_smoothing; int32_t threads;
   int32_t bits; int32_t exp_bits; int32_t color_space; int32_t white_point; int32_t primaries; int32_t tf; int32_t intent; float intensity_target; int32_t premultiplied; int32_t black_channel; int32_t num_passes; int32_t pass_shift; float varblock_scale; int32_t varblock_pattern;
+  int32_t canvas_w, canvas_h, crop_x0, crop_y0, blend_mode, alpha_blend_mode, blend_source, blend_clamp, is_last, save_as_reference, frame_only;
 };
 
 static thread_local std::vector<uint8_t> g_next_icc;
@@ -31,7 +32,7 @@ static void SetErr(char* err, size_t n, const char* msg) { if (err && n) { strnc
 
 void jxlo_default_params(jxlo_encode_params* p) {
   EncodeParams d; memset(p, 0, sizeof(*p)); p->distance = d.distance; p->effort = d.effort; p->gab = -1; p->epf = -1; p->varblocks = -1; p->cfl = -1; p->adaptive_quant = -1; p->force_strategy = -1;
-  p->container = 1; p->modular_group_shift = 1; p->orientation = 1; p->threads = 1; p->bits = 8; p->color_space = 0; p->white_point = 1; p->primaries = 1; p->tf = 13; p->intent = 1; p->intensity_target = 255.f; p->num_passes = 1; p->pass_shift = 1; p->varblock_scale = 1.0f;
+  p->container = 1; p->modular_group_shift = 1; p->orientation = 1; p->threads = 1; p->bits = 8; p->color_space = 0; p->white_point = 1; p->primaries = 1; p->tf = 13; p->intent = 1; p->intensity_target = 255.f; p->num_passes = 1; p->pass_shift = 1; p->varblock_scale = 1.0f; p->is_last = 1;
 }
 
 // pixels: interleaved u8 (is_float=0) or f32 (is_float=1) with num_color + alpha (+black before alpha) channels
@@ -42,6 +43,8 @@ int jxlo_encode(const void* pixels, int is_float, uint32_t width, uint32_t heigh
     p.force_strategy = cp->force_strategy; p.use_prefix = cp->use_prefix != 0; p.container = cp->container != 0; p.modular_group_shift = cp->modular_group_shift; p.orientation = uint32_t(cp->orientation); p.skip_lf_smoothing = cp->skip_lf_smoothing != 0;
     p.threads = cp->threads; p.bd.bits = uint32_t(cp->bits); p.bd.exp_bits = uint32_t(cp->exp_bits); p.bd.float_sample = cp->exp_bits > 0; p.ce.color_space = uint32_t(cp->color_space); p.ce.white_point = uint32_t(cp->white_point);
     p.ce.primaries = uint32_t(cp->primaries); p.ce.tf = uint32_t(cp->tf); p.ce.intent = uint32_t(cp->intent); p.intensity_target = cp->intensity_target; p.premultiplied = cp->premultiplied != 0; p.black_channel = cp->black_channel != 0; p.num_passes = cp->num_passes; p.pass_shift = cp->pass_shift; p.varblock_scale = cp->varblock_scale; p.varblock_pattern = cp->varblock_pattern;
+    p.canvas_w = uint32_t(cp->canvas_w); p.canvas_h = uint32_t(cp->canvas_h); p.crop_x0 = cp->crop_x0; p.crop_y0 = cp->crop_y0; p.blend_mode = uint32_t(cp->blend_mode); p.alpha_blend_mode = uint32_t(cp->alpha_blend_mode);
+    p.blend_source = uint32_t(cp->blend_source); p.blend_clamp = cp->blend_clamp != 0; p.is_last = cp->is_last != 0; p.save_as_reference = uint32_t(cp->save_as_reference); p.frame_only = cp->frame_only != 0;
     EncodeInput in; in.width = width; in.height = height; in.num_color = num_color; in.has_alpha = has_alpha != 0; if (is_float) in.f32 = static_cast<const float*>(pixels); else in.u8 = static_cast<const uint8_t*>(pixels);
     in.exif = exif; in.exif_size = exif_size; in.xmp = xmp; in.xmp_size = xmp_size;
     std::vector<uint8_t> icc; icc.swap(g_next_icc); in.icc = icc.data(); in.icc_size = icc.size();

@@ -23,6 +23,11 @@ struct EncodeParams {
   int num_passes = 1, pass_shift = 1;     // 2 passes: pass 0 carries the quantised coefficients >> pass_shift, pass 1 the remainder (progressive files)
   // source description for non-8-bit sources (tests of 16-bit / float / HDR output paths)
   BitDepth bd; ColorEncoding ce; float intensity_target = 255.f; bool premultiplied = false; bool black_channel = false;
+  // Layers (multi-frame stills): the pixels are one frame of a canvas_w x canvas_h image, placed at (crop_x0, crop_y0) and blended onto reference
+  // slot blend_source with blend_mode (colour) / alpha_blend_mode (alpha channel). frame_only: emit the frame alone (header, TOC, sections), to be
+  // appended to a codestream whose image header was written by an earlier call with the same source description.
+  uint32_t canvas_w = 0, canvas_h = 0; int32_t crop_x0 = 0, crop_y0 = 0; uint32_t blend_mode = 0, alpha_blend_mode = 0, blend_source = 0; bool blend_clamp = false;
+  bool is_last = true; uint32_t save_as_reference = 0; bool frame_only = false;
 };
 struct EncodeInput {
   uint32_t width = 0, height = 0; int num_color = 3; bool has_alpha = false;
@@ -122,6 +127,13 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
   if (in.u8) JXLO_CHECK(!p.bd.float_sample && p.bd.bits == 8, "u8 input requires an 8-bit stream");
 
   FrameHeader fh; fh.encoding = p.lossless ? 1 : 0; fh.name = p.frame_name; fh.ec_upsampling.assign(num_ec, 1); fh.ec_blending.assign(num_ec, BlendingInfo());
+  if (p.canvas_w || p.canvas_h) {   // one layer of a larger (or equal) canvas
+    m.xsize = p.canvas_w; m.ysize = p.canvas_h; fh.have_crop = true; fh.x0 = p.crop_x0; fh.y0 = p.crop_y0; fh.width = in.width; fh.height = in.height;
+  }
+  fh.is_last = p.is_last; fh.save_as_reference = p.is_last ? 0 : p.save_as_reference;
+  { const int alpha_ec = m.alpha_index(); fh.blending.mode = p.blend_mode; fh.blending.source = p.blend_source; fh.blending.clamp = p.blend_clamp; fh.blending.alpha_channel = alpha_ec >= 0 ? uint32_t(alpha_ec) : 0;
+    JXLO_CHECK(!(p.blend_mode == 2 || p.blend_mode == 3) || alpha_ec >= 0, "alpha blending needs an alpha channel");
+    for (int i = 0; i < num_ec; i++) { BlendingInfo& b = fh.ec_blending[i]; b.mode = i == alpha_ec ? p.alpha_blend_mode : p.blend_mode; b.source = p.blend_source; b.clamp = p.blend_clamp; b.alpha_channel = alpha_ec >= 0 ? uint32_t(alpha_ec) : 0; } }
   if (p.lossless) { fh.group_size_shift = uint32_t(p.modular_group_shift); fh.lf.gab = false; fh.lf.epf_iters = 0; }
   else {
     int gab = p.gab >= 0 ? p.gab : (p.effort >= 5 ? 1 : 0); int epf = p.epf;
@@ -294,12 +306,12 @@ inline std::vector<uint8_t> EncodeImage(const EncodeInput& in, const EncodeParam
     if (mg_present[g] && pass + 1 == np) { WriteGroupHeader(bw, plain); WriteTokens(bw, mcode, mg_tokens[g]); } }
 
   // ---- assemble codestream
-  BitWriter cs; cs.Write(16, 0x0AFF); WriteImageHeaders(cs, m); WriteFrameHeader(cs, fh, m);
+  BitWriter cs; if (!p.frame_only) { cs.Write(16, 0x0AFF); WriteImageHeaders(cs, m); } WriteFrameHeader(cs, fh, m);
   std::vector<std::vector<uint8_t>> secs; std::vector<size_t> sizes;
   if (sw.single) { secs.push_back(sw.shared.Finish()); } else for (auto& w : sw.w) secs.push_back(w.Finish());
   for (auto& s : secs) sizes.push_back(s.size());
   WriteToc(cs, sizes); std::vector<uint8_t> out = cs.Finish(); for (auto& s : secs) out.insert(out.end(), s.begin(), s.end());
-  if (!p.container) return out;
+  if (!p.container || p.frame_only) return out;
   // container: always used by the reference (JxlEncoderUseBoxes, N/Encoder/JxlEncoder.cpp:201); Exif / xml boxes uncompressed (:284-310)
   std::vector<uint8_t> file = ContainerPrologue();
   if (in.exif_size) AppendBox(file, "Exif", in.exif, in.exif_size);   // blob already carries the 4-byte TIFF offset (S/Exif/ExifWriter.cs:78-90)

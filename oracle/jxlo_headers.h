@@ -281,9 +281,23 @@ inline void WriteFrameHeader(BitWriter& bw, const FrameHeader& f, const ImageMet
   bw.U32(Val(1), Val(2), Val(3), BitsOffset(3, 4), f.passes.num_passes);
   if (f.passes.num_passes != 1) { bw.U32(Val(0), Val(1), Val(2), BitsOffset(1, 3), f.passes.num_ds); for (uint32_t i = 0; i + 1 < f.passes.num_passes; i++) bw.Write(2, f.passes.shift[i]);
     for (uint32_t i = 0; i < f.passes.num_ds; i++) bw.U32(Val(1), Val(2), Val(4), Val(8), f.passes.downsample[i]); for (uint32_t i = 0; i < f.passes.num_ds; i++) bw.U32(Val(0), Val(1), Val(2), Bits(3), f.passes.last_pass[i]); }
-  bw.Bool(false);                                         // no crop
-  bw.U32(Val(0), Val(1), Val(2), BitsOffset(2, 3), 0); for (size_t i = 0; i < m.ec.size(); i++) bw.U32(Val(0), Val(1), Val(2), BitsOffset(2, 3), 0);
-  bw.Bool(true);                                          // is_last
+  // crop, blending, is_last, save_as_reference: mirrors ReadFrameHeader field by field (regular frames of a still image: no duration)
+  JXLO_CHECK(f.frame_type == kFrameRegular, "the oracle encoder writes regular frames only");
+  bw.Bool(f.have_crop); bool full_frame = true;
+  if (f.have_crop) {
+    auto d = [&](uint32_t v) { bw.U32(Bits(8), BitsOffset(11, 256), BitsOffset(14, 2304), BitsOffset(30, 18688), v); };
+    d(PackSigned(f.x0)); d(PackSigned(f.y0)); d(f.width); d(f.height);
+    full_frame = f.x0 <= 0 && f.y0 <= 0 && int64_t(f.x0) + f.width >= int64_t(m.xsize) && int64_t(f.y0) + f.height >= int64_t(m.ysize);
+  }
+  auto blending = [&](const BlendingInfo& b) {
+    bw.U32(Val(0), Val(1), Val(2), BitsOffset(2, 3), b.mode); const bool have_ec = !m.ec.empty();
+    if (have_ec && (b.mode == 2 || b.mode == 3)) bw.U32(Val(0), Val(1), Val(2), BitsOffset(3, 3), b.alpha_channel);
+    if ((have_ec && (b.mode == 2 || b.mode == 3)) || b.mode == 4) bw.Bool(b.clamp);
+    if (b.mode != 0 || !full_frame) bw.Write(2, b.source);
+  };
+  blending(f.blending); for (size_t i = 0; i < m.ec.size(); i++) blending(i < f.ec_blending.size() ? f.ec_blending[i] : BlendingInfo());
+  bw.Bool(f.is_last);
+  if (!f.is_last) { bw.Write(2, f.save_as_reference); if (f.blending.mode == 0 && full_frame) bw.Bool(f.save_before_ct); }   // can_ref holds: duration is 0
   bw.U32(Val(0), Bits(4), BitsOffset(5, 16), BitsOffset(10, 48), uint32_t(f.name.size())); for (char ch : f.name) bw.Write(8, uint8_t(ch));
   const LoopFilter& l = f.lf; LoopFilter d;
   bool gab_custom = memcmp(l.gab_w, d.gab_w, sizeof(d.gab_w)) != 0;

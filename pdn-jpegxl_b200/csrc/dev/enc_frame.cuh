@@ -32,6 +32,7 @@ void EncLaunchModTokens(const DEncFrame* d, const DEncModStream* streams, uint32
 void EncLaunchAcTokens(const DEncFrame* d, const DEncFrame& h, cudaStream_t st);
 void EncLaunchHistogram(const uint2* tokens, const DEncStream* streams, uint32_t nstreams, uint32_t max_count, uint32_t* hist, cudaStream_t st);
 void EncLaunchAns(const DEncFrame* d, const DEncStream* streams, uint32_t nstreams, const DEncCode* code, uint32_t bits_off, cudaStream_t st);   // stream si reports its bit count in stream_bits[bits_off + si]
+void EncLaunchCompact(const uint8_t* src, const DEncStream* streams, uint32_t nstreams, const uint64_t* bits, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st);
 void LaunchGaborishPlanes(const DFrame* d, const DFrame& h, const float* src, float* dst, cudaStream_t st);
 
 }  // namespace jxlgpu

@@ -225,6 +225,17 @@ __global__ void __launch_bounds__(128) k_enc_ans(const DEncFrame* ep, const DEnc
   if (lane == 0) { if (pos & 31) out[pos >> 5] = carry; e.stream_bits[bits_off + si] = pos; }
 }
 
+// The ANS writer leaves every stream at the start of a slot sized for its worst case (6 bytes per token); the host wants the bytes that
+// were actually written. One CTA per stream copies ceil(bits / 8) bytes, 16 at a time, to its place in a dense buffer (offsets are
+// multiples of 16), so that the device-to-host copy carries the compressed size, not the worst case (r02: 1.6 GB -> 60 MB per 537 MP band).
+__global__ void __launch_bounds__(256) k_enc_compact(const uint8_t* __restrict__ src, const DEncStream* streams, const uint64_t* __restrict__ bits, const uint64_t* __restrict__ dst_off, uint8_t* __restrict__ dst) {
+  const uint32_t si = blockIdx.x; const uint64_t nvec = ((bits[si] + 7) / 8 + 15) / 16;
+  const uint4* s = reinterpret_cast<const uint4*>(src + streams[si].byte_off); uint4* d = reinterpret_cast<uint4*>(dst + dst_off[si]);
+  for (uint64_t i = threadIdx.x; i < nvec; i += 256) d[i] = s[i];
+}
+void EncLaunchCompact(const uint8_t* src, const DEncStream* streams, uint32_t nstreams, const uint64_t* bits, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st) {
+  if (!nstreams) return; k_enc_compact<<<nstreams, 256, 0, st>>>(src, streams, bits, dst_off, dst); CountLaunch();
+}
 void EncLaunchScan(const uint8_t* bgra, uint32_t w, uint32_t h, uint32_t stride, uint32_t* flags, cudaStream_t st) { dim3 grid((w + 255) / 256, h); k_enc_scan<<<grid, 256, 0, st>>>(bgra, w, h, stride, flags); CountLaunch(); }
 void EncLaunchToXyb(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st) { dim3 blk(32, 8), grid((h.xpad + 31) / 32, (h.ext_rows + 7) / 8); k_enc_to_xyb<<<grid, blk, 0, st>>>(d, bgra); CountLaunch(); }
 void EncLaunchToPlanes(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st) { dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8); k_enc_to_planes<<<grid, blk, 0, st>>>(d, bgra); CountLaunch(); }

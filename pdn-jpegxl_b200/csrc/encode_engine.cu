@@ -72,7 +72,12 @@ void QuantizerFromDistance(float d, uint32_t* global_scale, uint32_t* quant_lf, 
 
 // appends `nbits` bits of a byte buffer to a bit writer at any alignment
 void AppendBits(BitWriter& bw, const uint8_t* p, uint64_t nbits) {
-  uint64_t full = nbits / 8; size_t i = 0; for (; i + 7 <= full; i += 7) { uint64_t v = 0; memcpy(&v, p + i, 7); bw.Write(56, v); } for (; i < full; i++) bw.Write(8, p[i]);
+  uint64_t full = nbits / 8; size_t i = 0;
+  if ((bw.pos & 7) == 0 && full) {   // byte-aligned destination (an AC stream opens its section): one memcpy
+    const size_t byte = bw.pos >> 3, need = byte + full + 16; if (bw.buf.size() < need) bw.buf.resize(need * 2, 0);
+    memcpy(&bw.buf[byte], p, full); bw.pos += full * 8; i = full;
+  }
+  for (; i + 7 <= full; i += 7) { uint64_t v = 0; memcpy(&v, p + i, 7); bw.Write(56, v); } for (; i < full; i++) bw.Write(8, p[i]);
   int rem = int(nbits & 7); if (rem) bw.Write(rem, p[full] & ((1u << rem) - 1));
 }
 
@@ -337,7 +342,7 @@ FrameCodes CodesFromHist(const EncPlan& plan, const std::vector<uint64_t>& hist)
 std::vector<BandSection> BandEncoder::Finish(const std::vector<uint64_t>& frame_hist) {
   const bool lossless = plan.lossless; const uint32_t nlf = fb.num_lf_groups, ng = fb.num_groups;
   FrameCodes codes = CodesFromHist(plan, frame_hist);
-  std::vector<uint64_t> bits_m(m_streams.size(), 0), bits_a(ng, 0); std::vector<uint8_t> bytes(byte_cursor);
+  std::vector<uint64_t> bits_m(m_streams.size(), 0), bits_a(ng, 0), dense_off; std::vector<uint8_t> bytes;
   {
     Timer t(st, &device_ms);
     DeviceEncCode dm, da; UploadEncCode(codes.mcode, &dm, st); if (!lossless) UploadEncCode(codes.acode, &da, st);
@@ -352,21 +357,30 @@ std::vector<BandSection> BandEncoder::Finish(const std::vector<uint64_t>& frame_
     if (nm) CUDA_OK(cudaMemcpyAsync(bits_m.data(), e.stream_bits, size_t(nm) * 8, cudaMemcpyDeviceToHost, st));
     if (!lossless) CUDA_OK(cudaMemcpyAsync(bits_a.data(), e.stream_bits + nm, size_t(ng) * 8, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st)); cudaStreamDestroy(st2); cudaEventDestroy(ready); cudaEventDestroy(done2);
-    if (byte_cursor) CUDA_OK(cudaMemcpyAsync(bytes.data(), d_bytes.p, byte_cursor, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+    // dense copy of what was written: stream k (Modular streams first, then AC) lands at dense_off[k] of `bytes`
+    const size_t ns = size_t(nm) + (lossless ? 0 : ng); dense_off.assign(ns + 1, 0);
+    for (size_t k = 0; k < ns; k++) { const uint64_t b = k < nm ? bits_m[k] : bits_a[k - nm]; dense_off[k + 1] = dense_off[k] + ((b + 7) / 8 + 15) / 16 * 16; }
+    bytes.assign(dense_off[ns], 0);
+    if (dense_off[ns]) {
+      Buf d_off, d_dense; d_off.Alloc(ns * 8); d_dense.Alloc(dense_off[ns]);
+      CUDA_OK(cudaMemcpyAsync(d_off.p, dense_off.data(), ns * 8, cudaMemcpyHostToDevice, st));
+      EncLaunchCompact(e.stream_bytes, d_m, uint32_t(ns), e.stream_bits, d_off.as<uint64_t>(), d_dense.as<uint8_t>(), st);
+      CUDA_OK(cudaMemcpyAsync(bytes.data(), d_dense.p, dense_off[ns], cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+    }
   }
   std::vector<BandSection> out;
   auto emit = [&](uint32_t kind, uint32_t index, BitWriter& bw) { BandSection s; s.kind = kind; s.index = index; s.bits = bw.pos; s.bytes = bw.Finish(); out.push_back(std::move(s)); };
-  if (plan.global_has_modular) { BitWriter bw; const DEncStream& s = m_streams[first_group_stream]; AppendBits(bw, &bytes[s.byte_off], bits_m[first_group_stream]); emit(0, 0, bw); }
+  if (plan.global_has_modular) { BitWriter bw; const DEncStream& s = m_streams[first_group_stream]; (void)s; AppendBits(bw, &bytes[dense_off[first_group_stream]], bits_m[first_group_stream]); emit(0, 0, bw); }
   if (!lossless) for (uint32_t g = 0; g < nlf; g++) {
-    BitWriter bw; bw.Write(2, 0); WriteGroupHeader(bw, plan.plain); AppendBits(bw, &bytes[m_streams[first_lf_stream + g].byte_off], bits_m[first_lf_stream + g]);
+    BitWriter bw; bw.Write(2, 0); WriteGroupHeader(bw, plan.plain); AppendBits(bw, &bytes[dense_off[first_lf_stream + g]], bits_m[first_lf_stream + g]);
     const uint32_t gx = g % fb.xlfgroups, gy = g / fb.xlfgroups; const uint64_t wh = uint64_t(std::min<uint32_t>(256, e.xb - gx * 256)) * std::min<uint32_t>(256, e.yb - gy * 256);
     bw.Write(CeilLog2(wh), hfmeta_nb[g] - 1); WriteGroupHeader(bw, plan.plain); WriteTokens(bw, codes.mcode, hfmeta_tokens[g]);
     emit(1, lf_group0 + g, bw);
   }
   for (uint32_t g = 0; g < ng; g++) {
     BitWriter bw;
-    if (!lossless) AppendBits(bw, &bytes[a_streams[g].byte_off], bits_a[g]);
-    if (plan.groups_have_modular) { WriteGroupHeader(bw, plan.plain); AppendBits(bw, &bytes[m_streams[first_group_stream + g].byte_off], bits_m[first_group_stream + g]); }
+    if (!lossless) AppendBits(bw, &bytes[dense_off[m_streams.size() + g]], bits_a[g]);
+    if (plan.groups_have_modular) { WriteGroupHeader(bw, plan.plain); AppendBits(bw, &bytes[dense_off[first_group_stream + g]], bits_m[first_group_stream + g]); }
     emit(2, group0 + g, bw);
   }
   return out;

@@ -28,7 +28,8 @@ class EncodeParams(C.Structure):
     _fields_ = [("distance", C.c_float)] + [(n, C.c_int32) for n in (
         "effort", "lossless", "gab", "epf", "varblocks", "cfl", "adaptive_quant", "force_strategy", "use_prefix", "container",
         "modular_group_shift", "orientation", "skip_lf_smoothing", "threads", "bits", "exp_bits", "color_space", "white_point",
-        "primaries", "tf", "intent")] + [("intensity_target", C.c_float), ("premultiplied", C.c_int32), ("black_channel", C.c_int32), ("num_passes", C.c_int32), ("pass_shift", C.c_int32), ("varblock_scale", C.c_float), ("varblock_pattern", C.c_int32)]
+        "primaries", "tf", "intent")] + [("intensity_target", C.c_float), ("premultiplied", C.c_int32), ("black_channel", C.c_int32), ("num_passes", C.c_int32), ("pass_shift", C.c_int32), ("varblock_scale", C.c_float), ("varblock_pattern", C.c_int32)] + [
+        (n, C.c_int32) for n in ("canvas_w", "canvas_h", "crop_x0", "crop_y0", "blend_mode", "alpha_blend_mode", "blend_source", "blend_clamp", "is_last", "save_as_reference", "frame_only")]
 
 
 _lib = None
@@ -114,6 +115,23 @@ def encode(pixels, num_color=None, has_alpha=None, exif=b"", xmp=b"", icc=b"", *
     data = C.string_at(out, n.value)
     lib().jxlo_free(out)
     return data
+
+
+BLEND = dict(replace=0, add=1, blend=2, muladd=3, mul=4)
+
+
+def encode_layers(canvas_w, canvas_h, layers, **common):
+    """A multi-frame still: layers = [(pixels, dict(x0=, y0=, mode=, alpha_mode=, source=, save=, clamp=))...], every layer a regular frame
+    of zero duration, the last one is_last. All layers share the source description in `common` (bit depth, colour, lossless / effort ...).
+    Returns a bare codestream (no container)."""
+    out = b""
+    for i, (px, kw) in enumerate(layers):
+        last = i + 1 == len(layers)
+        out += encode(px, container=0, canvas_w=canvas_w, canvas_h=canvas_h, crop_x0=kw.get("x0", 0), crop_y0=kw.get("y0", 0),
+                      blend_mode=BLEND[kw.get("mode", "replace")], alpha_blend_mode=BLEND[kw.get("alpha_mode", kw.get("mode", "replace"))],
+                      blend_source=kw.get("source", 0), blend_clamp=int(kw.get("clamp", False)), is_last=int(last), save_as_reference=kw.get("save", 0),
+                      frame_only=int(i > 0), **common)
+    return out
 
 
 def last_encode_strategy_cells():
