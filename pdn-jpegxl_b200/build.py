@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libJpegXLFileTypeIO_X64.so")
-SOURCES = ["abi.cu", "decode_engine.cu", "encode_engine.cu", "dev/entropy_kernels.cu", "dev/recon_kernels.cu", "dev/encode_kernels.cu", "dev/layer_kernels.cu"]
+SOURCES = ["abi.cu", "decode_engine.cu", "encode_engine.cu", "dev/entropy_kernels.cu", "dev/recon_kernels.cu", "dev/encode_kernels.cu", "dev/layer_kernels.cu", "dev/composite_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-sign-compare,-Wno-unused-function,-Wno-misleading-indentation",
               "-diag-suppress", "177,550"]

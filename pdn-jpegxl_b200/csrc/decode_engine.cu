@@ -78,7 +78,8 @@ void DumpPoolStats() { Pool& d = DevPool(); Pool& h = HostPool(); fprintf(stderr
 void* PinnedGet(size_t bytes) { return HostPool().Get(bytes ? bytes : 1); }
 void PinnedPut(void* p, size_t bytes) { HostPool().Put(p, bytes ? bytes : 1); }
 
-struct DevBuf { void* p = nullptr; size_t n = 0; bool host = false; Pool* pool = nullptr; void Alloc(size_t bytes, bool pinned = false) { Free(); host = pinned; n = bytes ? bytes : 1; pool = pinned ? &HostPool() : &DevPool(); p = pool->Get(n); } void Free() { if (p) pool->Put(p, n); p = nullptr; n = 0; } ~DevBuf() { Free(); } template <class T> T* as() const { return static_cast<T*>(p); } };
+struct DevBuf { void* p = nullptr; size_t n = 0; bool host = false; Pool* pool = nullptr; void Alloc(size_t bytes, bool pinned = false) { Free(); host = pinned; n = bytes ? bytes : 1; pool = pinned ? &HostPool() : &DevPool(); p = pool->Get(n); } void Free() { if (p) pool->Put(p, n); p = nullptr; n = 0; } ~DevBuf() { Free(); } DevBuf() {} DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+  void Swap(DevBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(host, o.host); std::swap(pool, o.pool); } template <class T> T* as() const { return static_cast<T*>(p); } };
 
 static const DTables* DeviceTables() {
   static std::mutex mu; static std::map<int, DTables*> per_dev; std::lock_guard<std::mutex> lk(mu); int dev = 0; CUDA_OK(cudaGetDevice(&dev));
@@ -104,6 +105,13 @@ static std::vector<uint8_t> BrotliDecompress(const uint8_t* data, size_t size) {
   JXLG_CHECK(fn != nullptr, "brob box: libbrotlidec.so.1 not available");
   for (size_t cap = std::max<size_t>(size * 8, 1 << 16); cap <= (size_t(1) << 31); cap *= 4) { std::vector<uint8_t> out(cap); size_t n = cap; if (fn(size, data, &n, out.data()) == 1) { out.resize(n); return out; } }
   throw Error("brob box: brotli stream invalid or too large");
+}
+
+// A frame that is shown as it is: full canvas, replaces what was there, and the first frame the reference would receive as a full image.
+static bool FrameIsPlain(const FrameHeader& fh, const ImageMetadata& m) {
+  const bool shown = (fh.frame_type == kFrameRegular || fh.frame_type == kFrameSkipProgressive) && (fh.is_last || fh.duration > 0);
+  const bool full = !fh.have_crop || (fh.x0 <= 0 && fh.y0 <= 0 && int64_t(fh.x0) + fh.width >= int64_t(m.xsize) && int64_t(fh.y0) + fh.height >= int64_t(m.ysize));
+  return shown && full && fh.blending.mode == 0;
 }
 
 // ---------------------------------------------------------------- pass 1: info + metadata
@@ -218,8 +226,8 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 // ---------------------------------------------------------------- the job
 class DecodeJob {
  public:
-  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false; uint64_t mod_total_ints = 0;   /* int32 samples of all Modular planes: coded channels + the outputs of palette expansions */
-  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend, d_lz;
+  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false, layer = false; uint64_t mod_total_ints = 0;   /* int32 samples of all Modular planes: coded channels + the outputs of palette expansions */
+  DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend, d_lz, d_layer_out, h_layer_out;   /* *_layer_out: the finished canvas of a layered file (owned by the job of the frame that is shown) */
   std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false; size_t coeffs_bytes = 0, xyb_row_shift = 0;
   bool defer_entropy = false, lf_pending = false, ac_pending = false;   // bundle mode: the LF / AC entropy launch is left to DecodeBundleLaunch*
   cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {nullptr}; bool timed = false; size_t out_bytes = 0; size_t comp_size = 0; const uint8_t* frame_ptr = nullptr; size_t frame_off = 0;
@@ -346,12 +354,15 @@ void DecodeJob::ParseHfGlobal(BitReader& br) {
 }
 
 void DecodeJob::Setup(const DecodeRequest& req) {
-  const ImageMetadata& m = hd.meta; const ByteSpan& cs = hd.ci.codestream; size_t pos = hd.frame_pos;
-  if (m.have_preview) { ImageMetadata pm = m; pm.xsize = m.preview_x; pm.ysize = m.preview_y; BitReader br(cs.data() + pos, cs.size() - pos); FrameHeader pf = ReadFrameHeader(br, pm); Toc t = ReadToc(br, pf); pos += br.pos / 8 + t.total; JXLG_CHECK(pos <= cs.size(), "preview frame truncated"); }
+  const ImageMetadata& m = hd.meta; const ByteSpan& cs = hd.ci.codestream; size_t pos = req.layer ? req.layer_pos : hd.frame_pos; layer = req.layer;
+  if (m.have_preview && !req.layer) { ImageMetadata pm = m; pm.xsize = m.preview_x; pm.ysize = m.preview_y; BitReader br(cs.data() + pos, cs.size() - pos); FrameHeader pf = ReadFrameHeader(br, pm); Toc t = ReadToc(br, pf); pos += br.pos / 8 + t.total; JXLG_CHECK(pos <= cs.size(), "preview frame truncated"); }
   BitReader br(cs.data() + pos, cs.size() - pos); fh = ReadFrameHeader(br, m);
-  JXLG_CHECK(fh.frame_type == kFrameRegular || fh.frame_type == kFrameSkipProgressive, "reference-only / LF frames are not supported");
+  JXLG_CHECK(fh.frame_type != kFrameLF, "LF frames are not supported");
   JXLG_CHECK(fh.upsampling == 1, "upsampling is not supported"); JXLG_CHECK(!fh.do_ycbcr, "YCbCr (JPEG-recompressed) frames are not supported");
-  JXLG_CHECK(!fh.have_crop || (fh.x0 == 0 && fh.y0 == 0 && fh.width == m.xsize && fh.height == m.ysize), "cropped frames are not supported");
+  if (!req.layer) {   // the plain single-frame file; layered files go through DecodeOnGpu's compositing loop, which sets req.layer for every frame
+    const bool full = !fh.have_crop || (fh.x0 == 0 && fh.y0 == 0 && fh.width == m.xsize && fh.height == m.ysize);
+    JXLG_CHECK(FrameIsPlain(fh, m) && full, "layered (multi-frame) files are decoded by LoadImage / JxlB200LoadImageBgra only, not by the batch and band calls");
+  }
   JXLG_CHECK(fh.passes.num_passes <= uint32_t(kMaxPasses), "too many passes");
   JXLG_CHECK(fh.encoding != 0 || m.xyb_encoded, "VarDCT frames that are not XYB-encoded are not supported");
   toc = ReadToc(br, fh); frame_off = pos + br.pos / 8; JXLG_CHECK(frame_off + toc.total <= cs.size(), "JxlDecoderProcessInput needs more input, but it already received the entire image.");
@@ -400,6 +411,10 @@ void DecodeJob::Setup(const DecodeRequest& req) {
   o.alpha_plane = alpha >= 0 ? int32_t(ec_base + alpha) : -1; o.black_plane = info.format == 2 ? int32_t(ec_base + black) : -1; o.premultiplied = alpha >= 0 && m.ec[alpha].alpha_associated;
   if (alpha >= 0) { o.alpha_bits = m.ec[alpha].bd.bits; o.alpha_exp_bits = m.ec[alpha].bd.exp_bits; } if (black >= 0) o.black_bits = m.ec[black].bd.bits;
   if (bgra) JXLG_CHECK(info.format != 2, "BGRA surface output is not defined for CMYK images");
+  if (layer) {   // float samples of the frame itself; orientation, unpremultiply and the sample type are applied to the finished canvas
+    JXLG_CHECK(info.format != 2, "multi-frame CMYK images are not supported");
+    o.sample_type = 3; o.orientation = 1; o.premultiplied = 0; o.bgra = 0; bgra = false; device_output = true; o.out_w = fh.xsize; o.out_h = fh.ysize;
+  }
   for (size_t i = 0; i < m.ec.size(); i++) JXLG_CHECK(m.ec[i].dim_shift < 3, "extra channels with dim_shift >= 3 (Modular LF-group data) are not supported by the GPU decoder yet");
 }
 
@@ -604,6 +619,65 @@ void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res) {
     res->times.lf = ms(0, 1); res->times.ac = ms(1, 2); res->times.recon = ms(2, 3); res->times.filters = ms(3, 4); res->times.output = ms(4, 5); res->times.d2h = ms(5, 6); res->times.total = ms(0, 6); }
 }
 
+// Position of the first frame after an optional preview frame, and whether that frame is a plain single-frame image.
+static bool FirstFrameIsPlain(const Headers& hd, size_t* first_pos) {
+  const ImageMetadata& m = hd.meta; const ByteSpan& cs = hd.ci.codestream; size_t pos = hd.frame_pos;
+  if (m.have_preview) { ImageMetadata pm = m; pm.xsize = m.preview_x; pm.ysize = m.preview_y; BitReader br(cs.data() + pos, cs.size() - pos); FrameHeader pf = ReadFrameHeader(br, pm); Toc t = ReadToc(br, pf); pos += br.pos / 8 + t.total; JXLG_CHECK(pos <= cs.size(), "preview frame truncated"); }
+  *first_pos = pos; BitReader br(cs.data() + pos, cs.size() - pos); FrameHeader fh = ReadFrameHeader(br, m);
+  const bool exact = !fh.have_crop || (fh.x0 == 0 && fh.y0 == 0 && fh.width == m.xsize && fh.height == m.ysize);
+  return FrameIsPlain(fh, m) && exact;
+}
+
+// Layered stills (N/Decoder/JxlDecoder.cpp:252-400: the reference takes the first full image of a coalescing decoder). Every frame up to the
+// first one that is shown is decoded by the ordinary pipeline into float samples and blended onto a canvas-sized float image that starts as a
+// copy of the frame's source slot (dev/composite_kernels.cu); frames that may be referenced leave their result in a slot. The canvas that is
+// shown becomes the output: unpremultiply, sample type, orientation. Reference-only frames saved before the colour transform can only feed
+// patches (rejected) and are skipped.
+static void DecodeLayered(const DecodeRequest& req, size_t pos, cudaStream_t st, DecodeResult* res) {
+  struct SlotBuf { DevBuf buf; bool valid = false; }; SlotBuf slots[4]; ParsedInfo info;
+  for (int guard = 0; guard < 4096; guard++) {
+    std::shared_ptr<DecodeJob> job = std::make_shared<DecodeJob>(); job->stream = st;
+    Status hs = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res->message); if (hs != Status::Ok) { res->status = hs; return; }
+    const ImageMetadata& m = job->hd.meta; const ByteSpan& cs = job->hd.ci.codestream; info = job->info;
+    JXLG_CHECK(pos < cs.size(), "JxlDecoderProcessInput needs more input, but it already received the entire image.");
+    BitReader br(cs.data() + pos, cs.size() - pos); const FrameHeader fh = ReadFrameHeader(br, m); const Toc toc = ReadToc(br, fh); const size_t next = pos + br.pos / 8 + toc.total;
+    JXLG_CHECK(next <= cs.size(), "JxlDecoderProcessInput needs more input, but it already received the entire image.");
+    JXLG_CHECK(fh.frame_type != kFrameLF, "LF frames are not supported");
+    const bool ref_only = fh.frame_type == kFrameReferenceOnly;
+    if (ref_only && fh.save_before_ct) { pos = next; continue; }
+    const bool shown = !ref_only && (fh.is_last || fh.duration > 0);
+    const int alpha = info.has_alpha ? m.alpha_index() : -1; const BlendingInfo cb = fh.blending, ab = alpha >= 0 ? fh.ec_blending[alpha] : BlendingInfo();
+    JXLG_CHECK(!(cb.mode == 2 || cb.mode == 3) || (alpha >= 0 && int(cb.alpha_channel) == alpha), "blending needs the image's alpha channel");
+    JXLG_CHECK(alpha < 0 || ref_only || ab.source == cb.source, "colour and alpha blended from different reference slots are not supported");
+    DecodeRequest r = req; r.layer = true; r.layer_pos = pos; r.device_output = true; r.out_device = nullptr; r.out_pinned = nullptr; r.bgra = false; r.band_begin = r.band_end = 0; r.device_input = nullptr;
+    job->Setup(r); job->Run(r); DecodeResult fr; DecodeFinish(job, &fr);
+    if (fr.status != Status::Ok) { res->status = fr.status; res->message = fr.message; res->info = info; return; }
+    const int W = int(m.xsize), H = int(m.ysize), C = info.num_channels, cc = int(m.num_color_channels()); const size_t canvas_bytes = size_t(W) * H * C * sizeof(float);
+    DevBuf canvas; canvas.Alloc(canvas_bytes);
+    if (!ref_only && slots[cb.source].valid) CUDA_OK(cudaMemcpyAsync(canvas.p, slots[cb.source].buf.p, canvas_bytes, cudaMemcpyDeviceToDevice, st)); else CUDA_OK(cudaMemsetAsync(canvas.p, 0, canvas_bytes, st));
+    const bool premul = alpha >= 0 && m.ec[alpha].alpha_associated;
+    LaunchBlendLayer(canvas.as<float>(), reinterpret_cast<const float*>(fr.pixels), W, H, int(fh.xsize), int(fh.ysize), ref_only ? 0 : fh.x0, ref_only ? 0 : fh.y0, C, cc,
+                     ref_only ? 0u : cb.mode, ref_only ? 0u : ab.mode, cb.clamp, ab.clamp, premul, st);
+    if (shown) {
+      const uint32_t ori = m.orientation; const size_t bps = req.bgra ? 1 : (info.sample_type == 0 ? 1 : info.sample_type == 3 ? 4 : 2); const size_t chans = req.bgra ? 4 : size_t(C);
+      const size_t out_bytes = size_t(W) * H * bps * chans;
+      if (req.out_device || req.out_pinned) JXLG_CHECK(req.out_capacity >= out_bytes, "output buffer too small");
+      uint8_t* d_final = req.out_device; if (!d_final) { job->d_layer_out.Alloc(out_bytes); d_final = job->d_layer_out.as<uint8_t>(); }
+      LaunchFinalizeCanvas(canvas.as<float>(), d_final, W, H, C, cc, premul, uint32_t(info.sample_type), ori, req.bgra, st);
+      uint8_t* host = nullptr;
+      if (!req.device_output) { host = req.out_pinned; if (!host) { job->h_layer_out.Alloc(out_bytes, true); host = job->h_layer_out.as<uint8_t>(); } CUDA_OK(cudaMemcpyAsync(host, d_final, out_bytes, cudaMemcpyDeviceToHost, st)); }
+      CUDA_OK(cudaStreamSynchronize(st));
+      info.frame_name = fh.name; res->status = Status::Ok; res->info = info; res->pixels = req.device_output ? d_final : host; res->pixel_bytes = out_bytes;
+      res->out_width = ori >= 5 ? uint32_t(H) : uint32_t(W); res->out_height = ori >= 5 ? uint32_t(W) : uint32_t(H); res->job = job; return;
+    }
+    CUDA_OK(cudaStreamSynchronize(st));   // the frame's buffers go back to the pools with the job
+    const bool can_ref = ref_only || (!fh.is_last && (fh.duration == 0 || fh.save_as_reference != 0));
+    if (can_ref) { SlotBuf& s = slots[fh.save_as_reference]; s.buf.Free(); s.buf.Swap(canvas); s.valid = true; }
+    pos = next;
+  }
+  throw Error("too many frames before the first one that is shown");
+}
+
 DecodeResult DecodeOnGpu(const DecodeRequest& req) {
   DecodeResult res; cudaStream_t st = nullptr;
   std::string why; if (!req.data) { res.status = Status::NullParameter; return res; }
@@ -620,7 +694,11 @@ DecodeResult DecodeOnGpu(const DecodeRequest& req) {
     try {
       job = std::make_shared<DecodeJob>(); job->stream = st; Timed::Enable(job.get());
       res.status = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res.message);
-      if (res.status == Status::Ok) { job->Setup(req); job->Run(req); DecodeFinish(job, &res); }
+      if (res.status == Status::Ok) {
+        size_t first_pos = 0; const bool plain = FirstFrameIsPlain(job->hd, &first_pos);
+        if (plain || req.band_begin || req.band_end) { job->Setup(req); job->Run(req); DecodeFinish(job, &res); }
+        else { job.reset(); DecodeLayered(req, first_pos, st, &res); }
+      }
     } catch (const std::bad_alloc&) { res.status = Status::OutOfMemory; }
     catch (const std::exception& e) { res.status = Status::DecodeError; res.message = e.what(); if (job) res.info = job->info; }
     if (res.status != Status::Ok) cudaStreamSynchronize(st);

@@ -18,6 +18,9 @@ bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st);      
 void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st);
 void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st);            // colour transform + sample conversion + interleave (+BGRA)
 void LaunchSplitLayers(const void* src, void* color, uint8_t* alpha, size_t npix, int format, int sample_type, bool has_alpha, cudaStream_t st);   // I/DecoderLayerData.cs repack
+// layers of a multi-frame still (dev/composite_kernels.cu): float canvas [H][W][C], frame [fh][fw][C]
+void LaunchBlendLayer(float* canvas, const float* frame, int W, int H, int fw, int fh, int x0, int y0, int C, int cc, uint32_t cmode, uint32_t amode, bool cclamp, bool aclamp, bool premultiplied, cudaStream_t st);
+void LaunchFinalizeCanvas(const float* canvas, uint8_t* out, int W, int H, int C, int cc, bool premultiplied, uint32_t sample_type, uint32_t orientation, bool bgra, cudaStream_t st);
 void FillDeviceTables(DTables* host_tables);
 int LaunchCount();                                                                 // kernels launched by this process so far (bench gpu_launches)
 void CountLaunch(int n = 1);

@@ -31,6 +31,9 @@ struct DecodeRequest {
   uint8_t* out_pinned = nullptr;    // optional: copy the pixels straight into this page-locked host buffer (out_capacity bytes)
   size_t out_capacity = 0;
   uint32_t band_begin = 0, band_end = 0;   // band decode: output only group rows [band_begin, band_end) of the frame (0,0 = whole frame); needs orientation 1
+  // Layer of a multi-frame still (internal, set by DecodeOnGpu): decode the frame whose header starts at byte layer_pos of the codestream into float
+  // samples of the output encoding (interleaved colour [+ alpha], the frame's own size, device memory): no orientation, no unpremultiply.
+  bool layer = false; size_t layer_pos = 0;
   int ac_lanes = 0;                 // AC sections walked per warp (power of two, 1..32); 0: 1 (lowest latency). Batches raise it for throughput.
 };
 

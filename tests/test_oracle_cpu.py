@@ -245,3 +245,24 @@ def test_icc_profile_travels_through_the_codestream(oracle):
     img = oracle.synthetic_image(96, 64, seed=9)
     d = oracle.decode(oracle.encode(img, lossless=True, icc=icc))
     assert d.icc == icc and d.known_profile == -1 and np.array_equal(d.pixels, img)
+
+
+@pytest.mark.parametrize("mode", ["replace", "add", "blend", "muladd", "mul"])
+def test_layered_files_decode_to_the_blend_formulas(oracle, mode):
+    """Multi-frame stills (layers): the oracle's compositing loop against a numpy statement of the blend modes, crops inside and across the
+    canvas border, and a third layer that blends onto a reference slot other than the one the second layer wrote."""
+    import layer_util as L
+    W, H = 160, 120
+    base = oracle.synthetic_image(W, H, seed=1, channels=4)
+    base[..., 3] = np.maximum(base[..., 3], 100)
+    over = oracle.synthetic_image(70, 50, seed=2, channels=4)
+    for x0, y0 in ((30, 20), (-20, 90), (120, -10)):
+        data = oracle.encode_layers(W, H, [(base, dict()), (over, dict(x0=x0, y0=y0, mode=mode))], lossless=1)
+        got = oracle.decode(data).pixels
+        want = L.to_u8(L.composite(base.astype(np.float32) / 255.0, over.astype(np.float32) / 255.0, x0, y0, mode))
+        assert got.shape == (H, W, 4) and int(np.abs(got.astype(np.int32) - want.astype(np.int32)).max()) == 0
+    other = oracle.synthetic_image(W, H, seed=3, channels=4)
+    layers = [(base, dict(save=1)), (other, dict(source=2, save=2, mode="add")), (over, dict(x0=40, y0=30, source=1, mode=mode))]
+    got = oracle.decode(oracle.encode_layers(W, H, layers, lossless=1)).pixels
+    want = L.to_u8(L.composite(base.astype(np.float32) / 255.0, over.astype(np.float32) / 255.0, 40, 30, mode))
+    assert int(np.abs(got.astype(np.int32) - want.astype(np.int32)).max()) == 0
