@@ -16,6 +16,9 @@ struct DEncFrame {
   uint32_t ext_top, ext_rows; int32_t src_row_min, src_row_max;
   float* xyb; int32_t* planes; float* lf; int32_t* lfq; int16_t* coeffs; uint8_t* nz; const float* dequant8; const uint16_t* order8; const DTables* tables;
   const float* src_lut; float src_matrix[9]; uint32_t has_src_profile, pad0;   // ICC-described source: per-channel tone LUT [3][256] + matrix to linear sRGB (null / 0: sRGB input)
+  // Effort >= 5 (null otherwise): per-block quantiser multiplier (adaptive quantisation) and per-64x64-tile chroma-from-luma factors, both
+  // derived on the device from block statistics (k_enc_block_stats, k_enc_tile_params) and coded in the HF metadata.
+  uint8_t* hf_mul_map; int8_t* ytox_map; int8_t* ytob_map; float* block_stats; uint32_t xt, yt; float aq_ref; uint32_t aq_on, cfl_on, pad1;
   uint2* tokens; uint64_t ac_token_off; uint32_t* ac_token_count; uint8_t* stream_bytes; uint64_t* stream_bits;
 };
 struct DEncModStream { uint32_t x0, y0, w, h, kind, pad; uint64_t token_off; };
@@ -28,6 +31,7 @@ void EncLaunchToXyb(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra,
 void EncLaunchToPlanes(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st);
 void EncLaunchSharpen(float* cur, const float* orig, const float* blur, size_t n, cudaStream_t st);
 void EncLaunchDct8(const DEncFrame* d, const DEncFrame& h, cudaStream_t st);
+void EncLaunchBlockParams(const DEncFrame* d, const DEncFrame& h, cudaStream_t st);   // block statistics -> hf_mul_map, ytox_map, ytob_map (before EncLaunchDct8)
 void EncLaunchModTokens(const DEncFrame* d, const DEncModStream* streams, uint32_t nstreams, uint32_t max_tokens, const int32_t* planes, uint32_t pw, uint32_t ph, uint32_t nch, const uint16_t* leaf_lut, cudaStream_t st);
 void EncLaunchAcTokens(const DEncFrame* d, const DEncFrame& h, cudaStream_t st);
 void EncLaunchHistogram(const uint2* tokens, const DEncStream* streams, uint32_t nstreams, uint32_t max_count, uint32_t* hist, cudaStream_t st);

@@ -52,22 +52,67 @@ __global__ void k_enc_sharpen(float* __restrict__ cur, const float* __restrict__
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i < n) cur[i] += orig[i] - blur[i];
 }
 
+// Forward DCT8 of one block in the storage layout of square blocks (S[hf * 8 + vf]); S[0] is the LF sample.
+__device__ __forceinline__ void ForwardDct8(const float* px, size_t stride, const float* cos8, float* S) {
+  float t[64];
+  for (int y = 0; y < 8; y++) { float v[8]; for (int x = 0; x < 8; x++) v[x] = px[size_t(y) * stride + x]; for (int k = 0; k < 8; k++) { float a = 0; for (int x = 0; x < 8; x++) a += v[x] * cos8[k * 8 + x]; t[y * 8 + k] = a * 0.125f; } }
+  for (int hf = 0; hf < 8; hf++) for (int vf = 0; vf < 8; vf++) { float a = 0; for (int y = 0; y < 8; y++) a += t[y * 8 + hf] * cos8[vf * 8 + y]; S[hf * 8 + vf] = a * 0.125f; }
+}
+
+// Effort >= 5, step 1: per-block statistics of the unquantised coefficients — activity (sum of |AC| of Y) and the three sums of the
+// least-squares chroma-from-luma fit over the AC coefficients. One thread per block; block_stats[cell] = {activity, sum X*Y, sum B*Y, sum Y*Y}.
+__global__ void __launch_bounds__(64) k_enc_block_stats(const DEncFrame* ep) {
+  const DEncFrame& e = *ep; const int cell = blockIdx.x * blockDim.x + threadIdx.x; if (cell >= int(e.xb * e.yb)) return;
+  const int cy = cell / int(e.xb), cx = cell % int(e.xb); const float* cos8 = e.tables->cosines + CosOff(3); const size_t plane = size_t(e.xpad) * e.ext_rows;
+  const float* base = e.xyb + (size_t(e.ext_top) + size_t(cy) * 8) * e.xpad + size_t(cx) * 8; float Y[64], C[64];
+  ForwardDct8(base + plane, e.xpad, cos8, Y);
+  float act = 0, syy = 0; for (int k = 1; k < 64; k++) { act += fabsf(Y[k]); syy += Y[k] * Y[k]; }
+  ForwardDct8(base, e.xpad, cos8, C); float sxy = 0; for (int k = 1; k < 64; k++) sxy += C[k] * Y[k];
+  ForwardDct8(base + 2 * plane, e.xpad, cos8, C); float sby = 0; for (int k = 1; k < 64; k++) sby += C[k] * Y[k];
+  reinterpret_cast<float4*>(e.block_stats)[cell] = make_float4(act, sxy, sby, syy);
+}
+// Step 2: one warp per 64x64 tile (8 x 8 blocks, two per lane, summed in a fixed order: the result does not depend on scheduling).
+//   chroma from luma: ytox = round(84 * sum(XY) / sum(YY)), ytob = round(84 * (sum(BY) / sum(YY) - 1))   (kx = ytox / 84, kb = 1 + ytob / 84)
+//   adaptive quantisation: the block's multiplier is the frame's base multiplier times (aq_ref / activity)^0.2, limited to [0.75, 1.35] and
+//   snapped to five levels (the map costs < 0.02 bpp): finer steps where the block is smooth, coarser where texture masks the error.
+//   aq_ref is a constant of the encoder, not a statistic of the frame, so bands of a sharded encode need no exchange for it.
+__global__ void __launch_bounds__(128) k_enc_tile_params(const DEncFrame* ep) {
+  const DEncFrame& e = *ep; const int lane = threadIdx.x & 31; const uint32_t tile = blockIdx.x * 4 + (threadIdx.x >> 5); if (tile >= e.xt * e.yt) return;
+  const uint32_t ty = tile / e.xt, tx = tile % e.xt; float sxy = 0, sby = 0, syy = 0;
+  for (int k = 0; k < 2; k++) {
+    const uint32_t by = ty * 8 + uint32_t(lane >> 3) + 4u * k, bx = tx * 8 + uint32_t(lane & 7);
+    if (by < e.yb && bx < e.xb) {
+      const size_t cell = size_t(by) * e.xb + bx; const float4 st = reinterpret_cast<const float4*>(e.block_stats)[cell]; sxy += st.y; sby += st.z; syy += st.w;
+      if (e.aq_on) {
+        const float mulq = fminf(1.35f, fmaxf(0.75f, __powf(e.aq_ref / (st.x + 1e-4f), 0.2f)));
+        const float level = mulq < 0.81f ? 0.75f : mulq < 0.93f ? 0.87f : mulq < 1.08f ? 1.0f : mulq < 1.25f ? 1.16f : 1.35f;
+        e.hf_mul_map[cell] = uint8_t(max(1, min(255, __float2int_rn(float(e.hf_mul) * level))));
+      } else e.hf_mul_map[cell] = uint8_t(e.hf_mul);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { sxy += __shfl_xor_sync(0xffffffffu, sxy, d); sby += __shfl_xor_sync(0xffffffffu, sby, d); syy += __shfl_xor_sync(0xffffffffu, syy, d); }
+  if (lane == 0) {
+    int fx = 0, fb = 0; if (e.cfl_on && syy > 1e-12f) { fx = __float2int_rn(84.0f * (sxy / syy)); fb = __float2int_rn(84.0f * (sby / syy - 1.0f)); }
+    e.ytox_map[tile] = int8_t(max(-128, min(127, fx))); e.ytob_map[tile] = int8_t(max(-128, min(127, fb)));
+  }
+}
+
 // One thread per 8x8 block; channels in order Y, X, B because X/B quantise against the dequantised Y (A.8 chroma from luma).
 __global__ void __launch_bounds__(64) k_enc_dct8(const DEncFrame* ep) {
   const DEncFrame& e = *ep; int cell = blockIdx.x * blockDim.x + threadIdx.x; if (cell >= int(e.xb * e.yb)) return;
   int cy = cell / int(e.xb), cx = cell % int(e.xb); int g = (cy >> 5) * int(e.xgroups) + (cx >> 5); int by = cy & 31, bx = cx & 31;
   const float* cos8 = e.tables->cosines + CosOff(3); const float* dq = e.dequant8; size_t plane = size_t(e.xpad) * e.ext_rows, lfplane = size_t(e.xb) * e.yb;
-  float scale = e.inv_gs / float(e.hf_mul); float ydq[64]; uint32_t nzc[3];
+  const uint32_t hfm = e.hf_mul_map ? e.hf_mul_map[cell] : e.hf_mul; float kx = e.kx, kb = e.kb;
+  if (e.ytox_map) { const size_t tile = size_t(cy >> 3) * e.xt + (cx >> 3); kx = float(e.ytox_map[tile]) * (1.0f / 84.0f); kb = 1.0f + float(e.ytob_map[tile]) * (1.0f / 84.0f); }
+  float scale = e.inv_gs / float(hfm); float ydq[64]; uint32_t nzc[3];
 #pragma unroll 1
   for (int ci = 0; ci < 3; ci++) {
-    const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; const float* px = e.xyb + c * plane + (size_t(e.ext_top) + size_t(cy) * 8) * e.xpad + size_t(cx) * 8; float t[64], S[64];
-    // rows: t[y][hf] = (1/8) sum_x px[y][x] cos[hf][x]
-    for (int y = 0; y < 8; y++) { float v[8]; for (int x = 0; x < 8; x++) v[x] = px[size_t(y) * e.xpad + x]; for (int k = 0; k < 8; k++) { float a = 0; for (int x = 0; x < 8; x++) a += v[x] * cos8[k * 8 + x]; t[y * 8 + k] = a * 0.125f; } }
-    // columns: F[vf][hf]; storage (square block) S[hf][vf]
-    for (int hf = 0; hf < 8; hf++) for (int vf = 0; vf < 8; vf++) { float a = 0; for (int y = 0; y < 8; y++) a += t[y * 8 + hf] * cos8[vf * 8 + y]; S[hf * 8 + vf] = a * 0.125f; }
+    const int c = ci == 0 ? 1 : ci == 1 ? 0 : 2; const float* px = e.xyb + c * plane + (size_t(e.ext_top) + size_t(cy) * 8) * e.xpad + size_t(cx) * 8; float S[64];
+    ForwardDct8(px, e.xpad, cos8, S);
     e.lf[c * lfplane + cell] = S[0];
     int16_t* out = e.coeffs + (size_t(g) * 3 + c) * 65536 + (size_t(by) * 32 + bx) * 64; uint32_t nz = 0;
-    const float mulc = c == 1 ? scale : c == 0 ? scale * e.xm : scale * e.bm, kc = c == 0 ? e.kx : e.kb;
+    const float mulc = c == 1 ? scale : c == 0 ? scale * e.xm : scale * e.bm, kc = c == 0 ? kx : kb;
     for (int p = 0; p < 64; p++) {
       int q = 0;
       if (p) { float step = dq[c * 64 + p] * mulc; float v = S[p]; if (c != 1) v -= kc * ydq[p]; float qf = v / step; if (fabsf(qf) >= 0.56f) q = __float2int_rn(qf); q = max(-32768, min(32767, q));
@@ -240,6 +285,9 @@ void EncLaunchScan(const uint8_t* bgra, uint32_t w, uint32_t h, uint32_t stride,
 void EncLaunchToXyb(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st) { dim3 blk(32, 8), grid((h.xpad + 31) / 32, (h.ext_rows + 7) / 8); k_enc_to_xyb<<<grid, blk, 0, st>>>(d, bgra); CountLaunch(); }
 void EncLaunchToPlanes(const DEncFrame* d, const DEncFrame& h, const uint8_t* bgra, cudaStream_t st) { dim3 blk(32, 8), grid((h.xsize + 31) / 32, (h.ysize + 7) / 8); k_enc_to_planes<<<grid, blk, 0, st>>>(d, bgra); CountLaunch(); }
 void EncLaunchSharpen(float* cur, const float* orig, const float* blur, size_t n, cudaStream_t st) { k_enc_sharpen<<<unsigned((n + 255) / 256), 256, 0, st>>>(cur, orig, blur, n); CountLaunch(); }
+void EncLaunchBlockParams(const DEncFrame* d, const DEncFrame& h, cudaStream_t st) {
+  const uint32_t cells = h.xb * h.yb, tiles = h.xt * h.yt; k_enc_block_stats<<<(cells + 63) / 64, 64, 0, st>>>(d); k_enc_tile_params<<<(tiles + 3) / 4, 128, 0, st>>>(d); CountLaunch(2);
+}
 void EncLaunchDct8(const DEncFrame* d, const DEncFrame& h, cudaStream_t st) { uint32_t cells = h.xb * h.yb; k_enc_dct8<<<(cells + 63) / 64, 64, 0, st>>>(d); k_enc_lf_quant<<<(cells + 255) / 256, 256, 0, st>>>(d); CountLaunch(2); }
 void EncLaunchModTokens(const DEncFrame* d, const DEncModStream* streams, uint32_t nstreams, uint32_t max_tokens, const int32_t* planes, uint32_t pw, uint32_t ph, uint32_t nch, const uint16_t* leaf_lut, cudaStream_t st) {
   if (!nstreams || !max_tokens) return; dim3 grid((max_tokens + 255) / 256, nstreams); k_enc_mod_tokens<<<grid, 256, 0, st>>>(d, streams, planes, pw, ph, nch, leaf_lut); CountLaunch();

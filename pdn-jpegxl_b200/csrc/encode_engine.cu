@@ -40,8 +40,9 @@ struct TreeBuilder {
     return tree;
   }
 };
-Tree MakeVarDctTree(uint32_t nlf, int num_ec) {
-  TreeBuilder b; int sharp = b.Leaf(0), hfmul = b.Leaf(0), strat = b.Leaf(0), cflc = b.Leaf(0);   // Zero predictor: constant maps decode as zero-entropy rows
+Tree MakeVarDctTree(uint32_t nlf, int num_ec, bool varying_hf_mul, bool varying_cfl) {
+  // Zero predictor: constant maps decode as zero-entropy rows. Maps that vary (effort >= 5) are predicted from the left neighbour.
+  TreeBuilder b; int sharp = b.Leaf(0), hfmul = b.Leaf(varying_hf_mul ? 1 : 0), strat = b.Leaf(0), cflc = b.Leaf(varying_cfl ? 1 : 0);
   int blockinfo = b.Split(2, 0, hfmul, strat); int hfmeta = b.Split(0, 1, b.Split(0, 2, sharp, blockinfo), cflc);
   int groups = num_ec > 0 ? b.Channels(num_ec, 0, 5) : b.Leaf(5); int upper = b.Split(1, int32_t(3 * nlf + 17), groups, hfmeta);
   int lfc = b.Channels(3, 0, 5); int global = b.Leaf(5); int lower = b.Split(1, 0, lfc, global);
@@ -128,7 +129,7 @@ struct EncPlan {
   ImageMetadata m; FrameHeader fh;
   Tree tree; std::vector<Token> tree_tokens; EncCode tree_code; size_t nleaves = 0; std::vector<uint16_t> leaf_lut;
   EncOptions mopt, aopt; uint32_t global_scale = 1, quant_lf = 16; float q_ac = 1;
-  bool groups_have_modular = false, global_has_modular = false, single = false; GroupHeader plain, gheader;
+  bool groups_have_modular = false, global_has_modular = false, single = false, aq = false, cfl = false; GroupHeader plain, gheader;
   size_t HistWords() const { return (nleaves + (lossless ? 0 : kNumAcCtx)) * kEncAlphabet; }
 };
 
@@ -150,7 +151,10 @@ EncPlan MakePlan(uint32_t xs, uint32_t ys, uint32_t flags, const EncodeRequest& 
   DeriveFrameDims(fh, m);
   const uint32_t nlf = fh.num_lf_groups;
   p.single = NumTocEntries(fh) == 1;
-  p.tree = p.lossless ? MakeLosslessTree(p.ncolor + p.num_ec) : MakeVarDctTree(nlf, p.num_ec); TokenizeTree(p.tree, &p.tree_tokens);
+  // effort >= 5: adaptive quantisation and chroma from luma (block-local decisions made on the device; what libjxl's higher efforts add first)
+  p.aq = p.cfl = !p.lossless && req.effort >= 5;
+  { const char* v = getenv("JXLB200_ENC_AQ"); if (v && *v == '0') p.aq = false; v = getenv("JXLB200_ENC_CFL"); if (v && *v == '0') p.cfl = false; }   // measurement switches (scripts/compare_efforts.py)
+  p.tree = p.lossless ? MakeLosslessTree(p.ncolor + p.num_ec) : MakeVarDctTree(nlf, p.num_ec, p.aq, p.cfl); TokenizeTree(p.tree, &p.tree_tokens);
   EncOptions topt; topt.cfg = HybridCfg{4, 1, 0}; p.mopt.cfg = HybridCfg{4, 1, 0}; p.mopt.max_clusters = 48; p.aopt.cfg = HybridCfg{4, 2, 0}; p.aopt.max_clusters = 64;
   p.tree_code = BuildCode({&p.tree_tokens}, 6, topt); p.nleaves = NumLeaves(p.tree);
   // leaf LUT for the device tokeniser: kind 0 = LF coefficient streams, 1 = pass-group streams, 2 = global stream
@@ -197,7 +201,7 @@ class BandEncoder {
   EncodeRequest req; cudaStream_t st = nullptr; EncPlan plan; DEncFrame e; FrameHeader fb;   // fb: frame header of the band taken as an image of its own (group / LF-group layout)
   uint32_t frame_h = 0, lf_group0 = 0, group0 = 0;      // frame height; index of the band's first LF group / first group in the frame
   const uint8_t* d_bgra = nullptr;                       // first row of the band itself (halo rows lie before it)
-  Buf d_in, d_flags, d_e, d_xyb, d_tmp1, d_tmp2, d_planes, d_lf, d_lfq, d_coeffs, d_nz, d_dq, d_order, d_tokens, d_account, d_lut, d_modstreams, d_streams, d_hist_m, d_hist_a, d_bytes, d_bits, d_gabframe, d_srclut;
+  Buf d_in, d_flags, d_e, d_xyb, d_tmp1, d_tmp2, d_planes, d_lf, d_lfq, d_coeffs, d_nz, d_dq, d_order, d_tokens, d_account, d_lut, d_modstreams, d_streams, d_hist_m, d_hist_a, d_bytes, d_bits, d_gabframe, d_srclut, d_hfm, d_ytox, d_ytob, d_stats;
   std::vector<DEncModStream> mod_streams; std::vector<DEncStream> m_streams, a_streams; std::vector<uint32_t> ac_counts;
   uint32_t first_lf_stream = 0, first_group_stream = 0, max_mod_tokens = 0; uint64_t byte_cursor = 0;
   std::vector<std::vector<Token>> hfmeta_tokens; std::vector<uint32_t> hfmeta_nb;
@@ -277,6 +281,12 @@ std::vector<uint64_t> BandEncoder::Tokenize(uint32_t frame_flags) {
     e.xyb = d_xyb.as<float>(); e.lf = d_lf.as<float>(); e.lfq = d_lfq.as<int32_t>(); e.coeffs = d_coeffs.as<int16_t>(); e.nz = d_nz.as<uint8_t>();
     e.dequant8 = d_dq.as<float>(); e.order8 = d_order.as<uint16_t>(); e.ac_token_count = d_account.as<uint32_t>();
     CUDA_OK(cudaMemsetAsync(d_coeffs.p, 0, d_coeffs.n, st));
+    e.xt = (e.xb + 7) / 8; e.yt = (e.yb + 7) / 8;
+    if (plan.aq || plan.cfl) {
+      d_hfm.Alloc(cells); d_ytox.Alloc(size_t(e.xt) * e.yt); d_ytob.Alloc(size_t(e.xt) * e.yt); d_stats.Alloc(cells * 16);
+      e.hf_mul_map = d_hfm.as<uint8_t>(); e.ytox_map = d_ytox.as<int8_t>(); e.ytob_map = d_ytob.as<int8_t>(); e.block_stats = d_stats.as<float>();
+      e.aq_on = plan.aq; e.cfl_on = plan.cfl; e.aq_ref = 0.05f;
+    }
   }
   d_bytes.Alloc(std::max<uint64_t>(byte_cursor + (lossless ? 0 : uint64_t(ng) * (size_t(kMaxAcTokensPerGroup) * 6 + 16)), 16)); d_bits.Alloc((mod_streams.size() + ng + 1) * 8);
   e.stream_bytes = d_bytes.as<uint8_t>(); e.stream_bits = d_bits.as<uint64_t>();
@@ -292,6 +302,7 @@ std::vector<uint64_t> BandEncoder::Tokenize(uint32_t frame_flags) {
       CUDA_OK(cudaMemcpyAsync(d_gabframe.p, &gf, sizeof(gf), cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(d_tmp1.p, d_xyb.p, epx * 12, cudaMemcpyDeviceToDevice, st));
       for (int it = 0; it < 2; it++) { LaunchGaborishPlanes(d_gabframe.as<DFrame>(), gf, e.xyb, d_tmp2.as<float>(), st); EncLaunchSharpen(e.xyb, d_tmp1.as<float>(), d_tmp2.as<float>(), epx * 3, st); }
     }
+    if (e.hf_mul_map) EncLaunchBlockParams(de, e, st);
     EncLaunchDct8(de, e, st); EncLaunchAcTokens(de, e, st);
   }
   // ---- Modular tokens on the device
@@ -316,13 +327,22 @@ std::vector<uint64_t> BandEncoder::Tokenize(uint32_t frame_flags) {
   std::vector<uint64_t> hist(plan.HistWords(), 0);
   { std::vector<uint32_t> raw(nleaves * kEncAlphabet); CUDA_OK(cudaMemcpyAsync(raw.data(), d_hist_m.p, raw.size() * 4, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); for (size_t i = 0; i < raw.size(); i++) hist[i] = raw[i]; }
   if (!lossless) { std::vector<uint32_t> raw(kNumAcCtx * kEncAlphabet); CUDA_OK(cudaMemcpyAsync(raw.data(), d_hist_a.p, raw.size() * 4, cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); uint64_t* dst = hist.data() + nleaves * kEncAlphabet; for (size_t i = 0; i < raw.size(); i++) dst[i] = raw[i]; }
-  // HF metadata (tiny) is tokenised on the host: CfL maps all zero, every block DCT8 with one hf multiplier, constant EPF sharpness
+  // HF metadata is tokenised on the host: every block DCT8, constant EPF sharpness; the quantiser multipliers and chroma-from-luma factors are
+  // constants below effort 5 and device-computed maps from effort 5 on (one byte per block / per tile to download)
+  std::vector<uint8_t> h_hfm; std::vector<int8_t> h_ytox, h_ytob;
+  if (e.hf_mul_map) { h_hfm.resize(cells); h_ytox.resize(size_t(e.xt) * e.yt); h_ytob.resize(h_ytox.size());
+    CUDA_OK(cudaMemcpyAsync(h_hfm.data(), d_hfm.p, h_hfm.size(), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaMemcpyAsync(h_ytox.data(), d_ytox.p, h_ytox.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(h_ytob.data(), d_ytob.p, h_ytob.size(), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st)); }
   hfmeta_tokens.assign(nlf, {}); hfmeta_nb.assign(nlf, 0);
   if (!lossless) for (uint32_t g = 0; g < nlf; g++) {
     const uint32_t gx = g % fb.xlfgroups, gy = g / fb.xlfgroups; const int w = int(std::min<uint32_t>(256, e.xb - gx * 256)), h = int(std::min<uint32_t>(256, e.yb - gy * 256)), tw = (w + 7) / 8, th = (h + 7) / 8, nb = w * h; hfmeta_nb[g] = uint32_t(nb);
     const int sid = int(1 + 2 * plan.fh.num_lf_groups + lf_group0 + g);
-    std::vector<int32_t> zeros(size_t(tw) * th, 0), info(size_t(nb) * 2, 0), sharp(size_t(w) * h, plan.fh.lf.epf_iters ? 4 : 0); for (int i = 0; i < nb; i++) info[nb + i] = int32_t(e.hf_mul) - 1;
-    TokenizeSmallChannel(zeros, tw, th, 0, sid, plan.tree, &hfmeta_tokens[g]); TokenizeSmallChannel(zeros, tw, th, 1, sid, plan.tree, &hfmeta_tokens[g]);
+    std::vector<int32_t> cflx(size_t(tw) * th, 0), cflb(size_t(tw) * th, 0), info(size_t(nb) * 2, 0), sharp(size_t(w) * h, plan.fh.lf.epf_iters ? 4 : 0); for (int i = 0; i < nb; i++) info[nb + i] = int32_t(e.hf_mul) - 1;
+    if (!h_hfm.empty()) {   // maps decided on the device: per-block multiplier, per-tile chroma-from-luma factors
+      for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) info[size_t(nb) + size_t(y) * w + x] = int32_t(h_hfm[size_t(gy * 256 + y) * e.xb + gx * 256 + x]) - 1;
+      for (int y = 0; y < th; y++) for (int x = 0; x < tw; x++) { const size_t t = size_t(gy * 32 + y) * e.xt + gx * 32 + x; cflx[size_t(y) * tw + x] = h_ytox[t]; cflb[size_t(y) * tw + x] = h_ytob[t]; }
+    }
+    TokenizeSmallChannel(cflx, tw, th, 0, sid, plan.tree, &hfmeta_tokens[g]); TokenizeSmallChannel(cflb, tw, th, 1, sid, plan.tree, &hfmeta_tokens[g]);
     TokenizeSmallChannel(info, nb, 2, 2, sid, plan.tree, &hfmeta_tokens[g]); TokenizeSmallChannel(sharp, w, h, 3, sid, plan.tree, &hfmeta_tokens[g]);
     for (const Token& t : hfmeta_tokens[g]) { uint32_t tok, nbits, bits; HybridEncode(plan.mopt.cfg, t.value, &tok, &nbits, &bits); JXLG_CHECK(tok < kEncAlphabet, "HF metadata token"); hist[size_t(t.ctx) * kEncAlphabet + tok]++; }
   }
