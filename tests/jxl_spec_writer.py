@@ -228,8 +228,9 @@ FLAG_NOISE, FLAG_PATCHES, FLAG_SPLINES, FLAG_USE_LF_FRAME, FLAG_SKIP_LF_SMOOTHIN
 
 
 def frame_header(b, modular, num_extra=0, xyb_encoded=False, flags=0, group_size_shift=1, num_passes=1, pass_shifts=(), name=b"",
-                 x_qm_scale=3, b_qm_scale=2):
-    """A regular, full-size, last frame (blend mode Replace) without restoration filters."""
+                 x_qm_scale=3, b_qm_scale=2, crop=None, canvas=None, blend=None, ec_blend=None, is_last=True, save_as_reference=0):
+    """A regular frame without restoration filters. Defaults: full size, last, blend mode Replace. crop = (x0, y0, width, height) with
+    canvas = (image width, image height); blend / ec_blend[i] = dict(mode, alpha_channel, clamp, source) (F.2: BlendingInfo)."""
     b.bool(False)                 # all_default
     b.u(2, 0)                     # frame_type: regular
     b.u(1, 1 if modular else 0)   # encoding
@@ -247,12 +248,37 @@ def frame_header(b, modular, num_extra=0, xyb_encoded=False, flags=0, group_size
         b.u(3, x_qm_scale)
         b.u(3, b_qm_scale)
     passes(b, num_passes, pass_shifts)
-    b.bool(False)                 # have_crop
+    b.bool(crop is not None)      # have_crop
+    full_frame = True
+    if crop is not None:
+        dim = (("bits", 8), ("bo", 11, 256), ("bo", 14, 2304), ("bo", 30, 18688))
+        x0, y0, cw, chh = crop
+        b.u32(dim, pack_signed(x0))
+        b.u32(dim, pack_signed(y0))
+        b.u32(dim, cw)
+        b.u32(dim, chh)
+        full_frame = x0 <= 0 and y0 <= 0 and x0 + cw >= canvas[0] and y0 + chh >= canvas[1]
     mode = (("val", 0), ("val", 1), ("val", 2), ("bo", 2, 3))
-    b.u32(mode, 0)                # blending_info.mode = Replace (full frame: no source field)
-    for _ in range(num_extra):
-        b.u32(mode, 0)            # ec_blending_info[i].mode
-    b.bool(True)                  # is_last (so no save_as_reference / save_before_color_transform)
+
+    def blending_info(info):
+        info = info or {}
+        m = info.get("mode", 0)
+        b.u32(mode, m)
+        if num_extra and m in (2, 3):
+            b.u32((("val", 0), ("val", 1), ("val", 2), ("bo", 3, 3)), info.get("alpha_channel", 0))
+        if (num_extra and m in (2, 3)) or m == 4:
+            b.bool(info.get("clamp", False))
+        if m != 0 or not full_frame:
+            b.u(2, info.get("source", 0))
+
+    blending_info(blend)
+    for i in range(num_extra):
+        blending_info(ec_blend[i] if ec_blend else None)
+    b.bool(is_last)               # (no animation: no duration field)
+    if not is_last:
+        b.u(2, save_as_reference)
+        if (blend or {}).get("mode", 0) == 0 and full_frame:
+            b.bool(False)         # save_before_color_transform
     b.u32((("val", 0), ("bits", 4), ("bo", 5, 16), ("bo", 10, 48)), len(name))
     for ch in name:
         b.u(8, ch)
@@ -736,7 +762,18 @@ def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_co
     image_metadata(b, bits=bits, extra_channels=ecs, xyb_encoded=False, orientation=orientation,
                    color=dict(color_space=CS_GRAY) if gray else None)
     b.pad_to_byte()
-    frame_header(b, modular=True, num_extra=len(ecs), xyb_encoded=False, group_size_shift=group_size_shift, name=name)
+    return b.bytes() + modular_frame(channels, len(ecs), bits=bits, tree=tree, data_code=data_code, rct=rct, name=name, group_size_shift=group_size_shift,
+                                     toc_permutation=toc_permutation, rle=rle, palette=palette)
+
+
+def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=None, name=b"", group_size_shift=1, toc_permutation=None, rle=None, palette=None,
+                  **header):
+    """One Modular frame (frame header, TOC, sections) of `channels` (its own size); starts byte-aligned. **header: crop, canvas, blend, ec_blend,
+    is_last, save_as_reference of frame_header()."""
+    h, w = len(channels[0]), len(channels[0][0])
+    tree = tree or Leaf(0, 5)
+    b = Bits()
+    frame_header(b, modular=True, num_extra=num_extra, xyb_encoded=False, group_size_shift=group_size_shift, name=name, **header)
     gdim = 128 << group_size_shift
     gx, gy = -(-w // gdim), -(-h // gdim)
     ngroups, nlf = gx * gy, (-(-w // (gdim * 8))) * (-(-h // (gdim * 8)))
@@ -818,6 +855,23 @@ def forward_rct(planes, begin, rct_type):
             for k in range(3):
                 out[k][y][x] = o[k]
     return planes[:begin] + out + planes[begin + 3:]
+
+
+def modular_layers(canvas_w, canvas_h, layers, bits=8, alpha_bits=8, alpha_associated=False, group_size_shift=1):
+    """A layered still: RGB + alpha image of canvas_w x canvas_h whose frames are `layers` = [dict(channels=[R, G, B, A planes], x0, y0,
+    blend=dict(...), alpha_blend=dict(...), save=slot)], the last one is_last. Every frame carries its crop rectangle."""
+    b = Bits()
+    b.u(16, 0x0AFF)
+    size_header(b, canvas_w, canvas_h)
+    image_metadata(b, bits=bits, extra_channels=[dict(type=EC_ALPHA, bits=alpha_bits, alpha_associated=alpha_associated)], xyb_encoded=False)
+    b.pad_to_byte()
+    out = b.bytes()
+    for i, ly in enumerate(layers):
+        ch = ly["channels"]
+        hh, ww = len(ch[0]), len(ch[0][0])
+        out += modular_frame(ch, 1, bits=bits, group_size_shift=group_size_shift, crop=(ly.get("x0", 0), ly.get("y0", 0), ww, hh), canvas=(canvas_w, canvas_h),
+                             blend=ly.get("blend"), ec_blend=[ly.get("alpha_blend", ly.get("blend"))], is_last=i + 1 == len(layers), save_as_reference=ly.get("save", 0))
+    return out
 
 
 # ----------------------------------------------------------------------------- DC-only VarDCT frame

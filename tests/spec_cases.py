@@ -157,6 +157,24 @@ def cases():
     assert a.min() >= 0 and a.max() <= 255
     pald = dict(begin=0, num_c=3, colors=starts, deltas=deltas, predictor=1, delta_mask=mask)
     out.append(("rgb8_palette_deltas", W.modular_image(_planes(a), tree=tree, data_code=code, palette=pald), a.astype(np.uint8), dict(width=ww, height=hh, format="Rgb", num_channels=3)))
+    # 14. Layered stills (F.2 crop + BlendingInfo, reference slots): every frame carries its crop rectangle; expected pixels from the numpy
+    #     statement of the blend modes (tests/layer_util.py). (a) alpha-blend of a layer that hangs over the canvas border, (b) add, (c) three
+    #     layers: the second goes to slot 2 from the empty slot 2, the last one multiplies onto slot 1
+    import layer_util as LU
+    cw, chh = 60, 50
+    base = _img(chh, cw, 4, seed=15)
+    base[..., 3] = np.maximum(base[..., 3], 90)
+    over = _img(22, 28, 4, seed=16, smooth=False)
+    f = lambda a: a.astype(np.float32) / 255.0
+    for nm, mode, mname, (x0, y0) in (("layers_blend_over_border", 2, "blend", (45, -6)), ("layers_add", 1, "add", (10, 8))):
+        data = W.modular_layers(cw, chh, [dict(channels=_planes(base)), dict(channels=_planes(over), x0=x0, y0=y0, blend=dict(mode=mode, alpha_channel=0, source=0))])
+        want = LU.to_u8(LU.composite(f(base), f(over), x0, y0, mname))
+        out.append((nm, data, ("within1", want), dict(width=cw, height=chh, format="Rgb", num_channels=4, has_transparency=True)))
+    other = _img(chh, cw, 4, seed=17)
+    data = W.modular_layers(cw, chh, [dict(channels=_planes(base), save=1), dict(channels=_planes(other), blend=dict(mode=1, source=2), save=2),
+                                      dict(channels=_planes(over), x0=5, y0=20, blend=dict(mode=4, source=1, clamp=True))])
+    want = LU.to_u8(LU.composite(f(base), f(over), 5, 20, "mul"))
+    out.append(("layers_three_slots_mul", data, ("within1", want), dict(width=cw, height=chh, format="Rgb", num_channels=4, has_transparency=True)))
     return out
 
 

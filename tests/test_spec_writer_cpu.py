@@ -13,6 +13,8 @@ def expected_pixels(px):
         rgb = a[..., :3] / np.maximum(a[..., 3:4], 1.0 / 67108864.0)
         out = np.concatenate([np.clip(rgb, 0, 1), a[..., 3:4]], axis=2) * 65535.0
         return np.rot90(out, -1), 1.0
+    if isinstance(px, tuple) and px[0] == "within1":    # float blending rounded to 8 bits: a rounding flip at x.5 is allowed
+        return px[1], 0.5
     return px, 0
 
 
