@@ -785,17 +785,17 @@ def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=No
     code = data_code or EntropyCode([0] * nleaf, [("flat", 256)], log_alpha=8)
     code.write_header(g)
     transforms = [("rct", rct[0], rct[1])] if rct else []
-    if palette:
-        transforms.append(("palette", palette["begin"], palette["num_c"], len(palette["colors"]), len(palette.get("deltas", ())), palette.get("predictor", 0)))
+    for pl in ([palette] if isinstance(palette, dict) else (palette or [])):
+        transforms.append(("palette", pl["begin"], pl["num_c"], len(pl["colors"]), len(pl.get("deltas", ())), pl.get("predictor", 0)))
     group_header(g, transforms)
     planes = [[list(r) for r in ch] for ch in channels]
     if rct:
         planes = forward_rct(planes, rct[0], rct[1])
     nb_meta = 0
-    if palette:
-        pal, idx = forward_palette(planes, palette["begin"], palette["num_c"], palette["colors"], bits, palette.get("deltas", ()), palette.get("predictor", 0), palette.get("delta_mask"))
-        planes = [pal] + planes[:palette["begin"]] + [idx] + planes[palette["begin"] + palette["num_c"]:]
-        nb_meta = 1
+    for pl in ([palette] if isinstance(palette, dict) else (palette or [])):   # several palettes: each `begin` indexes the channel list as it is then
+        pal, idx = forward_palette(planes, pl["begin"], pl["num_c"], pl["colors"], bits, pl.get("deltas", ()), pl.get("predictor", 0), pl.get("delta_mask"))
+        planes = [pal] + planes[:pl["begin"]] + [idx] + planes[pl["begin"] + pl["num_c"]:]
+        nb_meta += 1
     fits = w <= gdim and h <= gdim
     pack = (lambda it: rle_copies(it, rle[0], rle[1])) if rle else (lambda it: it)   # rle = (min run to replace, distance symbol)
     if fits:

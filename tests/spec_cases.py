@@ -157,6 +157,17 @@ def cases():
     assert a.min() >= 0 and a.max() <= 255
     pald = dict(begin=0, num_c=3, colors=starts, deltas=deltas, predictor=1, delta_mask=mask)
     out.append(("rgb8_palette_deltas", W.modular_image(_planes(a), tree=tree, data_code=code, palette=pald), a.astype(np.uint8), dict(width=ww, height=hh, format="Rgb", num_channels=3)))
+    # 13b. A channel palette on alpha alone (begin_c = 3, num_c = 1: 5 alpha levels) after a YCgCo RCT of the colour channels; then two palettes in one
+    #      image: R,G,B -> index, and alpha -> index (the second one addresses the channel list AFTER the first: palette, index, alpha -> begin 2)
+    levels = [0, 60, 128, 200, 255]
+    a = np.concatenate([_img(40, 52, 3, seed=18), np.array(levels)[np.random.default_rng(19).integers(0, 5, size=(40, 52, 1))]], axis=2)
+    tree_a = W.Split(0, 0, W.Leaf(0, 5), W.Leaf(1, 0))
+    code_a = W.EntropyCode([0, 1], [("flat", 256), ("flat", 256)], hybrids=[W.Hybrid(4, 2, 0)] * 2, log_alpha=8)
+    out.append(("rgba8_rct_then_alpha_palette", W.modular_image(_planes(a), alpha_bits=8, tree=tree_a, data_code=code_a, rct=(0, 6), palette=dict(begin=3, num_c=1, colors=[(v,) for v in levels])),
+                a.astype(np.uint8), dict(width=52, height=40, format="Rgb", num_channels=4, has_transparency=True)))
+    a = np.concatenate([paletted(36, 44, 4), np.array(levels)[np.random.default_rng(20).integers(0, 5, size=(36, 44, 1))]], axis=2)
+    out.append(("rgba8_two_palettes", W.modular_image(_planes(a), alpha_bits=8, tree=tree_a, data_code=code_a, palette=[dict(begin=0, num_c=3, colors=explicit), dict(begin=2, num_c=1, colors=[(v,) for v in levels])]),
+                a.astype(np.uint8), dict(width=44, height=36, format="Rgb", num_channels=4, has_transparency=True)))
     # 14. Layered stills (F.2 crop + BlendingInfo, reference slots): every frame carries its crop rectangle; expected pixels from the numpy
     #     statement of the blend modes (tests/layer_util.py). (a) alpha-blend of a layer that hangs over the canvas border, (b) add, (c) three
     #     layers: the second goes to slot 2 from the empty slot 2, the last one multiplies onto slot 1
