@@ -176,6 +176,9 @@ JXLFT_API void JXLFT_CALL JxlB200LastStageTimes(float* ms8);
 JXLFT_API int64_t JXLFT_CALL JxlB200KernelLaunchCount(void);
 JXLFT_API int64_t JXLFT_CALL JxlB200DebugDecodeStage(const uint8_t* data, size_t dataSize, int32_t which, float* out, int64_t capacity, int32_t* dims2, ErrorInfo* errorInfo);
 JXLFT_API int32_t JXLFT_CALL JxlB200CudaAvailable(ErrorInfo* errorInfo);
+/* Host-only instrumentation: byte sizes of the first frame's sections in logical TOC order (LfGlobal, LF groups, HfGlobal, pass groups);
+ * counts[2] = {LF groups, groups}. Returns the number of entries written or 0. */
+JXLFT_API int64_t JXLFT_CALL JxlB200DebugSectionSizes(const uint8_t* data, size_t dataSize, uint64_t* sizes, int64_t capacity, int32_t* counts, ErrorInfo* errorInfo);
 
 #ifdef __cplusplus
 }

@@ -78,7 +78,7 @@ class IOCallbacks(C.Structure):
 EXPORTS = ["GetLibJxlVersion", "LoadImage", "SaveImage", "JxlB200LoadImageBgra", "JxlB200PeekInfo", "JxlB200DecodeBatch", "JxlB200EncodeToMemory",
            "JxlB200Free", "JxlB200LastStageTimes", "JxlB200KernelLaunchCount", "JxlB200DebugDecodeStage", "JxlB200CudaAvailable", "JxlB200BandLayout",
            "JxlB200DecodeBand", "JxlB200ReleaseMemory", "JxlB200DebugParseIcc", "JxlB200DecodeBatchSubmit", "JxlB200DecodeBatchWait", "JxlB200LoadImageLayers",
-           "JxlB200BandEncoderCreate", "JxlB200BandEncoderTokenize", "JxlB200BandEncoderFinish", "JxlB200BandEncoderDestroy", "JxlB200AssembleBands"]
+           "JxlB200BandEncoderCreate", "JxlB200BandEncoderTokenize", "JxlB200BandEncoderFinish", "JxlB200BandEncoderDestroy", "JxlB200AssembleBands", "JxlB200DebugSectionSizes"]
 
 _lib.GetLibJxlVersion.restype = C.c_uint32
 _lib.LoadImage.argtypes = [C.POINTER(DecoderCallbacks), C.c_void_p, C.c_size_t, C.POINTER(ErrorInfo)]
@@ -769,6 +769,20 @@ def decode_batch_submit(datas, out_arrays=None, bgra=False, device=-1, max_in_fl
 def decode_batch(datas, out_arrays=None, bgra=False, device=-1, max_in_flight=16, device_inputs=None, device_outputs=None, sizes=None, out_sizes=None, raise_on_error=True):
     """Synchronous batch decode (submit + wait)."""
     return decode_batch_submit(datas, out_arrays, bgra, device, max_in_flight, device_inputs, device_outputs, sizes, out_sizes).wait(raise_on_error)
+
+
+def section_sizes(data):
+    """(sizes of the first frame's sections in logical TOC order, number of LF groups, number of groups) — host only."""
+    b = bytes(data)
+    out = (C.c_uint64 * 70000)()
+    counts = (C.c_int32 * 2)()
+    ei = ErrorInfo()
+    _lib.JxlB200DebugSectionSizes.restype = C.c_int64
+    _lib.JxlB200DebugSectionSizes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(ErrorInfo)]
+    n = _lib.JxlB200DebugSectionSizes(b, len(b), out, 70000, counts, C.byref(ei))
+    if n == 0:
+        raise FormatException("DecodeError", _message(ei) or "section sizes")
+    return list(out[:n]), counts[0], counts[1]
 
 
 def last_stage_times():

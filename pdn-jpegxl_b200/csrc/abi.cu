@@ -484,6 +484,12 @@ EncoderStatus JxlB200AssembleBands(uint32_t width, uint32_t height, const Encode
   } catch (const std::bad_alloc&) { return EncoderStatus_OutOfMemory; } catch (...) { return EncoderStatus_EncodeError; }
 }
 
+int64_t JxlB200DebugSectionSizes(const uint8_t* data, size_t dataSize, uint64_t* sizes, int64_t capacity, int32_t* counts2, ErrorInfo* errorInfo) {
+  if (!data || !sizes) return 0;
+  std::vector<uint64_t> v; uint32_t nlf = 0, ng = 0; std::string msg; Status st = DecodeSectionSizes(data, dataSize, &v, &nlf, &ng, &msg);
+  if (st != Status::Ok) { SetErrorMessage(errorInfo, msg); return 0; }
+  if (int64_t(v.size()) > capacity) return 0; for (size_t i = 0; i < v.size(); i++) sizes[i] = v[i]; if (counts2) { counts2[0] = int32_t(nlf); counts2[1] = int32_t(ng); } return int64_t(v.size());
+}
 void JxlB200ReleaseMemory(void) { try { cudaDeviceSynchronize(); TrimPools(); for (auto& w : g_pools_warm) w.store(0); } catch (...) {} }
 
 void JxlB200LastStageTimes(float* ms8) { if (!ms8) return; const StageTimes& t = g_last_times; ms8[0] = t.h2d; ms8[1] = t.lf; ms8[2] = t.ac; ms8[3] = t.recon; ms8[4] = t.filters; ms8[5] = t.output; ms8[6] = t.d2h; ms8[7] = t.total; }

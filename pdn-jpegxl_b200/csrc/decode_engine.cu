@@ -603,6 +603,14 @@ Status DecodeBandLayout(const uint8_t* data, size_t size, ParsedInfo* info, std:
   catch (const std::bad_alloc&) { return Status::OutOfMemory; }
   catch (const std::exception& e) { if (message) *message = e.what(); return Status::DecodeError; }
 }
+// Host-only: byte sizes of the first frame's TOC entries (sections in logical order). Instrumentation for the load-balance analysis of the AC kernel.
+Status DecodeSectionSizes(const uint8_t* data, size_t size, std::vector<uint64_t>* sizes, uint32_t* num_lf_groups, uint32_t* num_groups, std::string* message) {
+  if (!data) return Status::NullParameter;
+  try { DecodeJob job; Status st = ParseHeadersInto(data, size, &job.hd, &job.info, message); if (st != Status::Ok) return st; DecodeRequest req; req.data = data; req.size = size; job.Setup(req);
+    sizes->assign(job.toc.size.begin(), job.toc.size.end()); *num_lf_groups = job.fh.num_lf_groups; *num_groups = job.fh.num_groups; return Status::Ok; }
+  catch (const std::bad_alloc&) { return Status::OutOfMemory; }
+  catch (const std::exception& e) { if (message) *message = e.what(); return Status::DecodeError; }
+}
 void DecodeReservePools(const std::shared_ptr<DecodeJob>& job, size_t count) { if (job) job->ReservePools(count); }
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job) { if (job) cudaStreamSynchronize(job->stream); }
 bool DecodeStreamIdle(const std::shared_ptr<DecodeJob>& job) { return !job || cudaStreamQuery(job->stream) != cudaErrorNotReady; }

@@ -61,6 +61,7 @@ void DecodeReservePools(const std::shared_ptr<DecodeJob>& job, size_t count);   
 void DecodeStreamSync(const std::shared_ptr<DecodeJob>& job);
 Status DecodeBandLayout(const uint8_t* data, size_t size, ParsedInfo* info, std::string* message);
 void DecodeFinish(const std::shared_ptr<DecodeJob>& job, DecodeResult* res);
+Status DecodeSectionSizes(const uint8_t* data, size_t size, std::vector<uint64_t>* sizes, uint32_t* num_lf_groups, uint32_t* num_groups, std::string* message);
 // stage dumps for parity tests (3 planes xpad*ypad floats or coefficient ints), copied to host
 bool DecodeDebugPlanes(const std::shared_ptr<DecodeJob>& job, int which, std::vector<float>* out, int* xpad, int* ypad);
 bool DecodeDebugCoeffs(const std::shared_ptr<DecodeJob>& job, std::vector<int16_t>* out);
