@@ -226,7 +226,7 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 // ---------------------------------------------------------------- the job
 class DecodeJob {
  public:
-  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false, layer = false; uint64_t mod_total_ints = 0;   /* int32 samples of all Modular planes: coded channels + the outputs of palette expansions */
+  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false, layer = false; DLocalTree global_local = DLocalTree(); uint64_t mod_total_ints = 0;   /* int32 samples of all Modular planes: coded channels + the outputs of palette expansions */
   DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend, d_lz, d_layer_out, h_layer_out;   /* *_layer_out: the finished canvas of a layered file (owned by the job of the frame that is shown) */
   std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false; size_t coeffs_bytes = 0, xyb_row_shift = 0;
   bool defer_entropy = false, lf_pending = false, ac_pending = false;   // bundle mode: the LF / AC entropy launch is left to DecodeBundleLaunch*
@@ -243,11 +243,28 @@ class DecodeJob {
     for (DevBuf* b : all) if (b->p && b->pool) mult[std::make_pair(b->pool, Pool::Round(b->n))]++;
     for (auto& kv : mult) kv.first.first->Reserve(kv.first.second, (count + 1) * kv.second); }
   void Run(const DecodeRequest& req) { RunLf(req); RunAc(); RunRender(); }
-  void ParseLfGlobal(BitReader& br);
+  void ParseLfGlobal(BitReader& br); uint32_t AddTree(const Tree& t, uint32_t* uses_wp); DLocalTree ParseLocalTree(BitReader& br, size_t pixels);
   void ParseHfGlobal(BitReader& br);
   void AllocateAndUpload(const DecodeRequest& req);
   void UploadFrame();
 };
+
+// An MA tree as the kernels walk it (flat int4 nodes in the blob); *uses_wp: some node needs the weighted predictor's state.
+uint32_t DecodeJob::AddTree(const Tree& t, uint32_t* uses_wp) {
+  std::vector<DTreeNode> nodes(t.size());
+  for (size_t i = 0; i < t.size(); i++) { const TreeNode& n = t[i];
+    if (n.property >= 0) { nodes[i] = make_int4(n.property, n.splitval, n.lchild, n.rchild); if (n.property == 15) *uses_wp = 1;
+      JXLG_CHECK(n.property < 16 + 4 * 4, "MA-tree properties of more than four previous channels are not supported by the GPU decoder"); }
+    else { nodes[i] = make_int4(-1, (n.leaf_id << 4) | n.predictor, n.offset, int(n.multiplier)); if (n.predictor == 6) *uses_wp = 1; } }
+  return blob.Add(nodes.data(), nodes.size() * sizeof(DTreeNode));
+}
+// A sub-bitstream with its own MA tree (use_global_tree = 0): tree and code follow its header; parsed here, tables into the blob.
+DLocalTree DecodeJob::ParseLocalTree(BitReader& br, size_t pixels) {
+  DLocalTree lt; memset(&lt, 0, sizeof(lt));
+  Tree t = DecodeTree(br, std::max<size_t>(std::min<size_t>(size_t(1) << 22, 1024 + pixels), 1 << 10)); Code code = DecodeCode(br, NumLeaves(t)); JXLG_CHECK(!br.overrun, "local MA tree truncated");
+  uint32_t wp = 0; lt.tree_off = AddTree(t, &wp); lt.tree_size = uint32_t(t.size()); lt.uses_wp = wp; lt.code = blob.AddCode(code); lt.present = 1; if (wp) h.uses_wp = 1;   // the weighted-predictor kernels for the whole frame
+  return lt;
+}
 
 void DecodeJob::ParseLfGlobal(BitReader& br) {
   const ImageMetadata& m = hd.meta;
@@ -277,11 +294,7 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
   if (has_tree) {
     size_t nch = (fh.encoding == 1 ? 3 : 0) + m.ec.size(); size_t limit = std::min<size_t>(size_t(1) << 22, 1024 + size_t(fh.xsize) * fh.ysize * std::max<size_t>(nch, 1) / 16); limit = std::max<size_t>(limit, 1 << 16);
     tree = DecodeTree(br, limit); tree_code = DecodeCode(br, NumLeaves(tree));
-    std::vector<DTreeNode> nodes(tree.size()); uint32_t uses_wp = 0;
-    for (size_t i = 0; i < tree.size(); i++) { const TreeNode& n = tree[i];
-      if (n.property >= 0) { nodes[i] = make_int4(n.property, n.splitval, n.lchild, n.rchild); if (n.property == 15) uses_wp = 1; JXLG_CHECK(n.property < 16 + 4 * 4, "MA-tree properties of more than four previous channels are not supported by the GPU decoder"); }
-      else { nodes[i] = make_int4(-1, (n.leaf_id << 4) | n.predictor, n.offset, int(n.multiplier)); if (n.predictor == 6) uses_wp = 1; } }
-    h.tree_off = blob.Add(nodes.data(), nodes.size() * sizeof(DTreeNode)); h.tree_size = uint32_t(nodes.size()); h.uses_wp = uses_wp; h.mod_code = blob.AddCode(tree_code);
+    uint32_t uses_wp = 0; h.tree_off = AddTree(tree, &uses_wp); h.tree_size = uint32_t(tree.size()); h.uses_wp = uses_wp; h.mod_code = blob.AddCode(tree_code);
   }
   h.has_tree = has_tree;
   // global Modular image: colour channels (Modular frames) + extra channels
@@ -313,7 +326,13 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
     size_t c = 0; for (; c < ch.size(); c++) if (int(c) >= nb_meta && (ch[c].w > fh.group_dim || ch[c].h > fh.group_dim)) break;
     global_decoded = c; h.first_group_channel = uint32_t(c);
     size_t nonempty = 0; for (size_t i = 0; i < c; i++) if (ch[i].w && ch[i].h) nonempty++;
-    if (nonempty) { JXLG_CHECK(gheader.use_global_tree && has_tree, "local MA trees are not supported by the GPU decoder yet"); global_has_data = true; }
+    if (nonempty) {
+      global_has_data = true;
+      if (!gheader.use_global_tree) { size_t px = 0; for (size_t i = 0; i < c; i++) px += size_t(ch[i].w) * ch[i].h; global_local = ParseLocalTree(br, px); }   // data starts where this parse stops
+      else JXLG_CHECK(has_tree, "the global Modular stream uses the global MA tree, but the frame has none");
+    }
+    const WPHeader& gw = gheader.wp; h.global_wp.p1 = gw.p1; h.global_wp.p2 = gw.p2; h.global_wp.p3a = gw.p3a; h.global_wp.p3b = gw.p3b; h.global_wp.p3c = gw.p3c; h.global_wp.p3d = gw.p3d; h.global_wp.p3e = gw.p3e;
+    for (int i = 0; i < 4; i++) h.global_wp.w[i] = gw.w[i];
     // ---- the inverse transforms as device ops, last transform first; `cur` follows the channel list back to the image's own channels
     std::vector<DModChannel> cur = ch;
     for (size_t ti = gheader.transforms.size(); ti-- > 0;) {
@@ -490,6 +509,20 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
     if (vardct && !single) ac_budget();
     { static const bool tr = getenv("JXLB200_TRACE") != nullptr; static std::atomic<int> shown{0}; if (tr && shown.fetch_add(1) < 2) fprintf(stderr, "[jxlb200] table staging: lf_smem %u B, ac_smem %u B (ac_fast %u), AC clusters %u, log_alpha %u\n", h.lf_smem, h.ac_smem, h.ac_fast, h.ac_code[0].num_clusters, h.ac_code[0].log_alpha); }
   }
+  // ---- sub-bitstreams with their own MA tree. Group sections of Modular frames start with their Modular header, so the host can parse the tree and
+  // the code that follow it (VarDCT frames keep their group-local Modular data behind the AC coefficients, where only the device knows the position).
+  h.local_off = 0;
+  { std::vector<DLocalTree> lts(size_t(h.num_groups) + 1); memset(lts.data(), 0, lts.size() * sizeof(DLocalTree)); bool any = false;
+    if (global_local.present) { lts[h.num_groups] = global_local; lts[h.num_groups].data_bitpos = after_lfglobal; any = true; }
+    if (fh.encoding == 1 && !single && h.num_passes == 1 && h.num_mod_channels > h.first_group_channel) {
+      for (uint32_t g = 0; g < h.num_groups; g++) {
+        const size_t t = size_t(2) + h.num_lf_groups + g; if (toc.size[t] == 0) continue;
+        BitReader gb(cs.data() + frame_off + toc.offset[t], toc.size[t]); const GroupHeader gh = ReadGroupHeader(gb);
+        if (gb.overrun || gh.use_global_tree || !gh.transforms.empty()) continue;   // (transforms: the kernel reports them)
+        lts[g] = ParseLocalTree(gb, size_t(h.group_dim) * h.group_dim * (h.num_mod_channels - h.first_group_channel)); lts[g].data_bitpos = base_bits + uint64_t(toc.offset[t]) * 8 + gb.pos; any = true;
+      }
+    }
+    if (any) h.local_off = blob.Add(lts.data(), lts.size() * sizeof(DLocalTree)); }
   std::vector<uint64_t> sec(2 * nlog + 2, 0);
   for (size_t i = 0; i < nlog; i++) { size_t t = single ? 0 : i; sec[i] = base_bits + uint64_t(toc.offset[t]) * 8; sec[nlog + i] = base_bits + uint64_t(toc.offset[t] + toc.size[t]) * 8; }
   h.sec_off = blob.Add(sec.data(), sec.size() * 8);

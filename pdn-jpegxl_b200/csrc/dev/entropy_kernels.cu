@@ -22,14 +22,23 @@ __device__ __constant__ uint8_t kNumNzCtx[64] = {0, 0, 31, 62, 62, 93, 93, 93, 9
 
 // Parses a Modular GroupHeader (A.7 "Sub-bitstream header"). Streams that need host-side parsing
 // (local MA trees, per-group transforms) are reported as unsupported instead of being mis-decoded.
-__device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f) {
+__device__ __forceinline__ const DLocalTree* LocalTreeOf(const DFrame& f, uint32_t index) { return f.local_off ? reinterpret_cast<const DLocalTree*>(f.blob + f.local_off) + index : nullptr; }
+// Switches the decoder to a stream's own MA tree and code (tables in global memory: the speculative shared-memory loop does not apply)
+__device__ void BindLocalTree(ModDecoder& md, const DFrame& f, const DLocalTree& lt) {
+  md.tree = reinterpret_cast<const DTreeNode*>(f.blob + lt.tree_off); md.cv.Bind(f.blob, lt.code); md.uses_wp = lt.uses_wp != 0; md.rd.br.Init(f.comp, lt.data_bitpos);
+}
+__device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f, const DLocalTree* lt = nullptr) {
   BitRd& br = md.rd.br;
   bool use_global = br.Read(1);
   if (!br.Read(1)) { md.wp.p1 = br.Read(5); md.wp.p2 = br.Read(5); md.wp.p3a = br.Read(5); md.wp.p3b = br.Read(5); md.wp.p3c = br.Read(5); md.wp.p3d = br.Read(5); md.wp.p3e = br.Read(5); for (int i = 0; i < 4; i++) md.wp.w[i] = br.Read(4); }
   else { md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12; }
   uint32_t nt = br.ReadU32(0, 0, 0, 1, 4, 2, 8, 18);
-  if (!use_global || !f.has_tree) { md.rd.err = kErrLocalTree; return false; }
   if (nt != 0) { md.rd.err = kErrGroupTransform; return false; }
+  if (!use_global) {   // the tree and the code follow in the stream: the host has parsed them (Modular frames) or the stream is not supported
+    if (!lt || !lt->present) { md.rd.err = kErrLocalTree; return false; }
+    BindLocalTree(md, f, *lt); return true;
+  }
+  if (!f.has_tree) { md.rd.err = kErrLocalTree; return false; }
   return true;
 }
 
@@ -231,7 +240,7 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   int nch = 0; uint32_t dm = 0;
   for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { int rx0, ry0, rw, rh; if (region(c, rx0, ry0, rw, rh)) { nch++; dm = max(dm, uint32_t(rw)); } }
   if (nch == 0) return;
-  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f); if (ok) { md.rd.Init(md.cv); md.dist_mult = dm; } *flag = ok ? 1u : 0u; }
+  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, f.encoding == 1 && pass == 0 ? LocalTreeOf(f, uint32_t(g)) : nullptr); if (ok) { md.rd.Init(md.cv); md.dist_mult = dm; } *flag = ok ? 1u : 0u; }
   __syncwarp();
   if (!*flag) return;
   const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g; int k = 0;
@@ -377,8 +386,9 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
   __syncthreads();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   md.rd.br.Init(f.comp, start_bitpos);
-  // header already parsed on the host (it carries the global transforms); the ANS state word follows
-  md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12;
+  // header already parsed on the host (it carries the global transforms, the weighted-predictor parameters and, if local, the tree and code); the ANS state word follows
+  md.wp = f.global_wp;
+  { const DLocalTree* lt = LocalTreeOf(f, f.num_groups); if (lt && lt->present) BindLocalTree(md, f, *lt); }   // data_bitpos == start_bitpos: the host stopped right after the code
   if (f.lz_window) md.rd.win = f.lz_window + size_t(max(f.num_lf_groups, f.num_groups)) * kLzWindow;
   { uint32_t dm = 0; for (uint32_t c = 0; c < num_channels; c++) dm = max(dm, f.mod_ch[c].w); md.dist_mult = dm; }
   md.rd.Init(md.cv);

@@ -30,6 +30,9 @@ struct DModChannel { uint32_t w, h, hshift, vshift; uint64_t plane_off; };   // 
 // One inverse transform of the global Modular image, in the order the kernels run them (the reverse of the order the file lists them).
 // kind 0 RCT: planes p[0..2] of n samples, in place. kind 1 Palette: index plane p[0] (w x h) and palette plane p[1] (pal_w entries per row,
 // one row per output channel) expand into num_c new planes out[0..num_c) — out of place, the index plane is read by every output channel.
+// A Modular sub-bitstream that brings its own MA tree and entropy code (use_global_tree = 0): parsed on the host, tables in the blob. One entry per
+// group section of a Modular frame (index g) plus one for the global stream (index num_groups); data_bitpos: where the channel data starts.
+struct DLocalTree { uint32_t present, tree_off, tree_size, uses_wp; uint64_t data_bitpos; DCode code; };
 struct DModOp { uint32_t kind, rct_type, num_c, pal_w, nb_deltas, predictor, w, h; uint64_t p[3]; uint64_t out[4]; };
 
 // Per-device constant tables (built once): scaled DCT cosines c[k*N+i] = ck*cos((2i+1)k*pi/2N) for N = 1..256 and
@@ -51,7 +54,7 @@ struct DFrame {
   uint32_t sec_off;          // uint64 sec_bitpos[nsec] then uint64 sec_bitend[nsec], byte offset into blob
   uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8];   // the channels as CODED (after the file's forward transforms): what the entropy kernels fill
   DModChannel out_ch[8];   // the image's own channels (colour, then extra channels) after the inverse transforms: what the output kernels read
-  uint32_t mod_bitdepth, mod_wide; uint32_t num_ops, ops_pad; DModOp ops[4];
+  uint32_t mod_bitdepth, mod_wide; uint32_t num_ops, local_off /* DLocalTree[num_groups + 1] in the blob, 0: every stream uses the global tree */; DModOp ops[4]; DWPHeader global_wp;   // weighted-predictor parameters of the global stream's header
   DLoopFilter lpf; DColor color; DOutput out;
   // device buffers
   const uint8_t* comp; const uint8_t* blob; const uint8_t* static_blob;

@@ -665,8 +665,10 @@ def rle_copies(items, min_length, dist_sym):
     return out
 
 
-def group_header(b, transforms=()):
-    b.bool(True)       # use_global_tree
+def group_header(b, transforms=(), local=None):
+    """Modular sub-bitstream header (H.2). local = (tree root, EntropyCode): the stream brings its own MA tree and code, written after the
+    transforms (use_global_tree = 0)."""
+    b.bool(local is None)   # use_global_tree
     b.bool(True)       # default weighted-predictor parameters
     b.u32((("val", 0), ("val", 1), ("bo", 4, 2), ("bo", 8, 18)), len(transforms))
     begin_c = (("bits", 3), ("bo", 6, 8), ("bo", 10, 72), ("bo", 13, 1096))
@@ -683,6 +685,9 @@ def group_header(b, transforms=()):
             b.u32((("bo", 8, 0), ("bo", 10, 256), ("bo", 12, 1280), ("bo", 16, 5376)), t[3])
             b.u32((("val", 0), ("bo", 8, 1), ("bo", 10, 257), ("bo", 16, 1281)), t[4])
             b.u(4, t[5])
+    if local is not None:
+        write_tree(b, local[0])
+        local[1].write_header(b)
 
 
 def implicit_palette_index(pixel, bits=8):
@@ -741,7 +746,8 @@ def container(codestream, boxes=(), split_at=None, level=None):
 
 
 def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_code=None, rct=None, name=b"", orientation=1,
-                  small_size=True, group_size_shift=1, toc_permutation=None, alpha_associated=False, extra=None, rle=None, palette=None):
+                  small_size=True, group_size_shift=1, toc_permutation=None, alpha_associated=False, extra=None, rle=None, palette=None,
+                  local_global=False, group_local=None):
     """A lossless Modular frame. channels: colour planes (1 or 3) + optional alpha + optional `extra` channels, each a list of rows.
     tree/data_code default to a single gradient-predictor leaf over a flat 256-symbol ANS code. Images larger than one group are
     written with a real multi-section TOC (each group its own section); toc_permutation reorders the sections in the file.
@@ -763,13 +769,14 @@ def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_co
                    color=dict(color_space=CS_GRAY) if gray else None)
     b.pad_to_byte()
     return b.bytes() + modular_frame(channels, len(ecs), bits=bits, tree=tree, data_code=data_code, rct=rct, name=name, group_size_shift=group_size_shift,
-                                     toc_permutation=toc_permutation, rle=rle, palette=palette)
+                                     toc_permutation=toc_permutation, rle=rle, palette=palette, local_global=local_global, group_local=group_local)
 
 
 def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=None, name=b"", group_size_shift=1, toc_permutation=None, rle=None, palette=None,
-                  **header):
+                  local_global=False, group_local=None, **header):
     """One Modular frame (frame header, TOC, sections) of `channels` (its own size); starts byte-aligned. **header: crop, canvas, blend, ec_blend,
-    is_last, save_as_reference of frame_header()."""
+    is_last, save_as_reference of frame_header(). local_global: the frame has NO global MA tree and the global stream brings its own (tree, data_code).
+    group_local = (tree, code): every group section brings this tree and code of its own instead of using the global ones."""
     h, w = len(channels[0]), len(channels[0][0])
     tree = tree or Leaf(0, 5)
     b = Bits()
@@ -780,15 +787,20 @@ def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=No
     # ---- LfGlobal: LF dequantisation (default), global tree + code, global Modular header (+ data when it fits one group)
     g = Bits()
     g.bool(True)                                         # LfChannelDequantization.all_default
-    g.bool(True)                                         # global tree present
-    nleaf = write_tree(g, tree)
+    nleaf = len([n for n in tree_nodes_bfs(tree) if isinstance(n, Leaf)])
     code = data_code or EntropyCode([0] * nleaf, [("flat", 256)], log_alpha=8)
-    code.write_header(g)
+    g.bool(not local_global)                             # global tree present
+    if not local_global:
+        write_tree(g, tree)
+        code.write_header(g)
     transforms = [("rct", rct[0], rct[1])] if rct else []
     for pl in ([palette] if isinstance(palette, dict) else (palette or [])):
         transforms.append(("palette", pl["begin"], pl["num_c"], len(pl["colors"]), len(pl.get("deltas", ())), pl.get("predictor", 0)))
-    group_header(g, transforms)
     planes = [[list(r) for r in ch] for ch in channels]
+    will_fit = w <= gdim and h <= gdim
+    has_global_data = will_fit or bool(palette)
+    assert not local_global or has_global_data or group_local, "a frame without a global tree needs local trees wherever data is coded"
+    group_header(g, transforms, local=(tree, code) if (local_global and has_global_data) else None)
     if rct:
         planes = forward_rct(planes, rct[0], rct[1])
     nb_meta = 0
@@ -810,9 +822,10 @@ def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=No
             x0, y0 = (gi % gx) * gdim, (gi // gx) * gdim
             s = Bits()
             if not fits:
-                group_header(s)
+                gtree, gcode = group_local if group_local else (tree, code)
+                group_header(s, local=group_local)
                 sub = [[row[x0:x0 + gdim] for row in ch[y0:y0 + gdim]] for ch in planes[nb_meta:]]
-                code.write_stream(s, pack(modular_items(tree, sub, 1 + 3 * nlf + 17 + gi)))   # channels are numbered from 0 inside a group section
+                gcode.write_stream(s, pack(modular_items(gtree, sub, 1 + 3 * nlf + 17 + gi)))   # channels are numbered from 0 inside a group section
             sections.append(s.bytes())
     # toc_permutation lists the logical section indices in the order they are stored in the file. The TOC codes the sizes in FILE
     # order plus the permutation that maps a logical section to its file slot.

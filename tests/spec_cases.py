@@ -168,6 +168,22 @@ def cases():
     a = np.concatenate([paletted(36, 44, 4), np.array(levels)[np.random.default_rng(20).integers(0, 5, size=(36, 44, 1))]], axis=2)
     out.append(("rgba8_two_palettes", W.modular_image(_planes(a), alpha_bits=8, tree=tree_a, data_code=code_a, palette=[dict(begin=0, num_c=3, colors=explicit), dict(begin=2, num_c=1, colors=[(v,) for v in levels])]),
                 a.astype(np.uint8), dict(width=44, height=36, format="Rgb", num_channels=4, has_transparency=True)))
+    # 13c. Local MA trees (use_global_tree = 0): (a) a frame without a global tree whose single stream brings its own; (b) a 2 x 2-group frame whose
+    #      global tree is never used by data: every group section brings a different tree (predictor W + gradient split on |N|) and its own code;
+    #      (c) no global tree at all, the palette in the global stream and the index groups all local
+    a = _img(50, 70, 3, seed=21)
+    ltree = W.Split(4, 20, W.Leaf(0, 5), W.Leaf(1, 1))                                                      # |N| > 20 ? gradient : W
+    lcode = W.EntropyCode([0, 1], [("flat", 256), ("flat", 256)], hybrids=[W.Hybrid(4, 2, 0)] * 2, log_alpha=8)
+    out.append(("rgb8_local_tree_single_stream", W.modular_image(_planes(a), tree=ltree, data_code=lcode, local_global=True), a.astype(np.uint8), dict(width=70, height=50, format="Rgb", num_channels=3)))
+    a = _img(200, 150, 3, seed=22)
+    out.append(("rgb8_local_trees_in_groups", W.modular_image(_planes(a), group_size_shift=0, group_local=(ltree, lcode)), a.astype(np.uint8), dict(width=150, height=200, format="Rgb", num_channels=3)))
+    a = paletted(140, 150, 5)
+    ptree = W.Split(0, 0, W.Leaf(0, 1), W.Leaf(1, 0))
+    pcode = W.EntropyCode([0, 1], [("flat", 128), ("flat", 256)], hybrids=[W.Hybrid(4, 2, 0)] * 2, log_alpha=8)
+    itree = W.Leaf(0, 1)
+    icode = W.EntropyCode([0], [("flat", 128)], hybrids=[W.Hybrid(4, 2, 0)], log_alpha=8)
+    out.append(("rgb8_palette_all_local", W.modular_image(_planes(a), tree=ptree, data_code=pcode, palette=pal, group_size_shift=0, local_global=True, group_local=(itree, icode)),
+                a.astype(np.uint8), dict(width=150, height=140, format="Rgb", num_channels=3)))
     # 14. Layered stills (F.2 crop + BlendingInfo, reference slots): every frame carries its crop rectangle; expected pixels from the numpy
     #     statement of the blend modes (tests/layer_util.py). (a) alpha-blend of a layer that hangs over the canvas border, (b) add, (c) three
     #     layers: the second goes to slot 2 from the empty slot 2, the last one multiplies onto slot 1
