@@ -518,7 +518,8 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
       for (uint32_t g = 0; g < h.num_groups; g++) {
         const size_t t = size_t(2) + h.num_lf_groups + g; if (toc.size[t] == 0) continue;
         BitReader gb(cs.data() + frame_off + toc.offset[t], toc.size[t]); const GroupHeader gh = ReadGroupHeader(gb);
-        if (gb.overrun || gh.use_global_tree || !gh.transforms.empty()) continue;   // (transforms: the kernel reports them)
+        bool only_rct = true; for (const Transform& tr : gh.transforms) only_rct = only_rct && tr.id == 0;
+        if (gb.overrun || gh.use_global_tree || !only_rct) continue;   // (palette / squeeze inside a group section: the kernel reports them)
         lts[g] = ParseLocalTree(gb, size_t(h.group_dim) * h.group_dim * (h.num_mod_channels - h.first_group_channel)); lts[g].data_bitpos = base_bits + uint64_t(toc.offset[t]) * 8 + gb.pos; any = true;
       }
     }

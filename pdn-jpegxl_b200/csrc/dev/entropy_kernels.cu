@@ -27,13 +27,20 @@ __device__ __forceinline__ const DLocalTree* LocalTreeOf(const DFrame& f, uint32
 __device__ void BindLocalTree(ModDecoder& md, const DFrame& f, const DLocalTree& lt) {
   md.tree = reinterpret_cast<const DTreeNode*>(f.blob + lt.tree_off); md.cv.Bind(f.blob, lt.code); md.uses_wp = lt.uses_wp != 0; md.rd.br.Init(f.comp, lt.data_bitpos);
 }
-__device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f, const DLocalTree* lt = nullptr) {
+__device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f, const DLocalTree* lt = nullptr, bool rct_allowed = false) {
   BitRd& br = md.rd.br;
   bool use_global = br.Read(1);
   if (!br.Read(1)) { md.wp.p1 = br.Read(5); md.wp.p2 = br.Read(5); md.wp.p3a = br.Read(5); md.wp.p3b = br.Read(5); md.wp.p3c = br.Read(5); md.wp.p3d = br.Read(5); md.wp.p3e = br.Read(5); for (int i = 0; i < 4; i++) md.wp.w[i] = br.Read(4); }
   else { md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12; }
   uint32_t nt = br.ReadU32(0, 0, 0, 1, 4, 2, 8, 18);
-  if (nt != 0) { md.rd.err = kErrGroupTransform; return false; }
+  md.grct_n = 0;
+  if (nt != 0 && (!rct_allowed || nt > uint32_t(ModDecoder::kMaxGroupRct))) { md.rd.err = kErrGroupTransform; return false; }
+  for (uint32_t i = 0; i < nt; i++) {
+    if (br.Read(2) != 0) { md.rd.err = kErrGroupTransform; return false; }   // palette / squeeze inside a group section
+    const uint32_t begin_c = br.ReadU32(3, 0, 6, 8, 10, 72, 13, 1096), type = br.ReadU32(0, 6, 2, 0, 4, 2, 6, 10);
+    if (type >= 42) { md.rd.err = kErrGroupTransform; return false; }
+    md.grct_begin[md.grct_n] = begin_c; md.grct_type[md.grct_n] = type; md.grct_n++;
+  }
   if (!use_global) {   // the tree and the code follow in the stream: the host has parsed them (Modular frames) or the stream is not supported
     if (!lt || !lt->present) { md.rd.err = kErrLocalTree; return false; }
     BindLocalTree(md, f, *lt); return true;
@@ -240,9 +247,13 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   int nch = 0; uint32_t dm = 0;
   for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { int rx0, ry0, rw, rh; if (region(c, rx0, ry0, rw, rh)) { nch++; dm = max(dm, uint32_t(rw)); } }
   if (nch == 0) return;
-  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, f.encoding == 1 && pass == 0 ? LocalTreeOf(f, uint32_t(g)) : nullptr); if (ok) { md.rd.Init(md.cv); md.dist_mult = dm; } *flag = ok ? 1u : 0u; }
+  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, f.encoding == 1 && pass == 0 ? LocalTreeOf(f, uint32_t(g)) : nullptr, true); if (ok) { md.rd.Init(md.cv); md.dist_mult = dm; } *flag = ok ? 1u : 0u; }
   __syncwarp();
   if (!*flag) return;
+  // the RCTs of this group's header, for every lane (lane 0 parsed them)
+  const uint32_t grct_n = __shfl_sync(0xffffffffu, md.grct_n, 0); uint32_t grct_begin[ModDecoder::kMaxGroupRct], grct_type[ModDecoder::kMaxGroupRct];
+#pragma unroll
+  for (int i = 0; i < ModDecoder::kMaxGroupRct; i++) { grct_begin[i] = __shfl_sync(0xffffffffu, md.grct_begin[i], 0); grct_type[i] = __shfl_sync(0xffffffffu, md.grct_type[i], 0); }
   const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g; int k = 0;
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth);
   for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) {
@@ -255,6 +266,28 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
     k++;
   }
   if (lane == 0 && !md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
+  // ---- undo the group's own RCTs on its rectangles, last listed first (the channel indices count the channels of THIS section)
+  __syncwarp();
+  for (int t = int(grct_n) - 1; t >= 0; t--) {
+    int32_t* p[3] = {nullptr, nullptr, nullptr}; int stride[3] = {0, 0, 0}, rw0 = 0, rh0 = 0; bool same = true; int kk = 0;
+    for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) {
+      int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
+      const int j = kk - int(grct_begin[t]);
+      if (j >= 0 && j < 3) { const DModChannel& ch = f.mod_ch[c]; p[j] = f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0; stride[j] = int(ch.w); if (j == 0) { rw0 = rw; rh0 = rh; } else same = same && rw == rw0 && rh == rh0; }
+      kk++;
+    }
+    if (!p[0] || !p[1] || !p[2] || !same) { if (lane == 0) md.rd.err = md.rd.err ? md.rd.err : kErrGroupTransform; break; }
+    const uint32_t perm = grct_type[t] / 7, kind = grct_type[t] % 7;
+    for (int i = lane; i < rw0 * rh0; i += 32) {
+      const int y = i / rw0, x = i - y * rw0; int32_t* q0 = p[0] + size_t(y) * stride[0] + x; int32_t* q1 = p[1] + size_t(y) * stride[1] + x; int32_t* q2 = p[2] + size_t(y) * stride[2] + x;
+      const int32_t A = *q0, B = *q1, C = *q2; int32_t o[3];
+      if (kind == 6) { const int32_t tt = A - (C >> 1), G = C + tt, Bl = tt - (B >> 1), R = Bl + B; o[0] = R; o[1] = G; o[2] = Bl; }
+      else { int32_t D = A, E = B, F = C; if (kind & 1) F += A; if ((kind >> 1) == 1) E += A; if ((kind >> 1) == 2) E += (A + F) >> 1; o[0] = D; o[1] = E; o[2] = F; }
+      int32_t r[3]; r[perm % 3] = o[0]; r[(perm + 1 + perm / 3) % 3] = o[1]; r[(perm + 2 - perm / 3) % 3] = o[2];
+      *q0 = r[0]; *q1 = r[1]; *q2 = r[2];
+    }
+    __syncwarp();
+  }
 }
 
 // AC coefficients of 256x256 groups (A.8 "PassGroup AC decode"), SIMT over independent sections.

@@ -98,6 +98,9 @@ struct ModDecoder {
   SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; uint32_t dist_mult = 0; /* LZ77: widest channel of the sub-bitstream */ ChanLut* lut;
   // Earlier channels of the same sub-bitstream with the geometry of the channel being decoded, nearest first (MA-tree properties 16 + 4k .. 19 + 4k:
   // |v|, v, |v - g|, v - g of that channel's sample at the same position, g its clamped gradient). The caller keeps the list (NoteChannel).
+  // Transforms listed in the sub-bitstream's own header (group sections): only RCTs are undone on the device (what libjxl's lossless encoder picks
+  // per group); a header that lists anything else, or RCTs where the caller cannot undo them, is refused.
+  static const int kMaxGroupRct = 4; uint32_t grct_n = 0, grct_begin[kMaxGroupRct], grct_type[kMaxGroupRct];
   static const int kMaxRefs = 4; const int32_t* ref_p[kMaxRefs]; size_t ref_stride[kMaxRefs]; int ref_n = 0;
   struct Seen { const int32_t* p; size_t stride; int w, h, hs, vs; }; Seen seen[8]; int num_seen = 0;
   __device__ void ResetChannels() { num_seen = 0; ref_n = 0; }

@@ -747,7 +747,7 @@ def container(codestream, boxes=(), split_at=None, level=None):
 
 def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_code=None, rct=None, name=b"", orientation=1,
                   small_size=True, group_size_shift=1, toc_permutation=None, alpha_associated=False, extra=None, rle=None, palette=None,
-                  local_global=False, group_local=None):
+                  local_global=False, group_local=None, group_rct=None):
     """A lossless Modular frame. channels: colour planes (1 or 3) + optional alpha + optional `extra` channels, each a list of rows.
     tree/data_code default to a single gradient-predictor leaf over a flat 256-symbol ANS code. Images larger than one group are
     written with a real multi-section TOC (each group its own section); toc_permutation reorders the sections in the file.
@@ -769,14 +769,16 @@ def modular_image(channels, bits=8, gray=False, alpha_bits=0, tree=None, data_co
                    color=dict(color_space=CS_GRAY) if gray else None)
     b.pad_to_byte()
     return b.bytes() + modular_frame(channels, len(ecs), bits=bits, tree=tree, data_code=data_code, rct=rct, name=name, group_size_shift=group_size_shift,
-                                     toc_permutation=toc_permutation, rle=rle, palette=palette, local_global=local_global, group_local=group_local)
+                                     toc_permutation=toc_permutation, rle=rle, palette=palette, local_global=local_global, group_local=group_local, group_rct=group_rct)
 
 
 def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=None, name=b"", group_size_shift=1, toc_permutation=None, rle=None, palette=None,
-                  local_global=False, group_local=None, **header):
+                  local_global=False, group_local=None, group_rct=None, **header):
     """One Modular frame (frame header, TOC, sections) of `channels` (its own size); starts byte-aligned. **header: crop, canvas, blend, ec_blend,
     is_last, save_as_reference of frame_header(). local_global: the frame has NO global MA tree and the global stream brings its own (tree, data_code).
-    group_local = (tree, code): every group section brings this tree and code of its own instead of using the global ones."""
+    group_local = (tree, code): every group section brings this tree and code of its own instead of using the global ones.
+    group_rct = function(group index) -> list of (begin_c, rct_type): RCTs listed in that group's own header (what libjxl's lossless encoder chooses
+    per group), applied to the group's rectangles in the order listed."""
     h, w = len(channels[0]), len(channels[0][0])
     tree = tree or Leaf(0, 5)
     b = Bits()
@@ -823,8 +825,11 @@ def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=No
             s = Bits()
             if not fits:
                 gtree, gcode = group_local if group_local else (tree, code)
-                group_header(s, local=group_local)
+                rcts = group_rct(gi) if group_rct else []
+                group_header(s, transforms=[("rct", bc, ty) for bc, ty in rcts], local=group_local)
                 sub = [[row[x0:x0 + gdim] for row in ch[y0:y0 + gdim]] for ch in planes[nb_meta:]]
+                for bc, ty in rcts:
+                    sub = forward_rct(sub, bc, ty)
                 gcode.write_stream(s, pack(modular_items(gtree, sub, 1 + 3 * nlf + 17 + gi)))   # channels are numbered from 0 inside a group section
             sections.append(s.bytes())
     # toc_permutation lists the logical section indices in the order they are stored in the file. The TOC codes the sizes in FILE

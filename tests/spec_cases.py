@@ -184,6 +184,14 @@ def cases():
     icode = W.EntropyCode([0], [("flat", 128)], hybrids=[W.Hybrid(4, 2, 0)], log_alpha=8)
     out.append(("rgb8_palette_all_local", W.modular_image(_planes(a), tree=ptree, data_code=pcode, palette=pal, group_size_shift=0, local_global=True, group_local=(itree, icode)),
                 a.astype(np.uint8), dict(width=150, height=140, format="Rgb", num_channels=3)))
+    # 13d. RCTs chosen per group (listed in each group section's own header): 3 x 2 groups, a different RCT in every group, two RCTs in one of them,
+    #      none in another; then the same on R,G,B of an RGBA image together with a local tree per group
+    a = _img(200, 300, 3, seed=23)
+    per_group = {0: [(0, 6)], 1: [(0, 10)], 2: [], 3: [(0, 17), (0, 2)], 4: [(0, 41)], 5: [(0, 1)]}
+    out.append(("rgb8_rct_per_group", W.modular_image(_planes(a), group_size_shift=0, group_rct=lambda gi: per_group[gi]), a.astype(np.uint8), dict(width=300, height=200, format="Rgb", num_channels=3)))
+    a = _img(150, 200, 4, seed=24)
+    out.append(("rgba8_rct_per_group_local_trees", W.modular_image(_planes(a), alpha_bits=8, group_size_shift=0, group_rct=lambda gi: [(0, 6 + gi)], group_local=(ltree, lcode)),
+                a.astype(np.uint8), dict(width=200, height=150, format="Rgb", num_channels=4, has_transparency=True)))
     # 14. Layered stills (F.2 crop + BlendingInfo, reference slots): every frame carries its crop rectangle; expected pixels from the numpy
     #     statement of the blend modes (tests/layer_util.py). (a) alpha-blend of a layer that hangs over the canvas border, (b) add, (c) three
     #     layers: the second goes to slot 2 from the empty slot 2, the last one multiplies onto slot 1
