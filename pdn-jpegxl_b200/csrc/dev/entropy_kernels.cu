@@ -33,13 +33,17 @@ __device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f, const DLocal
   if (!br.Read(1)) { md.wp.p1 = br.Read(5); md.wp.p2 = br.Read(5); md.wp.p3a = br.Read(5); md.wp.p3b = br.Read(5); md.wp.p3c = br.Read(5); md.wp.p3d = br.Read(5); md.wp.p3e = br.Read(5); for (int i = 0; i < 4; i++) md.wp.w[i] = br.Read(4); }
   else { md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12; }
   uint32_t nt = br.ReadU32(0, 0, 0, 1, 4, 2, 8, 18);
-  md.grct_n = 0;
-  if (nt != 0 && (!rct_allowed || nt > uint32_t(ModDecoder::kMaxGroupRct))) { md.rd.err = kErrGroupTransform; return false; }
+  md.gt_n = 0;
+  if (nt != 0 && (!rct_allowed || nt > uint32_t(ModDecoder::kMaxGroupTransforms))) { md.rd.err = kErrGroupTransform; return false; }
   for (uint32_t i = 0; i < nt; i++) {
-    if (br.Read(2) != 0) { md.rd.err = kErrGroupTransform; return false; }   // palette / squeeze inside a group section
-    const uint32_t begin_c = br.ReadU32(3, 0, 6, 8, 10, 72, 13, 1096), type = br.ReadU32(0, 6, 2, 0, 4, 2, 6, 10);
-    if (type >= 42) { md.rd.err = kErrGroupTransform; return false; }
-    md.grct_begin[md.grct_n] = begin_c; md.grct_type[md.grct_n] = type; md.grct_n++;
+    const uint32_t id = br.Read(2); if (id > 1) { md.rd.err = kErrGroupTransform; return false; }   // squeeze inside a group section
+    const uint32_t begin_c = br.ReadU32(3, 0, 6, 8, 10, 72, 13, 1096); uint32_t a, b = 0;
+    if (id == 0) { a = br.ReadU32(0, 6, 2, 0, 4, 2, 6, 10); if (a >= 42) { md.rd.err = kErrGroupTransform; return false; } }
+    else {
+      a = br.ReadU32(0, 1, 0, 3, 0, 4, 13, 1); b = br.ReadU32(8, 0, 10, 256, 12, 1280, 16, 5376); const uint32_t nb_deltas = br.ReadU32(0, 0, 8, 1, 10, 257, 16, 1281); br.Read(4);   // predictor: only used by delta entries
+      if (nb_deltas != 0 || a > 4) { md.rd.err = kErrGroupTransform; return false; }
+    }
+    md.gt_kind[md.gt_n] = id; md.gt_begin[md.gt_n] = begin_c; md.gt_a[md.gt_n] = a; md.gt_b[md.gt_n] = b; md.gt_n++;
   }
   if (!use_global) {   // the tree and the code follow in the stream: the host has parsed them (Modular frames) or the stream is not supported
     if (!lt || !lt->present) { md.rd.err = kErrLocalTree; return false; }
@@ -244,47 +248,72 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
     rx0 = x0 >> ch.hshift; ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) return false;
     rw = min(gd >> ch.hshift, int(ch.w) - rx0); rh = min(gd >> ch.vshift, int(ch.h) - ry0); return rw > 0 && rh > 0;
   };
-  int nch = 0; uint32_t dm = 0;
-  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) { int rx0, ry0, rw, rh; if (region(c, rx0, ry0, rw, rh)) { nch++; dm = max(dm, uint32_t(rw)); } }
-  if (nch == 0) return;
-  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, f.encoding == 1 && pass == 0 ? LocalTreeOf(f, uint32_t(g)) : nullptr, true); if (ok) { md.rd.Init(md.cv); md.dist_mult = dm; } *flag = ok ? 1u : 0u; }
+  // the section's channel list: rectangles of the frame's channels (every lane derives the same list from the frame descriptor)
+  struct Loc { int32_t* p; int stride, w, h, hs, vs; };
+  static const int kMaxLoc = 12; Loc loc[kMaxLoc]; int nloc = 0; uint32_t dm = 0;
+  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels && nloc < 8; c++) {
+    int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
+    const DModChannel& ch = f.mod_ch[c]; loc[nloc++] = Loc{f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, int(ch.w), rw, rh, int(ch.hshift), int(ch.vshift)}; dm = max(dm, uint32_t(rw));
+  }
+  if (nloc == 0) return;
+  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, f.encoding == 1 && pass == 0 ? LocalTreeOf(f, uint32_t(g)) : nullptr, true); *flag = ok ? 1u : 0u; }
   __syncwarp();
   if (!*flag) return;
-  // the RCTs of this group's header, for every lane (lane 0 parsed them)
-  const uint32_t grct_n = __shfl_sync(0xffffffffu, md.grct_n, 0); uint32_t grct_begin[ModDecoder::kMaxGroupRct], grct_type[ModDecoder::kMaxGroupRct];
+  // the transforms of this section's own header, for every lane (lane 0 parsed them)
+  const int gt_n = int(__shfl_sync(0xffffffffu, md.gt_n, 0)); uint32_t gt_kind[ModDecoder::kMaxGroupTransforms], gt_begin[ModDecoder::kMaxGroupTransforms], gt_a[ModDecoder::kMaxGroupTransforms], gt_b[ModDecoder::kMaxGroupTransforms];
 #pragma unroll
-  for (int i = 0; i < ModDecoder::kMaxGroupRct; i++) { grct_begin[i] = __shfl_sync(0xffffffffu, md.grct_begin[i], 0); grct_type[i] = __shfl_sync(0xffffffffu, md.grct_type[i], 0); }
-  const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g; int k = 0;
+  for (int i = 0; i < ModDecoder::kMaxGroupTransforms; i++) { gt_kind[i] = __shfl_sync(0xffffffffu, md.gt_kind[i], 0); gt_begin[i] = __shfl_sync(0xffffffffu, md.gt_begin[i], 0); gt_a[i] = __shfl_sync(0xffffffffu, md.gt_a[i], 0); gt_b[i] = __shfl_sync(0xffffffffu, md.gt_b[i], 0); }
+  // ---- the channel list as coded: a palette replaces its channels by one index channel and puts the palette itself in front (meta channel)
+  Loc saved[ModDecoder::kMaxGroupTransforms][3]; int nb_meta = 0; uint32_t pal_used = 0; bool bad = false;
+  for (int t = 0; t < gt_n && !bad; t++) {
+    if (gt_kind[t] != 1) continue;
+    const int b0 = int(gt_begin[t]), nc = int(gt_a[t]), ncol = int(gt_b[t]);
+    if (b0 < nb_meta || b0 + nc > nloc || nloc + 1 > kMaxLoc || pal_used + uint32_t(ncol * nc) > kGroupPalInts || !f.group_pal) { bad = true; break; }
+    for (int j = 1; j < nc; j++) { bad = bad || loc[b0 + j].w != loc[b0].w || loc[b0 + j].h != loc[b0].h; saved[t][j - 1] = loc[b0 + j]; }
+    for (int j = b0 + nc; j < nloc; j++) loc[j - (nc - 1)] = loc[j];
+    nloc -= nc - 1;
+    for (int j = nloc; j > 0; j--) loc[j] = loc[j - 1];
+    loc[0] = Loc{f.group_pal + size_t(g) * kGroupPalInts + pal_used, ncol, ncol, nc, -1, -1}; nloc++; nb_meta++; pal_used += uint32_t(ncol * nc); dm = max(dm, uint32_t(ncol));
+  }
+  if (bad) { if (lane == 0) md.rd.err = kErrGroupTransform; return; }
+  if (lane == 0) { md.rd.Init(md.cv); md.dist_mult = dm; }
+  const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g;
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth);
-  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) {
-    int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
-    const DModChannel& ch = f.mod_ch[c]; int32_t* dst = f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0;
-    if (lane == 0) { if (k == 0) md.ResetChannels(); md.NoteChannel(dst, ch.w, rw, rh, int(ch.hshift), int(ch.vshift)); prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(k, sid, prep, spec_bytes))) md.DecodeChannel<kNarrow>(k, sid, dst, ch.w, rw, rh, wp); }
+  for (int k = 0; k < nloc; k++) {
+    const Loc& L = loc[k];
+    if (lane == 0) { if (k == 0) md.ResetChannels(); md.NoteChannel(L.p, size_t(L.stride), L.w, L.h, L.hs, L.vs); prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(k, sid, prep, spec_bytes))) md.DecodeChannel<kNarrow>(k, sid, L.p, size_t(L.stride), L.w, L.h, wp); }
     __syncwarp();
-    if (prep.ok) { DecodeRowsLeanSpec(prep, reinterpret_cast<const uint8_t*>(md.cv.alias), md.cv.log_alpha, T, dst, ch.w, rw, rh, lane); if (lane == 0) md.FinishLeanSpec(prep); }
+    if (prep.ok) { DecodeRowsLeanSpec(prep, reinterpret_cast<const uint8_t*>(md.cv.alias), md.cv.log_alpha, T, L.p, size_t(L.stride), L.w, L.h, lane); if (lane == 0) md.FinishLeanSpec(prep); }
     __syncwarp();
-    k++;
   }
   if (lane == 0 && !md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
-  // ---- undo the group's own RCTs on its rectangles, last listed first (the channel indices count the channels of THIS section)
+  // ---- undo the section's own transforms on its rectangles, last listed first
   __syncwarp();
-  for (int t = int(grct_n) - 1; t >= 0; t--) {
-    int32_t* p[3] = {nullptr, nullptr, nullptr}; int stride[3] = {0, 0, 0}, rw0 = 0, rh0 = 0; bool same = true; int kk = 0;
-    for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) {
-      int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
-      const int j = kk - int(grct_begin[t]);
-      if (j >= 0 && j < 3) { const DModChannel& ch = f.mod_ch[c]; p[j] = f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0; stride[j] = int(ch.w); if (j == 0) { rw0 = rw; rh0 = rh; } else same = same && rw == rw0 && rh == rh0; }
-      kk++;
-    }
-    if (!p[0] || !p[1] || !p[2] || !same) { if (lane == 0) md.rd.err = md.rd.err ? md.rd.err : kErrGroupTransform; break; }
-    const uint32_t perm = grct_type[t] / 7, kind = grct_type[t] % 7;
-    for (int i = lane; i < rw0 * rh0; i += 32) {
-      const int y = i / rw0, x = i - y * rw0; int32_t* q0 = p[0] + size_t(y) * stride[0] + x; int32_t* q1 = p[1] + size_t(y) * stride[1] + x; int32_t* q2 = p[2] + size_t(y) * stride[2] + x;
-      const int32_t A = *q0, B = *q1, C = *q2; int32_t o[3];
-      if (kind == 6) { const int32_t tt = A - (C >> 1), G = C + tt, Bl = tt - (B >> 1), R = Bl + B; o[0] = R; o[1] = G; o[2] = Bl; }
-      else { int32_t D = A, E = B, F = C; if (kind & 1) F += A; if ((kind >> 1) == 1) E += A; if ((kind >> 1) == 2) E += (A + F) >> 1; o[0] = D; o[1] = E; o[2] = F; }
-      int32_t r[3]; r[perm % 3] = o[0]; r[(perm + 1 + perm / 3) % 3] = o[1]; r[(perm + 2 - perm / 3) % 3] = o[2];
-      *q0 = r[0]; *q1 = r[1]; *q2 = r[2];
+  for (int t = gt_n - 1; t >= 0; t--) {
+    const int b0 = int(gt_begin[t]);
+    if (gt_kind[t] == 0) {
+      if (b0 < nb_meta || b0 + 3 > nloc || loc[b0 + 1].w != loc[b0].w || loc[b0 + 2].w != loc[b0].w || loc[b0 + 1].h != loc[b0].h || loc[b0 + 2].h != loc[b0].h) { if (lane == 0) md.rd.err = md.rd.err ? md.rd.err : kErrGroupTransform; break; }
+      const uint32_t perm = gt_a[t] / 7, kind = gt_a[t] % 7; const int rw0 = loc[b0].w, rh0 = loc[b0].h;
+      for (int i = lane; i < rw0 * rh0; i += 32) {
+        const int y = i / rw0, x = i - y * rw0; int32_t* q0 = loc[b0].p + size_t(y) * loc[b0].stride + x; int32_t* q1 = loc[b0 + 1].p + size_t(y) * loc[b0 + 1].stride + x; int32_t* q2 = loc[b0 + 2].p + size_t(y) * loc[b0 + 2].stride + x;
+        const int32_t A = *q0, B = *q1, C = *q2; int32_t o[3];
+        if (kind == 6) { const int32_t tt = A - (C >> 1), G = C + tt, Bl = tt - (B >> 1), R = Bl + B; o[0] = R; o[1] = G; o[2] = Bl; }
+        else { int32_t D = A, E = B, F = C; if (kind & 1) F += A; if ((kind >> 1) == 1) E += A; if ((kind >> 1) == 2) E += (A + F) >> 1; o[0] = D; o[1] = E; o[2] = F; }
+        int32_t r[3]; r[perm % 3] = o[0]; r[(perm + 1 + perm / 3) % 3] = o[1]; r[(perm + 2 - perm / 3) % 3] = o[2];
+        *q0 = r[0]; *q1 = r[1]; *q2 = r[2];
+      }
+    } else {   // palette: loc[0] is the palette, loc[b0 + 1] the index channel; colour 0 overwrites the index plane, the others go back to their own planes
+      const Loc pal = loc[0], idx = loc[b0 + 1]; const int nc = int(gt_a[t]); bool neg = false;
+      for (int i = lane; i < idx.w * idx.h; i += 32) {
+        const int y = i / idx.w, x = i - y * idx.w; const int index = idx.p[size_t(y) * idx.stride + x];
+        for (int c = nc - 1; c >= 0; c--) { const int32_t v = PaletteLookup(pal.p + size_t(c) * pal.stride, index, c, pal.w, int(f.mod_bitdepth), &neg); const Loc& o = c == 0 ? idx : saved[t][c - 1]; o.p[size_t(y) * o.stride + x] = v; }
+      }
+      if (__any_sync(0xffffffffu, neg) && lane == 0) md.rd.err = md.rd.err ? md.rd.err : kErrPaletteDelta;   // only lane 0's error word is reported
+      for (int j = 0; j + 1 < nloc; j++) loc[j] = loc[j + 1];   // drop the palette: the index channel is now at b0
+      nloc--; nb_meta--;
+      for (int j = nloc - 1; j > b0; j--) loc[j + nc - 1] = loc[j];
+      for (int j = 1; j < nc; j++) loc[b0 + j] = saved[t][j - 1];
+      nloc += nc - 1;
     }
     __syncwarp();
   }

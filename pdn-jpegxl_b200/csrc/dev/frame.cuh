@@ -60,13 +60,14 @@ struct DFrame {
   const uint8_t* comp; const uint8_t* blob; const uint8_t* static_blob;
   int32_t* lfq; float* lf; float* lf_tmp; uint8_t* acs; uint8_t* hf_mul_m1; uint8_t* sharp; uint8_t* lf_idx; int8_t* ytox; int8_t* ytob; int32_t* hfmeta_scratch;
   const float* lf_src; const struct DTables* tables;
-  int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos; uint64_t* ac_endpos; uint8_t* nz_scratch; uint32_t* host_flags; uint32_t* lz_window;   /* LZ77 windows: kLzWindow values per stream (slots: LF group g | group g | last: global), null when no code uses LZ77 */ uint32_t* group_other;   // group_other[g]: number of varblocks in group g that are not plain DCT8
+  int16_t* coeffs; float* xyb; float* xyb_tmp; float* inv_sigma; int32_t* mod_planes; int32_t* wp_scratch; uint8_t* out_px; uint32_t* err; uint64_t* end_bitpos; uint64_t* ac_endpos; uint8_t* nz_scratch; uint32_t* host_flags; int32_t* group_pal;   /* kGroupPalInts ints per group: the palette channels of palettes listed in group sections' own headers */ uint32_t* lz_window;   /* LZ77 windows: kLzWindow values per stream (slots: LF group g | group g | last: global), null when no code uses LZ77 */ uint32_t* group_other;   // group_other[g]: number of varblocks in group g that are not plain DCT8
 };
 // A bundle of images decoded by one launch of an entropy kernel (batches): passed by value like DFrame (4 x 3.4 KB of the 32 KB
 // parameter space). CTA `first[i]` .. `first[i+1]-1` (after `cta_offset` empty CTAs) belong to image i. Raises the number of images
 // in flight past the 128-resident-grid limit of the device.
 static const int kMaxBundle = 4;
 struct DFrameSet { uint32_t n, cta_offset; uint32_t first[kMaxBundle + 1]; uint32_t pad; DFrame f[kMaxBundle]; };
+static const uint32_t kGroupPalInts = 4096;   // colours x channels a group section's own palettes may hold
 static const uint32_t kHfMetaScratchInts = 2 * 1024 + 2 * 65536 + 65536;
 
 // Offsets with the top bit set address the per-device static blob (default dequant tables, natural coefficient orders)

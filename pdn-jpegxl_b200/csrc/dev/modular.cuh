@@ -98,9 +98,10 @@ struct ModDecoder {
   SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; uint32_t dist_mult = 0; /* LZ77: widest channel of the sub-bitstream */ ChanLut* lut;
   // Earlier channels of the same sub-bitstream with the geometry of the channel being decoded, nearest first (MA-tree properties 16 + 4k .. 19 + 4k:
   // |v|, v, |v - g|, v - g of that channel's sample at the same position, g its clamped gradient). The caller keeps the list (NoteChannel).
-  // Transforms listed in the sub-bitstream's own header (group sections): only RCTs are undone on the device (what libjxl's lossless encoder picks
-  // per group); a header that lists anything else, or RCTs where the caller cannot undo them, is refused.
-  static const int kMaxGroupRct = 4; uint32_t grct_n = 0, grct_begin[kMaxGroupRct], grct_type[kMaxGroupRct];
+  // Transforms listed in the sub-bitstream's own header (group sections): RCTs and palettes without delta entries are undone on the device (what
+  // libjxl's lossless encoder picks per group); a header that lists anything else, or transforms where the caller cannot undo them, is refused.
+  // kind 0 RCT: a = rct_type. kind 1 Palette (no delta entries): a = num_c, b = number of colours.
+  static const int kMaxGroupTransforms = 4; uint32_t gt_n = 0, gt_kind[kMaxGroupTransforms], gt_begin[kMaxGroupTransforms], gt_a[kMaxGroupTransforms], gt_b[kMaxGroupTransforms];
   static const int kMaxRefs = 4; const int32_t* ref_p[kMaxRefs]; size_t ref_stride[kMaxRefs]; int ref_n = 0;
   struct Seen { const int32_t* p; size_t stride; int w, h, hs, vs; }; Seen seen[8]; int num_seen = 0;
   __device__ void ResetChannels() { num_seen = 0; ref_n = 0; }
@@ -355,5 +356,17 @@ static __device__ __noinline__ void DecodeRowsLeanSpec(LeanSpecPrep& P, const ui
   __syncwarp();
 }
 #endif
+
+// Palette index -> sample of colour channel c (SURVEY.md A.7 "Palette"): explicit entries [0, pal_w), then the implicit 4x4x4 cube (64 entries,
+// offset by 2^(bitdepth-3)) and the implicit 5x5x5 cube. Negative indices address the 72-entry delta palette, whose table is not available
+// offline: *bad is set for them.
+__device__ __forceinline__ int32_t PaletteLookup(const int32_t* pal_row, int index, int c, int pal_w, int bitdepth, bool* bad) {
+  if (index < 0) { *bad = true; return 0; }
+  if (index < pal_w) return pal_row[index];
+  if (c > 2) return 0;
+  const long long maxv = (1ll << bitdepth) - 1;
+  if (index < pal_w + 64) { const int i2 = index - pal_w, div = c == 0 ? 1 : c == 1 ? 4 : 16; return int32_t((((long long)((i2 / div) % 4) * maxv) >> 2) + (1ll << max(0, bitdepth - 3))); }
+  const int i2 = index - pal_w - 64, div = c == 0 ? 1 : c == 1 ? 5 : 25; return int32_t(((long long)((i2 / div) % 5) * maxv) >> 2);
+}
 
 }  // namespace jxlgpu

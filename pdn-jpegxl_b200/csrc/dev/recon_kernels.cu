@@ -426,12 +426,7 @@ __global__ void k_inverse_rct(const DFrame* fp, uint32_t op_index) {
 // Index -> colour: explicit entries [0, pal_w), then the implicit 4x4x4 cube (64 entries, offset by 2^(bitdepth-3)) and the implicit 5x5x5
 // cube. Negative indices address the 72-entry delta palette, whose table is not available offline: they raise kErrPaletteDelta.
 __device__ __forceinline__ int32_t PaletteValue(const int32_t* pal_row, int index, int c, int pal_w, int bitdepth, uint32_t* err) {
-  if (index < 0) { SetError(err, kErrPaletteDelta); return 0; }
-  if (index < pal_w) return pal_row[index];
-  if (c > 2) return 0;
-  const long long maxv = (1ll << bitdepth) - 1;
-  if (index < pal_w + 64) { const int i2 = index - pal_w, div = c == 0 ? 1 : c == 1 ? 4 : 16; return int32_t((((long long)((i2 / div) % 4) * maxv) >> 2) + (1ll << max(0, bitdepth - 3))); }
-  const int i2 = index - pal_w - 64, div = c == 0 ? 1 : c == 1 ? 5 : 25; return int32_t(((long long)((i2 / div) % 5) * maxv) >> 2);
+  bool bad = false; const int32_t v = PaletteLookup(pal_row, index, c, pal_w, bitdepth, &bad); if (bad) SetError(err, kErrPaletteDelta); return v;
 }
 // Pure gather: one thread per sample and output channel (blockIdx.y). Used when the palette has no delta entries.
 __global__ void k_inverse_palette(const DFrame* fp, uint32_t op_index) {

@@ -777,8 +777,8 @@ def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=No
     """One Modular frame (frame header, TOC, sections) of `channels` (its own size); starts byte-aligned. **header: crop, canvas, blend, ec_blend,
     is_last, save_as_reference of frame_header(). local_global: the frame has NO global MA tree and the global stream brings its own (tree, data_code).
     group_local = (tree, code): every group section brings this tree and code of its own instead of using the global ones.
-    group_rct = function(group index) -> list of (begin_c, rct_type): RCTs listed in that group's own header (what libjxl's lossless encoder chooses
-    per group), applied to the group's rectangles in the order listed."""
+    group_rct = function(group index) -> list of (begin_c, rct_type) / ("palette", dict(begin, num_c, colors)): transforms listed in that group's own
+    header (what libjxl's lossless encoder chooses per group), applied to the group's rectangles in the order listed."""
     h, w = len(channels[0]), len(channels[0][0])
     tree = tree or Leaf(0, 5)
     b = Bits()
@@ -825,11 +825,19 @@ def modular_frame(channels, num_extra, bits=8, tree=None, data_code=None, rct=No
             s = Bits()
             if not fits:
                 gtree, gcode = group_local if group_local else (tree, code)
-                rcts = group_rct(gi) if group_rct else []
-                group_header(s, transforms=[("rct", bc, ty) for bc, ty in rcts], local=group_local)
+                gts = group_rct(gi) if group_rct else []      # (begin_c, rct_type) or ("palette", dict(begin, num_c, colors)), in the order listed
                 sub = [[row[x0:x0 + gdim] for row in ch[y0:y0 + gdim]] for ch in planes[nb_meta:]]
-                for bc, ty in rcts:
-                    sub = forward_rct(sub, bc, ty)
+                listed = []
+                for gt in gts:
+                    if gt[0] == "palette":
+                        pl = gt[1]
+                        gpal, gidx = forward_palette(sub, pl["begin"], pl["num_c"], pl["colors"], bits)
+                        sub = [gpal] + sub[:pl["begin"]] + [gidx] + sub[pl["begin"] + pl["num_c"]:]
+                        listed.append(("palette", pl["begin"], pl["num_c"], len(pl["colors"]), 0, 0))
+                    else:
+                        sub = forward_rct(sub, gt[0], gt[1])
+                        listed.append(("rct", gt[0], gt[1]))
+                group_header(s, transforms=listed, local=group_local)
                 gcode.write_stream(s, pack(modular_items(gtree, sub, 1 + 3 * nlf + 17 + gi)))   # channels are numbered from 0 inside a group section
             sections.append(s.bytes())
     # toc_permutation lists the logical section indices in the order they are stored in the file. The TOC codes the sizes in FILE

@@ -192,6 +192,26 @@ def cases():
     a = _img(150, 200, 4, seed=24)
     out.append(("rgba8_rct_per_group_local_trees", W.modular_image(_planes(a), alpha_bits=8, group_size_shift=0, group_rct=lambda gi: [(0, 6 + gi)], group_local=(ltree, lcode)),
                 a.astype(np.uint8), dict(width=200, height=150, format="Rgb", num_channels=4, has_transparency=True)))
+    # 13e. Palettes listed in group sections' own headers: a channel palette on alpha in every group (its own level set per group), and in one group an
+    #      RGB palette of that group's colours followed by nothing, in another an RCT followed by a channel palette on the first channel
+    a = _img(150, 200, 4, seed=25)
+    a[..., 3] = (a[..., 3] // 40) * 40 + 7
+    def gt_alpha(gi):
+        x0g, y0g = (gi % 2) * 128, (gi // 2) * 128
+        sub = a[y0g:y0g + 128, x0g:x0g + 128]
+        lv = sorted(set(int(v) for v in sub[..., 3].ravel()))
+        gts = [("palette", dict(begin=3, num_c=1, colors=[(v,) for v in lv]))]
+        if gi == 1:
+            gts = [(0, 6)] + gts
+        return gts
+    out.append(("rgba8_group_alpha_palettes", W.modular_image(_planes(a), alpha_bits=8, group_size_shift=0, group_rct=gt_alpha), a.astype(np.uint8), dict(width=200, height=150, format="Rgb", num_channels=4, has_transparency=True)))
+    a = paletted(130, 250, 6)
+    def gt_rgb(gi):
+        x0g, y0g = (gi % 2) * 128, (gi // 2) * 128
+        sub = a[y0g:y0g + 128, x0g:x0g + 128].reshape(-1, 3)
+        cols = sorted(set(tuple(int(v) for v in px) for px in sub))
+        return [("palette", dict(begin=0, num_c=3, colors=cols))] if gi != 2 else []
+    out.append(("rgb8_group_rgb_palettes", W.modular_image(_planes(a), group_size_shift=0, group_rct=gt_rgb), a.astype(np.uint8), dict(width=250, height=130, format="Rgb", num_channels=3)))
     # 14. Layered stills (F.2 crop + BlendingInfo, reference slots): every frame carries its crop rectangle; expected pixels from the numpy
     #     statement of the blend modes (tests/layer_util.py). (a) alpha-blend of a layer that hangs over the canvas border, (b) add, (c) three
     #     layers: the second goes to slot 2 from the empty slot 2, the last one multiplies onto slot 1
