@@ -13,12 +13,14 @@ host_only = "--host-only" in sys.argv
 img = O.synthetic_image(200, 136, seed=1, channels=4)
 seeds = [O.encode(img, effort=7), O.encode(img, lossless=1), O.encode(img[..., :3], effort=3, use_prefix=1), O.encode(img, effort=5, num_passes=2),
          O.encode_layers(200, 136, [(img, {}), (img[:60, :80], dict(x0=15, y0=25, mode="blend"))], lossless=1)]
-seeds += [bytes(c[1]) for c in spec_cases.cases() if c[0] in ("rgb8_palette_groups", "rgb8_lz77_multigroup", "rgb8_prev_channel_props", "rgb8_permuted_toc")]
+seeds += [bytes(c[1]) for c in spec_cases.cases() if c[0] in ("rgb8_palette_groups", "rgb8_lz77_multigroup", "rgb8_prev_channel_props", "rgb8_permuted_toc", "rgb8_palette_deltas",
+                                                            "rgb8_local_trees_in_groups", "rgb8_palette_all_local", "rgba8_rct_per_group_local_trees", "rgba8_group_alpha_palettes",
+                                                            "rgb8_group_rgb_palettes", "layers_three_slots_mul", "rgba8_two_palettes")]
 rng = random.Random(4321); n = 0; t0 = time.time(); hist = {}
 while time.time() - t0 < budget:
     s = bytearray(rng.choice(seeds))
     for _ in range(rng.randint(1, 4)):
-        if len(s) < 8:
+        if len(s) < 10:
             break
         m = rng.random()
         if m < 0.55:
