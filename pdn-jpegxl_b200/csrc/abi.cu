@@ -216,6 +216,18 @@ static std::vector<cudaStream_t>& ShardStreams(int device, int slot, int want) {
   return v;
 }
 
+// Pacing of batches whose pixels go to HOST memory. Such a batch is bound by the device-to-host copy (9.2 GB per 256 images of 12 MP: 166 ms at
+// the 55.6 GB/s this box's PCIe link delivers, against 151 ms of decode), and started all at once its images move through LF / AC / tiles in
+// lock-step, so every copy waits for the tiles phase at the end (r02: 267 ms per step = ~100 ms until the first image is rendered + 167 ms of
+// copies). Starting the images at the rate the link can take them away turns the batch into a rolling pipeline: copies run from the first
+// finished image on, beside the entropy phases of the images started later. One pacer per device, shared by every batch in flight on it.
+static std::atomic<int64_t> g_pace_next_ns[64];
+static int64_t SteadyNs() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static int64_t PaceReserve(int dev, int64_t step_ns) {   // -> earliest start time of the caller's next bundle
+  std::atomic<int64_t>& next = g_pace_next_ns[dev & 63]; const int64_t now = SteadyNs(); int64_t prev = next.load();
+  for (;;) { const int64_t t = std::max(prev, now); if (next.compare_exchange_weak(prev, t + step_ns)) return t; }
+}
+
 static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int nstreams, int batch_lanes, int bundle_size, size_t reserve_sets, ShardResult* out) {
   const int count = end - begin;
   if (count <= 0) return;
@@ -307,9 +319,18 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
       return progressed;
     };
     bool reserved = reserve_sets == 0;
+    // pacing (host outputs only): ns per image = its output bytes over the link rate (JXLB200_D2H_GBPS, default 60: a little faster than the
+    // link, the in-flight cap gives the back-pressure); JXLB200_PACE=0 switches it off
+    int64_t pace_ns = 0, launch_at = 0;
+    if (a.hostOutputs && a.count >= 64) {
+      const char* off = getenv("JXLB200_PACE"); const double gbps = getenv("JXLB200_D2H_GBPS") ? atof(getenv("JXLB200_D2H_GBPS")) : 60.0;
+      if (!(off && *off == '0') && gbps > 0) pace_ns = int64_t(double(a.outputBytes[begin]) / gbps);
+    }
     while (done < count) {
       double t0 = now(); bool progressed = advance(); t_ret += now() - t0;
-      if (next < count && !free_streams.empty()) {
+      if (pace_ns && next < count && !free_streams.empty() && launch_at == 0) launch_at = PaceReserve(cur_dev, pace_ns * std::min(bundle_size, count - next));
+      if (next < count && !free_streams.empty() && (launch_at == 0 || SteadyNs() >= launch_at)) {
+        launch_at = 0;
         t0 = now();
         std::unique_ptr<Bundle> b(new Bundle); b->stream = free_streams.back(); free_streams.pop_back();
         for (int k = 0; k < bundle_size && next < count; k++) {
