@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images (seeds 0..distinct-1), repeated to fill the batch")
     ap.add_argument("--in-flight", type=int, default=128)
-    ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the end-to-end measurement (JxlB200DecodeBatchSubmit / Wait); 1 = synchronous calls")
+    ap.add_argument("--e2e-depth", type=int, default=1, help="batches in flight in the end-to-end measurement (JxlB200DecodeBatchSubmit / Wait); 1 = synchronous calls")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--no-mixed", action="store_true", help="skip the second (variable-block) workload")
     return ap.parse_args()
@@ -246,8 +246,8 @@ def main():
     out_bytes_one = W * H * 3
     total_mp_step = (args.batch if args.scaling == "strong" else args.batch * world) * W * H / 1e6
     dev_out = [torch.empty(out_bytes_one, dtype=torch.uint8, device="cuda") for _ in range(B)]
-    # two sets of host output buffers: the end-to-end steps are submitted asynchronously with two batches in flight (a service that
-    # keeps the link busy: the copies of step k run beside the entropy phases of step k + 1), each writing its own set
+    # --e2e-depth N > 1: the end-to-end steps are submitted asynchronously with N batches in flight, each writing its own set of host buffers
+    # (measured in r02: two batches in flight are SLOWER than synchronous calls, 378 vs 260 ms per step — profiles/r02_e2e_pipeline.md)
     E2E_DEPTH = max(1, args.e2e_depth)
     try:
         host_out = [torch.empty(out_bytes_one, dtype=torch.uint8).pin_memory() for _ in range(B * E2E_DEPTH)]
