@@ -183,7 +183,9 @@ std::vector<std::vector<uint64_t>> TrimmedHist(const uint64_t* flat, size_t num_
 
 }  // namespace
 
-struct BandSection { uint32_t kind = 0, index = 0; uint64_t bits = 0; std::vector<uint8_t> bytes; };   // kind: 0 global Modular stream, 1 LF group, 2 pass group
+// kind: 0 global Modular stream, 1 LF group, 2 pass group. The payload is either owned (`bytes`) or a view into a band's serialised blob.
+struct BandSection { uint32_t kind = 0, index = 0; uint64_t bits = 0; std::vector<uint8_t> bytes; const uint8_t* view = nullptr; size_t view_n = 0;
+  const uint8_t* data() const { return view ? view : bytes.data(); } size_t size() const { return view ? view_n : bytes.size(); } };
 
 class BandEncoder {
  public:
@@ -419,8 +421,34 @@ std::vector<uint8_t> AssembleFile(const EncPlan& plan, const std::vector<uint64_
   if (!lossless) for (uint32_t g = 0; g < nlf; g++) JXLG_CHECK(lf_sec[g], "a band is missing: LF group without a section");
   for (uint32_t g = 0; g < ng; g++) JXLG_CHECK(grp_sec[g], "a band is missing: group without a section");
   JXLG_CHECK(!plan.global_has_modular || global_sec, "global Modular stream missing");
+  if (!single) {
+    // Every section of a multi-section frame is byte-aligned and arrives padded: LfGlobal and HfGlobal are written here, the TOC follows from the
+    // sizes, and the bands' sections are copied ONCE, straight into the file (a 1 GP frame is 119 MB of sections: every extra pass over them counts).
+    BitWriter lfg; lfg.Bool(true);
+    if (!lossless) { lfg.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193), plan.global_scale); lfg.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1), plan.quant_lf); lfg.Bool(true); lfg.Bool(true); }
+    lfg.Bool(true); WriteCode(lfg, plan.tree_code); WriteTokens(lfg, plan.tree_code, plan.tree_tokens); WriteCode(lfg, codes.mcode);
+    if (plan.nplanes > 0) WriteGroupHeader(lfg, plan.gheader);
+    BitWriter hfg; if (!lossless) { hfg.Bool(true); hfg.Write(CeilLog2(ng), 0); hfg.U32(Val(0x5F), Val(0x13), Val(0), Bits(13), 0); WriteCode(hfg, codes.acode); }
+    const std::vector<uint8_t> lfg_bytes = lfg.Finish(), hfg_bytes = hfg.Finish();
+    std::vector<size_t> sizes(nsec, 0); sizes[0] = lfg_bytes.size(); sizes[1 + nlf] = hfg_bytes.size();
+    for (uint32_t g = 0; g < nlf; g++) sizes[1 + g] = lf_sec[g] ? lf_sec[g]->size() : 0;
+    for (uint32_t g = 0; g < ng; g++) sizes[2 + nlf + g] = grp_sec[g]->size();
+    BitWriter cs; cs.Write(16, 0x0AFF); WriteImageHeaders(cs, plan.m); WriteFrameHeader(cs, fh, plan.m); WriteToc(cs, sizes); const std::vector<uint8_t> head = cs.Finish();
+    uint64_t payload = head.size(); for (size_t v : sizes) payload += v;
+    std::vector<uint8_t> file = ContainerPrologue();
+    if (meta.exif_size) AppendBox(file, "Exif", meta.exif, meta.exif_size); if (meta.xmp_size) AppendBox(file, "xml ", meta.xmp, meta.xmp_size);
+    file.reserve(file.size() + 16 + payload);
+    {   // the jxlc box header (extended size past 4 GB), then the payload piece by piece
+      uint64_t total = payload + 8; if (total > 0xffffffffull) { total += 8; uint8_t hh[16] = {0, 0, 0, 1, 'j', 'x', 'l', 'c'}; for (int i = 0; i < 8; i++) hh[8 + i] = uint8_t(total >> (56 - 8 * i)); file.insert(file.end(), hh, hh + 16); }
+      else { uint8_t hh[8] = {uint8_t(total >> 24), uint8_t(total >> 16), uint8_t(total >> 8), uint8_t(total), 'j', 'x', 'l', 'c'}; file.insert(file.end(), hh, hh + 8); } }
+    file.insert(file.end(), head.begin(), head.end()); file.insert(file.end(), lfg_bytes.begin(), lfg_bytes.end());
+    for (uint32_t g = 0; g < nlf; g++) if (lf_sec[g]) file.insert(file.end(), lf_sec[g]->data(), lf_sec[g]->data() + lf_sec[g]->size());
+    file.insert(file.end(), hfg_bytes.begin(), hfg_bytes.end());
+    for (uint32_t g = 0; g < ng; g++) file.insert(file.end(), grp_sec[g]->data(), grp_sec[g]->data() + grp_sec[g]->size());
+    return file;
+  }
   std::vector<BitWriter> secw(single ? 1 : nsec); auto W = [&](size_t i) -> BitWriter& { return single ? secw[0] : secw[i]; };
-  auto append = [&](BitWriter& bw, const BandSection* s) { if (s) AppendBits(bw, s->bytes.data(), s->bits); };
+  auto append = [&](BitWriter& bw, const BandSection* s) { if (s) AppendBits(bw, s->data(), s->bits); };
   { BitWriter& bw = W(0);
     bw.Bool(true);   // LfChannelDequantization all_default: present for Modular frames too
     if (!lossless) { bw.U32(BitsOffset(11, 1), BitsOffset(11, 2049), BitsOffset(12, 4097), BitsOffset(16, 8193), plan.global_scale); bw.U32(Val(16), BitsOffset(5, 1), BitsOffset(8, 1), BitsOffset(16, 1), plan.quant_lf); bw.Bool(true); bw.Bool(true); }
@@ -468,7 +496,7 @@ static std::vector<uint8_t> SerializeSections(const std::vector<BandSection>& se
 static std::vector<BandSection> ParseSections(const uint8_t* p, size_t n) {
   std::vector<BandSection> out; size_t pos = 0; auto get = [&](void* d, size_t k) { JXLG_CHECK(k <= n - pos, "band sections truncated"); memcpy(d, p + pos, k); pos += k; };
   uint32_t magic = 0, count = 0; get(&magic, 4); get(&count, 4); JXLG_CHECK(magic == 0x4253584a, "band sections: bad magic");
-  for (uint32_t i = 0; i < count; i++) { BandSection s; uint64_t nb = 0; get(&s.kind, 4); get(&s.index, 4); get(&s.bits, 8); get(&nb, 8); JXLG_CHECK(nb <= n - pos && s.bits <= nb * 8, "band sections truncated"); s.bytes.assign(p + pos, p + pos + nb); pos += nb; out.push_back(std::move(s)); }
+  for (uint32_t i = 0; i < count; i++) { BandSection s; uint64_t nb = 0; get(&s.kind, 4); get(&s.index, 4); get(&s.bits, 8); get(&nb, 8); JXLG_CHECK(nb <= n - pos && s.bits <= nb * 8, "band sections truncated"); s.view = p + pos; s.view_n = size_t(nb); pos += nb; out.push_back(std::move(s)); }   // a view: the blob outlives the assembly
   return out;
 }
 
