@@ -342,6 +342,9 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
           if (reserve_sets == 0 && a.count >= 32) for (int spin = 0; spin < 40000 && !g_pools_warm[cur_dev & 63].load(); spin++) std::this_thread::sleep_for(std::chrono::microseconds(50));   // at most 2 s, first batch only
           f->job = DecodeEnqueue(req, b->stream, &f->res, true, bundle_size > 1);
           if (!reserved) { reserved = true; if (f->job) DecodeReservePools(f->job, reserve_sets); g_pools_warm[cur_dev & 63].store(1); }   // the first image tells the buffer sizes of the batch
+          if (!f->job && f->res.layered) {   // a layered still inside a batch: composited by the single-image path, on this shard's thread
+            DecodeRequest lr = req; lr.ac_lanes = 0; f->res = DecodeOnGpu(lr);
+          }
           if (f->job) b->items.push_back(std::move(f)); else finish(*f);
         }
         if (bundle_size > 1) DecodeBundleLaunch(jobs_of(*b), 1);

@@ -601,7 +601,7 @@ std::shared_ptr<DecodeJob> DecodeEnqueue(const DecodeRequest& req, cudaStream_t 
     res->status = ParseHeadersInto(req.data, req.size, &job->hd, &job->info, &res->message); if (res->status != Status::Ok) { job.reset(); return job; }
     g_trace.t[0] += NowMs() - t0; t0 = NowMs(); job->phased = lf_phase_only; job->defer_entropy = defer_entropy && lf_phase_only; job->Setup(req); g_trace.t[1] += NowMs() - t0; if (lf_phase_only) job->RunLf(req); else job->Run(req); res->info = job->info;
   } catch (const std::bad_alloc&) { res->status = Status::OutOfMemory; job.reset(); }
-  catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); if (job) res->info = job->info; job.reset(); }
+  catch (const std::exception& e) { res->status = Status::DecodeError; res->message = e.what(); res->layered = res->message.rfind("layered (multi-frame)", 0) == 0; if (job) res->info = job->info; job.reset(); }
   return job;
 }
 

@@ -44,6 +44,7 @@ struct DecodeResult {
   Status status = Status::Ok; std::string message; ParsedInfo info;
   uint8_t* pixels = nullptr; size_t pixel_bytes = 0;   // pinned host memory (or device memory when device_output), owned by the job
   uint32_t out_width = 0, out_height = 0; StageTimes times;
+  bool layered = false;   // DecodeEnqueue only: the file is a layered (multi-frame) still, which the phased batch pipeline does not decode — use DecodeOnGpu
   std::shared_ptr<DecodeJob> job;                       // keeps `pixels` alive
 };
 

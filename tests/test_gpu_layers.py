@@ -92,11 +92,18 @@ def test_layered_file_to_bgra_surface(gpu, oracle):
     assert int(np.abs(doc.surface.astype(np.int32) - fused.astype(np.int32)).max()) <= 1
 
 
-def test_batch_and_band_calls_refuse_layered_files(gpu, oracle):
+def test_layered_files_inside_a_batch_and_band_refusal(gpu, oracle):
+    """A batch may contain layered stills: they are composited by the single-image path while the other files go through the phased pipeline.
+    Band decode (one frame cut by group rows) has no meaning for a layered file and says so."""
     base = oracle.synthetic_image(W, H, seed=12, channels=4)
-    data = oracle.encode_layers(W, H, [(base, dict()), (base[:50, :50], dict(mode="add"))], lossless=1)
-    out = [np.empty((H, W, 4), np.uint8)]
-    st = gpu.decode_batch([data], out, raise_on_error=False)
-    assert st[0] != 0                                                                  # DecodeError, with the message below
+    layered = oracle.encode_layers(W, H, [(base, dict()), (base[:50, :50], dict(x0=20, y0=30, mode="add"))], lossless=1)
+    plain = oracle.encode(base, lossless=1)
+    files = [plain, layered, plain, layered]
+    outs = [np.zeros((H, W, 4), np.uint8) for _ in files]
+    st = gpu.decode_batch(files, outs)
+    assert list(st) == [0, 0, 0, 0]
+    want_layered = oracle.decode(layered).pixels
+    assert np.array_equal(outs[0], base) and np.array_equal(outs[2], base)
+    assert int(np.abs(outs[1].astype(np.int32) - want_layered.astype(np.int32)).max()) <= 1 and np.array_equal(outs[1], outs[3])
     with pytest.raises(gpu.FormatException, match="layered"):
-        gpu.band_layout(data)
+        gpu.band_layout(layered)
