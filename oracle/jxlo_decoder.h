@@ -148,7 +148,8 @@ inline void DecodeLfGroup(FrameState& fs, BitReader& br, uint32_t g) {
       }
     }
   }
-  DecodeModularGroup(fs, br, cx0 * 8, cy0 * 8, 2048, 2048, 3, 1000, StreamIdModularLf(fh, g));
+  { const int lf_dim = int(fh.group_dim) * 8;   // an LF group is 8 x 8 groups: 2048 px for VarDCT, 1024 .. 8192 px for Modular frames (group_size_shift)
+    DecodeModularGroup(fs, br, gx * lf_dim, gy * lf_dim, lf_dim, lf_dim, 3, 1000, StreamIdModularLf(fh, g)); }
   if (fh.encoding == 0) {
     int w = std::min(256, fs.xb - cx0), h = std::min(256, fs.yb - cy0);
     uint32_t nb = br.ReadBits(CeilLog2(uint64_t(w) * h)) + 1;

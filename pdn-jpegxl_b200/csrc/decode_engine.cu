@@ -178,7 +178,7 @@ DecodeResult ParseInfo(const uint8_t* data, size_t size) {
 // ---------------------------------------------------------------- blob builder
 struct Blob {
   std::vector<uint8_t> b; bool uses_lz77 = false;   // some code of this frame is LZ77-enabled: the kernels need their windows
-  uint32_t Add(const void* p, size_t n, size_t align = 16) { size_t o = (b.size() + align - 1) / align * align; b.resize(o + n); if (n) memcpy(&b[o], p, n); JXLG_CHECK(b.size() < (size_t(1) << 31), "table blob too large"); return uint32_t(o); }
+  uint32_t Add(const void* p, size_t n, size_t align = 16) { if (b.empty()) b.resize(16, 0);   /* offset 0 means "no table" to the kernels */ size_t o = (b.size() + align - 1) / align * align; b.resize(o + n); if (n) memcpy(&b[o], p, n); JXLG_CHECK(b.size() < (size_t(1) << 31), "table blob too large"); return uint32_t(o); }
   DCode AddCode(const Code& c) {
     DCode d; memset(&d, 0, sizeof(d)); d.num_ctx = uint32_t(c.ctx_map.size()); d.num_clusters = uint32_t(c.cfg.size()); d.log_alpha = uint32_t(c.log_alpha); d.use_prefix = c.use_prefix;
     d.ctx_map_off = Add(c.ctx_map.data(), c.ctx_map.size()); std::vector<DHybrid> cfg(c.cfg.size()); for (size_t i = 0; i < cfg.size(); i++) cfg[i] = DHybrid{uint8_t(c.cfg[i].split_exp), uint8_t(c.cfg[i].msb), uint8_t(c.cfg[i].lsb), 0};
@@ -226,7 +226,7 @@ static QuantEncoding ReadQuantEncodingHost(BitReader& br, int t) {
 // ---------------------------------------------------------------- the job
 class DecodeJob {
  public:
-  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false, layer = false; DLocalTree global_local = DLocalTree(); uint64_t mod_total_ints = 0;   /* int32 samples of all Modular planes: coded channels + the outputs of palette expansions */
+  Headers hd; ParsedInfo info; FrameHeader fh; Toc toc; DFrame h; Blob blob; bool bgra = false, device_output = false, layer = false; DLocalTree global_local = DLocalTree(); std::vector<DModOp> ops_host; bool mod_has_lf_level = false; uint64_t mod_total_ints = 0;   /* int32 samples of all Modular planes: coded channels + the outputs of palette expansions */
   DevBuf d_frame, d_blob, d_comp, d_lfq, d_lf, d_lf_tmp, d_acs, d_qf, d_sharp, d_lfidx, d_ytox, d_ytob, d_hfmeta, d_coeffs, d_xyb, d_xyb_tmp, d_sigma, d_mod, d_wp, d_out, d_err, h_out, h_err, h_comp, h_blob, h_misc, d_gother, d_nz, d_acend, d_lz, d_gpal, d_layer_out, h_layer_out;   /* *_layer_out: the finished canvas of a layered file (owned by the job of the frame that is shown) */
   std::function<void()> ac_budget; int ac_lanes = 1; bool phased = false; size_t coeffs_bytes = 0, xyb_row_shift = 0;
   bool defer_entropy = false, lf_pending = false, ac_pending = false;   // bundle mode: the LF / AC entropy launch is left to DecodeBundleLaunch*
@@ -304,27 +304,49 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
   JXLG_CHECK(ch.size() <= 8, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size()); h.num_ops = 0; h.first_group_channel = 0; global_has_data = false; mod_total_ints = 0;
   h.mod_bitdepth = m.bd.bits; { uint32_t mb = m.bd.bits; for (const auto& e : m.ec) mb = std::max(mb, e.bd.bits); h.mod_wide = (mb > 20 || !m.modular_16bit) ? 1 : 0; }
   const size_t num_image_channels = ch.size();
+  int nb_meta = 0;
   if (!ch.empty()) {
     gheader = ReadGroupHeader(br);
     // ---- the channel list as coded: the forward side of every transform (libjxl's MetaApply)
-    int nb_meta = 0;
-    for (const Transform& t : gheader.transforms) {
-      JXLG_CHECK(t.id != 2, "squeeze transforms are not supported by the GPU decoder yet");
+    for (Transform& t : gheader.transforms) {
       if (t.id == 0) { JXLG_CHECK(t.begin_c + 3 <= ch.size(), "RCT channel range"); continue; }
-      const uint32_t end_c = t.begin_c + t.num_c - 1; JXLG_CHECK(t.num_c >= 1 && t.num_c <= 4 && end_c < ch.size(), "palette channel range");
-      for (uint32_t c = t.begin_c + 1; c <= end_c; c++) JXLG_CHECK(ch[c].w == ch[t.begin_c].w && ch[c].h == ch[t.begin_c].h && ch[c].hshift == ch[t.begin_c].hshift && ch[c].vshift == ch[t.begin_c].vshift, "palette channel sizes");
-      if (int(t.begin_c) < nb_meta) { JXLG_CHECK(int(end_c) < nb_meta, "palette across the meta-channel boundary"); nb_meta += 2 - int(t.num_c); } else nb_meta += 1;
-      ch.erase(ch.begin() + t.begin_c + 1, ch.begin() + end_c + 1);
-      ch.insert(ch.begin(), DModChannel{t.nb_colors + t.nb_deltas, t.num_c, 0, 0, 0});   // the palette itself: one row per colour channel, always coded in the global section
+      if (t.id == 1) {
+        const uint32_t end_c = t.begin_c + t.num_c - 1; JXLG_CHECK(t.num_c >= 1 && t.num_c <= 4 && end_c < ch.size(), "palette channel range");
+        for (uint32_t c = t.begin_c + 1; c <= end_c; c++) JXLG_CHECK(ch[c].w == ch[t.begin_c].w && ch[c].h == ch[t.begin_c].h && ch[c].hshift == ch[t.begin_c].hshift && ch[c].vshift == ch[t.begin_c].vshift, "palette channel sizes");
+        if (int(t.begin_c) < nb_meta) { JXLG_CHECK(int(end_c) < nb_meta, "palette across the meta-channel boundary"); nb_meta += 2 - int(t.num_c); } else nb_meta += 1;
+        ch.erase(ch.begin() + t.begin_c + 1, ch.begin() + end_c + 1);
+        ch.insert(ch.begin(), DModChannel{t.nb_colors + t.nb_deltas, t.num_c, 0, 0, 0});   // the palette itself: one row per colour channel, always coded in the global section
+        continue;
+      }
+      // Squeeze: every step halves its channels (average, shift + 1) and appends / inserts the residual channels
+      if (t.squeezes.empty()) {   // default parameters (libjxl's DefaultSqueezeParameters): chroma first when the first two channels match, then alternate until <= 8 x 8
+        const int nb = int(ch.size()) - nb_meta; JXLG_CHECK(nb > 0, "squeeze without channels"); uint32_t w = ch[nb_meta].w, hh = ch[nb_meta].h;
+        if (nb > 2 && ch[nb_meta + 1].w == w && ch[nb_meta + 1].h == hh) { SqueezeParams p; p.horizontal = true; p.in_place = false; p.begin_c = uint32_t(nb_meta + 1); p.num_c = 2; t.squeezes.push_back(p); p.horizontal = false; t.squeezes.push_back(p); }
+        SqueezeParams p; p.begin_c = uint32_t(nb_meta); p.num_c = uint32_t(nb); p.in_place = true;
+        if (!(w > hh)) { if (hh > 8) { p.horizontal = false; t.squeezes.push_back(p); hh = (hh + 1) / 2; } }
+        while (w > 8 || hh > 8) { if (w > 8) { p.horizontal = true; t.squeezes.push_back(p); w = (w + 1) / 2; } if (hh > 8) { p.horizontal = false; t.squeezes.push_back(p); hh = (hh + 1) / 2; } }
+      }
+      for (const SqueezeParams& sq : t.squeezes) {
+        const uint32_t end_c = sq.begin_c + sq.num_c - 1; JXLG_CHECK(sq.num_c >= 1 && end_c < ch.size(), "squeeze channel range"); JXLG_CHECK(int(sq.begin_c) >= nb_meta, "squeeze of meta channels is not supported");
+        const size_t offset = sq.in_place ? size_t(end_c) + 1 : ch.size();
+        for (uint32_t c = sq.begin_c; c <= end_c; c++) {
+          DModChannel a = ch[c], r = a;
+          if (sq.horizontal) { a.w = (ch[c].w + 1) / 2; a.hshift++; r = DModChannel{ch[c].w - a.w, a.h, a.hshift, a.vshift, 0}; }
+          else { a.h = (ch[c].h + 1) / 2; a.vshift++; r = DModChannel{a.w, ch[c].h - a.h, a.hshift, a.vshift, 0}; }
+          JXLG_CHECK(a.hshift < 30 && a.vshift < 30, "squeeze depth"); ch[c] = a; ch.insert(ch.begin() + offset + (c - sq.begin_c), r);
+        }
+      }
     }
-    JXLG_CHECK(ch.size() <= 8, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size());
+    JXLG_CHECK(ch.size() <= 255, "too many Modular channels"); h.num_mod_channels = uint32_t(ch.size());
   }
-  uint64_t off = 0; for (auto& c : ch) { c.plane_off = off; off += uint64_t(c.w) * c.h; } for (size_t i = 0; i < ch.size(); i++) h.mod_ch[i] = ch[i];
+  uint64_t off = 0; for (auto& c : ch) { c.plane_off = off; off += uint64_t(c.w) * c.h; }
+  h.mod_ch_off = 0; if (ch.size() <= 8) { for (size_t i = 0; i < ch.size(); i++) h.mod_ch[i] = ch[i]; } else h.mod_ch_off = blob.Add(ch.data(), ch.size() * sizeof(DModChannel));
+  mod_has_lf_level = false; ops_host.clear(); h.ops_off = 0;
   if (!ch.empty()) {
     // ---- which of them the global section holds: meta channels always, then every channel up to the first one larger than a group
-    int nb_meta = 0; for (const Transform& t : gheader.transforms) if (t.id == 1) { if (int(t.begin_c) < nb_meta) nb_meta += 2 - int(t.num_c); else nb_meta += 1; }
     size_t c = 0; for (; c < ch.size(); c++) if (int(c) >= nb_meta && (ch[c].w > fh.group_dim || ch[c].h > fh.group_dim)) break;
     global_decoded = c; h.first_group_channel = uint32_t(c);
+    for (size_t i = c; i < ch.size(); i++) if (std::min(ch[i].hshift, ch[i].vshift) >= 3 && ch[i].w && ch[i].h) mod_has_lf_level = true;   // coded in the LF-group sections
     size_t nonempty = 0; for (size_t i = 0; i < c; i++) if (ch[i].w && ch[i].h) nonempty++;
     if (nonempty) {
       global_has_data = true;
@@ -335,23 +357,40 @@ void DecodeJob::ParseLfGlobal(BitReader& br) {
     for (int i = 0; i < 4; i++) h.global_wp.w[i] = gw.w[i];
     // ---- the inverse transforms as device ops, last transform first; `cur` follows the channel list back to the image's own channels
     std::vector<DModChannel> cur = ch;
+    auto new_op = [&]() -> DModOp& { JXLG_CHECK(ops_host.size() < 1024, "too many Modular transform steps"); ops_host.emplace_back(); memset(&ops_host.back(), 0, sizeof(DModOp)); return ops_host.back(); };
     for (size_t ti = gheader.transforms.size(); ti-- > 0;) {
-      const Transform& t = gheader.transforms[ti]; JXLG_CHECK(h.num_ops < 4, "too many Modular transforms"); DModOp& op = h.ops[h.num_ops++]; memset(&op, 0, sizeof(op));
+      const Transform& t = gheader.transforms[ti];
       if (t.id == 0) {
         JXLG_CHECK(t.begin_c + 3 <= cur.size(), "RCT channel range"); const DModChannel& a = cur[t.begin_c];
         for (int k = 1; k < 3; k++) JXLG_CHECK(cur[t.begin_c + k].w == a.w && cur[t.begin_c + k].h == a.h, "RCT channel sizes");
-        op.kind = 0; op.rct_type = t.rct_type; op.w = a.w; op.h = a.h; for (int k = 0; k < 3; k++) op.p[k] = cur[t.begin_c + k].plane_off;
-      } else {
+        DModOp& op = new_op(); op.kind = 0; op.rct_type = t.rct_type; op.w = a.w; op.h = a.h; for (int k = 0; k < 3; k++) op.p[k] = cur[t.begin_c + k].plane_off;
+      } else if (t.id == 1) {
         JXLG_CHECK(t.begin_c + 1 < cur.size(), "palette channel range"); const DModChannel pal = cur[0], idx = cur[t.begin_c + 1];
         JXLG_CHECK(pal.h == t.num_c && pal.w == t.nb_colors + t.nb_deltas, "palette geometry"); JXLG_CHECK(t.nb_deltas == 0 || t.predictor != 6, "delta palettes with the weighted predictor are not supported");
-        op.kind = 1; op.num_c = t.num_c; op.pal_w = pal.w; op.nb_deltas = t.nb_deltas; op.predictor = t.predictor; op.w = idx.w; op.h = idx.h; op.p[0] = idx.plane_off; op.p[1] = pal.plane_off;
+        DModOp& op = new_op(); op.kind = 1; op.num_c = t.num_c; op.pal_w = pal.w; op.nb_deltas = t.nb_deltas; op.predictor = t.predictor; op.w = idx.w; op.h = idx.h; op.p[0] = idx.plane_off; op.p[1] = pal.plane_off;
         cur.erase(cur.begin()); std::vector<DModChannel> outs;
         for (uint32_t k = 0; k < t.num_c; k++) { DModChannel o = idx; o.plane_off = off; off += uint64_t(idx.w) * idx.h; op.out[k] = o.plane_off; outs.push_back(o); }
         cur.erase(cur.begin() + t.begin_c); cur.insert(cur.begin() + t.begin_c, outs.begin(), outs.end());
+      } else {
+        for (size_t si = t.squeezes.size(); si-- > 0;) {   // steps in reverse; each channel's (average, residual) pair interleaves into a new plane
+          const SqueezeParams& sq = t.squeezes[si]; const uint32_t end_c = sq.begin_c + sq.num_c - 1;
+          JXLG_CHECK(cur.size() >= sq.num_c && size_t(end_c) < cur.size(), "squeeze channel range"); const size_t offset = sq.in_place ? size_t(end_c) + 1 : cur.size() - sq.num_c; JXLG_CHECK(offset + sq.num_c <= cur.size() && offset > end_c, "squeeze channel range");
+          for (uint32_t c = sq.begin_c; c <= end_c; c++) {
+            const DModChannel avg = cur[c], res = cur[offset + (c - sq.begin_c)]; DModChannel o = avg;
+            if (sq.horizontal) { JXLG_CHECK(res.h == avg.h && (res.w == avg.w || res.w + 1 == avg.w) && avg.hshift > 0, "squeeze geometry"); o.w = avg.w + res.w; o.hshift = avg.hshift - 1; }
+            else { JXLG_CHECK(res.w == avg.w && (res.h == avg.h || res.h + 1 == avg.h) && avg.vshift > 0, "squeeze geometry"); o.h = avg.h + res.h; o.vshift = avg.vshift - 1; }
+            o.plane_off = off; off += uint64_t(o.w) * o.h;
+            DModOp& op = new_op(); op.kind = 2; op.rct_type = sq.horizontal ? 1 : 0; op.w = avg.w; op.h = avg.h; op.num_c = res.w; op.pal_w = res.h; op.p[0] = avg.plane_off; op.p[1] = res.plane_off; op.out[0] = o.plane_off;
+            cur[c] = o;
+          }
+          cur.erase(cur.begin() + offset, cur.begin() + offset + sq.num_c);
+        }
       }
     }
     JXLG_CHECK(cur.size() == num_image_channels, "Modular transforms do not restore the channel list");
     for (size_t i = 0; i < cur.size(); i++) h.out_ch[i] = cur[i];
+    h.num_ops = uint32_t(ops_host.size());
+    if (ops_host.size() <= 4) { for (size_t i = 0; i < ops_host.size(); i++) h.ops[i] = ops_host[i]; } else h.ops_off = blob.Add(ops_host.data(), ops_host.size() * sizeof(DModOp));
   }
   mod_total_ints = off;
 }
@@ -434,7 +473,7 @@ void DecodeJob::Setup(const DecodeRequest& req) {
     JXLG_CHECK(info.format != 2, "multi-frame CMYK images are not supported");
     o.sample_type = 3; o.orientation = 1; o.premultiplied = 0; o.bgra = 0; bgra = false; device_output = true; o.out_w = fh.xsize; o.out_h = fh.ysize;
   }
-  for (size_t i = 0; i < m.ec.size(); i++) JXLG_CHECK(m.ec[i].dim_shift < 3, "extra channels with dim_shift >= 3 (Modular LF-group data) are not supported by the GPU decoder yet");
+  if (fh.encoding == 0) for (size_t i = 0; i < m.ec.size(); i++) JXLG_CHECK(m.ec[i].dim_shift < 3, "extra channels with dim_shift >= 3 (Modular LF-group data inside VarDCT frames) are not supported by the GPU decoder yet");
 }
 
 void DecodeJob::UploadFrame() { if (!h_misc.p) h_misc.Alloc(2 * sizeof(DFrame) + 64, true); DFrame* slot = h_misc.as<DFrame>() + (frame_uploads++ & 1); *slot = h; CUDA_OK(cudaMemcpyAsync(d_frame.p, slot, sizeof(DFrame), cudaMemcpyHostToDevice, stream)); }
@@ -536,6 +575,7 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
   if (timed) cudaEventRecord(ev[0], stream);
   // global Modular stream
   if (global_has_data) { LaunchModularGlobal(d, h, after_lfglobal, uint32_t(global_decoded), stream); CountLaunch(); }
+  if (!vardct && !single && mod_has_lf_level) LaunchModLfGroups(h, stream);
   else if (single) { uint64_t* slot = reinterpret_cast<uint64_t*>(h_misc.as<uint8_t>() + 2 * sizeof(DFrame)); slot[0] = after_lfglobal; CUDA_OK(cudaMemcpyAsync(h.end_bitpos, slot, 8, cudaMemcpyHostToDevice, stream)); }
   if (vardct) { if (defer_entropy && !single) lf_pending = true; else { LaunchLfGroups(d, h, stream); CountLaunch(); } }
   else if (single) { /* Modular frame, single section: LF group and HfGlobal parts are empty; groups continue where the global stream ended */ CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, h.end_bitpos, 8, cudaMemcpyDeviceToDevice, stream)); }
@@ -578,7 +618,7 @@ void DecodeJob::RunRender() {
   if (vardct && !(dbg_skip & 1)) LaunchReconstruct(d, h, stream);
   if (timed) cudaEventRecord(ev[3], stream);
   bool fused = false;
-  if (h.num_ops) LaunchInverseRct(d, h, stream);
+  if (h.num_ops) LaunchInverseRct(d, h, ops_host.data(), stream);
   if (dbg_skip & 2) fused = true; else
   if (vardct && !unfused) fused = LaunchFusedRender(d, h, stream);   // gaborish + EPF + colour + pack in one kernel
   if (vardct && !fused) LaunchFilters(d, h, stream);

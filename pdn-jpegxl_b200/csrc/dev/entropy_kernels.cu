@@ -239,24 +239,25 @@ __global__ void k_lf_smooth(const DFrame* fp) {
 // Decodes the group-local Modular channels (extra channels of VarDCT frames, everything of Modular frames). Warp-collective: lane 0 owns the
 // bit stream and parses; channels that qualify run through the speculative loop with every lane (DecodeRowsLeanSpec), the others on lane 0.
 // `prep` / `flag` are this warp's shared-memory words, `T` its room for the transposed alias table (spec_bytes bytes, may be 0).
+// A section covers the square (x0, y0, dim) of the frame and holds the channels whose shift min(hshift, vshift) lies in [min_shift, max_shift]:
+// pass groups take the bracket of their pass (0..2 for a single pass), LF groups everything from 3 up (channels squeezed or subsampled 8x or more).
 template <bool kNarrow>
-__device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, int pass, int lane, LeanSpecPrep& prep, volatile uint32_t* flag, uint2* T, uint32_t spec_bytes) {
-  const int gd = int(f.group_dim), gx = g % int(f.xgroups), gy = g / int(f.xgroups), x0 = gx * gd, y0 = gy * gd;
-  // the channels of this group and pass (every lane derives the same list from the frame descriptor)
+__device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, int x0, int y0, int gd, int min_shift, int max_shift, int sid, const DLocalTree* lt, int32_t* wp, int lane,
+                                      LeanSpecPrep& prep, volatile uint32_t* flag, uint2* T, uint32_t spec_bytes) {
   auto region = [&](uint32_t c, int& rx0, int& ry0, int& rw, int& rh) -> bool {
-    const DModChannel& ch = f.mod_ch[c]; const int shift = int(min(ch.hshift, ch.vshift)); if (shift > f.pass_max_shift[pass] || shift < f.pass_min_shift[pass]) return false;
+    const DModChannel& ch = ModCh(f, c); const int shift = int(min(ch.hshift, ch.vshift)); if (shift > max_shift || shift < min_shift) return false;
     rx0 = x0 >> ch.hshift; ry0 = y0 >> ch.vshift; if (rx0 >= int(ch.w) || ry0 >= int(ch.h)) return false;
     rw = min(gd >> ch.hshift, int(ch.w) - rx0); rh = min(gd >> ch.vshift, int(ch.h) - ry0); return rw > 0 && rh > 0;
   };
   // the section's channel list: rectangles of the frame's channels (every lane derives the same list from the frame descriptor)
   struct Loc { int32_t* p; int stride, w, h, hs, vs; };
-  static const int kMaxLoc = 12; Loc loc[kMaxLoc]; int nloc = 0; uint32_t dm = 0;
-  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels && nloc < 8; c++) {
+  static const int kMaxLoc = 44; Loc loc[kMaxLoc]; int nloc = 0; uint32_t dm = 0;   // a squeezed image has a few dozen residual channels per section
+  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels && nloc < kMaxLoc - 4; c++) {
     int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
-    const DModChannel& ch = f.mod_ch[c]; loc[nloc++] = Loc{f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, int(ch.w), rw, rh, int(ch.hshift), int(ch.vshift)}; dm = max(dm, uint32_t(rw));
+    const DModChannel& ch = ModCh(f, c); loc[nloc++] = Loc{f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, int(ch.w), rw, rh, int(ch.hshift), int(ch.vshift)}; dm = max(dm, uint32_t(rw));
   }
   if (nloc == 0) return;
-  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, f.encoding == 1 && pass == 0 ? LocalTreeOf(f, uint32_t(g)) : nullptr, true); *flag = ok ? 1u : 0u; }
+  if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, lt, true); *flag = ok ? 1u : 0u; }
   __syncwarp();
   if (!*flag) return;
   // the transforms of this section's own header, for every lane (lane 0 parsed them)
@@ -277,8 +278,6 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   }
   if (bad) { if (lane == 0) md.rd.err = kErrGroupTransform; return; }
   if (lane == 0) { md.rd.Init(md.cv); md.dist_mult = dm; }
-  const int sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g;
-  int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth);
   for (int k = 0; k < nloc; k++) {
     const Loc& L = loc[k];
     if (lane == 0) { if (k == 0) md.ResetChannels(); md.NoteChannel(L.p, size_t(L.stride), L.w, L.h, L.hs, L.vs); prep.ok = 0; if (!(kNarrow && md.PrepareLeanSpec(k, sid, prep, spec_bytes))) md.DecodeChannel<kNarrow>(k, sid, L.p, size_t(L.stride), L.w, L.h, wp); }
@@ -435,9 +434,35 @@ __global__ void __launch_bounds__(32 * kModGroupsPerCta) k_mod_group(const __gri
   uint64_t start = single ? f.end_bitpos[2] : sec[sidx], end = single ? sec[nsec] : sec[nsec + sidx];
   if (f.encoding == 0) start = f.ac_endpos[size_t(pass) * f.num_groups + g];
   md.rd.br.Init(f.comp, start); if (f.lz_window) md.rd.win = f.lz_window + size_t(g) * kLzWindow;
-  md.rd.err = 0; DecodeModularGroupDev<kNarrow>(md, f, g, pass, lane, sh_prep[warp], &sh_flag[warp], T, spec_bytes);
+  md.rd.err = 0;
+  { const int gd = int(f.group_dim), sid = 1 + 3 * int(f.num_lf_groups) + 17 + pass * int(f.num_groups) + g;
+    DecodeModularGroupDev<kNarrow>(md, f, g, (g % int(f.xgroups)) * gd, (g / int(f.xgroups)) * gd, gd, f.pass_min_shift[pass], f.pass_max_shift[pass], sid,
+                                   f.encoding == 1 && pass == 0 ? LocalTreeOf(f, uint32_t(g)) : nullptr, f.wp_scratch + (size_t(f.num_lf_groups) + g) * WPScratchInts(kMaxWpWidth), lane, sh_prep[warp], &sh_flag[warp], T, spec_bytes); }
   if (lane != 0) return;
   uint32_t err = md.rd.err; uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
+  SetError(f.err, err);
+}
+
+// Modular frames: the LF-group sections hold the channels of shift >= 3 (squeezed / subsampled 8x or more), one 8x8-group square per section.
+template <bool kNarrow>
+__global__ void __launch_bounds__(32 * kModGroupsPerCta) k_mod_lf_group(const __grid_constant__ DFrame f) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31; const int g = blockIdx.x * kModGroupsPerCta + warp; const bool active = g < int(f.num_lf_groups);
+  __shared__ ChanLut sh_lut[kModGroupsPerCta]; __shared__ LeanSpecPrep sh_prep[kModGroupsPerCta]; __shared__ uint32_t sh_flag[kModGroupsPerCta]; extern __shared__ __align__(16) uint8_t dsm[];
+  ModDecoder md; BindModDecoder(md, f, &sh_lut[warp]); uint32_t used = 0;
+  StageModDecoder(md, f, dsm, f.lf_smem, used, tid, 32 * kModGroupsPerCta);
+  __syncthreads();
+  if (!active) return;
+  const uint32_t spec_off = (used + 15u) & ~15u, spec_all = f.lf_smem > spec_off ? f.lf_smem - spec_off : 0u, spec_bytes = (spec_all / kModGroupsPerCta) & ~15u;
+  uint2* T = reinterpret_cast<uint2*>(dsm + spec_off + size_t(warp) * spec_bytes);
+  const uint64_t* sec = SecBitPos(f); const uint32_t nsec = f.num_passes * f.num_groups + f.num_lf_groups + 2; const bool single = (f.num_groups == 1 && f.num_passes == 1);
+  if (single) return;   // a one-group frame keeps every channel in its global stream
+  const uint64_t start = sec[1 + g], end = sec[nsec + 1 + g];
+  md.rd.br.Init(f.comp, start); if (f.lz_window) md.rd.win = f.lz_window + size_t(g) * kLzWindow;
+  md.rd.err = 0; const int dim = int(f.group_dim) * 8;
+  DecodeModularGroupDev<kNarrow>(md, f, g, (g % int(f.xlfgroups)) * dim, (g / int(f.xlfgroups)) * dim, dim, 3, 1000, 1 + int(f.num_lf_groups) + g, nullptr,
+                                 f.wp_scratch + size_t(g) * WPScratchInts(kMaxWpWidth), lane, sh_prep[warp], &sh_flag[warp], T, spec_bytes);
+  if (lane != 0) return;
+  uint32_t err = md.rd.err; const uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;
   SetError(f.err, err);
 }
 
@@ -452,11 +477,11 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
   md.wp = f.global_wp;
   { const DLocalTree* lt = LocalTreeOf(f, f.num_groups); if (lt && lt->present) BindLocalTree(md, f, *lt); }   // data_bitpos == start_bitpos: the host stopped right after the code
   if (f.lz_window) md.rd.win = f.lz_window + size_t(max(f.num_lf_groups, f.num_groups)) * kLzWindow;
-  { uint32_t dm = 0; for (uint32_t c = 0; c < num_channels; c++) dm = max(dm, f.mod_ch[c].w); md.dist_mult = dm; }
+  { uint32_t dm = 0; for (uint32_t c = 0; c < num_channels; c++) dm = max(dm, ModCh(f, c).w); md.dist_mult = dm; }
   md.rd.Init(md.cv);
   int32_t* wp = f.wp_scratch + (size_t(f.num_lf_groups) + f.num_groups) * WPScratchInts(kMaxWpWidth);
   md.ResetChannels();
-  for (uint32_t c = 0; c < num_channels; c++) { const DModChannel& ch = f.mod_ch[c]; md.NoteChannel(f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), int(ch.hshift), int(ch.vshift)); md.DecodeChannel(int(c), 0, f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), wp); }
+  for (uint32_t c = 0; c < num_channels; c++) { const DModChannel& ch = ModCh(f, c); md.NoteChannel(f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), int(ch.hshift), int(ch.vshift)); md.DecodeChannel(int(c), 0, f.mod_planes + ch.plane_off, ch.w, int(ch.w), int(ch.h), wp); }
   if (!md.rd.FinalOk(md.cv)) md.rd.err = md.rd.err ? md.rd.err : kErrAnsFinal;
   f.end_bitpos[0] = md.rd.br.BitPos();
   SetError(f.err, md.rd.err);
@@ -464,7 +489,8 @@ __global__ void k_modular_global(const __grid_constant__ DFrame f, uint64_t star
 
 static void EnsureSmemAttr() { static bool done[64] = {false}; int dev = 0; cudaGetDevice(&dev); if (done[dev & 63]) return; done[dev & 63] = true;   // function attributes are per device
   cudaFuncSetAttribute(k_lf_group_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_lf_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
+  cudaFuncSetAttribute(k_lf_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_lf_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_ac_vardct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_modular_global, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(k_mod_lf_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cudaFuncSetAttribute(k_mod_lf_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); }
 void LaunchLfGroups(const DFrame* d, const DFrame& h, cudaStream_t st) { EnsureSmemAttr(); if (!h.num_lf_groups) return; const bool narrow = LfNarrow(h);
   if (narrow) k_lf_group<true><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); else k_lf_group<false><<<h.num_lf_groups + h.lf_cta_offset, 32, h.lf_smem, st>>>(h); }
 // Bundle launches (JxlB200DecodeBatch): the images of `set` share one stream; all must be VarDCT, multi-section, of the same kind
@@ -496,6 +522,11 @@ int LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, int lanes, cudaSt
   if (h.num_mod_channels > h.first_group_channel) { const unsigned ctas = (h.num_groups + kModGroupsPerCta - 1) / kModGroupsPerCta;
     if (!h.uses_wp && !h.mod_wide) k_mod_group<true><<<ctas, 32 * kModGroupsPerCta, h.lf_smem, st>>>(h, pass); else k_mod_group<false><<<ctas, 32 * kModGroupsPerCta, h.lf_smem, st>>>(h, pass); n++; }
   return n;
+}
+void LaunchModLfGroups(const DFrame& h, cudaStream_t st) {
+  EnsureSmemAttr(); if (!h.num_lf_groups) return; const unsigned ctas = (h.num_lf_groups + kModGroupsPerCta - 1) / kModGroupsPerCta;
+  if (!h.uses_wp && !h.mod_wide) k_mod_lf_group<true><<<ctas, 32 * kModGroupsPerCta, h.lf_smem, st>>>(h); else k_mod_lf_group<false><<<ctas, 32 * kModGroupsPerCta, h.lf_smem, st>>>(h);
+  CountLaunch();
 }
 void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st) { EnsureSmemAttr(); k_modular_global<<<1, 32, h.lf_smem, st>>>(h, start_bitpos, num_channels); }
 

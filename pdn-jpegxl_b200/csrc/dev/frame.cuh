@@ -33,6 +33,8 @@ struct DModChannel { uint32_t w, h, hshift, vshift; uint64_t plane_off; };   // 
 // A Modular sub-bitstream that brings its own MA tree and entropy code (use_global_tree = 0): parsed on the host, tables in the blob. One entry per
 // group section of a Modular frame (index g) plus one for the global stream (index num_groups); data_bitpos: where the channel data starts.
 struct DLocalTree { uint32_t present, tree_off, tree_size, uses_wp; uint64_t data_bitpos; DCode code; };
+// kind 2 Squeeze (one channel of one squeeze step): average plane p[0] (w x h) and residual plane p[1] (rw x rh) interleave into the new plane out[0]
+// ((w + rw) x h when rct_type != 0 = horizontal, w x (h + rh) otherwise); num_c / pal_w carry rw / rh.
 struct DModOp { uint32_t kind, rct_type, num_c, pal_w, nb_deltas, predictor, w, h; uint64_t p[3]; uint64_t out[4]; };
 
 // Per-device constant tables (built once): scaled DCT cosines c[k*N+i] = ck*cos((2i+1)k*pi/2N) for N = 1..256 and
@@ -54,6 +56,7 @@ struct DFrame {
   uint32_t sec_off;          // uint64 sec_bitpos[nsec] then uint64 sec_bitend[nsec], byte offset into blob
   uint32_t num_mod_channels, first_group_channel; DModChannel mod_ch[8];   // the channels as CODED (after the file's forward transforms): what the entropy kernels fill
   DModChannel out_ch[8];   // the image's own channels (colour, then extra channels) after the inverse transforms: what the output kernels read
+  uint32_t mod_ch_off, ops_off;   // more than 8 coded channels / more than 4 ops (squeeze): the tables live in the blob at these offsets (0: the arrays here)
   uint32_t mod_bitdepth, mod_wide; uint32_t num_ops, local_off /* DLocalTree[num_groups + 1] in the blob, 0: every stream uses the global tree */; DModOp ops[4]; DWPHeader global_wp;   // weighted-predictor parameters of the global stream's header
   DLoopFilter lpf; DColor color; DOutput out;
   // device buffers
@@ -81,6 +84,8 @@ __device__ __forceinline__ uint32_t NibbleAt(uint64_t lo, uint64_t hi, int s) { 
 __device__ __forceinline__ uint32_t CoveredXLog2Dev(int s) { return NibbleAt(0x212010210000ull, 0x54543432300ull, s); }
 __device__ __forceinline__ uint32_t CoveredYLog2Dev(int s) { return NibbleAt(0x120201210000ull, 0x45534423300ull, s); }
 __device__ __forceinline__ uint32_t StrategyOrderDev(int s) { return NibbleAt(0x1111665544321110ull, 0xccbaa988711ull, s); }
+__device__ __forceinline__ const DModChannel& ModCh(const DFrame& f, uint32_t c) { return f.mod_ch_off ? reinterpret_cast<const DModChannel*>(f.blob + f.mod_ch_off)[c] : f.mod_ch[c]; }
+__device__ __forceinline__ const DModOp& ModOp(const DFrame& f, uint32_t i) { return f.ops_off ? reinterpret_cast<const DModOp*>(f.blob + f.ops_off)[i] : f.ops[i]; }
 __device__ __forceinline__ bool GroupInBand(const DFrame& f, int g) { if (!f.band_on) return true; const uint32_t gy = uint32_t(g) / f.xgroups; return gy >= f.comp_g0 && gy < f.comp_g1; }
 __device__ __forceinline__ const uint64_t* SecBitPos(const DFrame& f) { return reinterpret_cast<const uint64_t*>(f.blob + f.sec_off); }
 #endif

@@ -11,11 +11,12 @@ bool LfNarrow(const DFrame& h);
 void LaunchLfGroupsMulti(const DFrameSet& set, bool narrow, cudaStream_t st);
 void LaunchAcGroupsMulti(const DFrameSet& set, int lanes, cudaStream_t st);
 int LaunchAcGroups(const DFrame* d, const DFrame& h, int pass, int lanes, cudaStream_t st);
+void LaunchModLfGroups(const DFrame& h, cudaStream_t st);   // Modular frames: channels of shift >= 3 in the LF-group sections
 void LaunchModularGlobal(const DFrame* d, const DFrame& h, uint64_t start_bitpos, uint32_t num_channels, cudaStream_t st);
 void LaunchReconstruct(const DFrame* d, const DFrame& h, cudaStream_t st);       // dequant + CfL + LLF + inverse transforms
 void LaunchFilters(const DFrame* d, const DFrame& h, cudaStream_t st);           // gaborish + EPF (result in h.xyb)
 bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st);       // gaborish + EPF + colour fused (returns false when not applicable)
-void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st);
+void LaunchInverseRct(const DFrame* d, const DFrame& h, const DModOp* ops, cudaStream_t st);   // ops: host copy of the op table (h.ops or the blob table)
 void LaunchOutput(const DFrame* d, const DFrame& h, cudaStream_t st);            // colour transform + sample conversion + interleave (+BGRA)
 void LaunchSplitLayers(const void* src, void* color, uint8_t* alpha, size_t npix, int format, int sample_type, bool has_alpha, cudaStream_t st);   // I/DecoderLayerData.cs repack
 // layers of a multi-frame still (dev/composite_kernels.cu): float canvas [H][W][C], frame [fh][fw][C]

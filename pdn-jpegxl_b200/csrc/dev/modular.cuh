@@ -103,12 +103,13 @@ struct ModDecoder {
   // kind 0 RCT: a = rct_type. kind 1 Palette (no delta entries): a = num_c, b = number of colours.
   static const int kMaxGroupTransforms = 4; uint32_t gt_n = 0, gt_kind[kMaxGroupTransforms], gt_begin[kMaxGroupTransforms], gt_a[kMaxGroupTransforms], gt_b[kMaxGroupTransforms];
   static const int kMaxRefs = 4; const int32_t* ref_p[kMaxRefs]; size_t ref_stride[kMaxRefs]; int ref_n = 0;
-  struct Seen { const int32_t* p; size_t stride; int w, h, hs, vs; }; Seen seen[8]; int num_seen = 0;
+  struct Seen { const int32_t* p; size_t stride; int w, h, hs, vs; }; static const int kMaxSeen = 16; Seen seen[kMaxSeen]; int num_seen = 0;   // the most recent channels (a squeezed image has dozens)
   __device__ void ResetChannels() { num_seen = 0; ref_n = 0; }
   // call before decoding a channel: selects its reference channels among those noted so far, then notes the channel itself
   __device__ void NoteChannel(const int32_t* p, size_t stride, int w, int h, int hs, int vs) {
     ref_n = 0; for (int j = num_seen - 1; j >= 0 && ref_n < kMaxRefs; j--) if (seen[j].w == w && seen[j].h == h && seen[j].hs == hs && seen[j].vs == vs) { ref_p[ref_n] = seen[j].p; ref_stride[ref_n] = seen[j].stride; ref_n++; }
-    if (num_seen < 8) { seen[num_seen].p = p; seen[num_seen].stride = stride; seen[num_seen].w = w; seen[num_seen].h = h; seen[num_seen].hs = hs; seen[num_seen].vs = vs; num_seen++; }
+    if (num_seen == kMaxSeen) { for (int j = 1; j < kMaxSeen; j++) seen[j - 1] = seen[j]; num_seen--; }
+    if (num_seen < kMaxSeen) { seen[num_seen].p = p; seen[num_seen].stride = stride; seen[num_seen].w = w; seen[num_seen].h = h; seen[num_seen].hs = hs; seen[num_seen].vs = vs; num_seen++; }
   }
   __device__ __forceinline__ int32_t RefProp(int p, int x, int y) const {
     const int k = (p - 16) >> 2, which = (p - 16) & 3; if (k >= ref_n) return 0;   // fewer matching channels than the tree asks for: the property reads 0

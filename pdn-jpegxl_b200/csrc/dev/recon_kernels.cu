@@ -413,7 +413,7 @@ __global__ void k_epf(const DFrame* fp, const float* __restrict__ src, float* __
 
 // ------------------------------------------------------------------ inverse RCT on the global Modular image
 __global__ void k_inverse_rct(const DFrame* fp, uint32_t op_index) {
-  const DFrame& f = *fp; const DModOp& op = f.ops[op_index]; const uint32_t type = op.rct_type; const size_t n = size_t(op.w) * op.h; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
+  const DFrame& f = *fp; const DModOp& op = ModOp(f, op_index); const uint32_t type = op.rct_type; const size_t n = size_t(op.w) * op.h; size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
   int32_t* p0 = f.mod_planes + op.p[0]; int32_t* p1 = f.mod_planes + op.p[1]; int32_t* p2 = f.mod_planes + op.p[2];
   uint32_t perm = type / 7, k = type % 7; int32_t A = p0[i], B = p1[i], C = p2[i], o[3];
   if (k == 6) { int32_t t = A - (C >> 1); int32_t G = C + t; int32_t Bl = t - (B >> 1); int32_t R = Bl + B; o[0] = R; o[1] = G; o[2] = Bl; }
@@ -430,14 +430,14 @@ __device__ __forceinline__ int32_t PaletteValue(const int32_t* pal_row, int inde
 }
 // Pure gather: one thread per sample and output channel (blockIdx.y). Used when the palette has no delta entries.
 __global__ void k_inverse_palette(const DFrame* fp, uint32_t op_index) {
-  const DFrame& f = *fp; const DModOp& op = f.ops[op_index]; const size_t n = size_t(op.w) * op.h; const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
+  const DFrame& f = *fp; const DModOp& op = ModOp(f, op_index); const size_t n = size_t(op.w) * op.h; const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i >= n) return;
   const int c = blockIdx.y; const int32_t* idx = f.mod_planes + op.p[0]; const int32_t* pal = f.mod_planes + op.p[1] + size_t(c) * op.pal_w;
   f.mod_planes[op.out[c] + i] = PaletteValue(pal, idx[i], c, int(op.pal_w), int(f.mod_bitdepth), f.err);
 }
 // Palettes with delta entries (index < nb_deltas: the entry is ADDED to a prediction from the already reconstructed neighbours of the same
 // output channel): serial in raster order, one thread per output channel. A rare path (lossy-palette files); correctness only.
 __global__ void k_inverse_palette_delta(const DFrame* fp, uint32_t op_index) {
-  const DFrame& f = *fp; const DModOp& op = f.ops[op_index]; const int c = blockIdx.x; if (threadIdx.x) return;
+  const DFrame& f = *fp; const DModOp& op = ModOp(f, op_index); const int c = blockIdx.x; if (threadIdx.x) return;
   const int32_t* idx = f.mod_planes + op.p[0]; const int32_t* pal = f.mod_planes + op.p[1] + size_t(c) * op.pal_w; int32_t* out = f.mod_planes + op.out[c]; const int w = int(op.w), h = int(op.h);
   for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
     const int index = idx[size_t(y) * w + x]; int32_t v = PaletteValue(pal, index, c, int(op.pal_w), int(f.mod_bitdepth), f.err);
@@ -980,9 +980,37 @@ bool LaunchFusedRender(const DFrame* d, const DFrame& h, cudaStream_t st) {
   }
   return true;
 }
-void LaunchInverseRct(const DFrame* d, const DFrame& h, cudaStream_t st) {   // every inverse transform of the global Modular image, in execution order
+// ------------------------------------------------------------------ inverse Squeeze on the global Modular image (SURVEY.md A.7 "Squeeze")
+// avg, residual -> the two interleaved samples: diff = residual + tendency(previous output, avg, next avg); first = avg + diff / 2 (C division);
+// second = first - diff. The tendency term makes sample k depend on sample k - 1 along the squeezed direction: one thread per row (horizontal)
+// or per column (vertical, coalesced) walks that direction serially.
+__device__ __forceinline__ long long SmoothTendencyDev(long long B, long long a, long long n) {
+  long long diff = 0;
+  if (B >= a && a >= n) { diff = (4 * B - 3 * n - a + 6) / 12; if (diff - (diff & 1) > 2 * (B - a)) diff = 2 * (B - a) + 1; if (diff + (diff & 1) > 2 * (a - n)) diff = 2 * (a - n); }
+  else if (B <= a && a <= n) { diff = (4 * B - 3 * n - a - 6) / 12; if (diff + (diff & 1) < 2 * (B - a)) diff = 2 * (B - a) - 1; if (diff - (diff & 1) < 2 * (a - n)) diff = 2 * (a - n); }
+  return diff;
+}
+__global__ void k_unsqueeze(const DFrame* fp, uint32_t op_index) {
+  const DFrame& f = *fp; const DModOp& op = ModOp(f, op_index); const int aw = int(op.w), ah = int(op.h), rw = int(op.num_c), rh = int(op.pal_w);
+  const int32_t* avg = f.mod_planes + op.p[0]; const int32_t* res = f.mod_planes + op.p[1]; int32_t* out = f.mod_planes + op.out[0];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op.rct_type) {   // horizontal: out is (aw + rw) x ah, thread = row
+    if (t >= ah) return; const int ow = aw + rw; const int32_t* pa = avg + size_t(t) * aw; const int32_t* pr = res + size_t(t) * rw; int32_t* po = out + size_t(t) * ow;
+    for (int x = 0; x < rw; x++) { const long long a = pa[x], nx = x + 1 < aw ? pa[x + 1] : a, left = x ? po[2 * x - 1] : a; const long long diff = pr[x] + SmoothTendencyDev(left, a, nx); const long long A = a + diff / 2; po[2 * x] = int32_t(A); po[2 * x + 1] = int32_t(A - diff); }
+    if (ow & 1) po[ow - 1] = pa[aw - 1];
+  } else {             // vertical: out is aw x (ah + rh), thread = column
+    if (t >= aw) return; const int oh = ah + rh;
+    for (int y = 0; y < rh; y++) { const long long a = avg[size_t(y) * aw + t], nx = y + 1 < ah ? avg[size_t(y + 1) * aw + t] : a, top = y ? out[size_t(2 * y - 1) * aw + t] : a;
+      const long long diff = res[size_t(y) * aw + t] + SmoothTendencyDev(top, a, nx); const long long A = a + diff / 2; out[size_t(2 * y) * aw + t] = int32_t(A); out[size_t(2 * y + 1) * aw + t] = int32_t(A - diff); }
+    if (oh & 1) out[size_t(oh - 1) * aw + t] = avg[size_t(ah - 1) * aw + t];
+  }
+}
+
+void LaunchInverseRct(const DFrame* d, const DFrame& h, const DModOp* ops, cudaStream_t st) {   // every inverse transform of the global Modular image, in execution order
   for (uint32_t i = 0; i < h.num_ops; i++) {
-    const DModOp& op = h.ops[i]; const size_t n = size_t(op.w) * op.h; if (!n) continue;
+    const DModOp& op = ops[i]; const size_t n = size_t(op.w) * op.h;
+    if (op.kind == 2) { const unsigned threads = op.rct_type ? op.h : op.w; if (!threads) continue; k_unsqueeze<<<(threads + 63) / 64, 64, 0, st>>>(d, i); CountLaunch(); continue; }
+    if (!n) continue;
     if (op.kind == 0) k_inverse_rct<<<unsigned((n + 255) / 256), 256, 0, st>>>(d, i);
     else if (op.nb_deltas == 0) k_inverse_palette<<<dim3(unsigned((n + 255) / 256), op.num_c), 256, 0, st>>>(d, i);
     else k_inverse_palette_delta<<<op.num_c, 32, 0, st>>>(d, i);

@@ -677,6 +677,14 @@ def group_header(b, transforms=(), local=None):
             b.u(2, 0)
             b.u32(begin_c, t[1])
             b.u32((("val", 6), ("bits", 2), ("bo", 4, 2), ("bo", 6, 10)), t[2])                # rct_type
+        elif t[0] == "squeeze":                                                                # ("squeeze", [(horizontal, in_place, begin_c, num_c), ...]); [] = default parameters
+            b.u(2, 2)
+            b.u32((("val", 0), ("bo", 4, 1), ("bo", 6, 9), ("bo", 8, 41)), len(t[1]))
+            for horizontal, in_place, bc, nc in t[1]:
+                b.bool(horizontal)
+                b.bool(in_place)
+                b.u32(begin_c, bc)
+                b.u32((("val", 1), ("val", 2), ("val", 3), ("bo", 4, 4)), nc)
         else:
             assert t[0] == "palette"                                                           # ("palette", begin_c, num_c, nb_colours, nb_deltas, predictor)
             b.u(2, 1)
@@ -898,6 +906,167 @@ def modular_layers(canvas_w, canvas_h, layers, bits=8, alpha_bits=8, alpha_assoc
         out += modular_frame(ch, 1, bits=bits, group_size_shift=group_size_shift, crop=(ly.get("x0", 0), ly.get("y0", 0), ww, hh), canvas=(canvas_w, canvas_h),
                              blend=ly.get("blend"), ec_blend=[ly.get("alpha_blend", ly.get("blend"))], is_last=i + 1 == len(layers), save_as_reference=ly.get("save", 0))
     return out
+
+
+# ----------------------------------------------------------------------------- Squeeze (H.6.2)
+def _cdiv(v, d):
+    """C division (truncation toward zero), as the smooth-tendency term is specified."""
+    return -((-v) // d) if v < 0 else v // d
+
+
+def smooth_tendency(B, a, n):
+    diff = 0
+    if B >= a >= n:
+        diff = _cdiv(4 * B - 3 * n - a + 6, 12)
+        if diff - (diff & 1) > 2 * (B - a):
+            diff = 2 * (B - a) + 1
+        if diff + (diff & 1) > 2 * (a - n):
+            diff = 2 * (a - n)
+    elif B <= a <= n:
+        diff = _cdiv(4 * B - 3 * n - a - 6, 12)
+        if diff + (diff & 1) < 2 * (B - a):
+            diff = 2 * (B - a) - 1
+        if diff - (diff & 1) < 2 * (a - n):
+            diff = 2 * (a - n)
+    return diff
+
+
+def _squeeze_rows(rows):
+    """Horizontal forward squeeze of a plane given as rows: -> (average rows, residual rows)."""
+    avg_rows, res_rows = [], []
+    for row in rows:
+        w = len(row)
+        aw = (w + 1) // 2
+        avg = [(row[2 * x] + row[2 * x + 1] + (1 if row[2 * x] > row[2 * x + 1] else 0)) >> 1 if 2 * x + 1 < w else row[2 * x] for x in range(aw)]
+        res = []
+        for x in range(w - aw):
+            a = avg[x]
+            nxt = avg[x + 1] if x + 1 < aw else a
+            left = row[2 * x - 1] if x else a
+            res.append((row[2 * x] - row[2 * x + 1]) - smooth_tendency(left, a, nxt))
+        avg_rows.append(avg)
+        res_rows.append(res)
+    return avg_rows, res_rows
+
+
+def _transpose(rows):
+    return [list(col) for col in zip(*rows)] if rows and rows[0] else []
+
+
+def default_squeeze_params(chans, nb_meta):
+    """chans: list of dicts with "rows"; the default parameter list a decoder derives when the transform lists none."""
+    def dims(c):
+        return (len(c["rows"][0]) if c["rows"] else 0, len(c["rows"]))
+    nb = len(chans) - nb_meta
+    w, h = dims(chans[nb_meta])
+    out = []
+    if nb > 2 and dims(chans[nb_meta + 1]) == (w, h):
+        out += [(True, False, nb_meta + 1, 2), (False, False, nb_meta + 1, 2)]
+    if not w > h:
+        if h > 8:
+            out.append((False, True, nb_meta, nb))
+            h = (h + 1) // 2
+    while w > 8 or h > 8:
+        if w > 8:
+            out.append((True, True, nb_meta, nb))
+            w = (w + 1) // 2
+        if h > 8:
+            out.append((False, True, nb_meta, nb))
+            h = (h + 1) // 2
+    return out
+
+
+def apply_squeeze(chans, params):
+    """chans: list of dict(rows, hs, vs); applies the steps in order (the channel-list side and the samples)."""
+    chans = [dict(c) for c in chans]
+    for horizontal, in_place, bc, nc in params:
+        end = bc + nc - 1
+        offset = end + 1 if in_place else len(chans)
+        for c in range(bc, end + 1):
+            ch = chans[c]
+            if horizontal:
+                avg, res = _squeeze_rows(ch["rows"])
+                new_hs, new_vs = ch["hs"] + 1, ch["vs"]
+            else:
+                at, rt = _squeeze_rows(_transpose(ch["rows"]))
+                avg, res = _transpose(at), _transpose(rt)
+                if not res:
+                    res = []
+                new_hs, new_vs = ch["hs"], ch["vs"] + 1
+            chans[c] = dict(rows=avg, hs=new_hs, vs=new_vs)
+            chans.insert(offset + (c - bc), dict(rows=res, hs=new_hs, vs=new_vs))
+    return chans
+
+
+def modular_squeeze_image(channels, bits=8, alpha_bits=0, params=None, group_size_shift=1, tree=None, data_code=None):
+    """A lossless Modular frame whose global header lists one Squeeze transform (params = None: the default parameter list, written as an empty
+    list). The residual channels are spread over the sections as H.4 prescribes: the global stream takes the channels up to the first one larger
+    than a group, the LF-group sections those of shift >= 3, the pass-group sections the rest."""
+    h, w = len(channels[0]), len(channels[0][0])
+    ecs = [dict(type=EC_ALPHA, bits=alpha_bits)] if alpha_bits else []
+    assert len(channels) == 3 + len(ecs)
+    tree = tree or Leaf(0, 5)
+    nleaf = len([n for n in tree_nodes_bfs(tree) if isinstance(n, Leaf)])
+    code = data_code or EntropyCode([0] * nleaf, [("flat", 256)], log_alpha=8)
+    b = Bits()
+    b.u(16, 0x0AFF)
+    size_header(b, w, h)
+    image_metadata(b, bits=bits, extra_channels=ecs, xyb_encoded=False)
+    b.pad_to_byte()
+    frame_header(b, modular=True, num_extra=len(ecs), xyb_encoded=False, group_size_shift=group_size_shift)
+    gdim = 128 << group_size_shift
+    gx, gy = -(-w // gdim), -(-h // gdim)
+    lx, ly = -(-w // (gdim * 8)), -(-h // (gdim * 8))
+    ngroups, nlf = gx * gy, lx * ly
+    chans = [dict(rows=[list(r) for r in ch], hs=0, vs=0) for ch in channels]
+    used = default_squeeze_params(chans, 0) if params is None else list(params)
+    chans = apply_squeeze(chans, used)
+    dims = lambda c: (len(c["rows"][0]) if c["rows"] else 0, len(c["rows"]))
+    c0 = 0
+    while c0 < len(chans) and not (dims(chans[c0])[0] > gdim or dims(chans[c0])[1] > gdim):
+        c0 += 1
+    g = Bits()
+    g.bool(True)                                         # LfChannelDequantization.all_default
+    g.bool(True)                                         # global tree present
+    write_tree(g, tree)
+    code.write_header(g)
+    group_header(g, [("squeeze", [] if params is None else used)])
+    # (every channel of the global stream is coded, empty ones included: they keep their channel index)
+    glob = [c["rows"] for c in chans[:c0]]
+    if any(dims(c)[0] and dims(c)[1] for c in chans[:c0]):
+        code.write_stream(g, modular_items(tree, [r if r else [] for r in glob], 0))
+
+    def section(x0, y0, dim, lo, hi, stream_id):
+        sub = []
+        for c in chans[c0:]:
+            shift = min(c["hs"], c["vs"])
+            cw, chh = dims(c)
+            if shift < lo or shift > hi or not cw or not chh:
+                continue
+            rx0, ry0 = x0 >> c["hs"], y0 >> c["vs"]
+            if rx0 >= cw or ry0 >= chh:
+                continue
+            rw, rh = min(dim >> c["hs"], cw - rx0), min(dim >> c["vs"], chh - ry0)
+            if rw <= 0 or rh <= 0:
+                continue
+            sub.append([row[rx0:rx0 + rw] for row in c["rows"][ry0:ry0 + rh]])
+        s = Bits()
+        if sub:
+            group_header(s)
+            code.write_stream(s, modular_items(tree, sub, stream_id))
+        return s.bytes()
+
+    if ngroups == 1:
+        sections = [g.bytes()]
+    else:
+        sections = [g.bytes()]
+        for li in range(nlf):
+            sections.append(section((li % lx) * gdim * 8, (li // lx) * gdim * 8, gdim * 8, 3, 1000, 1 + nlf + li))
+        sections.append(b"")                              # HfGlobal: empty for Modular frames
+        for gi in range(ngroups):
+            sections.append(section((gi % gx) * gdim, (gi // gx) * gdim, gdim, 0, 2, 1 + 3 * nlf + 17 + gi))
+    toc(b, [len(sec) for sec in sections])
+    return b.bytes() + b"".join(sections)
 
 
 # ----------------------------------------------------------------------------- DC-only VarDCT frame

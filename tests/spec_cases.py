@@ -212,6 +212,19 @@ def cases():
         cols = sorted(set(tuple(int(v) for v in px) for px in sub))
         return [("palette", dict(begin=0, num_c=3, colors=cols))] if gi != 2 else []
     out.append(("rgb8_group_rgb_palettes", W.modular_image(_planes(a), group_size_shift=0, group_rct=gt_rgb), a.astype(np.uint8), dict(width=250, height=130, format="Rgb", num_channels=3)))
+    # 13f. Squeeze (H.6.2): the default parameter list (chroma first, then alternating steps down to 8 x 8) in a one-group frame (every channel in the
+    #      global stream) and in a 2 x 2-group frame (residual channels spread over global stream and pass groups); explicit steps incl. a
+    #      not-in-place one on an RGBA image; and a 1100-px-wide frame at group size 128, whose shift >= 3 channels are wider than a group and
+    #      therefore live in the LF-group sections (2 LF groups of 1024 px)
+    a = _img(40, 52, 3, seed=31)
+    out.append(("rgb8_squeeze_default_single", W.modular_squeeze_image(_planes(a)), a.astype(np.uint8), dict(width=52, height=40, format="Rgb", num_channels=3)))
+    a = _img(150, 200, 3, seed=32)
+    out.append(("rgb8_squeeze_default_groups", W.modular_squeeze_image(_planes(a), group_size_shift=0), a.astype(np.uint8), dict(width=200, height=150, format="Rgb", num_channels=3)))
+    a = _img(90, 70, 4, seed=33)
+    out.append(("rgba8_squeeze_explicit", W.modular_squeeze_image(_planes(a), alpha_bits=8, params=[(True, True, 0, 4), (False, True, 0, 4), (True, False, 1, 2)]),
+                a.astype(np.uint8), dict(width=70, height=90, format="Rgb", num_channels=4, has_transparency=True)))
+    a = _img(60, 1100, 3, seed=34)
+    out.append(("rgb8_squeeze_lf_sections", W.modular_squeeze_image(_planes(a), group_size_shift=0), a.astype(np.uint8), dict(width=1100, height=60, format="Rgb", num_channels=3)))
     # 14. Layered stills (F.2 crop + BlendingInfo, reference slots): every frame carries its crop rectangle; expected pixels from the numpy
     #     statement of the blend modes (tests/layer_util.py). (a) alpha-blend of a layer that hangs over the canvas border, (b) add, (c) three
     #     layers: the second goes to slot 2 from the empty slot 2, the last one multiplies onto slot 1
