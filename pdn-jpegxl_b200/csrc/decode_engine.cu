@@ -575,8 +575,8 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
   if (timed) cudaEventRecord(ev[0], stream);
   // global Modular stream
   if (global_has_data) { LaunchModularGlobal(d, h, after_lfglobal, uint32_t(global_decoded), stream); CountLaunch(); }
-  if (!vardct && !single && mod_has_lf_level) LaunchModLfGroups(h, stream);
   else if (single) { uint64_t* slot = reinterpret_cast<uint64_t*>(h_misc.as<uint8_t>() + 2 * sizeof(DFrame)); slot[0] = after_lfglobal; CUDA_OK(cudaMemcpyAsync(h.end_bitpos, slot, 8, cudaMemcpyHostToDevice, stream)); }
+  if (!vardct && !single && mod_has_lf_level) LaunchModLfGroups(h, stream);   // Modular frames: channels of shift >= 3 live in the LF-group sections
   if (vardct) { if (defer_entropy && !single) lf_pending = true; else { LaunchLfGroups(d, h, stream); CountLaunch(); } }
   else if (single) { /* Modular frame, single section: LF group and HfGlobal parts are empty; groups continue where the global stream ended */ CUDA_OK(cudaMemcpyAsync(h.end_bitpos + 2, h.end_bitpos, 8, cudaMemcpyDeviceToDevice, stream)); }
   if (single && vardct) {   // HfGlobal follows the LF group in the same bit stream: need its end position on the host
