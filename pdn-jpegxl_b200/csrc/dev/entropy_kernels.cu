@@ -33,8 +33,8 @@ __device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f, const DLocal
   if (!br.Read(1)) { md.wp.p1 = br.Read(5); md.wp.p2 = br.Read(5); md.wp.p3a = br.Read(5); md.wp.p3b = br.Read(5); md.wp.p3c = br.Read(5); md.wp.p3d = br.Read(5); md.wp.p3e = br.Read(5); for (int i = 0; i < 4; i++) md.wp.w[i] = br.Read(4); }
   else { md.wp.p1 = 16; md.wp.p2 = 10; md.wp.p3a = 7; md.wp.p3b = 7; md.wp.p3c = 7; md.wp.p3d = 0; md.wp.p3e = 0; md.wp.w[0] = 13; md.wp.w[1] = 12; md.wp.w[2] = 12; md.wp.w[3] = 12; }
   uint32_t nt = br.ReadU32(0, 0, 0, 1, 4, 2, 8, 18);
-  md.gt_n = 0;
-  if (nt != 0 && (!rct_allowed || nt > uint32_t(ModDecoder::kMaxGroupTransforms))) { md.rd.err = kErrGroupTransform; return false; }
+  GroupTransforms* gt = md.gt; if (gt) gt->n = 0;
+  if (nt != 0 && (!rct_allowed || !gt || nt > uint32_t(GroupTransforms::kMax))) { md.rd.err = kErrGroupTransform; return false; }
   for (uint32_t i = 0; i < nt; i++) {
     const uint32_t id = br.Read(2); if (id > 1) { md.rd.err = kErrGroupTransform; return false; }   // squeeze inside a group section
     const uint32_t begin_c = br.ReadU32(3, 0, 6, 8, 10, 72, 13, 1096); uint32_t a, b = 0;
@@ -43,7 +43,7 @@ __device__ bool ReadGroupHeaderDev(ModDecoder& md, const DFrame& f, const DLocal
       a = br.ReadU32(0, 1, 0, 3, 0, 4, 13, 1); b = br.ReadU32(8, 0, 10, 256, 12, 1280, 16, 5376); const uint32_t nb_deltas = br.ReadU32(0, 0, 8, 1, 10, 257, 16, 1281); br.Read(4);   // predictor: only used by delta entries
       if (nb_deltas != 0 || a > 4) { md.rd.err = kErrGroupTransform; return false; }
     }
-    md.gt_kind[md.gt_n] = id; md.gt_begin[md.gt_n] = begin_c; md.gt_a[md.gt_n] = a; md.gt_b[md.gt_n] = b; md.gt_n++;
+    gt->kind[gt->n] = id; gt->begin[gt->n] = begin_c; gt->a[gt->n] = a; gt->b[gt->n] = b; gt->n++;
   }
   if (!use_global) {   // the tree and the code follow in the stream: the host has parsed them (Modular frames) or the stream is not supported
     if (!lt || !lt->present) { md.rd.err = kErrLocalTree; return false; }
@@ -257,15 +257,17 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
     const DModChannel& ch = ModCh(f, c); loc[nloc++] = Loc{f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, int(ch.w), rw, rh, int(ch.hshift), int(ch.vshift)}; dm = max(dm, uint32_t(rw));
   }
   if (nloc == 0) return;
+  GroupTransforms gts; md.gt = &gts;
   if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, lt, true); *flag = ok ? 1u : 0u; }
+  md.gt = nullptr;
   __syncwarp();
   if (!*flag) return;
   // the transforms of this section's own header, for every lane (lane 0 parsed them)
-  const int gt_n = int(__shfl_sync(0xffffffffu, md.gt_n, 0)); uint32_t gt_kind[ModDecoder::kMaxGroupTransforms], gt_begin[ModDecoder::kMaxGroupTransforms], gt_a[ModDecoder::kMaxGroupTransforms], gt_b[ModDecoder::kMaxGroupTransforms];
+  const int gt_n = int(__shfl_sync(0xffffffffu, gts.n, 0)); uint32_t gt_kind[GroupTransforms::kMax], gt_begin[GroupTransforms::kMax], gt_a[GroupTransforms::kMax], gt_b[GroupTransforms::kMax];
 #pragma unroll
-  for (int i = 0; i < ModDecoder::kMaxGroupTransforms; i++) { gt_kind[i] = __shfl_sync(0xffffffffu, md.gt_kind[i], 0); gt_begin[i] = __shfl_sync(0xffffffffu, md.gt_begin[i], 0); gt_a[i] = __shfl_sync(0xffffffffu, md.gt_a[i], 0); gt_b[i] = __shfl_sync(0xffffffffu, md.gt_b[i], 0); }
+  for (int i = 0; i < GroupTransforms::kMax; i++) { gt_kind[i] = __shfl_sync(0xffffffffu, gts.kind[i], 0); gt_begin[i] = __shfl_sync(0xffffffffu, gts.begin[i], 0); gt_a[i] = __shfl_sync(0xffffffffu, gts.a[i], 0); gt_b[i] = __shfl_sync(0xffffffffu, gts.b[i], 0); }
   // ---- the channel list as coded: a palette replaces its channels by one index channel and puts the palette itself in front (meta channel)
-  Loc saved[ModDecoder::kMaxGroupTransforms][3]; int nb_meta = 0; uint32_t pal_used = 0; bool bad = false;
+  Loc saved[GroupTransforms::kMax][3]; int nb_meta = 0; uint32_t pal_used = 0; bool bad = false;
   for (int t = 0; t < gt_n && !bad; t++) {
     if (gt_kind[t] != 1) continue;
     const int b0 = int(gt_begin[t]), nc = int(gt_a[t]), ncol = int(gt_b[t]);

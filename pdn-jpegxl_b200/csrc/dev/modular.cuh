@@ -94,16 +94,17 @@ template <typename T> struct ModMath {
 // distinct clusters ("slots", at most 32: one per lane) this channel's contexts can select, and the context value -> slot map.
 struct LeanSpecPrep { BitRd br; uint32_t state, err, K, ok; uint32_t slot_info[32], slot_alias_off[32]; uint8_t slot_of[256]; };
 
+// Transforms listed in a sub-bitstream's own header (group sections): RCTs and palettes without delta entries are undone on the device (what
+// libjxl's lossless encoder picks per group). kind 0 RCT: a = rct_type. kind 1 Palette: a = num_c, b = number of colours.
+struct GroupTransforms { static const int kMax = 4; uint32_t n = 0, kind[kMax], begin[kMax], a[kMax], b[kMax]; };
+
 struct ModDecoder {
   SymReader rd; CodeView cv; const DTreeNode* tree; DWPHeader wp; bool uses_wp; bool wide; uint32_t dist_mult = 0; /* LZ77: widest channel of the sub-bitstream */ ChanLut* lut;
   // Earlier channels of the same sub-bitstream with the geometry of the channel being decoded, nearest first (MA-tree properties 16 + 4k .. 19 + 4k:
   // |v|, v, |v - g|, v - g of that channel's sample at the same position, g its clamped gradient). The caller keeps the list (NoteChannel).
-  // Transforms listed in the sub-bitstream's own header (group sections): RCTs and palettes without delta entries are undone on the device (what
-  // libjxl's lossless encoder picks per group); a header that lists anything else, or transforms where the caller cannot undo them, is refused.
-  // kind 0 RCT: a = rct_type. kind 1 Palette (no delta entries): a = num_c, b = number of colours.
-  static const int kMaxGroupTransforms = 4; uint32_t gt_n = 0, gt_kind[kMaxGroupTransforms], gt_begin[kMaxGroupTransforms], gt_a[kMaxGroupTransforms], gt_b[kMaxGroupTransforms];
+  GroupTransforms* gt = nullptr;   // where ReadGroupHeaderDev leaves the transforms of the stream's own header (null: the caller cannot undo any)
   static const int kMaxRefs = 4; const int32_t* ref_p[kMaxRefs]; size_t ref_stride[kMaxRefs]; int ref_n = 0;
-  struct Seen { const int32_t* p; size_t stride; int w, h, hs, vs; }; static const int kMaxSeen = 16; Seen seen[kMaxSeen]; int num_seen = 0;   // the most recent channels (a squeezed image has dozens)
+  struct Seen { const int32_t* p; size_t stride; int w, h, hs, vs; }; static const int kMaxSeen = 8; Seen seen[kMaxSeen]; int num_seen = 0;   // the most recent channels (a squeezed image has dozens)
   __device__ void ResetChannels() { num_seen = 0; ref_n = 0; }
   // call before decoding a channel: selects its reference channels among those noted so far, then notes the channel itself
   __device__ void NoteChannel(const int32_t* p, size_t stride, int w, int h, int hs, int vs) {
