@@ -319,11 +319,11 @@ static void RunBatchShard(const BatchArgs& a, int slot, int begin, int end, int 
       return progressed;
     };
     bool reserved = reserve_sets == 0;
-    // pacing (host outputs only): ns per image = its output bytes over the link rate (JXLB200_D2H_GBPS, default 60: a little faster than the
-    // link, the in-flight cap gives the back-pressure); JXLB200_PACE=0 switches it off
+    // pacing (host outputs only): ns per image = its output bytes over a rate somewhat above the link's (JXLB200_D2H_GBPS, default 80 against the
+    // 55.6 GB/s measured: the sweep in profiles/r02_e2e_pipeline.md; the in-flight cap gives the back-pressure); JXLB200_PACE=0 switches it off
     int64_t pace_ns = 0, launch_at = 0;
     if (a.hostOutputs && a.count >= 64) {
-      const char* off = getenv("JXLB200_PACE"); const double gbps = getenv("JXLB200_D2H_GBPS") ? atof(getenv("JXLB200_D2H_GBPS")) : 60.0;
+      const char* off = getenv("JXLB200_PACE"); const double gbps = getenv("JXLB200_D2H_GBPS") ? atof(getenv("JXLB200_D2H_GBPS")) : 80.0;
       if (!(off && *off == '0') && gbps > 0) pace_ns = int64_t(double(a.outputBytes[begin]) / gbps);
     }
     while (done < count) {
