@@ -232,3 +232,35 @@ def test_synthesised_profile_reads_back(pkg):
     v = np.arange(256) / 255.0
     bt709 = np.where(v < 0.081, v / 4.5, ((v + 0.099) / 1.099) ** (1 / 0.45))
     assert np.abs(lut - bt709[None, :]).max() < 3e-4
+
+
+def test_round2_entry_points_without_a_gpu(pkg, oracle):
+    """The entry points added in round 2 keep the boundary's rules: plain pointers, a status for every failure, a message, never a CPU
+    fallback. (On a GPU box this test only checks the host-only parts.)"""
+    import ctypes as C
+    import numpy as np
+    L = pkg._lib
+    ok, _ = pkg.cuda_available()
+    data = oracle.encode(oracle.synthetic_image(40, 30, seed=1, channels=4), lossless=1)
+    # JxlB200LoadImageLayers: null parameters first, then the device requirement
+    ei = pkg.ErrorInfo()
+    assert L.JxlB200LoadImageLayers(None, 0, None, 0, None, 0, None, C.byref(ei)) == pkg.DECODER_STATUS.index("NullParameter")
+    if not ok:
+        with pytest.raises(pkg.FormatException) as e:
+            pkg.load_image_layers(data)
+        assert e.value.status == "DecodeError" and "CUDA" in str(e.value)
+        # a band encoder session cannot be created without a device: NULL + message, no CPU path
+        with pytest.raises(pkg.FormatException) as e:
+            pkg.BandEncoder(np.zeros((16, 16, 4), np.uint8), 16, 0, 0, 0, pkg.EncoderOptions(quality=90, effort=3))
+        assert "CUDA" in str(e.value)
+    # JxlB200AssembleBands is host-only: garbage blobs and a histogram of the wrong size are refused with a message
+    opts = pkg.EncoderOptions(quality=90, effort=3)
+    with pytest.raises(pkg.FormatException) as e:
+        pkg.assemble_bands(64, 64, opts, 0, np.zeros(8, np.uint64), [b"not a section blob"])
+    assert e.value.status == "EncodeError"
+    # section sizes of a file (host-only instrumentation): LfGlobal .. groups in logical order
+    sizes, nlf, ng = pkg.section_sizes(oracle.encode(oracle.synthetic_image(300, 200, seed=2), effort=3))
+    assert (nlf, ng) == (1, 2) and len(sizes) == 2 + nlf + ng and all(v > 0 for v in sizes)
+    # the band partition of the sharded encoder: whole LF-group rows, halos of 8 rows towards every neighbour
+    assert pkg.encode_band_partition(5000, 4) == [(0, 2048), (2048, 2048), (4096, 904), (0, 0)]
+    assert pkg.band_rows_with_halo(5000, 2048, 2048) == (2040, 8, 8) and pkg.band_rows_with_halo(5000, 4096, 904) == (4088, 8, 0)
