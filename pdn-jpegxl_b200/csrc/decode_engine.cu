@@ -553,7 +553,7 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
   // ---- sub-bitstreams with their own MA tree. Group sections of Modular frames start with their Modular header, so the host can parse the tree and
   // the code that follow it (VarDCT frames keep their group-local Modular data behind the AC coefficients, where only the device knows the position).
   h.local_off = 0;
-  { std::vector<DLocalTree> lts(size_t(h.num_groups) + 1); memset(lts.data(), 0, lts.size() * sizeof(DLocalTree)); bool any = false;
+  { std::vector<DLocalTree> lts(size_t(h.num_groups) + 1 + h.num_lf_groups); memset(lts.data(), 0, lts.size() * sizeof(DLocalTree)); bool any = false;   // [group g | global | LF group g]
     if (global_local.present) { lts[h.num_groups] = global_local; lts[h.num_groups].data_bitpos = after_lfglobal; any = true; }
     if (fh.encoding == 1 && !single && h.num_passes == 1 && h.num_mod_channels > h.first_group_channel) {
       for (uint32_t g = 0; g < h.num_groups; g++) {
@@ -562,6 +562,15 @@ void DecodeJob::RunLf(const DecodeRequest& req) {
         bool only_rct = true; for (const Transform& tr : gh.transforms) only_rct = only_rct && tr.id == 0;
         if (gb.overrun || gh.use_global_tree || !only_rct) continue;   // (palette / squeeze inside a group section: the kernel reports them)
         lts[g] = ParseLocalTree(gb, size_t(h.group_dim) * h.group_dim * (h.num_mod_channels - h.first_group_channel)); lts[g].data_bitpos = base_bits + uint64_t(toc.offset[t]) * 8 + gb.pos; any = true;
+      }
+    }
+    if (fh.encoding == 1 && !single && mod_has_lf_level) {   // LF-group sections of Modular frames (channels of shift >= 3) start with their Modular header too
+      for (uint32_t g = 0; g < h.num_lf_groups; g++) {
+        const size_t t = size_t(1) + g; if (toc.size[t] == 0) continue;
+        BitReader gb(cs.data() + frame_off + toc.offset[t], toc.size[t]); const GroupHeader gh = ReadGroupHeader(gb);
+        bool only_rct = true; for (const Transform& tr : gh.transforms) only_rct = only_rct && tr.id == 0;
+        if (gb.overrun || gh.use_global_tree || !only_rct) continue;
+        const size_t dim = size_t(h.group_dim); DLocalTree& e = lts[size_t(h.num_groups) + 1 + g]; e = ParseLocalTree(gb, dim * dim * h.num_mod_channels); e.data_bitpos = base_bits + uint64_t(toc.offset[t]) * 8 + gb.pos; any = true;
       }
     }
     if (any) h.local_off = blob.Add(lts.data(), lts.size() * sizeof(DLocalTree)); }

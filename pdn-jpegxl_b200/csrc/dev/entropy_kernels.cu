@@ -252,10 +252,13 @@ __device__ void DecodeModularGroupDev(ModDecoder& md, const DFrame& f, int g, in
   // the section's channel list: rectangles of the frame's channels (every lane derives the same list from the frame descriptor)
   struct Loc { int32_t* p; int stride, w, h, hs, vs; };
   static const int kMaxLoc = 44; Loc loc[kMaxLoc]; int nloc = 0; uint32_t dm = 0;   // a squeezed image has a few dozen residual channels per section
-  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels && nloc < kMaxLoc - 4; c++) {
+  bool too_many = false;
+  for (uint32_t c = f.first_group_channel; c < f.num_mod_channels; c++) {
     int rx0, ry0, rw, rh; if (!region(c, rx0, ry0, rw, rh)) continue;
+    if (nloc >= kMaxLoc - 4) { too_many = true; break; }   // more channels in one section than the list holds: refused, never truncated
     const DModChannel& ch = ModCh(f, c); loc[nloc++] = Loc{f.mod_planes + ch.plane_off + size_t(ry0) * ch.w + rx0, int(ch.w), rw, rh, int(ch.hshift), int(ch.vshift)}; dm = max(dm, uint32_t(rw));
   }
+  if (too_many) { if (lane == 0) md.rd.err = kErrUnsupportedStream; return; }
   if (nloc == 0) return;
   GroupTransforms gts; md.gt = &gts;
   if (lane == 0) { const bool ok = ReadGroupHeaderDev(md, f, lt, true); *flag = ok ? 1u : 0u; }
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(32 * kModGroupsPerCta) k_mod_lf_group(const __
   const uint64_t start = sec[1 + g], end = sec[nsec + 1 + g];
   md.rd.br.Init(f.comp, start); if (f.lz_window) md.rd.win = f.lz_window + size_t(g) * kLzWindow;
   md.rd.err = 0; const int dim = int(f.group_dim) * 8;
-  DecodeModularGroupDev<kNarrow>(md, f, g, (g % int(f.xlfgroups)) * dim, (g / int(f.xlfgroups)) * dim, dim, 3, 1000, 1 + int(f.num_lf_groups) + g, nullptr,
+  DecodeModularGroupDev<kNarrow>(md, f, g, (g % int(f.xlfgroups)) * dim, (g / int(f.xlfgroups)) * dim, dim, 3, 1000, 1 + int(f.num_lf_groups) + g, LocalTreeOf(f, f.num_groups + 1 + uint32_t(g)),
                                  f.wp_scratch + size_t(g) * WPScratchInts(kMaxWpWidth), lane, sh_prep[warp], &sh_flag[warp], T, spec_bytes);
   if (lane != 0) return;
   uint32_t err = md.rd.err; const uint64_t pos = md.rd.br.BitPos(); if (!err && pos > end) err = kErrOverrun;

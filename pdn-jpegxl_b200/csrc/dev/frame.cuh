@@ -31,7 +31,8 @@ struct DModChannel { uint32_t w, h, hshift, vshift; uint64_t plane_off; };   // 
 // kind 0 RCT: planes p[0..2] of n samples, in place. kind 1 Palette: index plane p[0] (w x h) and palette plane p[1] (pal_w entries per row,
 // one row per output channel) expand into num_c new planes out[0..num_c) — out of place, the index plane is read by every output channel.
 // A Modular sub-bitstream that brings its own MA tree and entropy code (use_global_tree = 0): parsed on the host, tables in the blob. One entry per
-// group section of a Modular frame (index g) plus one for the global stream (index num_groups); data_bitpos: where the channel data starts.
+// group section of a Modular frame (index g), one for the global stream (index num_groups), one per LF-group section (num_groups + 1 + g);
+// data_bitpos: where the channel data starts.
 struct DLocalTree { uint32_t present, tree_off, tree_size, uses_wp; uint64_t data_bitpos; DCode code; };
 // kind 2 Squeeze (one channel of one squeeze step): average plane p[0] (w x h) and residual plane p[1] (rw x rh) interleave into the new plane out[0]
 // ((w + rw) x h when rct_type != 0 = horizontal, w x (h + rh) otherwise); num_c / pal_w carry rw / rh.

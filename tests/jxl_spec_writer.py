@@ -998,10 +998,11 @@ def apply_squeeze(chans, params):
     return chans
 
 
-def modular_squeeze_image(channels, bits=8, alpha_bits=0, params=None, group_size_shift=1, tree=None, data_code=None):
+def modular_squeeze_image(channels, bits=8, alpha_bits=0, params=None, group_size_shift=1, tree=None, data_code=None, section_local=None):
     """A lossless Modular frame whose global header lists one Squeeze transform (params = None: the default parameter list, written as an empty
     list). The residual channels are spread over the sections as H.4 prescribes: the global stream takes the channels up to the first one larger
-    than a group, the LF-group sections those of shift >= 3, the pass-group sections the rest."""
+    than a group, the LF-group sections those of shift >= 3, the pass-group sections the rest. section_local = (tree, code): every LF-group and
+    pass-group section brings this MA tree and code of its own (use_global_tree = 0)."""
     h, w = len(channels[0]), len(channels[0][0])
     ecs = [dict(type=EC_ALPHA, bits=alpha_bits)] if alpha_bits else []
     assert len(channels) == 3 + len(ecs)
@@ -1052,8 +1053,9 @@ def modular_squeeze_image(channels, bits=8, alpha_bits=0, params=None, group_siz
             sub.append([row[rx0:rx0 + rw] for row in c["rows"][ry0:ry0 + rh]])
         s = Bits()
         if sub:
-            group_header(s)
-            code.write_stream(s, modular_items(tree, sub, stream_id))
+            stree, scode = section_local if section_local else (tree, code)
+            group_header(s, local=section_local)
+            scode.write_stream(s, modular_items(stree, sub, stream_id))
         return s.bytes()
 
     if ngroups == 1:

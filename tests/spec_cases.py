@@ -225,6 +225,13 @@ def cases():
                 a.astype(np.uint8), dict(width=70, height=90, format="Rgb", num_channels=4, has_transparency=True)))
     a = _img(60, 1100, 3, seed=34)
     out.append(("rgb8_squeeze_lf_sections", W.modular_squeeze_image(_planes(a), group_size_shift=0), a.astype(np.uint8), dict(width=1100, height=60, format="Rgb", num_channels=3)))
+    a = _img(64, 80, 3, seed=35)
+    a[..., 1] = (a[..., 0] // 2 + a[..., 1] // 2) % 256                                                     # correlated channels: the reference properties carry information
+    sq_tree = W.Split(17, 0, W.Leaf(0, 5), W.Split(18, 3, W.Leaf(1, 1), W.Leaf(2, 4)))                        # previous same-size channel: value > 0 ? gradient : (|v - g| > 3 ? W : select)
+    sq_code = W.EntropyCode([0, 1, 2], [("flat", 256)] * 3, hybrids=[W.Hybrid(4, 2, 0)] * 3, log_alpha=8)
+    out.append(("rgb8_squeeze_prev_channel_tree", W.modular_squeeze_image(_planes(a), tree=sq_tree, data_code=sq_code), a.astype(np.uint8), dict(width=80, height=64, format="Rgb", num_channels=3)))
+    a = _img(60, 1100, 3, seed=36)
+    out.append(("rgb8_squeeze_lf_sections_local_trees", W.modular_squeeze_image(_planes(a), group_size_shift=0, section_local=(ltree, lcode)), a.astype(np.uint8), dict(width=1100, height=60, format="Rgb", num_channels=3)))
     # 14. Layered stills (F.2 crop + BlendingInfo, reference slots): every frame carries its crop rectangle; expected pixels from the numpy
     #     statement of the blend modes (tests/layer_util.py). (a) alpha-blend of a layer that hangs over the canvas border, (b) add, (c) three
     #     layers: the second goes to slot 2 from the empty slot 2, the last one multiplies onto slot 1
