@@ -76,6 +76,8 @@ static Pool& HostPool() { static Pool p(true); return p; }
 void TrimPools() { DevPool().Trim(); HostPool().Trim(); }
 void DumpPoolStats() { Pool& d = DevPool(); Pool& h = HostPool(); fprintf(stderr, "[jxlb200] pools: device misses %zu trims %zu cached %.1f GB; pinned misses %zu trims %zu cached %.2f GB\n", d.misses_, d.trims_, d.Cached() / 1e9, h.misses_, h.trims_, h.Cached() / 1e9); fprintf(stderr, "[jxlb200] device miss sizes:%s\n", d.MissReport().c_str()); }
 void* PinnedGet(size_t bytes) { return HostPool().Get(bytes ? bytes : 1); }
+void* DeviceGet(size_t bytes, void** pool_token) { Pool& p = DevPool(); *pool_token = &p; return p.Get(bytes ? bytes : 1); }   // the current device's pool
+void DevicePut(void* ptr, size_t bytes, void* pool_token) { if (ptr && pool_token) static_cast<Pool*>(pool_token)->Put(ptr, bytes ? bytes : 1); }
 void PinnedPut(void* p, size_t bytes) { HostPool().Put(p, bytes ? bytes : 1); }
 
 struct DevBuf { void* p = nullptr; size_t n = 0; bool host = false; Pool* pool = nullptr; void Alloc(size_t bytes, bool pinned = false) { Free(); host = pinned; n = bytes ? bytes : 1; pool = pinned ? &HostPool() : &DevPool(); p = pool->Get(n); } void Free() { if (p) pool->Put(p, n); p = nullptr; n = 0; } ~DevBuf() { Free(); } DevBuf() {} DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;

@@ -22,7 +22,10 @@ namespace jxlgpu {
 
 namespace {
 
-struct Buf { void* p = nullptr; size_t n = 0; void Alloc(size_t b) { Free(); n = b ? b : 1; if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); p = nullptr; throw std::bad_alloc(); } } void Free() { if (p) cudaFree(p); p = nullptr; } ~Buf() { Free(); } template <class T> T* as() const { return static_cast<T*>(p); } };
+// Device buffers come from the engine's caching pool (cudaMalloc / cudaFree cost more than most encoder kernels; cudaFree also synchronises).
+// A buffer goes back to the pool only after the work that uses it has been synchronised (the sessions sync their stream before they let go).
+struct Buf { void* p = nullptr; size_t n = 0; void* pool = nullptr; void Alloc(size_t b) { Free(); n = b ? b : 1; p = DeviceGet(n, &pool); } void Free() { if (p) DevicePut(p, n, pool); p = nullptr; } ~Buf() { Free(); }
+  Buf() {} Buf(const Buf&) = delete; Buf& operator=(const Buf&) = delete; template <class T> T* as() const { return static_cast<T*>(p); } };
 
 // ---- fixed MA trees (same shape the decoder kernels walk; BFS layout as DecodeTree allocates it)
 struct TreeBuilder {

@@ -72,6 +72,8 @@ void TrimPools();
 void DumpHostTrace();
 void* PinnedGet(size_t bytes);            // cached page-locked host memory (cudaHostAlloc costs far more than a decode)
 void PinnedPut(void* p, size_t bytes);
+void* DeviceGet(size_t bytes, void** pool_token);   // cached device memory of the current device (the encoder allocates ~25 buffers per call)
+void DevicePut(void* p, size_t bytes, void* pool_token);
 
 // ---- encoder
 struct EncodeRequest {
