@@ -147,7 +147,7 @@ DecoderStatus JxlB200LoadImageBgra(const uint8_t* data, size_t dataSize, uint8_t
 DecoderStatus JxlB200LoadImageLayers(const uint8_t* data, size_t dataSize, uint8_t* color, size_t colorBytes, uint8_t* transparency, size_t transparencyBytes,
                                      int32_t* info6, ErrorInfo* errorInfo) {
   if (!data || !color) return DecoderStatus_NullParameter;
-  void* d_color = nullptr; void* d_alpha = nullptr; DecoderStatus rc = DecoderStatus_Ok;
+  void* d_color = nullptr; void* d_alpha = nullptr; void* pool_c = nullptr; void* pool_a = nullptr; size_t bytes_c = 0, bytes_a = 0; DecoderStatus rc = DecoderStatus_Ok;   // cached device buffers (engine pool)
   try {
     DecodeRequest req; req.data = data; req.size = dataSize; req.device_output = true; DecodeResult res = DecodeOnGpu(req); g_last_times = res.times;
     if (res.status != Status::Ok) { SetErrorMessage(errorInfo, res.message); return DecoderStatus(res.status); }
@@ -156,15 +156,16 @@ DecoderStatus JxlB200LoadImageLayers(const uint8_t* data, size_t dataSize, uint8
     const size_t dst_ch = pi.format == 2 ? 4 : 3, need_color = npix * dst_ch * bps, need_alpha = pi.has_alpha ? npix : 0;
     if (info6) { info6[0] = int32_t(res.out_width); info6[1] = int32_t(res.out_height); info6[2] = pi.format; info6[3] = pi.sample_type; info6[4] = pi.has_alpha ? 1 : 0; info6[5] = int32_t(dst_ch); }
     if (colorBytes < need_color || (pi.has_alpha && (!transparency || transparencyBytes < need_alpha))) { SetErrorMessage(errorInfo, "layer buffers too small"); return DecoderStatus_InvalidParameter; }
-    if (cudaMalloc(&d_color, need_color ? need_color : 1) != cudaSuccess || cudaMalloc(&d_alpha, need_alpha ? need_alpha : 1) != cudaSuccess) { rc = DecoderStatus_OutOfMemory; }
-    else {
+    bytes_c = need_color ? need_color : 1; bytes_a = need_alpha ? need_alpha : 1; d_color = DeviceGet(bytes_c, &pool_c); d_alpha = DeviceGet(bytes_a, &pool_a);   // throw std::bad_alloc when the device is full
+    {
       LaunchSplitLayers(res.pixels, d_color, static_cast<uint8_t*>(d_alpha), npix, pi.format, pi.sample_type, pi.has_alpha, 0);
       cudaError_t e = cudaMemcpy(color, d_color, need_color, cudaMemcpyDeviceToHost);
       if (e == cudaSuccess && need_alpha) e = cudaMemcpy(transparency, d_alpha, need_alpha, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) { SetErrorMessage(errorInfo, std::string("CUDA: ") + cudaGetErrorString(e)); rc = DecoderStatus_DecodeError; }
     }
   } catch (const std::bad_alloc&) { rc = DecoderStatus_OutOfMemory; } catch (const std::exception& e) { SetErrorMessage(errorInfo, e.what()); rc = DecoderStatus_DecodeError; } catch (...) { rc = DecoderStatus_DecodeError; }
-  if (d_color) cudaFree(d_color); if (d_alpha) cudaFree(d_alpha);
+  if (d_color || d_alpha) cudaDeviceSynchronize();   // the split kernel ran on the default stream; the copies above were synchronous
+  DevicePut(d_color, bytes_c, pool_c); DevicePut(d_alpha, bytes_a, pool_a);
   return rc;
 }
 
