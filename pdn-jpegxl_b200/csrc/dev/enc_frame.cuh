@@ -35,6 +35,7 @@ void EncLaunchBlockParams(const DEncFrame* d, const DEncFrame& h, cudaStream_t s
 void EncLaunchModTokens(const DEncFrame* d, const DEncModStream* streams, uint32_t nstreams, uint32_t max_tokens, const int32_t* planes, uint32_t pw, uint32_t ph, uint32_t nch, const uint16_t* leaf_lut, cudaStream_t st);
 void EncLaunchAcTokens(const DEncFrame* d, const DEncFrame& h, cudaStream_t st);
 void EncLaunchHistogram(const uint2* tokens, const DEncStream* streams, uint32_t nstreams, uint32_t max_count, uint32_t* hist, cudaStream_t st);
+void EncLaunchPrefix(const DEncFrame* d, const DEncStream* streams, uint32_t nstreams, const DEncCode* code, uint32_t bits_off, cudaStream_t st);   // prefix codes: code->freq = lengths, code->start = bit-reversed code words
 void EncLaunchAns(const DEncFrame* d, const DEncStream* streams, uint32_t nstreams, const DEncCode* code, uint32_t bits_off, cudaStream_t st);   // stream si reports its bit count in stream_bits[bits_off + si]
 void EncLaunchCompact(const uint8_t* src, const DEncStream* streams, uint32_t nstreams, const uint64_t* bits, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st);
 void LaunchGaborishPlanes(const DFrame* d, const DFrame& h, const float* src, float* dst, cudaStream_t st);

@@ -87,7 +87,10 @@ void AppendBits(BitWriter& bw, const uint8_t* p, uint64_t nbits) {
 
 struct DeviceEncCode { Buf ctx_map, freq, start, rev, desc; };
 void UploadEncCode(const EncCode& c, DeviceEncCode* d, cudaStream_t st) {
-  size_t ncl = c.cfg.size(); std::vector<uint16_t> freq(ncl * kEncAlphabet, 0), start(ncl * kEncAlphabet, 0), rev(ncl * 4096, 0);
+  size_t ncl = c.cfg.size(); std::vector<uint16_t> freq(ncl * kEncAlphabet, 0), start(ncl * kEncAlphabet, 0), rev(c.use_prefix ? 8 : ncl * 4096, 0);
+  if (c.use_prefix) {   // prefix codes (efforts 1-2): `freq` carries the code lengths, `start` the bit-reversed code words (k_enc_prefix)
+    for (size_t k = 0; k < ncl; k++) { const PrefixTable& p = c.prefix[k]; JXLG_CHECK(p.len.size() <= kEncAlphabet, "encoder alphabet"); for (size_t s = 0; s < p.len.size(); s++) { freq[k * kEncAlphabet + s] = p.max_len ? p.len[s] : 0; start[k * kEncAlphabet + s] = p.max_len ? p.enc_code[s] : 0; } }
+  } else
   for (size_t k = 0; k < ncl; k++) { JXLG_CHECK((size_t(1) << c.log_alpha) <= kEncAlphabet, "encoder alphabet"); for (size_t s = 0; s < (size_t(1) << c.log_alpha); s++) { freq[k * kEncAlphabet + s] = c.ans[k].freq[s]; start[k * kEncAlphabet + s] = uint16_t(c.sym_start[k][s]); } memcpy(&rev[k * 4096], c.rev[k].data(), 4096 * 2); }
   d->ctx_map.Alloc(c.ctx_map.size()); d->freq.Alloc(freq.size() * 2); d->start.Alloc(start.size() * 2); d->rev.Alloc(rev.size() * 2); d->desc.Alloc(sizeof(DEncCode));
   CUDA_OK(cudaMemcpyAsync(d->ctx_map.p, c.ctx_map.data(), c.ctx_map.size(), cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(d->freq.p, freq.data(), freq.size() * 2, cudaMemcpyHostToDevice, st));
@@ -159,6 +162,7 @@ EncPlan MakePlan(uint32_t xs, uint32_t ys, uint32_t flags, const EncodeRequest& 
   { const char* v = getenv("JXLB200_ENC_AQ"); if (v && *v == '0') p.aq = false; v = getenv("JXLB200_ENC_CFL"); if (v && *v == '0') p.cfl = false; }   // measurement switches (scripts/compare_efforts.py)
   p.tree = p.lossless ? MakeLosslessTree(p.ncolor + p.num_ec) : MakeVarDctTree(nlf, p.num_ec, p.aq, p.cfl); TokenizeTree(p.tree, &p.tree_tokens);
   EncOptions topt; topt.cfg = HybridCfg{4, 1, 0}; p.mopt.cfg = HybridCfg{4, 1, 0}; p.mopt.max_clusters = 48; p.aopt.cfg = HybridCfg{4, 2, 0}; p.aopt.max_clusters = 64;
+  if (req.effort <= 2) { p.mopt.use_prefix = true; p.aopt.use_prefix = true; }   // the fastest efforts write prefix codes: no serial state chain in the stream writer
   p.tree_code = BuildCode({&p.tree_tokens}, 6, topt); p.nleaves = NumLeaves(p.tree);
   // leaf LUT for the device tokeniser: kind 0 = LF coefficient streams, 1 = pass-group streams, 2 = global stream
   p.leaf_lut.assign(3 * 8 * 11, 0);
@@ -376,8 +380,8 @@ std::vector<BandSection> BandEncoder::Finish(const std::vector<uint64_t>& frame_
     cudaStream_t st2 = nullptr; cudaEvent_t ready = nullptr, done2 = nullptr; CUDA_OK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking)); cudaEventCreateWithFlags(&ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&done2, cudaEventDisableTiming);
     cudaEventRecord(ready, st); cudaStreamWaitEvent(st2, ready, 0);
     const uint32_t nm = uint32_t(m_streams.size());
-    EncLaunchAns(de, d_m, nm, dm.desc.as<DEncCode>(), 0, st);
-    if (!lossless) EncLaunchAns(de, d_a, ng, da.desc.as<DEncCode>(), nm, st2);
+    if (codes.mcode.use_prefix) EncLaunchPrefix(de, d_m, nm, dm.desc.as<DEncCode>(), 0, st); else EncLaunchAns(de, d_m, nm, dm.desc.as<DEncCode>(), 0, st);
+    if (!lossless) { if (codes.acode.use_prefix) EncLaunchPrefix(de, d_a, ng, da.desc.as<DEncCode>(), nm, st2); else EncLaunchAns(de, d_a, ng, da.desc.as<DEncCode>(), nm, st2); }
     cudaEventRecord(done2, st2); cudaStreamWaitEvent(st, done2, 0);
     if (nm) CUDA_OK(cudaMemcpyAsync(bits_m.data(), e.stream_bits, size_t(nm) * 8, cudaMemcpyDeviceToHost, st));
     if (!lossless) CUDA_OK(cudaMemcpyAsync(bits_a.data(), e.stream_bits + nm, size_t(ng) * 8, cudaMemcpyDeviceToHost, st));

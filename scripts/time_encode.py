@@ -14,12 +14,12 @@ img = synthetic_image(args.w, args.h, seed=1, channels=4)
 bgra = np.ascontiguousarray(np.concatenate([img[..., 2::-1], img[..., 3:]], axis=2))
 opaque = bgra.copy(); opaque[..., 3] = 255
 mp = args.w * args.h / 1e6
-for name, surf, opts in (("lossy d=1.0 e=3 RGB", opaque, P.EncoderOptions(quality=90, effort=3)), ("lossy d=1.0 e=7 RGB (gaborish)", opaque, P.EncoderOptions(quality=90, effort=7)),
-                         ("lossy d=1.0 e=3 RGBA", bgra, P.EncoderOptions(quality=90, effort=3)), ("lossless RGBA", bgra, P.EncoderOptions(lossless=True))):
+for name, surf, opts in (("lossy d=1.0 e=1 RGB (prefix codes)", opaque, P.EncoderOptions(quality=90, effort=1)), ("lossy d=1.0 e=3 RGB", opaque, P.EncoderOptions(quality=90, effort=3)), ("lossy d=1.0 e=7 RGB (gaborish)", opaque, P.EncoderOptions(quality=90, effort=7)),
+                         ("lossy d=1.0 e=3 RGBA", bgra, P.EncoderOptions(quality=90, effort=3)), ("lossless RGBA", bgra, P.EncoderOptions(lossless=True)), ("lossless RGBA e=1 (prefix codes)", bgra, P.EncoderOptions(lossless=True, effort=1))):
     P.encode_to_memory(surf, opts)                         # warm-up: tables, first-use allocations
     best, dev, size = 1e9, 0.0, 0
     for _ in range(args.reps):
         t = time.time(); data = P.encode_to_memory(surf, opts); dt = (time.time() - t) * 1e3
         if dt < best:
             best, dev, size = dt, P.last_stage_times()["total"], len(data)
-    print("%-32s wall %7.1f ms = %6.0f MP/s   device sections %7.1f ms   %.3f bpp" % (name, best, mp / best * 1e3, dev, size * 8 / (args.w * args.h)), flush=True)
+    print("%-34s wall %7.1f ms = %6.0f MP/s   device sections %7.1f ms   %.3f bpp" % (name, best, mp / best * 1e3, dev, size * 8 / (args.w * args.h)), flush=True)

@@ -20,7 +20,8 @@ def _bgra(img):
     return out
 
 
-@pytest.mark.parametrize("w,h,ch,effort,quality", [(64, 48, 3, 3, 90), (300, 200, 3, 3, 90), (519, 387, 3, 7, 90), (300, 260, 4, 7, 75), (100, 90, 1, 7, 90), (2100, 300, 3, 5, 50)])
+@pytest.mark.parametrize("w,h,ch,effort,quality", [(64, 48, 3, 3, 90), (300, 200, 3, 3, 90), (300, 200, 3, 1, 90), (519, 387, 4, 2, 75), (2100, 300, 1, 1, 90),   # efforts 1-2: prefix codes
+                                                      (519, 387, 3, 7, 90), (300, 260, 4, 7, 75), (100, 90, 1, 7, 90), (2100, 300, 3, 5, 50)])
 def test_lossy_save_roundtrip(gpu, oracle, w, h, ch, effort, quality):
     img = oracle.synthetic_image(w, h, seed=w, channels=ch)
     out = io.BytesIO()
@@ -95,7 +96,7 @@ def test_write_error_is_sticky(gpu, oracle):
         gpu.JpegXLSave.Save(_bgra(img), Broken())
 
 
-@pytest.mark.parametrize("ch,kw,bands", [(3, dict(quality=90, effort=3), 3), (3, dict(quality=90, effort=7), 2), (4, dict(quality=75, effort=7), 3),
+@pytest.mark.parametrize("ch,kw,bands", [(3, dict(quality=90, effort=3), 3), (4, dict(quality=90, effort=1), 3), (4, dict(lossless=True, effort=1), 2), (3, dict(quality=90, effort=7), 2), (4, dict(quality=75, effort=7), 3),
                                          (4, dict(lossless=True), 3), (1, dict(quality=90, effort=5), 8)])
 def test_banded_encode_is_bit_identical_to_save_image(gpu, oracle, ch, kw, bands):
     """Sharded encode: bands of whole LF-group rows, each through its own JxlB200BandEncoder session, flags OR-ed and histograms
