@@ -85,7 +85,7 @@ JXLFT_API EncoderStatus JXLFT_CALL SaveImage(const BitmapData* bitmap, const Enc
 
 /* Decode straight into a BGRA32 surface (stride = 4*width), fusing the managed repack passes the reference performs after
  * LoadImage returns: I/DecoderLayerData.cs:667-744 (+ I/TransparencyMapping.cs:19-32) and S/JpegXLLoad.cs:219-249.
- * On success *width/*height receive the (post-orientation) size; `surface` must hold width*height*4 bytes, which the
+ * On success *width and *height receive the (post-orientation) size; `surface` must hold width*height*4 bytes, which the
  * caller learns from JxlB200PeekInfo. Returns a DecoderStatus. */
 JXLFT_API DecoderStatus JXLFT_CALL JxlB200LoadImageBgra(const uint8_t* data, size_t dataSize, uint8_t* surface, size_t surfaceBytes,
                                                          int32_t* width, int32_t* height, ErrorInfo* errorInfo);
