@@ -15,7 +15,8 @@ seeds = [O.encode(img, effort=7), O.encode(img, lossless=1), O.encode(img[..., :
          O.encode_layers(200, 136, [(img, {}), (img[:60, :80], dict(x0=15, y0=25, mode="blend"))], lossless=1)]
 seeds += [bytes(c[1]) for c in spec_cases.cases() if c[0] in ("rgb8_palette_groups", "rgb8_lz77_multigroup", "rgb8_prev_channel_props", "rgb8_permuted_toc", "rgb8_palette_deltas",
                                                             "rgb8_local_trees_in_groups", "rgb8_palette_all_local", "rgba8_rct_per_group_local_trees", "rgba8_group_alpha_palettes",
-                                                            "rgb8_group_rgb_palettes", "layers_three_slots_mul", "rgba8_two_palettes")]
+                                                            "rgb8_group_rgb_palettes", "layers_three_slots_mul", "rgba8_two_palettes", "rgb8_squeeze_default_groups",
+                                                            "rgb8_squeeze_lf_sections_local_trees", "rgba8_squeeze_explicit", "rgb8_squeeze_prev_channel_tree")]
 rng = random.Random(4321); n = 0; t0 = time.time(); hist = {}
 while time.time() - t0 < budget:
     s = bytearray(rng.choice(seeds))
